@@ -1,0 +1,198 @@
+/*
+ * wae_b200.h -- C ABI of libwae_b200.so: the B200 (sm_100a) hot path of
+ * MingjieChen/wavenet_autoencoders.
+ *
+ * This is the drop-in boundary. Every entry point is `extern "C"`, takes plain
+ * device pointers + sizes + a cudaStream_t passed as void*, returns an int
+ * status (0 = WAE_OK, negative = error; text via wae_last_error()), never
+ * throws, never allocates device memory (the caller owns every buffer,
+ * including the scratch `workspace`), and keeps no global state besides the
+ * per-thread last-error string.  There is NO CPU fallback behind these calls:
+ * on a machine without an sm_100 device they return WAE_ERR_DEVICE.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo):
+ *   wae_vq_search            vector_quantization.py:27-38 (VectorQuantize),
+ *                            :85-110 (SlicedVectorQuantize), :166-177, :267-281 (EMA variants)
+ *   wae_vq_ema_stats         vector_quantization.py:190-210, :282-292 (one-hot^T @ x, cluster counts)
+ *   wae_stack_forward_f32 /  wavenet_vocoder/wavenet.py:203-212 (first_conv, the conv_layers loop,
+ *   wae_stack_forward_bf16   skip scaling, last_conv_layers) + modules.py:115-163 (ResidualConv1dGLU._forward)
+ *   wae_ar_generate          wavenet_vocoder/wavenet.py:299-339 (the per-sample loop of incremental_forward),
+ *                            conv.py:17-46 (Conv1d.incremental_forward), mixture.py:118-156, :221-270 (sampling)
+ *   wae_upsample_stage       wavenet_vocoder/upsample.py:18-20,42,59-60 (nearest stretch + 1x(2s+1) smoothing conv)
+ *
+ * All matrices are packed by the Python host (wavenet_autoencoders_b200/packing.py);
+ * layouts are documented next to each struct and in DESIGN.md.
+ */
+#ifndef WAE_B200_H
+#define WAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WAE_OK 0
+#define WAE_ERR_ARG (-1)       /* bad shape / null pointer / unsupported size */
+#define WAE_ERR_DEVICE (-2)    /* no CUDA device, or device is not sm_100 */
+#define WAE_ERR_CUDA (-3)      /* a CUDA runtime/driver call failed */
+#define WAE_ERR_WORKSPACE (-4) /* workspace too small */
+#define WAE_ERR_ALIGN (-5)     /* misaligned pointer */
+
+#define WAE_MAX_LAYERS 64
+
+/* ---- library ---------------------------------------------------------- */
+int wae_version(void);
+/* Last error text of the calling thread ("" if none). */
+const char* wae_last_error(void);
+/* WAE_OK iff `device` exists and is compute capability 10.x. */
+int wae_device_check(int device);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t wae_launch_count(void);
+
+/* ---- VQ nearest-codeword search --------------------------------------- */
+/*
+ * x is the reference layout (B, D, T) fp32 contiguous.  For each of the N=B*T
+ * vectors, restricted to feature rows [d0, d0+sub_d), finds
+ *     argmin_k  fl( fl(e2[k] + x2) - 2*dot(x, E[k]) )          (first index on ties)
+ * which is the reference's addmm(...)+argmin / argmax(-dis) in fp32.
+ *   codebook : (K, sub_d) fp32 row-major (nn.Embedding.weight)
+ *   idx_out  : (B*T) int64, vector order n = b*T + t            (may be NULL)
+ *   quant_out: (B, D, T) fp32; rows [d0, d0+sub_d) are written with
+ *              fl(x + fl(E[idx] - x))   (the straight-through forward value)  (may be NULL)
+ *   sqerr_out: (1) double, += sum over the slice of (E[idx]-x)^2  (may be NULL; caller zeroes)
+ *   counts_out: (K) int32, += histogram of idx                   (may be NULL; caller zeroes)
+ */
+int wae_vq_search(const float* x, int B, int D, int T, int d0, int sub_d,
+                  const float* codebook, int K,
+                  int64_t* idx_out, float* quant_out, double* sqerr_out, int32_t* counts_out,
+                  void* stream);
+
+/*
+ * EMA statistics for the *EMA VQ variants: dw[k][j] += sum_{n: idx[n]==k} x[n][d0+j]
+ * (the reference's encodings.t() @ flat_in).  dw: (K, sub_d) fp32, caller zeroes.
+ */
+int wae_vq_ema_stats(const float* x, int B, int D, int T, int d0, int sub_d,
+                     const int64_t* idx, int K, float* dw, void* stream);
+
+/* ---- conditioning upsampler (one stage) -------------------------------- */
+/*
+ * out[b][c][u] = sum_{j=0..2s} w[j] * in[b][c][ floor((u + j - s) / s) ]   (zero outside [0, Tin*s))
+ * i.e. nearest-neighbour stretch by s followed by the 1 x (2s+1) smoothing conv, zero padded.
+ * in: (B*C, Tin), out: (B*C, Tin*s), w: (2s+1) fp32 (weight-norm already folded).
+ */
+int wae_upsample_stage(const float* in, int rows, int Tin, int s, const float* w, float* out, void* stream);
+
+/* ---- WaveNet decoder stack: shared description -------------------------- */
+typedef struct wae_stack_dims {
+    int32_t layers;       /* L */
+    int32_t kernel_size;  /* kw (3 in every preset) */
+    int32_t R;            /* residual_channels */
+    int32_t G;            /* gate_channels (even) */
+    int32_t S;            /* skip_out_channels */
+    int32_t C;            /* cin_channels after upsampling, 0 = no local conditioning */
+    int32_t Gi;           /* gin_channels, 0 = no global conditioning */
+    int32_t O;            /* out_channels */
+    int32_t Oin;          /* first_conv input channels: O, or 1 for scalar_input */
+    int32_t dilation[WAE_MAX_LAYERS];
+} wae_stack_dims;
+
+/*
+ * fp32 weights for the CUDA-core "fp32-faithful" stack (parity mode).  All device pointers, fp32,
+ * weight-norm folded.  H = G/2, K1 = kw*R + C.
+ *   wf  [Oin][R]        first_conv, input-channel major          bf [R]
+ *   w1  [L][K1][G]      row k = tap j (oldest first) * R + r, then the C conditioning rows;
+ *                       column order "pair-permuted": col 8q+i (i<4) = tanh channel 4q+i,
+ *                       col 8q+4+i = sigmoid channel 4q+i
+ *   b1  [L][G]          conv bias, same column order
+ *   wg  [L][Gi][G]      conv1x1g, same column order (NULL if Gi==0)
+ *   w2  [L][H][R+S]     conv1x1_out (cols 0..R) | conv1x1_skip (cols R..R+S)   b2 [L][R+S]
+ *   w3  [S][S], b3 [S]  last_conv_layers[1];   w4 [S][Opad], b4 [Opad]  last_conv_layers[3], Opad = O rounded up to 8
+ */
+typedef struct wae_stack_f32 {
+    wae_stack_dims d;
+    const float *wf, *bf, *w1, *b1, *wg, *w2, *b2, *w3, *b3, *w4, *b4;
+} wae_stack_f32;
+
+size_t wae_stack_workspace_f32(const wae_stack_dims* d, int B, int T);
+/*
+ * logits(B,O,T) = WaveNet stack(x (B,Oin,T) fp32, c (B,C,T) fp32 already upsampled or NULL,
+ *                               gemb (B,Gi) fp32 speaker embedding rows or NULL).
+ */
+int wae_stack_forward_f32(const wae_stack_f32* w, const float* x, const float* c, const float* gemb,
+                          int B, int T, float* logits, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/*
+ * bf16 weights for the tcgen05 tensor-core stack.  bf16 row-major "K-major" matrices (row = output
+ * channel, contiguous along the reduction dim), reduction dims padded to a multiple of 64:
+ *   w1  [L][G][K1p]     K order = taps (oldest first) x R, then C (zero padded to 64)
+ *   wo  [L][R][Hp]      conv1x1_out        ws [L][S][Hp]   conv1x1_skip   (Hp = H padded to 64)
+ *   w3  [S][S]          w4 [O][S]
+ *   fp32 vectors: b1 [L][G], wg [L][Gi][G] (natural column order), bo [L][R], bs_sum [S] (sum over layers),
+ *                 b3 [S], b4 [O];  first conv: wf [Oin][R] fp32, bf [R].
+ */
+typedef struct wae_stack_bf16 {
+    wae_stack_dims d;
+    const void *w1, *wo, *ws, *w3, *w4;                 /* bf16 */
+    const float *b1, *wg, *bo, *bs_sum, *b3, *b4, *wf, *bf;
+} wae_stack_bf16;
+
+size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T);
+int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb,
+                           int B, int T, float* logits, void* workspace, size_t workspace_bytes,
+                           void* stream);
+
+/* Plain C[M][N] (fp32) = A[M][K] * B[N][K]^T, bf16 K-major operands, on the same tcgen05/TMA
+ * pipeline the stack kernels use (unit-test entry point; K % 64 == 0, N % 16 == 0, N <= 256). */
+int wae_gemm_bf16_tn(const void* A, const void* B, float* Cout, int M, int N, int K, void* stream);
+
+/* ---- autoregressive synthesis ------------------------------------------ */
+#define WAE_AR_SAMPLE_CATEGORICAL 0 /* softmax -> inverse-CDF categorical with the supplied uniforms; feeds back one-hot */
+#define WAE_AR_SAMPLE_NONE 1        /* no sampling: emits logits (or probabilities) and feeds them back / uses test inputs */
+#define WAE_AR_SAMPLE_MOL 2         /* scalar input: discretized mixture of logistics (mixture.py:118-156) */
+#define WAE_AR_SAMPLE_GAUSS 3       /* scalar input: mixture of gaussians (mixture.py:221-270) */
+
+/*
+ * Weights for the AR kernel.  Each layer's two mat-vecs are split by OUTPUT ROW over the `cluster`
+ * CTAs of a thread-block cluster (balanced contiguous ranges: rank r owns rows [n*r/cs, n*(r+1)/cs)),
+ * and every rank streams only its own rows, so the host packs one contiguous blob per (stage, rank)
+ * (packing.py:pack_ar), row-major with the reduction dim padded to a multiple of 64:
+ *   stage 2l   : gate rows of rank r, interleaved (tanh row p, sigmoid row p) for its pairs p   [2*np][K1p]
+ *   stage 2l+1 : conv1x1_out rows then conv1x1_skip rows of rank r                              [nres+nsk][Hp]
+ *   stage 2L   : last_conv_layers[1] rows of rank r  [nsk][S]      stage 2L+1: last_conv_layers[3] rows  [nout][S]
+ * wtype: 0 = fp32 blobs, 1 = bf16 blobs.  layer_off: DEVICE array [2L+2][cluster] of int64 byte offsets into blob
+ * (each a multiple of 16).  fp32 vectors in natural channel order: b1 [L][G], wg [L][Gi][G] (or NULL), bo [L][R],
+ * bs [L][S], b3 [S], b4 [O], wf [Oin][R], bf [R].
+ */
+typedef struct wae_ar_weights {
+    wae_stack_dims d;
+    int32_t wtype, cluster;
+    int32_t utts_per_cluster;   /* 1 or 2 utterances share one cluster (and one pass over the weights) */
+    int32_t reserved;
+    const void* blob;
+    const int64_t* layer_off;
+    const float *b1, *wg, *bo, *bs, *b3, *b4, *wf, *bf;
+} wae_ar_weights;
+
+size_t wae_ar_workspace(const wae_ar_weights* w, int B, int T);
+/*
+ *   c_btc      (B,T,C) fp32 upsampled conditioning, or NULL
+ *   gemb       (B,Gi) fp32 or NULL
+ *   init       (B,Oin) fp32 first input (one-hot or scalar)
+ *   forced     (B,Tf,Oin) fp32 teacher-forcing inputs for steps t<Tf, or NULL (test_inputs)
+ *   uniforms   categorical: (T,B) fp32 in [0,1);  MoL/Gauss: (T,B,nmix+1 or +2)
+ *   out_idx    (B,T) int32 sampled class (categorical) or NULL
+ *   out_dense  (B,T,O) fp32 per-step logits/probabilities (SAMPLE_NONE) or (B,T) scalar samples (MoL/Gauss)
+ */
+int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* gemb,
+                    const float* init, const float* forced, int Tf,
+                    const float* uniforms, int B, int T, int sample_mode, int apply_softmax,
+                    int32_t* out_idx, float* out_dense,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAE_B200_H */

@@ -1,0 +1,116 @@
+"""ctypes binding of libwae_b200.so (include/wae_b200.h).
+
+There is deliberately no fallback here: if the shared library is missing, or a call reports an
+error (including "device is not sm_100"), a WaeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libwae_b200.so"
+
+WAE_MAX_LAYERS = 64
+
+AR_SAMPLE_CATEGORICAL = 0
+AR_SAMPLE_NONE = 1
+AR_SAMPLE_MOL = 2
+AR_SAMPLE_GAUSS = 3
+
+
+class WaeError(RuntimeError):
+    pass
+
+
+class StackDims(C.Structure):
+    _fields_ = [
+        ("layers", C.c_int32), ("kernel_size", C.c_int32), ("R", C.c_int32), ("G", C.c_int32),
+        ("S", C.c_int32), ("C", C.c_int32), ("Gi", C.c_int32), ("O", C.c_int32), ("Oin", C.c_int32),
+        ("dilation", C.c_int32 * WAE_MAX_LAYERS),
+    ]
+
+
+class StackF32(C.Structure):
+    _fields_ = [("d", StackDims)] + [(n, C.c_void_p) for n in
+                                    ("wf", "bf", "w1", "b1", "wg", "w2", "b2", "w3", "b3", "w4", "b4")]
+
+
+class StackBF16(C.Structure):
+    _fields_ = [("d", StackDims)] + [(n, C.c_void_p) for n in
+                                    ("w1", "wo", "ws", "w3", "w4", "b1", "wg", "bo", "bs_sum", "b3", "b4", "wf", "bf")]
+
+
+class ArWeights(C.Structure):
+    _fields_ = [
+        ("d", StackDims),
+        ("wtype", C.c_int32), ("cluster", C.c_int32), ("utts_per_cluster", C.c_int32), ("reserved", C.c_int32),
+        ("blob", C.c_void_p), ("layer_off", C.c_void_p),
+    ] + [(n, C.c_void_p) for n in ("b1", "wg", "bo", "bs", "b3", "b4", "wf", "bf")]
+
+
+_lib = None
+
+# name -> (restype, argtypes); also the list of symbols tests check against include/wae_b200.h
+SIGNATURES = {
+    "wae_version": (C.c_int, []),
+    "wae_last_error": (C.c_char_p, []),
+    "wae_device_check": (C.c_int, [C.c_int]),
+    "wae_launch_count": (C.c_int64, []),
+    "wae_vq_search": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wae_vq_ema_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                   C.c_void_p, C.c_void_p]),
+    "wae_upsample_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wae_stack_workspace_f32": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),
+    "wae_stack_forward_f32": (C.c_int, [C.POINTER(StackF32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wae_stack_workspace_bf16": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),
+    "wae_stack_forward_bf16": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wae_gemm_bf16_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "wae_ar_workspace": (C.c_size_t, [C.POINTER(ArWeights), C.c_int, C.c_int]),
+    "wae_ar_generate": (C.c_int, [C.POINTER(ArWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load libwae_b200.so (once). Raises WaeError if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise WaeError(
+                f"{LIB_PATH} not found: build it with `python -m wavenet_autoencoders_b200.build` "
+                "(this package has no CPU / PyTorch fallback for its CUDA kernels)")
+        handle = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().wae_last_error().decode(errors="replace")
+        raise WaeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t) -> int | None:
+    """Device pointer of a torch tensor (None -> NULL). The tensor must be contiguous."""
+    if t is None:
+        return None
+    assert t.is_contiguous(), "libwae_b200 takes contiguous tensors"
+    return t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    import torch
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().wae_launch_count())

@@ -1,0 +1,275 @@
+// vq_search.cu -- nearest-codeword search for VectorQuantize / SlicedVectorQuantize (+EMA variants).
+//
+// Replaces vector_quantization.py:27-38 / :85-110 of the reference: the (N,K) distance matrix, the
+// argmin, the (N,K) one-hot scatter and the one-hot @ codebook gather become ONE pass that never
+// materialises anything of size N*K.
+//
+// Arithmetic contract (bit-exact with oracle/vq_oracle.py, which restates the reference's fp32 addmm):
+//   x2   = sum_d fl(x_d*x_d)            sequential fp32 adds, d ascending
+//   e2_k = sum_d fl(e_kd*e_kd)          same
+//   dot  = fma chain over d ascending, starting from 0
+//   dist = fl( fl(e2_k + x2) - 2*dot )  (the -2*dot product is exact, so one rounding)
+//   idx  = first k with minimal dist    (torch.argmin / argmax(-dist) both return the first)
+//   quant= fl(x + fl(e_idx - x))        (the straight-through expression evaluated forward)
+//
+// Layout: x is (B, D, T) -- consecutive vectors are consecutive in memory for a fixed feature row,
+// so a tile of 64 vectors loads/stores 256-byte coalesced runs per feature row.  The codebook chunk
+// is staged in shared memory transposed ([d][k]) so the 16 code-lanes of a half-warp read
+// conflict-free float4s; each thread keeps a 4-vector x 8-code register tile.
+#include "wae_common.cuh"
+
+namespace {
+
+constexpr int VQ_THREADS = 256;
+constexpr int VQ_VT = 64;    // vectors per block
+constexpr int VQ_KC = 128;   // codes per shared-memory chunk (16 lanes x 8 codes)
+constexpr int VQ_EP = VQ_KC + 4;  // es row pitch: keeps float4 alignment, cuts transpose-store conflicts to 4-way
+
+// dynamic smem: xs[sub_d][VQ_VT] | es[sub_d][VQ_EP] | e2s[VQ_KC] | x2s[VQ_VT] | best_idx[VQ_VT]
+__global__ void __launch_bounds__(VQ_THREADS)
+vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int sub_d,
+                 const float* __restrict__ cb, int K,
+                 long long* __restrict__ idx_out, float* __restrict__ quant_out,
+                 double* __restrict__ sqerr_out, int* __restrict__ counts_out) {
+    extern __shared__ __align__(16) float smem[];
+    float* xs = smem;                         // [sub_d][VQ_VT]
+    float* es = xs + (size_t)sub_d * VQ_VT;   // [sub_d][VQ_KC]
+    float* e2s = es + (size_t)sub_d * VQ_EP;  // [VQ_KC]
+    float* x2s = e2s + VQ_KC;                 // [VQ_VT]
+    int* bidx = reinterpret_cast<int*>(x2s + VQ_VT);  // [VQ_VT]
+
+    const long long N = (long long)B * T;
+    const long long n0 = (long long)blockIdx.x * VQ_VT;
+    const int tid = threadIdx.x;
+
+    // ---- stage the x tile: xs[j][v] ----
+    for (int e = tid; e < sub_d * VQ_VT; e += VQ_THREADS) {
+        int j = e / VQ_VT, v = e % VQ_VT;
+        long long n = n0 + v;
+        float val = 0.f;
+        if (n < N) {
+            long long b = n / T, t = n % T;
+            val = x[(b * D + d0 + j) * (long long)T + t];
+        }
+        xs[j * VQ_VT + v] = val;
+    }
+    __syncthreads();
+    if (tid < VQ_VT) {
+        float s = 0.f;
+        for (int j = 0; j < sub_d; ++j) {
+            float v = xs[j * VQ_VT + tid];
+            s = __fadd_rn(s, __fmul_rn(v, v));
+        }
+        x2s[tid] = s;
+    }
+
+    const int kx = tid & 15;   // code lane: codes kx*8 .. kx*8+7 of the chunk
+    const int vy = tid >> 4;   // vector group: vectors vy*4 .. vy*4+3
+    float best[4];
+    int besti[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { best[i] = INFINITY; besti[i] = 0x7fffffff; }
+
+    for (int k0 = 0; k0 < K; k0 += VQ_KC) {
+        __syncthreads();  // previous chunk fully consumed (and x2s visible on first pass)
+        for (int e = tid; e < sub_d * VQ_KC; e += VQ_THREADS) {
+            int kk = e / sub_d, j = e % sub_d;  // coalesced read of codebook rows
+            int k = k0 + kk;
+            es[j * VQ_EP + kk] = (k < K) ? cb[(size_t)k * sub_d + j] : 0.f;
+        }
+        __syncthreads();
+        if (tid < VQ_KC) {  // ||e_k||^2 of this chunk, sequential fp32 (conflict-free column walk)
+            float s = 0.f;
+            for (int j = 0; j < sub_d; ++j) {
+                float v = es[j * VQ_EP + tid];
+                s = __fadd_rn(s, __fmul_rn(v, v));
+            }
+            e2s[tid] = s;
+        }
+        __syncthreads();
+
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+        for (int d = 0; d < sub_d; ++d) {
+            const float4 xv = *reinterpret_cast<const float4*>(&xs[d * VQ_VT + vy * 4]);
+            const float4 ea = *reinterpret_cast<const float4*>(&es[d * VQ_EP + kx * 8]);
+            const float4 eb = *reinterpret_cast<const float4*>(&es[d * VQ_EP + kx * 8 + 4]);
+            const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float er[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(xr[i], er[j], acc[i][j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float x2 = x2s[vy * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + kx * 8 + j;
+                const float s = __fadd_rn(e2s[kx * 8 + j], x2);
+                const float dist = __fmaf_rn(-2.0f, acc[i][j], s);
+                // ascending k within a thread: strict '<' keeps the first minimum
+                if (k < K && dist < best[i]) { best[i] = dist; besti[i] = k; }
+            }
+        }
+    }
+
+    // ---- argmin across the 16 code lanes (lexicographic on (dist, idx) = first minimum) ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int off = 8; off >= 1; off >>= 1) {
+            float od = __shfl_xor_sync(0xffffffffu, best[i], off);
+            int oi = __shfl_xor_sync(0xffffffffu, besti[i], off);
+            if (od < best[i] || (od == best[i] && oi < besti[i])) { best[i] = od; besti[i] = oi; }
+        }
+        if (kx == 0) bidx[vy * 4 + i] = besti[i];
+    }
+    __syncthreads();
+
+    // ---- outputs ----
+    if (tid < VQ_VT) {
+        long long n = n0 + tid;
+        if (n < N) {
+            int k = bidx[tid];
+            if (k == 0x7fffffff) k = 0;  // all-NaN row: torch.argmin returns the NaN position; we return 0
+            if (idx_out) idx_out[n] = k;
+            if (counts_out) atomicAdd(&counts_out[k], 1);
+        }
+    }
+    double local_err = 0.0;
+    if (quant_out != nullptr || sqerr_out != nullptr) {
+        for (int e = tid; e < sub_d * VQ_VT; e += VQ_THREADS) {
+            int j = e / VQ_VT, v = e % VQ_VT;
+            long long n = n0 + v;
+            if (n >= N) continue;
+            int k = bidx[v];
+            if (k == 0x7fffffff) k = 0;
+            const float xv = xs[j * VQ_VT + v];
+            const float q = __ldg(&cb[(size_t)k * sub_d + j]);
+            const float diff = __fsub_rn(q, xv);
+            if (quant_out) {
+                long long b = n / T, t = n % T;
+                quant_out[(b * D + d0 + j) * (long long)T + t] = __fadd_rn(xv, diff);
+            }
+            local_err += (double)diff * (double)diff;
+        }
+    }
+    if (sqerr_out) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) local_err += __shfl_xor_sync(0xffffffffu, local_err, off);
+        __shared__ double werr[VQ_THREADS / 32];
+        if ((tid & 31) == 0) werr[tid >> 5] = local_err;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < VQ_THREADS / 32; ++w) s += werr[w];
+            atomicAdd(sqerr_out, s);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+vq_ema_stats_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int sub_d,
+                    const long long* __restrict__ idx, int K, float* __restrict__ dw) {
+    const long long total = (long long)B * T * sub_d;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        // e = (b, j, t) with t fastest -> coalesced reads of x
+        long long t = e % T;
+        long long bj = e / T;
+        int j = (int)(bj % sub_d);
+        long long b = bj / sub_d;
+        long long k = idx[b * T + t];
+        if (k < 0 || k >= K) continue;
+        atomicAdd(&dw[k * sub_d + j], x[(b * D + d0 + j) * (long long)T + t]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+upsample_stage_kernel(const float* __restrict__ in, long long rows, int Tin, int s,
+                      const float* __restrict__ w, float* __restrict__ out) {
+    const long long Tout = (long long)Tin * s;
+    const long long total = rows * Tout;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / Tout;
+        const long long u = e % Tout;
+        const float* src = in + row * Tin;
+        float acc = 0.f;
+        for (int j = 0; j <= 2 * s; ++j) {
+            long long v = u + j - s;
+            if (v >= 0 && v < Tout) acc = fmaf(__ldg(&w[j]), __ldg(&src[v / s]), acc);
+        }
+        out[e] = acc;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int wae_vq_search(const float* x, int B, int D, int T, int d0, int sub_d, const float* codebook, int K,
+                  int64_t* idx_out, float* quant_out, double* sqerr_out, int32_t* counts_out,
+                  void* stream_) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(x && codebook, "wae_vq_search: null input");
+    WAE_REQUIRE(B >= 0 && T >= 0 && D > 0 && K > 0, "wae_vq_search: bad sizes B=%d D=%d T=%d K=%d", B, D, T, K);
+    WAE_REQUIRE(sub_d > 0 && d0 >= 0 && d0 + sub_d <= D, "wae_vq_search: slice [%d,%d) outside D=%d", d0,
+                d0 + sub_d, D);
+    WAE_REQUIRE(sub_d <= 256, "wae_vq_search: sub_d=%d > 256 unsupported", sub_d);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    const long long N = (long long)B * T;
+    if (N == 0) return WAE_OK;
+
+    const size_t smem = ((size_t)sub_d * (VQ_VT + VQ_EP) + VQ_KC + VQ_VT) * sizeof(float) + VQ_VT * sizeof(int);
+    static bool attr_set = false;
+    if (!attr_set) {
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(vq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            200 * 1024));
+        attr_set = true;
+    }
+    const long long blocks = (N + VQ_VT - 1) / VQ_VT;
+    WAE_REQUIRE(blocks <= 0x7fffffffLL, "wae_vq_search: too many vectors");
+    vq_search_kernel<<<(unsigned)blocks, VQ_THREADS, smem, stream>>>(
+        x, B, D, T, d0, sub_d, codebook, K, reinterpret_cast<long long*>(idx_out), quant_out, sqerr_out,
+        counts_out);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+int wae_vq_ema_stats(const float* x, int B, int D, int T, int d0, int sub_d, const int64_t* idx, int K,
+                     float* dw, void* stream_) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(x && idx && dw, "wae_vq_ema_stats: null pointer");
+    WAE_REQUIRE(sub_d > 0 && d0 >= 0 && d0 + sub_d <= D, "wae_vq_ema_stats: bad slice");
+    const long long total = (long long)B * T * sub_d;
+    if (total == 0) return WAE_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    vq_ema_stats_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(
+        x, B, D, T, d0, sub_d, reinterpret_cast<const long long*>(idx), K, dw);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+int wae_upsample_stage(const float* in, int rows, int Tin, int s, const float* w, float* out, void* stream_) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(in && w && out, "wae_upsample_stage: null pointer");
+    WAE_REQUIRE(rows >= 0 && Tin >= 0 && s >= 1, "wae_upsample_stage: bad sizes");
+    const long long total = (long long)rows * Tin * s;
+    if (total == 0) return WAE_OK;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    upsample_stage_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream_)>>>(in, rows, Tin, s, w,
+                                                                                             out);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+}  // extern "C"

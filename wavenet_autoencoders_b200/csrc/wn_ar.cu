@@ -1,0 +1,753 @@
+// wn_ar.cu -- autoregressive synthesis (WaveNet.incremental_forward) as ONE persistent kernel.
+//
+// Replaces the reference's Python loop over samples (wavenet_vocoder/wavenet.py:299-339) with its
+// ~700 kernel launches and >=1 host sync PER SAMPLE, and the O(dilation) shift-copy of every layer's
+// input buffer (conv.py:34-45), by a single launch for all T steps:
+//
+//  * one thread-block CLUSTER (8 or 16 CTAs) owns a group of U utterances for the whole utterance;
+//    clusters never talk to each other (synthesis shards by utterance, BASELINE north_star);
+//  * every layer's two mat-vecs are split by OUTPUT ROW across the CTAs of the cluster; each CTA
+//    streams only its row slice of the weights (bf16 or fp32) from L2 into shared memory with
+//    cp.async.bulk + mbarrier, two layers ahead of use (11.5 MB of weights do not fit 8 x 227 KB);
+//  * partial results are exchanged through DISTRIBUTED SHARED MEMORY (st.shared::cluster) and
+//    hardware cluster barriers -- no global-memory flags, no grid-wide sync, nothing that can
+//    dead-lock if clusters are scheduled in waves;
+//  * the dilation history is a ring in global memory ([kw-1]*d+1 rows per layer, the reference's own
+//    buffer length, conv.py:35) that is only ever touched at 3 rows per layer per step; the rows for
+//    the next layers are prefetched with cp.async while the current layer computes;
+//  * dot products: lanes split K, warp-shuffle reduce; tanh*sigmoid, residual, skip accumulation,
+//    the ReLU/1x1 head, softmax and the sampling (inverse-CDF categorical with caller-supplied
+//    uniforms, mixture of logistics, mixture of gaussians -- mixture.py:118-156, :221-270) are fused.
+//
+// Numerics: fp32 accumulate everywhere; with fp32 weights the per-step logits match the reference
+// to ~1e-6 relative (tests/test_ar_gpu.py), with bf16 weights to ~1e-2.
+#include "wae_common.cuh"
+
+using namespace wae::ptx;
+
+namespace {
+
+constexpr int AR_THREADS = 256;
+constexpr int AR_WARPS = AR_THREADS / 32;
+constexpr int NPF = 4;       // tap-prefetch depth (layers)
+constexpr int MAXM1 = 16;    // max K1p/64 (K1p <= 1024)
+constexpr int MAXM2 = 4;     // max Hp/64  (Hp  <= 256)
+constexpr int MAXMS = 4;     // max S/64   (S   <= 256)
+
+struct ArArgs {
+    wae_stack_dims d;
+    int wtype, cluster, B, T, Tf, sample_mode, apply_softmax, nmix;
+    int Hp, Cp, K1p;                 // padded reduction lengths (multiples of 64)
+    int ring_rows;                   // rows per utterance in the ring
+    int ring_off[WAE_MAX_LAYERS];    // first ring row of each layer
+    int ring_ns[WAE_MAX_LAYERS];     // ring slots of each layer = (kw-1)*d + 1
+    const uint8_t* blob;
+    const long long* blob_off;       // [2L+2][cluster] byte offsets: W1_l, W2_l, ..., W3, W4
+    const float *gb;                 // [L][B][G]  conv bias + g term (natural order)
+    const float *bo, *bs, *b3, *b4;  // [L][R], [L][S], [S], [O]
+    const float *wf, *bf;            // [Oin][R], [R]
+    const float* c_btc;              // (B,T,C) or null
+    const float* init;               // (B,Oin)
+    const float* forced;             // (B,Tf,Oin) or null
+    const float* uniforms;           // (T,B,nu)
+    int nu;
+    float* ring;                     // [B][ring_rows][R]
+    int* out_idx;                    // (B,T) or null
+    float* out_dense;                // (B,T,O) / (B,T) or null
+    float skip_scale;
+};
+
+__host__ __device__ inline int part(int n, int r, int cs) { return (int)(((long long)n * r) / cs); }
+
+template <typename WT> struct WLoad;
+template <> struct WLoad<float> {
+    static __device__ __forceinline__ float2 ld2(const float* row, int k) { return *reinterpret_cast<const float2*>(row + k); }
+};
+template <> struct WLoad<__nv_bfloat16> {
+    static __device__ __forceinline__ float2 ld2(const __nv_bfloat16* row, int k) {
+        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + k));
+    }
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+    return v;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// write one float to the same shared-memory location of every CTA in the cluster (lanes = ranks)
+__device__ __forceinline__ void bcast_store(float* local_ptr, float v, int lane, int cs) {
+    if (lane < cs) st_cluster_f32(mapa(smem_u32(local_ptr), (uint32_t)lane), v);
+}
+
+// Shared-memory carve-up (all sizes in bytes, computed identically on host and device).
+struct ArSmem {
+    int w1_slot, w2_slot;      // bytes per weight slot
+    int off_w1, off_w2, off_xin, off_c, off_h, off_s1, off_s2, off_logit, off_skip, off_bias, off_in, off_misc, total;
+    int n_bias;                // floats in the bias cache
+};
+
+__host__ __device__ inline ArSmem ar_smem_layout(const wae_stack_dims& d, int cs, int U, int wbytes, int Hp, int Cp, int K1p) {
+    ArSmem s;
+    const int H = d.G / 2;
+    int max_np = 0, max_n2 = 0, max_n3 = 0, max_n4 = 0;
+    for (int r = 0; r < cs; ++r) {
+        int np = part(H, r + 1, cs) - part(H, r, cs);
+        int n2 = (part(d.R, r + 1, cs) - part(d.R, r, cs)) + (part(d.S, r + 1, cs) - part(d.S, r, cs));
+        int n3 = part(d.S, r + 1, cs) - part(d.S, r, cs);
+        int n4 = part(d.O, r + 1, cs) - part(d.O, r, cs);
+        if (np > max_np) max_np = np;
+        if (n2 > max_n2) max_n2 = n2;
+        if (n3 > max_n3) max_n3 = n3;
+        if (n4 > max_n4) max_n4 = n4;
+    }
+    auto up = [](int x) { return (x + 127) / 128 * 128; };
+    s.w1_slot = up(2 * max_np * K1p * wbytes);
+    int w2 = max_n2 * Hp * wbytes, w3 = max_n3 * d.S * wbytes, w4 = max_n4 * d.S * wbytes;
+    s.w2_slot = up(w2 > w3 ? (w2 > w4 ? w2 : w4) : (w3 > w4 ? w3 : w4));
+    int off = 0;
+    s.off_w1 = off; off += 2 * s.w1_slot;
+    s.off_w2 = off; off += 2 * s.w2_slot;
+    s.off_xin = off; off += up(NPF * U * d.kernel_size * d.R * 4);
+    s.off_c = off; off += up(2 * U * (Cp > 0 ? Cp : 16) * 4);
+    s.off_h = off; off += up(U * Hp * 4);
+    s.off_s1 = off; off += up(U * d.S * 4);
+    s.off_s2 = off; off += up(U * d.S * 4);
+    s.off_logit = off; off += up(U * d.O * 4);
+    s.off_skip = off; off += up(U * (max_n3 + 1) * 4);
+    s.n_bias = d.layers * (2 * max_np * U + max_n2) + max_n3 + max_n4;
+    s.off_bias = off; off += up(s.n_bias * 4);
+    s.off_in = off; off += up(U * d.Oin * 4);
+    s.off_misc = off; off += 256;  // mbarriers + small ints
+    s.total = off;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <typename WT, int U>
+__global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant__ ArArgs a) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const wae_stack_dims& d = a.d;
+    const int cs = a.cluster;
+    const int rank = (int)cluster_ctarank();
+    const int cid = (int)blockIdx.x / cs;           // cluster index (1-D grid, cluster along x)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = d.layers, kw = d.kernel_size, R = d.R, G = d.G, S = d.S, O = d.O, Oin = d.Oin;
+    const int H = G / 2, Hp = a.Hp, Cp = a.Cp, K1p = a.K1p;
+    const int KX = kw * R;  // taps + current sample part of the GEMV1 input
+    const int nm1 = K1p / 64, nm2 = Hp / 64, nms = S / 64;
+
+    const ArSmem sl = ar_smem_layout(d, cs, U, (int)sizeof(WT), Hp, Cp, K1p);
+    uint8_t* w1buf = smem + sl.off_w1;
+    uint8_t* w2buf = smem + sl.off_w2;
+    float* xin = reinterpret_cast<float*>(smem + sl.off_xin);      // [NPF][U][KX]
+    float* cbuf = reinterpret_cast<float*>(smem + sl.off_c);       // [2][U][Cp]
+    float* hbuf = reinterpret_cast<float*>(smem + sl.off_h);       // [U][Hp]
+    float* s1buf = reinterpret_cast<float*>(smem + sl.off_s1);     // [U][S]
+    float* s2buf = reinterpret_cast<float*>(smem + sl.off_s2);     // [U][S]
+    float* lgbuf = reinterpret_cast<float*>(smem + sl.off_logit);  // [U][O]
+    float* skipacc = reinterpret_cast<float*>(smem + sl.off_skip); // [U][ns]
+    float* biasc = reinterpret_cast<float*>(smem + sl.off_bias);
+    float* inbuf = reinterpret_cast<float*>(smem + sl.off_in);     // [U][Oin] dense input of the current step
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sl.off_misc);
+    uint64_t* w1_full = bars;       // [2]
+    uint64_t* w2_full = bars + 2;   // [2]
+    int* cur_idx = reinterpret_cast<int*>(bars + 4);  // [U] class index of the current input, or -1 = dense (inbuf)
+
+    // ---- row ownership of this rank ----
+    const int p0 = part(H, rank, cs), np = part(H, rank + 1, cs) - p0;          // gate pairs
+    const int ro0 = part(R, rank, cs), nres = part(R, rank + 1, cs) - ro0;      // residual rows
+    const int so0 = part(S, rank, cs), nsk = part(S, rank + 1, cs) - so0;       // skip rows (also head-1 rows)
+    const int oo0 = part(O, rank, cs), nout = part(O, rank + 1, cs) - oo0;      // logit rows
+    const int n2 = nres + nsk;
+    int max_np = 0, max_n2 = 0;
+    for (int r = 0; r < cs; ++r) {
+        int q = part(H, r + 1, cs) - part(H, r, cs);
+        int q2 = (part(R, r + 1, cs) - part(R, r, cs)) + (part(S, r + 1, cs) - part(S, r, cs));
+        max_np = q > max_np ? q : max_np;
+        max_n2 = q2 > max_n2 ? q2 : max_n2;
+    }
+    // bias cache layout: [L][2*max_np*U] gate biases | [L][max_n2] out/skip biases | [nsk] b3 | [nout] b4
+    float* gbc = biasc;
+    float* b2c = biasc + (size_t)L * 2 * max_np * U;
+    float* b3c = b2c + (size_t)L * max_n2;
+    float* b4c = b3c + nsk;
+
+    const long long* boff = a.blob_off;
+    auto w1_bytes = [&]() { return (uint32_t)(2 * np * K1p * sizeof(WT)); };
+    auto w2_bytes = [&](int i) {  // i in [0, L+2): layer out/skip, head1, head2
+        int rows = (i < L) ? n2 : (i == L ? nsk : nout);
+        int k = (i < L) ? Hp : S;
+        return (uint32_t)(rows * k * sizeof(WT));
+    };
+    // issue the bulk copy of weight blob #j of each ring (thread 0 only)
+    const long long n1_total = (long long)a.T * L, n2_total = (long long)a.T * (L + 2);
+    auto issue_w1 = [&](long long j) {
+        if (j >= n1_total) return;
+        const int l = (int)(j % L), slot = (int)(j & 1);
+        const uint32_t bytes = w1_bytes();
+        if (bytes == 0) { mbar_arrive(&w1_full[slot]); return; }  // empty slice: just complete the phase
+        mbar_arrive_expect_tx(&w1_full[slot], bytes);
+        bulk_load_1d(w1buf + (size_t)slot * sl.w1_slot, a.blob + boff[(size_t)(2 * l) * cs + rank], bytes, &w1_full[slot]);
+    };
+    auto issue_w2 = [&](long long j) {
+        if (j >= n2_total) return;
+        const int i = (int)(j % (L + 2)), slot = (int)(j & 1);
+        const uint32_t bytes = w2_bytes(i);
+        if (bytes == 0) { mbar_arrive(&w2_full[slot]); return; }
+        const int stage = (i < L) ? 2 * i + 1 : 2 * L + (i - L);
+        mbar_arrive_expect_tx(&w2_full[slot], bytes);
+        bulk_load_1d(w2buf + (size_t)slot * sl.w2_slot, a.blob + boff[(size_t)stage * cs + rank], bytes, &w2_full[slot]);
+    };
+
+    // ---- one-time setup ----
+    if (tid == 0) {
+        mbar_init(&w1_full[0], 1); mbar_init(&w1_full[1], 1);
+        mbar_init(&w2_full[0], 1); mbar_init(&w2_full[1], 1);
+        fence_mbar_init();
+    }
+    for (int e = tid; e < sl.n_bias; e += AR_THREADS) biasc[e] = 0.f;
+    for (int e = tid; e < NPF * U * KX; e += AR_THREADS) xin[e] = 0.f;
+    for (int e = tid; e < 2 * U * (Cp > 0 ? Cp : 16); e += AR_THREADS) cbuf[e] = 0.f;
+    for (int e = tid; e < U * Hp; e += AR_THREADS) hbuf[e] = 0.f;
+    __syncthreads();
+    for (int e = tid; e < L * np * 2 * U; e += AR_THREADS) {  // gate biases: [l][pair j][a|b][u]
+        const int u = e % U, ab = (e / U) % 2, j = (e / (2 * U)) % np, l = e / (2 * U * np);
+        const int b = cid * U + u;
+        gbc[(size_t)l * 2 * max_np * U + (j * 2 + ab) * U + u] =
+            (b < a.B) ? a.gb[((size_t)l * a.B + b) * G + ab * H + p0 + j] : 0.f;
+    }
+    for (int e = tid; e < L * n2; e += AR_THREADS) {
+        const int i = e % n2, l = e / n2;
+        b2c[(size_t)l * max_n2 + i] = (i < nres) ? a.bo[(size_t)l * R + ro0 + i] : a.bs[(size_t)l * S + so0 + (i - nres)];
+    }
+    for (int e = tid; e < nsk; e += AR_THREADS) b3c[e] = a.b3[so0 + e];
+    for (int e = tid; e < nout; e += AR_THREADS) b4c[e] = a.b4[oo0 + e];
+    if (tid < U) cur_idx[tid] = -1;
+    // initial input (wavenet.py:283-295); forced inputs override it below
+    for (int e = tid; e < U * Oin; e += AR_THREADS) {
+        const int u = e / Oin, o = e % Oin, b = cid * U + u;
+        inbuf[e] = (b < a.B) ? a.init[(size_t)b * Oin + o] : 0.f;
+    }
+    if (tid == 0) { issue_w1(0); issue_w1(1); issue_w2(0); issue_w2(1); }
+    cluster_sync();  // also: every CTA of the cluster is running before any DSMEM traffic
+
+    // cp.async prefetch of the tap rows of (step tt, layer l) into xin[l % NPF]
+    auto prefetch_taps = [&](int tt, int l) {
+        if (tt < a.T && kw > 1) {
+            const int ns = a.ring_ns[l], dil = d.dilation[l];
+            const int chunks = U * (kw - 1) * (R / 4);  // 16-byte chunks
+            for (int e = tid; e < chunks; e += AR_THREADS) {
+                const int c4 = e % (R / 4), j = (e / (R / 4)) % (kw - 1), u = e / ((R / 4) * (kw - 1));
+                const int b = cid * U + u;
+                const int ts = tt - (kw - 1 - j) * dil;  // source time of tap j
+                float* dst = xin + ((size_t)(l % NPF) * U + u) * KX + j * R + c4 * 4;
+                if (b < a.B && ts >= 0) {
+                    const int slot = ts % ns;
+                    cp_async16(dst, a.ring + (((size_t)b * a.ring_rows + a.ring_off[l] + slot) * R + c4 * 4));
+                } else {
+                    *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    // conditioning row of step tt into cbuf[tt & 1]
+    auto prefetch_c = [&](int tt) {
+        if (a.c_btc != nullptr && tt < a.T) {
+            const int chunks = U * (d.C / 4);
+            for (int e = tid; e < chunks; e += AR_THREADS) {
+                const int c4 = e % (d.C / 4), u = e / (d.C / 4), b = cid * U + u;
+                if (b < a.B)
+                    cp_async16(cbuf + ((size_t)(tt & 1) * U + u) * Cp + c4 * 4, a.c_btc + (((size_t)b * a.T + tt) * d.C + c4 * 4));
+            }
+        }
+    };
+
+    // prologue: taps for layers 0..NPF-2 of step 0 (all zero: t<0), c(0)
+    prefetch_c(0);
+    for (int l = 0; l < NPF - 1; ++l) prefetch_taps(0, l);  // host guarantees L >= NPF
+
+    long long j1 = 0, j2 = 0;  // consumed-blob counters of the two weight rings
+
+    for (int t = 0; t < a.T; ++t) {
+        // ================= input -> first conv (wavenet.py:300-311) =================
+        // input of step t: forced[t] if t < Tf, else the value left in cur_idx/inbuf by the previous step
+        if (a.forced != nullptr && t < a.Tf) {
+            for (int e = tid; e < U * Oin; e += AR_THREADS) {
+                const int u = e / Oin, o = e % Oin, b = cid * U + u;
+                inbuf[e] = (b < a.B) ? __ldg(&a.forced[((size_t)b * a.Tf + t) * Oin + o]) : 0.f;
+            }
+            if (tid < U) cur_idx[tid] = -1;
+            __syncthreads();
+        }
+        // one-hot detection of dense inputs (warp u)
+        if (warp < U && cur_idx[warp] < 0 && Oin > 1) {
+            int nz = 0, pos = -1;
+            bool is_one = true;
+            for (int o = lane; o < Oin; o += 32) {
+                const float v = inbuf[warp * Oin + o];
+                if (v != 0.f) { ++nz; pos = o; is_one = is_one && (v == 1.f); }
+            }
+            nz = __reduce_add_sync(0xffffffffu, nz);
+            pos = __reduce_max_sync(0xffffffffu, pos);
+            const bool ok = __all_sync(0xffffffffu, is_one);
+            if (lane == 0 && nz == 1 && ok) cur_idx[warp] = pos;
+        }
+        __syncthreads();
+        {
+            float* x0 = xin + (size_t)(0 % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer 0
+            for (int e = tid; e < U * R; e += AR_THREADS) {
+                const int u = e / R, r = e % R;
+                const int ci = cur_idx[u];
+                float acc;
+                if (ci >= 0) {
+                    acc = __ldg(&a.wf[(size_t)ci * R + r]) + __ldg(&a.bf[r]);
+                } else {
+                    acc = 0.f;
+                    for (int o = 0; o < Oin; ++o) acc = fmaf(__ldg(&a.wf[(size_t)o * R + r]), inbuf[u * Oin + o], acc);
+                    acc += __ldg(&a.bf[r]);
+                }
+                x0[(size_t)u * KX + r] = acc;
+                const int b = cid * U + u;
+                if (b < a.B && r >= ro0 && r < ro0 + nres)  // ring row of layer 0, written by the owning rank
+                    __stcg(&a.ring[((size_t)b * a.ring_rows + a.ring_off[0] + (t % a.ring_ns[0])) * R + r], acc);
+            }
+        }
+        for (int e = tid; e < U * (nsk + 1); e += AR_THREADS) skipacc[e] = 0.f;
+        prefetch_c(t + 1);  // joins the next committed cp.async group
+        cp_async_wait<NPF - 2>();  // taps of layer 0 (and c(t)) have landed for this thread
+        __syncthreads();
+
+        // ================= residual layers =================
+        for (int l = 0; l < L; ++l) {
+            {   // prefetch the taps NPF-1 layers ahead (possibly of the next step)
+                const int lp = l + NPF - 1;
+                if (lp < L) prefetch_taps(t, lp); else prefetch_taps(t + 1, lp - L);
+            }
+            const float* xl = xin + (size_t)(l % NPF) * U * KX;     // [U][KX]
+            const float* cl = cbuf + (size_t)(t & 1) * U * Cp;       // [U][Cp]
+
+            // ---- GEMV1: gate pre-activations of this rank's pairs ----
+            float2 xr[MAXM1][U];
+#pragma unroll
+            for (int m = 0; m < MAXM1; ++m) {
+                if (m < nm1) {
+                    const int k = m * 64 + lane * 2;
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        xr[m][u] = (k < KX) ? *reinterpret_cast<const float2*>(xl + (size_t)u * KX + k)
+                                            : *reinterpret_cast<const float2*>(cl + (size_t)u * Cp + (k - KX));
+                }
+            }
+            mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
+            const WT* w1s = reinterpret_cast<const WT*>(w1buf + (size_t)(j1 & 1) * sl.w1_slot);
+            for (int j = warp; j < np; j += AR_WARPS) {
+                const WT* wa = w1s + (size_t)(2 * j) * K1p;
+                const WT* wb = wa + K1p;
+                float aa[U], ab[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { aa[u] = 0.f; ab[u] = 0.f; }
+#pragma unroll
+                for (int m = 0; m < MAXM1; ++m) {
+                    if (m < nm1) {
+                        const int k = m * 64 + lane * 2;
+                        const float2 fa = WLoad<WT>::ld2(wa, k), fb = WLoad<WT>::ld2(wb, k);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            aa[u] = fmaf(fa.x, xr[m][u].x, aa[u]); aa[u] = fmaf(fa.y, xr[m][u].y, aa[u]);
+                            ab[u] = fmaf(fb.x, xr[m][u].x, ab[u]); ab[u] = fmaf(fb.y, xr[m][u].y, ab[u]);
+                        }
+                    }
+                }
+                const float* gbp = gbc + (size_t)l * 2 * max_np * U + (size_t)j * 2 * U;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float za = warp_sum(aa[u]) + gbp[u];
+                    const float zb = warp_sum(ab[u]) + gbp[U + u];
+                    const float h = tanhf(za) * (1.f / (1.f + expf(-zb)));   // modules.py:154
+                    bcast_store(hbuf + (size_t)u * Hp + p0 + j, h, lane, cs);
+                }
+            }
+            ++j1;
+            cluster_arrive();
+            mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
+            cluster_wait();
+            // Refill the W1 slot just consumed (blob j1+1 has the parity of j1-1).  Every warp of this CTA
+            // finished reading it before arriving at the cluster barrier we just passed, so the
+            // asynchronous overwrite cannot race with a reader.
+            if (tid == 0) issue_w1(j1 + 1);
+            __syncwarp();
+
+            // ---- GEMV2: residual + skip rows of this rank ----
+            float2 hr[MAXM2][U];
+#pragma unroll
+            for (int m = 0; m < MAXM2; ++m)
+                if (m < nm2) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        hr[m][u] = *reinterpret_cast<const float2*>(hbuf + (size_t)u * Hp + m * 64 + lane * 2);
+                }
+            const WT* w2s = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
+            const bool last = (l == L - 1);
+            float* xnext = xin + (size_t)((l + 1) % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer l+1
+            for (int i = warp; i < n2; i += AR_WARPS) {
+                if (last && i < nres) continue;  // residual output of the last layer is dead (wavenet.py:205-210)
+                const WT* wr = w2s + (size_t)i * Hp;
+                float acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc[u] = 0.f;
+#pragma unroll
+                for (int m = 0; m < MAXM2; ++m)
+                    if (m < nm2) {
+                        const float2 f = WLoad<WT>::ld2(wr, m * 64 + lane * 2);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) { acc[u] = fmaf(f.x, hr[m][u].x, acc[u]); acc[u] = fmaf(f.y, hr[m][u].y, acc[u]); }
+                    }
+                const float bias = b2c[(size_t)l * max_n2 + i];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float o = warp_sum(acc[u]) + bias;
+                    if (i < nres) {
+                        const int r = ro0 + i;
+                        const float xo = (o + xl[(size_t)u * KX + (kw - 1) * R + r]) * 0.70710678118654752440f;  // modules.py:162
+                        bcast_store(xnext + (size_t)u * KX + r, xo, lane, cs);
+                        const int b = cid * U + u;
+                        if (lane == 0 && b < a.B)
+                            __stcg(&a.ring[((size_t)b * a.ring_rows + a.ring_off[l + 1] + (t % a.ring_ns[l + 1])) * R + r], xo);
+                    } else if (lane == 0) {
+                        skipacc[u * (nsk + 1) + (i - nres)] += o;   // skips += h (wavenet.py:207); one writer per row
+                    }
+                }
+            }
+            ++j2;
+            cp_async_wait<NPF - 2>();  // taps of the next layer have landed (this thread's copies)
+            cluster_arrive();
+            cluster_wait();
+            if (tid == 0) issue_w2(j2 + 1);
+            __syncwarp();
+        }
+
+        // ================= head (wavenet.py:208-212 / :316-322) =================
+        // relu(skips * sqrt(1/L)) -> all-gather
+        for (int e = tid; e < U * nsk; e += AR_THREADS) {
+            const int u = e / nsk, i = e % nsk;
+            const float v = fmaxf(skipacc[u * (nsk + 1) + i] * a.skip_scale, 0.f);
+            float* dst = s1buf + (size_t)u * S + so0 + i;
+            for (int r = 0; r < cs; ++r) st_cluster_f32(mapa(smem_u32(dst), (uint32_t)r), v);
+        }
+        cluster_arrive();
+        mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
+        cluster_wait();
+        {   // 1x1 S->S + ReLU
+            float2 sr[MAXMS][U];
+#pragma unroll
+            for (int m = 0; m < MAXMS; ++m)
+                if (m < nms) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) sr[m][u] = *reinterpret_cast<const float2*>(s1buf + (size_t)u * S + m * 64 + lane * 2);
+                }
+            const WT* w3s = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
+            for (int i = warp; i < nsk; i += AR_WARPS) {
+                const WT* wr = w3s + (size_t)i * S;
+                float acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc[u] = 0.f;
+#pragma unroll
+                for (int m = 0; m < MAXMS; ++m)
+                    if (m < nms) {
+                        const float2 f = WLoad<WT>::ld2(wr, m * 64 + lane * 2);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) { acc[u] = fmaf(f.x, sr[m][u].x, acc[u]); acc[u] = fmaf(f.y, sr[m][u].y, acc[u]); }
+                    }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float v = fmaxf(warp_sum(acc[u]) + b3c[i], 0.f);
+                    bcast_store(s2buf + (size_t)u * S + so0 + i, v, lane, cs);
+                }
+            }
+        }
+        ++j2;
+        cluster_arrive();
+        mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
+        cluster_wait();
+        if (tid == 0) issue_w2(j2 + 1);
+        __syncwarp();
+        {   // 1x1 S->O
+            float2 sr[MAXMS][U];
+#pragma unroll
+            for (int m = 0; m < MAXMS; ++m)
+                if (m < nms) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) sr[m][u] = *reinterpret_cast<const float2*>(s2buf + (size_t)u * S + m * 64 + lane * 2);
+                }
+            const WT* w4s = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
+            for (int i = warp; i < nout; i += AR_WARPS) {
+                const WT* wr = w4s + (size_t)i * S;
+                float acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) acc[u] = 0.f;
+#pragma unroll
+                for (int m = 0; m < MAXMS; ++m)
+                    if (m < nms) {
+                        const float2 f = WLoad<WT>::ld2(wr, m * 64 + lane * 2);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) { acc[u] = fmaf(f.x, sr[m][u].x, acc[u]); acc[u] = fmaf(f.y, sr[m][u].y, acc[u]); }
+                    }
+#pragma unroll
+                for (int u = 0; u < U; ++u) bcast_store(lgbuf + (size_t)u * O + oo0 + i, warp_sum(acc[u]) + b4c[i], lane, cs);
+            }
+        }
+        ++j2;
+        cluster_arrive();
+        cluster_wait();
+        if (tid == 0) issue_w2(j2 + 1);
+        __syncwarp();
+
+        // ================= output / sampling (every CTA redundantly, warp u = utterance u) =================
+        if (warp < U) {
+            const int u = warp, b = cid * U + u;
+            const bool writer = (rank == 0 && b < a.B);
+            const float* lg = lgbuf + (size_t)u * O;
+            if (a.sample_mode == WAE_AR_SAMPLE_CATEGORICAL || a.sample_mode == WAE_AR_SAMPLE_NONE) {
+                // softmax over O classes; lane owns classes lane*per .. (contiguous chunk)
+                const int per = (O + 31) / 32;
+                float mx = -INFINITY;
+                for (int i = 0; i < per; ++i) { const int o = lane * per + i; if (o < O) mx = fmaxf(mx, lg[o]); }
+                mx = warp_max(mx);
+                float ex[8];
+                float loc = 0.f;
+                for (int i = 0; i < per && i < 8; ++i) {
+                    const int o = lane * per + i;
+                    ex[i] = (o < O) ? expf(lg[o] - mx) : 0.f;
+                    loc += ex[i];   // sequential within the lane
+                }
+                // inclusive Kogge-Stone scan of the lane totals (order mirrored by oracle/sampling.py)
+                float inc = loc;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const float v = __shfl_up_sync(0xffffffffu, inc, off);
+                    if (lane >= off) inc += v;
+                }
+                const float total = __shfl_sync(0xffffffffu, inc, 31);
+                if (a.sample_mode == WAE_AR_SAMPLE_CATEGORICAL) {
+                    const float uu = (b < a.B) ? __ldg(&a.uniforms[((size_t)t * a.B + b) * a.nu]) : 0.f;
+                    const float thr = uu * total;
+                    // first class whose inclusive cumulative mass exceeds thr
+                    float run = inc - loc;
+                    int pick = 0x7fffffff;
+                    for (int i = 0; i < per && i < 8; ++i) {
+                        run += ex[i];
+                        const int o = lane * per + i;
+                        if (o < O && run > thr && pick == 0x7fffffff) pick = o;
+                    }
+                    pick = __reduce_min_sync(0xffffffffu, pick);
+                    if (pick == 0x7fffffff) pick = O - 1;
+                    if (lane == 0) {
+                        cur_idx[u] = pick;
+                        if (writer && a.out_idx) a.out_idx[(size_t)b * a.T + t] = pick;
+                    }
+                } else {
+                    const float inv = 1.f / total;
+                    for (int i = 0; i < per && i < 8; ++i) {
+                        const int o = lane * per + i;
+                        if (o < O) {
+                            const float v = a.apply_softmax ? ex[i] * inv : lg[o];
+                            inbuf[u * Oin + (Oin == O ? o : 0)] = v;   // fed back as the next dense input
+                            if (writer && a.out_dense) a.out_dense[((size_t)b * a.T + t) * O + o] = v;
+                        }
+                    }
+                    if (lane == 0) cur_idx[u] = -1;
+                }
+            } else {
+                // scalar-input models: O = 3*nmix (or 2 for a single gaussian): [logit | mean | log_scale]
+                const int nmix = a.nmix;
+                const float* un = a.uniforms + ((size_t)t * a.B + (b < a.B ? b : 0)) * a.nu;
+                float best = -INFINITY;
+                int bi = 0x7fffffff;
+                if (nmix > 1 || a.sample_mode == WAE_AR_SAMPLE_MOL) {
+                    for (int i = lane; i < nmix; i += 32) {   // gumbel-max over mixture logits (mixture.py:138-140)
+                        const float uq = 1e-5f + __ldg(&un[i]) * (1.0f - 2e-5f);
+                        const float g = lg[i] - logf(-logf(uq));
+                        if (g > best) { best = g; bi = i; }
+                    }
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                    }
+                } else {
+                    bi = 0;
+                }
+                float xs;
+                if (a.sample_mode == WAE_AR_SAMPLE_MOL) {
+                    const float mean = lg[nmix + bi], ls = lg[2 * nmix + bi];
+                    const float uq = 1e-5f + __ldg(&un[nmix]) * (1.0f - 2e-5f);
+                    xs = mean + expf(ls) * (logf(uq) - logf(1.f - uq));     // mixture.py:151-152
+                } else {
+                    float mean, ls;
+                    if (O == 2) { mean = lg[0]; ls = lg[1]; }
+                    else if (nmix == 1) { mean = lg[1]; ls = lg[2]; }
+                    else { mean = lg[nmix + bi]; ls = lg[2 * nmix + bi]; }
+                    xs = mean + expf(ls) * __ldg(&un[nmix]);                 // Normal(mean, exp(ls)).sample() with a supplied N(0,1) draw
+                }
+                xs = fminf(fmaxf(xs, -1.f), 1.f);
+                if (lane == 0) {
+                    inbuf[u * Oin] = xs;
+                    cur_idx[u] = -1;
+                    if (writer && a.out_dense) a.out_dense[(size_t)b * a.T + t] = xs;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    cluster_sync();  // no CTA exits while peers may still write into its shared memory
+}
+
+__global__ void __launch_bounds__(256)
+ar_gbias_kernel(const float* __restrict__ b1, const float* __restrict__ wg, const float* __restrict__ gemb, int L,
+                int B, int G, int Gi, float* __restrict__ gb) {
+    const int l = blockIdx.x / B, b = blockIdx.x % B;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float acc = 0.f;
+        if (wg != nullptr && gemb != nullptr)
+            for (int i = 0; i < Gi; ++i)
+                acc = fmaf(__ldg(&wg[((size_t)l * Gi + i) * G + g]), __ldg(&gemb[(size_t)b * Gi + i]), acc);
+        gb[((size_t)l * B + b) * G + g] = __ldg(&b1[(size_t)l * G + g]) + acc;
+    }
+}
+
+int ring_rows_total(const wae_stack_dims& d) {
+    int n = 0;
+    for (int l = 0; l < d.layers; ++l) n += (d.kernel_size - 1) * d.dilation[l] + 1;
+    return n;
+}
+
+template <typename WT, int U>
+int launch_ar(const ArArgs& args, int clusters, size_t smem, cudaStream_t stream) {
+    auto kern = ar_kernel<WT, U>;
+    WAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (args.cluster > 8)
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(clusters * args.cluster));
+    cfg.blockDim = dim3(AR_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)args.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, args));
+    wae::count_launch();
+    return WAE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t wae_ar_workspace(const wae_ar_weights* w, int B, int T) {
+    if (!w || B <= 0 || T <= 0) return 0;
+    const wae_stack_dims& d = w->d;
+    size_t n = wae::align_up((size_t)B * ring_rows_total(d) * d.R * sizeof(float), 256);
+    n += wae::align_up((size_t)d.layers * B * d.G * sizeof(float), 256);
+    return n;
+}
+
+int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* gemb, const float* init,
+                    const float* forced, int Tf, const float* uniforms, int B, int T, int sample_mode,
+                    int apply_softmax, int32_t* out_idx, float* out_dense, void* workspace, size_t workspace_bytes,
+                    void* stream_) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(w && init && workspace, "wae_ar_generate: null pointer");
+    const wae_stack_dims& d = w->d;
+    const int H = d.G / 2;
+    WAE_REQUIRE(B > 0 && T > 0, "wae_ar_generate: B=%d T=%d", B, T);
+    WAE_REQUIRE(d.layers >= NPF && d.layers <= WAE_MAX_LAYERS && d.kernel_size >= 1,
+                "wae_ar_generate: need %d <= layers <= %d", NPF, WAE_MAX_LAYERS);
+    WAE_REQUIRE(w->cluster == 8 || w->cluster == 16 || w->cluster == 4 || w->cluster == 2 || w->cluster == 1,
+                "wae_ar_generate: cluster must be 1,2,4,8 or 16 (got %d)", w->cluster);
+    WAE_REQUIRE(w->utts_per_cluster == 1 || w->utts_per_cluster == 2, "wae_ar_generate: utts_per_cluster must be 1 or 2");
+    WAE_REQUIRE(d.R % 64 == 0 && d.S % 64 == 0 && d.S <= 64 * MAXMS && d.G % 2 == 0,
+                "wae_ar_generate: need R%%64==0, S%%64==0, S<=256 (R=%d S=%d)", d.R, d.S);
+    WAE_REQUIRE(d.C % 4 == 0, "wae_ar_generate: C%%4 != 0");
+    WAE_REQUIRE((d.C == 0) == (c_btc == nullptr), "wae_ar_generate: c must be given iff C>0");
+    WAE_REQUIRE(sample_mode >= 0 && sample_mode <= 3, "wae_ar_generate: bad sample_mode");
+    WAE_REQUIRE(sample_mode == WAE_AR_SAMPLE_NONE || uniforms != nullptr, "wae_ar_generate: uniforms required for sampling");
+    WAE_REQUIRE(d.O <= 256, "wae_ar_generate: O > 256 unsupported");
+    WAE_REQUIRE(forced != nullptr || Tf == 0, "wae_ar_generate: Tf > 0 without forced inputs");
+    if (workspace_bytes < wae_ar_workspace(w, B, T))
+        return wae::set_error(WAE_ERR_WORKSPACE, "wae_ar_generate: workspace %zu < %zu", workspace_bytes, wae_ar_workspace(w, B, T));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+    ArArgs a;
+    memset(&a, 0, sizeof(a));
+    a.d = d;
+    a.wtype = w->wtype; a.cluster = w->cluster; a.B = B; a.T = T; a.Tf = forced ? Tf : 0;
+    a.sample_mode = sample_mode; a.apply_softmax = apply_softmax;
+    a.Hp = (H + 63) / 64 * 64;
+    a.Cp = (d.C + 63) / 64 * 64;
+    a.K1p = d.kernel_size * d.R + a.Cp;
+    WAE_REQUIRE(a.K1p <= 64 * MAXM1 && a.Hp <= 64 * MAXM2, "wae_ar_generate: K1p=%d or Hp=%d too large", a.K1p, a.Hp);
+    int rows = 0;
+    for (int l = 0; l < d.layers; ++l) {
+        a.ring_off[l] = rows;
+        a.ring_ns[l] = (d.kernel_size - 1) * d.dilation[l] + 1;
+        rows += a.ring_ns[l];
+    }
+    a.ring_rows = rows;
+    a.blob = static_cast<const uint8_t*>(w->blob);
+    a.blob_off = reinterpret_cast<const long long*>(w->layer_off);
+    WAE_REQUIRE(w->blob && w->layer_off && w->b1 && w->bo && w->bs && w->b3 && w->b4 && w->wf && w->bf, "wae_ar_generate: null weight pointer");
+    a.bo = w->bo; a.bs = w->bs; a.b3 = w->b3; a.b4 = w->b4; a.wf = w->wf; a.bf = w->bf;
+    a.c_btc = c_btc; a.init = init; a.forced = forced; a.uniforms = uniforms;
+    if (sample_mode == WAE_AR_SAMPLE_CATEGORICAL) { a.nmix = 0; a.nu = 1; }
+    else if (sample_mode == WAE_AR_SAMPLE_MOL || sample_mode == WAE_AR_SAMPLE_GAUSS) {
+        a.nmix = (d.O == 2) ? 1 : d.O / 3;
+        a.nu = a.nmix + 1;
+        WAE_REQUIRE(d.Oin == 1, "wae_ar_generate: mixture sampling needs scalar input (Oin=1)");
+    }
+    a.out_idx = out_idx; a.out_dense = out_dense;
+    a.skip_scale = (float)sqrt(1.0 / (double)d.layers);
+
+    char* p = static_cast<char*>(workspace);
+    a.ring = reinterpret_cast<float*>(p);
+    const size_t ring_bytes = wae::align_up((size_t)B * rows * d.R * sizeof(float), 256);
+    float* gb = reinterpret_cast<float*>(p + ring_bytes);
+    a.gb = gb;
+    WAE_CHECK_CUDA(cudaMemsetAsync(a.ring, 0, ring_bytes, stream));
+    ar_gbias_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, gemb, d.layers, B, d.G, d.Gi, gb);
+    WAE_CHECK_LAUNCH();
+
+    const int U = w->utts_per_cluster;
+    const int wbytes = (w->wtype == 0) ? 4 : 2;
+    const ArSmem sl = ar_smem_layout(d, a.cluster, U, wbytes, a.Hp, a.Cp, a.K1p);
+    WAE_REQUIRE(sl.total <= 232448, "wae_ar_generate: shared memory %d B exceeds 227 KB (use a larger cluster or bf16 weights)", sl.total);
+    const int clusters = (B + U - 1) / U;
+    if (w->wtype == 0) {
+        if (U == 1) return launch_ar<float, 1>(a, clusters, sl.total, stream);
+        return launch_ar<float, 2>(a, clusters, sl.total, stream);
+    } else {
+        if (U == 1) return launch_ar<__nv_bfloat16, 1>(a, clusters, sl.total, stream);
+        return launch_ar<__nv_bfloat16, 2>(a, clusters, sl.total, stream);
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,864 @@
+// wn_stack_bf16.cu -- the teacher-forced WaveNet decoder stack on 5th-gen tensor cores (sm_100a).
+//
+// Replaces the reference's per-layer chain of cuDNN dilated conv + five 1x1 convs + ~7 element-wise
+// kernels (wavenet_vocoder/modules.py:115-163, called from wavenet.py:205-207) by ONE persistent,
+// warp-specialised kernel per layer:
+//
+//   GEMM1  z[128 samples x G]   = [x(t-2d) | x(t-d) | x(t) | c(t)] (K = kw*R + C)  x  W1^T
+//                                 tcgen05.mma kind::f16 (bf16 in, fp32 accumulate in TMEM), operands
+//                                 staged by TMA (128B swizzle); the dilated causal taps are just three
+//                                 TMA boxes at time coordinates t0-2d, t0-d, t0 of a (R, T, B) tensor
+//                                 map -- negative / past-the-end coordinates zero-fill, per utterance.
+//   EPI1   h = tanh(z_a + bias_a) * sigmoid(z_b + bias_b)   TMEM -> registers -> bf16, written (a) to
+//                                 shared memory in the UMMA K-major swizzled layout (A operand of GEMM2)
+//                                 and (b) to the h_all[l] plane in HBM for the deferred skip GEMM
+//   GEMM2  o[128 x R]           = h (K = H) x Wo^T
+//   EPI2   x' = (o + bo + x) * sqrt(.5)  -> bf16 channels-last
+//
+// The skip path (wavenet.py:207-208) is NOT accumulated layer by layer in HBM: sum_l Ws_l h_l is one
+// K = L*H contraction, done once by the head kernel straight from the h_all planes, fused with
+// sqrt(1/L), ReLU, the S->S 1x1, ReLU and the S->O 1x1 (wavenet.py:208-212): three chained tcgen05
+// GEMMs whose intermediate activations never leave shared memory / TMEM.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA
+// issuer (one elected lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its warp_id % 4).
+#include "wae_common.cuh"
+#include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint
+
+using namespace wae::ptx;
+
+namespace {
+
+constexpr int BM = 128;                 // samples per tile (UMMA M)
+constexpr int BK = 64;                  // bf16 per k-block = one 128-byte swizzle row
+constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int NUM_THREADS = 192;
+constexpr int EPI_WARP0 = 2;
+constexpr int TMEM_COLS = 512;
+constexpr float kSqrtHalf = 0.70710678118654752440f;
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+// bf16 tensor [d2][d1][d0] (d0 contiguous), box {b0, b1, 1}, 128B swizzle (b0 must be 64).
+int make_tmap(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_elems,
+              uint64_t stride2_elems, uint32_t b0, uint32_t b1) {
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return wae::set_error(WAE_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {stride1_elems * 2, stride2_elems * 2};
+    cuuint32_t box[3] = {b0, b1, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return wae::set_error(WAE_ERR_CUDA,
+                              "cuTensorMapEncodeTiled failed (%d): base=%p dims=(%llu,%llu,%llu) strides=(%llu,%llu) box=(%u,%u)",
+                              (int)r, base, (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2,
+                              (unsigned long long)strides[0], (unsigned long long)strides[1], b0, b1);
+    return WAE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// device: pipeline bookkeeping
+// ---------------------------------------------------------------------------------------------
+struct Ring {  // smem stage ring shared by the producer and the MMA issuer (each keeps its own cursor)
+    uint32_t stage = 0, phase = 0;
+    int nstages;
+    __device__ explicit Ring(int n) : nstages(n) {}
+    __device__ __forceinline__ void advance() {
+        if (++stage == (uint32_t)nstages) { stage = 0; phase ^= 1; }
+    }
+};
+
+// Issue the 4 UMMA_K=16 steps of one 64-wide k-block.  a_addr/b_addr: shared addresses of the
+// swizzled [rows][64] bf16 tiles (1024-byte aligned).
+__device__ __forceinline__ void issue_kblock(uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc,
+                                             bool zero_init) {
+    const uint64_t ad = umma_desc_sw128(a_addr);
+    const uint64_t bd = umma_desc_sw128(b_addr);
+#pragma unroll
+    for (int k = 0; k < BK / 16; ++k)  // +32 bytes per step = +2 in the 16-byte-unit address field
+        umma_bf16(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (zero_init && k == 0) ? 0u : 1u);
+}
+
+// byte offset of the 16-byte chunk `c16` (0..7) of row `r` inside a swizzled [rows][64] bf16 tile
+__device__ __forceinline__ uint32_t sw128_off(int r, int c16) {
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c16 ^ (r & 7)) << 4));
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// unit-test GEMM: C[M][N] = A[M][K] * B[N][K]^T   (validates TMA + descriptors + TMEM readback)
+// ---------------------------------------------------------------------------------------------
+struct GemmArgs {
+    CUtensorMap tm_a, tm_b;
+    float* C;
+    int M, N, K;
+};
+
+constexpr int GEMM_STAGES = 3;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __grid_constant__ GemmArgs g) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int B_TILE_BYTES = g.N * BK * 2;
+    const int STAGE_BYTES = A_TILE_BYTES + ((B_TILE_BYTES + 1023) / 1024) * 1024;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + GEMM_STAGES;
+    uint64_t* acc_full = bars + 2 * GEMM_STAGES;
+    uint64_t* acc_empty = acc_full + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GEMM_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 128);
+        fence_mbar_init();
+        tma_prefetch_desc(&g.tm_a);
+        tma_prefetch_desc(&g.tm_b);
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ntiles = (g.M + BM - 1) / BM;
+    const int nkb = g.K / BK;
+    const uint32_t idesc = umma_idesc_bf16(BM, g.N);
+
+    if (warp == 0) {
+        if (elect_one()) {
+            Ring ring(GEMM_STAGES);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + B_TILE_BYTES);
+                    tma_load_3d(&g.tm_a, &full[ring.stage], sa, kb * BK, tile * BM, 0);
+                    tma_load_3d(&g.tm_b, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, 0);
+                    ring.advance();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            Ring ring(GEMM_STAGES);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                if (it > 0) { mbar_wait(acc_empty, (it - 1) & 1); tc_fence_after(); }
+                for (int kb = 0; kb < nkb; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    issue_kblock(tmem_base, sa, sa + A_TILE_BYTES, idesc, kb == 0);
+                    umma_commit(&empty[ring.stage]);
+                    ring.advance();
+                }
+                umma_commit(acc_full);
+            }
+        }
+    } else {
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            mbar_wait(acc_full, it & 1);
+            tc_fence_after();
+            const int m = tile * BM + row;
+            for (int c0 = 0; c0 < g.N; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+                tmem_ld_wait();
+                if (m < g.M) {
+                    float4* dst = reinterpret_cast<float4*>(g.C + (size_t)m * g.N + c0);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// prep kernels
+// ---------------------------------------------------------------------------------------------
+// gb[l][b][:] = b1[l] + wg[l]^T gemb[b]   (natural column order)
+__global__ void __launch_bounds__(256)
+gbias_bf16_kernel(const float* __restrict__ b1, const float* __restrict__ wg, const float* __restrict__ gemb, int L,
+                  int B, int G, int Gi, float* __restrict__ gb) {
+    const int l = blockIdx.x / B, b = blockIdx.x % B;
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+        float acc = 0.f;
+        if (wg != nullptr && gemb != nullptr)
+            for (int i = 0; i < Gi; ++i)
+                acc = fmaf(__ldg(&wg[((size_t)l * Gi + i) * G + g]), __ldg(&gemb[(size_t)b * Gi + i]), acc);
+        gb[((size_t)l * B + b) * G + g] = __ldg(&b1[(size_t)l * G + g]) + acc;
+    }
+}
+
+// first_conv on (B,Oin,T) fp32 input -> bf16 channels-last [B][T][R].  One-hot columns (the
+// mu-law input of every preset) are detected per sample and become a gather of one weight row;
+// anything else takes the dense dot product.  32 samples per block.
+constexpr int FC_T = 32;
+__global__ void __launch_bounds__(256)
+first_conv_bf16_kernel(const float* __restrict__ x, const float* __restrict__ wf, const float* __restrict__ bf,
+                       int T, int Oin, int R, __nv_bfloat16* __restrict__ x0) {
+    extern __shared__ float xs[];  // [Oin][FC_T+1]
+    __shared__ int hot[FC_T];
+    const int b = blockIdx.y, t0 = blockIdx.x * FC_T;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < Oin * FC_T; e += 256) {
+        const int o = e / FC_T, tt = e % FC_T;
+        const int t = t0 + tt;
+        xs[o * (FC_T + 1) + tt] = (t < T) ? __ldg(&x[((size_t)b * Oin + o) * T + t]) : 0.f;
+    }
+    __syncthreads();
+    // one-hot detection: warp w scans samples w*4 .. w*4+3
+    for (int s = 0; s < FC_T / 8; ++s) {
+        const int tt = warp * (FC_T / 8) + s;
+        int nz = 0, pos = -1;
+        bool is_one = true;
+        for (int o = lane; o < Oin; o += 32) {
+            const float v = xs[o * (FC_T + 1) + tt];
+            if (v != 0.f) { ++nz; pos = o; is_one = is_one && (v == 1.f); }
+        }
+        const int nz_all = __reduce_add_sync(0xffffffffu, nz);
+        const int pos_all = __reduce_max_sync(0xffffffffu, pos);
+        const bool ok = __all_sync(0xffffffffu, is_one);
+        if (lane == 0) hot[tt] = (Oin > 1 && nz_all == 1 && ok) ? pos_all : -1;
+    }
+    __syncthreads();
+    for (int tt = 0; tt < FC_T; ++tt) {
+        const int t = t0 + tt;
+        if (t >= T) break;
+        const int h = hot[tt];
+        for (int r = tid; r < R; r += 256) {
+            float acc;
+            if (h >= 0) {
+                acc = __ldg(&wf[(size_t)h * R + r]) + __ldg(&bf[r]);
+            } else {
+                acc = 0.f;
+                for (int o = 0; o < Oin; ++o) acc = fmaf(__ldg(&wf[(size_t)o * R + r]), xs[o * (FC_T + 1) + tt], acc);
+                acc += __ldg(&bf[r]);
+            }
+            x0[((size_t)b * T + t) * R + r] = __float2bfloat16_rn(acc);
+        }
+    }
+}
+
+// (B,C,T) fp32 -> [B][T][Cp] bf16, zero padded channels
+__global__ void __launch_bounds__(256)
+cond_to_cl_kernel(const float* __restrict__ c, int T, int C, int Cp, __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[32][65];
+    const int b = blockIdx.z, t0 = blockIdx.x * 64, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+    for (int i = ty; i < 32; i += 4) {
+        const int ch = c0 + i, t = t0 + tx;
+        tile[i][tx] = (ch < C && t < T) ? __ldg(&c[((size_t)b * C + ch) * T + t]) : 0.f;
+    }
+    __syncthreads();
+    const int cx = threadIdx.x & 31, tyy = threadIdx.x >> 5;  // 32 x 8
+    for (int i = tyy; i < 64; i += 8) {
+        const int t = t0 + i, ch = c0 + cx;
+        if (t < T && ch < Cp) out[((size_t)b * T + t) * Cp + ch] = __float2bfloat16_rn(tile[cx][i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused residual layer
+// ---------------------------------------------------------------------------------------------
+struct LayerArgs {
+    CUtensorMap tm_x;    // layer input  [B][T][R]   box {64, 128}
+    CUtensorMap tm_c;    // conditioning [B][T][Cp]  box {64, 128}
+    CUtensorMap tm_w1;   // [L][G][K1p]              box {64, G}
+    CUtensorMap tm_wo;   // [L][R][Hp]               box {64, R}
+    const float* gb;     // [B][G]  conv bias + g term of this layer
+    const float* bo;     // [R]
+    const __nv_bfloat16* x_in;   // [B][T][R]
+    __nv_bfloat16* x_out;        // [B][T][R] or null (last layer: residual output is dead)
+    __nv_bfloat16* h_out;        // [B][T][Hp] plane of this layer
+    int B, T, R, G, Hp, Cp, kw, dil, layer, tiles_per_utt;
+};
+
+constexpr int LAYER_STAGES = 4;
+
+// shared memory: [stages x (A 16K | B G*128)] [h: Hp/64 x 16K] [barriers]
+__global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid_constant__ LayerArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int H = a.G / 2;
+    const int B_BYTES = 256 * BK * 2;  // stage B slot sized for N = 256
+    const int STAGE_BYTES = A_TILE_BYTES + B_BYTES;
+    uint8_t* hbuf = smem + LAYER_STAGES * STAGE_BYTES;
+    const int nkh = a.Hp / BK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hbuf + nkh * A_TILE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + LAYER_STAGES;
+    uint64_t* acc1_full = bars + 2 * LAYER_STAGES;
+    uint64_t* epi1_done = acc1_full + 1;
+    uint64_t* acc2_full = acc1_full + 2;
+    uint64_t* epi2_done = acc1_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < LAYER_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc1_full, 1);
+        mbar_init(epi1_done, 128);
+        mbar_init(acc2_full, 1);
+        mbar_init(epi2_done, 128);
+        fence_mbar_init();
+        tma_prefetch_desc(&a.tm_x);
+        tma_prefetch_desc(&a.tm_c);
+        tma_prefetch_desc(&a.tm_w1);
+        tma_prefetch_desc(&a.tm_wo);
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc1 = tmem_base;        // columns [0, G)
+    const uint32_t tmem_acc2 = tmem_base + 256;  // columns [256, 256+R)
+
+    const int ntiles = a.B * a.tiles_per_utt;
+    const int nk_taps = a.kw * (a.R / BK);
+    const int nk_c = a.Cp / BK;
+    const bool has_out = (a.x_out != nullptr);
+    const int w1_bytes = a.G * BK * 2, wo_bytes = a.R * BK * 2;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            Ring ring(LAYER_STAGES);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+                int kcol = 0;
+                for (int kb = 0; kb < nk_taps + nk_c; ++kb, kcol += BK) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + w1_bytes);
+                    if (kb < nk_taps) {
+                        const int tap = kb / (a.R / BK), r0 = (kb % (a.R / BK)) * BK;
+                        tma_load_3d(&a.tm_x, &full[ring.stage], sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
+                    } else {
+                        tma_load_3d(&a.tm_c, &full[ring.stage], sa, (kb - nk_taps) * BK, t0, b);
+                    }
+                    tma_load_3d(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES, kcol, 0, a.layer);
+                    ring.advance();
+                }
+                if (has_out) {
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                        uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[ring.stage], wo_bytes);
+                        tma_load_3d(&a.tm_wo, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, a.layer);
+                        ring.advance();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            Ring ring(LAYER_STAGES);
+            const uint32_t idesc1 = umma_idesc_bf16(BM, a.G);
+            const uint32_t idesc2 = umma_idesc_bf16(BM, a.R);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                // acc1 of the previous tile was drained before its GEMM2 was issued (epi1_done wait below),
+                // or -- when there is no GEMM2 -- must be waited for here.
+                if (!has_out && it > 0) { mbar_wait(epi1_done, (it - 1) & 1); tc_fence_after(); }
+                for (int kb = 0; kb < nk_taps + nk_c; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    issue_kblock(tmem_acc1, sa, sa + A_TILE_BYTES, idesc1, kb == 0);
+                    umma_commit(&empty[ring.stage]);
+                    ring.advance();
+                }
+                umma_commit(acc1_full);
+                if (has_out) {
+                    mbar_wait(epi1_done, it & 1);  // h is in shared memory, acc1 drained
+                    tc_fence_after();
+                    if (it > 0) { mbar_wait(epi2_done, (it - 1) & 1); tc_fence_after(); }
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait(&full[ring.stage], ring.phase);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                        issue_kblock(tmem_acc2, smem_u32(hbuf + kb * A_TILE_BYTES), sb, idesc2, kb == 0);
+                        umma_commit(&empty[ring.stage]);
+                        ring.advance();
+                    }
+                    umma_commit(acc2_full);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t hbuf_addr = smem_u32(hbuf);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+            const int t = t0 + row;
+            const bool live = (t < a.T);
+            const float* gbp = a.gb + (size_t)b * a.G;
+            __nv_bfloat16* hrow = a.h_out + ((size_t)b * a.T + t) * a.Hp;
+
+            // ---- EPI1: gate ----
+            mbar_wait(acc1_full, it & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < a.Hp; c0 += 16) {
+                uint32_t packed[8];
+                if (c0 < H) {  // H % 16 == 0 is required by the host wrapper
+                    float va[16], vb[16];
+                    tmem_ld16(tmem_acc1 + lane_base + c0, va);
+                    tmem_ld16(tmem_acc1 + lane_base + H + c0, vb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float2 ba = __ldg(reinterpret_cast<const float2*>(gbp + c0 + i));
+                        const float2 bb = __ldg(reinterpret_cast<const float2*>(gbp + H + c0 + i));
+                        const float h0 = tanh_fast(va[i] + ba.x) * sigmoid_fast(vb[i] + bb.x);
+                        const float h1 = tanh_fast(va[i + 1] + ba.y) * sigmoid_fast(vb[i + 1] + bb.y);
+                        packed[i >> 1] = pack_bf16x2(h0, h1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = 0u;  // K padding of GEMM2 / skip GEMM
+                }
+                const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                const uint32_t base = hbuf_addr + kb * A_TILE_BYTES;
+                st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+                if (live) {
+                    uint4* dst = reinterpret_cast<uint4*>(hrow + c0);
+                    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();  // generic-proxy writes of h -> visible to the tensor-core (async) proxy
+            mbar_arrive(epi1_done);
+
+            // ---- EPI2: residual ----
+            if (has_out) {
+                mbar_wait(acc2_full, it & 1);
+                tc_fence_after();
+                const __nv_bfloat16* xin = a.x_in + ((size_t)b * a.T + t) * a.R;
+                __nv_bfloat16* xout = a.x_out + ((size_t)b * a.T + t) * a.R;
+                for (int c0 = 0; c0 < a.R; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_acc2 + lane_base + c0, v);
+                    tmem_ld_wait();
+                    if (live) {
+                        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(xin + c0));
+                        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(xin + c0 + 8));
+                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                            const float2 bo2 = __ldg(reinterpret_cast<const float2*>(a.bo + c0 + 2 * i));
+                            const float o0 = ((v[2 * i] + bo2.x) + __low2float(rv)) * kSqrtHalf;
+                            const float o1 = ((v[2 * i + 1] + bo2.y) + __high2float(rv)) * kSqrtHalf;
+                            packed[i] = pack_bf16x2(o0, o1);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(xout + c0);
+                        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(epi2_done);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the head: skip GEMM over all layers + ReLU + 1x1 + ReLU + 1x1
+// ---------------------------------------------------------------------------------------------
+struct HeadArgs {
+    CUtensorMap tm_h;    // h_all viewed as [L*B][T][Hp]  box {64, 128}
+    CUtensorMap tm_ws;   // [L][S][Hp]                    box {64, S}
+    CUtensorMap tm_w3;   // [1][S][S]                     box {64, S}
+    CUtensorMap tm_w4;   // [1][Op][S]                    box {64, Op}
+    const float* bs_sum; // [S] sum of the skip biases of all layers
+    const float* b3;     // [S]
+    const float* b4;     // [O]
+    float* logits;       // (B, O, T)
+    float scale;         // sqrt(1/L)
+    int B, T, L, S, O, Op, Hp, tiles_per_utt;
+};
+
+constexpr int HEAD_STAGES = 3;
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) head_bf16_kernel(const __grid_constant__ HeadArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int B_BYTES = 256 * BK * 2;
+    const int STAGE_BYTES = A_TILE_BYTES + B_BYTES;
+    uint8_t* act = smem + HEAD_STAGES * STAGE_BYTES;   // [S/64][128 x 64] bf16 swizzled
+    const int nks = a.S / BK, nkh = a.Hp / BK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(act + nks * A_TILE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + HEAD_STAGES;
+    uint64_t* accs_full = bars + 2 * HEAD_STAGES;
+    uint64_t* epis_done = accs_full + 1;
+    uint64_t* acc3_full = accs_full + 2;
+    uint64_t* epi3_done = accs_full + 3;
+    uint64_t* acc4_full = accs_full + 4;
+    uint64_t* epi4_done = accs_full + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accs_full + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HEAD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(accs_full, 1); mbar_init(epis_done, 128);
+        mbar_init(acc3_full, 1); mbar_init(epi3_done, 128);
+        mbar_init(acc4_full, 1); mbar_init(epi4_done, 128);
+        fence_mbar_init();
+        tma_prefetch_desc(&a.tm_h);
+        tma_prefetch_desc(&a.tm_ws);
+        tma_prefetch_desc(&a.tm_w3);
+        tma_prefetch_desc(&a.tm_w4);
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base;          // skip accumulator, columns [0, S)
+    const uint32_t tmem_34 = tmem_base + 256;   // GEMM3 then GEMM4 accumulator, columns [256, 512)
+
+    const int ntiles = a.B * a.tiles_per_utt;
+    const int ws_bytes = a.S * BK * 2, w4_bytes = a.Op * BK * 2;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            Ring ring(HEAD_STAGES);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+                for (int l = 0; l < a.L; ++l)
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                        uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + ws_bytes);
+                        tma_load_3d(&a.tm_h, &full[ring.stage], sa, kb * BK, t0, l * a.B + b);
+                        tma_load_3d(&a.tm_ws, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, l);
+                        ring.advance();
+                    }
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[ring.stage], ws_bytes);
+                    tma_load_3d(&a.tm_w3, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, 0);
+                    ring.advance();
+                }
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[ring.stage], w4_bytes);
+                    tma_load_3d(&a.tm_w4, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, 0);
+                    ring.advance();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            Ring ring(HEAD_STAGES);
+            const uint32_t idesc_s = umma_idesc_bf16(BM, a.S);
+            const uint32_t idesc_4 = umma_idesc_bf16(BM, a.Op);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                // skip accumulator region was drained by EPI_S of the previous tile (waited below, before GEMM3)
+                for (int kb = 0; kb < a.L * nkh; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    issue_kblock(tmem_s, sa, sa + A_TILE_BYTES, idesc_s, kb == 0);
+                    umma_commit(&empty[ring.stage]);
+                    ring.advance();
+                }
+                umma_commit(accs_full);
+                mbar_wait(epis_done, it & 1);
+                tc_fence_after();
+                if (it > 0) { mbar_wait(epi4_done, (it - 1) & 1); tc_fence_after(); }
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                    issue_kblock(tmem_34, smem_u32(act + kb * A_TILE_BYTES), sb, idesc_s, kb == 0);
+                    umma_commit(&empty[ring.stage]);
+                    ring.advance();
+                }
+                umma_commit(acc3_full);
+                mbar_wait(epi3_done, it & 1);
+                tc_fence_after();
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                    issue_kblock(tmem_34, smem_u32(act + kb * A_TILE_BYTES), sb, idesc_4, kb == 0);
+                    umma_commit(&empty[ring.stage]);
+                    ring.advance();
+                }
+                umma_commit(acc4_full);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t act_addr = smem_u32(act);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+            const int t = t0 + row;
+            const bool live = (t < a.T);
+
+            // relu(scale * (acc + bias)) / relu(acc + bias) -> bf16 -> `act` (A operand of the next GEMM)
+            auto relu_to_act = [&](uint32_t tmem_acc, const float* bias, float scale) {
+                for (int c0 = 0; c0 < a.S; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_acc + lane_base + c0, v);
+                    tmem_ld_wait();
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c0 + 2 * i));
+                        const float o0 = fmaxf((v[2 * i] + b2.x) * scale, 0.f);
+                        const float o1 = fmaxf((v[2 * i + 1] + b2.y) * scale, 0.f);
+                        packed[i] = pack_bf16x2(o0, o1);
+                    }
+                    const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                    const uint32_t base = act_addr + kb * A_TILE_BYTES;
+                    st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                    st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+            };
+
+            mbar_wait(accs_full, it & 1);
+            tc_fence_after();
+            relu_to_act(tmem_s, a.bs_sum, a.scale);
+            mbar_arrive(epis_done);
+
+            mbar_wait(acc3_full, it & 1);
+            tc_fence_after();
+            relu_to_act(tmem_34, a.b3, 1.0f);
+            mbar_arrive(epi3_done);
+
+            mbar_wait(acc4_full, it & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < a.Op; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_34 + lane_base + c0, v);
+                tmem_ld_wait();
+                if (live) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.O)  // lanes of a warp = consecutive samples -> 128-byte coalesced rows
+                            a.logits[((size_t)b * a.O + c0 + i) * a.T + t] = v[i] + __ldg(a.b4 + c0 + i);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(epi4_done);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+struct Bf16Workspace {
+    __nv_bfloat16 *xa, *xb, *ccl, *hall;
+    float* gb;
+    size_t total;
+};
+
+Bf16Workspace carve(const wae_stack_dims& d, int B, int T, void* base) {
+    Bf16Workspace w;
+    const size_t bt = (size_t)B * T;
+    const int Hp = (d.G / 2 + BK - 1) / BK * BK;
+    const int Cp = (d.C + BK - 1) / BK * BK;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char* r = p ? p + off : nullptr; off += wae::align_up(bytes, 1024); return r; };
+    w.xa = reinterpret_cast<__nv_bfloat16*>(take(bt * d.R * 2));
+    w.xb = reinterpret_cast<__nv_bfloat16*>(take(bt * d.R * 2));
+    w.ccl = reinterpret_cast<__nv_bfloat16*>(take(bt * (Cp > 0 ? Cp : 1) * 2));
+    w.hall = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.layers * bt * Hp * 2));
+    w.gb = reinterpret_cast<float*>(take((size_t)d.layers * B * d.G * 4));
+    w.total = off;
+    return w;
+}
+
+}  // namespace
+
+extern "C" {
+
+int wae_gemm_bf16_tn(const void* A, const void* Bm, float* Cout, int M, int N, int K, void* stream_) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(A && Bm && Cout, "wae_gemm_bf16_tn: null pointer");
+    WAE_REQUIRE(M > 0 && N >= 16 && N <= 256 && N % 16 == 0 && K >= BK && K % BK == 0,
+                "wae_gemm_bf16_tn: need N%%16==0, 16<=N<=256, K%%64==0 (M=%d N=%d K=%d)", M, N, K);
+    GemmArgs g;
+    if (int rc = make_tmap(&g.tm_a, A, K, M, 1, K, (uint64_t)M * K, BK, BM)) return rc;
+    if (int rc = make_tmap(&g.tm_b, Bm, K, N, 1, K, (uint64_t)N * K, BK, N)) return rc;
+    g.C = Cout; g.M = M; g.N = N; g.K = K;
+    const int b_bytes = ((N * BK * 2 + 1023) / 1024) * 1024;
+    const size_t smem = 1024 + (size_t)GEMM_STAGES * (A_TILE_BYTES + b_bytes) + 256;
+    WAE_CHECK_CUDA(cudaFuncSetAttribute(gemm_bf16_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ntiles = (M + BM - 1) / BM;
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+    gemm_bf16_tn_kernel<<<grid, NUM_THREADS, smem, static_cast<cudaStream_t>(stream_)>>>(g);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T) {
+    if (!d || B <= 0 || T <= 0) return 0;
+    return carve(*d, B, T, nullptr).total;
+}
+
+int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,
+                           int T, float* logits, void* workspace, size_t workspace_bytes, void* stream_) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(w && x && logits && workspace, "wae_stack_forward_bf16: null pointer");
+    const wae_stack_dims& d = w->d;
+    const int H = d.G / 2;
+    WAE_REQUIRE(B > 0 && T > 0 && B <= 65535, "wae_stack_forward_bf16: B=%d T=%d", B, T);
+    WAE_REQUIRE(d.layers >= 1 && d.layers <= WAE_MAX_LAYERS && d.kernel_size >= 1, "bad layers/kernel_size");
+    WAE_REQUIRE(d.R % BK == 0 && d.R <= 256 && d.S % BK == 0 && d.S <= 256 && d.G % 32 == 0 && d.G <= 256 && d.O <= 256,
+                "wae_stack_forward_bf16: this build supports R,S in {64,128,192,256}, G%%32==0, G<=256, O<=256 "
+                "(R=%d G=%d S=%d O=%d); use the fp32 stack for other shapes", d.R, d.G, d.S, d.O);
+    WAE_REQUIRE((d.C == 0) == (c == nullptr), "wae_stack_forward_bf16: c must be given iff C>0");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
+        return wae::set_error(WAE_ERR_ALIGN, "wae_stack_forward_bf16: workspace must be 1024-byte aligned");
+    Bf16Workspace ws = carve(d, B, T, workspace);
+    if (workspace_bytes < ws.total)
+        return wae::set_error(WAE_ERR_WORKSPACE, "wae_stack_forward_bf16: workspace %zu < %zu", workspace_bytes, ws.total);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+    const int Hp = (H + BK - 1) / BK * BK;
+    const int Cp = (d.C + BK - 1) / BK * BK;
+    const int K1p = d.kernel_size * d.R + Cp;
+    const int Op = (d.O + 15) / 16 * 16;
+    const int tiles_per_utt = (T + BM - 1) / BM;
+    const int ntiles = B * tiles_per_utt;
+    const int grid = ntiles < num_sms() ? ntiles : num_sms();
+
+    // ---- prep: g bias, first conv, conditioning layout ----
+    gbias_bf16_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, gemb, d.layers, B, d.G, d.Gi, ws.gb);
+    WAE_CHECK_LAUNCH();
+    {
+        const size_t sm = (size_t)d.Oin * (FC_T + 1) * sizeof(float);
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(first_conv_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        first_conv_bf16_kernel<<<dim3((T + FC_T - 1) / FC_T, B), 256, sm, stream>>>(x, w->wf, w->bf, T, d.Oin, d.R, ws.xa);
+        WAE_CHECK_LAUNCH();
+    }
+    if (d.C > 0) {
+        cond_to_cl_kernel<<<dim3((T + 63) / 64, (Cp + 31) / 32, B), 256, 0, stream>>>(c, T, d.C, Cp, ws.ccl);
+        WAE_CHECK_LAUNCH();
+    }
+
+    // ---- layers ----
+    const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 256;
+    WAE_REQUIRE(smem_layer <= 232448, "wae_stack_forward_bf16: layer kernel shared memory %zu too large", smem_layer);
+    WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
+
+    LayerArgs la;
+    CUtensorMap tm_xa, tm_xb;
+    if (int rc = make_tmap(&tm_xa, ws.xa, d.R, T, B, d.R, (uint64_t)T * d.R, BK, BM)) return rc;
+    if (int rc = make_tmap(&tm_xb, ws.xb, d.R, T, B, d.R, (uint64_t)T * d.R, BK, BM)) return rc;
+    if (d.C > 0) {
+        if (int rc = make_tmap(&la.tm_c, ws.ccl, Cp, T, B, Cp, (uint64_t)T * Cp, BK, BM)) return rc;
+    } else {
+        la.tm_c = tm_xa;  // never used (nk_c == 0)
+    }
+    if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, d.G, d.layers, K1p, (uint64_t)d.G * K1p, BK, d.G)) return rc;
+    if (int rc = make_tmap(&la.tm_wo, w->wo, Hp, d.R, d.layers, Hp, (uint64_t)d.R * Hp, BK, d.R)) return rc;
+    la.B = B; la.T = T; la.R = d.R; la.G = d.G; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
+    la.tiles_per_utt = tiles_per_utt;
+    __nv_bfloat16* cur = ws.xa;
+    __nv_bfloat16* nxt = ws.xb;
+    for (int l = 0; l < d.layers; ++l) {
+        la.tm_x = (cur == ws.xa) ? tm_xa : tm_xb;
+        la.gb = ws.gb + (size_t)l * B * d.G;
+        la.bo = w->bo + (size_t)l * d.R;
+        la.x_in = cur;
+        la.x_out = (l + 1 < d.layers) ? nxt : nullptr;
+        la.h_out = ws.hall + (size_t)l * B * T * Hp;
+        la.dil = d.dilation[l];
+        la.layer = l;
+        layer_bf16_kernel<<<grid, NUM_THREADS, smem_layer, stream>>>(la);
+        WAE_CHECK_LAUNCH();
+        __nv_bfloat16* t = cur; cur = nxt; nxt = t;
+    }
+
+    // ---- head ----
+    HeadArgs ha;
+    if (int rc = make_tmap(&ha.tm_h, ws.hall, Hp, T, (uint64_t)d.layers * B, Hp, (uint64_t)T * Hp, BK, BM)) return rc;
+    if (int rc = make_tmap(&ha.tm_ws, w->ws, Hp, d.S, d.layers, Hp, (uint64_t)d.S * Hp, BK, d.S)) return rc;
+    if (int rc = make_tmap(&ha.tm_w3, w->w3, d.S, d.S, 1, d.S, (uint64_t)d.S * d.S, BK, d.S)) return rc;
+    if (int rc = make_tmap(&ha.tm_w4, w->w4, d.S, Op, 1, d.S, (uint64_t)Op * d.S, BK, Op)) return rc;
+    ha.bs_sum = w->bs_sum; ha.b3 = w->b3; ha.b4 = w->b4; ha.logits = logits;
+    ha.scale = (float)sqrt(1.0 / (double)d.layers);
+    ha.B = B; ha.T = T; ha.L = d.layers; ha.S = d.S; ha.O = d.O; ha.Op = Op; ha.Hp = Hp; ha.tiles_per_utt = tiles_per_utt;
+    const size_t smem_head = 1024 + (size_t)HEAD_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(d.S / BK) * A_TILE_BYTES + 256;
+    WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
+    head_bf16_kernel<<<grid, NUM_THREADS, smem_head, stream>>>(ha);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+}  // extern "C"
