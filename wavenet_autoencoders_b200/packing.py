@@ -1,0 +1,272 @@
+"""Weight packing for libwae_b200.so.
+
+Everything here reads a WaveNet-shaped ``nn.Module`` purely through the attribute names the reference
+defines (``first_conv``, ``conv_layers[i].{conv,conv1x1c,conv1x1g,conv1x1_out,conv1x1_skip}``,
+``last_conv_layers[1|3]`` -- wavenet_vocoder/wavenet.py:119-141, modules.py:88-107), so it packs both
+this package's modules and an imported reference model (the GPU parity tests use that).
+
+Weight norm (modules.py:18, old-style ``weight_g``/``weight_v``) is folded here with the same ATen
+primitive the reference's pre-forward hook uses (torch._weight_norm), so folded weights are bit-identical.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib
+
+
+def folded_weight(m: torch.nn.Module) -> torch.Tensor:
+    """w = g * v / ||v||  (norm over all dims but 0), or the plain weight after remove_weight_norm."""
+    if hasattr(m, "weight_g") and hasattr(m, "weight_v"):
+        return torch._weight_norm(m.weight_v.detach(), m.weight_g.detach(), 0)
+    return m.weight.detach()
+
+
+def _bias(m, n, device):
+    b = getattr(m, "bias", None)
+    if b is None:
+        return torch.zeros(n, dtype=torch.float32, device=device)
+    return b.detach().float()
+
+
+@dataclass
+class StackShape:
+    layers: int
+    kernel_size: int
+    R: int
+    G: int
+    S: int
+    C: int
+    Gi: int
+    O: int
+    Oin: int
+    dilations: list
+
+    @property
+    def H(self):
+        return self.G // 2
+
+    def dims(self) -> _lib.StackDims:
+        d = _lib.StackDims()
+        d.layers, d.kernel_size = self.layers, self.kernel_size
+        d.R, d.G, d.S, d.C, d.Gi, d.O, d.Oin = self.R, self.G, self.S, self.C, self.Gi, self.O, self.Oin
+        for i, v in enumerate(self.dilations):
+            d.dilation[i] = int(v)
+        return d
+
+
+def stack_shape(wn) -> StackShape:
+    l0 = wn.conv_layers[0]
+    conv = l0.conv
+    G, R, kw = conv.out_channels, conv.in_channels, conv.kernel_size[0]
+    S = l0.conv1x1_skip.out_channels
+    C = l0.conv1x1c.in_channels if getattr(l0, "conv1x1c", None) is not None else 0
+    Gi = l0.conv1x1g.in_channels if getattr(l0, "conv1x1g", None) is not None else 0
+    O = wn.last_conv_layers[3].out_channels
+    Oin = wn.first_conv.in_channels
+    dil = [f.conv.dilation[0] for f in wn.conv_layers]
+    if len(dil) > _lib.WAE_MAX_LAYERS:
+        raise ValueError(f"at most {_lib.WAE_MAX_LAYERS} layers supported")
+    return StackShape(len(dil), kw, R, G, S, C, Gi, O, Oin, dil)
+
+
+def params_fingerprint(wn) -> tuple:
+    """Changes whenever any parameter of the module is modified in place or replaced."""
+    return tuple((p.data_ptr(), p._version) for p in wn.parameters())
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+def _gather_layer_mats(wn, sh: StackShape):
+    """Per-layer folded fp32 matrices in natural layout."""
+    out = []
+    dev = next(wn.parameters()).device
+    for f in wn.conv_layers:
+        w = folded_weight(f.conv).float()                       # (G, R, kw)
+        wc = folded_weight(f.conv1x1c).float()[:, :, 0] if sh.C else None   # (G, C)
+        wg = folded_weight(f.conv1x1g).float()[:, :, 0] if sh.Gi else None  # (G, Gi)
+        wo = folded_weight(f.conv1x1_out).float()[:, :, 0]      # (R, H)
+        ws = folded_weight(f.conv1x1_skip).float()[:, :, 0]     # (S, H)
+        out.append(dict(w=w, wc=wc, wg=wg, wo=wo, ws=ws,
+                        b=_bias(f.conv, sh.G, dev), bo=_bias(f.conv1x1_out, sh.R, dev),
+                        bs=_bias(f.conv1x1_skip, sh.S, dev)))
+    return out
+
+
+def _w1_kmajor(m, sh: StackShape, cpad: int) -> torch.Tensor:
+    """(G, kw*R + cpad): taps oldest first (conv weight index j multiplies x[t-(kw-1-j)d], conv.py:56-61), then c."""
+    parts = [m["w"][:, :, j] for j in range(sh.kernel_size)]
+    if sh.C:
+        wc = m["wc"]
+        if cpad > sh.C:
+            wc = torch.nn.functional.pad(wc, (0, cpad - sh.C))
+        parts.append(wc)
+    return torch.cat(parts, dim=1).contiguous()
+
+
+class Packed:
+    """Holds the packed tensors (keeps them alive) and the ctypes struct pointing at them."""
+
+    def __init__(self):
+        self.t = {}
+        self.struct = None
+        self.shape: StackShape | None = None
+
+
+def pack_f32(wn) -> Packed:
+    sh = stack_shape(wn)
+    H = sh.H
+    if sh.G % 8 or sh.R % 16 or sh.S % 8:
+        raise _lib.WaeError(f"fp32 stack needs G%8==0, R%16==0, S%8==0 (got G={sh.G} R={sh.R} S={sh.S})")
+    mats = _gather_layer_mats(wn, sh)
+    dev = mats[0]["w"].device
+    # pair-permuted gate columns: col 8q+i (i<4) = tanh channel 4q+i, col 8q+4+i = sigmoid channel 4q+i
+    q = torch.arange(H // 4, device=dev).repeat_interleave(8)
+    i = torch.arange(8, device=dev).repeat(H // 4)
+    perm = torch.where(i < 4, 4 * q + i, H + 4 * q + (i - 4))
+    p = Packed()
+    p.shape = sh
+    t = p.t
+    t["w1"] = torch.stack([_w1_kmajor(m, sh, sh.C)[perm].t().contiguous() for m in mats])      # [L][K1][G]
+    t["b1"] = torch.stack([m["b"][perm] for m in mats]).contiguous()
+    t["wg"] = torch.stack([m["wg"][perm].t().contiguous() for m in mats]) if sh.Gi else None   # [L][Gi][G]
+    t["w2"] = torch.stack([torch.cat([m["wo"], m["ws"]], 0).t().contiguous() for m in mats])   # [L][H][R+S]
+    t["b2"] = torch.stack([torch.cat([m["bo"], m["bs"]]) for m in mats]).contiguous()
+    t["wf"] = folded_weight(wn.first_conv).float()[:, :, 0].t().contiguous()                   # [Oin][R]
+    t["bf"] = _bias(wn.first_conv, sh.R, dev).contiguous()
+    l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
+    t["w3"] = folded_weight(l1).float()[:, :, 0].t().contiguous()                              # [S][S]
+    t["b3"] = _bias(l1, sh.S, dev).contiguous()
+    Opad = _ru(sh.O, 8)
+    w4 = folded_weight(l3).float()[:, :, 0].t()                                                # [S][O]
+    t["w4"] = torch.nn.functional.pad(w4, (0, Opad - sh.O)).contiguous()
+    t["b4"] = torch.nn.functional.pad(_bias(l3, sh.O, dev), (0, Opad - sh.O)).contiguous()
+    s = _lib.StackF32()
+    s.d = sh.dims()
+    for name in ("wf", "bf", "w1", "b1", "wg", "w2", "b2", "w3", "b3", "w4", "b4"):
+        setattr(s, name, _lib.ptr(t[name]))
+    p.struct = s
+    return p
+
+
+def pack_bf16(wn) -> Packed:
+    sh = stack_shape(wn)
+    H = sh.H
+    mats = _gather_layer_mats(wn, sh)
+    dev = mats[0]["w"].device
+    Hp, Cp, Op = _ru(H, 64), _ru(sh.C, 64) if sh.C else 0, _ru(sh.O, 16)
+    bf = torch.bfloat16
+    p = Packed()
+    p.shape = sh
+    t = p.t
+    t["w1"] = torch.stack([_w1_kmajor(m, sh, Cp) for m in mats]).to(bf).contiguous()                              # [L][G][K1p]
+    t["wo"] = torch.stack([torch.nn.functional.pad(m["wo"], (0, Hp - H)) for m in mats]).to(bf).contiguous()     # [L][R][Hp]
+    t["ws"] = torch.stack([torch.nn.functional.pad(m["ws"], (0, Hp - H)) for m in mats]).to(bf).contiguous()     # [L][S][Hp]
+    l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
+    t["w3"] = folded_weight(l1).float()[:, :, 0].to(bf).contiguous()                                              # [S][S]
+    w4 = folded_weight(l3).float()[:, :, 0]                                                                       # [O][S]
+    t["w4"] = torch.nn.functional.pad(w4, (0, 0, 0, Op - sh.O)).to(bf).contiguous()                               # [Op][S]
+    t["b1"] = torch.stack([m["b"] for m in mats]).contiguous()
+    t["wg"] = torch.stack([m["wg"].t().contiguous() for m in mats]) if sh.Gi else None                            # [L][Gi][G]
+    t["bo"] = torch.stack([m["bo"] for m in mats]).contiguous()
+    t["bs_sum"] = torch.stack([m["bs"] for m in mats]).sum(0).contiguous()
+    t["b3"] = _bias(l1, sh.S, dev).contiguous()
+    t["b4"] = torch.nn.functional.pad(_bias(l3, sh.O, dev), (0, Op - sh.O)).contiguous()
+    t["wf"] = folded_weight(wn.first_conv).float()[:, :, 0].t().contiguous()
+    t["bf"] = _bias(wn.first_conv, sh.R, dev).contiguous()
+    s = _lib.StackBF16()
+    s.d = sh.dims()
+    for name in ("w1", "wo", "ws", "w3", "w4", "b1", "wg", "bo", "bs_sum", "b3", "b4", "wf", "bf"):
+        setattr(s, name, _lib.ptr(t[name]))
+    p.struct = s
+    return p
+
+
+def part(n: int, r: int, cs: int) -> int:
+    return (n * r) // cs
+
+
+def pack_ar(wn, cluster: int = 8, wtype: str = "bf16", utts_per_cluster: int = 2) -> Packed:
+    """Per-(stage, rank) row-sliced blobs for the cluster AR kernel (see include/wae_b200.h)."""
+    sh = stack_shape(wn)
+    H, L = sh.H, sh.layers
+    mats = _gather_layer_mats(wn, sh)
+    dev = mats[0]["w"].device
+    Hp, Cp = _ru(H, 64), _ru(sh.C, 64) if sh.C else 0
+    dt = torch.float32 if wtype == "fp32" else torch.bfloat16
+    esz = 4 if wtype == "fp32" else 2
+    l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
+    w3 = folded_weight(l1).float()[:, :, 0]
+    w4 = folded_weight(l3).float()[:, :, 0]
+    chunks, offs, off = [], [], 0
+
+    def add(mat: torch.Tensor):
+        nonlocal off
+        raw = mat.to(dt).contiguous().view(torch.uint8).flatten()
+        n = raw.numel()
+        pad = (-n) % 16
+        if pad:
+            raw = torch.cat([raw, torch.zeros(pad, dtype=torch.uint8, device=dev)])
+        offs.append(off)
+        chunks.append(raw)
+        off += n + pad
+
+    for m in mats:
+        w1 = _w1_kmajor(m, sh, Cp)                                           # (G, K1p)
+        for r in range(cluster):                                             # stage 2l
+            p0, p1 = part(H, r, cluster), part(H, r + 1, cluster)
+            rows = torch.stack([w1[p0:p1], w1[H + p0:H + p1]], dim=1).reshape(-1, w1.shape[1])  # a_p, b_p interleaved
+            add(rows)
+        wo = torch.nn.functional.pad(m["wo"], (0, Hp - H))
+        ws = torch.nn.functional.pad(m["ws"], (0, Hp - H))
+        for r in range(cluster):                                             # stage 2l+1
+            add(torch.cat([wo[part(sh.R, r, cluster):part(sh.R, r + 1, cluster)],
+                           ws[part(sh.S, r, cluster):part(sh.S, r + 1, cluster)]], 0))
+    for r in range(cluster):
+        add(w3[part(sh.S, r, cluster):part(sh.S, r + 1, cluster)])
+    for r in range(cluster):
+        add(w4[part(sh.O, r, cluster):part(sh.O, r + 1, cluster)])
+    p = Packed()
+    p.shape = sh
+    t = p.t
+    t["blob"] = torch.cat(chunks) if chunks else torch.zeros(16, dtype=torch.uint8, device=dev)
+    t["layer_off"] = torch.tensor(offs, dtype=torch.int64, device=dev)
+    t["b1"] = torch.stack([m["b"] for m in mats]).contiguous()
+    t["wg"] = torch.stack([m["wg"].t().contiguous() for m in mats]) if sh.Gi else None
+    t["bo"] = torch.stack([m["bo"] for m in mats]).contiguous()
+    t["bs"] = torch.stack([m["bs"] for m in mats]).contiguous()
+    t["b3"] = _bias(l1, sh.S, dev).contiguous()
+    t["b4"] = _bias(l3, sh.O, dev).contiguous()
+    t["wf"] = folded_weight(wn.first_conv).float()[:, :, 0].t().contiguous()
+    t["bf"] = _bias(wn.first_conv, sh.R, dev).contiguous()
+    s = _lib.ArWeights()
+    s.d = sh.dims()
+    s.wtype = 0 if wtype == "fp32" else 1
+    s.cluster = cluster
+    s.utts_per_cluster = utts_per_cluster
+    s.blob = _lib.ptr(t["blob"])
+    s.layer_off = _lib.ptr(t["layer_off"])
+    for name in ("b1", "wg", "bo", "bs", "b3", "b4", "wf", "bf"):
+        setattr(s, name, _lib.ptr(t[name]))
+    p.struct = s
+    assert esz * 0 == 0
+    return p
+
+
+class WorkspaceCache:
+    """Grow-only scratch buffer per device (the C ABI never allocates)."""
+
+    def __init__(self):
+        self.buf = None
+
+    def get(self, nbytes: int, device) -> torch.Tensor:
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != torch.device(device):
+            self.buf = None
+            self.buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        return self.buf

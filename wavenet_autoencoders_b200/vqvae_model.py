@@ -1,0 +1,58 @@
+"""Encoder -> VQ -> WaveNet composition with the reference's names (vqvae_model.py:9-84).
+
+The encoder is ordinary frame-rate convolution (1/640 of the sample rate, <2 % of the FLOPs) and stays
+in PyTorch; the VQ search and the WaveNet decoder are the B200 kernels of this package.
+"""
+import torch
+from torch import nn
+
+from .vector_quantization import VectorQuantize
+
+
+class ConvReLURes(nn.Module):
+    def __init__(self, dim_in, dim_out, kernel_size, stride=1):
+        super().__init__()
+        self.stride, self.dim_in, self.dim_out = stride, dim_in, dim_out
+        self.conv = nn.Conv1d(dim_in, dim_out, kernel_size, stride, padding=kernel_size // 2, bias=True)
+        self.relu = nn.ReLU()
+
+    def forward(self, x):
+        out = self.relu(self.conv(x))
+        if self.stride == 1 and self.dim_in == self.dim_out:
+            out = out + x   # the reference adds in place (vqvae_model.py:20), which modern autograd rejects
+        return out
+
+
+class Encoder(nn.Module):
+    def __init__(self, hid=768, c_in=39, c_out=64):
+        super().__init__()
+        spec = [(c_in, 3, 1), (hid, 3, 1), (hid, 5, 2), (hid, 5, 2), (hid, 3, 1), (hid, 3, 1)] + [(hid, 1, 1)] * 4
+        self.net = nn.Sequential(*[ConvReLURes(cin, hid, k, s) for cin, k, s in spec])
+        self.lin = nn.Linear(hid, c_out)
+
+    def forward(self, x):
+        out = self.net(x)
+        return self.lin(out.permute(0, 2, 1)).permute(0, 2, 1)
+
+
+class VQVAE(nn.Module):
+    def __init__(self, c_in=39, hid=64, K=256, wavenet=None, encoder_hid=768):
+        super().__init__()
+        self.wavenet = wavenet
+        self.encoder = Encoder(c_in=c_in, c_out=hid, hid=encoder_hid)
+        self.vq = VectorQuantize(K=K, D=hid)
+
+    def forward(self, x, c, g, softmax=False):
+        quant, vq_loss, perp = self.vq(self.encoder(c))
+        return self.wavenet(x, quant, g, softmax), vq_loss, perp
+
+    def incremental_forward(self, initial_input, c, g, T, softmax, quantize, tqdm, log_scale_min):
+        with torch.no_grad():
+            quant, _, _ = self.vq(self.encoder(c))
+            return self.wavenet.incremental_forward(initial_input, c=quant, g=g, T=T, softmax=softmax,
+                                                    quantize=quantize, tqdm=tqdm, log_scale_min=log_scale_min)
+
+    def encode(self, x):
+        with torch.no_grad():
+            quant, _, _ = self.vq(self.encoder(x))
+        return quant

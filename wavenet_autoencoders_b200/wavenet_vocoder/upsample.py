@@ -1,0 +1,78 @@
+"""Conditioning upsamplers with the reference's names and parameters (wavenet_vocoder/upsample.py).
+
+Inference runs each stage (nearest stretch by s + 1x(2s+1) smoothing conv, upsample.py:18-20,42) as one
+CUDA kernel (wae_upsample_stage); under autograd the same stage is expressed with torch ops.
+"""
+import numpy as np
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import _lib
+
+
+class Stretch2d(nn.Module):
+    def __init__(self, x_scale, y_scale, mode="nearest"):
+        super().__init__()
+        self.x_scale, self.y_scale, self.mode = x_scale, y_scale, mode
+
+    def forward(self, x):
+        return F.interpolate(x, scale_factor=(self.y_scale, self.x_scale), mode=self.mode)
+
+
+class UpsampleNetwork(nn.Module):
+    def __init__(self, upsample_scales, upsample_activation="none", upsample_activation_params={},
+                 mode="nearest", freq_axis_kernel_size=1, cin_pad=0, cin_channels=80):
+        super().__init__()
+        self.up_layers = nn.ModuleList()
+        self.indent = cin_pad * int(np.prod(upsample_scales))
+        self.scales = [int(s) for s in upsample_scales]
+        self.freq_axis_kernel_size = freq_axis_kernel_size
+        self.has_activation = upsample_activation != "none"
+        self.mode = mode
+        for scale in self.scales:
+            k_size = (freq_axis_kernel_size, scale * 2 + 1)
+            conv = nn.Conv2d(1, 1, kernel_size=k_size, padding=((freq_axis_kernel_size - 1) // 2, scale), bias=False)
+            conv.weight.data.fill_(1.0 / np.prod(k_size))
+            self.up_layers.append(Stretch2d(scale, 1, mode))
+            self.up_layers.append(nn.utils.weight_norm(conv))
+            if self.has_activation:
+                self.up_layers.append(getattr(nn, upsample_activation)(**upsample_activation_params))
+
+    def _kernel_ok(self, c):
+        return (c.is_cuda and not (torch.is_grad_enabled() and (c.requires_grad or any(p.requires_grad for p in self.parameters())))
+                and self.freq_axis_kernel_size == 1 and not self.has_activation and self.mode == "nearest")
+
+    def forward(self, c):
+        if self._kernel_ok(c):
+            from ..packing import folded_weight
+            B, C, T = c.shape
+            cur = c.contiguous().float()
+            convs = [m for m in self.up_layers if isinstance(m, nn.Conv2d)]
+            for s, conv in zip(self.scales, convs):
+                w = folded_weight(conv).float().reshape(-1).contiguous()
+                out = torch.empty(B, C, cur.shape[-1] * s, dtype=torch.float32, device=c.device)
+                _lib.check(_lib.lib().wae_upsample_stage(_lib.ptr(cur), B * C, cur.shape[-1], s, _lib.ptr(w),
+                                                         _lib.ptr(out), _lib.stream_ptr(c.device)), "wae_upsample_stage")
+                cur = out
+            c = cur
+        else:
+            c = c.unsqueeze(1)
+            for f in self.up_layers:
+                c = f(c)
+            c = c.squeeze(1)
+        if self.indent > 0:
+            c = c[:, :, self.indent:-self.indent]
+        return c
+
+
+class ConvInUpsampleNetwork(nn.Module):
+    def __init__(self, upsample_scales, upsample_activation="none", upsample_activation_params={},
+                 mode="nearest", freq_axis_kernel_size=1, cin_pad=0, cin_channels=80):
+        super().__init__()
+        self.conv_in = nn.Conv1d(cin_channels, cin_channels, kernel_size=2 * cin_pad + 1, bias=False)
+        self.upsample = UpsampleNetwork(upsample_scales, upsample_activation, upsample_activation_params,
+                                        mode, freq_axis_kernel_size, cin_pad=0, cin_channels=cin_channels)
+
+    def forward(self, c):
+        return self.upsample(self.conv_in(c))

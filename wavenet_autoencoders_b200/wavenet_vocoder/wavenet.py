@@ -1,0 +1,296 @@
+"""WaveNet decoder with the reference's module API (wavenet_vocoder/wavenet.py), backed by libwae_b200.
+
+Same constructor, sub-module names (hence ``state_dict`` keys), ``forward(x, c, g, softmax)``,
+``incremental_forward(...)``, ``clear_buffer``, ``make_generation_fast_``, ``receptive_field``.
+What differs is where the arithmetic runs:
+
+* ``forward`` (no autograd)        -> wae_stack_forward_f32 / wae_stack_forward_bf16: one fused kernel per layer
+* ``incremental_forward``          -> wae_ar_generate: ONE persistent cluster kernel for all T steps
+* ``forward`` while training       -> torch autograd ops (backward kernels are the next row)
+
+``precision`` ("fp32" | "bf16", default from $WAE_B200_PRECISION or "fp32") selects the fp32-faithful
+CUDA-core kernels (reference parity to ~1e-5) or the tcgen05 tensor-core kernels.
+There is no CPU fallback: inference on a CPU tensor, or without the built library, raises.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from .. import _lib, packing
+from . import upsample
+from .modules import Conv1d1x1, Embedding, ResidualConv1dGLU
+
+
+def _expand_global_features(B, T, g, bct=True):
+    """(B,C) or (B,C,1) -> (B,C,T) / (B,T,C) (wavenet.py:19-39). Only the autograd path needs the expansion."""
+    if g is None:
+        return None
+    g = g.unsqueeze(-1) if g.dim() == 2 else g
+    g = g.expand(B, -1, T)
+    return g.contiguous() if bct else g.transpose(1, 2).contiguous()
+
+
+def receptive_field_size(total_layers, num_cycles, kernel_size, dilation=lambda x: 2 ** x):
+    assert total_layers % num_cycles == 0
+    per = total_layers // num_cycles
+    return (kernel_size - 1) * sum(dilation(i % per) for i in range(total_layers)) + 1
+
+
+class WaveNet(nn.Module):
+    def __init__(self, out_channels=256, layers=20, stacks=2, residual_channels=512, gate_channels=512,
+                 skip_out_channels=512, kernel_size=3, dropout=1 - 0.95, cin_channels=-1, gin_channels=-1,
+                 n_speakers=None, upsample_conditional_features=False, upsample_net="ConvInUpsampleNetwork",
+                 upsample_params={"upsample_scales": [4, 4, 4, 4]}, scalar_input=False,
+                 use_speaker_embedding=False, output_distribution="Logistic", cin_pad=0):
+        super().__init__()
+        self.scalar_input = scalar_input
+        self.out_channels = out_channels
+        self.cin_channels = cin_channels
+        self.output_distribution = output_distribution
+        assert layers % stacks == 0
+        layers_per_stack = layers // stacks
+        self.first_conv = Conv1d1x1(1 if scalar_input else out_channels, residual_channels)
+        self.conv_layers = nn.ModuleList([
+            ResidualConv1dGLU(residual_channels, gate_channels, kernel_size=kernel_size,
+                              skip_out_channels=skip_out_channels, bias=True,
+                              dilation=2 ** (layer % layers_per_stack), dropout=dropout,
+                              cin_channels=cin_channels, gin_channels=gin_channels)
+            for layer in range(layers)])
+        self.last_conv_layers = nn.ModuleList([
+            nn.ReLU(inplace=True), Conv1d1x1(skip_out_channels, skip_out_channels),
+            nn.ReLU(inplace=True), Conv1d1x1(skip_out_channels, out_channels)])
+        if gin_channels > 0 and use_speaker_embedding:
+            assert n_speakers is not None
+            self.embed_speakers = Embedding(n_speakers, gin_channels, padding_idx=None, std=0.1)
+        else:
+            self.embed_speakers = None
+        if upsample_conditional_features:
+            self.upsample_net = getattr(upsample, upsample_net)(**upsample_params)
+        else:
+            self.upsample_net = None
+        self.receptive_field = receptive_field_size(layers, stacks, kernel_size)
+
+        # ---- B200 execution knobs (not part of the reference API; not in state_dict) ----
+        self.precision = os.environ.get("WAE_B200_PRECISION", "fp32")
+        self.ar_cluster = None            # None -> 16 CTAs for fp32 weights, 8 for bf16
+        self.ar_utts_per_cluster = 2
+        self.last_sampled_indices = None  # (B,T) int32 of the last categorical incremental_forward
+        self._packs = {}
+        self._ws = packing.WorkspaceCache()
+
+    # ------------------------------------------------------------------ reference API
+    def has_speaker_embedding(self):
+        return self.embed_speakers is not None
+
+    def local_conditioning_enabled(self):
+        return self.cin_channels > 0
+
+    def clear_buffer(self):
+        """The reference drops its per-layer shift buffers here (wavenet.py:348-356); the fused AR kernel keeps its
+        dilation ring in a scratch workspace that is re-zeroed by every call, so there is nothing to drop."""
+        self.first_conv.clear_buffer()
+        for f in self.conv_layers:
+            f.clear_buffer()
+        for f in self.last_conv_layers:
+            if hasattr(f, "clear_buffer"):
+                f.clear_buffer()
+
+    def make_generation_fast_(self):
+        def remove_weight_norm(m):
+            try:
+                nn.utils.remove_weight_norm(m)
+            except ValueError:
+                return
+        self.apply(remove_weight_norm)
+        self._packs.clear()
+
+    # ------------------------------------------------------------------ helpers
+    def _speaker_vectors(self, g, B):
+        """g: speaker ids (B,)/(B,1) with embed_speakers, else float (B,Gi) / (B,Gi,1)  ->  (B,Gi) fp32 or None."""
+        if g is None:
+            return None
+        if self.embed_speakers is not None:
+            g = self.embed_speakers(g.view(B, -1))      # (B,1,Gi)   (wavenet.py:186-191)
+            g = g.transpose(1, 2)
+        if g.dim() == 3:
+            if g.size(-1) != 1:
+                raise _lib.WaeError("time-varying global conditioning is not supported (g must be (B,Gi) or (B,Gi,1))")
+            g = g[:, :, 0]
+        return g
+
+    def _pack(self, kind, **kw):
+        key = (kind,) + tuple(sorted(kw.items()))
+        fp = packing.params_fingerprint(self)
+        hit = self._packs.get(key)
+        if hit is None or hit[0] != fp:
+            fn = {"f32": packing.pack_f32, "bf16": packing.pack_bf16, "ar": packing.pack_ar}[kind]
+            with torch.no_grad():
+                hit = (fp, fn(self, **kw))
+            self._packs[key] = hit
+        return hit[1]
+
+    def _require_cuda(self, t, what):
+        if not t.is_cuda:
+            raise _lib.WaeError(f"{what}: tensor is on {t.device}; wavenet_autoencoders_b200 runs on CUDA sm_100 only "
+                                "(no CPU fallback)")
+
+    # ------------------------------------------------------------------ teacher-forced forward
+    def forward(self, x, c=None, g=None, softmax=False):
+        """x (B,O,T) one-hot / (B,1,T) scalar; c (B,C,Tc); g ids or (B,Gi[,1])  ->  (B,O,T) (wavenet.py:164-216)."""
+        B, _, T = x.size()
+        gvec = self._speaker_vectors(g, B)
+        if c is not None and self.upsample_net is not None:
+            c = self.upsample_net(c)
+            if c.size(-1) != x.size(-1):
+                print(f"c {c.size() } x {x.size()}")
+                raise Exception
+        if self.training and torch.is_grad_enabled():
+            return self._forward_autograd(x, c, gvec, softmax)
+        with torch.no_grad():
+            out = self.stack_forward(x, c, gvec)
+        return F.softmax(out, dim=1) if softmax else out
+
+    def stack_forward(self, x, c_up, gvec, precision=None):
+        """The hot path proper: first_conv + residual stack + head on already-upsampled conditioning."""
+        self._require_cuda(x, "WaveNet.forward")
+        precision = precision or self.precision
+        B, _, T = x.shape
+        x = x.detach().float().contiguous()
+        c_up = None if c_up is None else c_up.detach().float().contiguous()
+        gvec = None if gvec is None else gvec.detach().float().contiguous()
+        logits = torch.empty(B, self.out_channels, T, dtype=torch.float32, device=x.device)
+        L = _lib.lib()
+        st = _lib.stream_ptr(x.device)
+        if precision == "fp32":
+            pk = self._pack("f32")
+            n = L.wae_stack_workspace_f32(pk.struct.d, B, T)
+            ws = self._ws.get(n, x.device)
+            _lib.check(L.wae_stack_forward_f32(pk.struct, _lib.ptr(x), _lib.ptr(c_up), _lib.ptr(gvec), B, T,
+                                               _lib.ptr(logits), _lib.ptr(ws), ws.numel(), st), "wae_stack_forward_f32")
+        elif precision == "bf16":
+            pk = self._pack("bf16")
+            n = L.wae_stack_workspace_bf16(pk.struct.d, B, T)
+            ws = self._ws.get(n, x.device)
+            _lib.check(L.wae_stack_forward_bf16(pk.struct, _lib.ptr(x), _lib.ptr(c_up), _lib.ptr(gvec), B, T,
+                                                _lib.ptr(logits), _lib.ptr(ws), ws.numel(), st), "wae_stack_forward_bf16")
+        else:
+            raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
+        return logits
+
+    def _forward_autograd(self, x, c, gvec, softmax):
+        B, _, T = x.size()
+        g_bct = _expand_global_features(B, T, gvec, bct=True)
+        x = self.first_conv(x)
+        skips = 0
+        for f in self.conv_layers:
+            x, h = f(x, c, g_bct)
+            skips = skips + h
+        x = skips * math.sqrt(1.0 / len(self.conv_layers))
+        for f in self.last_conv_layers:
+            x = f(x)
+        return F.softmax(x, dim=1) if softmax else x
+
+    # ------------------------------------------------------------------ autoregressive synthesis
+    def incremental_forward(self, initial_input=None, c=None, g=None, T=100, test_inputs=None,
+                            tqdm=lambda x: x, softmax=True, quantize=True, log_scale_min=-50.0,
+                            uniforms=None, generator=None, return_indices=False):
+        """wavenet.py:218-346.  Extra (additive) keywords: ``uniforms`` -- the (T,B[,n]) random draws the fused
+        sampler consumes (default: torch.rand with ``generator``); ``return_indices`` -- return the (B,T) int32 sampled
+        classes instead of materialising the (B,O,T) one-hot tensor."""
+        if self.training:
+            raise RuntimeError("incremental_forward only supports eval mode")
+        self.clear_buffer()
+        dev = next(self.parameters()).device
+        Oin = 1 if self.scalar_input else self.out_channels
+        B = 1
+        if test_inputs is not None:
+            if test_inputs.size(1) == Oin:          # (B,C,T) -> (B,T,C)   (wavenet.py:249-255)
+                test_inputs = test_inputs.transpose(1, 2)
+            test_inputs = test_inputs.contiguous()
+            B = test_inputs.size(0)
+            T = test_inputs.size(1) if T is None else max(T, test_inputs.size(1))
+        elif c is not None:
+            B = c.shape[0]          # the reference only learns B here, after it already used B=1 for g
+        elif initial_input is not None:
+            B = initial_input.size(0)
+        T = int(T)
+        with torch.no_grad():
+            gvec = self._speaker_vectors(g, B)
+            c_btc = None
+            if c is not None:
+                if self.upsample_net is not None:
+                    c = self.upsample_net(c)
+                    assert c.size(-1) == T, f"c {c.size()} != T {T}"
+                if c.size(-1) == T:
+                    c = c.transpose(1, 2)
+                c_btc = c.float().contiguous()
+                self._require_cuda(c_btc, "WaveNet.incremental_forward")
+            if initial_input is None:
+                init = torch.zeros(B, Oin, device=dev)
+                if not self.scalar_input:
+                    init[:, 127] = 1
+            else:
+                init = initial_input
+                if init.dim() == 3:
+                    if init.size(1) == self.out_channels:   # (B,C,1) -> (B,1,C)   (wavenet.py:292-294)
+                        init = init.transpose(1, 2)
+                    init = init[:, -1, :]
+                init = init.to(dev).float().contiguous()
+            if dev.type != "cuda":
+                raise _lib.WaeError("WaveNet.incremental_forward: parameters are not on a CUDA device (no CPU fallback)")
+
+            if self.scalar_input:
+                mode = {"Logistic": _lib.AR_SAMPLE_MOL, "Normal": _lib.AR_SAMPLE_GAUSS}[self.output_distribution]
+                nmix = 1 if self.out_channels == 2 else self.out_channels // 3
+                if uniforms is None:
+                    uniforms = torch.rand(T, B, nmix + 1, device=dev, generator=generator)
+                    if mode == _lib.AR_SAMPLE_GAUSS:
+                        uniforms[:, :, nmix] = torch.randn(T, B, device=dev, generator=generator)
+            elif quantize:
+                if not softmax:
+                    raise ValueError("quantize=True needs softmax=True (sampling from unnormalised logits is undefined)")
+                mode = _lib.AR_SAMPLE_CATEGORICAL
+                if uniforms is None:
+                    uniforms = torch.rand(T, B, device=dev, generator=generator)
+            else:
+                mode = _lib.AR_SAMPLE_NONE
+            if uniforms is not None:
+                uniforms = uniforms.to(dev).float().contiguous()
+
+            wtype = "fp32" if self.precision == "fp32" else "bf16"
+            cluster = self.ar_cluster or (16 if wtype == "fp32" else 8)
+            pk = self._pack("ar", cluster=cluster, wtype=wtype, utts_per_cluster=self.ar_utts_per_cluster)
+            L = _lib.lib()
+            n = L.wae_ar_workspace(pk.struct, B, T)
+            ws = self._ws.get(n, dev)
+            forced = None if test_inputs is None else test_inputs.to(dev).float().contiguous()
+            Tf = 0 if forced is None else forced.size(1)
+            out_idx = torch.empty(B, T, dtype=torch.int32, device=dev) if mode == _lib.AR_SAMPLE_CATEGORICAL else None
+            if mode == _lib.AR_SAMPLE_NONE:
+                out_dense = torch.empty(B, T, self.out_channels, dtype=torch.float32, device=dev)
+            elif mode in (_lib.AR_SAMPLE_MOL, _lib.AR_SAMPLE_GAUSS):
+                out_dense = torch.empty(B, T, dtype=torch.float32, device=dev)
+            else:
+                out_dense = None
+            _lib.check(L.wae_ar_generate(pk.struct, _lib.ptr(c_btc), _lib.ptr(None if gvec is None else gvec.float().contiguous()),
+                                         _lib.ptr(init), _lib.ptr(forced), Tf, _lib.ptr(uniforms), B, T, mode,
+                                         1 if softmax else 0, _lib.ptr(out_idx), _lib.ptr(out_dense),
+                                         _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "wae_ar_generate")
+            if mode == _lib.AR_SAMPLE_CATEGORICAL:
+                self.last_sampled_indices = out_idx
+                if return_indices:
+                    outputs = out_idx
+                else:
+                    outputs = torch.zeros(B, self.out_channels, T, dtype=torch.float32, device=dev)
+                    outputs.scatter_(1, out_idx.long().unsqueeze(1), 1.0)
+            elif mode == _lib.AR_SAMPLE_NONE:
+                outputs = out_dense.transpose(1, 2).contiguous()
+            else:
+                outputs = out_dense.unsqueeze(1)
+        self.clear_buffer()
+        return outputs
