@@ -1,0 +1,152 @@
+"""CPU tests of the host side: the C-ABI library loads and exports what include/wae_b200.h declares, the product
+path fails loudly without a GPU (no fallback), state_dict layout matches the reference, weight packing is right."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, build_model, load_golden, rel_err
+from oracle import wavenet_oracle as wo
+from wavenet_autoencoders_b200 import _lib, packing, testing as T
+from wavenet_autoencoders_b200 import vector_quantization as vqm
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "wae_b200.h")).read()
+    declared = set(re.findall(r"\b(wae_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no prototypes parsed"
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/wae_b200.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.wae_version() >= 100
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    lib = _lib.lib()
+    assert lib.wae_device_check(0) == -2 and b"no CPU fallback" in lib.wae_last_error()
+    m = build_model("tiny", 1)
+    x, _, c, g = T.synth_inputs(T.CONFIGS["tiny"], 1, 32, 0)
+    with pytest.raises(_lib.WaeError):
+        with torch.no_grad():
+            m(x, c, g)
+    with pytest.raises(_lib.WaeError):
+        m.incremental_forward(initial_input=x[:, :, :1], c=c, g=g, T=32)
+    with pytest.raises(_lib.WaeError):
+        vqm.VectorQuantize(8, 4)(torch.zeros(1, 4, 3))
+    with pytest.raises(_lib.WaeError):
+        vqm.SlicedVectorQuantize(8, 4).encode_indices(torch.zeros(1, 4, 3))
+
+
+def test_state_dict_layout_matches_reference():
+    """Key names/shapes of SURVEY.md 3.4 (302 keys, 7,555,218 parameters at hps/vqwae.json)."""
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet, receptive_field_size
+    wn = WaveNet(**T.VQWAE)
+    m = VQVAE(c_in=39, hid=64, wavenet=wn, encoder_hid=256)
+    sd = m.state_dict()
+    assert len(sd) == 302
+    assert sum(p.numel() for p in m.parameters()) == 7555218
+    assert sum(p.numel() for p in wn.parameters()) == 5982546
+    for k, shape in {"wavenet.conv_layers.3.conv.weight_v": (256, 256, 3), "wavenet.conv_layers.3.conv.weight_g": (256, 1, 1),
+                     "wavenet.conv_layers.19.conv1x1c.weight_v": (256, 64, 1), "wavenet.conv_layers.0.conv1x1g.weight_g": (256, 1, 1),
+                     "wavenet.conv_layers.7.conv1x1_out.bias": (256,), "wavenet.conv_layers.7.conv1x1_skip.weight_v": (256, 128, 1),
+                     "wavenet.first_conv.weight_v": (256, 256, 1), "wavenet.last_conv_layers.3.bias": (256,),
+                     "wavenet.embed_speakers.weight": (153, 32), "wavenet.upsample_net.conv_in.weight": (64, 64, 1),
+                     "wavenet.upsample_net.upsample.up_layers.5.weight_v": (1, 1, 1, 17),
+                     "encoder.net.2.conv.weight": (256, 256, 5), "encoder.lin.weight": (64, 256), "vq.embedding.weight": (256, 64)}.items():
+        assert tuple(sd[k].shape) == shape, k
+    assert wn.receptive_field == 4093 == receptive_field_size(20, 2, 3)
+    assert [f.conv.dilation[0] for f in wn.conv_layers] == [2 ** (i % 10) for i in range(20)]
+    assert wn.has_speaker_embedding() and wn.local_conditioning_enabled()
+    wn.make_generation_fast_()
+    assert "conv_layers.0.conv.weight" in wn.state_dict() and "conv_layers.0.conv.weight_g" not in wn.state_dict()
+    with pytest.raises(AssertionError):
+        WaveNet(layers=5, stacks=2)
+
+
+def test_api_errors_match_reference():
+    m = build_model("tiny", 1)
+    x, _, c, g = T.synth_inputs(T.CONFIGS["tiny"], 1, 32, 0)
+    with pytest.raises(Exception):                      # upsampled c length != T (wavenet.py:196-200)
+        m(x[:, :, :31], c, g)
+    m.train()
+    with pytest.raises(RuntimeError):                   # conv.py:19-20
+        m.incremental_forward(c=c, g=g, T=32)
+
+
+def test_training_path_is_differentiable_and_matches_oracle():
+    g = load_golden("wavenet_tiny")
+    cfg = T.CONFIGS["tiny"]
+    m = build_model("tiny", int(g["seed"])).train()
+    x, _, c, spk = T.synth_inputs(cfg, int(g["B"]), int(g["T"]), int(g["in_seed"]))
+    y = m(x, c, spk)
+    assert rel_err(y.detach().numpy(), g["logits"]) < 2e-5
+    y.square().mean().backward()
+    grads = {n: p.grad for n, p in m.named_parameters()}
+    # the last layer's residual 1x1 never receives a gradient
+    assert grads["conv_layers.3.conv1x1_out.weight_v"] is None or float(grads["conv_layers.3.conv1x1_out.weight_v"].abs().sum()) == 0
+    assert float(grads["conv_layers.0.conv.weight_v"].abs().sum()) > 0
+
+
+@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_k2", "vqwae", "inwae"])
+def test_packing_layouts(cfg_name):
+    cfg = T.CONFIGS[cfg_name]
+    m = build_model(cfg_name, 3)
+    sd = {k: v.numpy() for k, v in m.state_dict().items()}
+    p = wo.extract_params(sd, cfg["layers"], cfg["stacks"])
+    sh = packing.stack_shape(m)
+    assert (sh.layers, sh.kernel_size, sh.R, sh.G, sh.S, sh.C, sh.Gi, sh.O) == (
+        cfg["layers"], cfg["kernel_size"], cfg["residual_channels"], cfg["gate_channels"], cfg["skip_out_channels"],
+        cfg["cin_channels"], cfg["gin_channels"], cfg["out_channels"])
+    H, L, kw, R = sh.H, sh.layers, sh.kernel_size, sh.R
+    lay = p["layers"][L - 1]
+    # fp32 pack: [K1][G] with pair-permuted columns
+    pf = packing.pack_f32(m)
+    w1 = pf.t["w1"][L - 1].numpy()
+    assert w1.shape == (kw * R + sh.C, sh.G)
+    q, i = 5, 2
+    np.testing.assert_allclose(w1[1 * R + 7, 8 * q + i], lay["w"][4 * q + i, 7, 1], rtol=1e-6)           # tanh ch, tap 1
+    np.testing.assert_allclose(w1[kw * R + 3, 8 * q + 4 + i], lay["wc"][H + 4 * q + i, 3], rtol=1e-6)   # sigmoid ch, cond row
+    np.testing.assert_allclose(pf.t["w2"][0].numpy()[9, R + 11], p["layers"][0]["ws"][11, 9], rtol=1e-6)
+    # bf16 pack: K-major [G][K1p]
+    pb = packing.pack_bf16(m)
+    w1b = pb.t["w1"][L - 1].float().numpy()
+    assert w1b.shape[1] % 64 == 0 and w1b.shape[0] == sh.G
+    np.testing.assert_allclose(w1b[H + 3, 2 * R + 5] if kw == 3 else w1b[H + 3, 1 * R + 5], lay["w"][H + 3, 5, kw - 1], rtol=1e-2)
+    assert float(np.abs(w1b[:, kw * R + sh.C:]).sum()) == 0                                                # K padding is zero
+    np.testing.assert_allclose(pb.t["bs_sum"].numpy(), sum(l["bs"] for l in p["layers"]), rtol=1e-5, atol=1e-6)
+    # AR pack: per-(stage, rank) row slices
+    for cs, wt in ((8, "fp32"), (16, "bf16")):
+        pa = packing.pack_ar(m, cluster=cs, wtype=wt)
+        offs = pa.t["layer_off"].numpy().reshape(2 * L + 2, cs)
+        assert (offs % 16 == 0).all() and (np.diff(offs.reshape(-1)) >= 0).all()
+        dt = np.float32 if wt == "fp32" else None
+        r = cs - 1
+        p0, p1 = packing.part(H, r, cs), packing.part(H, r + 1, cs)
+        K1p = kw * R + (-(-sh.C // 64) * 64 if sh.C else 0)
+        blob = pa.t["blob"]
+        n = 2 * (p1 - p0) * K1p
+        raw = blob[offs[2 * (L - 1), r]: offs[2 * (L - 1), r] + n * (4 if wt == "fp32" else 2)]
+        rows = (raw.view(torch.float32) if wt == "fp32" else raw.view(torch.bfloat16).float()).numpy().reshape(-1, K1p)
+        np.testing.assert_allclose(rows[0, :R], lay["w"][p0, :, 0], rtol=1e-2)            # tanh row of first pair, oldest tap
+        np.testing.assert_allclose(rows[1, :R], lay["w"][H + p0, :, 0], rtol=1e-2)        # its sigmoid partner
+    # cache invalidation: an in-place parameter update changes the fingerprint
+    fp = packing.params_fingerprint(m)
+    with torch.no_grad():
+        next(m.parameters()).add_(1.0)
+    assert packing.params_fingerprint(m) != fp
+
+
+def test_vq_module_api():
+    for cls, names in ((vqm.VectorQuantize, {"embedding.weight"}), (vqm.SlicedVectorQuantize, {"embedding1.weight", "embedding2.weight"}),
+                       (vqm.VectorQuantizeEMA, {"embedding.weight", "ema_cluster_size", "ema_w"}),
+                       (vqm.SlicedVectorQuantizeEMA, {"embedding1.weight", "embedding2.weight", "ema_cluster_size1", "ema_w1",
+                                                      "ema_cluster_size2", "ema_w2"})):
+        m = cls(16, 8)
+        assert set(m.state_dict()) == names
+    m = vqm.SlicedVectorQuantize(16, 8, K1=4)
+    assert m.embedding2.weight.shape == (4, 4) and float(m.embedding1.weight.abs().max()) <= 1 / 16

@@ -782,8 +782,8 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
                 "wae_stack_forward_bf16: this build supports R,S in {64,128,192,256}, G%%32==0, G<=256, O<=256 "
                 "(R=%d G=%d S=%d O=%d); use the fp32 stack for other shapes", d.R, d.G, d.S, d.O);
     WAE_REQUIRE((d.C == 0) == (c == nullptr), "wae_stack_forward_bf16: c must be given iff C>0");
-    if ((reinterpret_cast<uintptr_t>(workspace) & 1023) != 0)
-        return wae::set_error(WAE_ERR_ALIGN, "wae_stack_forward_bf16: workspace must be 1024-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
+        return wae::set_error(WAE_ERR_ALIGN, "wae_stack_forward_bf16: workspace must be 256-byte aligned");
     Bf16Workspace ws = carve(d, B, T, workspace);
     if (workspace_bytes < ws.total)
         return wae::set_error(WAE_ERR_WORKSPACE, "wae_stack_forward_bf16: workspace %zu < %zu", workspace_bytes, ws.total);
