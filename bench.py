@@ -1,0 +1,362 @@
+"""bench.py -- WaveNet-decoder samples/s (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of the workload BASELINE.json quotes the metric on
+(configs[1]): VQ-WAE (hps/vqwae.json) encoder -> VQ -> WaveNet decoder teacher-forced forward, 16 utterances x 1 s
+of synthetic 16 kHz audio per GPU, with synthetic MFCC conditioning and random-init weights.
+
+  value     device-timed samples/s, inputs resident in HBM, tcgen05 bf16 kernels (weak scaling: 16 utt per GPU)
+  e2e       the same through the public module API from pinned HOST buffers: H2D of the mu-law class indices, MFCCs
+            and speaker ids, on-device one-hot, forward, teacher-forced NLL, D2H of the loss -- all inside the timing
+  roofline  the residual-layer kernel (layer_bf16_kernel): algorithmic FLOPs / CUDA-event time vs the measured bf16 peak
+  cpu_baseline   oracle/torch_port.py (the reference's ATen calls, folded weights) on the host cores, bounded sample
+  extras    fp32-faithful stack, autoregressive synthesis (config 4 shape, truncated T), VQ search throughput
+
+--impl reference times the CPU port alone (the reference is pure Python/PyTorch and /root/reference does not exist
+on the GPU box; see DESIGN.md "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "WaveNet-decoder samples/s (teacher-forced forward)"
+UNIT = "samples/s"
+B_PER_GPU, T_SAMPLES, FRAMES = 16, 16000, 100          # configs[1]: 16 x 1 s; 100 MFCC frames -> 25 latents -> 16000
+FLOP_PER_SAMPLE_LAYER = 557056                         # 2kRG + 2CG + 2HR + 2HS at hps/vqwae.json
+FLOP_PER_SAMPLE_TOTAL = 11403264                       # 20 layers + head (first conv on one-hot input = gather)
+
+
+def workload_config(world):
+    return {"workload": "VQ-WAE hps/vqwae.json encoder->VQ->WaveNet decoder teacher-forced forward (BASELINE configs[1])",
+            "batch_per_gpu": B_PER_GPU, "samples_per_utt": T_SAMPLES, "global_batch": world * B_PER_GPU,
+            "parallelism": f"utterance-sharded x{world}, no data-path collective",
+            "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
+            "weights": "synthetic seeded (testing.synth_state_dict)"}
+
+
+def _peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md: ~1.4 PF sustained, 6.65 TB/s)"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc, self.path = None, f"/tmp/wae_clocks_{os.getpid()}.csv"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [s for s in sm if s > 0]
+            out = {"sm_mhz": float(np.median(busy[len(busy) // 4:] or busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons)}
+        return out
+
+
+def build_vqvae(device):
+    from wavenet_autoencoders_b200 import testing as T
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    torch.manual_seed(0)
+    wn = WaveNet(**T.VQWAE)
+    m = VQVAE(c_in=39, hid=64, K=256, wavenet=wn, encoder_hid=256).eval()     # vqwae_train.py:946 with hps/vqwae.json
+    m.load_state_dict(T.synth_state_dict(m, 1))
+    return m.to(device)
+
+
+def synth_batch(B, seed):
+    rs = np.random.RandomState(seed)
+    idx = torch.tensor(rs.randint(0, 256, size=(B, T_SAMPLES)), dtype=torch.long)
+    mfcc = torch.tensor(rs.normal(size=(B, 39, FRAMES)), dtype=torch.float32)
+    g = torch.tensor(rs.randint(0, 153, size=(B, 1)), dtype=torch.long)
+    return idx, mfcc, g
+
+
+def cpu_port_setup():
+    """Decoder of the same model on the host cores through oracle/torch_port.py (kind "port")."""
+    from oracle import torch_port
+    from oracle import wavenet_oracle as wo
+    from wavenet_autoencoders_b200 import testing as T
+    m = build_vqvae("cpu")
+    sd = {k[len("wavenet."):]: v.numpy() for k, v in m.state_dict().items() if k.startswith("wavenet.")}
+    p = wo.extract_params(sd, T.VQWAE["layers"], T.VQWAE["stacks"])
+    tp = torch_port.params_from_numpy(p)
+    idx, mfcc, g = synth_batch(1, 100)
+    x = torch.nn.functional.one_hot(idx, 256).float().transpose(1, 2).contiguous()
+    with torch.no_grad():
+        quant = torch.randn(1, 64, FRAMES // 4)
+        c_up = torch_port.upsample(tp, quant)
+        gv = torch.tensor(wo.speaker_vectors(p, g.numpy()))
+
+    def step():
+        with torch.no_grad():
+            return torch_port.stack_forward(tp, x, c_up, gv)
+    return step
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_port_setup()
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = args.steps * T_SAMPLES / dt
+    sample = f"decoder teacher-forced forward, B=1 x T={T_SAMPLES} per step (1/16 of the per-GPU batch), fp32, torch {torch.__version__} CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--ar-steps", type=int, default=2400, help="AR extra: samples per utterance (config 4 uses 48000)")
+    ap.add_argument("--no-extras", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback); use --impl reference for the CPU port")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from wavenet_autoencoders_b200 import _lib
+    L = _lib.lib()
+    model = build_vqvae(dev)
+    model.wavenet.precision = "bf16"
+    B = B_PER_GPU                                               # weak scaling: every rank runs its own 16 utterances
+    idx_h, mfcc_h, g_h = synth_batch(B, 1000 + rank)
+    idx_p, mfcc_p, g_p = idx_h.pin_memory(), mfcc_h.pin_memory(), g_h.pin_memory()
+    idx, mfcc, g = idx_p.to(dev), mfcc_p.to(dev), g_p.to(dev)
+    x = torch.nn.functional.one_hot(idx, 256).float().transpose(1, 2).contiguous()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_device():
+        with torch.no_grad():
+            return model(x, mfcc, g)[0]
+
+    def step_e2e():
+        with torch.no_grad():
+            i_d = idx_p.to(dev, non_blocking=True)
+            m_d = mfcc_p.to(dev, non_blocking=True)
+            g_d = g_p.to(dev, non_blocking=True)
+            xo = torch.nn.functional.one_hot(i_d, 256).float().transpose(1, 2).contiguous()
+            y = model(xo, m_d, g_d)[0]
+            loss = torch.nn.functional.cross_entropy(y[:, :, :-1], i_d[:, 1:])       # teacher-forced NLL (vqwae_train.py:760-766)
+            return float(loss.item())                                                # D2H of the step's result
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    clocks = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    ms = timed(step_device, args.steps, args.warmup)
+    launches = (_lib.launch_count() - n0) * args.steps // (args.steps + args.warmup)
+    clk = clocks.stop() if clocks else None
+    value = world * B * T_SAMPLES * args.steps / (ms * 1e-3)
+
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
+    e2e_value = world * B * T_SAMPLES * args.steps / (ms_e2e * 1e-3)
+    h2d = idx_p.numel() * 8 + mfcc_p.numel() * 4 + g_p.numel() * 8
+
+    # ---- roofline of the dominant kernel, measured live with CUDA events around each launch ----
+    import ctypes
+    L.wae_profile_enable(1)
+    for _ in range(3):
+        step_device()
+    torch.cuda.synchronize()
+    ms_kind = (ctypes.c_float * 4)()
+    n_kind = (ctypes.c_int32 * 4)()
+    L.wae_profile_read(ms_kind, n_kind, 4)      # discard warm-up
+    prof_steps = max(3, min(args.steps, 10))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(prof_steps):
+        step_device()
+    e1.record()
+    torch.cuda.synchronize()
+    L.wae_profile_read(ms_kind, n_kind, 4)
+    L.wae_profile_enable(0)
+    prof_total = e0.elapsed_time(e1)
+    layer_launches = max(int(n_kind[1]), 1)
+    layer_ms = float(ms_kind[1]) / layer_launches
+    n_layers = 20
+    flops_per_launch = B * T_SAMPLES * (FLOP_PER_SAMPLE_LAYER - 2 * 128 * 256 / n_layers)   # last layer has no residual 1x1
+    peak_tf, peak_hbm, peak_src = _peaks()
+    achieved = flops_per_launch / (layer_ms * 1e-3) / 1e12
+    roofline = {"kernel": "layer_bf16_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "avg_launch_ms": layer_ms, "share_of_step": float(ms_kind[1]) / prof_total,
+                "head_share_of_step": float(ms_kind[2]) / prof_total, "prep_share_of_step": float(ms_kind[0]) / prof_total,
+                "step_frac_of_peak": value / world * FLOP_PER_SAMPLE_TOTAL / 1e12 / peak_tf}
+    try:
+        roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")))["dram_bytes_per_launch"]
+    except Exception:
+        pass
+
+    extras = {}
+    if not args.no_extras:
+        # fp32-faithful stack (the parity mode of configs[1])
+        model.wavenet.precision = "fp32"
+        ms32 = timed(step_device, max(2, args.steps // 5), 1)
+        extras["fp32_stack_samples_per_s"] = world * B * T_SAMPLES * max(2, args.steps // 5) / (ms32 * 1e-3)
+        # autoregressive synthesis, configs[3] shape per GPU (32 utterances), truncated to --ar-steps samples
+        wn = model.wavenet
+        Tar = (args.ar_steps // 640) * 640
+        lat = torch.randn(32, 64, Tar // 640, device=dev)
+        gar = torch.randint(0, 153, (32, 1), device=dev)
+        for prec in ("bf16", "fp32"):
+            wn.precision = prec
+            u = torch.rand(Tar, 32, device=dev)
+            wn.incremental_forward(c=lat[:, :, :1], g=gar, T=640, uniforms=u[:640], return_indices=True)   # warm-up / packing
+            barrier()
+            e0.record()
+            wn.incremental_forward(c=lat, g=gar, T=Tar, uniforms=u, return_indices=True)
+            e1.record()
+            barrier()
+            t_ar = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
+            extras[f"ar_{prec}_samples_per_s"] = world * 32 * Tar / t_ar
+            extras[f"ar_{prec}_realtime_factor_per_utt"] = Tar / t_ar / 16000.0
+            extras[f"ar_{prec}_us_per_step"] = 1e6 * t_ar / Tar
+        extras["ar_config"] = f"32 utt/GPU x {Tar} samples (configs[3] is 48000), categorical sampling, cluster kernel"
+        # VQ search throughput, N sweep (HBM roofline: 4D read + 4D write + 8 B index per vector)
+        from wavenet_autoencoders_b200.vector_quantization import VectorQuantize
+        vq = VectorQuantize(256, 64).to(dev)
+        for N in (400, 1 << 20):
+            lat_v = torch.randn(N // 25 if N == 400 else 64, 64, 25 if N == 400 else N // 64, device=dev) * 0.05
+            with torch.no_grad():
+                for _ in range(3):
+                    vq(lat_v)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(10):
+                    vq(lat_v)
+                e1.record()
+                torch.cuda.synchronize()
+            sec = e0.elapsed_time(e1) * 1e-3 / 10
+            extras[f"vq_vectors_per_s_N{N}"] = N / sec
+            extras[f"vq_hbm_frac_N{N}"] = N * (64 * 4 * 2 + 8) / sec / 1e9 / peak_hbm
+        model.wavenet.precision = "bf16"
+
+    cpu = None
+    if rank == 0 and world == 1:
+        torch.set_num_threads(os.cpu_count() or 1)
+        step = cpu_port_setup()
+        step()
+        reps, t0 = 0, time.perf_counter()
+        while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 20):
+            step()
+            reps += 1
+        dtc = time.perf_counter() - t0
+        cpu = {"value": reps * T_SAMPLES / dtc, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"decoder teacher-forced forward B=1 x T={T_SAMPLES}, {reps} reps, oracle/torch_port.py (reference's ATen calls), fp32"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": workload_config(world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "what": "pinned host idx/mfcc/speaker -> H2D -> one-hot -> VQVAE.forward -> teacher-forced NLL -> D2H loss"},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline, "cpu_baseline": cpu, "extras": extras,
+        }))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,6 +144,12 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
                            int B, int T, float* logits, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* Per-kernel-class device timing of wae_stack_forward_bf16 (CUDA events on the launching stream; used by bench.py
+ * for the roofline of the dominant kernel).  Kinds: 0 = prep kernels, 1 = residual-layer kernels, 2 = head kernel.
+ * wae_profile_read synchronises on the recorded events, returns accumulated ms / launch counts and resets them. */
+void wae_profile_enable(int on);
+int wae_profile_read(float* ms_by_kind, int32_t* launches_by_kind, int nkinds);
+
 /* Plain C[M][N] (fp32) = A[M][K] * B[N][K]^T, bf16 K-major operands, on the same tcgen05/TMA
  * pipeline the stack kernels use (unit-test entry point; K % 64 == 0, N % 16 == 0, N <= 256). */
 int wae_gemm_bf16_tn(const void* A, const void* B, float* Cout, int M, int N, int K, void* stream);

@@ -115,11 +115,13 @@ def test_forward_full_size_properties_bf16():
         y2 = m(x2, c, spk)
         assert torch.equal(y2[:, :, :9000], y[:, :, :9000])
         assert not torch.equal(y2[:, :, 9000:], y[:, :, 9000:])
-    # fp32 kernels on a slice of the same batch agree with the bf16 ones within the stated bf16 bound
+    # fp32 kernels on a slice of the same batch agree with the bf16 ones within the stated bf16 bound (the last
+    # ~850 samples of the slice see a different upsampled conditioning: the smoothing filters reach over the cut)
     m.precision = "fp32"
     with torch.no_grad():
         yf = m(x[:2, :, :6400], c[:2, :, :10], spk[:2])
-    assert rel_err(y[:2, :, :6400].cpu().numpy(), yf.cpu().numpy()) < TOL_BF16
+    err = rel_err(y[:2, :, :5000].cpu().numpy(), yf[:, :, :5000].cpu().numpy())
+    assert err < TOL_BF16, err
 
 
 # ------------------------------------------------------------------ autoregressive synthesis

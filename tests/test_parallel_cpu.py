@@ -1,0 +1,75 @@
+"""world_size-2 gloo tests (CPU) of the N>1 host logic: utterance sharding and the flat gradient all-reduce."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from wavenet_autoencoders_b200 import parallel
+from wavenet_autoencoders_b200 import testing as T
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+        torch.manual_seed(0)
+        m = WaveNet(**T.CONFIGS["tiny"]).train()
+        m.load_state_dict(T.synth_state_dict(m, 1))
+        # each rank: its own utterance shard of a global batch of 4
+        ids = parallel.shard_utterances(4, world, rank)
+        x, _, c, g = T.synth_inputs(T.CONFIGS["tiny"], 4, 64, 0)
+        sl = slice(ids.start, ids.stop)
+        y = m(x[sl], c[sl], g[sl])
+        (y.square().sum() / (4 * y[0].numel())).backward()
+        n = parallel.allreduce_gradients(m)
+        grads = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+        u = parallel.utterance_uniforms(ids, 8, 1, seed=7, device="cpu")
+        q.put((rank, n, grads, list(ids), u))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_dp_allreduce_and_sharding_world2():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # single-process reference: full batch, same loss normalisation; DP averages per-rank grads -> x world
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    torch.manual_seed(0)
+    m = WaveNet(**T.CONFIGS["tiny"]).train()
+    m.load_state_dict(T.synth_state_dict(m, 1))
+    x, _, c, g = T.synth_inputs(T.CONFIGS["tiny"], 4, 64, 0)
+    y = m(x, c, g)
+    (y.square().sum() / (4 * y[0].numel())).backward()
+    full = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in m.parameters()])
+    assert res[0][1] == full.numel() == sum(p.numel() for p in m.parameters())
+    assert torch.allclose(res[0][2], res[1][2])                       # replicas agree after the all-reduce
+    assert torch.allclose(res[0][2] * world, full, rtol=1e-4, atol=1e-6)
+    assert res[0][3] == [0, 1] and res[1][3] == [2, 3]
+    # random streams depend on the global utterance id only
+    all_u = parallel.utterance_uniforms(range(4), 8, 1, seed=7, device="cpu")
+    assert torch.equal(torch.cat([res[0][4], res[1][4]], dim=1), all_u)
+
+
+def test_shard_utterances_is_a_partition():
+    for n, w in [(256, 8), (7, 4), (3, 8), (0, 2)]:
+        got = [i for r in range(w) for i in parallel.shard_utterances(n, w, r)]
+        assert got == list(range(n))

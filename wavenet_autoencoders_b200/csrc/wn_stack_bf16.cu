@@ -23,6 +23,8 @@
 // Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA
 // issuer (one elected lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its warp_id % 4).
 #include "wae_common.cuh"
+#include <vector>
+#include <utility>
 #include <cuda.h>  // CUtensorMap + enums only; the encoder is fetched through cudaGetDriverEntryPoint
 
 using namespace wae::ptx;
@@ -719,6 +721,26 @@ int num_sms() {
     return n;
 }
 
+// ---- optional per-kernel-class timing (bench.py's roofline leg): CUDA events on the launching stream ----
+constexpr int PROF_KINDS = 4;  // 0 prep (g-bias, first conv, cond layout), 1 residual layers, 2 head, 3 unused
+struct Profiler {
+    bool on = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[PROF_KINDS];
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
+    }
+};
+Profiler g_prof;
+struct ProfScope {
+    int kind; cudaStream_t st; cudaEvent_t a, b; bool on;
+    ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(g_prof.on) {
+        if (on) { a = g_prof.get(); b = g_prof.get(); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() { if (on) { cudaEventRecord(b, st); g_prof.ev[kind].push_back({a, b}); } }
+};
+
 struct Bf16Workspace {
     __nv_bfloat16 *xa, *xb, *ccl, *hall;
     float* gb;
@@ -765,6 +787,30 @@ int wae_gemm_bf16_tn(const void* A, const void* Bm, float* Cout, int M, int N, i
     return WAE_OK;
 }
 
+void wae_profile_enable(int on) { g_prof.on = (on != 0); }
+
+int wae_profile_read(float* ms_by_kind, int32_t* launches_by_kind, int nkinds) {
+    for (int k = 0; k < nkinds; ++k) {
+        float total = 0.f;
+        int n = 0;
+        if (k < PROF_KINDS) {
+            for (auto& pr : g_prof.ev[k]) {
+                if (cudaEventSynchronize(pr.second) != cudaSuccess) return wae::set_error(WAE_ERR_CUDA, "wae_profile_read: event sync failed");
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, pr.first, pr.second);
+                total += ms;
+                ++n;
+                g_prof.pool.push_back(pr.first);
+                g_prof.pool.push_back(pr.second);
+            }
+            g_prof.ev[k].clear();
+        }
+        if (ms_by_kind) ms_by_kind[k] = total;
+        if (launches_by_kind) launches_by_kind[k] = n;
+    }
+    return WAE_OK;
+}
+
 size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T) {
     if (!d || B <= 0 || T <= 0) return 0;
     return carve(*d, B, T, nullptr).total;
@@ -798,6 +844,8 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     const int grid = ntiles < num_sms() ? ntiles : num_sms();
 
     // ---- prep: g bias, first conv, conditioning layout ----
+    {
+    ProfScope prof(0, stream);
     gbias_bf16_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, gemb, d.layers, B, d.G, d.Gi, ws.gb);
     WAE_CHECK_LAUNCH();
     {
@@ -809,6 +857,7 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     if (d.C > 0) {
         cond_to_cl_kernel<<<dim3((T + 63) / 64, (Cp + 31) / 32, B), 256, 0, stream>>>(c, T, d.C, Cp, ws.ccl);
         WAE_CHECK_LAUNCH();
+    }
     }
 
     // ---- layers ----
@@ -840,7 +889,10 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
         la.h_out = ws.hall + (size_t)l * B * T * Hp;
         la.dil = d.dilation[l];
         la.layer = l;
-        layer_bf16_kernel<<<grid, NUM_THREADS, smem_layer, stream>>>(la);
+        {
+            ProfScope prof(1, stream);
+            layer_bf16_kernel<<<grid, NUM_THREADS, smem_layer, stream>>>(la);
+        }
         WAE_CHECK_LAUNCH();
         __nv_bfloat16* t = cur; cur = nxt; nxt = t;
     }
@@ -856,7 +908,10 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     ha.B = B; ha.T = T; ha.L = d.layers; ha.S = d.S; ha.O = d.O; ha.Op = Op; ha.Hp = Hp; ha.tiles_per_utt = tiles_per_utt;
     const size_t smem_head = 1024 + (size_t)HEAD_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(d.S / BK) * A_TILE_BYTES + 256;
     WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
-    head_bf16_kernel<<<grid, NUM_THREADS, smem_head, stream>>>(ha);
+    {
+        ProfScope prof(2, stream);
+        head_bf16_kernel<<<grid, NUM_THREADS, smem_head, stream>>>(ha);
+    }
     WAE_CHECK_LAUNCH();
     return WAE_OK;
 }

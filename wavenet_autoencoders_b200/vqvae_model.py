@@ -31,7 +31,10 @@ class Encoder(nn.Module):
         self.lin = nn.Linear(hid, c_out)
 
     def forward(self, x):
-        out = self.net(x)
+        # keep the (out-of-scope, cuDNN) encoder in true fp32: TF32 convolutions would move latents by ~1e-3 and
+        # flip VQ codes relative to the reference's fp32 path
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            out = self.net(x)
         return self.lin(out.permute(0, 2, 1)).permute(0, 2, 1)
 
 
