@@ -183,6 +183,9 @@ typedef struct wae_ar_weights {
 } wae_ar_weights;
 
 size_t wae_ar_workspace(const wae_ar_weights* w, int B, int T);
+/* Debug/profiling: if non-NULL, every CTA of wae_ar_generate writes 12 int64 cycle counters (phase breakdown as seen by
+ * its thread 0) to dev_buf[blockIdx.x*16 ...]; the buffer must hold 16 int64 per launched CTA. */
+void wae_ar_set_profile_buffer(int64_t* dev_buf);
 /*
  *   c_btc      (B,T,C) fp32 upsampled conditioning, or NULL
  *   gemb       (B,Gi) fp32 or NULL

@@ -72,6 +72,7 @@ SIGNATURES = {
     "wae_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wae_gemm_bf16_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wae_ar_workspace": (C.c_size_t, [C.POINTER(ArWeights), C.c_int, C.c_int]),
+    "wae_ar_set_profile_buffer": (None, [C.c_void_p]),
     "wae_ar_generate": (C.c_int, [C.POINTER(ArWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_size_t, C.c_void_p]),

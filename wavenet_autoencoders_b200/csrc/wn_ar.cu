@@ -55,6 +55,7 @@ struct ArArgs {
     int* out_idx;                    // (B,T) or null
     float* out_dense;                // (B,T,O) / (B,T) or null
     float skip_scale;
+    long long* prof;                 // optional [gridDim.x][16] cycle counters (thread 0 of each CTA), or null
 };
 
 __host__ __device__ inline int part(int n, int r, int cs) { return (int)(((long long)n * r) / cs); }
@@ -94,7 +95,7 @@ __device__ __forceinline__ void bcast_store(float* local_ptr, float v, int lane,
 // Shared-memory carve-up (all sizes in bytes, computed identically on host and device).
 struct ArSmem {
     int w1_slot, w2_slot;      // bytes per weight slot
-    int off_w1, off_w2, off_xin, off_c, off_h, off_s1, off_s2, off_logit, off_skip, off_bias, off_in, off_misc, total;
+    int off_w1, off_w2, off_xin, off_c, off_h, off_s1, off_s2, off_logit, off_skip, off_bias, off_in, off_boff, off_misc, total;
     int n_bias;                // floats in the bias cache
 };
 
@@ -129,10 +130,13 @@ __host__ __device__ inline ArSmem ar_smem_layout(const wae_stack_dims& d, int cs
     s.n_bias = d.layers * (2 * max_np * U + max_n2) + max_n3 + max_n4;
     s.off_bias = off; off += up(s.n_bias * 4);
     s.off_in = off; off += up(U * d.Oin * 4);
+    s.off_boff = off; off += up((2 * d.layers + 2) * 8);
     s.off_misc = off; off += 256;  // mbarriers + small ints
     s.total = off;
     return s;
 }
+
+#define AR_PROF(i) do { if (a.prof != nullptr && tid == 0) { const long long _n = clock64(); pacc[i] += _n - pt; pt = _n; } } while (0)
 
 // ------------------------------------------------------------------------------------------------
 template <typename WT, int U>
@@ -164,6 +168,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     uint64_t* w1_full = bars;       // [2]
     uint64_t* w2_full = bars + 2;   // [2]
     int* cur_idx = reinterpret_cast<int*>(bars + 4);  // [U] class index of the current input, or -1 = dense (inbuf)
+    long long* boffs = reinterpret_cast<long long*>(smem + sl.off_boff);  // [2L+2] blob offsets of this rank
 
     // ---- row ownership of this rank ----
     const int p0 = part(H, rank, cs), np = part(H, rank + 1, cs) - p0;          // gate pairs
@@ -199,7 +204,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         const uint32_t bytes = w1_bytes();
         if (bytes == 0) { mbar_arrive(&w1_full[slot]); return; }  // empty slice: just complete the phase
         mbar_arrive_expect_tx(&w1_full[slot], bytes);
-        bulk_load_1d(w1buf + (size_t)slot * sl.w1_slot, a.blob + boff[(size_t)(2 * l) * cs + rank], bytes, &w1_full[slot]);
+        bulk_load_1d(w1buf + (size_t)slot * sl.w1_slot, a.blob + boffs[2 * l], bytes, &w1_full[slot]);
     };
     auto issue_w2 = [&](long long j) {
         if (j >= n2_total) return;
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         if (bytes == 0) { mbar_arrive(&w2_full[slot]); return; }
         const int stage = (i < L) ? 2 * i + 1 : 2 * L + (i - L);
         mbar_arrive_expect_tx(&w2_full[slot], bytes);
-        bulk_load_1d(w2buf + (size_t)slot * sl.w2_slot, a.blob + boff[(size_t)stage * cs + rank], bytes, &w2_full[slot]);
+        bulk_load_1d(w2buf + (size_t)slot * sl.w2_slot, a.blob + boffs[stage], bytes, &w2_full[slot]);
     };
 
     // ---- one-time setup ----
@@ -235,15 +240,18 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     for (int e = tid; e < nsk; e += AR_THREADS) b3c[e] = a.b3[so0 + e];
     for (int e = tid; e < nout; e += AR_THREADS) b4c[e] = a.b4[oo0 + e];
     if (tid < U) cur_idx[tid] = -1;
+    for (int e = tid; e < 2 * L + 2; e += AR_THREADS) boffs[e] = boff[(size_t)e * cs + rank];
     // initial input (wavenet.py:283-295); forced inputs override it below
     for (int e = tid; e < U * Oin; e += AR_THREADS) {
         const int u = e / Oin, o = e % Oin, b = cid * U + u;
         inbuf[e] = (b < a.B) ? a.init[(size_t)b * Oin + o] : 0.f;
     }
+    __syncthreads();
     if (tid == 0) { issue_w1(0); issue_w1(1); issue_w2(0); issue_w2(1); }
     cluster_sync();  // also: every CTA of the cluster is running before any DSMEM traffic
 
-    // cp.async prefetch of the tap rows of (step tt, layer l) into xin[l % NPF]
+    // cp.async prefetch of the tap rows of (step tt, layer l) into xin[(tt*L + l) % NPF]  (slots rotate with the
+    // GLOBAL layer sequence number so that L need not be a multiple of NPF)
     auto prefetch_taps = [&](int tt, int l) {
         if (tt < a.T && kw > 1) {
             const int ns = a.ring_ns[l], dil = d.dilation[l];
@@ -252,7 +260,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 const int c4 = e % (R / 4), j = (e / (R / 4)) % (kw - 1), u = e / ((R / 4) * (kw - 1));
                 const int b = cid * U + u;
                 const int ts = tt - (kw - 1 - j) * dil;  // source time of tap j
-                float* dst = xin + ((size_t)(l % NPF) * U + u) * KX + j * R + c4 * 4;
+                float* dst = xin + ((size_t)(((long long)tt * L + l) % NPF) * U + u) * KX + j * R + c4 * 4;
                 if (b < a.B && ts >= 0) {
                     const int slot = ts % ns;
                     cp_async16(dst, a.ring + (((size_t)b * a.ring_rows + a.ring_off[l] + slot) * R + c4 * 4));
@@ -280,8 +288,16 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     for (int l = 0; l < NPF - 1; ++l) prefetch_taps(0, l);  // host guarantees L >= NPF
 
     long long j1 = 0, j2 = 0;  // consumed-blob counters of the two weight rings
+    long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt = clock64();
 
     for (int t = 0; t < a.T; ++t) {
+        // random draw(s) of this step: issue the (HBM-latency) load now, consume it after the head
+        float u_pref = 0.f;
+        if (warp < U && a.uniforms != nullptr) {
+            const int b = cid * U + warp;
+            if (b < a.B && lane < a.nu) u_pref = __ldg(&a.uniforms[((size_t)t * a.B + b) * a.nu + lane]);
+        }
         // ================= input -> first conv (wavenet.py:300-311) =================
         // input of step t: forced[t] if t < Tf, else the value left in cur_idx/inbuf by the previous step
         if (a.forced != nullptr && t < a.Tf) {
@@ -307,7 +323,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         }
         __syncthreads();
         {
-            float* x0 = xin + (size_t)(0 % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer 0
+            float* x0 = xin + (size_t)(((long long)t * L) % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer 0
             for (int e = tid; e < U * R; e += AR_THREADS) {
                 const int u = e / R, r = e % R;
                 const int ci = cur_idx[u];
@@ -329,6 +345,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         prefetch_c(t + 1);  // joins the next committed cp.async group
         cp_async_wait<NPF - 2>();  // taps of layer 0 (and c(t)) have landed for this thread
         __syncthreads();
+        AR_PROF(0);
 
         // ================= residual layers =================
         for (int l = 0; l < L; ++l) {
@@ -336,7 +353,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 const int lp = l + NPF - 1;
                 if (lp < L) prefetch_taps(t, lp); else prefetch_taps(t + 1, lp - L);
             }
-            const float* xl = xin + (size_t)(l % NPF) * U * KX;     // [U][KX]
+            const long long seq = (long long)t * L + l;
+            const float* xl = xin + (size_t)(seq % NPF) * U * KX;     // [U][KX]
             const float* cl = cbuf + (size_t)(t & 1) * U * Cp;       // [U][Cp]
 
             // ---- GEMV1: gate pre-activations of this rank's pairs ----
@@ -351,7 +369,9 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                                             : *reinterpret_cast<const float2*>(cl + (size_t)u * Cp + (k - KX));
                 }
             }
+            AR_PROF(1);
             mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
+            AR_PROF(2);
             const WT* w1s = reinterpret_cast<const WT*>(w1buf + (size_t)(j1 & 1) * sl.w1_slot);
             for (int j = warp; j < np; j += AR_WARPS) {
                 const WT* wa = w1s + (size_t)(2 * j) * K1p;
@@ -381,9 +401,12 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 }
             }
             ++j1;
+            AR_PROF(3);
             cluster_arrive();
             mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
+            AR_PROF(4);
             cluster_wait();
+            AR_PROF(5);
             // Refill the W1 slot just consumed (blob j1+1 has the parity of j1-1).  Every warp of this CTA
             // finished reading it before arriving at the cluster barrier we just passed, so the
             // asynchronous overwrite cannot race with a reader.
@@ -401,7 +424,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 }
             const WT* w2s = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
             const bool last = (l == L - 1);
-            float* xnext = xin + (size_t)((l + 1) % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer l+1
+            float* xnext = xin + (size_t)((seq + 1) % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer l+1
             for (int i = warp; i < n2; i += AR_WARPS) {
                 if (last && i < nres) continue;  // residual output of the last layer is dead (wavenet.py:205-210)
                 const WT* wr = w2s + (size_t)i * Hp;
@@ -432,9 +455,12 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 }
             }
             ++j2;
+            AR_PROF(6);
             cp_async_wait<NPF - 2>();  // taps of the next layer have landed (this thread's copies)
+            AR_PROF(7);
             cluster_arrive();
             cluster_wait();
+            AR_PROF(8);
             if (tid == 0) issue_w2(j2 + 1);
             __syncwarp();
         }
@@ -515,6 +541,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         if (tid == 0) issue_w2(j2 + 1);
         __syncwarp();
 
+        AR_PROF(9);
         // ================= output / sampling (every CTA redundantly, warp u = utterance u) =================
         if (warp < U) {
             const int u = warp, b = cid * U + u;
@@ -542,7 +569,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 }
                 const float total = __shfl_sync(0xffffffffu, inc, 31);
                 if (a.sample_mode == WAE_AR_SAMPLE_CATEGORICAL) {
-                    const float uu = (b < a.B) ? __ldg(&a.uniforms[((size_t)t * a.B + b) * a.nu]) : 0.f;
+                    const float uu = __shfl_sync(0xffffffffu, u_pref, 0);
                     const float thr = uu * total;
                     // first class whose inclusive cumulative mass exceeds thr
                     float run = inc - loc;
@@ -573,14 +600,13 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             } else {
                 // scalar-input models: O = 3*nmix (or 2 for a single gaussian): [logit | mean | log_scale]
                 const int nmix = a.nmix;
-                const float* un = a.uniforms + ((size_t)t * a.B + (b < a.B ? b : 0)) * a.nu;
                 float best = -INFINITY;
                 int bi = 0x7fffffff;
                 if (nmix > 1 || a.sample_mode == WAE_AR_SAMPLE_MOL) {
-                    for (int i = lane; i < nmix; i += 32) {   // gumbel-max over mixture logits (mixture.py:138-140)
-                        const float uq = 1e-5f + __ldg(&un[i]) * (1.0f - 2e-5f);
-                        const float g = lg[i] - logf(-logf(uq));
-                        if (g > best) { best = g; bi = i; }
+                    if (lane < nmix) {   // gumbel-max over mixture logits (mixture.py:138-140); lane i holds uniform i
+                        const float uq = 1e-5f + u_pref * (1.0f - 2e-5f);
+                        best = lg[lane] - logf(-logf(uq));
+                        bi = lane;
                     }
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
@@ -594,14 +620,14 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 float xs;
                 if (a.sample_mode == WAE_AR_SAMPLE_MOL) {
                     const float mean = lg[nmix + bi], ls = lg[2 * nmix + bi];
-                    const float uq = 1e-5f + __ldg(&un[nmix]) * (1.0f - 2e-5f);
+                    const float uq = 1e-5f + __shfl_sync(0xffffffffu, u_pref, nmix) * (1.0f - 2e-5f);
                     xs = mean + expf(ls) * (logf(uq) - logf(1.f - uq));     // mixture.py:151-152
                 } else {
                     float mean, ls;
                     if (O == 2) { mean = lg[0]; ls = lg[1]; }
                     else if (nmix == 1) { mean = lg[1]; ls = lg[2]; }
                     else { mean = lg[nmix + bi]; ls = lg[2 * nmix + bi]; }
-                    xs = mean + expf(ls) * __ldg(&un[nmix]);                 // Normal(mean, exp(ls)).sample() with a supplied N(0,1) draw
+                    xs = mean + expf(ls) * __shfl_sync(0xffffffffu, u_pref, nmix);                 // Normal(mean, exp(ls)).sample() with a supplied N(0,1) draw
                 }
                 xs = fminf(fmaxf(xs, -1.f), 1.f);
                 if (lane == 0) {
@@ -612,7 +638,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             }
         }
         __syncthreads();
+        AR_PROF(10);
     }
+    if (a.prof != nullptr && tid == 0)
+        for (int i = 0; i < 12; ++i) a.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
     cp_async_wait<0>();
     cluster_sync();  // no CTA exits while peers may still write into its shared memory
 }
@@ -629,6 +658,8 @@ ar_gbias_kernel(const float* __restrict__ b1, const float* __restrict__ wg, cons
         gb[((size_t)l * B + b) * G + g] = __ldg(&b1[(size_t)l * G + g]) + acc;
     }
 }
+
+long long* g_ar_prof = nullptr;
 
 int ring_rows_total(const wae_stack_dims& d) {
     int n = 0;
@@ -662,6 +693,8 @@ int launch_ar(const ArArgs& args, int clusters, size_t smem, cudaStream_t stream
 }  // namespace
 
 extern "C" {
+
+void wae_ar_set_profile_buffer(int64_t* dev_buf) { g_ar_prof = reinterpret_cast<long long*>(dev_buf); }
 
 size_t wae_ar_workspace(const wae_ar_weights* w, int B, int T) {
     if (!w || B <= 0 || T <= 0) return 0;
@@ -723,9 +756,11 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
         a.nmix = (d.O == 2) ? 1 : d.O / 3;
         a.nu = a.nmix + 1;
         WAE_REQUIRE(d.Oin == 1, "wae_ar_generate: mixture sampling needs scalar input (Oin=1)");
+        WAE_REQUIRE(a.nu <= 32, "wae_ar_generate: at most 31 mixture components");
     }
     a.out_idx = out_idx; a.out_dense = out_dense;
     a.skip_scale = (float)sqrt(1.0 / (double)d.layers);
+    a.prof = g_ar_prof;
 
     char* p = static_cast<char*>(workspace);
     a.ring = reinterpret_cast<float*>(p);
