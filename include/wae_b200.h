@@ -144,6 +144,10 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
                            int B, int T, float* logits, void* workspace, size_t workspace_bytes,
                            void* stream);
 
+/* Tuning knob of the bf16 stack: CTAs per cluster of the residual-layer kernel (1, 2 or 4; default 2).  The CTAs of a
+ * cluster share every weight k-block through TMA multicast, which divides the L2->SM weight traffic by that factor. */
+int wae_set_layer_cluster(int cs);
+
 /* Per-kernel-class device timing of wae_stack_forward_bf16 (CUDA events on the launching stream; used by bench.py
  * for the roofline of the dominant kernel).  Kinds: 0 = prep kernels, 1 = residual-layer kernels, 2 = head kernel.
  * wae_profile_read synchronises on the recorded events, returns accumulated ms / launch counts and resets them. */

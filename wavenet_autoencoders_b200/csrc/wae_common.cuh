@@ -141,6 +141,18 @@ __device__ __forceinline__ void tma_load_2d(const void* desc, uint64_t* bar, voi
           "r"(c0), "r"(c1)
         : "memory");
 }
+// Multicast variant: the box lands at the same CTA-relative offset in every CTA of `cta_mask`, and completes
+// the transaction on the mbarrier at the same offset in each of them.
+__device__ __forceinline__ void tma_load_3d_mc(const void* desc, uint64_t* bar, void* smem_dst, int32_t c0,
+                                               int32_t c1, int32_t c2, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+        :
+        : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)),
+          "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
+        : "memory");
+}
 // 1D bulk copy global -> shared (no tensor map), completes on an mbarrier. bytes % 16 == 0.
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
                                              uint64_t* bar) {
@@ -218,10 +230,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// Same, arriving on the mbarrier at this offset in every CTA of `cta_mask` (stage release in a multicast pipeline).
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
+}
+
 // ---- clusters / DSMEM ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
     return r;
 }
 __device__ __forceinline__ uint32_t cluster_id_x() {

@@ -87,15 +87,25 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// write one float to the same shared-memory location of every CTA in the cluster (lanes = ranks)
-__device__ __forceinline__ void bcast_store(float* local_ptr, float v, int lane, int cs) {
-    if (lane < cs) st_cluster_f32(mapa(smem_u32(local_ptr), (uint32_t)lane), v);
+// All-gather of this CTA's slice through distributed shared memory: src[u][i] (i < n, local staging) is written to
+// dst[u*dst_stride + off + i] in EVERY CTA of the cluster.  One warp instruction = up to 32 consecutive floats to ONE
+// destination CTA (a single 128-byte DSMEM transaction); per-lane scalar stores to different CTAs were measured at
+// ~16 cycles each and dominated the step (profiles/ar_phase_r1.txt).
+__device__ __forceinline__ void allgather_slice(const float* src, int src_stride, float* dst, int dst_stride, int off,
+                                                int n, int U, int cs, int warp, int lane) {
+    const int nchunk = (n + 31) >> 5;
+    const int items = cs * U * nchunk;
+    for (int it = warp; it < items; it += AR_WARPS) {
+        const int c = it % nchunk, u = (it / nchunk) % U, r = it / (nchunk * U);
+        const int i = c * 32 + lane;
+        if (i < n) st_cluster_f32(mapa(smem_u32(dst + (size_t)u * dst_stride + off + i), (uint32_t)r), src[u * src_stride + i]);
+    }
 }
 
 // Shared-memory carve-up (all sizes in bytes, computed identically on host and device).
 struct ArSmem {
     int w1_slot, w2_slot;      // bytes per weight slot
-    int off_w1, off_w2, off_xin, off_c, off_h, off_s1, off_s2, off_logit, off_skip, off_bias, off_in, off_boff, off_misc, total;
+    int off_w1, off_w2, off_xin, off_c, off_h, off_s1, off_s2, off_logit, off_skip, off_bias, off_in, off_stg, off_boff, off_misc, total;
     int n_bias;                // floats in the bias cache
 };
 
@@ -130,6 +140,7 @@ __host__ __device__ inline ArSmem ar_smem_layout(const wae_stack_dims& d, int cs
     s.n_bias = d.layers * (2 * max_np * U + max_n2) + max_n3 + max_n4;
     s.off_bias = off; off += up(s.n_bias * 4);
     s.off_in = off; off += up(U * d.Oin * 4);
+    s.off_stg = off; off += up(U * 64 * 4 > U * (max_n2 + 1) * 4 ? U * 64 * 4 : U * (max_n2 + 1) * 4);
     s.off_boff = off; off += up((2 * d.layers + 2) * 8);
     s.off_misc = off; off += 256;  // mbarriers + small ints
     s.total = off;
@@ -169,6 +180,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     uint64_t* w2_full = bars + 2;   // [2]
     int* cur_idx = reinterpret_cast<int*>(bars + 4);  // [U] class index of the current input, or -1 = dense (inbuf)
     long long* boffs = reinterpret_cast<long long*>(smem + sl.off_boff);  // [2L+2] blob offsets of this rank
+    float* stg = reinterpret_cast<float*>(smem + sl.off_stg);       // [U][STG] local staging of this CTA's slice before the all-gather
 
     // ---- row ownership of this rank ----
     const int p0 = part(H, rank, cs), np = part(H, rank + 1, cs) - p0;          // gate pairs
@@ -183,6 +195,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         max_np = q > max_np ? q : max_np;
         max_n2 = q2 > max_n2 ? q2 : max_n2;
     }
+    const int STG = (max_n2 + 1) > 64 ? (max_n2 + 1) : 64;  // staging row pitch (floats)
     // bias cache layout: [L][2*max_np*U] gate biases | [L][max_n2] out/skip biases | [nsk] b3 | [nout] b4
     float* gbc = biasc;
     float* b2c = biasc + (size_t)L * 2 * max_np * U;
@@ -197,8 +210,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         return (uint32_t)(rows * k * sizeof(WT));
     };
     // issue the bulk copy of weight blob #j of each ring (thread 0 only)
-    const long long n1_total = (long long)a.T * L, n2_total = (long long)a.T * (L + 2);
-    auto issue_w1 = [&](long long j) {
+    const unsigned n1_total = (unsigned)a.T * L, n2_total = (unsigned)a.T * (L + 2);   // host checks T*(L+2) < 2^31
+    auto issue_w1 = [&](unsigned j) {
         if (j >= n1_total) return;
         const int l = (int)(j % L), slot = (int)(j & 1);
         const uint32_t bytes = w1_bytes();
@@ -206,7 +219,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         mbar_arrive_expect_tx(&w1_full[slot], bytes);
         bulk_load_1d(w1buf + (size_t)slot * sl.w1_slot, a.blob + boffs[2 * l], bytes, &w1_full[slot]);
     };
-    auto issue_w2 = [&](long long j) {
+    auto issue_w2 = [&](unsigned j) {
         if (j >= n2_total) return;
         const int i = (int)(j % (L + 2)), slot = (int)(j & 1);
         const uint32_t bytes = w2_bytes(i);
@@ -250,6 +263,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     if (tid == 0) { issue_w1(0); issue_w1(1); issue_w2(0); issue_w2(1); }
     cluster_sync();  // also: every CTA of the cluster is running before any DSMEM traffic
 
+    const int pf_r4 = R / 4;
+    const int pf_c4 = tid % pf_r4, pf_j = (kw > 1) ? (tid / pf_r4) % (kw - 1) : 0, pf_u = (kw > 1) ? tid / (pf_r4 * (kw - 1)) : 0;
     // cp.async prefetch of the tap rows of (step tt, layer l) into xin[(tt*L + l) % NPF]  (slots rotate with the
     // GLOBAL layer sequence number so that L need not be a multiple of NPF)
     auto prefetch_taps = [&](int tt, int l) {
@@ -257,10 +272,11 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             const int ns = a.ring_ns[l], dil = d.dilation[l];
             const int chunks = U * (kw - 1) * (R / 4);  // 16-byte chunks
             for (int e = tid; e < chunks; e += AR_THREADS) {
-                const int c4 = e % (R / 4), j = (e / (R / 4)) % (kw - 1), u = e / ((R / 4) * (kw - 1));
+                int c4 = pf_c4, j = pf_j, u = pf_u;
+                if (e != tid) { c4 = e % pf_r4; j = (e / pf_r4) % (kw - 1); u = e / (pf_r4 * (kw - 1)); }
                 const int b = cid * U + u;
                 const int ts = tt - (kw - 1 - j) * dil;  // source time of tap j
-                float* dst = xin + ((size_t)(((long long)tt * L + l) % NPF) * U + u) * KX + j * R + c4 * 4;
+                float* dst = xin + ((size_t)(((unsigned)tt * L + l) % NPF) * U + u) * KX + j * R + c4 * 4;
                 if (b < a.B && ts >= 0) {
                     const int slot = ts % ns;
                     cp_async16(dst, a.ring + (((size_t)b * a.ring_rows + a.ring_off[l] + slot) * R + c4 * 4));
@@ -287,7 +303,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     prefetch_c(0);
     for (int l = 0; l < NPF - 1; ++l) prefetch_taps(0, l);  // host guarantees L >= NPF
 
-    long long j1 = 0, j2 = 0;  // consumed-blob counters of the two weight rings
+    unsigned j1 = 0, j2 = 0;  // consumed-blob counters of the two weight rings
     long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long pt = clock64();
 
@@ -323,7 +339,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         }
         __syncthreads();
         {
-            float* x0 = xin + (size_t)(((long long)t * L) % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer 0
+            float* x0 = xin + (size_t)(((unsigned)t * L) % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer 0
             for (int e = tid; e < U * R; e += AR_THREADS) {
                 const int u = e / R, r = e % R;
                 const int ci = cur_idx[u];
@@ -353,7 +369,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 const int lp = l + NPF - 1;
                 if (lp < L) prefetch_taps(t, lp); else prefetch_taps(t + 1, lp - L);
             }
-            const long long seq = (long long)t * L + l;
+            const unsigned seq = (unsigned)t * L + l;
             const float* xl = xin + (size_t)(seq % NPF) * U * KX;     // [U][KX]
             const float* cl = cbuf + (size_t)(t & 1) * U * Cp;       // [U][Cp]
 
@@ -397,9 +413,11 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                     const float za = warp_sum(aa[u]) + gbp[u];
                     const float zb = warp_sum(ab[u]) + gbp[U + u];
                     const float h = tanhf(za) * (1.f / (1.f + expf(-zb)));   // modules.py:154
-                    bcast_store(hbuf + (size_t)u * Hp + p0 + j, h, lane, cs);
+                    if (lane == 0) stg[u * STG + j] = h;
                 }
             }
+            __syncthreads();
+            allgather_slice(stg, STG, hbuf, Hp, p0, np, U, cs, warp, lane);
             ++j1;
             AR_PROF(3);
             cluster_arrive();
@@ -445,14 +463,20 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                     if (i < nres) {
                         const int r = ro0 + i;
                         const float xo = (o + xl[(size_t)u * KX + (kw - 1) * R + r]) * 0.70710678118654752440f;  // modules.py:162
-                        bcast_store(xnext + (size_t)u * KX + r, xo, lane, cs);
                         const int b = cid * U + u;
-                        if (lane == 0 && b < a.B)
-                            __stcg(&a.ring[((size_t)b * a.ring_rows + a.ring_off[l + 1] + (t % a.ring_ns[l + 1])) * R + r], xo);
+                        if (lane == 0) {
+                            stg[u * STG + i] = xo;
+                            if (b < a.B)
+                                __stcg(&a.ring[((size_t)b * a.ring_rows + a.ring_off[l + 1] + (t % a.ring_ns[l + 1])) * R + r], xo);
+                        }
                     } else if (lane == 0) {
                         skipacc[u * (nsk + 1) + (i - nres)] += o;   // skips += h (wavenet.py:207); one writer per row
                     }
                 }
+            }
+            if (!last) {
+                __syncthreads();
+                allgather_slice(stg, STG, xnext, KX, ro0, nres, U, cs, warp, lane);
             }
             ++j2;
             AR_PROF(6);
@@ -469,10 +493,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         // relu(skips * sqrt(1/L)) -> all-gather
         for (int e = tid; e < U * nsk; e += AR_THREADS) {
             const int u = e / nsk, i = e % nsk;
-            const float v = fmaxf(skipacc[u * (nsk + 1) + i] * a.skip_scale, 0.f);
-            float* dst = s1buf + (size_t)u * S + so0 + i;
-            for (int r = 0; r < cs; ++r) st_cluster_f32(mapa(smem_u32(dst), (uint32_t)r), v);
+            stg[u * STG + i] = fmaxf(skipacc[u * (nsk + 1) + i] * a.skip_scale, 0.f);
         }
+        __syncthreads();
+        allgather_slice(stg, STG, s1buf, S, so0, nsk, U, cs, warp, lane);
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
@@ -500,10 +524,12 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const float v = fmaxf(warp_sum(acc[u]) + b3c[i], 0.f);
-                    bcast_store(s2buf + (size_t)u * S + so0 + i, v, lane, cs);
+                    if (lane == 0) stg[u * STG + i] = v;
                 }
             }
         }
+        __syncthreads();
+        allgather_slice(stg, STG, s2buf, S, so0, nsk, U, cs, warp, lane);
         ++j2;
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
@@ -532,9 +558,14 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                         for (int u = 0; u < U; ++u) { acc[u] = fmaf(f.x, sr[m][u].x, acc[u]); acc[u] = fmaf(f.y, sr[m][u].y, acc[u]); }
                     }
 #pragma unroll
-                for (int u = 0; u < U; ++u) bcast_store(lgbuf + (size_t)u * O + oo0 + i, warp_sum(acc[u]) + b4c[i], lane, cs);
+                for (int u = 0; u < U; ++u) {
+                    const float v = warp_sum(acc[u]) + b4c[i];
+                    if (lane == 0) stg[u * STG + i] = v;
+                }
             }
         }
+        __syncthreads();
+        allgather_slice(stg, STG, lgbuf, O, oo0, nout, U, cs, warp, lane);
         ++j2;
         cluster_arrive();
         cluster_wait();
@@ -713,6 +744,7 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
     const wae_stack_dims& d = w->d;
     const int H = d.G / 2;
     WAE_REQUIRE(B > 0 && T > 0, "wae_ar_generate: B=%d T=%d", B, T);
+    WAE_REQUIRE((long long)T * (d.layers + 2) < (1ll << 31), "wae_ar_generate: T too large");
     WAE_REQUIRE(d.layers >= NPF && d.layers <= WAE_MAX_LAYERS && d.kernel_size >= 1,
                 "wae_ar_generate: need %d <= layers <= %d", NPF, WAE_MAX_LAYERS);
     WAE_REQUIRE(w->cluster == 8 || w->cluster == 16 || w->cluster == 4 || w->cluster == 2 || w->cluster == 1,

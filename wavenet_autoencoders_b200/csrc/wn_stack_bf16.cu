@@ -301,8 +301,8 @@ cond_to_cl_kernel(const float* __restrict__ c, int T, int C, int Cp, __nv_bfloat
 struct LayerArgs {
     CUtensorMap tm_x;    // layer input  [B][T][R]   box {64, 128}
     CUtensorMap tm_c;    // conditioning [B][T][Cp]  box {64, 128}
-    CUtensorMap tm_w1;   // [L][G][K1p]              box {64, G}
-    CUtensorMap tm_wo;   // [L][R][Hp]               box {64, R}
+    CUtensorMap tm_w1;   // [L][G][K1p]              box {64, G / cluster}: every CTA of a cluster loads one row slice
+    CUtensorMap tm_wo;   // [L][R][Hp]               box {64, R / cluster}  and multicasts it to all of them
     const float* gb;     // [B][G]  conv bias + g term of this layer
     const float* bo;     // [R]
     const __nv_bfloat16* x_in;   // [B][T][R]
@@ -314,6 +314,12 @@ struct LayerArgs {
 constexpr int LAYER_STAGES = 4;
 
 // shared memory: [stages x (A 16K | B G*128)] [h: Hp/64 x 16K] [barriers]
+//
+// Launched in clusters of cs = 1, 2 or 4 CTAs.  All CTAs of a cluster work on different sample tiles of the SAME
+// layer, i.e. they need the same weight k-blocks, so each CTA fetches only 1/cs of every weight tile from L2 and
+// TMA-multicasts it into the shared memory of all cs CTAs (the kernel is L2->SM bandwidth bound otherwise:
+// 48 KB per k-block per CTA, 2/3 of it weights).  A stage may be refilled only when ALL cs CTAs have consumed it,
+// so the stage-release commit is multicast too (empty barriers count cs arrivals).
 __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -332,8 +338,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cs = (int)cluster_nctarank();              // 1, 2 or 4
+    const int crank = (int)cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < LAYER_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < LAYER_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], cs); }
         mbar_init(acc1_full, 1);
         mbar_init(epi1_done, 128);
         mbar_init(acc2_full, 1);
@@ -347,23 +356,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
     if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync();   // peers' barriers are initialised before any multicast load / remote commit targets them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_acc1 = tmem_base;        // columns [0, G)
     const uint32_t tmem_acc2 = tmem_base + 256;  // columns [256, 256+R)
 
+    // Work is dealt to clusters in "super tiles" of cs consecutive 128-sample tiles; rank r takes tile super*cs + r.
+    // Every CTA of a cluster runs the same number of pipeline steps (a tile past the end loads zeros and stores nothing).
     const int ntiles = a.B * a.tiles_per_utt;
+    const int nsuper = (ntiles + cs - 1) / cs;
+    const int ncluster = (int)gridDim.x / cs, cluster_id = (int)blockIdx.x / cs;
     const int nk_taps = a.kw * (a.R / BK);
     const int nk_c = a.Cp / BK;
     const bool has_out = (a.x_out != nullptr);
     const int w1_bytes = a.G * BK * 2, wo_bytes = a.R * BK * 2;
+    const int w1_rows = a.G / cs, wo_rows = a.R / cs;    // weight rows this CTA fetches (and multicasts) per k-block
 
     if (warp == 0) {
         // ================= TMA producer =================
         if (elect_one()) {
             Ring ring(LAYER_STAGES);
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster) {
+                const int tile = sup * cs + crank;
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: TMA zero-fills
                 int kcol = 0;
                 for (int kb = 0; kb < nk_taps + nk_c; ++kb, kcol += BK) {
                     mbar_wait(&empty[ring.stage], ring.phase ^ 1);
@@ -375,7 +391,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                     } else {
                         tma_load_3d(&a.tm_c, &full[ring.stage], sa, (kb - nk_taps) * BK, t0, b);
                     }
-                    tma_load_3d(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES, kcol, 0, a.layer);
+                    if (cs == 1)
+                        tma_load_3d(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES, kcol, 0, a.layer);
+                    else
+                        tma_load_3d_mc(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES + crank * w1_rows * BK * 2, kcol,
+                                       crank * w1_rows, a.layer, cmask);
                     ring.advance();
                 }
                 if (has_out) {
@@ -383,7 +403,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                         mbar_wait(&empty[ring.stage], ring.phase ^ 1);
                         uint8_t* sa = smem + ring.stage * STAGE_BYTES;
                         mbar_arrive_expect_tx(&full[ring.stage], wo_bytes);
-                        tma_load_3d(&a.tm_wo, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, a.layer);
+                        if (cs == 1)
+                            tma_load_3d(&a.tm_wo, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, a.layer);
+                        else
+                            tma_load_3d_mc(&a.tm_wo, &full[ring.stage], sa + A_TILE_BYTES + crank * wo_rows * BK * 2, kb * BK,
+                                           crank * wo_rows, a.layer, cmask);
                         ring.advance();
                     }
                 }
@@ -396,7 +420,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
             const uint32_t idesc1 = umma_idesc_bf16(BM, a.G);
             const uint32_t idesc2 = umma_idesc_bf16(BM, a.R);
             int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
                 // acc1 of the previous tile was drained before its GEMM2 was issued (epi1_done wait below),
                 // or -- when there is no GEMM2 -- must be waited for here.
                 if (!has_out && it > 0) { mbar_wait(epi1_done, (it - 1) & 1); tc_fence_after(); }
@@ -405,7 +429,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
                     issue_kblock(tmem_acc1, sa, sa + A_TILE_BYTES, idesc1, kb == 0);
-                    umma_commit(&empty[ring.stage]);
+                    if (cs == 1) umma_commit(&empty[ring.stage]); else umma_commit_mc(&empty[ring.stage], cmask);
                     ring.advance();
                 }
                 umma_commit(acc1_full);
@@ -418,7 +442,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                         tc_fence_after();
                         const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
                         issue_kblock(tmem_acc2, smem_u32(hbuf + kb * A_TILE_BYTES), sb, idesc2, kb == 0);
-                        umma_commit(&empty[ring.stage]);
+                        if (cs == 1) umma_commit(&empty[ring.stage]); else umma_commit_mc(&empty[ring.stage], cmask);
                         ring.advance();
                     }
                     umma_commit(acc2_full);
@@ -432,10 +456,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t hbuf_addr = smem_u32(hbuf);
         int it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-            const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+        for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+            const int tile = sup * cs + crank;
+            const bool tile_ok = (tile < ntiles);
+            const int b = tile_ok ? tile / a.tiles_per_utt : 0, t0 = (tile % a.tiles_per_utt) * BM;
             const int t = t0 + row;
-            const bool live = (t < a.T);
+            const bool live = tile_ok && (t < a.T);
             const float* gbp = a.gb + (size_t)b * a.G;
             __nv_bfloat16* hrow = a.h_out + ((size_t)b * a.T + t) * a.Hp;
 
@@ -510,6 +536,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
     }
     tc_fence_before();
     __syncthreads();
+    if (cs > 1) cluster_sync();   // no CTA retires while a peer may still multicast into it or arrive on its barriers
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
@@ -733,6 +760,7 @@ struct Profiler {
     }
 };
 Profiler g_prof;
+int g_layer_cluster = 2;   // wae_set_layer_cluster(): 1, 2 or 4 CTAs share every weight k-block via TMA multicast
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a, b; bool on;
     ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(g_prof.on) {
@@ -788,6 +816,12 @@ int wae_gemm_bf16_tn(const void* A, const void* Bm, float* Cout, int M, int N, i
 }
 
 void wae_profile_enable(int on) { g_prof.on = (on != 0); }
+
+int wae_set_layer_cluster(int cs) {
+    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be 1, 2 or 4");
+    g_layer_cluster = cs;
+    return WAE_OK;
+}
 
 int wae_profile_read(float* ms_by_kind, int32_t* launches_by_kind, int nkinds) {
     for (int k = 0; k < nkinds; ++k) {
@@ -874,8 +908,16 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     } else {
         la.tm_c = tm_xa;  // never used (nk_c == 0)
     }
-    if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, d.G, d.layers, K1p, (uint64_t)d.G * K1p, BK, d.G)) return rc;
-    if (int rc = make_tmap(&la.tm_wo, w->wo, Hp, d.R, d.layers, Hp, (uint64_t)d.R * Hp, BK, d.R)) return rc;
+    // cluster size of the layer kernel: weight k-blocks are fetched once per cluster and multicast (see kernel comment)
+    int cs = g_layer_cluster;
+    while (cs > 1 && (d.G % (8 * cs) != 0 || d.R % (8 * cs) != 0 || num_sms() / cs < 1)) cs >>= 1;
+    if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, d.G, d.layers, K1p, (uint64_t)d.G * K1p, BK, d.G / cs)) return rc;
+    if (int rc = make_tmap(&la.tm_wo, w->wo, Hp, d.R, d.layers, Hp, (uint64_t)d.R * Hp, BK, d.R / cs)) return rc;
+    const int nsuper = (ntiles + cs - 1) / cs;
+    int nclusters = num_sms() / cs;
+    if (cs == 4) nclusters = 33;   // 132 SMs: 4-CTA clusters cannot use all 148 (GPC granularity); more would queue a 2nd wave
+    if (nclusters > nsuper) nclusters = nsuper;
+    const int grid_layer = nclusters * cs;
     la.B = B; la.T = T; la.R = d.R; la.G = d.G; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
     la.tiles_per_utt = tiles_per_utt;
     __nv_bfloat16* cur = ws.xa;
@@ -891,7 +933,19 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
         la.layer = l;
         {
             ProfScope prof(1, stream);
-            layer_bf16_kernel<<<grid, NUM_THREADS, smem_layer, stream>>>(la);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)grid_layer);
+            cfg.blockDim = dim3(NUM_THREADS);
+            cfg.dynamicSmemBytes = smem_layer;
+            cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = (unsigned)cs;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_kernel, la));
         }
         WAE_CHECK_LAUNCH();
         __nv_bfloat16* t = cur; cur = nxt; nxt = t;
