@@ -168,7 +168,8 @@ int wae_gemm_bf16_tn(const void* A, const void* B, float* Cout, int M, int N, in
  * Weights for the AR kernel.  Each layer's two mat-vecs are split by OUTPUT ROW over the `cluster`
  * CTAs of a thread-block cluster (balanced contiguous ranges: rank r owns rows [n*r/cs, n*(r+1)/cs)),
  * and every rank streams only its own rows, so the host packs one contiguous blob per (stage, rank)
- * (packing.py:pack_ar), row-major with the reduction dim padded to a multiple of 64:
+ * (packing.py:pack_ar), reduction dim padded to a multiple of 64 and stored chunk-major: a [rows][K] slice is laid out
+ * [K/c][rows][c] with c = 16 (8 lanes share a row) for stages 2l, 2L, 2L+1 and c = 8 (4 lanes per row) for stage 2l+1:
  *   stage 2l   : gate rows of rank r, interleaved (tanh row p, sigmoid row p) for its pairs p   [2*np][K1p]
  *   stage 2l+1 : conv1x1_out rows then conv1x1_skip rows of rank r                              [nres+nsk][Hp]
  *   stage 2L   : last_conv_layers[1] rows of rank r  [nsk][S]      stage 2L+1: last_conv_layers[3] rows  [nout][S]

@@ -140,7 +140,7 @@ __host__ __device__ inline ArSmem ar_smem_layout(const wae_stack_dims& d, int cs
     s.n_bias = d.layers * (2 * max_np * U + max_n2) + max_n3 + max_n4;
     s.off_bias = off; off += up(s.n_bias * 4);
     s.off_in = off; off += up(U * d.Oin * 4);
-    s.off_stg = off; off += up(U * 64 * 4 > U * (max_n2 + 1) * 4 ? U * 64 * 4 : U * (max_n2 + 1) * 4);
+    s.off_stg = off; off += 2 * up(U * 64 * 4 > U * (max_n2 + 1) * 4 ? U * 64 * 4 : U * (max_n2 + 1) * 4);   // two staging buffers
     s.off_boff = off; off += up((2 * d.layers + 2) * 8);
     s.off_misc = off; off += 256;  // mbarriers + small ints
     s.total = off;
@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     int* cur_idx = reinterpret_cast<int*>(bars + 4);  // [U] class index of the current input, or -1 = dense (inbuf)
     long long* boffs = reinterpret_cast<long long*>(smem + sl.off_boff);  // [2L+2] blob offsets of this rank
     float* stg = reinterpret_cast<float*>(smem + sl.off_stg);       // [U][STG] local staging of this CTA's slice before the all-gather
+    float* stgx = reinterpret_cast<float*>(smem + sl.off_stg + (sl.off_boff - sl.off_stg) / 2);  // second staging buffer (layer outputs; read again after the barrier)
 
     // ---- row ownership of this rank ----
     const int p0 = part(H, rank, cs), np = part(H, rank + 1, cs) - p0;          // gate pairs
@@ -374,46 +375,50 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             const float* cl = cbuf + (size_t)(t & 1) * U * Cp;       // [U][Cp]
 
             // ---- GEMV1: gate pre-activations of this rank's pairs ----
-            float2 xr[MAXM1][U];
-#pragma unroll
-            for (int m = 0; m < MAXM1; ++m) {
-                if (m < nm1) {
-                    const int k = m * 64 + lane * 2;
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        xr[m][u] = (k < KX) ? *reinterpret_cast<const float2*>(xl + (size_t)u * KX + k)
-                                            : *reinterpret_cast<const float2*>(cl + (size_t)u * Cp + (k - KX));
-                }
-            }
+            // 8 lanes share one weight row (each walks K/8 elements, 3 shuffle steps finish the dot product), so a warp
+            // finishes 4 rows = 2 (tanh, sigmoid) pairs per pass with 4x fewer dependent shuffle chains than a
+            // 32-lane-per-row split.  Weights are packed [K/16][row][16] so the 32 lanes of a warp read 32
+            // consecutive words of shared memory (conflict free); the input vector is a broadcast read.
             AR_PROF(1);
             mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
             AR_PROF(2);
-            const WT* w1s = reinterpret_cast<const WT*>(w1buf + (size_t)(j1 & 1) * sl.w1_slot);
-            for (int j = warp; j < np; j += AR_WARPS) {
-                const WT* wa = w1s + (size_t)(2 * j) * K1p;
-                const WT* wb = wa + K1p;
-                float aa[U], ab[U];
+            {
+                const WT* w1s = reinterpret_cast<const WT*>(w1buf + (size_t)(j1 & 1) * sl.w1_slot);
+                const int rows1 = 2 * np, grp = lane >> 3, s8 = lane & 7;
+                for (int r0 = warp * 4; r0 < rows1; r0 += AR_WARPS * 4) {
+                    const int row = r0 + grp;
+                    const bool rvalid = row < rows1;
+                    const WT* wrow = w1s + (size_t)(rvalid ? row : 0) * 16 + s8 * 2;
+                    float acc[U][2];
 #pragma unroll
-                for (int u = 0; u < U; ++u) { aa[u] = 0.f; ab[u] = 0.f; }
-#pragma unroll
-                for (int m = 0; m < MAXM1; ++m) {
-                    if (m < nm1) {
-                        const int k = m * 64 + lane * 2;
-                        const float2 fa = WLoad<WT>::ld2(wa, k), fb = WLoad<WT>::ld2(wb, k);
+                    for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+#pragma unroll 4
+                    for (int m = 0; m < nm1 * 4; ++m) {                      // K1p / 16 chunks
+                        const int k = m * 16 + s8 * 2;
+                        const float2 w = WLoad<WT>::ld2(wrow + (size_t)m * rows1 * 16, 0);
+                        const float* xs = (k < KX) ? (xl + k) : (cl + (k - KX));
+                        const int xstride = (k < KX) ? KX : Cp;
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            aa[u] = fmaf(fa.x, xr[m][u].x, aa[u]); aa[u] = fmaf(fa.y, xr[m][u].y, aa[u]);
-                            ab[u] = fmaf(fb.x, xr[m][u].x, ab[u]); ab[u] = fmaf(fb.y, xr[m][u].y, ab[u]);
+                            const float2 xv = *reinterpret_cast<const float2*>(xs + (size_t)u * xstride);
+                            acc[u][0] = fmaf(w.x, xv.x, acc[u][0]);
+                            acc[u][1] = fmaf(w.y, xv.y, acc[u][1]);
                         }
                     }
-                }
-                const float* gbp = gbc + (size_t)l * 2 * max_np * U + (size_t)j * 2 * U;
+                    const int j = row >> 1;   // pair index within the slice
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float za = warp_sum(aa[u]) + gbp[u];
-                    const float zb = warp_sum(ab[u]) + gbp[U + u];
-                    const float h = tanhf(za) * (1.f / (1.f + expf(-zb)));   // modules.py:154
-                    if (lane == 0) stg[u * STG + j] = h;
+                    for (int u = 0; u < U; ++u) {
+                        float z = acc[u][0] + acc[u][1];
+                        z += __shfl_xor_sync(0xffffffffu, z, 4);
+                        z += __shfl_xor_sync(0xffffffffu, z, 2);
+                        z += __shfl_xor_sync(0xffffffffu, z, 1);
+                        const float zo = __shfl_xor_sync(0xffffffffu, z, 8);     // partner row (tanh <-> sigmoid)
+                        if (rvalid && (grp & 1) == 0 && s8 == 0) {
+                            const float* gbp = gbc + (size_t)l * 2 * max_np * U + (size_t)j * 2 * U;
+                            const float za = z + gbp[u], zb = zo + gbp[U + u];
+                            stg[u * STG + j] = tanhf(za) * (1.f / (1.f + expf(-zb)));   // modules.py:154
+                        }
+                    }
                 }
             }
             __syncthreads();
@@ -431,62 +436,70 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             if (tid == 0) issue_w1(j1 + 1);
             __syncwarp();
 
-            // ---- GEMV2: residual + skip rows of this rank ----
-            float2 hr[MAXM2][U];
-#pragma unroll
-            for (int m = 0; m < MAXM2; ++m)
-                if (m < nm2) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u)
-                        hr[m][u] = *reinterpret_cast<const float2*>(hbuf + (size_t)u * Hp + m * 64 + lane * 2);
-                }
-            const WT* w2s = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
+            // ---- GEMV2: residual + skip rows of this rank (4 lanes per row, 8 rows per warp and pass) ----
             const bool last = (l == L - 1);
             float* xnext = xin + (size_t)((seq + 1) % NPF) * U * KX + (kw - 1) * R;  // current-sample slot of layer l+1
-            for (int i = warp; i < n2; i += AR_WARPS) {
-                if (last && i < nres) continue;  // residual output of the last layer is dead (wavenet.py:205-210)
-                const WT* wr = w2s + (size_t)i * Hp;
-                float acc[U];
+            {
+                const WT* w2s = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
+                const int grp = lane >> 2, s4 = lane & 3;
+                for (int r0 = warp * 8; r0 < n2; r0 += AR_WARPS * 8) {
+                    const int i = r0 + grp;
+                    const bool rvalid = i < n2;
+                    const WT* wrow = w2s + (size_t)(rvalid ? i : 0) * 8 + s4 * 2;
+                    float acc[U][2];
 #pragma unroll
-                for (int u = 0; u < U; ++u) acc[u] = 0.f;
+                    for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+#pragma unroll 4
+                    for (int m = 0; m < nm2 * 8; ++m) {                      // Hp / 8 chunks
+                        const float2 w = WLoad<WT>::ld2(wrow + (size_t)m * n2 * 8, 0);
 #pragma unroll
-                for (int m = 0; m < MAXM2; ++m)
-                    if (m < nm2) {
-                        const float2 f = WLoad<WT>::ld2(wr, m * 64 + lane * 2);
-#pragma unroll
-                        for (int u = 0; u < U; ++u) { acc[u] = fmaf(f.x, hr[m][u].x, acc[u]); acc[u] = fmaf(f.y, hr[m][u].y, acc[u]); }
-                    }
-                const float bias = b2c[(size_t)l * max_n2 + i];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float o = warp_sum(acc[u]) + bias;
-                    if (i < nres) {
-                        const int r = ro0 + i;
-                        const float xo = (o + xl[(size_t)u * KX + (kw - 1) * R + r]) * 0.70710678118654752440f;  // modules.py:162
-                        const int b = cid * U + u;
-                        if (lane == 0) {
-                            stg[u * STG + i] = xo;
-                            if (b < a.B)
-                                __stcg(&a.ring[((size_t)b * a.ring_rows + a.ring_off[l + 1] + (t % a.ring_ns[l + 1])) * R + r], xo);
+                        for (int u = 0; u < U; ++u) {
+                            const float2 hv = *reinterpret_cast<const float2*>(hbuf + (size_t)u * Hp + m * 8 + s4 * 2);
+                            acc[u][0] = fmaf(w.x, hv.x, acc[u][0]);
+                            acc[u][1] = fmaf(w.y, hv.y, acc[u][1]);
                         }
-                    } else if (lane == 0) {
-                        skipacc[u * (nsk + 1) + (i - nres)] += o;   // skips += h (wavenet.py:207); one writer per row
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        float o = acc[u][0] + acc[u][1];
+                        o += __shfl_xor_sync(0xffffffffu, o, 2);
+                        o += __shfl_xor_sync(0xffffffffu, o, 1);
+                        if (rvalid && s4 == 0) {
+                            o += b2c[(size_t)l * max_n2 + i];
+                            if (i < nres) {
+                                if (!last) {   // residual output of the last layer is dead (wavenet.py:205-210)
+                                    const int r = ro0 + i;
+                                    stgx[u * STG + i] = (o + xl[(size_t)u * KX + (kw - 1) * R + r]) * 0.70710678118654752440f;  // modules.py:162
+                                }
+                            } else {
+                                skipacc[u * (nsk + 1) + (i - nres)] += o;   // skips += h (wavenet.py:207); one writer per row
+                            }
+                        }
                     }
                 }
             }
             if (!last) {
                 __syncthreads();
-                allgather_slice(stg, STG, xnext, KX, ro0, nres, U, cs, warp, lane);
+                allgather_slice(stgx, STG, xnext, KX, ro0, nres, U, cs, warp, lane);
             }
             ++j2;
             AR_PROF(6);
             cp_async_wait<NPF - 2>();  // taps of the next layer have landed (this thread's copies)
             AR_PROF(7);
             cluster_arrive();
+            // The ring rows of layer l+1 are written AFTER the arrive: the release above then does not wait for their
+            // L2 round trip; they are covered by the next barrier, long before any prefetch reads them.
+            if (!last) {
+                for (int e = tid; e < U * nres; e += AR_THREADS) {
+                    const int u = e / nres, i = e % nres, b = cid * U + u;
+                    if (b < a.B)
+                        __stcg(&a.ring[((size_t)b * a.ring_rows + a.ring_off[l + 1] + (t % a.ring_ns[l + 1])) * R + ro0 + i], stgx[u * STG + i]);
+                }
+            }
             cluster_wait();
-            AR_PROF(8);
             if (tid == 0) issue_w2(j2 + 1);
             __syncwarp();
+            AR_PROF(8);
         }
 
         // ================= head (wavenet.py:208-212 / :316-322) =================
@@ -500,34 +513,41 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
-        {   // 1x1 S->S + ReLU
-            float2 sr[MAXMS][U];
+        // the two 1x1 convolutions of the head: 8 lanes per row, weights packed [S/16][row][16]
+        auto head_gemv = [&](const float* src, int nrows, const float* bias, bool relu) {
+            const WT* ws_ = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
+            const int grp = lane >> 3, s8 = lane & 7;
+            for (int r0 = warp * 4; r0 < nrows; r0 += AR_WARPS * 4) {
+                const int i = r0 + grp;
+                const bool rvalid = i < nrows;
+                const WT* wrow = ws_ + (size_t)(rvalid ? i : 0) * 16 + s8 * 2;
+                float acc[U][2];
 #pragma unroll
-            for (int m = 0; m < MAXMS; ++m)
-                if (m < nms) {
+                for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+#pragma unroll 4
+                for (int m = 0; m < nms * 4; ++m) {
+                    const float2 w = WLoad<WT>::ld2(wrow + (size_t)m * nrows * 16, 0);
 #pragma unroll
-                    for (int u = 0; u < U; ++u) sr[m][u] = *reinterpret_cast<const float2*>(s1buf + (size_t)u * S + m * 64 + lane * 2);
-                }
-            const WT* w3s = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
-            for (int i = warp; i < nsk; i += AR_WARPS) {
-                const WT* wr = w3s + (size_t)i * S;
-                float acc[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) acc[u] = 0.f;
-#pragma unroll
-                for (int m = 0; m < MAXMS; ++m)
-                    if (m < nms) {
-                        const float2 f = WLoad<WT>::ld2(wr, m * 64 + lane * 2);
-#pragma unroll
-                        for (int u = 0; u < U; ++u) { acc[u] = fmaf(f.x, sr[m][u].x, acc[u]); acc[u] = fmaf(f.y, sr[m][u].y, acc[u]); }
+                    for (int u = 0; u < U; ++u) {
+                        const float2 sv = *reinterpret_cast<const float2*>(src + (size_t)u * S + m * 16 + s8 * 2);
+                        acc[u][0] = fmaf(w.x, sv.x, acc[u][0]);
+                        acc[u][1] = fmaf(w.y, sv.y, acc[u][1]);
                     }
+                }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const float v = fmaxf(warp_sum(acc[u]) + b3c[i], 0.f);
-                    if (lane == 0) stg[u * STG + i] = v;
+                    float v = acc[u][0] + acc[u][1];
+                    v += __shfl_xor_sync(0xffffffffu, v, 4);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    if (rvalid && s8 == 0) {
+                        v += bias[i];
+                        stg[u * STG + i] = relu ? fmaxf(v, 0.f) : v;
+                    }
                 }
             }
-        }
+        };
+        head_gemv(s1buf, nsk, b3c, true);        // 1x1 S->S + ReLU
         __syncthreads();
         allgather_slice(stg, STG, s2buf, S, so0, nsk, U, cs, warp, lane);
         ++j2;
@@ -536,34 +556,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         cluster_wait();
         if (tid == 0) issue_w2(j2 + 1);
         __syncwarp();
-        {   // 1x1 S->O
-            float2 sr[MAXMS][U];
-#pragma unroll
-            for (int m = 0; m < MAXMS; ++m)
-                if (m < nms) {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) sr[m][u] = *reinterpret_cast<const float2*>(s2buf + (size_t)u * S + m * 64 + lane * 2);
-                }
-            const WT* w4s = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
-            for (int i = warp; i < nout; i += AR_WARPS) {
-                const WT* wr = w4s + (size_t)i * S;
-                float acc[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) acc[u] = 0.f;
-#pragma unroll
-                for (int m = 0; m < MAXMS; ++m)
-                    if (m < nms) {
-                        const float2 f = WLoad<WT>::ld2(wr, m * 64 + lane * 2);
-#pragma unroll
-                        for (int u = 0; u < U; ++u) { acc[u] = fmaf(f.x, sr[m][u].x, acc[u]); acc[u] = fmaf(f.y, sr[m][u].y, acc[u]); }
-                    }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const float v = warp_sum(acc[u]) + b4c[i];
-                    if (lane == 0) stg[u * STG + i] = v;
-                }
-            }
-        }
+        head_gemv(s2buf, nout, b4c, false);      // 1x1 S->O
         __syncthreads();
         allgather_slice(stg, STG, lgbuf, O, oo0, nout, U, cs, warp, lane);
         ++j2;

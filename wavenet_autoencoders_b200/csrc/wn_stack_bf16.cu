@@ -455,6 +455,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t hbuf_addr = smem_u32(hbuf);
+        // conv1x1_out bias: staged once in shared memory (broadcast reads instead of per-chunk global loads)
+        float* sb_bo = reinterpret_cast<float*>(bars) + 32;   // bars region is 128 B, then 256 floats
+        for (int i = threadIdx.x - 64; i < a.R; i += 128) sb_bo[i] = __ldg(a.bo + i);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         int it = 0;
         for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
             const int tile = sup * cs + crank;
@@ -465,6 +469,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
             const float* gbp = a.gb + (size_t)b * a.G;
             __nv_bfloat16* hrow = a.h_out + ((size_t)b * a.T + t) * a.Hp;
 
+            // Residual row of this thread (R bf16 = up to 512 B): issued NOW, consumed in EPI2.  The first version
+            // loaded it chunk by chunk inside EPI2 and exposed one L2 round trip per 16 channels (ncu: long-scoreboard
+            // stalls on those loads were the top stall of the kernel, profiles/r1_layer_kernel_ncu.txt).
+            uint4 res[32];
+            if (has_out && live) {
+                const uint4* xin = reinterpret_cast<const uint4*>(a.x_in + ((size_t)b * a.T + t) * a.R);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j * 8 < a.R) res[j] = __ldg(xin + j);
+            }
+
             // ---- EPI1: gate ----
             mbar_wait(acc1_full, it & 1);
             tc_fence_after();
@@ -474,13 +489,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                     float va[16], vb[16];
                     tmem_ld16(tmem_acc1 + lane_base + c0, va);
                     tmem_ld16(tmem_acc1 + lane_base + H + c0, vb);
+                    float ba[16], bb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
+                        *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + H + c0 + i));
+                    }
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; i += 2) {
-                        const float2 ba = __ldg(reinterpret_cast<const float2*>(gbp + c0 + i));
-                        const float2 bb = __ldg(reinterpret_cast<const float2*>(gbp + H + c0 + i));
-                        const float h0 = tanh_fast(va[i] + ba.x) * sigmoid_fast(vb[i] + bb.x);
-                        const float h1 = tanh_fast(va[i + 1] + ba.y) * sigmoid_fast(vb[i + 1] + bb.y);
+                        const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
+                        const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
                         packed[i >> 1] = pack_bf16x2(h0, h1);
                     }
                 } else {
@@ -505,28 +524,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
             if (has_out) {
                 mbar_wait(acc2_full, it & 1);
                 tc_fence_after();
-                const __nv_bfloat16* xin = a.x_in + ((size_t)b * a.T + t) * a.R;
                 __nv_bfloat16* xout = a.x_out + ((size_t)b * a.T + t) * a.R;
-                for (int c0 = 0; c0 < a.R; c0 += 16) {
-                    float v[16];
-                    tmem_ld16(tmem_acc2 + lane_base + c0, v);
-                    tmem_ld_wait();
-                    if (live) {
-                        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(xin + c0));
-                        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(xin + c0 + 8));
-                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                        uint32_t packed[8];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-                            const float2 bo2 = __ldg(reinterpret_cast<const float2*>(a.bo + c0 + 2 * i));
-                            const float o0 = ((v[2 * i] + bo2.x) + __low2float(rv)) * kSqrtHalf;
-                            const float o1 = ((v[2 * i + 1] + bo2.y) + __high2float(rv)) * kSqrtHalf;
-                            packed[i] = pack_bf16x2(o0, o1);
+                for (int jc = 0; jc < 16; ++jc) {
+                    const int c0 = jc * 16;
+                    if (c0 < a.R) {
+                        float v[16];
+                        tmem_ld16(tmem_acc2 + lane_base + c0, v);
+                        float bo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bo[i]) = *reinterpret_cast<const float4*>(sb_bo + c0 + i);
+                        tmem_ld_wait();
+                        if (live) {
+                            const uint4 r0 = res[2 * jc], r1 = res[2 * jc + 1];
+                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                            uint32_t packed[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                                const float o0 = ((v[2 * i] + bo[2 * i]) + __low2float(rv)) * kSqrtHalf;
+                                const float o1 = ((v[2 * i + 1] + bo[2 * i + 1]) + __high2float(rv)) * kSqrtHalf;
+                                packed[i] = pack_bf16x2(o0, o1);
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(xout + c0);
+                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
                         }
-                        uint4* dst = reinterpret_cast<uint4*>(xout + c0);
-                        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
                     }
                 }
                 tc_fence_before();
@@ -895,7 +918,7 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     }
 
     // ---- layers ----
-    const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 256;
+    const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 128 + 1024;
     WAE_REQUIRE(smem_layer <= 232448, "wae_stack_forward_bf16: layer kernel shared memory %zu too large", smem_layer);
     WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
 

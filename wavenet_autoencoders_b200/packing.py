@@ -206,8 +206,14 @@ def pack_ar(wn, cluster: int = 8, wtype: str = "bf16", utts_per_cluster: int = 2
     w4 = folded_weight(l3).float()[:, :, 0]
     chunks, offs, off = [], [], 0
 
-    def add(mat: torch.Tensor):
+    def add(mat: torch.Tensor, lanes: int):
+        """mat [rows][K] -> [K/(2*lanes)][rows][2*lanes]: `lanes` lanes share one row in the AR kernel's mat-vecs, and
+        the 32 lanes of a warp then read 32 consecutive words of shared memory."""
         nonlocal off
+        rows, K = mat.shape
+        ch = 2 * lanes
+        assert K % ch == 0
+        mat = mat.reshape(rows, K // ch, ch).permute(1, 0, 2)
         raw = mat.to(dt).contiguous().view(torch.uint8).flatten()
         n = raw.numel()
         pad = (-n) % 16
@@ -222,16 +228,16 @@ def pack_ar(wn, cluster: int = 8, wtype: str = "bf16", utts_per_cluster: int = 2
         for r in range(cluster):                                             # stage 2l
             p0, p1 = part(H, r, cluster), part(H, r + 1, cluster)
             rows = torch.stack([w1[p0:p1], w1[H + p0:H + p1]], dim=1).reshape(-1, w1.shape[1])  # a_p, b_p interleaved
-            add(rows)
+            add(rows, 8)
         wo = torch.nn.functional.pad(m["wo"], (0, Hp - H))
         ws = torch.nn.functional.pad(m["ws"], (0, Hp - H))
         for r in range(cluster):                                             # stage 2l+1
             add(torch.cat([wo[part(sh.R, r, cluster):part(sh.R, r + 1, cluster)],
-                           ws[part(sh.S, r, cluster):part(sh.S, r + 1, cluster)]], 0))
+                           ws[part(sh.S, r, cluster):part(sh.S, r + 1, cluster)]], 0), 4)
     for r in range(cluster):
-        add(w3[part(sh.S, r, cluster):part(sh.S, r + 1, cluster)])
+        add(w3[part(sh.S, r, cluster):part(sh.S, r + 1, cluster)], 8)
     for r in range(cluster):
-        add(w4[part(sh.O, r, cluster):part(sh.O, r + 1, cluster)])
+        add(w4[part(sh.O, r, cluster):part(sh.O, r + 1, cluster)], 8)
     p = Packed()
     p.shape = sh
     t = p.t
