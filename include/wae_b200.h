@@ -144,8 +144,9 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
                            int B, int T, float* logits, void* workspace, size_t workspace_bytes,
                            void* stream);
 
-/* Tuning knob of the bf16 stack: CTAs per cluster of the residual-layer kernel (1, 2 or 4; default 2).  The CTAs of a
- * cluster share every weight k-block through TMA multicast, which divides the L2->SM weight traffic by that factor. */
+/* Variant of the bf16 residual-layer kernel: 0 (default) = CTA-pair kernel (tcgen05 cta_group::2, M = 256 per MMA, each CTA
+ * holds half of every weight k-block); 1, 2 or 4 = the 1-CTA kernel in clusters of that size, the CTAs of a cluster sharing
+ * every weight k-block through TMA multicast. */
 int wae_set_layer_cluster(int cs);
 
 /* Per-kernel-class device timing of wae_stack_forward_bf16 (CUDA events on the launching stream; used by bench.py
@@ -169,7 +170,7 @@ int wae_gemm_bf16_tn(const void* A, const void* B, float* Cout, int M, int N, in
  * CTAs of a thread-block cluster (balanced contiguous ranges: rank r owns rows [n*r/cs, n*(r+1)/cs)),
  * and every rank streams only its own rows, so the host packs one contiguous blob per (stage, rank)
  * (packing.py:pack_ar), reduction dim padded to a multiple of 64 and stored chunk-major: a [rows][K] slice is laid out
- * [K/c][rows][c] with c = 16 (8 lanes share a row) for stages 2l, 2L, 2L+1 and c = 8 (4 lanes per row) for stage 2l+1:
+ * [K/c][rows][c] with c = 32 (8 lanes x 4 elements share a row) for stages 2l, 2L, 2L+1 and c = 16 (4 lanes) for stage 2l+1:
  *   stage 2l   : gate rows of rank r, interleaved (tanh row p, sigmoid row p) for its pairs p   [2*np][K1p]
  *   stage 2l+1 : conv1x1_out rows then conv1x1_skip rows of rank r                              [nres+nsk][Hp]
  *   stage 2L   : last_conv_layers[1] rows of rank r  [nsk][S]      stage 2L+1: last_conv_layers[3] rows  [nout][S]
@@ -180,7 +181,7 @@ int wae_gemm_bf16_tn(const void* A, const void* B, float* Cout, int M, int N, in
 typedef struct wae_ar_weights {
     wae_stack_dims d;
     int32_t wtype, cluster;
-    int32_t utts_per_cluster;   /* 1 or 2 utterances share one cluster (and one pass over the weights) */
+    int32_t utts_per_cluster;   /* 1, 2 or 4 utterances share one cluster (and one pass over the weights) */
     int32_t reserved;
     const void* blob;
     const int64_t* layer_off;

@@ -132,7 +132,7 @@ def test_packing_layouts(cfg_name):
         n = 2 * (p1 - p0) * K1p
         raw = blob[offs[2 * (L - 1), r]: offs[2 * (L - 1), r] + n * (4 if wt == "fp32" else 2)]
         rows = (raw.view(torch.float32) if wt == "fp32" else raw.view(torch.bfloat16).float()).numpy()
-        rows = rows.reshape(K1p // 16, 2 * (p1 - p0), 16).transpose(1, 0, 2).reshape(-1, K1p)   # undo [K/16][rows][16]
+        rows = rows.reshape(K1p // 32, 2 * (p1 - p0), 32).transpose(1, 0, 2).reshape(-1, K1p)   # undo [K/32][rows][32]
         np.testing.assert_allclose(rows[0, :R], lay["w"][p0, :, 0], rtol=1e-2)            # tanh row of first pair, oldest tap
         np.testing.assert_allclose(rows[1, :R], lay["w"][H + p0, :, 0], rtol=1e-2)        # its sigmoid partner
     # cache invalidation: an in-place parameter update changes the fingerprint

@@ -70,6 +70,19 @@ template <> struct WLoad<__nv_bfloat16> {
     }
 };
 
+template <typename WT> struct WLoad4;
+template <> struct WLoad4<float> {
+    static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
+};
+template <> struct WLoad4<__nv_bfloat16> {
+    static __device__ __forceinline__ float4 ld(const __nv_bfloat16* p) {
+        const uint2 raw = *reinterpret_cast<const uint2*>(p);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+    }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             // ---- GEMV1: gate pre-activations of this rank's pairs ----
             // 8 lanes share one weight row (each walks K/8 elements, 3 shuffle steps finish the dot product), so a warp
             // finishes 4 rows = 2 (tanh, sigmoid) pairs per pass with 4x fewer dependent shuffle chains than a
-            // 32-lane-per-row split.  Weights are packed [K/16][row][16] so the 32 lanes of a warp read 32
+            // 32-lane-per-row split.  Weights are packed [K/32][row][32] (4 elements per lane) so the 32 lanes of a warp read 32
             // consecutive words of shared memory (conflict free); the input vector is a broadcast read.
             AR_PROF(1);
             mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
@@ -388,27 +401,29 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 for (int r0 = warp * 4; r0 < rows1; r0 += AR_WARPS * 4) {
                     const int row = r0 + grp;
                     const bool rvalid = row < rows1;
-                    const WT* wrow = w1s + (size_t)(rvalid ? row : 0) * 16 + s8 * 2;
-                    float acc[U][2];
+                    const WT* wrow = w1s + (size_t)(rvalid ? row : 0) * 32 + s8 * 4;
+                    float acc[U][4];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+                    for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; acc[u][2] = 0.f; acc[u][3] = 0.f; }
 #pragma unroll 4
-                    for (int m = 0; m < nm1 * 4; ++m) {                      // K1p / 16 chunks
-                        const int k = m * 16 + s8 * 2;
-                        const float2 w = WLoad<WT>::ld2(wrow + (size_t)m * rows1 * 16, 0);
+                    for (int m = 0; m < nm1 * 2; ++m) {                      // K1p / 32 chunks, 4 elements per lane
+                        const int k = m * 32 + s8 * 4;
+                        const float4 w = WLoad4<WT>::ld(wrow + (size_t)m * rows1 * 32);
                         const float* xs = (k < KX) ? (xl + k) : (cl + (k - KX));
                         const int xstride = (k < KX) ? KX : Cp;
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            const float2 xv = *reinterpret_cast<const float2*>(xs + (size_t)u * xstride);
+                            const float4 xv = *reinterpret_cast<const float4*>(xs + (size_t)u * xstride);
                             acc[u][0] = fmaf(w.x, xv.x, acc[u][0]);
                             acc[u][1] = fmaf(w.y, xv.y, acc[u][1]);
+                            acc[u][2] = fmaf(w.z, xv.z, acc[u][2]);
+                            acc[u][3] = fmaf(w.w, xv.w, acc[u][3]);
                         }
                     }
                     const int j = row >> 1;   // pair index within the slice
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        float z = acc[u][0] + acc[u][1];
+                        float z = (acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3]);
                         z += __shfl_xor_sync(0xffffffffu, z, 4);
                         z += __shfl_xor_sync(0xffffffffu, z, 2);
                         z += __shfl_xor_sync(0xffffffffu, z, 1);
@@ -445,23 +460,25 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                 for (int r0 = warp * 8; r0 < n2; r0 += AR_WARPS * 8) {
                     const int i = r0 + grp;
                     const bool rvalid = i < n2;
-                    const WT* wrow = w2s + (size_t)(rvalid ? i : 0) * 8 + s4 * 2;
-                    float acc[U][2];
+                    const WT* wrow = w2s + (size_t)(rvalid ? i : 0) * 16 + s4 * 4;
+                    float acc[U][4];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+                    for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; acc[u][2] = 0.f; acc[u][3] = 0.f; }
 #pragma unroll 4
-                    for (int m = 0; m < nm2 * 8; ++m) {                      // Hp / 8 chunks
-                        const float2 w = WLoad<WT>::ld2(wrow + (size_t)m * n2 * 8, 0);
+                    for (int m = 0; m < nm2 * 4; ++m) {                      // Hp / 16 chunks
+                        const float4 w = WLoad4<WT>::ld(wrow + (size_t)m * n2 * 16);
 #pragma unroll
                         for (int u = 0; u < U; ++u) {
-                            const float2 hv = *reinterpret_cast<const float2*>(hbuf + (size_t)u * Hp + m * 8 + s4 * 2);
+                            const float4 hv = *reinterpret_cast<const float4*>(hbuf + (size_t)u * Hp + m * 16 + s4 * 4);
                             acc[u][0] = fmaf(w.x, hv.x, acc[u][0]);
                             acc[u][1] = fmaf(w.y, hv.y, acc[u][1]);
+                            acc[u][2] = fmaf(w.z, hv.z, acc[u][2]);
+                            acc[u][3] = fmaf(w.w, hv.w, acc[u][3]);
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        float o = acc[u][0] + acc[u][1];
+                        float o = (acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3]);
                         o += __shfl_xor_sync(0xffffffffu, o, 2);
                         o += __shfl_xor_sync(0xffffffffu, o, 1);
                         if (rvalid && s4 == 0) {
@@ -513,30 +530,32 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
-        // the two 1x1 convolutions of the head: 8 lanes per row, weights packed [S/16][row][16]
+        // the two 1x1 convolutions of the head: 8 lanes per row, weights packed [S/32][row][32]
         auto head_gemv = [&](const float* src, int nrows, const float* bias, bool relu) {
             const WT* ws_ = reinterpret_cast<const WT*>(w2buf + (size_t)(j2 & 1) * sl.w2_slot);
             const int grp = lane >> 3, s8 = lane & 7;
             for (int r0 = warp * 4; r0 < nrows; r0 += AR_WARPS * 4) {
                 const int i = r0 + grp;
                 const bool rvalid = i < nrows;
-                const WT* wrow = ws_ + (size_t)(rvalid ? i : 0) * 16 + s8 * 2;
-                float acc[U][2];
+                const WT* wrow = ws_ + (size_t)(rvalid ? i : 0) * 32 + s8 * 4;
+                float acc[U][4];
 #pragma unroll
-                for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; }
+                for (int u = 0; u < U; ++u) { acc[u][0] = 0.f; acc[u][1] = 0.f; acc[u][2] = 0.f; acc[u][3] = 0.f; }
 #pragma unroll 4
-                for (int m = 0; m < nms * 4; ++m) {
-                    const float2 w = WLoad<WT>::ld2(wrow + (size_t)m * nrows * 16, 0);
+                for (int m = 0; m < nms * 2; ++m) {
+                    const float4 w = WLoad4<WT>::ld(wrow + (size_t)m * nrows * 32);
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
-                        const float2 sv = *reinterpret_cast<const float2*>(src + (size_t)u * S + m * 16 + s8 * 2);
+                        const float4 sv = *reinterpret_cast<const float4*>(src + (size_t)u * S + m * 32 + s8 * 4);
                         acc[u][0] = fmaf(w.x, sv.x, acc[u][0]);
                         acc[u][1] = fmaf(w.y, sv.y, acc[u][1]);
+                        acc[u][2] = fmaf(w.z, sv.z, acc[u][2]);
+                        acc[u][3] = fmaf(w.w, sv.w, acc[u][3]);
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    float v = acc[u][0] + acc[u][1];
+                    float v = (acc[u][0] + acc[u][1]) + (acc[u][2] + acc[u][3]);
                     v += __shfl_xor_sync(0xffffffffu, v, 4);
                     v += __shfl_xor_sync(0xffffffffu, v, 2);
                     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -742,7 +761,8 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
                 "wae_ar_generate: need %d <= layers <= %d", NPF, WAE_MAX_LAYERS);
     WAE_REQUIRE(w->cluster == 8 || w->cluster == 16 || w->cluster == 4 || w->cluster == 2 || w->cluster == 1,
                 "wae_ar_generate: cluster must be 1,2,4,8 or 16 (got %d)", w->cluster);
-    WAE_REQUIRE(w->utts_per_cluster == 1 || w->utts_per_cluster == 2, "wae_ar_generate: utts_per_cluster must be 1 or 2");
+    WAE_REQUIRE(w->utts_per_cluster == 1 || w->utts_per_cluster == 2 || w->utts_per_cluster == 4,
+                "wae_ar_generate: utts_per_cluster must be 1, 2 or 4");
     WAE_REQUIRE(d.R % 64 == 0 && d.S % 64 == 0 && d.S <= 64 * MAXMS && d.G % 2 == 0,
                 "wae_ar_generate: need R%%64==0, S%%64==0, S<=256 (R=%d S=%d)", d.R, d.S);
     WAE_REQUIRE(d.C % 4 == 0, "wae_ar_generate: C%%4 != 0");
@@ -803,9 +823,11 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
     const int clusters = (B + U - 1) / U;
     if (w->wtype == 0) {
         if (U == 1) return launch_ar<float, 1>(a, clusters, sl.total, stream);
+        if (U == 4) return launch_ar<float, 4>(a, clusters, sl.total, stream);
         return launch_ar<float, 2>(a, clusters, sl.total, stream);
     } else {
         if (U == 1) return launch_ar<__nv_bfloat16, 1>(a, clusters, sl.total, stream);
+        if (U == 4) return launch_ar<__nv_bfloat16, 4>(a, clusters, sl.total, stream);
         return launch_ar<__nv_bfloat16, 2>(a, clusters, sl.total, stream);
     }
 }

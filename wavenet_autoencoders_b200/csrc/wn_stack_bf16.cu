@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t hbuf_addr = smem_u32(hbuf);
         // conv1x1_out bias: staged once in shared memory (broadcast reads instead of per-chunk global loads)
-        float* sb_bo = reinterpret_cast<float*>(bars) + 32;   // bars region is 128 B, then 256 floats
+        float* sb_bo = reinterpret_cast<float*>(bars) + 64;   // barriers + tmem slot live in the first 256 B, then 256 floats
         for (int i = threadIdx.x - 64; i < a.R; i += 128) sb_bo[i] = __ldg(a.bo + i);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         int it = 0;
@@ -561,6 +561,257 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
     __syncthreads();
     if (cs > 1) cluster_sync();   // no CTA retires while a peer may still multicast into it or arrive on its barriers
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused residual layer on CTA PAIRS (tcgen05 cta_group::2)
+// ---------------------------------------------------------------------------------------------
+// Same maths and the same warp roles as layer_bf16_kernel, but two CTAs (one cluster of 2 = one TPC) execute every
+// MMA together: M = 256 samples (128 per CTA), and each CTA holds only HALF of every weight k-block (N/2 rows) in its
+// shared memory.  Measurements of the 1-CTA kernel (profiles/) showed it bound by shared-memory traffic -- every
+// 128x256x16 MMA reads 12 KB of operands while TMA writes another 12 KB -- not by L2 (weight multicast did not
+// help); the pair halves the B-operand bytes per CTA (32 KB instead of 48 KB per k-block written, and read), and
+// the smaller stages allow a 6-deep TMA ring in the same 192 KB.
+//   * TMA: each CTA loads its own A tile and its half of B; all transaction bytes are signalled on the LEADER's
+//     full barrier (the MMA issuer lives there).
+//   * MMA: one thread of the leader issues tcgen05.mma.cta_group::2; tcgen05.commit multicasts stage-release and
+//     accumulator-ready arrivals to both CTAs.
+//   * epilogues run per CTA on its own 128 TMEM lanes; "done" arrivals go to the leader's barriers (256 arrivals).
+constexpr int PAIR_STAGES = 6;
+constexpr int PAIR_B_BYTES = 128 * BK * 2;   // half of an N = 256 weight k-block
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_pair_kernel(const __grid_constant__ LayerArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int H = a.G / 2;
+    const int STAGE_BYTES = A_TILE_BYTES + PAIR_B_BYTES;
+    uint8_t* hbuf = smem + PAIR_STAGES * STAGE_BYTES;
+    const int nkh = a.Hp / BK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hbuf + nkh * A_TILE_BYTES);
+    uint64_t* full = bars;                       // [PAIR_STAGES]  used in the leader only
+    uint64_t* empty = bars + PAIR_STAGES;        // [PAIR_STAGES]  one per CTA (commit is multicast)
+    uint64_t* acc1_full = bars + 2 * PAIR_STAGES;
+    uint64_t* epi1_done = acc1_full + 1;         // leader only, 256 arrivals
+    uint64_t* acc2_full = acc1_full + 2;
+    uint64_t* epi2_done = acc1_full + 3;         // leader only, 256 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = (int)cluster_ctarank();    // 0 = leader
+    const bool leader = (crank == 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PAIR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc1_full, 1);
+        mbar_init(epi1_done, 256);
+        mbar_init(acc2_full, 1);
+        mbar_init(epi2_done, 256);
+        fence_mbar_init();
+        tma_prefetch_desc(&a.tm_x);
+        tma_prefetch_desc(&a.tm_c);
+        tma_prefetch_desc(&a.tm_w1);
+        tma_prefetch_desc(&a.tm_wo);
+    }
+    if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc1 = tmem_base;        // columns [0, G)
+    const uint32_t tmem_acc2 = tmem_base + 256;  // columns [256, 256+R)
+
+    const int ntiles = a.B * a.tiles_per_utt;
+    const int nsuper = (ntiles + 1) / 2;
+    const int ncluster = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+    const int nk_taps = a.kw * (a.R / BK);
+    const int nk_c = a.Cp / BK;
+    const bool has_out = (a.x_out != nullptr);
+    const int w1_rows = a.G / 2, wo_rows = a.R / 2;       // weight rows held by this CTA
+    const uint32_t w1_half = (uint32_t)w1_rows * BK * 2, wo_half = (uint32_t)wo_rows * BK * 2;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (elect_one()) {
+            Ring ring(PAIR_STAGES);
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster) {
+                const int tile = sup * 2 + crank;
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
+                int kcol = 0;
+                for (int kb = 0; kb < nk_taps + nk_c; ++kb, kcol += BK) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
+                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + w1_half));
+                    if (kb < nk_taps) {
+                        const int tap = kb / (a.R / BK), r0 = (kb % (a.R / BK)) * BK;
+                        tma_load_3d_2cta(&a.tm_x, fb, sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
+                    } else {
+                        tma_load_3d_2cta(&a.tm_c, fb, sa, (kb - nk_taps) * BK, t0, b);
+                    }
+                    tma_load_3d_2cta(&a.tm_w1, fb, sa + A_TILE_BYTES, kcol, crank * w1_rows, a.layer);
+                    ring.advance();
+                }
+                if (has_out) {
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                        uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                        const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
+                        if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * wo_half);
+                        tma_load_3d_2cta(&a.tm_wo, fb, sa + A_TILE_BYTES, kb * BK, crank * wo_rows, a.layer);
+                        ring.advance();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && elect_one()) {
+            Ring ring(PAIR_STAGES);
+            const uint32_t idesc1 = umma_idesc_bf16(2 * BM, a.G);
+            const uint32_t idesc2 = umma_idesc_bf16(2 * BM, a.R);
+            int it = 0;
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+                if (!has_out && it > 0) { mbar_wait_cluster(epi1_done, (it - 1) & 1); tc_fence_after(); }
+                for (int kb = 0; kb < nk_taps + nk_c; ++kb) {
+                    mbar_wait_cluster(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_2cta(tmem_acc1, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc1, (kb == 0 && k == 0) ? 0u : 1u);
+                    umma_commit_2cta(&empty[ring.stage], 3);
+                    ring.advance();
+                }
+                umma_commit_2cta(acc1_full, 3);
+                if (has_out) {
+                    mbar_wait_cluster(epi1_done, it & 1);  // h of BOTH CTAs is in shared memory, acc1 drained
+                    tc_fence_after();
+                    if (it > 0) { mbar_wait_cluster(epi2_done, (it - 1) & 1); tc_fence_after(); }
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait_cluster(&full[ring.stage], ring.phase);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                        const uint64_t ad = umma_desc_sw128(smem_u32(hbuf + kb * A_TILE_BYTES)), bd = umma_desc_sw128(sb);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_2cta(tmem_acc2, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc2, (kb == 0 && k == 0) ? 0u : 1u);
+                        umma_commit_2cta(&empty[ring.stage], 3);
+                        ring.advance();
+                    }
+                    umma_commit_2cta(acc2_full, 3);
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps (both CTAs, own 128 TMEM lanes) =================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t hbuf_addr = smem_u32(hbuf);
+        const uint32_t epi1_remote = mapa(smem_u32(epi1_done), 0), epi2_remote = mapa(smem_u32(epi2_done), 0);
+        float* sb_bo = reinterpret_cast<float*>(bars) + 64;   // barriers + tmem slot live in the first 256 B
+        for (int i = threadIdx.x - 64; i < a.R; i += 128) sb_bo[i] = __ldg(a.bo + i);
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        int it = 0;
+        for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+            const int tile = sup * 2 + crank;
+            const bool tile_ok = (tile < ntiles);
+            const int b = tile_ok ? tile / a.tiles_per_utt : 0, t0 = (tile % a.tiles_per_utt) * BM;
+            const int t = t0 + row;
+            const bool live = tile_ok && (t < a.T);
+            const float* gbp = a.gb + (size_t)b * a.G;
+            __nv_bfloat16* hrow = a.h_out + ((size_t)b * a.T + t) * a.Hp;
+
+            uint4 res[32];
+            if (has_out && live) {
+                const uint4* xin = reinterpret_cast<const uint4*>(a.x_in + ((size_t)b * a.T + t) * a.R);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (j * 8 < a.R) res[j] = __ldg(xin + j);
+            }
+
+            // ---- EPI1: gate ----
+            mbar_wait(acc1_full, it & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < a.Hp; c0 += 16) {
+                uint32_t packed[8];
+                if (c0 < H) {
+                    float va[16], vb[16];
+                    tmem_ld16(tmem_acc1 + lane_base + c0, va);
+                    tmem_ld16(tmem_acc1 + lane_base + H + c0, vb);
+                    float ba[16], bb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
+                        *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + H + c0 + i));
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
+                        const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
+                        packed[i >> 1] = pack_bf16x2(h0, h1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = 0u;
+                }
+                const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                const uint32_t base = hbuf_addr + kb * A_TILE_BYTES;
+                st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+                if (live) {
+                    uint4* dst = reinterpret_cast<uint4*>(hrow + c0);
+                    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive_cluster(epi1_remote);
+
+            // ---- EPI2: residual ----
+            if (has_out) {
+                mbar_wait(acc2_full, it & 1);
+                tc_fence_after();
+                __nv_bfloat16* xout = a.x_out + ((size_t)b * a.T + t) * a.R;
+#pragma unroll
+                for (int jc = 0; jc < 16; ++jc) {
+                    const int c0 = jc * 16;
+                    if (c0 < a.R) {
+                        float v[16];
+                        tmem_ld16(tmem_acc2 + lane_base + c0, v);
+                        float bo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bo[i]) = *reinterpret_cast<const float4*>(sb_bo + c0 + i);
+                        tmem_ld_wait();
+                        if (live) {
+                            const uint4 r0 = res[2 * jc], r1 = res[2 * jc + 1];
+                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                            uint32_t packed[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                                const float o0 = ((v[2 * i] + bo[2 * i]) + __low2float(rv)) * kSqrtHalf;
+                                const float o1 = ((v[2 * i + 1] + bo[2 * i + 1]) + __high2float(rv)) * kSqrtHalf;
+                                packed[i] = pack_bf16x2(o0, o1);
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(xout + c0);
+                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(epi2_remote);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 1) tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -783,7 +1034,8 @@ struct Profiler {
     }
 };
 Profiler g_prof;
-int g_layer_cluster = 2;   // wae_set_layer_cluster(): 1, 2 or 4 CTAs share every weight k-block via TMA multicast
+int g_layer_mode = 0;      // 0 = CTA-pair kernel (tcgen05 cta_group::2), 1 = 1-CTA kernel (wae_set_layer_cluster)
+int g_layer_cluster = 1;   // 1-CTA kernel only: 1, 2 or 4 CTAs share every weight k-block via TMA multicast
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a, b; bool on;
     ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(g_prof.on) {
@@ -841,7 +1093,9 @@ int wae_gemm_bf16_tn(const void* A, const void* Bm, float* Cout, int M, int N, i
 void wae_profile_enable(int on) { g_prof.on = (on != 0); }
 
 int wae_set_layer_cluster(int cs) {
-    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be 1, 2 or 4");
+    if (cs == 0) { g_layer_mode = 0; return WAE_OK; }     // CTA-pair kernel
+    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be 0, 1, 2 or 4");
+    g_layer_mode = 1;
     g_layer_cluster = cs;
     return WAE_OK;
 }
@@ -918,7 +1172,7 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     }
 
     // ---- layers ----
-    const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 128 + 1024;
+    const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 256 + 1024;
     WAE_REQUIRE(smem_layer <= 232448, "wae_stack_forward_bf16: layer kernel shared memory %zu too large", smem_layer);
     WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
 
@@ -931,9 +1185,10 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     } else {
         la.tm_c = tm_xa;  // never used (nk_c == 0)
     }
-    // cluster size of the layer kernel: weight k-blocks are fetched once per cluster and multicast (see kernel comment)
-    int cs = g_layer_cluster;
-    while (cs > 1 && (d.G % (8 * cs) != 0 || d.R % (8 * cs) != 0 || num_sms() / cs < 1)) cs >>= 1;
+    // Layer-kernel variant: CTA pairs (cta_group::2, default) or the 1-CTA kernel in clusters of 1/2/4 with weight multicast.
+    const bool pair = (g_layer_mode == 0) && d.G % 32 == 0 && d.R % 32 == 0;
+    int cs = pair ? 2 : g_layer_cluster;
+    while (!pair && cs > 1 && (d.G % (8 * cs) != 0 || d.R % (8 * cs) != 0)) cs >>= 1;
     if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, d.G, d.layers, K1p, (uint64_t)d.G * K1p, BK, d.G / cs)) return rc;
     if (int rc = make_tmap(&la.tm_wo, w->wo, Hp, d.R, d.layers, Hp, (uint64_t)d.R * Hp, BK, d.R / cs)) return rc;
     const int nsuper = (ntiles + cs - 1) / cs;
@@ -941,6 +1196,8 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     if (cs == 4) nclusters = 33;   // 132 SMs: 4-CTA clusters cannot use all 148 (GPC granularity); more would queue a 2nd wave
     if (nclusters > nsuper) nclusters = nsuper;
     const int grid_layer = nclusters * cs;
+    if (pair)
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
     la.B = B; la.T = T; la.R = d.R; la.G = d.G; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
     la.tiles_per_utt = tiles_per_utt;
     __nv_bfloat16* cur = ws.xa;
@@ -968,7 +1225,8 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_kernel, la));
+            if (pair) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair_kernel, la));
+            else WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_kernel, la));
         }
         WAE_CHECK_LAUNCH();
         __nv_bfloat16* t = cur; cur = nxt; nxt = t;

@@ -207,11 +207,11 @@ def pack_ar(wn, cluster: int = 8, wtype: str = "bf16", utts_per_cluster: int = 2
     chunks, offs, off = [], [], 0
 
     def add(mat: torch.Tensor, lanes: int):
-        """mat [rows][K] -> [K/(2*lanes)][rows][2*lanes]: `lanes` lanes share one row in the AR kernel's mat-vecs, and
-        the 32 lanes of a warp then read 32 consecutive words of shared memory."""
+        """mat [rows][K] -> [K/(4*lanes)][rows][4*lanes]: `lanes` lanes share one row in the AR kernel's mat-vecs (4
+        consecutive elements per lane), so the 32 lanes of a warp read one contiguous run of shared memory."""
         nonlocal off
         rows, K = mat.shape
-        ch = 2 * lanes
+        ch = 4 * lanes
         assert K % ch == 0
         mat = mat.reshape(rows, K // ch, ch).permute(1, 0, 2)
         raw = mat.to(dt).contiguous().view(torch.uint8).flatten()
