@@ -148,6 +148,8 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
  * holds half of every weight k-block); 1, 2 or 4 = the 1-CTA kernel in clusters of that size, the CTAs of a cluster sharing
  * every weight k-block through TMA multicast. */
 int wae_set_layer_cluster(int cs);
+/* Debug: per-CTA cycle counters of the 1-CTA residual-layer kernel's three roles (16 int64 per CTA), or NULL to disable. */
+void wae_layer_set_profile_buffer(int64_t* dev_buf);
 
 /* Per-kernel-class device timing of wae_stack_forward_bf16 (CUDA events on the launching stream; used by bench.py
  * for the roofline of the dominant kernel).  Kinds: 0 = prep kernels, 1 = residual-layer kernels, 2 = head kernel.

@@ -1,0 +1,27 @@
+"""Role-level cycle breakdown of layer_bf16_kernel (1-CTA variant). GPU box only."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import bench
+from wavenet_autoencoders_b200 import _lib
+L = _lib.lib()
+m = bench.build_vqvae("cuda"); m.wavenet.precision = "bf16"
+idx, mfcc, g = bench.synth_batch(16, 1000)
+idx, mfcc, g = idx.cuda(), mfcc.cuda(), g.cuda()
+x = torch.nn.functional.one_hot(idx, 256).float().transpose(1, 2).contiguous()
+_lib.check(L.wae_set_layer_cluster(1), "mode")
+with torch.no_grad():
+    for _ in range(2):
+        m(x, mfcc, g)
+    buf = torch.zeros(148 * 16, dtype=torch.int64, device="cuda")
+    L.wae_layer_set_profile_buffer(buf.data_ptr())
+    m(x, mfcc, g)          # the buffer holds the LAST layer launched that has GEMM2?  (every launch overwrites) -> last layer
+    torch.cuda.synchronize()
+    L.wae_layer_set_profile_buffer(None)
+p = buf.view(148, 16).double().cpu()
+names = ["prod wait-empty", "prod total", "mma wait-full", "mma wait-epi1", "mma wait-epi2", "mma issue", "mma total", "tiles",
+         "epi wait-acc1", "epi E1", "epi wait-acc2", "epi E2", "epi prefetch", "epi total"]
+tiles = p[:, 7].clamp(min=1)
+print("counters of layer 5 (dilation 32), cycles")
+for i, n in enumerate(names):
+    print(f"{n:18s} mean {p[:, i].mean().item():10.0f}  per tile {(p[:, i] / tiles).mean().item():9.0f}")

@@ -69,6 +69,7 @@ SIGNATURES = {
     "wae_stack_forward_bf16": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "wae_set_layer_cluster": (C.c_int, [C.c_int]),
+    "wae_layer_set_profile_buffer": (None, [C.c_void_p]),
     "wae_profile_enable": (None, [C.c_int]),
     "wae_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wae_gemm_bf16_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

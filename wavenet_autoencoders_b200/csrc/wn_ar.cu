@@ -592,16 +592,18 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             const float* lg = lgbuf + (size_t)u * O;
             if (a.sample_mode == WAE_AR_SAMPLE_CATEGORICAL || a.sample_mode == WAE_AR_SAMPLE_NONE) {
                 // softmax over O classes; lane owns classes lane*per .. (contiguous chunk)
-                const int per = (O + 31) / 32;
+                const int per = (O + 31) / 32;          // <= 8 (O <= 256); loops below are fully unrolled so ex[] stays in registers
                 float mx = -INFINITY;
-                for (int i = 0; i < per; ++i) { const int o = lane * per + i; if (o < O) mx = fmaxf(mx, lg[o]); }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const int o = lane * per + i; if (i < per && o < O) mx = fmaxf(mx, lg[o]); }
                 mx = warp_max(mx);
                 float ex[8];
                 float loc = 0.f;
-                for (int i = 0; i < per && i < 8; ++i) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
                     const int o = lane * per + i;
-                    ex[i] = (o < O) ? expf(lg[o] - mx) : 0.f;
-                    loc += ex[i];   // sequential within the lane
+                    ex[i] = (i < per && o < O) ? expf(lg[o] - mx) : 0.f;
+                    if (i < per) loc += ex[i];   // sequential within the lane
                 }
                 // inclusive Kogge-Stone scan of the lane totals (order mirrored by oracle/sampling.py)
                 float inc = loc;
@@ -617,10 +619,13 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                     // first class whose inclusive cumulative mass exceeds thr
                     float run = inc - loc;
                     int pick = 0x7fffffff;
-                    for (int i = 0; i < per && i < 8; ++i) {
-                        run += ex[i];
-                        const int o = lane * per + i;
-                        if (o < O && run > thr && pick == 0x7fffffff) pick = o;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        if (i < per) {
+                            run += ex[i];
+                            const int o = lane * per + i;
+                            if (o < O && run > thr && pick == 0x7fffffff) pick = o;
+                        }
                     }
                     pick = __reduce_min_sync(0xffffffffu, pick);
                     if (pick == 0x7fffffff) pick = O - 1;
@@ -630,9 +635,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                     }
                 } else {
                     const float inv = 1.f / total;
-                    for (int i = 0; i < per && i < 8; ++i) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
                         const int o = lane * per + i;
-                        if (o < O) {
+                        if (i < per && o < O) {
                             const float v = a.apply_softmax ? ex[i] * inv : lg[o];
                             inbuf[u * Oin + (Oin == O ? o : 0)] = v;   // fed back as the next dense input
                             if (writer && a.out_dense) a.out_dense[((size_t)b * a.T + t) * O + o] = v;

@@ -309,7 +309,11 @@ struct LayerArgs {
     __nv_bfloat16* x_out;        // [B][T][R] or null (last layer: residual output is dead)
     __nv_bfloat16* h_out;        // [B][T][Hp] plane of this layer
     int B, T, R, G, Hp, Cp, kw, dil, layer, tiles_per_utt;
+    long long* prof;     // optional [gridDim.x][16] cycle counters (debug), or null
 };
+
+#define LPROF_BEGIN() long long _pt = clock64()
+#define LPROF(acc) do { const long long _n = clock64(); (acc) += _n - _pt; _pt = _n; } while (0)
 
 constexpr int LAYER_STAGES = 4;
 
@@ -377,12 +381,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
         // ================= TMA producer =================
         if (elect_one()) {
             Ring ring(LAYER_STAGES);
+            long long p_wait = 0, p_tot = 0; const long long p_t0 = clock64(); LPROF_BEGIN();
             for (int sup = cluster_id; sup < nsuper; sup += ncluster) {
                 const int tile = sup * cs + crank;
                 const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: TMA zero-fills
                 int kcol = 0;
                 for (int kb = 0; kb < nk_taps + nk_c; ++kb, kcol += BK) {
+                    LPROF(p_tot);
                     mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    LPROF(p_wait);
                     uint8_t* sa = smem + ring.stage * STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + w1_bytes);
                     if (kb < nk_taps) {
@@ -412,6 +419,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                     }
                 }
             }
+            if (a.prof) { a.prof[blockIdx.x * 16 + 0] = p_wait; a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -420,12 +428,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
             const uint32_t idesc1 = umma_idesc_bf16(BM, a.G);
             const uint32_t idesc2 = umma_idesc_bf16(BM, a.R);
             int it = 0;
+            long long m_full = 0, m_e1 = 0, m_e2 = 0, m_iss = 0; const long long m_t0 = clock64(); LPROF_BEGIN();
             for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
                 // acc1 of the previous tile was drained before its GEMM2 was issued (epi1_done wait below),
                 // or -- when there is no GEMM2 -- must be waited for here.
                 if (!has_out && it > 0) { mbar_wait(epi1_done, (it - 1) & 1); tc_fence_after(); }
                 for (int kb = 0; kb < nk_taps + nk_c; ++kb) {
+                    LPROF(m_iss);
                     mbar_wait(&full[ring.stage], ring.phase);
+                    LPROF(m_full);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
                     issue_kblock(tmem_acc1, sa, sa + A_TILE_BYTES, idesc1, kb == 0);
@@ -434,11 +445,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                 }
                 umma_commit(acc1_full);
                 if (has_out) {
+                    LPROF(m_iss);
                     mbar_wait(epi1_done, it & 1);  // h is in shared memory, acc1 drained
+                    LPROF(m_e1);
                     tc_fence_after();
                     if (it > 0) { mbar_wait(epi2_done, (it - 1) & 1); tc_fence_after(); }
+                    LPROF(m_e2);
                     for (int kb = 0; kb < nkh; ++kb) {
+                        LPROF(m_iss);
                         mbar_wait(&full[ring.stage], ring.phase);
+                        LPROF(m_full);
                         tc_fence_after();
                         const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
                         issue_kblock(tmem_acc2, smem_u32(hbuf + kb * A_TILE_BYTES), sb, idesc2, kb == 0);
@@ -447,6 +463,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                     }
                     umma_commit(acc2_full);
                 }
+            }
+            if (a.prof) {
+                a.prof[blockIdx.x * 16 + 2] = m_full; a.prof[blockIdx.x * 16 + 3] = m_e1; a.prof[blockIdx.x * 16 + 4] = m_e2;
+                a.prof[blockIdx.x * 16 + 5] = m_iss; a.prof[blockIdx.x * 16 + 6] = clock64() - m_t0; a.prof[blockIdx.x * 16 + 7] = it;
             }
         }
     } else {
@@ -460,6 +480,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
         for (int i = threadIdx.x - 64; i < a.R; i += 128) sb_bo[i] = __ldg(a.bo + i);
         asm volatile("bar.sync 1, 128;" ::: "memory");
         int it = 0;
+        long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0, e_pre = 0; const long long e_t0 = clock64(); LPROF_BEGIN();
         for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
             const int tile = sup * cs + crank;
             const bool tile_ok = (tile < ntiles);
@@ -481,7 +502,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
             }
 
             // ---- EPI1: gate ----
+            LPROF(e_pre);
             mbar_wait(acc1_full, it & 1);
+            LPROF(e_w1);
             tc_fence_after();
             for (int c0 = 0; c0 < a.Hp; c0 += 16) {
                 uint32_t packed[8];
@@ -519,10 +542,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
             tc_fence_before();
             fence_proxy_async_smem();  // generic-proxy writes of h -> visible to the tensor-core (async) proxy
             mbar_arrive(epi1_done);
+            LPROF(e_e1);
 
             // ---- EPI2: residual ----
             if (has_out) {
                 mbar_wait(acc2_full, it & 1);
+                LPROF(e_w2);
                 tc_fence_after();
                 __nv_bfloat16* xout = a.x_out + ((size_t)b * a.T + t) * a.R;
 #pragma unroll
@@ -554,7 +579,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                 }
                 tc_fence_before();
                 mbar_arrive(epi2_done);
+                LPROF(e_e2);
             }
+        }
+        if (a.prof && threadIdx.x == 64) {
+            a.prof[blockIdx.x * 16 + 8] = e_w1; a.prof[blockIdx.x * 16 + 9] = e_e1; a.prof[blockIdx.x * 16 + 10] = e_w2;
+            a.prof[blockIdx.x * 16 + 11] = e_e2; a.prof[blockIdx.x * 16 + 12] = e_pre; a.prof[blockIdx.x * 16 + 13] = clock64() - e_t0;
         }
     }
     tc_fence_before();
@@ -1034,6 +1064,7 @@ struct Profiler {
     }
 };
 Profiler g_prof;
+long long* g_layer_prof = nullptr;
 int g_layer_mode = 0;      // 0 = CTA-pair kernel (tcgen05 cta_group::2), 1 = 1-CTA kernel (wae_set_layer_cluster)
 int g_layer_cluster = 1;   // 1-CTA kernel only: 1, 2 or 4 CTAs share every weight k-block via TMA multicast
 struct ProfScope {
@@ -1091,6 +1122,8 @@ int wae_gemm_bf16_tn(const void* A, const void* Bm, float* Cout, int M, int N, i
 }
 
 void wae_profile_enable(int on) { g_prof.on = (on != 0); }
+
+void wae_layer_set_profile_buffer(int64_t* dev_buf) { g_layer_prof = reinterpret_cast<long long*>(dev_buf); }
 
 int wae_set_layer_cluster(int cs) {
     if (cs == 0) { g_layer_mode = 0; return WAE_OK; }     // CTA-pair kernel
@@ -1211,6 +1244,7 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
         la.h_out = ws.hall + (size_t)l * B * T * Hp;
         la.dil = d.dilation[l];
         la.layer = l;
+        la.prof = (l == (d.layers > 5 ? 5 : 0)) ? g_layer_prof : nullptr;   // debug counters of one representative layer
         {
             ProfScope prof(1, stream);
             cudaLaunchConfig_t cfg = {};
