@@ -94,15 +94,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a pipeline bug must never hang the GPU.  ~2^26 polls (seconds) then trap.
+// Bounded wait: a pipeline bug must never hang the GPU.  ~2^26 polls (seconds) then trap.  The report path is kept
+// out of line so that the many wait sites stay a few instructions each (instruction-cache footprint).
+__device__ __noinline__ void mbar_timeout(const void* bar, uint32_t parity) {
+    printf("wae: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > (1u << 26)) {
-            printf("wae: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x,
-                   threadIdx.x, (void*)bar, parity);
-            __trap();
-        }
+        if (++spins > (1u << 26)) mbar_timeout(bar, parity);
     }
 }
 
@@ -299,11 +300,7 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t spins = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if (++spins > (1u << 26)) {
-            printf("wae: cluster mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x,
-                   (void*)bar, parity);
-            __trap();
-        }
+        if (++spins > (1u << 26)) mbar_timeout(bar, parity);
     }
 }
 

@@ -312,10 +312,162 @@ struct LayerArgs {
     long long* prof;     // optional [gridDim.x][16] cycle counters (debug), or null
 };
 
+// role-level cycle counters: compiled in only with -DWAE_LAYER_PROF (WAE_LAYER_PROF=1 python -m ...build); they cost registers
+#ifdef WAE_LAYER_PROF
 #define LPROF_BEGIN() long long _pt = clock64()
 #define LPROF(acc) do { const long long _n = clock64(); (acc) += _n - _pt; _pt = _n; } while (0)
+#define LPROF_ON 1
+#else
+#define LPROF_BEGIN() do { } while (0)
+#define LPROF(acc) do { } while (0)
+#define LPROF_ON 0
+#endif
 
 constexpr int LAYER_STAGES = 4;
+
+// ---------------------------------------------------------------------------------------------
+// epilogue of the residual-layer kernels (shared by the 1-CTA and the CTA-pair variant)
+// ---------------------------------------------------------------------------------------------
+// 16 epilogue warps: warp w owns TMEM lanes 32*(w%4).. (one sample row per thread) and column group (w-2)/4; the four
+// column groups split the 16-channel chunks of both epilogues round-robin.  The first version used 4 warps (one per
+// SM sub-partition): with nothing to switch to, every LDTM / MUFU / store latency was exposed and the two epilogues cost
+// ~20k cycles per 128-sample tile against ~7.7k cycles of MMA work (role counters, profiles/layer_roles_r1.txt).
+constexpr int LAYER_EPI_WARPS = 16;
+constexpr int LAYER_THREADS = 64 + 32 * LAYER_EPI_WARPS;
+constexpr int LAYER_NCG = LAYER_EPI_WARPS / 4;
+
+template <bool kPair>
+__device__ __forceinline__ void layer_epilogue(const LayerArgs& a, int cs, int crank, int cluster_id, int ncluster, int nsuper,
+                                               int ntiles, uint32_t tmem_acc1, uint32_t tmem_acc2, uint8_t* hbuf, float* sb_bo,
+                                               uint64_t* acc1_full, uint64_t* acc2_full, uint64_t* epi1_done,
+                                               uint64_t* epi2_done) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.G / 2;
+    const bool has_out = (a.x_out != nullptr);
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t hbuf_addr = smem_u32(hbuf);
+    const uint32_t epi1_remote = kPair ? mapa(smem_u32(epi1_done), 0) : 0u;
+    const uint32_t epi2_remote = kPair ? mapa(smem_u32(epi2_done), 0) : 0u;
+    for (int i = threadIdx.x - 64; i < a.R; i += 32 * LAYER_EPI_WARPS) sb_bo[i] = __ldg(a.bo + i);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+    int it = 0;
+    long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0, e_pre = 0;
+    const long long e_t0 = clock64();
+    LPROF_BEGIN();
+    for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+        const int tile = sup * cs + crank;
+        const bool tile_ok = (tile < ntiles);
+        const int b = tile_ok ? tile / a.tiles_per_utt : 0, t0 = (tile % a.tiles_per_utt) * BM;
+        const int t = t0 + row;
+        const bool live = tile_ok && (t < a.T);
+        const float* gbp = a.gb + (size_t)b * a.G;
+        __nv_bfloat16* hrow = a.h_out + ((size_t)b * a.T + t) * a.Hp;
+
+        // Residual channels of this thread (its column group's chunks of the row): issued NOW, consumed in EPI2, so the
+        // L2 round trip hides behind GEMM1 / EPI1 instead of stalling every chunk of EPI2.
+        uint4 res[8];
+        if (has_out && live) {
+            const __nv_bfloat16* xin = a.x_in + ((size_t)b * a.T + t) * a.R;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c0 = (cg + LAYER_NCG * jj) * 16;
+                if (c0 < a.R) {
+                    res[2 * jj] = __ldg(reinterpret_cast<const uint4*>(xin + c0));
+                    res[2 * jj + 1] = __ldg(reinterpret_cast<const uint4*>(xin + c0 + 8));
+                }
+            }
+        }
+
+        // ---- EPI1: gate ----
+        LPROF(e_pre);
+        mbar_wait(acc1_full, it & 1);
+        LPROF(e_w1);
+        tc_fence_after();
+        for (int c0 = cg * 16; c0 < a.Hp; c0 += LAYER_NCG * 16) {
+            uint32_t packed[8];
+            if (c0 < H) {  // H % 16 == 0 is required by the host wrapper
+                float va[16], vb[16];
+                tmem_ld16(tmem_acc1 + lane_base + c0, va);
+                tmem_ld16(tmem_acc1 + lane_base + H + c0, vb);
+                float ba[16], bb[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
+                    *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + H + c0 + i));
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
+                    const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
+                    packed[i >> 1] = pack_bf16x2(h0, h1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) packed[i] = 0u;  // K padding of GEMM2 / skip GEMM
+            }
+            const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+            const uint32_t base = hbuf_addr + kb * A_TILE_BYTES;
+            st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+            st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+            if (live) {
+                uint4* dst = reinterpret_cast<uint4*>(hrow + c0);
+                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();  // generic-proxy writes of h -> visible to the tensor-core (async) proxy
+        if (kPair) mbar_arrive_cluster(epi1_remote); else mbar_arrive(epi1_done);
+        LPROF(e_e1);
+
+        // ---- EPI2: residual ----
+        if (has_out) {
+            mbar_wait(acc2_full, it & 1);
+            LPROF(e_w2);
+            tc_fence_after();
+            __nv_bfloat16* xout = a.x_out + ((size_t)b * a.T + t) * a.R;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c0 = (cg + LAYER_NCG * jj) * 16;
+                if (c0 < a.R) {
+                    float v[16];
+                    tmem_ld16(tmem_acc2 + lane_base + c0, v);
+                    float bo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bo[i]) = *reinterpret_cast<const float4*>(sb_bo + c0 + i);
+                    tmem_ld_wait();
+                    if (live) {
+                        const uint4 r0 = res[2 * jj], r1 = res[2 * jj + 1];
+                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                            const float o0 = ((v[2 * i] + bo[2 * i]) + __low2float(rv)) * kSqrtHalf;
+                            const float o1 = ((v[2 * i + 1] + bo[2 * i + 1]) + __high2float(rv)) * kSqrtHalf;
+                            packed[i] = pack_bf16x2(o0, o1);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(xout + c0);
+                        dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                        dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+                    }
+                }
+            }
+            tc_fence_before();
+            if (kPair) mbar_arrive_cluster(epi2_remote); else mbar_arrive(epi2_done);
+            LPROF(e_e2);
+        }
+    }
+    if (LPROF_ON && a.prof && threadIdx.x == 64) {
+        a.prof[blockIdx.x * 16 + 8] = e_w1; a.prof[blockIdx.x * 16 + 9] = e_e1; a.prof[blockIdx.x * 16 + 10] = e_w2;
+        a.prof[blockIdx.x * 16 + 11] = e_e2; a.prof[blockIdx.x * 16 + 12] = e_pre; a.prof[blockIdx.x * 16 + 13] = clock64() - e_t0;
+    }
+}
+
 
 // shared memory: [stages x (A 16K | B G*128)] [h: Hp/64 x 16K] [barriers]
 //
@@ -324,7 +476,7 @@ constexpr int LAYER_STAGES = 4;
 // TMA-multicasts it into the shared memory of all cs CTAs (the kernel is L2->SM bandwidth bound otherwise:
 // 48 KB per k-block per CTA, 2/3 of it weights).  A stage may be refilled only when ALL cs CTAs have consumed it,
 // so the stage-release commit is multicast too (empty barriers count cs arrivals).
-__global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid_constant__ LayerArgs a) {
+__global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = a.G / 2;
@@ -348,9 +500,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
     if (threadIdx.x == 0) {
         for (int s = 0; s < LAYER_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], cs); }
         mbar_init(acc1_full, 1);
-        mbar_init(epi1_done, 128);
+        mbar_init(epi1_done, 32 * LAYER_EPI_WARPS);
         mbar_init(acc2_full, 1);
-        mbar_init(epi2_done, 128);
+        mbar_init(epi2_done, 32 * LAYER_EPI_WARPS);
         fence_mbar_init();
         tma_prefetch_desc(&a.tm_x);
         tma_prefetch_desc(&a.tm_c);
@@ -419,7 +571,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                     }
                 }
             }
-            if (a.prof) { a.prof[blockIdx.x * 16 + 0] = p_wait; a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0; }
+            if (LPROF_ON && a.prof) { a.prof[blockIdx.x * 16 + 0] = p_wait; a.prof[blockIdx.x * 16 + 1] = clock64() - p_t0; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
@@ -464,128 +616,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
                     umma_commit(acc2_full);
                 }
             }
-            if (a.prof) {
+            if (LPROF_ON && a.prof) {
                 a.prof[blockIdx.x * 16 + 2] = m_full; a.prof[blockIdx.x * 16 + 3] = m_e1; a.prof[blockIdx.x * 16 + 4] = m_e2;
                 a.prof[blockIdx.x * 16 + 5] = m_iss; a.prof[blockIdx.x * 16 + 6] = clock64() - m_t0; a.prof[blockIdx.x * 16 + 7] = it;
             }
         }
     } else {
         // ================= epilogue warps =================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const uint32_t hbuf_addr = smem_u32(hbuf);
-        // conv1x1_out bias: staged once in shared memory (broadcast reads instead of per-chunk global loads)
-        float* sb_bo = reinterpret_cast<float*>(bars) + 64;   // barriers + tmem slot live in the first 256 B, then 256 floats
-        for (int i = threadIdx.x - 64; i < a.R; i += 128) sb_bo[i] = __ldg(a.bo + i);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        int it = 0;
-        long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0, e_pre = 0; const long long e_t0 = clock64(); LPROF_BEGIN();
-        for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
-            const int tile = sup * cs + crank;
-            const bool tile_ok = (tile < ntiles);
-            const int b = tile_ok ? tile / a.tiles_per_utt : 0, t0 = (tile % a.tiles_per_utt) * BM;
-            const int t = t0 + row;
-            const bool live = tile_ok && (t < a.T);
-            const float* gbp = a.gb + (size_t)b * a.G;
-            __nv_bfloat16* hrow = a.h_out + ((size_t)b * a.T + t) * a.Hp;
-
-            // Residual row of this thread (R bf16 = up to 512 B): issued NOW, consumed in EPI2.  The first version
-            // loaded it chunk by chunk inside EPI2 and exposed one L2 round trip per 16 channels (ncu: long-scoreboard
-            // stalls on those loads were the top stall of the kernel, profiles/r1_layer_kernel_ncu.txt).
-            uint4 res[32];
-            if (has_out && live) {
-                const uint4* xin = reinterpret_cast<const uint4*>(a.x_in + ((size_t)b * a.T + t) * a.R);
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j * 8 < a.R) res[j] = __ldg(xin + j);
-            }
-
-            // ---- EPI1: gate ----
-            LPROF(e_pre);
-            mbar_wait(acc1_full, it & 1);
-            LPROF(e_w1);
-            tc_fence_after();
-            for (int c0 = 0; c0 < a.Hp; c0 += 16) {
-                uint32_t packed[8];
-                if (c0 < H) {  // H % 16 == 0 is required by the host wrapper
-                    float va[16], vb[16];
-                    tmem_ld16(tmem_acc1 + lane_base + c0, va);
-                    tmem_ld16(tmem_acc1 + lane_base + H + c0, vb);
-                    float ba[16], bb[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
-                        *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + H + c0 + i));
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
-                        const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
-                        packed[i >> 1] = pack_bf16x2(h0, h1);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) packed[i] = 0u;  // K padding of GEMM2 / skip GEMM
-                }
-                const int kb = c0 / BK, c16 = (c0 % BK) / 8;
-                const uint32_t base = hbuf_addr + kb * A_TILE_BYTES;
-                st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
-                st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
-                if (live) {
-                    uint4* dst = reinterpret_cast<uint4*>(hrow + c0);
-                    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                }
-            }
-            tc_fence_before();
-            fence_proxy_async_smem();  // generic-proxy writes of h -> visible to the tensor-core (async) proxy
-            mbar_arrive(epi1_done);
-            LPROF(e_e1);
-
-            // ---- EPI2: residual ----
-            if (has_out) {
-                mbar_wait(acc2_full, it & 1);
-                LPROF(e_w2);
-                tc_fence_after();
-                __nv_bfloat16* xout = a.x_out + ((size_t)b * a.T + t) * a.R;
-#pragma unroll
-                for (int jc = 0; jc < 16; ++jc) {
-                    const int c0 = jc * 16;
-                    if (c0 < a.R) {
-                        float v[16];
-                        tmem_ld16(tmem_acc2 + lane_base + c0, v);
-                        float bo[16];
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bo[i]) = *reinterpret_cast<const float4*>(sb_bo + c0 + i);
-                        tmem_ld_wait();
-                        if (live) {
-                            const uint4 r0 = res[2 * jc], r1 = res[2 * jc + 1];
-                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                            uint32_t packed[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-                                const float o0 = ((v[2 * i] + bo[2 * i]) + __low2float(rv)) * kSqrtHalf;
-                                const float o1 = ((v[2 * i + 1] + bo[2 * i + 1]) + __high2float(rv)) * kSqrtHalf;
-                                packed[i] = pack_bf16x2(o0, o1);
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(xout + c0);
-                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                        }
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive(epi2_done);
-                LPROF(e_e2);
-            }
-        }
-        if (a.prof && threadIdx.x == 64) {
-            a.prof[blockIdx.x * 16 + 8] = e_w1; a.prof[blockIdx.x * 16 + 9] = e_e1; a.prof[blockIdx.x * 16 + 10] = e_w2;
-            a.prof[blockIdx.x * 16 + 11] = e_e2; a.prof[blockIdx.x * 16 + 12] = e_pre; a.prof[blockIdx.x * 16 + 13] = clock64() - e_t0;
-        }
+        layer_epilogue<false>(a, cs, crank, cluster_id, ncluster, nsuper, ntiles, tmem_acc1, tmem_acc2, hbuf,
+                              reinterpret_cast<float*>(bars) + 64, acc1_full, acc2_full, epi1_done, epi2_done);
     }
     tc_fence_before();
     __syncthreads();
@@ -610,7 +649,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_kernel(const __grid
 constexpr int PAIR_STAGES = 6;
 constexpr int PAIR_B_BYTES = 128 * BK * 2;   // half of an N = 256 weight k-block
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_pair_kernel(const __grid_constant__ LayerArgs a) {
+__global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_pair_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int H = a.G / 2;
@@ -632,9 +671,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_pair_kernel(const _
     if (threadIdx.x == 0) {
         for (int s = 0; s < PAIR_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc1_full, 1);
-        mbar_init(epi1_done, 256);
+        mbar_init(epi1_done, 2 * 32 * LAYER_EPI_WARPS);
         mbar_init(acc2_full, 1);
-        mbar_init(epi2_done, 256);
+        mbar_init(epi2_done, 2 * 32 * LAYER_EPI_WARPS);
         fence_mbar_init();
         tma_prefetch_desc(&a.tm_x);
         tma_prefetch_desc(&a.tm_c);
@@ -735,108 +774,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) layer_bf16_pair_kernel(const _
         }
     } else {
         // ================= epilogue warps (both CTAs, own 128 TMEM lanes) =================
-        const int q = warp & 3;
-        const int row = q * 32 + lane;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const uint32_t hbuf_addr = smem_u32(hbuf);
-        const uint32_t epi1_remote = mapa(smem_u32(epi1_done), 0), epi2_remote = mapa(smem_u32(epi2_done), 0);
-        float* sb_bo = reinterpret_cast<float*>(bars) + 64;   // barriers + tmem slot live in the first 256 B
-        for (int i = threadIdx.x - 64; i < a.R; i += 128) sb_bo[i] = __ldg(a.bo + i);
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        int it = 0;
-        for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
-            const int tile = sup * 2 + crank;
-            const bool tile_ok = (tile < ntiles);
-            const int b = tile_ok ? tile / a.tiles_per_utt : 0, t0 = (tile % a.tiles_per_utt) * BM;
-            const int t = t0 + row;
-            const bool live = tile_ok && (t < a.T);
-            const float* gbp = a.gb + (size_t)b * a.G;
-            __nv_bfloat16* hrow = a.h_out + ((size_t)b * a.T + t) * a.Hp;
-
-            uint4 res[32];
-            if (has_out && live) {
-                const uint4* xin = reinterpret_cast<const uint4*>(a.x_in + ((size_t)b * a.T + t) * a.R);
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (j * 8 < a.R) res[j] = __ldg(xin + j);
-            }
-
-            // ---- EPI1: gate ----
-            mbar_wait(acc1_full, it & 1);
-            tc_fence_after();
-            for (int c0 = 0; c0 < a.Hp; c0 += 16) {
-                uint32_t packed[8];
-                if (c0 < H) {
-                    float va[16], vb[16];
-                    tmem_ld16(tmem_acc1 + lane_base + c0, va);
-                    tmem_ld16(tmem_acc1 + lane_base + H + c0, vb);
-                    float ba[16], bb[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i += 4) {
-                        *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
-                        *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + H + c0 + i));
-                    }
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
-                        const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
-                        packed[i >> 1] = pack_bf16x2(h0, h1);
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) packed[i] = 0u;
-                }
-                const int kb = c0 / BK, c16 = (c0 % BK) / 8;
-                const uint32_t base = hbuf_addr + kb * A_TILE_BYTES;
-                st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
-                st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
-                if (live) {
-                    uint4* dst = reinterpret_cast<uint4*>(hrow + c0);
-                    dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                    dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                }
-            }
-            tc_fence_before();
-            fence_proxy_async_smem();
-            mbar_arrive_cluster(epi1_remote);
-
-            // ---- EPI2: residual ----
-            if (has_out) {
-                mbar_wait(acc2_full, it & 1);
-                tc_fence_after();
-                __nv_bfloat16* xout = a.x_out + ((size_t)b * a.T + t) * a.R;
-#pragma unroll
-                for (int jc = 0; jc < 16; ++jc) {
-                    const int c0 = jc * 16;
-                    if (c0 < a.R) {
-                        float v[16];
-                        tmem_ld16(tmem_acc2 + lane_base + c0, v);
-                        float bo[16];
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bo[i]) = *reinterpret_cast<const float4*>(sb_bo + c0 + i);
-                        tmem_ld_wait();
-                        if (live) {
-                            const uint4 r0 = res[2 * jc], r1 = res[2 * jc + 1];
-                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-                            uint32_t packed[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
-                                const float o0 = ((v[2 * i] + bo[2 * i]) + __low2float(rv)) * kSqrtHalf;
-                                const float o1 = ((v[2 * i + 1] + bo[2 * i + 1]) + __high2float(rv)) * kSqrtHalf;
-                                packed[i] = pack_bf16x2(o0, o1);
-                            }
-                            uint4* dst = reinterpret_cast<uint4*>(xout + c0);
-                            dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                            dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-                        }
-                    }
-                }
-                tc_fence_before();
-                mbar_arrive_cluster(epi2_remote);
-            }
-        }
+        layer_epilogue<true>(a, 2, crank, cluster_id, ncluster, nsuper, ntiles, tmem_acc1, tmem_acc2, hbuf,
+                             reinterpret_cast<float*>(bars) + 64, acc1_full, acc2_full, epi1_done, epi2_done);
     }
     tc_fence_before();
     __syncthreads();
@@ -1249,7 +1188,7 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
             ProfScope prof(1, stream);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)grid_layer);
-            cfg.blockDim = dim3(NUM_THREADS);
+            cfg.blockDim = dim3(LAYER_THREADS);
             cfg.dynamicSmemBytes = smem_layer;
             cfg.stream = stream;
             cudaLaunchAttribute attr[1];
