@@ -96,7 +96,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a pipeline bug must never hang the GPU.  ~2^26 polls (seconds) then trap.  The report path is kept
 // out of line so that the many wait sites stay a few instructions each (instruction-cache footprint).
-__device__ __noinline__ void mbar_timeout(const void* bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_timeout(const void* bar, uint32_t parity) {
     printf("wae: mbarrier timeout block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
     __trap();
 }
