@@ -127,10 +127,14 @@ def test_forward_full_size_properties_bf16():
 # ------------------------------------------------------------------ autoregressive synthesis
 @pytest.mark.parametrize("case,prec,cluster,tol", [
     ("wavenet_tiny", "fp32", 16, 1e-4), ("wavenet_tiny", "fp32", 8, 1e-4), ("wavenet_tiny", "bf16", 8, 3e-2),
-    ("wavenet_tiny_k2", "fp32", 8, 1e-4), ("wavenet_tiny_k2", "bf16", 16, 3e-2)])
+    ("wavenet_tiny_k2", "fp32", 8, 1e-4), ("wavenet_tiny_k2", "bf16", 16, 3e-2),
+    ("wavenet_tiny", "bf16-simt", 8, 3e-2), ("wavenet_tiny_k2", "bf16-simt", 8, 3e-2)])
 def test_incremental_teacher_forced_logits(case, prec, cluster, tol):
-    """L1 of the RNG contract: identical test_inputs for all T, softmax=False, quantize=False -> per-step logits."""
+    """L1 of the RNG contract: identical test_inputs for all T, softmax=False, quantize=False -> per-step logits.
+    "bf16" runs the tensor-core (mma.sync) AR kernel, "bf16-simt" the CUDA-core kernel on bf16 weights."""
     g, cfg, m, x, c, spk = _inputs(case)
+    if prec.endswith("-simt"):
+        prec, m.ar_impl = "bf16", "simt"
     m.precision, m.ar_cluster = prec, cluster
     y = m.incremental_forward(initial_input=x[:, :, :1], c=c, g=spk, T=int(g["T"]), test_inputs=x, softmax=False, quantize=False)
     assert y.shape == tuple(g["inc_logits"].shape)

@@ -154,6 +154,16 @@ __device__ __forceinline__ void tma_load_3d_mc(const void* desc, uint64_t* bar, 
           "r"(c0), "r"(c1), "r"(c2), "h"(cta_mask)
         : "memory");
 }
+// TMA store shared -> global (bulk async-group completion).  OOB parts of the box are clipped.
+__device__ __forceinline__ void tma_store_3d(const void* desc, const void* smem_src, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :
+                 : "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 // 1D bulk copy global -> shared (no tensor map), completes on an mbarrier. bytes % 16 == 0.
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes,
                                              uint64_t* bar) {

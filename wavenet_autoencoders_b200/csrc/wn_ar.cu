@@ -37,6 +37,7 @@ constexpr int MAXMS = 4;     // max S/64   (S   <= 256)
 struct ArArgs {
     wae_stack_dims d;
     int wtype, cluster, B, T, Tf, sample_mode, apply_softmax, nmix;
+    int utts;                        // utterances per cluster (tensor-core variant; the SIMT kernel has it as a template parameter)
     int Hp, Cp, K1p;                 // padded reduction lengths (multiples of 64)
     int ring_rows;                   // rows per utterance in the ring
     int ring_off[WAE_MAX_LAYERS];    // first ring row of each layer
@@ -698,6 +699,532 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     cluster_sync();  // no CTA exits while peers may still write into its shared memory
 }
 
+// ================================================================================================
+// Tensor-core variant of the AR kernel (bf16 weights): same cluster/row-slice/all-gather structure as ar_kernel, but
+//  * every mat-vec is an mma.sync.m16n8k16 (bf16 in, fp32 accumulate) with the utterances of the cluster as the
+//    n = 8 columns -- up to 8 utterances share one pass over the weights at no extra cost, and a layer's slice is
+//    ~13 mma per warp instead of ~900 scalar instructions (the SIMT kernel is issue/latency bound with 8 warps);
+//  * activations live in shared memory as bf16 ([utterance][k], 16-byte row padding -> conflict-free ldmatrix);
+//  * K is split over the 8 warps, partial 16x8 tiles are reduced through shared memory, the reduction threads apply
+//    bias / gate / residual exactly like the SIMT kernel.
+// Ring history, weights blobs ([rows padded to 16][K + 8]) and exchanged slices are bf16; accumulators, skip sum,
+// logits and the sampler are fp32.
+// ================================================================================================
+constexpr int UC = 8;          // utterance columns per cluster (mma n)
+constexpr int NPF_M = 3;       // tap prefetch depth of this variant (shared memory budget)
+constexpr int KPAD = 8;        // bf16 elements of row padding
+
+struct ArMmaLayout {
+    int w1_slot, w2_slot;                       // bytes
+    int rows1p, rows2p, rows3p, rows4p;         // row counts padded to 16 (max over ranks)
+    int off_w1, off_w2, off_xin, off_c, off_h, off_s1, off_s2, off_logit, off_red, off_skip, off_b2, off_stgh, off_stgx,
+        off_boff, off_misc, total;
+    int max_np, max_n2, max_n3, max_n4;
+};
+
+inline ArMmaLayout ar_mma_layout(const wae_stack_dims& d, int cs, int Hp, int Cp, int K1p) {
+    ArMmaLayout s;
+    const int H = d.G / 2;
+    s.max_np = s.max_n2 = s.max_n3 = s.max_n4 = 0;
+    for (int r = 0; r < cs; ++r) {
+        int np = part(H, r + 1, cs) - part(H, r, cs);
+        int n2 = (part(d.R, r + 1, cs) - part(d.R, r, cs)) + (part(d.S, r + 1, cs) - part(d.S, r, cs));
+        int n3 = part(d.S, r + 1, cs) - part(d.S, r, cs);
+        int n4 = part(d.O, r + 1, cs) - part(d.O, r, cs);
+        if (np > s.max_np) s.max_np = np;
+        if (n2 > s.max_n2) s.max_n2 = n2;
+        if (n3 > s.max_n3) s.max_n3 = n3;
+        if (n4 > s.max_n4) s.max_n4 = n4;
+    }
+    auto r16 = [](int x) { return (x + 15) / 16 * 16; };
+    auto up = [](int x) { return (x + 127) / 128 * 128; };
+    s.rows1p = r16(2 * s.max_np); s.rows2p = r16(s.max_n2); s.rows3p = r16(s.max_n3); s.rows4p = r16(s.max_n4);
+    s.w1_slot = up(s.rows1p * (K1p + KPAD) * 2);
+    int w2 = s.rows2p * (Hp + KPAD) * 2, w3 = s.rows3p * (d.S + KPAD) * 2, w4 = s.rows4p * (d.S + KPAD) * 2;
+    s.w2_slot = up(w2 > w3 ? (w2 > w4 ? w2 : w4) : (w3 > w4 ? w3 : w4));
+    int maxrows = s.rows1p > s.rows2p ? s.rows1p : s.rows2p;
+    if (s.rows3p > maxrows) maxrows = s.rows3p;
+    if (s.rows4p > maxrows) maxrows = s.rows4p;
+    int off = 0;
+    s.off_w1 = off; off += 2 * s.w1_slot;
+    s.off_w2 = off; off += 2 * s.w2_slot;
+    s.off_xin = off; off += up(NPF_M * UC * (d.kernel_size * d.R + KPAD) * 2);
+    s.off_c = off; off += up(2 * UC * (Cp + KPAD) * 2);
+    s.off_h = off; off += up(UC * (Hp + KPAD) * 2);
+    s.off_s1 = off; off += up(UC * (d.S + KPAD) * 2);
+    s.off_s2 = off; off += up(UC * (d.S + KPAD) * 2);
+    s.off_logit = off; off += up(UC * d.O * 4);
+    int red = AR_WARPS * maxrows * UC * 4, inb = UC * d.Oin * 4;      // reduction scratch, also the dense-input buffer
+    s.off_red = off; off += up(red > inb ? red : inb);
+    s.off_skip = off; off += up(UC * (s.max_n3 + 1) * 4);
+    s.off_b2 = off; off += up((d.layers * s.max_n2 + s.max_n3 + s.max_n4) * 4);
+    s.off_stgh = off; off += up(UC * (s.max_np + 8) * 2);
+    s.off_stgx = off; off += up(UC * (maxrows + 8) * 2 > UC * (d.O + 8) * 4 ? UC * (maxrows + 8) * 2 : UC * (d.O + 8) * 4);
+    s.off_boff = off; off += up((2 * d.layers + 2) * 8);
+    s.off_misc = off; off += 256;
+    s.total = off;
+    return s;
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// partial[warp][row][u] = sum over this warp's k-steps of W[row][k] * X[u][k];   W: [mt*16][wstride] bf16 in smem,
+// X given per k-step by bsrc(ks) -> (shared address of element [0][ks*16], row stride in bytes)
+template <int MAXMT, class BSrc>
+__device__ __forceinline__ void mma_gemv(uint32_t w_addr, int mt, int wstride_bytes, int nk, BSrc bsrc, float* red, int rows_pad,
+                                         int warp, int lane) {
+    float acc[MAXMT][4];
+#pragma unroll
+    for (int m = 0; m < MAXMT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;    // ldmatrix.x4 lane -> (row, k) of its 8x8 matrix
+    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
+    for (int ks = warp; ks < nk; ks += AR_WARPS) {
+        uint32_t baddr, bstride;
+        bsrc(ks, baddr, bstride);
+        uint32_t b0, b1;
+        ldsm_x2(baddr + brow * bstride + bcol * 2, b0, b1);
+#pragma unroll
+        for (int m = 0; m < MAXMT; ++m) {
+            if (m < mt) {
+                uint32_t a0, a1, a2, a3;
+                ldsm_x4(w_addr + (uint32_t)((m * 16 + arow) * wstride_bytes + (ks * 16 + acol) * 2), a0, a1, a2, a3);
+                mma_bf16_16816(acc[m], a0, a1, a2, a3, b0, b1);
+            }
+        }
+    }
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+    for (int m = 0; m < MAXMT; ++m) {
+        if (m < mt) {
+            float* p = red + ((size_t)warp * rows_pad + m * 16 + g) * UC + t2;
+            *reinterpret_cast<float2*>(p) = make_float2(acc[m][0], acc[m][1]);
+            *reinterpret_cast<float2*>(p + 8 * UC) = make_float2(acc[m][2], acc[m][3]);
+        }
+    }
+}
+
+__device__ __forceinline__ float red_sum(const float* red, int rows_pad, int row, int u) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < AR_WARPS; ++w) s += red[((size_t)w * rows_pad + row) * UC + u];
+    return s;
+}
+
+// all-gather of a bf16 slice: src[u][i] (i < n, row pitch spitch elements) -> dst[u*dpitch + off + i] in every CTA
+__device__ __forceinline__ void allgather_bf16(const __nv_bfloat16* src, int spitch, __nv_bfloat16* dst, int dpitch, int off, int n,
+                                               int cs, int tid) {
+    if (((n | off | spitch | dpitch) & 1) == 0) {
+        const int nw = n >> 1, per = UC * nw;                      // 32-bit words per destination
+        for (int e = tid; e < cs * per; e += AR_THREADS) {
+            const int r = e / per, w = e - r * per, u = w / nw, i = w - u * nw;
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(src + u * spitch + 2 * i);
+            st_cluster_u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + 2 * i), (uint32_t)r), v);
+        }
+    } else {
+        const int per = UC * n;
+        for (int e = tid; e < cs * per; e += AR_THREADS) {
+            const int r = e / per, w = e - r * per, u = w / n, i = w - u * n;
+            const unsigned short v = *reinterpret_cast<const unsigned short*>(src + u * spitch + i);
+            asm volatile("st.shared::cluster.u16 [%0], %1;" ::"r"(mapa(smem_u32(dst + (size_t)u * dpitch + off + i), (uint32_t)r)), "h"(v) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void allgather_f32(const float* src, int spitch, float* dst, int dpitch, int off, int n, int cs, int tid) {
+    const int per = UC * n;
+    for (int e = tid; e < cs * per; e += AR_THREADS) {
+        const int r = e / per, w = e - r * per, u = w / n, i = w - u * n;
+        st_cluster_f32(mapa(smem_u32(dst + (size_t)u * dpitch + off + i), (uint32_t)r), src[u * spitch + i]);
+    }
+}
+
+__global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_constant__ ArArgs a, const __grid_constant__ ArMmaLayout sl) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    typedef __nv_bfloat16 bf16;
+    const wae_stack_dims& d = a.d;
+    const int cs = a.cluster, U = a.utts;
+    const int rank = (int)cluster_ctarank();
+    const int cid = (int)blockIdx.x / cs;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = d.layers, kw = d.kernel_size, R = d.R, G = d.G, S = d.S, O = d.O, Oin = d.Oin;
+    const int H = G / 2, Hp = a.Hp, Cp = a.Cp, K1p = a.K1p;
+    const int KX = kw * R;
+    const int XS = KX + KPAD, CSd = Cp + KPAD, HS = Hp + KPAD, SS = S + KPAD;     // row pitches (elements)
+    const int W1S = (K1p + KPAD) * 2, W2S = (Hp + KPAD) * 2, W3S = (S + KPAD) * 2;  // weight row pitches (bytes)
+
+    uint8_t* w1buf = smem + sl.off_w1;
+    uint8_t* w2buf = smem + sl.off_w2;
+    bf16* xin = reinterpret_cast<bf16*>(smem + sl.off_xin);      // [NPF_M][UC][XS]
+    bf16* cbuf = reinterpret_cast<bf16*>(smem + sl.off_c);       // [2][UC][CSd]
+    bf16* hbuf = reinterpret_cast<bf16*>(smem + sl.off_h);       // [UC][HS]
+    bf16* s1buf = reinterpret_cast<bf16*>(smem + sl.off_s1);     // [UC][SS]
+    bf16* s2buf = reinterpret_cast<bf16*>(smem + sl.off_s2);
+    float* lgbuf = reinterpret_cast<float*>(smem + sl.off_logit); // [UC][O]
+    float* red = reinterpret_cast<float*>(smem + sl.off_red);    // [AR_WARPS][rows_pad][UC]
+    float* inbuf = red;                                          // dense input of the current step (used before the layers)
+    float* skipacc = reinterpret_cast<float*>(smem + sl.off_skip);
+    float* b2c = reinterpret_cast<float*>(smem + sl.off_b2);
+    bf16* stgh = reinterpret_cast<bf16*>(smem + sl.off_stgh);    // [UC][STH]
+    bf16* stgx = reinterpret_cast<bf16*>(smem + sl.off_stgx);    // [UC][STX]   (also fp32 logits staging)
+    long long* boffs = reinterpret_cast<long long*>(smem + sl.off_boff);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + sl.off_misc);
+    uint64_t* w1_full = bars;
+    uint64_t* w2_full = bars + 2;
+    int* cur_idx = reinterpret_cast<int*>(bars + 4);             // [UC]
+
+    const int p0 = part(H, rank, cs), np = part(H, rank + 1, cs) - p0;
+    const int ro0 = part(R, rank, cs), nres = part(R, rank + 1, cs) - ro0;
+    const int so0 = part(S, rank, cs), nsk = part(S, rank + 1, cs) - so0;
+    const int oo0 = part(O, rank, cs), nout = part(O, rank + 1, cs) - oo0;
+    const int n2 = nres + nsk;
+    const int mt1 = (2 * np + 15) / 16, mt2 = (n2 + 15) / 16, mt3 = (nsk + 15) / 16, mt4 = (nout + 15) / 16;
+    const int STH = sl.max_np + 8, STX = (sl.rows1p > sl.rows2p ? sl.rows1p : sl.rows2p) + 8;
+    float* b3c = b2c + (size_t)L * sl.max_n2;
+    float* b4c = b3c + sl.max_n3;
+
+    const unsigned n1_total = (unsigned)a.T * L, n2_total = (unsigned)a.T * (L + 2);
+    auto issue_w1 = [&](unsigned j) {
+        if (j >= n1_total) return;
+        const int l = (int)(j % L), slot = (int)(j & 1);
+        const uint32_t bytes = (uint32_t)(mt1 * 16 * W1S);
+        if (bytes == 0) { mbar_arrive(&w1_full[slot]); return; }
+        mbar_arrive_expect_tx(&w1_full[slot], bytes);
+        bulk_load_1d(w1buf + (size_t)slot * sl.w1_slot, a.blob + boffs[2 * l], bytes, &w1_full[slot]);
+    };
+    auto issue_w2 = [&](unsigned j) {
+        if (j >= n2_total) return;
+        const int i = (int)(j % (L + 2)), slot = (int)(j & 1);
+        const uint32_t bytes = (uint32_t)((i < L) ? mt2 * 16 * W2S : (i == L ? mt3 * 16 * W3S : mt4 * 16 * W3S));
+        if (bytes == 0) { mbar_arrive(&w2_full[slot]); return; }
+        const int stage = (i < L) ? 2 * i + 1 : 2 * L + (i - L);
+        mbar_arrive_expect_tx(&w2_full[slot], bytes);
+        bulk_load_1d(w2buf + (size_t)slot * sl.w2_slot, a.blob + boffs[stage], bytes, &w2_full[slot]);
+    };
+
+    // ---- one-time setup ----
+    if (tid == 0) {
+        mbar_init(&w1_full[0], 1); mbar_init(&w1_full[1], 1);
+        mbar_init(&w2_full[0], 1); mbar_init(&w2_full[1], 1);
+        fence_mbar_init();
+    }
+    for (int e = tid; e < (sl.off_boff - sl.off_xin) / 4; e += AR_THREADS) reinterpret_cast<uint32_t*>(smem + sl.off_xin)[e] = 0u;
+    __syncthreads();
+    for (int e = tid; e < L * n2; e += AR_THREADS) {
+        const int i = e % n2, l = e / n2;
+        b2c[(size_t)l * sl.max_n2 + i] = (i < nres) ? a.bo[(size_t)l * R + ro0 + i] : a.bs[(size_t)l * S + so0 + (i - nres)];
+    }
+    for (int e = tid; e < nsk; e += AR_THREADS) b3c[e] = a.b3[so0 + e];
+    for (int e = tid; e < nout; e += AR_THREADS) b4c[e] = a.b4[oo0 + e];
+    if (tid < UC) cur_idx[tid] = -1;
+    for (int e = tid; e < 2 * L + 2; e += AR_THREADS) boffs[e] = a.blob_off[(size_t)e * cs + rank];
+    for (int e = tid; e < UC * Oin; e += AR_THREADS) {
+        const int u = e / Oin, o = e % Oin, b = cid * U + u;
+        inbuf[e] = (u < U && b < a.B) ? a.init[(size_t)b * Oin + o] : 0.f;
+    }
+    __syncthreads();
+    if (tid == 0) { issue_w1(0); issue_w1(1); issue_w2(0); issue_w2(1); }
+    cluster_sync();
+
+    const bf16* ringb = reinterpret_cast<const bf16*>(a.ring);
+    bf16* ringw = reinterpret_cast<bf16*>(a.ring);
+    const bf16* c_bf = reinterpret_cast<const bf16*>(a.c_btc);
+    auto prefetch_taps = [&](int tt, int l) {
+        if (tt < a.T && kw > 1) {
+            const int ns = a.ring_ns[l], dil = d.dilation[l];
+            const int r8 = R / 8;
+            const int chunks = U * (kw - 1) * r8;   // 16-byte chunks (8 bf16)
+            for (int e = tid; e < chunks; e += AR_THREADS) {
+                const int c8 = e % r8, j = (e / r8) % (kw - 1), u = e / (r8 * (kw - 1));
+                const int b = cid * U + u;
+                const int ts = tt - (kw - 1 - j) * dil;
+                bf16* dst = xin + ((size_t)(((unsigned)tt * L + l) % NPF_M) * UC + u) * XS + j * R + c8 * 8;
+                if (b < a.B && ts >= 0)
+                    cp_async16(dst, ringb + (((size_t)b * a.ring_rows + a.ring_off[l] + (ts % ns)) * R + c8 * 8));
+                else
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        cp_async_commit();
+    };
+    auto prefetch_c = [&](int tt) {
+        if (c_bf != nullptr && tt < a.T) {
+            const int c8n = d.C / 8;
+            for (int e = tid; e < U * c8n; e += AR_THREADS) {
+                const int c8 = e % c8n, u = e / c8n, b = cid * U + u;
+                if (b < a.B) cp_async16(cbuf + ((size_t)(tt & 1) * UC + u) * CSd + c8 * 8, c_bf + (((size_t)b * a.T + tt) * d.C + c8 * 8));
+            }
+        }
+    };
+    prefetch_c(0);
+    for (int l = 0; l < NPF_M - 1; ++l) prefetch_taps(0, l);
+
+    unsigned j1 = 0, j2 = 0;
+    for (int t = 0; t < a.T; ++t) {
+        float u_pref = 0.f;
+        if (warp < U && a.uniforms != nullptr) {
+            const int b = cid * U + warp;
+            if (b < a.B && lane < a.nu) u_pref = __ldg(&a.uniforms[((size_t)t * a.B + b) * a.nu + lane]);
+        }
+        // ---- input -> first conv ----
+        if (a.forced != nullptr && t < a.Tf) {
+            for (int e = tid; e < U * Oin; e += AR_THREADS) {
+                const int u = e / Oin, o = e % Oin, b = cid * U + u;
+                inbuf[e] = (b < a.B) ? __ldg(&a.forced[((size_t)b * a.Tf + t) * Oin + o]) : 0.f;
+            }
+            if (tid < UC) cur_idx[tid] = -1;
+            __syncthreads();
+        }
+        if (warp < U && cur_idx[warp] < 0 && Oin > 1) {
+            int nz = 0, pos = -1;
+            bool is_one = true;
+            for (int o = lane; o < Oin; o += 32) {
+                const float v = inbuf[warp * Oin + o];
+                if (v != 0.f) { ++nz; pos = o; is_one = is_one && (v == 1.f); }
+            }
+            nz = __reduce_add_sync(0xffffffffu, nz);
+            pos = __reduce_max_sync(0xffffffffu, pos);
+            const bool ok = __all_sync(0xffffffffu, is_one);
+            if (lane == 0 && nz == 1 && ok) cur_idx[warp] = pos;
+        }
+        __syncthreads();
+        {
+            bf16* x0 = xin + (size_t)(((unsigned)t * L) % NPF_M) * UC * XS + (kw - 1) * R;
+            for (int e = tid; e < U * R; e += AR_THREADS) {
+                const int u = e / R, r = e % R;
+                const int ci = cur_idx[u];
+                float acc;
+                if (ci >= 0) {
+                    acc = __ldg(&a.wf[(size_t)ci * R + r]) + __ldg(&a.bf[r]);
+                } else {
+                    acc = 0.f;
+                    for (int o = 0; o < Oin; ++o) acc = fmaf(__ldg(&a.wf[(size_t)o * R + r]), inbuf[u * Oin + o], acc);
+                    acc += __ldg(&a.bf[r]);
+                }
+                const bf16 xb = __float2bfloat16_rn(acc);
+                x0[(size_t)u * XS + r] = xb;
+                const int b = cid * U + u;
+                if (b < a.B && r >= ro0 && r < ro0 + nres)
+                    ringw[((size_t)b * a.ring_rows + a.ring_off[0] + (t % a.ring_ns[0])) * R + r] = xb;
+            }
+        }
+        for (int e = tid; e < UC * (nsk + 1); e += AR_THREADS) skipacc[e] = 0.f;
+        prefetch_c(t + 1);
+        cp_async_wait<NPF_M - 2>();
+        __syncthreads();
+
+        // ---- residual layers ----
+        for (int l = 0; l < L; ++l) {
+            {
+                const int lp = l + NPF_M - 1;
+                prefetch_taps(lp < L ? t : t + 1, lp < L ? lp : lp - L);
+            }
+            const unsigned seq = (unsigned)t * L + l;
+            const bf16* xl = xin + (size_t)(seq % NPF_M) * UC * XS;
+            const bf16* cl = cbuf + (size_t)(t & 1) * UC * CSd;
+            // gate biases of this thread's (pair, utterance) items: issue the loads now, use them after the mma loop
+            float gba[2] = {0.f, 0.f}, gbb[2] = {0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * AR_THREADS;
+                if (e < np * UC) {
+                    const int j = e >> 3, u = e & 7, b = cid * U + u;
+                    if (u < U && b < a.B) {
+                        gba[q] = __ldg(&a.gb[((size_t)l * a.B + b) * G + p0 + j]);
+                        gbb[q] = __ldg(&a.gb[((size_t)l * a.B + b) * G + H + p0 + j]);
+                    }
+                }
+            }
+            mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
+            {
+                const uint32_t xaddr = smem_u32(xl), caddr = smem_u32(cl);
+                mma_gemv<4>(smem_u32(w1buf + (size_t)(j1 & 1) * sl.w1_slot), mt1, W1S, K1p / 16,
+                            [&](int ks, uint32_t& addr, uint32_t& stride) {
+                                const int k0 = ks * 16;
+                                if (k0 < KX) { addr = xaddr + k0 * 2; stride = XS * 2; } else { addr = caddr + (k0 - KX) * 2; stride = CSd * 2; }
+                            },
+                            red, sl.rows1p, warp, lane);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * AR_THREADS;
+                if (e < np * UC) {
+                    const int j = e >> 3, u = e & 7;
+                    const float za = red_sum(red, sl.rows1p, 2 * j, u) + gba[q];
+                    const float zb = red_sum(red, sl.rows1p, 2 * j + 1, u) + gbb[q];
+                    const float e2 = __expf(-2.f * fabsf(za));
+                    const float th = copysignf(__fdividef(1.f - e2, 1.f + e2), za);
+                    stgh[u * STH + j] = __float2bfloat16_rn(th * __fdividef(1.f, 1.f + __expf(-zb)));
+                }
+            }
+            __syncthreads();
+            allgather_bf16(stgh, STH, hbuf, HS, p0, np, cs, tid);
+            ++j1;
+            cluster_arrive();
+            mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
+            cluster_wait();
+            if (tid == 0) issue_w1(j1 + 1);
+            __syncwarp();
+
+            const bool last = (l == L - 1);
+            bf16* xnext = xin + (size_t)((seq + 1) % NPF_M) * UC * XS + (kw - 1) * R;
+            {
+                const uint32_t haddr = smem_u32(hbuf);
+                mma_gemv<8>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt2, W2S, Hp / 16,
+                            [&](int ks, uint32_t& addr, uint32_t& stride) { addr = haddr + ks * 32; stride = HS * 2; },
+                            red, sl.rows2p, warp, lane);
+            }
+            __syncthreads();
+            for (int e = tid; e < n2 * UC; e += AR_THREADS) {
+                const int i = e >> 3, u = e & 7;
+                const float o = red_sum(red, sl.rows2p, i, u) + b2c[(size_t)l * sl.max_n2 + i];
+                if (i < nres) {
+                    if (!last) {
+                        const float xo = (o + __bfloat162float(xl[(size_t)u * XS + (kw - 1) * R + ro0 + i])) * 0.70710678118654752440f;
+                        stgx[u * STX + i] = __float2bfloat16_rn(xo);
+                    }
+                } else {
+                    skipacc[u * (nsk + 1) + (i - nres)] += o;
+                }
+            }
+            if (!last) {
+                __syncthreads();
+                allgather_bf16(stgx, STX, xnext, XS, ro0, nres, cs, tid);
+            }
+            ++j2;
+            cp_async_wait<NPF_M - 2>();
+            cluster_arrive();
+            if (!last) {
+                for (int e = tid; e < U * nres; e += AR_THREADS) {
+                    const int u = e / nres, i = e % nres, b = cid * U + u;
+                    if (b < a.B)
+                        ringw[((size_t)b * a.ring_rows + a.ring_off[l + 1] + (t % a.ring_ns[l + 1])) * R + ro0 + i] = stgx[u * STX + i];
+                }
+            }
+            cluster_wait();
+            if (tid == 0) issue_w2(j2 + 1);
+            __syncwarp();
+        }
+
+        // ---- head ----
+        for (int e = tid; e < UC * nsk; e += AR_THREADS) {
+            const int u = e / nsk, i = e % nsk;
+            stgx[u * STX + i] = __float2bfloat16_rn(fmaxf(skipacc[u * (nsk + 1) + i] * a.skip_scale, 0.f));
+        }
+        __syncthreads();
+        allgather_bf16(stgx, STX, s1buf, SS, so0, nsk, cs, tid);
+        cluster_arrive();
+        mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
+        cluster_wait();
+        {
+            const uint32_t saddr = smem_u32(s1buf);
+            mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt3, W3S, S / 16,
+                        [&](int ks, uint32_t& addr, uint32_t& stride) { addr = saddr + ks * 32; stride = SS * 2; }, red, sl.rows3p, warp, lane);
+        }
+        __syncthreads();
+        for (int e = tid; e < nsk * UC; e += AR_THREADS) {
+            const int i = e >> 3, u = e & 7;
+            stgx[u * STX + i] = __float2bfloat16_rn(fmaxf(red_sum(red, sl.rows3p, i, u) + b3c[i], 0.f));
+        }
+        __syncthreads();
+        allgather_bf16(stgx, STX, s2buf, SS, so0, nsk, cs, tid);
+        ++j2;
+        cluster_arrive();
+        mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
+        cluster_wait();
+        if (tid == 0) issue_w2(j2 + 1);
+        __syncwarp();
+        {
+            const uint32_t saddr = smem_u32(s2buf);
+            mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt4, W3S, S / 16,
+                        [&](int ks, uint32_t& addr, uint32_t& stride) { addr = saddr + ks * 32; stride = SS * 2; }, red, sl.rows4p, warp, lane);
+        }
+        __syncthreads();
+        float* stgl = reinterpret_cast<float*>(stgx);       // fp32 logits staging [UC][O + 8]
+        for (int e = tid; e < nout * UC; e += AR_THREADS) {
+            const int i = e >> 3, u = e & 7;
+            stgl[u * (O + 8) + i] = red_sum(red, sl.rows4p, i, u) + b4c[i];
+        }
+        __syncthreads();
+        allgather_f32(stgl, O + 8, lgbuf, O, oo0, nout, cs, tid);
+        ++j2;
+        cluster_arrive();
+        cluster_wait();
+        if (tid == 0) issue_w2(j2 + 1);
+        __syncwarp();
+
+        // ---- output / sampling (categorical or none; scalar-input models use the SIMT kernel) ----
+        if (warp < U) {
+            const int u = warp, b = cid * U + u;
+            const bool writer = (rank == 0 && b < a.B);
+            const float* lg = lgbuf + (size_t)u * O;
+            const int per = (O + 31) / 32;
+            float mx = -INFINITY;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int o = lane * per + i; if (i < per && o < O) mx = fmaxf(mx, lg[o]); }
+            mx = warp_max(mx);
+            float ex[8];
+            float loc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int o = lane * per + i;
+                ex[i] = (i < per && o < O) ? expf(lg[o] - mx) : 0.f;
+                if (i < per) loc += ex[i];
+            }
+            float inc = loc;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const float v = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += v;
+            }
+            const float total = __shfl_sync(0xffffffffu, inc, 31);
+            if (a.sample_mode == WAE_AR_SAMPLE_CATEGORICAL) {
+                const float thr = __shfl_sync(0xffffffffu, u_pref, 0) * total;
+                float run = inc - loc;
+                int pick = 0x7fffffff;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < per) {
+                        run += ex[i];
+                        const int o = lane * per + i;
+                        if (o < O && run > thr && pick == 0x7fffffff) pick = o;
+                    }
+                }
+                pick = __reduce_min_sync(0xffffffffu, pick);
+                if (pick == 0x7fffffff) pick = O - 1;
+                if (lane == 0) {
+                    cur_idx[u] = pick;
+                    if (writer && a.out_idx) a.out_idx[(size_t)b * a.T + t] = pick;
+                }
+            } else {
+                const float inv = 1.f / total;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int o = lane * per + i;
+                    if (i < per && o < O) {
+                        const float v = a.apply_softmax ? ex[i] * inv : lg[o];
+                        inbuf[u * Oin + (Oin == O ? o : 0)] = v;
+                        if (writer && a.out_dense) a.out_dense[((size_t)b * a.T + t) * O + o] = v;
+                    }
+                }
+                if (lane == 0) cur_idx[u] = -1;
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+    cluster_sync();
+}
+
 __global__ void __launch_bounds__(256)
 ar_gbias_kernel(const float* __restrict__ b1, const float* __restrict__ wg, const float* __restrict__ gemb, int L,
                 int B, int G, int Gi, float* __restrict__ gb) {
@@ -770,7 +1297,7 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
                 "wae_ar_generate: need %d <= layers <= %d", NPF, WAE_MAX_LAYERS);
     WAE_REQUIRE(w->cluster == 8 || w->cluster == 16 || w->cluster == 4 || w->cluster == 2 || w->cluster == 1,
                 "wae_ar_generate: cluster must be 1,2,4,8 or 16 (got %d)", w->cluster);
-    WAE_REQUIRE(w->utts_per_cluster == 1 || w->utts_per_cluster == 2 || w->utts_per_cluster == 4,
+    WAE_REQUIRE(w->wtype == 2 || w->utts_per_cluster == 1 || w->utts_per_cluster == 2 || w->utts_per_cluster == 4,
                 "wae_ar_generate: utts_per_cluster must be 1, 2 or 4");
     WAE_REQUIRE(d.R % 64 == 0 && d.S % 64 == 0 && d.S <= 64 * MAXMS && d.G % 2 == 0,
                 "wae_ar_generate: need R%%64==0, S%%64==0, S<=256 (R=%d S=%d)", d.R, d.S);
@@ -826,6 +1353,36 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
     WAE_CHECK_LAUNCH();
 
     const int U = w->utts_per_cluster;
+    if (w->wtype == 2) {
+        // tensor-core variant: bf16 weights in the [rows%16][K+8] layout, bf16 conditioning / ring
+        WAE_REQUIRE(sample_mode == WAE_AR_SAMPLE_CATEGORICAL || sample_mode == WAE_AR_SAMPLE_NONE,
+                    "wae_ar_generate: the tensor-core variant samples categorical / none only (scalar-input models: wtype 0/1)");
+        WAE_REQUIRE(U >= 1 && U <= UC, "wae_ar_generate: utts_per_cluster must be 1..8 for the tensor-core variant");
+        WAE_REQUIRE(d.C % 8 == 0 && d.R % 16 == 0 && d.layers >= NPF_M, "wae_ar_generate: tensor-core variant needs C%%8==0, R%%16==0");
+        a.utts = U;
+        const ArMmaLayout ml = ar_mma_layout(d, a.cluster, a.Hp, a.Cp, a.K1p);
+        WAE_REQUIRE(ml.rows1p <= 64 && ml.rows2p <= 128 && ml.rows3p <= 64 && ml.rows4p <= 64,
+                    "wae_ar_generate: row slices too large for the tensor-core variant (use a larger cluster)");
+        WAE_REQUIRE(ml.total <= 232448, "wae_ar_generate: shared memory %d B exceeds 227 KB (use a larger cluster)", ml.total);
+        const int clusters = (B + U - 1) / U;
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(ar_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ml.total));
+        if (a.cluster > 8) WAE_CHECK_CUDA(cudaFuncSetAttribute(ar_mma_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(clusters * a.cluster));
+        cfg.blockDim = dim3(AR_THREADS);
+        cfg.dynamicSmemBytes = ml.total;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)a.cluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, ar_mma_kernel, a, ml));
+        wae::count_launch();
+        return WAE_OK;
+    }
     const int wbytes = (w->wtype == 0) ? 4 : 2;
     const ArSmem sl = ar_smem_layout(d, a.cluster, U, wbytes, a.Hp, a.Cp, a.K1p);
     WAE_REQUIRE(sl.total <= 232448, "wae_ar_generate: shared memory %d B exceeds 227 KB (use a larger cluster or bf16 weights)", sl.total);

@@ -303,6 +303,7 @@ struct LayerArgs {
     CUtensorMap tm_c;    // conditioning [B][T][Cp]  box {64, 128}
     CUtensorMap tm_w1;   // [L][G][K1p]              box {64, G / cluster}: every CTA of a cluster loads one row slice
     CUtensorMap tm_wo;   // [L][R][Hp]               box {64, R / cluster}  and multicasts it to all of them
+    CUtensorMap tm_hst;  // h_all viewed as [L*B][T][Hp], box {64, 128}: TMA store of the gated activations
     const float* gb;     // [B][G]  conv bias + g term of this layer
     const float* bo;     // [R]
     const __nv_bfloat16* x_in;   // [B][T][R]
@@ -364,8 +365,6 @@ __device__ __forceinline__ void layer_epilogue(const LayerArgs& a, int cs, int c
         const int t = t0 + row;
         const bool live = tile_ok && (t < a.T);
         const float* gbp = a.gb + (size_t)b * a.G;
-        __nv_bfloat16* hrow = a.h_out + ((size_t)b * a.T + t) * a.Hp;
-
         // Residual channels of this thread (its column group's chunks of the row): issued NOW, consumed in EPI2, so the
         // L2 round trip hides behind GEMM1 / EPI1 instead of stalling every chunk of EPI2.
         uint4 res[8];
@@ -386,6 +385,10 @@ __device__ __forceinline__ void layer_epilogue(const LayerArgs& a, int cs, int c
         mbar_wait(acc1_full, it & 1);
         LPROF(e_w1);
         tc_fence_after();
+        if (it > 0) {   // the TMA store of the previous tile's h must have finished READING hbuf before it is overwritten
+            if (threadIdx.x == 64) tma_store_wait_read();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+        }
         for (int c0 = cg * 16; c0 < a.Hp; c0 += LAYER_NCG * 16) {
             uint32_t packed[8];
             if (c0 < H) {  // H % 16 == 0 is required by the host wrapper
@@ -413,14 +416,16 @@ __device__ __forceinline__ void layer_epilogue(const LayerArgs& a, int cs, int c
             const uint32_t base = hbuf_addr + kb * A_TILE_BYTES;
             st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
             st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
-            if (live) {
-                uint4* dst = reinterpret_cast<uint4*>(hrow + c0);
-                dst[0] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                dst[1] = make_uint4(packed[4], packed[5], packed[6], packed[7]);
-            }
         }
         tc_fence_before();
-        fence_proxy_async_smem();  // generic-proxy writes of h -> visible to the tensor-core (async) proxy
+        fence_proxy_async_smem();  // generic-proxy writes of h -> visible to the tensor-core / TMA (async) proxy
+        // The h tile in shared memory is already in the TMA 128B-swizzle box format: one thread stores it to the h_all
+        // plane with TMA (rows past T are clipped) instead of 512 threads writing 32 scattered sectors per instruction.
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+        if (threadIdx.x == 64 && tile_ok) {
+            for (int kb = 0; kb < a.Hp / BK; ++kb) tma_store_3d(&a.tm_hst, hbuf + kb * A_TILE_BYTES, kb * BK, t0, a.layer * a.B + b);
+            tma_store_commit();
+        }
         if (kPair) mbar_arrive_cluster(epi1_remote); else mbar_arrive(epi1_done);
         LPROF(e_e1);
 
@@ -462,6 +467,7 @@ __device__ __forceinline__ void layer_epilogue(const LayerArgs& a, int cs, int c
             LPROF(e_e2);
         }
     }
+    if (threadIdx.x == 64) tma_store_wait_all();   // global writes of the last h tile complete before the CTA retires
     if (LPROF_ON && a.prof && threadIdx.x == 64) {
         a.prof[blockIdx.x * 16 + 8] = e_w1; a.prof[blockIdx.x * 16 + 9] = e_e1; a.prof[blockIdx.x * 16 + 10] = e_w2;
         a.prof[blockIdx.x * 16 + 11] = e_e2; a.prof[blockIdx.x * 16 + 12] = e_pre; a.prof[blockIdx.x * 16 + 13] = clock64() - e_t0;
@@ -1170,6 +1176,7 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     const int grid_layer = nclusters * cs;
     if (pair)
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
+    if (int rc = make_tmap(&la.tm_hst, ws.hall, Hp, T, (uint64_t)d.layers * B, Hp, (uint64_t)T * Hp, BK, BM)) return rc;
     la.B = B; la.T = T; la.R = d.R; la.G = d.G; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
     la.tiles_per_utt = tiles_per_utt;
     __nv_bfloat16* cur = ws.xa;

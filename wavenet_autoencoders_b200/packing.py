@@ -199,6 +199,7 @@ def pack_ar(wn, cluster: int = 8, wtype: str = "bf16", utts_per_cluster: int = 2
     mats = _gather_layer_mats(wn, sh)
     dev = mats[0]["w"].device
     Hp, Cp = _ru(H, 64), _ru(sh.C, 64) if sh.C else 0
+    mma = (wtype == "bf16mma")      # tensor-core AR kernel: plain row-major [rows padded to 16][K + 8] bf16 blobs
     dt = torch.float32 if wtype == "fp32" else torch.bfloat16
     esz = 4 if wtype == "fp32" else 2
     l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
@@ -211,9 +212,12 @@ def pack_ar(wn, cluster: int = 8, wtype: str = "bf16", utts_per_cluster: int = 2
         consecutive elements per lane), so the 32 lanes of a warp read one contiguous run of shared memory."""
         nonlocal off
         rows, K = mat.shape
-        ch = 4 * lanes
-        assert K % ch == 0
-        mat = mat.reshape(rows, K // ch, ch).permute(1, 0, 2)
+        if mma:
+            mat = torch.nn.functional.pad(mat, (0, 8, 0, (-rows) % 16))   # 16-byte row padding -> conflict-free ldmatrix
+        else:
+            ch = 4 * lanes
+            assert K % ch == 0
+            mat = mat.reshape(rows, K // ch, ch).permute(1, 0, 2)
         raw = mat.to(dt).contiguous().view(torch.uint8).flatten()
         n = raw.numel()
         pad = (-n) % 16
@@ -253,7 +257,7 @@ def pack_ar(wn, cluster: int = 8, wtype: str = "bf16", utts_per_cluster: int = 2
     t["bf"] = _bias(wn.first_conv, sh.R, dev).contiguous()
     s = _lib.ArWeights()
     s.d = sh.dims()
-    s.wtype = 0 if wtype == "fp32" else 1
+    s.wtype = {"fp32": 0, "bf16": 1, "bf16mma": 2}[wtype]
     s.cluster = cluster
     s.utts_per_cluster = utts_per_cluster
     s.blob = _lib.ptr(t["blob"])

@@ -78,7 +78,8 @@ class WaveNet(nn.Module):
         # ---- B200 execution knobs (not part of the reference API; not in state_dict) ----
         self.precision = os.environ.get("WAE_B200_PRECISION", "fp32")
         self.ar_cluster = None            # None -> 16 CTAs for fp32 weights, 8 for bf16
-        self.ar_utts_per_cluster = 2
+        self.ar_utts_per_cluster = None   # None -> 8 for the tensor-core AR kernel, 2 for the SIMT kernel
+        self.ar_impl = "mma"               # "mma" | "simt" (bf16 precision only)
         self.last_sampled_indices = None  # (B,T) int32 of the last categorical incremental_forward
         self._packs = {}
         self._ws = packing.WorkspaceCache()
@@ -262,9 +263,19 @@ class WaveNet(nn.Module):
             if uniforms is not None:
                 uniforms = uniforms.to(dev).float().contiguous()
 
-            wtype = "fp32" if self.precision == "fp32" else "bf16"
+            # fp32 weights -> SIMT kernel (reference parity); bf16 -> tensor-core (mma.sync) kernel with up to 8 utterances
+            # per cluster, except for scalar-input models whose mixture samplers live in the SIMT kernel only
+            if self.precision == "fp32":
+                wtype = "fp32"
+            else:
+                wtype = "bf16" if (self.scalar_input or self.ar_impl == "simt") else "bf16mma"
             cluster = self.ar_cluster or (16 if wtype == "fp32" else 8)
-            pk = self._pack("ar", cluster=cluster, wtype=wtype, utts_per_cluster=self.ar_utts_per_cluster)
+            upc = self.ar_utts_per_cluster or (8 if wtype == "bf16mma" else 2)
+            if wtype != "bf16mma" and upc not in (1, 2, 4):
+                upc = 2
+            pk = self._pack("ar", cluster=cluster, wtype=wtype, utts_per_cluster=upc)
+            if wtype == "bf16mma" and c_btc is not None:
+                c_btc = c_btc.to(torch.bfloat16).contiguous()
             L = _lib.lib()
             n = L.wae_ar_workspace(pk.struct, B, T)
             ws = self._ws.get(n, dev)
