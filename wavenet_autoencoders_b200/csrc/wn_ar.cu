@@ -759,7 +759,7 @@ inline ArMmaLayout ar_mma_layout(const wae_stack_dims& d, int cs, int Hp, int Cp
     s.off_skip = off; off += up(UC * (s.max_n3 + 1) * 4);
     s.off_b2 = off; off += up((d.layers * s.max_n2 + s.max_n3 + s.max_n4) * 4);
     s.off_stgh = off; off += up(UC * (s.max_np + 8) * 2);
-    s.off_stgx = off; off += up(UC * (maxrows + 8) * 2 > UC * (d.O + 8) * 4 ? UC * (maxrows + 8) * 2 : UC * (d.O + 8) * 4);
+    s.off_stgx = off; off += up(UC * (maxrows + 8) * 2 > UC * (s.max_n4 + 8) * 4 ? UC * (maxrows + 8) * 2 : UC * (s.max_n4 + 8) * 4);
     s.off_boff = off; off += up((2 * d.layers + 2) * 8);
     s.off_misc = off; off += 256;
     s.total = off;
@@ -1149,13 +1149,14 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                         [&](int ks, uint32_t& addr, uint32_t& stride) { addr = saddr + ks * 32; stride = SS * 2; }, red, sl.rows4p, warp, lane);
         }
         __syncthreads();
-        float* stgl = reinterpret_cast<float*>(stgx);       // fp32 logits staging [UC][O + 8]
+        float* stgl = reinterpret_cast<float*>(stgx);       // fp32 logits staging [UC][max_n4 + 8]
+        const int STL = sl.max_n4 + 8;
         for (int e = tid; e < nout * UC; e += AR_THREADS) {
             const int i = e >> 3, u = e & 7;
-            stgl[u * (O + 8) + i] = red_sum(red, sl.rows4p, i, u) + b4c[i];
+            stgl[u * STL + i] = red_sum(red, sl.rows4p, i, u) + b4c[i];
         }
         __syncthreads();
-        allgather_f32(stgl, O + 8, lgbuf, O, oo0, nout, cs, tid);
+        allgather_f32(stgl, STL, lgbuf, O, oo0, nout, cs, tid);
         ++j2;
         cluster_arrive();
         cluster_wait();
