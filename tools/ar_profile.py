@@ -5,16 +5,19 @@ import torch
 from wavenet_autoencoders_b200 import _lib, testing as T
 from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
 
-NAMES = ["x0/firstconv", "xr-load", "wait-W1", "gemv1", "wait-W2", "cluster-wait-1", "gemv2", "cpasync-wait", "cluster-sync-2",
-         "head", "sample"]
+NAMES_SIMT = ["x0/firstconv", "xr-load", "wait-W1", "gemv1", "wait-W2", "cluster-wait-1", "gemv2", "cpasync-wait", "cluster-sync-2",
+              "head", "sample", "-"]
+NAMES_MMA = ["x0/firstconv", "prefetch+gb", "wait-W1", "mma1+sync", "reduce+gate", "allgather-h", "barrier-1", "mma2+sync",
+             "reduce2+allgather-x", "barrier-2+ring", "head", "sample"]
 
-def run(cfg_name, B, Tn, prec, cluster, U):
+def run(cfg_name, B, Tn, prec, cluster, U, impl='simt'):
     cfg = T.CONFIGS[cfg_name]
     torch.manual_seed(0)
     m = WaveNet(**cfg).eval()
     m.load_state_dict(T.synth_state_dict(m, 1))
     m = m.cuda()
-    m.precision, m.ar_cluster, m.ar_utts_per_cluster = prec, cluster, U
+    m.precision, m.ar_cluster, m.ar_utts_per_cluster, m.ar_impl = prec, cluster, U, impl
+    NAMES = NAMES_MMA if (impl == 'mma' and prec == 'bf16') else NAMES_SIMT
     hop = T.hop(cfg)
     lat = torch.randn(B, cfg["cin_channels"], Tn // hop, device="cuda")
     g = torch.randint(0, cfg["n_speakers"], (B, 1), device="cuda")
@@ -30,7 +33,7 @@ def run(cfg_name, B, Tn, prec, cluster, U):
     e1.record(); torch.cuda.synchronize()
     _lib.lib().wae_ar_set_profile_buffer(None)
     ms = e0.elapsed_time(e1)
-    p = buf.view(nct, 16)[:, :11].double().cpu()
+    p = buf.view(nct, 16)[:, :12].double().cpu()
     tot = p.sum(1)
     print(f"--- {cfg_name} B={B} T={Tn} {prec} cluster={cluster} U={U}: {ms:.2f} ms total, {1e3*ms/Tn:.1f} us/step, "
           f"{B*Tn/ms*1e3:.0f} samples/s; cycles/step (CTA0) = {tot[0].item()/Tn:.0f}, max over CTAs {tot.max().item()/Tn:.0f}")
@@ -38,9 +41,6 @@ def run(cfg_name, B, Tn, prec, cluster, U):
         print(f"    {n:16s} CTA0 {p[0, i].item()/Tn:9.0f} cyc/step   mean {p[:, i].mean().item()/Tn:9.0f}   max {p[:, i].max().item()/Tn:9.0f}")
 
 if __name__ == "__main__":
-    run("vqwae", 2, 640, "bf16", 8, 2)
-    run("vqwae", 32, 640, "bf16", 8, 2)
-    run("vqwae", 16, 640, "bf16", 8, 2)
-    run("vqwae", 32, 640, "fp32", 16, 2)
-    run("vqwae", 8, 640, "bf16", 16, 2)
-    run("vqwae", 2, 640, "bf16", 8, 1)
+    run("vqwae", 8, 640, "bf16", 8, 8, "mma")
+    run("vqwae", 64, 640, "bf16", 8, 8, "mma")
+    run("vqwae", 2, 640, "fp32", 16, 2)

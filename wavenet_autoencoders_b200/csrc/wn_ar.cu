@@ -968,6 +968,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     for (int l = 0; l < NPF_M - 1; ++l) prefetch_taps(0, l);
 
     unsigned j1 = 0, j2 = 0;
+    long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt = clock64();
     for (int t = 0; t < a.T; ++t) {
         float u_pref = 0.f;
         if (warp < U && a.uniforms != nullptr) {
@@ -1020,6 +1022,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         prefetch_c(t + 1);
         cp_async_wait<NPF_M - 2>();
         __syncthreads();
+        AR_PROF(0);
 
         // ---- residual layers ----
         for (int l = 0; l < L; ++l) {
@@ -1043,7 +1046,9 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                     }
                 }
             }
+            AR_PROF(1);
             mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
+            AR_PROF(2);
             {
                 const uint32_t xaddr = smem_u32(xl), caddr = smem_u32(cl);
                 mma_gemv<4>(smem_u32(w1buf + (size_t)(j1 & 1) * sl.w1_slot), mt1, W1S, K1p / 16,
@@ -1054,6 +1059,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                             red, sl.rows1p, warp, lane);
             }
             __syncthreads();
+            AR_PROF(3);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 const int e = tid + q * AR_THREADS;
@@ -1067,13 +1073,16 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 }
             }
             __syncthreads();
+            AR_PROF(4);
             allgather_bf16(stgh, STH, hbuf, HS, p0, np, cs, tid);
             ++j1;
+            AR_PROF(5);
             cluster_arrive();
             mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
             cluster_wait();
             if (tid == 0) issue_w1(j1 + 1);
             __syncwarp();
+            AR_PROF(6);
 
             const bool last = (l == L - 1);
             bf16* xnext = xin + (size_t)((seq + 1) % NPF_M) * UC * XS + (kw - 1) * R;
@@ -1084,6 +1093,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                             red, sl.rows2p, warp, lane);
             }
             __syncthreads();
+            AR_PROF(7);
             for (int e = tid; e < n2 * UC; e += AR_THREADS) {
                 const int i = e >> 3, u = e & 7;
                 const float o = red_sum(red, sl.rows2p, i, u) + b2c[(size_t)l * sl.max_n2 + i];
@@ -1101,6 +1111,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 allgather_bf16(stgx, STX, xnext, XS, ro0, nres, cs, tid);
             }
             ++j2;
+            AR_PROF(8);
             cp_async_wait<NPF_M - 2>();
             cluster_arrive();
             if (!last) {
@@ -1113,6 +1124,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             cluster_wait();
             if (tid == 0) issue_w2(j2 + 1);
             __syncwarp();
+            AR_PROF(9);
         }
 
         // ---- head ----
@@ -1163,6 +1175,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         if (tid == 0) issue_w2(j2 + 1);
         __syncwarp();
 
+        AR_PROF(10);
         // ---- output / sampling (categorical or none; scalar-input models use the SIMT kernel) ----
         if (warp < U) {
             const int u = warp, b = cid * U + u;
@@ -1221,7 +1234,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             }
         }
         __syncthreads();
+        AR_PROF(11);
     }
+    if (a.prof != nullptr && tid == 0)
+        for (int i = 0; i < 12; ++i) a.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
     cp_async_wait<0>();
     cluster_sync();
 }
