@@ -761,7 +761,7 @@ inline ArMmaLayout ar_mma_layout(const wae_stack_dims& d, int cs, int Hp, int Cp
     s.off_stgh = off; off += up(UC * (s.max_np + 8) * 2);
     s.off_stgx = off; off += up(UC * (maxrows + 8) * 2 > UC * (s.max_n4 + 8) * 4 ? UC * (maxrows + 8) * 2 : UC * (s.max_n4 + 8) * 4);
     s.off_boff = off; off += up((2 * d.layers + 2) * 8);
-    s.off_misc = off; off += 256;
+    s.off_misc = off; off += 512;   // mbarriers, current class per utterance, ring positions per layer
     s.total = off;
     return s;
 }
@@ -813,6 +813,35 @@ __device__ __forceinline__ void mma_gemv(uint32_t w_addr, int mt, int wstride_by
     }
 }
 
+// Variant for short reductions (K <= 256): warps are dealt (m-tile, k-part) pairs, so only AR_WARPS/mt partial tiles have to be
+// summed afterwards instead of AR_WARPS.  Requires mt to divide AR_WARPS.
+template <class BSrc>
+__device__ __forceinline__ void mma_gemv_msplit(uint32_t w_addr, int mt, int wstride_bytes, int nk, BSrc bsrc, float* red, int rows_pad,
+                                                int warp, int lane) {
+    const int nparts = AR_WARPS / mt, m = warp % mt, part_ = warp / mt;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
+    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
+    for (int ks = part_; ks < nk; ks += nparts) {
+        uint32_t baddr, bstride;
+        bsrc(ks, baddr, bstride);
+        uint32_t b0, b1, a0, a1, a2, a3;
+        ldsm_x2(baddr + brow * bstride + bcol * 2, b0, b1);
+        ldsm_x4(w_addr + (uint32_t)((m * 16 + arow) * wstride_bytes + (ks * 16 + acol) * 2), a0, a1, a2, a3);
+        mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
+    }
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+    float* p = red + ((size_t)part_ * rows_pad + m * 16 + g) * UC + t2;
+    *reinterpret_cast<float2*>(p) = make_float2(acc[0], acc[1]);
+    *reinterpret_cast<float2*>(p + 8 * UC) = make_float2(acc[2], acc[3]);
+}
+
+__device__ __forceinline__ float red_sum_n(const float* red, int rows_pad, int row, int u, int nparts) {
+    float s = 0.f;
+    for (int w = 0; w < nparts; ++w) s += red[((size_t)w * rows_pad + row) * UC + u];
+    return s;
+}
+
 __device__ __forceinline__ float red_sum(const float* red, int rows_pad, int row, int u) {
     float s = 0.f;
 #pragma unroll
@@ -825,10 +854,19 @@ __device__ __forceinline__ void allgather_bf16(const __nv_bfloat16* src, int spi
                                                int cs, int tid) {
     if (((n | off | spitch | dpitch) & 1) == 0) {
         const int nw = n >> 1, per = UC * nw;                      // 32-bit words per destination
-        for (int e = tid; e < cs * per; e += AR_THREADS) {
-            const int r = e / per, w = e - r * per, u = w / nw, i = w - u * nw;
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(src + u * spitch + 2 * i);
-            st_cluster_u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + 2 * i), (uint32_t)r), v);
+        if ((nw & (nw - 1)) == 0) {                                // power-of-two slices (every preset): shifts, no divisions
+            const int sh = 31 - __clz(nw), shp = sh + 3;
+            for (int e = tid; e < cs * per; e += AR_THREADS) {
+                const int r = e >> shp, w = e & (per - 1), u = w >> sh, i = w & (nw - 1);
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(src + u * spitch + 2 * i);
+                st_cluster_u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + 2 * i), (uint32_t)r), v);
+            }
+        } else {
+            for (int e = tid; e < cs * per; e += AR_THREADS) {
+                const int r = e / per, w = e - r * per, u = w / nw, i = w - u * nw;
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(src + u * spitch + 2 * i);
+                st_cluster_u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + 2 * i), (uint32_t)r), v);
+            }
         }
     } else {
         const int per = UC * n;
@@ -844,6 +882,37 @@ __device__ __forceinline__ void allgather_f32(const float* src, int spitch, floa
     for (int e = tid; e < cs * per; e += AR_THREADS) {
         const int r = e / per, w = e - r * per, u = w / n, i = w - u * n;
         st_cluster_f32(mapa(smem_u32(dst + (size_t)u * dpitch + off + i), (uint32_t)r), src[u * spitch + i]);
+    }
+}
+
+// PULL all-gather: every CTA has written its own slice of a [UC][pitch] buffer (elements [part(n,r), part(n,r+1)) of each
+// row belong to rank r) into its OWN shared memory and a cluster barrier has passed; fetch the other ranks' slices through
+// distributed shared memory loads.  Compared with pushing the slice into all peers before the barrier, the barrier's release
+// no longer has to wait for remote stores to drain (measured: ~1.5-2k cycles per barrier with pushes).
+template <typename T>   // T = uint32_t words of 2 bf16, or fp32 bit patterns
+__device__ __forceinline__ void pull_words(T* buf, int pitch_words, int n_words, int elems_per_word, int n_total, int cs, int rank, int tid) {
+    const bool pow2 = ((n_words & (n_words - 1)) == 0) && (n_total % cs == 0) && (((n_total / cs) & ((n_total / cs) - 1)) == 0) &&
+                      ((n_total / cs) % elems_per_word == 0);
+    if (pow2) {
+        const int sh = 31 - __clz(n_words);
+        const int osh = 31 - __clz((n_total / cs) / elems_per_word);      // words per owner
+        for (int e = tid; e < UC * n_words; e += AR_THREADS) {
+            const int u = e >> sh, w = e & (n_words - 1), r = w >> osh;
+            if (r != rank) {
+                T* p = buf + (size_t)u * pitch_words + w;
+                *reinterpret_cast<uint32_t*>(p) = ld_cluster_u32(mapa(smem_u32(p), (uint32_t)r));
+            }
+        }
+    } else {
+        for (int e = tid; e < UC * n_words; e += AR_THREADS) {
+            const int u = e / n_words, w = e - u * n_words;
+            const int el = w * elems_per_word;                              // slice boundaries must be multiples of elems_per_word
+            const int r = ((el + 1) * cs - 1) / n_total;
+            if (r != rank) {
+                T* p = buf + (size_t)u * pitch_words + w;
+                *reinterpret_cast<uint32_t*>(p) = ld_cluster_u32(mapa(smem_u32(p), (uint32_t)r));
+            }
+        }
     }
 }
 
@@ -890,6 +959,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     const int STH = sl.max_np + 8, STX = (sl.rows1p > sl.rows2p ? sl.rows1p : sl.rows2p) + 8;
     float* b3c = b2c + (size_t)L * sl.max_n2;
     float* b4c = b3c + sl.max_n3;
+    const bool msplit2 = (mt2 >= 1 && mt2 <= AR_WARPS && AR_WARPS % mt2 == 0);   // GEMV2: few k-steps -> deal m-tiles to warps
+    const int nparts2 = msplit2 ? AR_WARPS / mt2 : AR_WARPS;
 
     const unsigned n1_total = (unsigned)a.T * L, n2_total = (unsigned)a.T * (L + 2);
     auto issue_w1 = [&](unsigned j) {
@@ -937,18 +1008,49 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     const bf16* ringb = reinterpret_cast<const bf16*>(a.ring);
     bf16* ringw = reinterpret_cast<bf16*>(a.ring);
     const bf16* c_bf = reinterpret_cast<const bf16*>(a.c_btc);
-    auto prefetch_taps = [&](int tt, int l) {
+    // ring slot of the current step per layer (t % ns[l]) is kept incrementally in shared memory: ns = (kw-1)*d+1 is odd,
+    // so every "% ns" would be a real division on the critical path
+    int* rpos = cur_idx + UC;                                    // [L]
+    const int r8 = R / 8;
+    const int pf_chunks = U * (kw - 1) * r8;                      // 16-byte chunks (8 bf16) per layer
+    int pf_c8[2], pf_j[2], pf_u[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int e = tid + q * AR_THREADS;
+        pf_c8[q] = e % r8; pf_j[q] = (kw > 1) ? (e / r8) % (kw - 1) : 0; pf_u[q] = (kw > 1) ? e / (r8 * (kw - 1)) : 0;
+    }
+    auto prefetch_taps = [&](int tt, int l, bool next_step) {
         if (tt < a.T && kw > 1) {
             const int ns = a.ring_ns[l], dil = d.dilation[l];
-            const int r8 = R / 8;
-            const int chunks = U * (kw - 1) * r8;   // 16-byte chunks (8 bf16)
-            for (int e = tid; e < chunks; e += AR_THREADS) {
+            int pos = rpos[l];
+            if (next_step) { pos = (pos + 1 == ns) ? 0 : pos + 1; }
+            const unsigned slot_x = ((unsigned)tt * L + l) % NPF_M;
+            const size_t ring_base = (size_t)a.ring_off[l];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int e = tid + q * AR_THREADS;
+                if (e < pf_chunks) {
+                    const int c8 = pf_c8[q], j = pf_j[q], u = pf_u[q];
+                    const int b = cid * U + u;
+                    const int back = (kw - 1 - j) * dil;
+                    int sl_ = pos - back;
+                    if (sl_ < 0) sl_ += ns;
+                    bf16* dst = xin + ((size_t)slot_x * UC + u) * XS + j * R + c8 * 8;
+                    if (b < a.B && tt - back >= 0)
+                        cp_async16(dst, ringb + (((size_t)b * a.ring_rows + ring_base + sl_) * R + c8 * 8));
+                    else
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            for (int e = tid + 2 * AR_THREADS; e < pf_chunks; e += AR_THREADS) {   // rare: more than 512 chunks
                 const int c8 = e % r8, j = (e / r8) % (kw - 1), u = e / (r8 * (kw - 1));
                 const int b = cid * U + u;
-                const int ts = tt - (kw - 1 - j) * dil;
-                bf16* dst = xin + ((size_t)(((unsigned)tt * L + l) % NPF_M) * UC + u) * XS + j * R + c8 * 8;
-                if (b < a.B && ts >= 0)
-                    cp_async16(dst, ringb + (((size_t)b * a.ring_rows + a.ring_off[l] + (ts % ns)) * R + c8 * 8));
+                const int back = (kw - 1 - j) * dil;
+                int sl_ = pos - back;
+                if (sl_ < 0) sl_ += ns;
+                bf16* dst = xin + ((size_t)slot_x * UC + u) * XS + j * R + c8 * 8;
+                if (b < a.B && tt - back >= 0)
+                    cp_async16(dst, ringb + (((size_t)b * a.ring_rows + ring_base + sl_) * R + c8 * 8));
                 else
                     *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
             }
@@ -964,8 +1066,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             }
         }
     };
+    for (int e = tid; e < L; e += AR_THREADS) rpos[e] = 0;
+    __syncthreads();
     prefetch_c(0);
-    for (int l = 0; l < NPF_M - 1; ++l) prefetch_taps(0, l);
+    for (int l = 0; l < NPF_M - 1; ++l) prefetch_taps(0, l, false);
 
     unsigned j1 = 0, j2 = 0;
     long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1000,22 +1104,31 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         __syncthreads();
         {
             bf16* x0 = xin + (size_t)(((unsigned)t * L) % NPF_M) * UC * XS + (kw - 1) * R;
-            for (int e = tid; e < U * R; e += AR_THREADS) {
-                const int u = e / R, r = e % R;
-                const int ci = cur_idx[u];
-                float acc;
-                if (ci >= 0) {
-                    acc = __ldg(&a.wf[(size_t)ci * R + r]) + __ldg(&a.bf[r]);
-                } else {
-                    acc = 0.f;
-                    for (int o = 0; o < Oin; ++o) acc = fmaf(__ldg(&a.wf[(size_t)o * R + r]), inbuf[u * Oin + o], acc);
-                    acc += __ldg(&a.bf[r]);
+            for (int r = tid; r < R; r += AR_THREADS) {
+                const float bias = __ldg(&a.bf[r]);
+                float acc[UC];
+#pragma unroll
+                for (int u = 0; u < UC; ++u) {
+                    acc[u] = 0.f;
+                    if (u < U) {
+                        const int ci = cur_idx[u];
+                        if (ci >= 0) {
+                            acc[u] = __ldg(&a.wf[(size_t)ci * R + r]);
+                        } else {
+                            for (int o = 0; o < Oin; ++o) acc[u] = fmaf(__ldg(&a.wf[(size_t)o * R + r]), inbuf[u * Oin + o], acc[u]);
+                        }
+                    }
                 }
-                const bf16 xb = __float2bfloat16_rn(acc);
-                x0[(size_t)u * XS + r] = xb;
-                const int b = cid * U + u;
-                if (b < a.B && r >= ro0 && r < ro0 + nres)
-                    ringw[((size_t)b * a.ring_rows + a.ring_off[0] + (t % a.ring_ns[0])) * R + r] = xb;
+                const bool mine = (r >= ro0 && r < ro0 + nres);
+#pragma unroll
+                for (int u = 0; u < UC; ++u) {
+                    if (u < U) {
+                        const bf16 xb = __float2bfloat16_rn(acc[u] + bias);
+                        x0[(size_t)u * XS + r] = xb;
+                        const int b = cid * U + u;
+                        if (mine && b < a.B) ringw[((size_t)b * a.ring_rows + a.ring_off[0] + rpos[0]) * R + r] = xb;
+                    }
+                }
             }
         }
         for (int e = tid; e < UC * (nsk + 1); e += AR_THREADS) skipacc[e] = 0.f;
@@ -1028,7 +1141,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         for (int l = 0; l < L; ++l) {
             {
                 const int lp = l + NPF_M - 1;
-                prefetch_taps(lp < L ? t : t + 1, lp < L ? lp : lp - L);
+                prefetch_taps(lp < L ? t : t + 1, lp < L ? lp : lp - L, lp >= L);
             }
             const unsigned seq = (unsigned)t * L + l;
             const bf16* xl = xin + (size_t)(seq % NPF_M) * UC * XS;
@@ -1069,74 +1182,71 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                     const float zb = red_sum(red, sl.rows1p, 2 * j + 1, u) + gbb[q];
                     const float e2 = __expf(-2.f * fabsf(za));
                     const float th = copysignf(__fdividef(1.f - e2, 1.f + e2), za);
-                    stgh[u * STH + j] = __float2bfloat16_rn(th * __fdividef(1.f, 1.f + __expf(-zb)));
+                    hbuf[u * HS + p0 + j] = __float2bfloat16_rn(th * __fdividef(1.f, 1.f + __expf(-zb)));   // own slice, in place
                 }
             }
-            __syncthreads();
-            AR_PROF(4);
-            allgather_bf16(stgh, STH, hbuf, HS, p0, np, cs, tid);
             ++j1;
-            AR_PROF(5);
+            AR_PROF(4);
             cluster_arrive();
             mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
             cluster_wait();
+            AR_PROF(5);
             if (tid == 0) issue_w1(j1 + 1);
-            __syncwarp();
+            pull_words(reinterpret_cast<uint32_t*>(hbuf), HS / 2, H / 2, 2, H, cs, rank, tid);
+            __syncthreads();
             AR_PROF(6);
 
             const bool last = (l == L - 1);
             bf16* xnext = xin + (size_t)((seq + 1) % NPF_M) * UC * XS + (kw - 1) * R;
             {
                 const uint32_t haddr = smem_u32(hbuf);
-                mma_gemv<8>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt2, W2S, Hp / 16,
-                            [&](int ks, uint32_t& addr, uint32_t& stride) { addr = haddr + ks * 32; stride = HS * 2; },
-                            red, sl.rows2p, warp, lane);
+                auto hsrc = [&](int ks, uint32_t& addr, uint32_t& stride) { addr = haddr + ks * 32; stride = HS * 2; };
+                if (msplit2) mma_gemv_msplit(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt2, W2S, Hp / 16, hsrc, red, sl.rows2p, warp, lane);
+                else mma_gemv<8>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt2, W2S, Hp / 16, hsrc, red, sl.rows2p, warp, lane);
             }
             __syncthreads();
             AR_PROF(7);
             for (int e = tid; e < n2 * UC; e += AR_THREADS) {
                 const int i = e >> 3, u = e & 7;
-                const float o = red_sum(red, sl.rows2p, i, u) + b2c[(size_t)l * sl.max_n2 + i];
+                const float o = red_sum_n(red, sl.rows2p, i, u, nparts2) + b2c[(size_t)l * sl.max_n2 + i];
                 if (i < nres) {
                     if (!last) {
                         const float xo = (o + __bfloat162float(xl[(size_t)u * XS + (kw - 1) * R + ro0 + i])) * 0.70710678118654752440f;
-                        stgx[u * STX + i] = __float2bfloat16_rn(xo);
+                        xnext[(size_t)u * XS + ro0 + i] = __float2bfloat16_rn(xo);      // own slice of the next layer's input, in place
                     }
                 } else {
                     skipacc[u * (nsk + 1) + (i - nres)] += o;
                 }
             }
-            if (!last) {
-                __syncthreads();
-                allgather_bf16(stgx, STX, xnext, XS, ro0, nres, cs, tid);
-            }
             ++j2;
             AR_PROF(8);
             cp_async_wait<NPF_M - 2>();
             cluster_arrive();
-            if (!last) {
-                for (int e = tid; e < U * nres; e += AR_THREADS) {
-                    const int u = e / nres, i = e % nres, b = cid * U + u;
-                    if (b < a.B)
-                        ringw[((size_t)b * a.ring_rows + a.ring_off[l + 1] + (t % a.ring_ns[l + 1])) * R + ro0 + i] = stgx[u * STX + i];
-                }
-            }
             cluster_wait();
             if (tid == 0) issue_w2(j2 + 1);
-            __syncwarp();
+            if (!last) {
+                // ring rows of layer l+1 (own slice) -- covered by the next barrier, long before any prefetch reads them
+                for (int e = tid; e < U * nres; e += AR_THREADS) {
+                    const int u = e / nres, i = e % nres, b_ = cid * U + u;
+                    if (b_ < a.B)
+                        ringw[((size_t)b_ * a.ring_rows + a.ring_off[l + 1] + rpos[l + 1]) * R + ro0 + i] = xnext[(size_t)u * XS + ro0 + i];
+                }
+                pull_words(reinterpret_cast<uint32_t*>(xnext), XS / 2, R / 2, 2, R, cs, rank, tid);
+            }
+            __syncthreads();
             AR_PROF(9);
         }
 
         // ---- head ----
         for (int e = tid; e < UC * nsk; e += AR_THREADS) {
             const int u = e / nsk, i = e % nsk;
-            stgx[u * STX + i] = __float2bfloat16_rn(fmaxf(skipacc[u * (nsk + 1) + i] * a.skip_scale, 0.f));
+            s1buf[u * SS + so0 + i] = __float2bfloat16_rn(fmaxf(skipacc[u * (nsk + 1) + i] * a.skip_scale, 0.f));
         }
-        __syncthreads();
-        allgather_bf16(stgx, STX, s1buf, SS, so0, nsk, cs, tid);
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
+        pull_words(reinterpret_cast<uint32_t*>(s1buf), SS / 2, S / 2, 2, S, cs, rank, tid);
+        __syncthreads();
         {
             const uint32_t saddr = smem_u32(s1buf);
             mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt3, W3S, S / 16,
@@ -1145,35 +1255,31 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         __syncthreads();
         for (int e = tid; e < nsk * UC; e += AR_THREADS) {
             const int i = e >> 3, u = e & 7;
-            stgx[u * STX + i] = __float2bfloat16_rn(fmaxf(red_sum(red, sl.rows3p, i, u) + b3c[i], 0.f));
+            s2buf[u * SS + so0 + i] = __float2bfloat16_rn(fmaxf(red_sum(red, sl.rows3p, i, u) + b3c[i], 0.f));
         }
-        __syncthreads();
-        allgather_bf16(stgx, STX, s2buf, SS, so0, nsk, cs, tid);
         ++j2;
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
         if (tid == 0) issue_w2(j2 + 1);
-        __syncwarp();
+        pull_words(reinterpret_cast<uint32_t*>(s2buf), SS / 2, S / 2, 2, S, cs, rank, tid);
+        __syncthreads();
         {
             const uint32_t saddr = smem_u32(s2buf);
             mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt4, W3S, S / 16,
                         [&](int ks, uint32_t& addr, uint32_t& stride) { addr = saddr + ks * 32; stride = SS * 2; }, red, sl.rows4p, warp, lane);
         }
         __syncthreads();
-        float* stgl = reinterpret_cast<float*>(stgx);       // fp32 logits staging [UC][max_n4 + 8]
-        const int STL = sl.max_n4 + 8;
         for (int e = tid; e < nout * UC; e += AR_THREADS) {
             const int i = e >> 3, u = e & 7;
-            stgl[u * STL + i] = red_sum(red, sl.rows4p, i, u) + b4c[i];
+            lgbuf[u * O + oo0 + i] = red_sum(red, sl.rows4p, i, u) + b4c[i];
         }
-        __syncthreads();
-        allgather_f32(stgl, STL, lgbuf, O, oo0, nout, cs, tid);
         ++j2;
         cluster_arrive();
         cluster_wait();
         if (tid == 0) issue_w2(j2 + 1);
-        __syncwarp();
+        pull_words(lgbuf, O, O, 1, O, cs, rank, tid);
+        __syncthreads();
 
         AR_PROF(10);
         // ---- output / sampling (categorical or none; scalar-input models use the SIMT kernel) ----
@@ -1233,6 +1339,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 if (lane == 0) cur_idx[u] = -1;
             }
         }
+        for (int e = tid; e < L; e += AR_THREADS) { const int v = rpos[e] + 1; rpos[e] = (v == a.ring_ns[e]) ? 0 : v; }
         __syncthreads();
         AR_PROF(11);
     }
@@ -1377,6 +1484,10 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
         WAE_REQUIRE(U >= 1 && U <= UC, "wae_ar_generate: utts_per_cluster must be 1..8 for the tensor-core variant");
         WAE_REQUIRE(d.C % 8 == 0 && d.R % 16 == 0 && d.layers >= NPF_M, "wae_ar_generate: tensor-core variant needs C%%8==0, R%%16==0");
         a.utts = U;
+        for (int r = 1; r < a.cluster; ++r)
+            WAE_REQUIRE(part(H, r, a.cluster) % 2 == 0 && part(d.R, r, a.cluster) % 2 == 0 && part(d.S, r, a.cluster) % 2 == 0,
+                        "wae_ar_generate: the tensor-core variant needs even row-slice boundaries (H=%d R=%d S=%d over %d CTAs); use wtype 1",
+                        H, d.R, d.S, a.cluster);
         const ArMmaLayout ml = ar_mma_layout(d, a.cluster, a.Hp, a.Cp, a.K1p);
         WAE_REQUIRE(ml.rows1p <= 64 && ml.rows2p <= 128 && ml.rows3p <= 64 && ml.rows4p <= 64,
                     "wae_ar_generate: row slices too large for the tensor-core variant (use a larger cluster)");

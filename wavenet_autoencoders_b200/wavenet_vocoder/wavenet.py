@@ -270,6 +270,10 @@ class WaveNet(nn.Module):
             else:
                 wtype = "bf16" if (self.scalar_input or self.ar_impl == "simt") else "bf16mma"
             cluster = self.ar_cluster or (16 if wtype == "fp32" else 8)
+            if wtype == "bf16mma":
+                sh = packing.stack_shape(self)     # the tensor-core kernel exchanges bf16 pairs: slice boundaries must be even
+                if any(packing.part(n, r, cluster) % 2 for n in (sh.H, sh.R, sh.S) for r in range(1, cluster)):
+                    wtype = "bf16"
             upc = self.ar_utts_per_cluster or (8 if wtype == "bf16mma" else 2)
             if wtype != "bf16mma" and upc not in (1, 2, 4):
                 upc = 2
