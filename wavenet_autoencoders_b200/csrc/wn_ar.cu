@@ -1182,18 +1182,19 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                     const float zb = red_sum(red, sl.rows1p, 2 * j + 1, u) + gbb[q];
                     const float e2 = __expf(-2.f * fabsf(za));
                     const float th = copysignf(__fdividef(1.f - e2, 1.f + e2), za);
-                    hbuf[u * HS + p0 + j] = __float2bfloat16_rn(th * __fdividef(1.f, 1.f + __expf(-zb)));   // own slice, in place
+                    stgh[u * STH + j] = __float2bfloat16_rn(th * __fdividef(1.f, 1.f + __expf(-zb)));
                 }
             }
-            ++j1;
+            __syncthreads();
             AR_PROF(4);
+            allgather_bf16(stgh, STH, hbuf, HS, p0, np, cs, tid);
+            ++j1;
+            AR_PROF(5);
             cluster_arrive();
             mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
             cluster_wait();
-            AR_PROF(5);
             if (tid == 0) issue_w1(j1 + 1);
-            pull_words(reinterpret_cast<uint32_t*>(hbuf), HS / 2, H / 2, 2, H, cs, rank, tid);
-            __syncthreads();
+            __syncwarp();
             AR_PROF(6);
 
             const bool last = (l == L - 1);
@@ -1212,41 +1213,43 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 if (i < nres) {
                     if (!last) {
                         const float xo = (o + __bfloat162float(xl[(size_t)u * XS + (kw - 1) * R + ro0 + i])) * 0.70710678118654752440f;
-                        xnext[(size_t)u * XS + ro0 + i] = __float2bfloat16_rn(xo);      // own slice of the next layer's input, in place
+                        stgx[u * STX + i] = __float2bfloat16_rn(xo);
                     }
                 } else {
                     skipacc[u * (nsk + 1) + (i - nres)] += o;
                 }
             }
+            if (!last) {
+                __syncthreads();
+                allgather_bf16(stgx, STX, xnext, XS, ro0, nres, cs, tid);
+            }
             ++j2;
             AR_PROF(8);
             cp_async_wait<NPF_M - 2>();
             cluster_arrive();
+            if (!last) {
+                for (int e = tid; e < U * nres; e += AR_THREADS) {
+                    const int u = e / nres, i = e % nres, b = cid * U + u;
+                    if (b < a.B)
+                        ringw[((size_t)b * a.ring_rows + a.ring_off[l + 1] + rpos[l + 1]) * R + ro0 + i] = stgx[u * STX + i];
+                }
+            }
             cluster_wait();
             if (tid == 0) issue_w2(j2 + 1);
-            if (!last) {
-                // ring rows of layer l+1 (own slice) -- covered by the next barrier, long before any prefetch reads them
-                for (int e = tid; e < U * nres; e += AR_THREADS) {
-                    const int u = e / nres, i = e % nres, b_ = cid * U + u;
-                    if (b_ < a.B)
-                        ringw[((size_t)b_ * a.ring_rows + a.ring_off[l + 1] + rpos[l + 1]) * R + ro0 + i] = xnext[(size_t)u * XS + ro0 + i];
-                }
-                pull_words(reinterpret_cast<uint32_t*>(xnext), XS / 2, R / 2, 2, R, cs, rank, tid);
-            }
-            __syncthreads();
+            __syncwarp();
             AR_PROF(9);
         }
 
         // ---- head ----
         for (int e = tid; e < UC * nsk; e += AR_THREADS) {
             const int u = e / nsk, i = e % nsk;
-            s1buf[u * SS + so0 + i] = __float2bfloat16_rn(fmaxf(skipacc[u * (nsk + 1) + i] * a.skip_scale, 0.f));
+            stgx[u * STX + i] = __float2bfloat16_rn(fmaxf(skipacc[u * (nsk + 1) + i] * a.skip_scale, 0.f));
         }
+        __syncthreads();
+        allgather_bf16(stgx, STX, s1buf, SS, so0, nsk, cs, tid);
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
-        pull_words(reinterpret_cast<uint32_t*>(s1buf), SS / 2, S / 2, 2, S, cs, rank, tid);
-        __syncthreads();
         {
             const uint32_t saddr = smem_u32(s1buf);
             mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt3, W3S, S / 16,
@@ -1255,31 +1258,35 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         __syncthreads();
         for (int e = tid; e < nsk * UC; e += AR_THREADS) {
             const int i = e >> 3, u = e & 7;
-            s2buf[u * SS + so0 + i] = __float2bfloat16_rn(fmaxf(red_sum(red, sl.rows3p, i, u) + b3c[i], 0.f));
+            stgx[u * STX + i] = __float2bfloat16_rn(fmaxf(red_sum(red, sl.rows3p, i, u) + b3c[i], 0.f));
         }
+        __syncthreads();
+        allgather_bf16(stgx, STX, s2buf, SS, so0, nsk, cs, tid);
         ++j2;
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
         if (tid == 0) issue_w2(j2 + 1);
-        pull_words(reinterpret_cast<uint32_t*>(s2buf), SS / 2, S / 2, 2, S, cs, rank, tid);
-        __syncthreads();
+        __syncwarp();
         {
             const uint32_t saddr = smem_u32(s2buf);
             mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt4, W3S, S / 16,
                         [&](int ks, uint32_t& addr, uint32_t& stride) { addr = saddr + ks * 32; stride = SS * 2; }, red, sl.rows4p, warp, lane);
         }
         __syncthreads();
+        float* stgl = reinterpret_cast<float*>(stgx);       // fp32 logits staging [UC][max_n4 + 8]
+        const int STL = sl.max_n4 + 8;
         for (int e = tid; e < nout * UC; e += AR_THREADS) {
             const int i = e >> 3, u = e & 7;
-            lgbuf[u * O + oo0 + i] = red_sum(red, sl.rows4p, i, u) + b4c[i];
+            stgl[u * STL + i] = red_sum(red, sl.rows4p, i, u) + b4c[i];
         }
+        __syncthreads();
+        allgather_f32(stgl, STL, lgbuf, O, oo0, nout, cs, tid);
         ++j2;
         cluster_arrive();
         cluster_wait();
         if (tid == 0) issue_w2(j2 + 1);
-        pull_words(lgbuf, O, O, 1, O, cs, rank, tid);
-        __syncthreads();
+        __syncwarp();
 
         AR_PROF(10);
         // ---- output / sampling (categorical or none; scalar-input models use the SIMT kernel) ----
