@@ -144,7 +144,8 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
                            int B, int T, float* logits, void* workspace, size_t workspace_bytes,
                            void* stream);
 
-/* Variant of the bf16 residual-layer kernel: 0 (default) = CTA-pair kernel (tcgen05 cta_group::2, M = 256 per MMA, each CTA
+/* Variant of the bf16 residual-layer kernel: -1 (default) = version-2 kernel (residual added by an identity MMA, x' and h
+ * stored by TMA from shared memory); 0 = CTA-pair kernel (tcgen05 cta_group::2, M = 256 per MMA, each CTA
  * holds half of every weight k-block); 1, 2 or 4 = the 1-CTA kernel in clusters of that size, the CTAs of a cluster sharing
  * every weight k-block through TMA multicast. */
 int wae_set_layer_cluster(int cs);

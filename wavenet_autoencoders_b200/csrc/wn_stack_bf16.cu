@@ -304,6 +304,7 @@ struct LayerArgs {
     CUtensorMap tm_w1;   // [L][G][K1p]              box {64, G / cluster}: every CTA of a cluster loads one row slice
     CUtensorMap tm_wo;   // [L][R][Hp]               box {64, R / cluster}  and multicasts it to all of them
     CUtensorMap tm_hst;  // h_all viewed as [L*B][T][Hp], box {64, 128}: TMA store of the gated activations
+    CUtensorMap tm_xout; // layer output [B][T][R], box {64, 128}: TMA store of x' (version-2 kernel)
     const float* gb;     // [B][G]  conv bias + g term of this layer
     const float* bo;     // [R]
     const __nv_bfloat16* x_in;   // [B][T][R]
@@ -635,6 +636,272 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_kernel(const __gr
     tc_fence_before();
     __syncthreads();
     if (cs > 1) cluster_sync();   // no CTA retires while a peer may still multicast into it or arrive on its barriers
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused residual layer, version 2 (default): no per-thread global memory traffic in the epilogues
+// ---------------------------------------------------------------------------------------------
+// Role counters of the first versions (profiles/layer_roles_r1.txt) showed the kernel bound by its epilogues, and those by the
+// load/store unit: one sample row per thread means every global load/store instruction of a warp touches 32 different
+// cache lines.  Version 2 removes all of them:
+//   * the residual add is done by the tensor core: while GEMM1 walks the k-blocks of the newest tap (time shift 0) its A tile
+//     IS x[t0:t0+128, 64j:64j+64], so four extra N=64 MMAs against a 64x64 identity tile accumulate x into the GEMM2
+//     accumulator (bf16 * 1.0 in fp32 is exact); GEMM2 then accumulates Wo*h on top;
+//   * EPI2 only reads TMEM, adds the bias, scales, and writes bf16 into shared memory in the TMA box layout; one thread
+//     stores the 128 x R tile with TMA (rows past T are clipped);
+//   * h is stored the same way from the GEMM2 operand buffer (as before).
+// Shared memory: 3 stages x 48 KB, the h / x' staging tiles (x' reuses the h tiles once GEMM2 is done), the identity tile.
+constexpr int V2_STAGES = 3;
+
+template <int kDummy>
+__device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles, uint32_t tmem_acc1, uint32_t tmem_acc2, uint8_t* hx,
+                                                  float* sb_bo, uint64_t* acc1_full, uint64_t* acc2_full, uint64_t* epi1_done,
+                                                  uint64_t* epi2_done) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int H = a.G / 2;
+    const bool has_out = (a.x_out != nullptr);
+    const int q = warp & 3;
+    const int cg = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t hx_addr = smem_u32(hx);
+    for (int i = threadIdx.x - 64; i < a.R; i += 32 * LAYER_EPI_WARPS) sb_bo[i] = __ldg(a.bo + i);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+        const float* gbp = a.gb + (size_t)b * a.G;
+
+        // ---- EPI1: gate ----
+        mbar_wait(acc1_full, it & 1);
+        tc_fence_after();
+        if (it > 0) {   // the TMA stores of the previous tile (h and x') must have finished READING the staging tiles
+            if (threadIdx.x == 64) tma_store_wait_read();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+        }
+        for (int c0 = cg * 16; c0 < a.Hp; c0 += LAYER_NCG * 16) {
+            uint32_t packed[8];
+            if (c0 < H) {
+                float va[16], vb[16];
+                tmem_ld16(tmem_acc1 + lane_base + c0, va);
+                tmem_ld16(tmem_acc1 + lane_base + H + c0, vb);
+                float ba[16], bb[16];
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
+                    *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + H + c0 + i));
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i += 2) {
+                    const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
+                    const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
+                    packed[i >> 1] = pack_bf16x2(h0, h1);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) packed[i] = 0u;
+            }
+            const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+            const uint32_t base = hx_addr + kb * A_TILE_BYTES;
+            st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+            st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+        if (threadIdx.x == 64) {
+            for (int kb = 0; kb < a.Hp / BK; ++kb) tma_store_3d(&a.tm_hst, hx + kb * A_TILE_BYTES, kb * BK, t0, a.layer * a.B + b);
+            tma_store_commit();
+        }
+        mbar_arrive(epi1_done);
+
+        // ---- EPI2: x' = (acc2 + bo) * sqrt(.5)   (acc2 already holds Wo*h + x) ----
+        if (has_out) {
+            mbar_wait(acc2_full, it & 1);
+            tc_fence_after();
+            // GEMM2 has finished reading the h tiles; the h TMA store must have finished reading them too before x' overwrites them
+            if (threadIdx.x == 64) tma_store_wait_read();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int c0 = (cg + LAYER_NCG * jj) * 16;
+                if (c0 < a.R) {
+                    float v[16];
+                    tmem_ld16(tmem_acc2 + lane_base + c0, v);
+                    float bo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bo[i]) = *reinterpret_cast<const float4*>(sb_bo + c0 + i);
+                    tmem_ld_wait();
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        packed[i] = pack_bf16x2((v[2 * i] + bo[2 * i]) * kSqrtHalf, (v[2 * i + 1] + bo[2 * i + 1]) * kSqrtHalf);
+                    const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                    const uint32_t base = hx_addr + kb * A_TILE_BYTES;
+                    st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                    st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(epi2_done);     // acc2 is drained: the MMA warp may start the next tile's residual MMAs
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+            if (threadIdx.x == 64) {
+                for (int kb = 0; kb < a.R / BK; ++kb) tma_store_3d(&a.tm_xout, hx + kb * A_TILE_BYTES, kb * BK, t0, b);
+                tma_store_commit();
+            }
+        }
+    }
+    if (threadIdx.x == 64) tma_store_wait_all();
+}
+
+__global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const __grid_constant__ LayerArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int B_BYTES = 256 * BK * 2;
+    const int STAGE_BYTES = A_TILE_BYTES + B_BYTES;
+    const int nkh = a.Hp / BK, nkr = a.R / BK;
+    const int hx_tiles = nkh > nkr ? nkh : nkr;
+    uint8_t* hx = smem + V2_STAGES * STAGE_BYTES;                 // h tiles (GEMM2 A operand), later the x' staging tiles
+    uint8_t* ident = hx + hx_tiles * A_TILE_BYTES;                // 64 x 64 bf16 identity, K-major, 128B swizzle (8 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ident + 64 * BK * 2);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + V2_STAGES;
+    uint64_t* acc1_full = bars + 2 * V2_STAGES;
+    uint64_t* epi1_done = acc1_full + 1;
+    uint64_t* acc2_full = acc1_full + 2;
+    uint64_t* epi2_done = acc1_full + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
+
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc1_full, 1);
+        mbar_init(epi1_done, 32 * LAYER_EPI_WARPS);
+        mbar_init(acc2_full, 1);
+        mbar_init(epi2_done, 32 * LAYER_EPI_WARPS);
+        fence_mbar_init();
+        tma_prefetch_desc(&a.tm_x);
+        tma_prefetch_desc(&a.tm_c);
+        tma_prefetch_desc(&a.tm_w1);
+        tma_prefetch_desc(&a.tm_wo);
+        tma_prefetch_desc(&a.tm_hst);
+        tma_prefetch_desc(&a.tm_xout);
+    }
+    // identity tile: element (n, k) = (n == k); 16-byte chunk c16 of row n holds k = 8*c16 .. 8*c16+7
+    for (int e = threadIdx.x; e < 64 * 8; e += LAYER_THREADS) {
+        const int n = e >> 3, c16 = e & 7;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if ((n >> 3) == c16) w[(n & 7) >> 1] = (n & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 in the high / low half
+        st_shared_v4(smem_u32(ident) + sw128_off(n, c16), w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async_smem();
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc1 = tmem_base;        // columns [0, G)
+    const uint32_t tmem_acc2 = tmem_base + 256;  // columns [256, 256+R)
+
+    const int ntiles = a.B * a.tiles_per_utt;
+    const int rk = a.R / BK;                     // k-blocks per tap
+    const int nk_old = (a.kw - 1) * rk;          // taps with a time shift
+    const int nk_c = a.Cp / BK;
+    const int nk1 = nk_old + nk_c + rk;          // + the newest tap, walked LAST (its A tiles also feed the residual MMAs)
+    const bool has_out = (a.x_out != nullptr);
+    const int w1_bytes = a.G * BK * 2, wo_bytes = a.R * BK * 2;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            Ring ring(V2_STAGES);
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+                for (int kb = 0; kb < nk1; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + w1_bytes);
+                    int kcol;
+                    if (kb < nk_old) {
+                        const int tap = kb / rk, r0 = (kb % rk) * BK;
+                        tma_load_3d(&a.tm_x, &full[ring.stage], sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
+                        kcol = tap * a.R + r0;
+                    } else if (kb < nk_old + nk_c) {
+                        const int c0 = (kb - nk_old) * BK;
+                        tma_load_3d(&a.tm_c, &full[ring.stage], sa, c0, t0, b);
+                        kcol = a.kw * a.R + c0;
+                    } else {
+                        const int r0 = (kb - nk_old - nk_c) * BK;
+                        tma_load_3d(&a.tm_x, &full[ring.stage], sa, r0, t0, b);
+                        kcol = (a.kw - 1) * a.R + r0;
+                    }
+                    tma_load_3d(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES, kcol, 0, a.layer);
+                    ring.advance();
+                }
+                if (has_out) {
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                        uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                        mbar_arrive_expect_tx(&full[ring.stage], wo_bytes);
+                        tma_load_3d(&a.tm_wo, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, a.layer);
+                        ring.advance();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            Ring ring(V2_STAGES);
+            const uint32_t idesc1 = umma_idesc_bf16(BM, a.G);
+            const uint32_t idesc2 = umma_idesc_bf16(BM, a.R);
+            const uint32_t idesc_id = umma_idesc_bf16(BM, 64);
+            const uint64_t id_desc = umma_desc_sw128(smem_u32(ident));
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                if (!has_out && it > 0) { mbar_wait(epi1_done, (it - 1) & 1); tc_fence_after(); }
+                for (int kb = 0; kb < nk1; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    issue_kblock(tmem_acc1, sa, sa + A_TILE_BYTES, idesc1, kb == 0);
+                    if (has_out && kb >= nk_old + nk_c) {
+                        // residual: acc2[:, 64j .. 64j+63] = x tile (A) x I^T  -- needs acc2 drained by the previous tile's EPI2
+                        const int j = kb - nk_old - nk_c;
+                        if (j == 0 && it > 0) { mbar_wait(epi2_done, (it - 1) & 1); tc_fence_after(); }
+                        const uint64_t ad = umma_desc_sw128(sa);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16(tmem_acc2 + 64 * j, ad + (uint64_t)(2 * k), id_desc + (uint64_t)(2 * k), idesc_id, k == 0 ? 0u : 1u);
+                    }
+                    umma_commit(&empty[ring.stage]);
+                    ring.advance();
+                }
+                umma_commit(acc1_full);
+                if (has_out) {
+                    mbar_wait(epi1_done, it & 1);  // h is in shared memory, acc1 drained
+                    tc_fence_after();
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait(&full[ring.stage], ring.phase);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                        issue_kblock(tmem_acc2, smem_u32(hx + kb * A_TILE_BYTES), sb, idesc2, false);   // accumulate on top of x
+                        umma_commit(&empty[ring.stage]);
+                        ring.advance();
+                    }
+                    umma_commit(acc2_full);
+                }
+            }
+        }
+    } else {
+        layer_epilogue_v2<0>(a, ntiles, tmem_acc1, tmem_acc2, hx, reinterpret_cast<float*>(bars) + 64, acc1_full, acc2_full,
+                             epi1_done, epi2_done);
+    }
+    tc_fence_before();
+    __syncthreads();
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
@@ -1010,7 +1277,7 @@ struct Profiler {
 };
 Profiler g_prof;
 long long* g_layer_prof = nullptr;
-int g_layer_mode = 0;      // 0 = CTA-pair kernel (tcgen05 cta_group::2), 1 = 1-CTA kernel (wae_set_layer_cluster)
+int g_layer_mode = 2;      // 2 = version-2 1-CTA kernel (default), 0 = CTA-pair kernel (cta_group::2), 1 = first 1-CTA kernel
 int g_layer_cluster = 1;   // 1-CTA kernel only: 1, 2 or 4 CTAs share every weight k-block via TMA multicast
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a, b; bool on;
@@ -1071,8 +1338,9 @@ void wae_profile_enable(int on) { g_prof.on = (on != 0); }
 void wae_layer_set_profile_buffer(int64_t* dev_buf) { g_layer_prof = reinterpret_cast<long long*>(dev_buf); }
 
 int wae_set_layer_cluster(int cs) {
+    if (cs == -1) { g_layer_mode = 2; return WAE_OK; }    // version-2 kernel (default)
     if (cs == 0) { g_layer_mode = 0; return WAE_OK; }     // CTA-pair kernel
-    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be 0, 1, 2 or 4");
+    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be -1, 0, 1, 2 or 4");
     g_layer_mode = 1;
     g_layer_cluster = cs;
     return WAE_OK;
@@ -1165,7 +1433,8 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     }
     // Layer-kernel variant: CTA pairs (cta_group::2, default) or the 1-CTA kernel in clusters of 1/2/4 with weight multicast.
     const bool pair = (g_layer_mode == 0) && d.G % 32 == 0 && d.R % 32 == 0;
-    int cs = pair ? 2 : g_layer_cluster;
+    const bool v2 = (g_layer_mode == 2);
+    int cs = pair ? 2 : (v2 ? 1 : g_layer_cluster);
     while (!pair && cs > 1 && (d.G % (8 * cs) != 0 || d.R % (8 * cs) != 0)) cs >>= 1;
     if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, d.G, d.layers, K1p, (uint64_t)d.G * K1p, BK, d.G / cs)) return rc;
     if (int rc = make_tmap(&la.tm_wo, w->wo, Hp, d.R, d.layers, Hp, (uint64_t)d.R * Hp, BK, d.R / cs)) return rc;
@@ -1176,6 +1445,12 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     const int grid_layer = nclusters * cs;
     if (pair)
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
+    const int hx_tiles = (Hp / BK) > (d.R / BK) ? (Hp / BK) : (d.R / BK);
+    const size_t smem_v2 = 1024 + (size_t)V2_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)hx_tiles * A_TILE_BYTES + 64 * BK * 2 + 256 + 1024;
+    if (v2) {
+        WAE_REQUIRE(smem_v2 <= 232448, "wae_stack_forward_bf16: layer kernel (v2) shared memory %zu too large", smem_v2);
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
+    }
     if (int rc = make_tmap(&la.tm_hst, ws.hall, Hp, T, (uint64_t)d.layers * B, Hp, (uint64_t)T * Hp, BK, BM)) return rc;
     la.B = B; la.T = T; la.R = d.R; la.G = d.G; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
     la.tiles_per_utt = tiles_per_utt;
@@ -1183,6 +1458,7 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     __nv_bfloat16* nxt = ws.xb;
     for (int l = 0; l < d.layers; ++l) {
         la.tm_x = (cur == ws.xa) ? tm_xa : tm_xb;
+        la.tm_xout = (cur == ws.xa) ? tm_xb : tm_xa;
         la.gb = ws.gb + (size_t)l * B * d.G;
         la.bo = w->bo + (size_t)l * d.R;
         la.x_in = cur;
@@ -1196,7 +1472,7 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)grid_layer);
             cfg.blockDim = dim3(LAYER_THREADS);
-            cfg.dynamicSmemBytes = smem_layer;
+            cfg.dynamicSmemBytes = v2 ? smem_v2 : smem_layer;
             cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1205,7 +1481,8 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            if (pair) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair_kernel, la));
+            if (v2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v2_kernel, la));
+            else if (pair) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair_kernel, la));
             else WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_kernel, la));
         }
         WAE_CHECK_LAUNCH();
