@@ -10,7 +10,7 @@ of synthetic 16 kHz audio per GPU, with synthetic MFCC conditioning and random-i
   value     device-timed samples/s, inputs resident in HBM, tcgen05 bf16 kernels (weak scaling: 16 utt per GPU)
   e2e       the same through the public module API from pinned HOST buffers: H2D of the mu-law class indices, MFCCs
             and speaker ids, on-device one-hot, forward, teacher-forced NLL, D2H of the loss -- all inside the timing
-  roofline  the residual-layer kernel (layer_bf16_kernel): algorithmic FLOPs / CUDA-event time vs the measured bf16 peak
+  roofline  the residual-layer kernel (layer_bf16_v2_kernel): algorithmic FLOPs / CUDA-event time vs the measured bf16 peak
   cpu_baseline   oracle/torch_port.py (the reference's ATen calls, folded weights) on the host cores, bounded sample
   extras    fp32-faithful stack, autoregressive synthesis (config 4 shape, truncated T), VQ search throughput
 
@@ -276,7 +276,7 @@ def main():
     flops_per_launch = B * T_SAMPLES * (FLOP_PER_SAMPLE_LAYER - 2 * 128 * 256 / n_layers)   # last layer has no residual 1x1
     peak_tf, peak_hbm, peak_src = _peaks()
     achieved = flops_per_launch / (layer_ms * 1e-3) / 1e12
-    roofline = {"kernel": "layer_bf16_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+    roofline = {"kernel": "layer_bf16_v2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": layer_ms, "share_of_step": float(ms_kind[1]) / prof_total,
                 "head_share_of_step": float(ms_kind[2]) / prof_total, "prep_share_of_step": float(ms_kind[0]) / prof_total,
