@@ -143,6 +143,15 @@ size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T);
 int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb,
                            int B, int T, float* logits, void* workspace, size_t workspace_bytes,
                            void* stream);
+/*
+ * Same forward with the LAST stage of the conditioning upsampler (wavenet_vocoder/upsample.py:53-64: nearest stretch by
+ * `up_scale` + the 1 x (2*up_scale+1) smoothing filter `up_filter`, weight norm folded) fused into the stack's own
+ * conditioning-layout pass: c_frames is the (B, C, Tc) fp32 output of the stage before it, Tc * up_scale == T.  The
+ * (B, C, T) fp32 conditioning tensor is never materialised.
+ */
+int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const float* c_frames, int Tc, int up_scale,
+                              const float* up_filter, const float* gemb, int B, int T, float* logits,
+                              void* workspace, size_t workspace_bytes, void* stream);
 
 /* Variant of the bf16 residual-layer kernel: -1 (default) = version-2 kernel (residual added by an identity MMA, x' and h
  * stored by TMA from shared memory); 0 = CTA-pair kernel (tcgen05 cta_group::2, M = 256 per MMA, each CTA

@@ -72,6 +72,27 @@ def test_forward_bf16_matches_reference_golden(case):
     assert err < TOL_BF16, err
 
 
+@pytest.mark.parametrize("case", ["wavenet_tiny", "wavenet_vqwae"])
+def test_forward_bf16_fused_last_upsample_stage(case):
+    """wae_stack_forward_bf16_up (last upsampler stage fused into the stack) against the unfused call on the
+    materialised (B,C,T) conditioning, and the mixed one-hot / dense first-conv path inside one block."""
+    g, cfg, m, x, c, spk = _inputs(case)
+    m.precision = "bf16"
+    with torch.no_grad():
+        assert m.upsample_net(c, defer_last=True) is not None          # the fused path is the one forward() takes
+        y_fused = m(x, c, spk)
+        c_up = m.upsample_net(c)
+        y_plain = m.stack_forward(x, c_up, m._speaker_vectors(spk, x.shape[0]))
+        assert rel_err(y_fused.cpu().numpy(), y_plain.cpu().numpy()) < 5e-3
+        x2 = x.clone()
+        x2[:, :, 5::7] = torch.softmax(torch.randn_like(x2[:, :, 5::7]), dim=1)   # every 7th sample dense
+        m.precision = "fp32"
+        y32 = m(x2, c, spk)
+        m.precision = "bf16"
+        y16 = m(x2, c, spk)
+    assert rel_err(y16.cpu().numpy(), y32.cpu().numpy()) < TOL_BF16
+
+
 def test_forward_ragged_tail_and_dense_input_fp32_bf16():
     """T not a multiple of any tile size; dense (non one-hot) x exercises the first-conv GEMV path."""
     cfg = dict(T.CONFIGS["tiny"], upsample_conditional_features=False)

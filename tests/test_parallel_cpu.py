@@ -35,7 +35,8 @@ def _worker(rank, world, port, q):
         n = parallel.allreduce_gradients(m)
         grads = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
         u = parallel.utterance_uniforms(ids, 8, 1, seed=7, device="cpu")
-        q.put((rank, n, grads, list(ids), u))
+        # numpy (pickled by value): tensors travel as shared-memory handles that die with an exiting worker
+        q.put((rank, n, grads.numpy(), list(ids), u.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -48,6 +49,7 @@ def test_dp_allreduce_and_sharding_world2():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=180) for _ in range(world)], key=lambda r: r[0])
+    res = [(r, n, torch.from_numpy(gr), ids, torch.from_numpy(u)) for r, n, gr, ids, u in res]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

@@ -68,6 +68,8 @@ SIGNATURES = {
     "wae_stack_workspace_bf16": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),
     "wae_stack_forward_bf16": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wae_stack_forward_bf16_up": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "wae_set_layer_cluster": (C.c_int, [C.c_int]),
     "wae_layer_set_profile_buffer": (None, [C.c_void_p]),
     "wae_profile_enable": (None, [C.c_int]),

@@ -229,51 +229,81 @@ gbias_bf16_kernel(const float* __restrict__ b1, const float* __restrict__ wg, co
 
 // first_conv on (B,Oin,T) fp32 input -> bf16 channels-last [B][T][R].  One-hot columns (the
 // mu-law input of every preset) are detected per sample and become a gather of one weight row;
-// anything else takes the dense dot product.  32 samples per block.
-constexpr int FC_T = 32;
+// anything else takes the dense dot product.  64 samples per block: the scan reads every input
+// row as 256 contiguous bytes (16 lanes x float4), 16 rows in flight per pass; the writer emits
+// 16-byte channel groups.
+constexpr int FC_T = 64;
 __global__ void __launch_bounds__(256)
 first_conv_bf16_kernel(const float* __restrict__ x, const float* __restrict__ wf, const float* __restrict__ bf,
-                       int T, int Oin, int R, __nv_bfloat16* __restrict__ x0) {
-    extern __shared__ float xs[];  // [Oin][FC_T+1]
-    __shared__ int hot[FC_T];
-    const int b = blockIdx.y, t0 = blockIdx.x * FC_T;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int e = tid; e < Oin * FC_T; e += 256) {
-        const int o = e / FC_T, tt = e % FC_T;
-        const int t = t0 + tt;
-        xs[o * (FC_T + 1) + tt] = (t < T) ? __ldg(&x[((size_t)b * Oin + o) * T + t]) : 0.f;
-    }
+                       int T, int Oin, int R, int vec_ok, __nv_bfloat16* __restrict__ x0) {
+    __shared__ int s_cnt[FC_T], s_pos[FC_T], s_bad[FC_T];
+    const int b = blockIdx.y, t0 = blockIdx.x * FC_T, tid = threadIdx.x;
+    const float* xb = x + (size_t)b * Oin * T;
+    if (tid < FC_T) { s_cnt[tid] = 0; s_pos[tid] = -1; s_bad[tid] = 0; }
     __syncthreads();
-    // one-hot detection: warp w scans samples w*4 .. w*4+3
-    for (int s = 0; s < FC_T / 8; ++s) {
-        const int tt = warp * (FC_T / 8) + s;
-        int nz = 0, pos = -1;
-        bool is_one = true;
-        for (int o = lane; o < Oin; o += 32) {
-            const float v = xs[o * (FC_T + 1) + tt];
-            if (v != 0.f) { ++nz; pos = o; is_one = is_one && (v == 1.f); }
+    {
+        const int q = tid & 15, ol = tid >> 4;
+        const int t = t0 + q * 4;
+        int cnt[4] = {0, 0, 0, 0}, pos[4] = {-1, -1, -1, -1}, bad[4] = {0, 0, 0, 0};
+        if (t < T) {
+#pragma unroll 4
+            for (int o = ol; o < Oin; o += 16) {
+                float v[4];
+                const float* src = xb + (size_t)o * T + t;
+                if (vec_ok) {
+                    const float4 f = __ldg(reinterpret_cast<const float4*>(src));
+                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = (t + j < T) ? __ldg(src + j) : 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (v[j] != 0.f) { ++cnt[j]; pos[j] = o; bad[j] |= (v[j] != 1.f); }
+            }
         }
-        const int nz_all = __reduce_add_sync(0xffffffffu, nz);
-        const int pos_all = __reduce_max_sync(0xffffffffu, pos);
-        const bool ok = __all_sync(0xffffffffu, is_one);
-        if (lane == 0) hot[tt] = (Oin > 1 && nz_all == 1 && ok) ? pos_all : -1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (cnt[j]) {
+                atomicAdd(&s_cnt[q * 4 + j], cnt[j]);
+                atomicMax(&s_pos[q * 4 + j], pos[j]);
+                if (bad[j]) s_bad[q * 4 + j] = 1;
+            }
     }
     __syncthreads();
-    for (int tt = 0; tt < FC_T; ++tt) {
+    const int r8n = R >> 3;
+    for (int e = tid; e < FC_T * r8n; e += 256) {
+        const int tt = e / r8n, r = (e - tt * r8n) * 8;
         const int t = t0 + tt;
         if (t >= T) break;
-        const int h = hot[tt];
-        for (int r = tid; r < R; r += 256) {
-            float acc;
-            if (h >= 0) {
-                acc = __ldg(&wf[(size_t)h * R + r]) + __ldg(&bf[r]);
-            } else {
-                acc = 0.f;
-                for (int o = 0; o < Oin; ++o) acc = fmaf(__ldg(&wf[(size_t)o * R + r]), xs[o * (FC_T + 1) + tt], acc);
-                acc += __ldg(&bf[r]);
+        const int h = (Oin > 1 && s_cnt[tt] == 1 && !s_bad[tt]) ? s_pos[tt] : -1;
+        float acc[8];
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bf + r)), b1 = __ldg(reinterpret_cast<const float4*>(bf + r + 4));
+        const float bias[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        if (h >= 0) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wf + (size_t)h * R + r));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wf + (size_t)h * R + r + 4));
+            const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = w[j] + bias[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+            for (int o = 0; o < Oin; ++o) {
+                const float xv = __ldg(xb + (size_t)o * T + t);
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wf + (size_t)o * R + r));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(wf + (size_t)o * R + r + 4));
+                const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(w[j], xv, acc[j]);
             }
-            x0[((size_t)b * T + t) * R + r] = __float2bfloat16_rn(acc);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += bias[j];
         }
+        uint4 o4;
+        o4.x = pack_bf16x2(acc[0], acc[1]); o4.y = pack_bf16x2(acc[2], acc[3]);
+        o4.z = pack_bf16x2(acc[4], acc[5]); o4.w = pack_bf16x2(acc[6], acc[7]);
+        *reinterpret_cast<uint4*>(x0 + ((size_t)b * T + t) * R + r) = o4;
     }
 }
 
@@ -292,6 +322,53 @@ cond_to_cl_kernel(const float* __restrict__ c, int T, int C, int Cp, __nv_bfloat
     for (int i = tyy; i < 64; i += 8) {
         const int t = t0 + i, ch = c0 + cx;
         if (t < T && ch < Cp) out[((size_t)b * T + t) * Cp + ch] = __float2bfloat16_rn(tile[cx][i]);
+    }
+}
+
+// Last conditioning-upsampler stage fused with the layout change: (B,C,Tin) fp32 frames -> [B][Tin*s][Cp] bf16.
+// A stage is a nearest-neighbour stretch by s followed by a (2s+1)-tap smoothing filter (upsample.py:18-20,42), so an
+// output sample of phase p inside frame f only sees frames f-1, f, f+1, each through a partial sum of the taps:
+//   out[f*s+p] = A[p]*in[f-1] + B[p]*in[f] + C[p]*in[f+1],  A[p] = sum_{j<s-p} w[j], B[p] = sum_{s-p<=j<2s-p} w[j], C[p] = rest
+constexpr int CS_T = 64;       // samples per block
+constexpr int CS_PITCH = 69;   // >= CS_T + 3 frames (s = 1), odd
+__global__ void __launch_bounds__(256)
+cond_stage_cl_kernel(const float* __restrict__ in, int C, int Cp, int Tin, int s, const float* __restrict__ w,
+                     __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float cs_sm[];
+    float* coef = cs_sm;               // [3][s]
+    float* xin = cs_sm + 3 * s;        // [Cp][CS_PITCH]
+    const int b = blockIdx.y, t0 = blockIdx.x * CS_T, tid = threadIdx.x;
+    const int T = Tin * s;
+    const int t_last = min(t0 + CS_T, T) - 1;
+    const int f_lo = t0 / s - 1, nfr = t_last / s + 1 - f_lo + 1;
+    for (int p = tid; p < s; p += 256) {
+        float a = 0.f, bb = 0.f, cc = 0.f;
+        for (int j = 0; j < s - p; ++j) a += __ldg(&w[j]);
+        for (int j = s - p; j < 2 * s - p; ++j) bb += __ldg(&w[j]);
+        for (int j = 2 * s - p; j <= 2 * s; ++j) cc += __ldg(&w[j]);
+        coef[p] = a; coef[s + p] = bb; coef[2 * s + p] = cc;
+    }
+    for (int e = tid; e < Cp * nfr; e += 256) {
+        const int ch = e / nfr, k = e - ch * nfr, f = f_lo + k;
+        xin[ch * CS_PITCH + k] = (ch < C && f >= 0 && f < Tin) ? __ldg(&in[((size_t)b * C + ch) * Tin + f]) : 0.f;
+    }
+    __syncthreads();
+    const int c8n = Cp >> 3;
+    for (int e = tid; e < CS_T * c8n; e += 256) {
+        const int tt = e / c8n, c8 = (e - tt * c8n) * 8, t = t0 + tt;
+        if (t >= T) break;
+        const int f = t / s, p = t - f * s, k = f - f_lo;
+        const float ca = coef[p], cb = coef[s + p], cc = coef[2 * s + p];
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float* xr = xin + (c8 + j) * CS_PITCH + k;
+            v[j] = fmaf(cc, xr[1], fmaf(cb, xr[0], ca * xr[-1]));
+        }
+        uint4 o4;
+        o4.x = pack_bf16x2(v[0], v[1]); o4.y = pack_bf16x2(v[2], v[3]);
+        o4.z = pack_bf16x2(v[4], v[5]); o4.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(out + ((size_t)b * T + t) * Cp + c8) = o4;
     }
 }
 
@@ -1373,8 +1450,9 @@ size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T) {
     return carve(*d, B, T, nullptr).total;
 }
 
-int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,
-                           int T, float* logits, void* workspace, size_t workspace_bytes, void* stream_) {
+static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, const float* c, int up_s, const float* up_w,
+                                   const float* gemb, int B, int T, float* logits, void* workspace,
+                                   size_t workspace_bytes, void* stream_) {
     if (int rc = wae::require_sm100()) return rc;
     WAE_REQUIRE(w && x && logits && workspace, "wae_stack_forward_bf16: null pointer");
     const wae_stack_dims& d = w->d;
@@ -1406,12 +1484,18 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     gbias_bf16_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, gemb, d.layers, B, d.G, d.Gi, ws.gb);
     WAE_CHECK_LAUNCH();
     {
-        const size_t sm = (size_t)d.Oin * (FC_T + 1) * sizeof(float);
-        WAE_CHECK_CUDA(cudaFuncSetAttribute(first_conv_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        first_conv_bf16_kernel<<<dim3((T + FC_T - 1) / FC_T, B), 256, sm, stream>>>(x, w->wf, w->bf, T, d.Oin, d.R, ws.xa);
+        const int vec_ok = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+        first_conv_bf16_kernel<<<dim3((T + FC_T - 1) / FC_T, B), 256, 0, stream>>>(x, w->wf, w->bf, T, d.Oin, d.R, vec_ok, ws.xa);
         WAE_CHECK_LAUNCH();
     }
-    if (d.C > 0) {
+    if (d.C > 0 && up_s > 0) {
+        // c holds the frames before the last upsampler stage: stretch + smooth + layout change in one pass
+        const size_t sm = ((size_t)3 * up_s + (size_t)Cp * CS_PITCH) * sizeof(float);
+        WAE_REQUIRE(sm <= 200 * 1024, "wae_stack_forward_bf16_up: C=%d / scale %d need %zu bytes of shared memory", d.C, up_s, sm);
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(cond_stage_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        cond_stage_cl_kernel<<<dim3((T + CS_T - 1) / CS_T, B), 256, sm, stream>>>(c, d.C, Cp, T / up_s, up_s, up_w, ws.ccl);
+        WAE_CHECK_LAUNCH();
+    } else if (d.C > 0) {
         cond_to_cl_kernel<<<dim3((T + 63) / 64, (Cp + 31) / 32, B), 256, 0, stream>>>(c, T, d.C, Cp, ws.ccl);
         WAE_CHECK_LAUNCH();
     }
@@ -1506,6 +1590,21 @@ int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float*
     }
     WAE_CHECK_LAUNCH();
     return WAE_OK;
+}
+
+int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,
+                           int T, float* logits, void* workspace, size_t workspace_bytes, void* stream) {
+    return stack_forward_bf16_impl(w, x, c, 0, nullptr, gemb, B, T, logits, workspace, workspace_bytes, stream);
+}
+
+int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const float* c_frames, int Tc, int up_scale,
+                              const float* up_filter, const float* gemb, int B, int T, float* logits, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+    WAE_REQUIRE(w && c_frames && up_filter, "wae_stack_forward_bf16_up: null pointer");
+    WAE_REQUIRE(w->d.C > 0, "wae_stack_forward_bf16_up: the stack has no local conditioning (C = 0)");
+    WAE_REQUIRE(up_scale >= 1 && Tc >= 1 && (long long)Tc * up_scale == T,
+                "wae_stack_forward_bf16_up: %d frames x scale %d != T = %d", Tc, up_scale, T);
+    return stack_forward_bf16_impl(w, x, c_frames, up_scale, up_filter, gemb, B, T, logits, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

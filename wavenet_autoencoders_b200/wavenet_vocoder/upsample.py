@@ -43,14 +43,20 @@ class UpsampleNetwork(nn.Module):
         return (c.is_cuda and not (torch.is_grad_enabled() and (c.requires_grad or any(p.requires_grad for p in self.parameters())))
                 and self.freq_axis_kernel_size == 1 and not self.has_activation and self.mode == "nearest")
 
-    def forward(self, c):
+    def forward(self, c, defer_last=False):
+        """defer_last=True (inference, CUDA kernels usable, no indent): run every stage but the last and return
+        ``(frames, filter, scale)`` of the last one, which wae_stack_forward_bf16_up fuses into the decoder stack."""
+        if defer_last and not (self._kernel_ok(c) and self.indent == 0 and len(self.scales) >= 1):
+            return None
         if self._kernel_ok(c):
             from ..packing import folded_weight
             B, C, T = c.shape
             cur = c.contiguous().float()
             convs = [m for m in self.up_layers if isinstance(m, nn.Conv2d)]
-            for s, conv in zip(self.scales, convs):
+            for i, (s, conv) in enumerate(zip(self.scales, convs)):
                 w = folded_weight(conv).float().reshape(-1).contiguous()
+                if defer_last and i == len(self.scales) - 1:
+                    return cur, w, s
                 out = torch.empty(B, C, cur.shape[-1] * s, dtype=torch.float32, device=c.device)
                 _lib.check(_lib.lib().wae_upsample_stage(_lib.ptr(cur), B * C, cur.shape[-1], s, _lib.ptr(w),
                                                          _lib.ptr(out), _lib.stream_ptr(c.device)), "wae_upsample_stage")
@@ -74,7 +80,7 @@ class ConvInUpsampleNetwork(nn.Module):
         self.upsample = UpsampleNetwork(upsample_scales, upsample_activation, upsample_activation_params,
                                         mode, freq_axis_kernel_size, cin_pad=0, cin_channels=cin_channels)
 
-    def forward(self, c):
+    def forward(self, c, defer_last=False):
         # conv_in is a frame-rate C x C conv (1x1 for cin_pad=0).  cuDNN convolutions default to TF32 on sm_80+
         # (torch.backends.cudnn.allow_tf32), which costs ~1e-3 relative accuracy against the reference's fp32 CPU
         # path, so it is evaluated as a plain fp32 matmul / with TF32 disabled.
@@ -84,4 +90,4 @@ class ConvInUpsampleNetwork(nn.Module):
         else:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 c = self.conv_in(c)
-        return self.upsample(c)
+        return self.upsample(c, defer_last=defer_last) if defer_last else self.upsample(c)

@@ -145,21 +145,34 @@ class WaveNet(nn.Module):
         """x (B,O,T) one-hot / (B,1,T) scalar; c (B,C,Tc); g ids or (B,Gi[,1])  ->  (B,O,T) (wavenet.py:164-216)."""
         B, _, T = x.size()
         gvec = self._speaker_vectors(g, B)
+        autograd = self.training and torch.is_grad_enabled()
+        last_stage = None
         if c is not None and self.upsample_net is not None:
-            c = self.upsample_net(c)
-            if c.size(-1) != x.size(-1):
+            if not autograd and self.precision == "bf16" and x.is_cuda and isinstance(self.upsample_net, (upsample.UpsampleNetwork, upsample.ConvInUpsampleNetwork)):
+                # inference: the last upsampler stage is fused into the stack's conditioning pass
+                with torch.no_grad():
+                    deferred = self.upsample_net(c, defer_last=True)
+                if deferred is not None:
+                    c, up_w, up_s = deferred
+                    last_stage = (up_w, up_s)
+            if last_stage is None:
+                c = self.upsample_net(c)
+            if c.size(-1) * (last_stage[1] if last_stage else 1) != x.size(-1):
                 print(f"c {c.size() } x {x.size()}")
                 raise Exception
-        if self.training and torch.is_grad_enabled():
+        if autograd:
             return self._forward_autograd(x, c, gvec, softmax)
         with torch.no_grad():
-            out = self.stack_forward(x, c, gvec)
+            out = self.stack_forward(x, c, gvec, last_stage=last_stage)
         return F.softmax(out, dim=1) if softmax else out
 
-    def stack_forward(self, x, c_up, gvec, precision=None):
-        """The hot path proper: first_conv + residual stack + head on already-upsampled conditioning."""
+    def stack_forward(self, x, c_up, gvec, precision=None, last_stage=None):
+        """The hot path proper: first_conv + residual stack + head on already-upsampled conditioning (or, with
+        ``last_stage=(filter, scale)``, on the frames entering the last upsampler stage; bf16 only)."""
         self._require_cuda(x, "WaveNet.forward")
         precision = precision or self.precision
+        if last_stage is not None and precision != "bf16":
+            raise ValueError("last_stage fusion exists for precision='bf16' only")
         B, _, T = x.shape
         x = x.detach().float().contiguous()
         c_up = None if c_up is None else c_up.detach().float().contiguous()
@@ -177,8 +190,15 @@ class WaveNet(nn.Module):
             pk = self._pack("bf16")
             n = L.wae_stack_workspace_bf16(pk.struct.d, B, T)
             ws = self._ws.get(n, x.device)
-            _lib.check(L.wae_stack_forward_bf16(pk.struct, _lib.ptr(x), _lib.ptr(c_up), _lib.ptr(gvec), B, T,
-                                                _lib.ptr(logits), _lib.ptr(ws), ws.numel(), st), "wae_stack_forward_bf16")
+            if last_stage is not None:
+                up_w, up_s = last_stage
+                up_w = up_w.detach().float().contiguous()
+                _lib.check(L.wae_stack_forward_bf16_up(pk.struct, _lib.ptr(x), _lib.ptr(c_up), c_up.shape[-1], int(up_s),
+                                                       _lib.ptr(up_w), _lib.ptr(gvec), B, T, _lib.ptr(logits),
+                                                       _lib.ptr(ws), ws.numel(), st), "wae_stack_forward_bf16_up")
+            else:
+                _lib.check(L.wae_stack_forward_bf16(pk.struct, _lib.ptr(x), _lib.ptr(c_up), _lib.ptr(gvec), B, T,
+                                                    _lib.ptr(logits), _lib.ptr(ws), ws.numel(), st), "wae_stack_forward_bf16")
         else:
             raise ValueError(f"precision must be 'fp32' or 'bf16', got {precision!r}")
         return logits
