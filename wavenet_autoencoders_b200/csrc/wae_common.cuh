@@ -364,6 +364,22 @@ __device__ __forceinline__ unsigned short ld_cluster_u16(uint32_t addr) {
     asm volatile("ld.shared::cluster.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
     return v;
 }
+// asynchronous remote store: the 4 bytes land in the peer CTA's shared memory and are counted (complete_tx) on an mbarrier
+// of that same peer -- data and signal travel together, no cluster barrier, no release fence on the sender
+__device__ __forceinline__ void st_async_u32(uint32_t addr, uint32_t v, uint32_t mbar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(addr), "r"(v), "r"(mbar_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_v2u32(uint32_t addr, uint32_t v0, uint32_t v1, uint32_t mbar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(addr), "r"(v0),
+                 "r"(v1), "r"(mbar_addr)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_v4u32(uint32_t addr, uint4 v, uint32_t mbar_addr) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(addr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(mbar_addr)
+                 : "memory");
+}
 __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
     asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }

@@ -877,6 +877,27 @@ __device__ __forceinline__ void allgather_bf16(const __nv_bfloat16* src, int spi
         }
     }
 }
+// the same all-gather with st.async: every 32-bit word is counted on the mbarrier `bar` of the CTA it lands in, whose
+// waiters expect UC * (sum of all ranks' n) * 2 bytes per phase.  Slices must be even (2 bf16 per word).
+__device__ __forceinline__ void allgather_bf16_async(const __nv_bfloat16* src, int spitch, __nv_bfloat16* dst, int dpitch, int off, int n,
+                                                     int cs, int tid, uint64_t* bar) {
+    const int nw = n >> 1, per = UC * nw;
+    const uint32_t bar_local = smem_u32(bar);
+    if ((nw & (nw - 1)) == 0) {
+        const int sh = 31 - __clz(nw), shp = sh + 3;
+        for (int e = tid; e < cs * per; e += AR_THREADS) {
+            const int r = e >> shp, w = e & (per - 1), u = w >> sh, i = w & (nw - 1);
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(src + u * spitch + 2 * i);
+            st_async_u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + 2 * i), (uint32_t)r), v, mapa(bar_local, (uint32_t)r));
+        }
+    } else {
+        for (int e = tid; e < cs * per; e += AR_THREADS) {
+            const int r = e / per, w = e - r * per, u = w / nw, i = w - u * nw;
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(src + u * spitch + 2 * i);
+            st_async_u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + 2 * i), (uint32_t)r), v, mapa(bar_local, (uint32_t)r));
+        }
+    }
+}
 __device__ __forceinline__ void allgather_f32(const float* src, int spitch, float* dst, int dpitch, int off, int n, int cs, int tid) {
     const int per = UC * n;
     for (int e = tid; e < cs * per; e += AR_THREADS) {
@@ -949,6 +970,9 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     uint64_t* w1_full = bars;
     uint64_t* w2_full = bars + 2;
     int* cur_idx = reinterpret_cast<int*>(bars + 4);             // [UC]
+    uint64_t* h_full = bars + 62;                                // all-gather barriers (end of the 512-byte misc region)
+    uint64_t* x_full = bars + 63;
+    const uint32_t h_bytes = (uint32_t)(UC * H * 2), x_bytes = (uint32_t)(UC * R * 2);
 
     const int p0 = part(H, rank, cs), np = part(H, rank + 1, cs) - p0;
     const int ro0 = part(R, rank, cs), nres = part(R, rank + 1, cs) - ro0;
@@ -985,7 +1009,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     if (tid == 0) {
         mbar_init(&w1_full[0], 1); mbar_init(&w1_full[1], 1);
         mbar_init(&w2_full[0], 1); mbar_init(&w2_full[1], 1);
+        mbar_init(h_full, 1); mbar_init(x_full, 1);
         fence_mbar_init();
+        mbar_arrive_expect_tx(h_full, h_bytes);   // arm phase 0 of both exchanges (peers start after the cluster_sync below)
+        mbar_arrive_expect_tx(x_full, x_bytes);
     }
     for (int e = tid; e < (sl.off_boff - sl.off_xin) / 4; e += AR_THREADS) reinterpret_cast<uint32_t*>(smem + sl.off_xin)[e] = 0u;
     __syncthreads();
@@ -1072,6 +1099,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     for (int l = 0; l < NPF_M - 1; ++l) prefetch_taps(0, l, false);
 
     unsigned j1 = 0, j2 = 0;
+    uint32_t hph = 0, xph = 0;                                   // phase parities of h_full / x_full
     long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long pt = clock64();
     for (int t = 0; t < a.T; ++t) {
@@ -1140,8 +1168,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         // ---- residual layers ----
         for (int l = 0; l < L; ++l) {
             {
+                // the first layers of the NEXT step are fetched in the head, behind its cluster barrier (their newest tap can be
+                // a ring row written earlier in this step by another CTA); keep one commit group per layer here
                 const int lp = l + NPF_M - 1;
-                prefetch_taps(lp < L ? t : t + 1, lp < L ? lp : lp - L, lp >= L);
+                if (lp < L) prefetch_taps(t, lp, false); else cp_async_commit();
             }
             const unsigned seq = (unsigned)t * L + l;
             const bf16* xl = xin + (size_t)(seq % NPF_M) * UC * XS;
@@ -1172,6 +1202,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                             red, sl.rows1p, warp, lane);
             }
             __syncthreads();
+            if (tid == 0) issue_w1(j1 + 2);        // every warp is done with this layer's W1 slice: refill its slot
+            ++j1;
             AR_PROF(3);
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
@@ -1187,14 +1219,12 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             }
             __syncthreads();
             AR_PROF(4);
-            allgather_bf16(stgh, STH, hbuf, HS, p0, np, cs, tid);
-            ++j1;
+            allgather_bf16_async(stgh, STH, hbuf, HS, p0, np, cs, tid, h_full);
             AR_PROF(5);
-            cluster_arrive();
             mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
-            cluster_wait();
-            if (tid == 0) issue_w1(j1 + 1);
-            __syncwarp();
+            mbar_wait(h_full, hph);                // all H channels of all utterances have landed in hbuf
+            hph ^= 1u;
+            if (tid == 0) mbar_arrive_expect_tx(h_full, h_bytes);
             AR_PROF(6);
 
             const bool last = (l == L - 1);
@@ -1206,6 +1236,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 else mma_gemv<8>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt2, W2S, Hp / 16, hsrc, red, sl.rows2p, warp, lane);
             }
             __syncthreads();
+            if (tid == 0) issue_w2(j2 + 2);
+            ++j2;
             AR_PROF(7);
             for (int e = tid; e < n2 * UC; e += AR_THREADS) {
                 const int i = e >> 3, u = e & 7;
@@ -1221,22 +1253,21 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             }
             if (!last) {
                 __syncthreads();
-                allgather_bf16(stgx, STX, xnext, XS, ro0, nres, cs, tid);
-            }
-            ++j2;
-            AR_PROF(8);
-            cp_async_wait<NPF_M - 2>();
-            cluster_arrive();
-            if (!last) {
+                allgather_bf16_async(stgx, STX, xnext, XS, ro0, nres, cs, tid, x_full);
                 for (int e = tid; e < U * nres; e += AR_THREADS) {
                     const int u = e / nres, i = e % nres, b = cid * U + u;
                     if (b < a.B)
                         ringw[((size_t)b * a.ring_rows + a.ring_off[l + 1] + rpos[l + 1]) * R + ro0 + i] = stgx[u * STX + i];
                 }
             }
-            cluster_wait();
-            if (tid == 0) issue_w2(j2 + 1);
-            __syncwarp();
+            AR_PROF(8);
+            cp_async_wait<NPF_M - 2>();
+            if (!last) {
+                mbar_wait(x_full, xph);            // the next layer's newest tap is complete in every CTA's xin slot
+                xph ^= 1u;
+                if (tid == 0) mbar_arrive_expect_tx(x_full, x_bytes);
+            }
+            __syncthreads();                       // taps fetched by other threads' cp.async; `red` / staging reuse
             AR_PROF(9);
         }
 
@@ -1250,6 +1281,9 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
+        // every ring row of this step is now visible cluster-wide (release/acquire of the barrier): fetch the taps of the next
+        // step's first layers
+        for (int l2 = 0; l2 < NPF_M - 1; ++l2) prefetch_taps(t + 1, l2, true);
         {
             const uint32_t saddr = smem_u32(s1buf);
             mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt3, W3S, S / 16,
