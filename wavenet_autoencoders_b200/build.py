@@ -31,7 +31,12 @@ NVCC_FLAGS = [
 
 
 def _extra_flags() -> list:
-    return ["-DWAE_LAYER_PROF"] if os.environ.get("WAE_LAYER_PROF") == "1" else []
+    flags = []
+    if os.environ.get("WAE_LAYER_PROF") == "1":
+        flags.append("-DWAE_LAYER_PROF")      # role counters of the residual-layer kernels (tools/layer_profile.py)
+    if os.environ.get("WAE_AR_PROF") == "1":
+        flags.append("-DWAE_AR_PROF")         # phase counters of the autoregressive kernels (tools/ar_profile.py)
+    return flags
 
 
 def _nvcc() -> str:

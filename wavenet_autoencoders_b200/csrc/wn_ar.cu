@@ -161,7 +161,16 @@ __host__ __device__ inline ArSmem ar_smem_layout(const wae_stack_dims& d, int cs
     return s;
 }
 
+// phase counters cost ~26 registers in kernels that are register-bound: compiled in only with -DWAE_AR_PROF (WAE_AR_PROF=1 build)
+#ifdef WAE_AR_PROF
 #define AR_PROF(i) do { if (a.prof != nullptr && tid == 0) { const long long _n = clock64(); pacc[i] += _n - pt; pt = _n; } } while (0)
+#define AR_PROF_DECL long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long pt = clock64()
+#define AR_PROF_FLUSH do { if (a.prof != nullptr && tid == 0) for (int i = 0; i < 12; ++i) a.prof[(size_t)blockIdx.x * 16 + i] = pacc[i]; } while (0)
+#else
+#define AR_PROF(i) do { } while (0)
+#define AR_PROF_DECL do { } while (0)
+#define AR_PROF_FLUSH do { } while (0)
+#endif
 
 // ------------------------------------------------------------------------------------------------
 template <typename WT, int U>
@@ -319,8 +328,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     for (int l = 0; l < NPF - 1; ++l) prefetch_taps(0, l);  // host guarantees L >= NPF
 
     unsigned j1 = 0, j2 = 0;  // consumed-blob counters of the two weight rings
-    long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long pt = clock64();
+    AR_PROF_DECL;
 
     for (int t = 0; t < a.T; ++t) {
         // random draw(s) of this step: issue the (HBM-latency) load now, consume it after the head
@@ -693,8 +701,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         __syncthreads();
         AR_PROF(10);
     }
-    if (a.prof != nullptr && tid == 0)
-        for (int i = 0; i < 12; ++i) a.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+    AR_PROF_FLUSH;
     cp_async_wait<0>();
     cluster_sync();  // no CTA exits while peers may still write into its shared memory
 }
@@ -760,7 +767,7 @@ inline ArMmaLayout ar_mma_layout(const wae_stack_dims& d, int cs, int Hp, int Cp
     s.off_b2 = off; off += up((d.layers * s.max_n2 + s.max_n3 + s.max_n4) * 4);
     s.off_stgh = off; off += up(UC * (s.max_np + 8) * 2);
     s.off_stgx = off; off += up(UC * (maxrows + 8) * 2 > UC * (s.max_n4 + 8) * 4 ? UC * (maxrows + 8) * 2 : UC * (s.max_n4 + 8) * 4);
-    s.off_boff = off; off += up((2 * d.layers + 2) * 8);
+    s.off_boff = off; off += up((2 * d.layers + 2) * 8 + d.layers * 16);   // blob offsets, then the per-layer {ns, dilation, ring offset} table
     s.off_misc = off; off += 512;   // mbarriers, current class per utterance, ring positions per layer
     s.total = off;
     return s;
@@ -773,67 +780,9 @@ __device__ __forceinline__ void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r
     asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
 }
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-
-// partial[warp][row][u] = sum over this warp's k-steps of W[row][k] * X[u][k];   W: [mt*16][wstride] bf16 in smem,
-// X given per k-step by bsrc(ks) -> (shared address of element [0][ks*16], row stride in bytes)
-template <int MAXMT, class BSrc>
-__device__ __forceinline__ void mma_gemv(uint32_t w_addr, int mt, int wstride_bytes, int nk, BSrc bsrc, float* red, int rows_pad,
-                                         int warp, int lane) {
-    float acc[MAXMT][4];
-#pragma unroll
-    for (int m = 0; m < MAXMT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
-    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;    // ldmatrix.x4 lane -> (row, k) of its 8x8 matrix
-    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
-    for (int ks = warp; ks < nk; ks += AR_WARPS) {
-        uint32_t baddr, bstride;
-        bsrc(ks, baddr, bstride);
-        uint32_t b0, b1;
-        ldsm_x2(baddr + brow * bstride + bcol * 2, b0, b1);
-#pragma unroll
-        for (int m = 0; m < MAXMT; ++m) {
-            if (m < mt) {
-                uint32_t a0, a1, a2, a3;
-                ldsm_x4(w_addr + (uint32_t)((m * 16 + arow) * wstride_bytes + (ks * 16 + acol) * 2), a0, a1, a2, a3);
-                mma_bf16_16816(acc[m], a0, a1, a2, a3, b0, b1);
-            }
-        }
-    }
-    const int g = lane >> 2, t2 = (lane & 3) * 2;
-#pragma unroll
-    for (int m = 0; m < MAXMT; ++m) {
-        if (m < mt) {
-            float* p = red + ((size_t)warp * rows_pad + m * 16 + g) * UC + t2;
-            *reinterpret_cast<float2*>(p) = make_float2(acc[m][0], acc[m][1]);
-            *reinterpret_cast<float2*>(p + 8 * UC) = make_float2(acc[m][2], acc[m][3]);
-        }
-    }
-}
-
-// Variant for short reductions (K <= 256): warps are dealt (m-tile, k-part) pairs, so only AR_WARPS/mt partial tiles have to be
-// summed afterwards instead of AR_WARPS.  Requires mt to divide AR_WARPS.
-template <class BSrc>
-__device__ __forceinline__ void mma_gemv_msplit(uint32_t w_addr, int mt, int wstride_bytes, int nk, BSrc bsrc, float* red, int rows_pad,
-                                                int warp, int lane) {
-    const int nparts = AR_WARPS / mt, m = warp % mt, part_ = warp / mt;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
-    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
-    for (int ks = part_; ks < nk; ks += nparts) {
-        uint32_t baddr, bstride;
-        bsrc(ks, baddr, bstride);
-        uint32_t b0, b1, a0, a1, a2, a3;
-        ldsm_x2(baddr + brow * bstride + bcol * 2, b0, b1);
-        ldsm_x4(w_addr + (uint32_t)((m * 16 + arow) * wstride_bytes + (ks * 16 + acol) * 2), a0, a1, a2, a3);
-        mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
-    }
-    const int g = lane >> 2, t2 = (lane & 3) * 2;
-    float* p = red + ((size_t)part_ * rows_pad + m * 16 + g) * UC + t2;
-    *reinterpret_cast<float2*>(p) = make_float2(acc[0], acc[1]);
-    *reinterpret_cast<float2*>(p + 8 * UC) = make_float2(acc[2], acc[3]);
 }
 
 __device__ __forceinline__ float red_sum_n(const float* red, int rows_pad, int row, int u, int nparts) {
@@ -850,7 +799,7 @@ __device__ __forceinline__ float red_sum(const float* red, int rows_pad, int row
 }
 
 // all-gather of a bf16 slice: src[u][i] (i < n, row pitch spitch elements) -> dst[u*dpitch + off + i] in every CTA
-__device__ __forceinline__ void allgather_bf16(const __nv_bfloat16* src, int spitch, __nv_bfloat16* dst, int dpitch, int off, int n,
+__device__ __noinline__ void allgather_bf16(const __nv_bfloat16* src, int spitch, __nv_bfloat16* dst, int dpitch, int off, int n,
                                                int cs, int tid) {
     if (((n | off | spitch | dpitch) & 1) == 0) {
         const int nw = n >> 1, per = UC * nw;                      // 32-bit words per destination
@@ -879,10 +828,19 @@ __device__ __forceinline__ void allgather_bf16(const __nv_bfloat16* src, int spi
 }
 // the same all-gather with st.async: every 32-bit word is counted on the mbarrier `bar` of the CTA it lands in, whose
 // waiters expect UC * (sum of all ranks' n) * 2 bytes per phase.  Slices must be even (2 bf16 per word).
-__device__ __forceinline__ void allgather_bf16_async(const __nv_bfloat16* src, int spitch, __nv_bfloat16* dst, int dpitch, int off, int n,
+__device__ __noinline__ void allgather_bf16_async(const __nv_bfloat16* src, int spitch, __nv_bfloat16* dst, int dpitch, int off, int n,
                                                      int cs, int tid, uint64_t* bar) {
-    const int nw = n >> 1, per = UC * nw;
     const uint32_t bar_local = smem_u32(bar);
+    if (((n | off | spitch | dpitch) & 7) == 0) {                  // 16-byte chunks (every preset)
+        const int nv = n >> 3, per = UC * nv;
+        for (int e = tid; e < cs * per; e += AR_THREADS) {
+            const int r = e / per, w = e - r * per, u = w / nv, i = w - u * nv;
+            const uint4 v = *reinterpret_cast<const uint4*>(src + u * spitch + 8 * i);
+            st_async_v4u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + 8 * i), (uint32_t)r), v, mapa(bar_local, (uint32_t)r));
+        }
+        return;
+    }
+    const int nw = n >> 1, per = UC * nw;
     if ((nw & (nw - 1)) == 0) {
         const int sh = 31 - __clz(nw), shp = sh + 3;
         for (int e = tid; e < cs * per; e += AR_THREADS) {
@@ -898,7 +856,7 @@ __device__ __forceinline__ void allgather_bf16_async(const __nv_bfloat16* src, i
         }
     }
 }
-__device__ __forceinline__ void allgather_f32(const float* src, int spitch, float* dst, int dpitch, int off, int n, int cs, int tid) {
+__device__ __noinline__ void allgather_f32(const float* src, int spitch, float* dst, int dpitch, int off, int n, int cs, int tid) {
     const int per = UC * n;
     for (int e = tid; e < cs * per; e += AR_THREADS) {
         const int r = e / per, w = e - r * per, u = w / n, i = w - u * n;
@@ -906,35 +864,183 @@ __device__ __forceinline__ void allgather_f32(const float* src, int spitch, floa
     }
 }
 
-// PULL all-gather: every CTA has written its own slice of a [UC][pitch] buffer (elements [part(n,r), part(n,r+1)) of each
-// row belong to rank r) into its OWN shared memory and a cluster barrier has passed; fetch the other ranks' slices through
-// distributed shared memory loads.  Compared with pushing the slice into all peers before the barrier, the barrier's release
-// no longer has to wait for remote stores to drain (measured: ~1.5-2k cycles per barrier with pushes).
-template <typename T>   // T = uint32_t words of 2 bf16, or fp32 bit patterns
-__device__ __forceinline__ void pull_words(T* buf, int pitch_words, int n_words, int elems_per_word, int n_total, int cs, int rank, int tid) {
-    const bool pow2 = ((n_words & (n_words - 1)) == 0) && (n_total % cs == 0) && (((n_total / cs) & ((n_total / cs) - 1)) == 0) &&
-                      ((n_total / cs) % elems_per_word == 0);
-    if (pow2) {
-        const int sh = 31 - __clz(n_words);
-        const int osh = 31 - __clz((n_total / cs) / elems_per_word);      // words per owner
-        for (int e = tid; e < UC * n_words; e += AR_THREADS) {
-            const int u = e >> sh, w = e & (n_words - 1), r = w >> osh;
-            if (r != rank) {
-                T* p = buf + (size_t)u * pitch_words + w;
-                *reinterpret_cast<uint32_t*>(p) = ld_cluster_u32(mapa(smem_u32(p), (uint32_t)r));
+// ---- inline fast paths of ar_mma_kernel -------------------------------------------------------------------------
+// ncu on the first tensor-core version: 2 warps per scheduler, an instruction issued every ~7 cycles per warp (fixed-latency
+// "wait" stalls dominate), ~1300 instructions per warp per layer of which the mma work itself is ~60.  These variants keep
+// the per-layer instruction count down: compile-time m-tile counts (no predicated dead tiles), pointer-increment loops,
+// per-thread exchange addresses computed once per kernel.
+
+// K-split mat-vec: warp w takes k-steps w, w+8, ...; k-steps below nkx read the tap buffer (xb), the rest the conditioning
+// rows (cb).  a_lane / xb / cb already contain this lane's ldmatrix row/column offset; redp its accumulator position.
+template <int MT>
+__device__ __forceinline__ void gemv_ksplit_t(uint32_t a_lane, int wstride_bytes, int nk, uint32_t xb, int nkx, uint32_t cb, float* redp,
+                                              int mt, int warp) {
+    float acc[MT][4];
+#pragma unroll
+    for (int m = 0; m < MT; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+    int ks = warp;
+    uint32_t aa = a_lane + ks * 32, bb = xb + ks * 32;
+    auto step = [&]() {
+        uint32_t b0, b1, af[MT][4];
+        ldsm_x2(bb, b0, b1);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) ldsm_x4(aa + (uint32_t)(m * 16 * wstride_bytes), af[m][0], af[m][1], af[m][2], af[m][3]);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) mma_bf16_16816(acc[m], af[m][0], af[m][1], af[m][2], af[m][3], b0, b1);
+        aa += AR_WARPS * 32; bb += AR_WARPS * 32; ks += AR_WARPS;
+    };
+#pragma unroll 2
+    while (ks < nkx) step();
+    bb = cb + (ks - nkx) * 32;
+#pragma unroll 1
+    while (ks < nk) step();
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+        if (m < mt) {      // tiles past mt (MT rounded up) multiplied whatever follows the weight slice: dropped here
+            *reinterpret_cast<float2*>(redp + m * 16 * UC) = make_float2(acc[m][0], acc[m][1]);
+            *reinterpret_cast<float2*>(redp + m * 16 * UC + 8 * UC) = make_float2(acc[m][2], acc[m][3]);
+        }
+    }
+}
+
+// short reductions (K <= 256): warp -> (m-tile, k-part); a_lane / xb include the lane offsets AND the warp's m-tile / first k-step
+__device__ __forceinline__ void gemv_msplit_t(uint32_t a_lane, uint32_t xb, int ks, int nk, int nparts, float* redp) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (; ks < nk; ks += nparts) {
+        uint32_t b0, b1, a0, a1, a2, a3;
+        ldsm_x2(xb, b0, b1);
+        ldsm_x4(a_lane, a0, a1, a2, a3);
+        mma_bf16_16816(acc, a0, a1, a2, a3, b0, b1);
+        xb += nparts * 32; a_lane += nparts * 32;
+    }
+    *reinterpret_cast<float2*>(redp) = make_float2(acc[0], acc[1]);
+    *reinterpret_cast<float2*>(redp + 8 * UC) = make_float2(acc[2], acc[3]);
+}
+
+// ---- out-of-line building blocks of ar_mma_kernel ------------------------------------------------------------------
+// The kernel runs ~10^5 cycles of mostly straight-line code per sample; with everything inlined its SASS was 211 KB and
+// adding 13 KB made every phase ~8% slower, 60 KB made it 1.8x slower (instruction-cache misses; profiles/ar_phase_r1.txt).
+// So: one copy of each building block, called; cold fallbacks kept out of the hot path.
+
+// partial[warp][row][u] = sum over this warp's k-steps of W[row][k] * X[u][k];   W: [mt*16][wstride] bf16 in smem (mt <= 4).
+// X: k-steps below nkx come from xaddr (row stride xstride bytes), the rest from caddr (conditioning rows).
+__device__ __noinline__ void gemv_ksplit(uint32_t w_addr, int mt, int wstride_bytes, int nk, uint32_t xaddr, uint32_t xstride, int nkx,
+                                         uint32_t caddr, uint32_t cstride, float* red, int rows_pad) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[4][4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
+    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;    // ldmatrix.x4 lane -> (row, k) of its 8x8 matrix
+    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
+    const uint32_t a_lane = w_addr + (uint32_t)(arow * wstride_bytes + acol * 2);
+    const uint32_t xb = xaddr + brow * xstride + bcol * 2, cb = caddr + brow * cstride + bcol * 2;
+    // two k-steps per round: the ldmatrix of the round are issued before its first mma, so their latencies overlap
+    for (int ks0 = warp; ks0 < nk; ks0 += 2 * AR_WARPS) {
+        uint32_t bq[2][2], aq[2][4][4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int ks = ks0 + j * AR_WARPS;
+            if (ks < nk) {
+                ldsm_x2(ks < nkx ? xb + ks * 32 : cb + (ks - nkx) * 32, bq[j][0], bq[j][1]);
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (m < mt) ldsm_x4(a_lane + (uint32_t)(m * 16 * wstride_bytes + ks * 32), aq[j][m][0], aq[j][m][1], aq[j][m][2], aq[j][m][3]);
             }
         }
-    } else {
-        for (int e = tid; e < UC * n_words; e += AR_THREADS) {
-            const int u = e / n_words, w = e - u * n_words;
-            const int el = w * elems_per_word;                              // slice boundaries must be multiples of elems_per_word
-            const int r = ((el + 1) * cs - 1) / n_total;
-            if (r != rank) {
-                T* p = buf + (size_t)u * pitch_words + w;
-                *reinterpret_cast<uint32_t*>(p) = ld_cluster_u32(mapa(smem_u32(p), (uint32_t)r));
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (ks0 + j * AR_WARPS < nk) {
+#pragma unroll
+                for (int m = 0; m < 4; ++m)
+                    if (m < mt) mma_bf16_16816(acc[m], aq[j][m][0], aq[j][m][1], aq[j][m][2], aq[j][m][3], bq[j][0], bq[j][1]);
             }
         }
     }
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (m < mt) {
+            float* p = red + ((size_t)warp * rows_pad + m * 16 + g) * UC + t2;
+            *reinterpret_cast<float2*>(p) = make_float2(acc[m][0], acc[m][1]);
+            *reinterpret_cast<float2*>(p + 8 * UC) = make_float2(acc[m][2], acc[m][3]);
+        }
+    }
+}
+
+// Variant for short reductions (K <= 256) and up to AR_WARPS m-tiles: warps are dealt (m-tile, k-part) pairs, so only
+// nparts = AR_WARPS / mt partial tiles have to be summed afterwards (warps beyond mt * nparts idle).
+__device__ __noinline__ void gemv_msplit(uint32_t w_addr, int mt, int wstride_bytes, int nk, uint32_t xaddr, uint32_t xstride, float* red,
+                                         int rows_pad) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nparts = AR_WARPS / mt, m = warp % mt, part_ = warp / mt;
+    if (part_ >= nparts) return;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
+    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
+    const uint32_t a_lane = w_addr + (uint32_t)((m * 16 + arow) * wstride_bytes + acol * 2);
+    const uint32_t xb = xaddr + brow * xstride + bcol * 2;
+    for (int ks0 = part_; ks0 < nk; ks0 += nparts * 4) {
+        uint32_t bq[4][2], aq[4][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int ks = ks0 + j * nparts;
+            if (ks < nk) {
+                ldsm_x2(xb + ks * 32, bq[j][0], bq[j][1]);
+                ldsm_x4(a_lane + ks * 32, aq[j][0], aq[j][1], aq[j][2], aq[j][3]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (ks0 + j * nparts < nk) mma_bf16_16816(acc, aq[j][0], aq[j][1], aq[j][2], aq[j][3], bq[j][0], bq[j][1]);
+    }
+    const int g = lane >> 2, t2 = (lane & 3) * 2;
+    float* p = red + ((size_t)part_ * rows_pad + m * 16 + g) * UC + t2;
+    *reinterpret_cast<float2*>(p) = make_float2(acc[0], acc[1]);
+    *reinterpret_cast<float2*>(p + 8 * UC) = make_float2(acc[2], acc[3]);
+}
+
+// dense (not one-hot) input of the first conv: dot product of one weight column with the step's input vector
+__device__ __noinline__ float first_conv_dense(const float* __restrict__ wf, const float* inrow, int Oin, int R, int r) {
+    float acc = 0.f;
+    for (int o = 0; o < Oin; ++o) acc = fmaf(__ldg(&wf[(size_t)o * R + r]), inrow[o], acc);
+    return acc;
+}
+
+// cp.async prefetch of the tap rows of (step tt, layer l) into xin slot (tt*L + l) % NPF_M; one commit group per call.
+// pfpack: this thread's two (chunk, tap, utterance) work items, 6 + 2 + 3 bits each (items past 2 * AR_THREADS: slow loop).
+__device__ __noinline__ void ar_prefetch_taps(const ArArgs& a, __nv_bfloat16* xin, const int* rpos, int XS, int cid, int tt, int l, int next_step,
+                                              uint32_t pfpack) {
+    typedef __nv_bfloat16 bf16;
+    const int kw = a.d.kernel_size, R = a.d.R, U = a.utts, tid = threadIdx.x;
+    if (tt < a.T && kw > 1) {
+        const bf16* ringb = reinterpret_cast<const bf16*>(a.ring);
+        const int r8 = R / 8, pf_chunks = U * (kw - 1) * r8;
+        const int ns = a.ring_ns[l], dil = a.d.dilation[l];
+        int pos = rpos[l];
+        if (next_step) { pos = (pos + 1 == ns) ? 0 : pos + 1; }
+        const unsigned slot_x = ((unsigned)tt * a.d.layers + l) % NPF_M;
+        const size_t ring_base = (size_t)a.ring_off[l];
+        auto item = [&](int c8, int j, int u) {
+            const int b = cid * U + u;
+            const int back = (kw - 1 - j) * dil;
+            int sl_ = pos - back;
+            if (sl_ < 0) sl_ += ns;
+            bf16* dst = xin + ((size_t)slot_x * UC + u) * XS + j * R + c8 * 8;
+            if (b < a.B && tt - back >= 0)
+                cp_async16(dst, ringb + (((size_t)b * a.ring_rows + ring_base + sl_) * R + c8 * 8));
+            else
+                *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+        };
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const uint32_t w = pfpack >> (16 * q);
+            if (tid + q * AR_THREADS < pf_chunks) item((int)(w & 63u), (int)((w >> 6) & 3u), (int)((w >> 8) & 7u));
+        }
+        for (int e = tid + 2 * AR_THREADS; e < pf_chunks; e += AR_THREADS)     // rare: more than 512 chunks per layer
+            item(e % r8, (e / r8) % (kw - 1), e / (r8 * (kw - 1)));
+    }
+    cp_async_commit();
 }
 
 __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_constant__ ArArgs a, const __grid_constant__ ArMmaLayout sl) {
@@ -983,8 +1089,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     const int STH = sl.max_np + 8, STX = (sl.rows1p > sl.rows2p ? sl.rows1p : sl.rows2p) + 8;
     float* b3c = b2c + (size_t)L * sl.max_n2;
     float* b4c = b3c + sl.max_n3;
-    const bool msplit2 = (mt2 >= 1 && mt2 <= AR_WARPS && AR_WARPS % mt2 == 0);   // GEMV2: few k-steps -> deal m-tiles to warps
-    const int nparts2 = msplit2 ? AR_WARPS / mt2 : AR_WARPS;
+    const int nparts2 = AR_WARPS / (mt2 > 0 ? mt2 : 1);          // GEMV2: few k-steps -> warps are dealt (m-tile, k-part) pairs
 
     const unsigned n1_total = (unsigned)a.T * L, n2_total = (unsigned)a.T * (L + 2);
     auto issue_w1 = [&](unsigned j) {
@@ -1038,52 +1143,17 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     // ring slot of the current step per layer (t % ns[l]) is kept incrementally in shared memory: ns = (kw-1)*d+1 is odd,
     // so every "% ns" would be a real division on the critical path
     int* rpos = cur_idx + UC;                                    // [L]
-    const int r8 = R / 8;
-    const int pf_chunks = U * (kw - 1) * r8;                      // 16-byte chunks (8 bf16) per layer
-    int pf_c8[2], pf_j[2], pf_u[2];
+    uint32_t pfpack = 0;                                         // this thread's two prefetch work items (see ar_prefetch_taps)
+    {
+        const int r8 = R / 8;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const int e = tid + q * AR_THREADS;
-        pf_c8[q] = e % r8; pf_j[q] = (kw > 1) ? (e / r8) % (kw - 1) : 0; pf_u[q] = (kw > 1) ? e / (r8 * (kw - 1)) : 0;
-    }
-    auto prefetch_taps = [&](int tt, int l, bool next_step) {
-        if (tt < a.T && kw > 1) {
-            const int ns = a.ring_ns[l], dil = d.dilation[l];
-            int pos = rpos[l];
-            if (next_step) { pos = (pos + 1 == ns) ? 0 : pos + 1; }
-            const unsigned slot_x = ((unsigned)tt * L + l) % NPF_M;
-            const size_t ring_base = (size_t)a.ring_off[l];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int e = tid + q * AR_THREADS;
-                if (e < pf_chunks) {
-                    const int c8 = pf_c8[q], j = pf_j[q], u = pf_u[q];
-                    const int b = cid * U + u;
-                    const int back = (kw - 1 - j) * dil;
-                    int sl_ = pos - back;
-                    if (sl_ < 0) sl_ += ns;
-                    bf16* dst = xin + ((size_t)slot_x * UC + u) * XS + j * R + c8 * 8;
-                    if (b < a.B && tt - back >= 0)
-                        cp_async16(dst, ringb + (((size_t)b * a.ring_rows + ring_base + sl_) * R + c8 * 8));
-                    else
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-                }
-            }
-            for (int e = tid + 2 * AR_THREADS; e < pf_chunks; e += AR_THREADS) {   // rare: more than 512 chunks
-                const int c8 = e % r8, j = (e / r8) % (kw - 1), u = e / (r8 * (kw - 1));
-                const int b = cid * U + u;
-                const int back = (kw - 1 - j) * dil;
-                int sl_ = pos - back;
-                if (sl_ < 0) sl_ += ns;
-                bf16* dst = xin + ((size_t)slot_x * UC + u) * XS + j * R + c8 * 8;
-                if (b < a.B && tt - back >= 0)
-                    cp_async16(dst, ringb + (((size_t)b * a.ring_rows + ring_base + sl_) * R + c8 * 8));
-                else
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
-            }
+        for (int q = 0; q < 2; ++q) {
+            const int e = tid + q * AR_THREADS;
+            const uint32_t c8 = (uint32_t)(e % r8), j = (kw > 1) ? (uint32_t)((e / r8) % (kw - 1)) : 0u, u = (kw > 1) ? (uint32_t)(e / (r8 * (kw - 1))) : 0u;
+            pfpack |= ((c8 & 63u) | ((j & 3u) << 6) | ((u & 7u) << 8)) << (16 * q);
         }
-        cp_async_commit();
-    };
+    }
+    auto prefetch_taps = [&](int tt, int l, bool next_step) { ar_prefetch_taps(a, xin, rpos, XS, cid, tt, l, next_step ? 1 : 0, pfpack); };
     auto prefetch_c = [&](int tt) {
         if (c_bf != nullptr && tt < a.T) {
             const int c8n = d.C / 8;
@@ -1094,14 +1164,89 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         }
     };
     for (int e = tid; e < L; e += AR_THREADS) rpos[e] = 0;
+
+    // ---- per-thread constants of the per-layer fast paths ----
+    int4* ltab = reinterpret_cast<int4*>(boffs + (2 * L + 2));   // [L] {ring slots, dilation, ring row offset, -}: one LDS.128 per layer
+    for (int e = tid; e < L; e += AR_THREADS) ltab[e] = make_int4(a.ring_ns[e], d.dilation[e], a.ring_off[e], 0);
+    const uint32_t slot_bytes = (uint32_t)(UC * XS * 2);
+    // ldmatrix lane offsets: A (x4) lane -> row (lane&7) + 8*((lane>>3)&1), k half (lane>>4); B (x2) lane -> row lane&7, k half (lane>>3)&1
+    const int l_arow = (lane & 7) + ((lane >> 3) & 1) * 8, l_acol2 = (lane >> 4) * 16;
+    const int l_brow = lane & 7, l_bcol2 = ((lane >> 3) & 1) * 16;
+    const int l_red = (lane >> 2) * UC + (lane & 3) * 2;
+    // GEMV2: warp -> (m-tile, k-part)
+    const int g2_m = (mt2 > 0) ? warp % mt2 : 0, g2_part = (mt2 > 0) ? warp / mt2 : AR_WARPS;
+    // tap prefetch: this thread's (up to two) 16-byte chunks per layer; dst offset inside a slot | taps back | valid
+    const int pf_chunks = U * (kw - 1) * (R / 8);
+    const bool pf_fast = pf_chunks <= 2 * AR_THREADS;
+    uint32_t pf_info[2] = {0u, 0u};
+    long long pf_src[2] = {0, 0};                                // element offset of (utterance, chunk) inside the ring
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int e = tid + q * AR_THREADS;
+        if (kw > 1 && e < pf_chunks) {
+            const int r8 = R / 8, c8 = e % r8, j = (e / r8) % (kw - 1), u = e / (r8 * (kw - 1)), b = cid * U + u;
+            pf_info[q] = (uint32_t)((u * XS + j * R + c8 * 8) * 2) | ((uint32_t)(kw - 1 - j) << 20) | (b < a.B ? (1u << 30) : 0u) | (1u << 31);
+            pf_src[q] = (long long)b * a.ring_rows * R + c8 * 8;
+        }
+    }
+    auto prefetch_taps_fast = [&](int tt, int l, bool next_step, uint32_t slot_x) {
+        if (tt < a.T) {
+            const int4 tb = ltab[l];
+            int pos = rpos[l];
+            if (next_step) pos = (pos + 1 == tb.x) ? 0 : pos + 1;
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                if (pf_info[q] >> 31) {
+                    const int back = (int)((pf_info[q] >> 20) & 0xffu) * tb.y;
+                    int sl_ = pos - back;
+                    if (sl_ < 0) sl_ += tb.x;
+                    uint8_t* dst = reinterpret_cast<uint8_t*>(xin) + slot_x * slot_bytes + (pf_info[q] & 0xfffffu);
+                    if (((pf_info[q] >> 30) & 1u) && tt - back >= 0)
+                        cp_async16(dst, ringb + (pf_src[q] + (long long)(tb.z + sl_) * R));
+                    else
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    // all-gather items: (destination rank, utterance, 16-byte chunk of this CTA's slice) -> one st.async per thread and layer
+    const int nvh = np >> 3, items_h = cs * UC * nvh, nvx = nres >> 3, items_x = cs * UC * nvx;
+    const bool fast_h = ((np | p0) & 7) == 0 && items_h <= AR_THREADS;
+    const bool fast_x = ((nres | ro0) & 7) == 0 && items_x <= AR_THREADS;
+    uint32_t hx_src = 0, hx_dst = 0, hx_bar = 0, xx_src = 0, xx_dst = 0, xx_bar = 0;
+    long long xx_ring = -1;                                      // ring element offset of this thread's chunk (rank-0 copy only)
+    if (fast_h && tid < items_h) {
+        const int r = tid / (UC * nvh), w = tid - r * UC * nvh, u = w / nvh, i = w - u * nvh;
+        hx_src = smem_u32(stgh + u * STH + 8 * i);
+        hx_dst = mapa(smem_u32(hbuf + (size_t)u * HS + p0 + 8 * i), (uint32_t)r);
+        hx_bar = mapa(smem_u32(h_full), (uint32_t)r);
+    }
+    if (fast_x && tid < items_x) {
+        const int r = tid / (UC * nvx), w = tid - r * UC * nvx, u = w / nvx, i = w - u * nvx, b = cid * U + u;
+        xx_src = smem_u32(stgx + u * STX + 8 * i);
+        xx_dst = mapa(smem_u32(xin + (size_t)u * XS + (kw - 1) * R + ro0 + 8 * i), (uint32_t)r);     // slot 0; + slot * slot_bytes
+        xx_bar = mapa(smem_u32(x_full), (uint32_t)r);
+        if (r == 0 && u < U && b < a.B) xx_ring = (long long)b * a.ring_rows * R + ro0 + 8 * i;
+    }
+    // gate-bias items of reduce+gate: (pair j, utterance u) = (e >> 3, e & 7)
+    int gb_off[2] = {-1, -1};
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const int e = tid + q * AR_THREADS, j = e >> 3, u = e & 7, b = cid * U + u;
+        if (e < np * UC && u < U && b < a.B) gb_off[q] = b * G + p0 + j;
+    }
+    uint32_t slot = 0;                                           // xin slot of the current (step, layer): (t * L + l) % NPF_M
+    auto slot_add = [](uint32_t s0, uint32_t k) { const uint32_t v = s0 + k; return v >= (uint32_t)NPF_M ? v - NPF_M : v; };
     __syncthreads();
     prefetch_c(0);
-    for (int l = 0; l < NPF_M - 1; ++l) prefetch_taps(0, l, false);
+    for (int l = 0; l < NPF_M - 1; ++l) {
+        if (pf_fast) prefetch_taps_fast(0, l, false, (uint32_t)l); else prefetch_taps(0, l, false);
+    }
 
     unsigned j1 = 0, j2 = 0;
     uint32_t hph = 0, xph = 0;                                   // phase parities of h_full / x_full
-    long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long pt = clock64();
+    AR_PROF_DECL;
     for (int t = 0; t < a.T; ++t) {
         float u_pref = 0.f;
         if (warp < U && a.uniforms != nullptr) {
@@ -1131,7 +1276,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         }
         __syncthreads();
         {
-            bf16* x0 = xin + (size_t)(((unsigned)t * L) % NPF_M) * UC * XS + (kw - 1) * R;
+            bf16* x0 = xin + (size_t)slot * UC * XS + (kw - 1) * R;
             for (int r = tid; r < R; r += AR_THREADS) {
                 const float bias = __ldg(&a.bf[r]);
                 float acc[UC];
@@ -1143,7 +1288,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                         if (ci >= 0) {
                             acc[u] = __ldg(&a.wf[(size_t)ci * R + r]);
                         } else {
-                            for (int o = 0; o < Oin; ++o) acc[u] = fmaf(__ldg(&a.wf[(size_t)o * R + r]), inbuf[u * Oin + o], acc[u]);
+                            acc[u] = first_conv_dense(a.wf, inbuf + u * Oin, Oin, R, r);
                         }
                     }
                 }
@@ -1166,40 +1311,40 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         AR_PROF(0);
 
         // ---- residual layers ----
+        const bf16* cl = cbuf + (size_t)(t & 1) * UC * CSd;
+        const size_t gb_layer = (size_t)a.B * G;
         for (int l = 0; l < L; ++l) {
             {
                 // the first layers of the NEXT step are fetched in the head, behind its cluster barrier (their newest tap can be
                 // a ring row written earlier in this step by another CTA); keep one commit group per layer here
                 const int lp = l + NPF_M - 1;
-                if (lp < L) prefetch_taps(t, lp, false); else cp_async_commit();
+                if (lp < L) {
+                    if (pf_fast) prefetch_taps_fast(t, lp, false, slot_add(slot, NPF_M - 1)); else prefetch_taps(t, lp, false);
+                } else {
+                    cp_async_commit();
+                }
             }
-            const unsigned seq = (unsigned)t * L + l;
-            const bf16* xl = xin + (size_t)(seq % NPF_M) * UC * XS;
-            const bf16* cl = cbuf + (size_t)(t & 1) * UC * CSd;
+            const bf16* xl = xin + (size_t)slot * UC * XS;
             // gate biases of this thread's (pair, utterance) items: issue the loads now, use them after the mma loop
             float gba[2] = {0.f, 0.f}, gbb[2] = {0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
-                const int e = tid + q * AR_THREADS;
-                if (e < np * UC) {
-                    const int j = e >> 3, u = e & 7, b = cid * U + u;
-                    if (u < U && b < a.B) {
-                        gba[q] = __ldg(&a.gb[((size_t)l * a.B + b) * G + p0 + j]);
-                        gbb[q] = __ldg(&a.gb[((size_t)l * a.B + b) * G + H + p0 + j]);
-                    }
+                if (gb_off[q] >= 0) {
+                    const float* gp = a.gb + (size_t)l * gb_layer + gb_off[q];
+                    gba[q] = __ldg(gp);
+                    gbb[q] = __ldg(gp + H);
                 }
             }
             AR_PROF(1);
             mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
             AR_PROF(2);
             {
-                const uint32_t xaddr = smem_u32(xl), caddr = smem_u32(cl);
-                mma_gemv<4>(smem_u32(w1buf + (size_t)(j1 & 1) * sl.w1_slot), mt1, W1S, K1p / 16,
-                            [&](int ks, uint32_t& addr, uint32_t& stride) {
-                                const int k0 = ks * 16;
-                                if (k0 < KX) { addr = xaddr + k0 * 2; stride = XS * 2; } else { addr = caddr + (k0 - KX) * 2; stride = CSd * 2; }
-                            },
-                            red, sl.rows1p, warp, lane);
+                const uint32_t a_lane = smem_u32(w1buf + (size_t)(j1 & 1) * sl.w1_slot) + (uint32_t)(l_arow * W1S + l_acol2);
+                const uint32_t xb = smem_u32(xl) + (uint32_t)(l_brow * XS * 2 + l_bcol2), cb = smem_u32(cl) + (uint32_t)(l_brow * CSd * 2 + l_bcol2);
+                float* redp = red + (size_t)warp * sl.rows1p * UC + l_red;
+                if (mt1 == 2) gemv_ksplit_t<2>(a_lane, W1S, K1p / 16, xb, KX / 16, cb, redp, mt1, warp);
+                else if (mt1 == 1) gemv_ksplit_t<1>(a_lane, W1S, K1p / 16, xb, KX / 16, cb, redp, mt1, warp);
+                else gemv_ksplit_t<4>(a_lane, W1S, K1p / 16, xb, KX / 16, cb, redp, mt1, warp);
             }
             __syncthreads();
             if (tid == 0) issue_w1(j1 + 2);        // every warp is done with this layer's W1 slice: refill its slot
@@ -1219,7 +1364,15 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             }
             __syncthreads();
             AR_PROF(4);
-            allgather_bf16_async(stgh, STH, hbuf, HS, p0, np, cs, tid, h_full);
+            if (fast_h) {
+                if (tid < items_h) {
+                    uint4 v;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(hx_src));
+                    st_async_v4u32(hx_dst, v, hx_bar);
+                }
+            } else {
+                allgather_bf16_async(stgh, STH, hbuf, HS, p0, np, cs, tid, h_full);
+            }
             AR_PROF(5);
             mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
             mbar_wait(h_full, hph);                // all H channels of all utterances have landed in hbuf
@@ -1228,12 +1381,11 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             AR_PROF(6);
 
             const bool last = (l == L - 1);
-            bf16* xnext = xin + (size_t)((seq + 1) % NPF_M) * UC * XS + (kw - 1) * R;
-            {
-                const uint32_t haddr = smem_u32(hbuf);
-                auto hsrc = [&](int ks, uint32_t& addr, uint32_t& stride) { addr = haddr + ks * 32; stride = HS * 2; };
-                if (msplit2) mma_gemv_msplit(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt2, W2S, Hp / 16, hsrc, red, sl.rows2p, warp, lane);
-                else mma_gemv<8>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt2, W2S, Hp / 16, hsrc, red, sl.rows2p, warp, lane);
+            const uint32_t slot_n = slot_add(slot, 1);
+            if (g2_part < nparts2) {
+                const uint32_t a_lane = smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot) + (uint32_t)((g2_m * 16 + l_arow) * W2S + l_acol2 + g2_part * 32);
+                const uint32_t xb = smem_u32(hbuf) + (uint32_t)(l_brow * HS * 2 + l_bcol2 + g2_part * 32);
+                gemv_msplit_t(a_lane, xb, g2_part, Hp / 16, nparts2, red + ((size_t)g2_part * sl.rows2p + g2_m * 16) * UC + l_red);
             }
             __syncthreads();
             if (tid == 0) issue_w2(j2 + 2);
@@ -1253,11 +1405,26 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             }
             if (!last) {
                 __syncthreads();
-                allgather_bf16_async(stgx, STX, xnext, XS, ro0, nres, cs, tid, x_full);
-                for (int e = tid; e < U * nres; e += AR_THREADS) {
-                    const int u = e / nres, i = e % nres, b = cid * U + u;
-                    if (b < a.B)
-                        ringw[((size_t)b * a.ring_rows + a.ring_off[l + 1] + rpos[l + 1]) * R + ro0 + i] = stgx[u * STX + i];
+                if (fast_x) {
+                    if (tid < items_x) {
+                        uint4 v;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(xx_src));
+                        st_async_v4u32(xx_dst + slot_n * slot_bytes, v, xx_bar);
+                        if (xx_ring >= 0) {
+                            const int4 tb = ltab[l + 1];
+                            *reinterpret_cast<uint4*>(ringw + (xx_ring + (long long)(tb.z + rpos[l + 1]) * R)) = v;
+                        }
+                    }
+                } else {
+                    bf16* xnext = xin + (size_t)slot_n * UC * XS + (kw - 1) * R;
+                    allgather_bf16_async(stgx, STX, xnext, XS, ro0, nres, cs, tid, x_full);
+                    const int nw = nres >> 1;                          // slices are even: 32-bit words
+                    for (int e = tid; e < U * nw; e += AR_THREADS) {
+                        const int u = e / nw, i = e - u * nw, b = cid * U + u;
+                        if (b < a.B)
+                            *reinterpret_cast<uint32_t*>(ringw + ((size_t)b * a.ring_rows + a.ring_off[l + 1] + rpos[l + 1]) * R + ro0 + 2 * i) =
+                                *reinterpret_cast<const uint32_t*>(stgx + u * STX + 2 * i);
+                    }
                 }
             }
             AR_PROF(8);
@@ -1268,6 +1435,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 if (tid == 0) mbar_arrive_expect_tx(x_full, x_bytes);
             }
             __syncthreads();                       // taps fetched by other threads' cp.async; `red` / staging reuse
+            slot = slot_n;
             AR_PROF(9);
         }
 
@@ -1283,12 +1451,11 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         cluster_wait();
         // every ring row of this step is now visible cluster-wide (release/acquire of the barrier): fetch the taps of the next
         // step's first layers
-        for (int l2 = 0; l2 < NPF_M - 1; ++l2) prefetch_taps(t + 1, l2, true);
-        {
-            const uint32_t saddr = smem_u32(s1buf);
-            mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt3, W3S, S / 16,
-                        [&](int ks, uint32_t& addr, uint32_t& stride) { addr = saddr + ks * 32; stride = SS * 2; }, red, sl.rows3p, warp, lane);
+        for (int l2 = 0; l2 < NPF_M - 1; ++l2) {
+            if (pf_fast) prefetch_taps_fast(t + 1, l2, true, slot_add(slot, (uint32_t)l2)); else prefetch_taps(t + 1, l2, true);
         }
+        gemv_ksplit(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt3, W3S, S / 16, smem_u32(s1buf), (uint32_t)(SS * 2), S / 16, 0u, 0u, red,
+                    sl.rows3p);
         __syncthreads();
         for (int e = tid; e < nsk * UC; e += AR_THREADS) {
             const int i = e >> 3, u = e & 7;
@@ -1302,11 +1469,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         cluster_wait();
         if (tid == 0) issue_w2(j2 + 1);
         __syncwarp();
-        {
-            const uint32_t saddr = smem_u32(s2buf);
-            mma_gemv<4>(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt4, W3S, S / 16,
-                        [&](int ks, uint32_t& addr, uint32_t& stride) { addr = saddr + ks * 32; stride = SS * 2; }, red, sl.rows4p, warp, lane);
-        }
+        gemv_ksplit(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt4, W3S, S / 16, smem_u32(s2buf), (uint32_t)(SS * 2), S / 16, 0u, 0u, red,
+                    sl.rows4p);
         __syncthreads();
         float* stgl = reinterpret_cast<float*>(stgx);       // fp32 logits staging [UC][max_n4 + 8]
         const int STL = sl.max_n4 + 8;
@@ -1384,8 +1548,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         __syncthreads();
         AR_PROF(11);
     }
-    if (a.prof != nullptr && tid == 0)
-        for (int i = 0; i < 12; ++i) a.prof[(size_t)blockIdx.x * 16 + i] = pacc[i];
+    AR_PROF_FLUSH;
     cp_async_wait<0>();
     cluster_sync();
 }
