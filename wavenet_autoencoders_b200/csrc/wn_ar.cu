@@ -1092,17 +1092,17 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     const int nparts2 = AR_WARPS / (mt2 > 0 ? mt2 : 1);          // GEMV2: few k-steps -> warps are dealt (m-tile, k-part) pairs
 
     const unsigned n1_total = (unsigned)a.T * L, n2_total = (unsigned)a.T * (L + 2);
-    auto issue_w1 = [&](unsigned j) {
+    auto issue_w1 = [&](unsigned j, int l) {                     // l = j % L, tracked by the caller (no division on the hot path)
         if (j >= n1_total) return;
-        const int l = (int)(j % L), slot = (int)(j & 1);
+        const int slot = (int)(j & 1);
         const uint32_t bytes = (uint32_t)(mt1 * 16 * W1S);
         if (bytes == 0) { mbar_arrive(&w1_full[slot]); return; }
         mbar_arrive_expect_tx(&w1_full[slot], bytes);
         bulk_load_1d(w1buf + (size_t)slot * sl.w1_slot, a.blob + boffs[2 * l], bytes, &w1_full[slot]);
     };
-    auto issue_w2 = [&](unsigned j) {
+    auto issue_w2 = [&](unsigned j, int i) {                     // i = j % (L + 2)
         if (j >= n2_total) return;
-        const int i = (int)(j % (L + 2)), slot = (int)(j & 1);
+        const int slot = (int)(j & 1);
         const uint32_t bytes = (uint32_t)((i < L) ? mt2 * 16 * W2S : (i == L ? mt3 * 16 * W3S : mt4 * 16 * W3S));
         if (bytes == 0) { mbar_arrive(&w2_full[slot]); return; }
         const int stage = (i < L) ? 2 * i + 1 : 2 * L + (i - L);
@@ -1134,7 +1134,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         inbuf[e] = (u < U && b < a.B) ? a.init[(size_t)b * Oin + o] : 0.f;
     }
     __syncthreads();
-    if (tid == 0) { issue_w1(0); issue_w1(1); issue_w2(0); issue_w2(1); }
+    if (tid == 0) { issue_w1(0, 0); issue_w1(1, 1 % L); issue_w2(0, 0); issue_w2(1, 1); }
     cluster_sync();
 
     const bf16* ringb = reinterpret_cast<const bf16*>(a.ring);
@@ -1347,7 +1347,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 else gemv_ksplit_t<4>(a_lane, W1S, K1p / 16, xb, KX / 16, cb, redp, mt1, warp);
             }
             __syncthreads();
-            if (tid == 0) issue_w1(j1 + 2);        // every warp is done with this layer's W1 slice: refill its slot
+            if (tid == 0) issue_w1(j1 + 2, l + 2 >= L ? l + 2 - L : l + 2);   // every warp is done with this layer's W1 slice: refill its slot
             ++j1;
             AR_PROF(3);
 #pragma unroll
@@ -1388,7 +1388,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 gemv_msplit_t(a_lane, xb, g2_part, Hp / 16, nparts2, red + ((size_t)g2_part * sl.rows2p + g2_m * 16) * UC + l_red);
             }
             __syncthreads();
-            if (tid == 0) issue_w2(j2 + 2);
+            if (tid == 0) issue_w2(j2 + 2, l + 2);     // stages L, L+1 are the two head matrices
             ++j2;
             AR_PROF(7);
             for (int e = tid; e < n2 * UC; e += AR_THREADS) {
@@ -1467,7 +1467,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         cluster_arrive();
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         cluster_wait();
-        if (tid == 0) issue_w2(j2 + 1);
+        if (tid == 0) issue_w2(j2 + 1, 0);      // the slot of head matrix 3 is free: first layer of the next step
         __syncwarp();
         gemv_ksplit(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt4, W3S, S / 16, smem_u32(s2buf), (uint32_t)(SS * 2), S / 16, 0u, 0u, red,
                     sl.rows4p);
@@ -1483,7 +1483,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         ++j2;
         cluster_arrive();
         cluster_wait();
-        if (tid == 0) issue_w2(j2 + 1);
+        if (tid == 0) issue_w2(j2 + 1, 1);
         __syncwarp();
 
         AR_PROF(10);

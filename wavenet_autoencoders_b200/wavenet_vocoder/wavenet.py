@@ -292,7 +292,12 @@ class WaveNet(nn.Module):
             cluster = self.ar_cluster or (16 if wtype == "fp32" else 8)
             if wtype == "bf16mma":
                 sh = packing.stack_shape(self)     # the tensor-core kernel exchanges bf16 pairs: slice boundaries must be even
-                if any(packing.part(n, r, cluster) % 2 for n in (sh.H, sh.R, sh.S) for r in range(1, cluster)):
+                even = lambda cs: not any(packing.part(n, r, cs) % 2 for n in (sh.H, sh.R, sh.S) for r in range(1, cs))
+                # clusters of 16 halve every CTA's weight slice (56 vs 60 us per step at the vqwae shape) but only 9 of them
+                # are co-resident on 148 SMs, 8 utterances each: take them when the batch fits
+                if self.ar_cluster is None and B <= 72 and even(16):
+                    cluster = 16
+                if not even(cluster):
                     wtype = "bf16"
             upc = self.ar_utts_per_cluster or (8 if wtype == "bf16mma" else 2)
             if wtype != "bf16mma" and upc not in (1, 2, 4):
