@@ -127,7 +127,9 @@ int wae_stack_forward_f32(const wae_stack_f32* w, const float* x, const float* c
 /*
  * bf16 weights for the tcgen05 tensor-core stack.  bf16 row-major "K-major" matrices (row = output
  * channel, contiguous along the reduction dim), reduction dims padded to a multiple of 64:
- *   w1  [L][G][K1p]     K order = taps (oldest first) x R, then C (zero padded to 64)
+ *   w1  [L][2*Hh][K1p]  K order = taps (oldest first) x R, then C (zero padded to 64).  Rows: tanh half then sigmoid half,
+ *                       each zero padded from H = G/2 to Hh = H rounded up to 16; if Hh > 128 the rows are grouped in two
+ *                       passes [tanh(0:128) | sigm(0:128) | tanh(128:Hh) | sigm(128:Hh)] (one UMMA N = 256 rows per pass)
  *   wo  [L][R][Hp]      conv1x1_out        ws [L][S][Hp]   conv1x1_skip   (Hp = H padded to 64)
  *   w3  [S][S]          w4 [O][S]
  *   fp32 vectors: b1 [L][G], wg [L][Gi][G] (natural column order), bo [L][R], bs_sum [S] (sum over layers),

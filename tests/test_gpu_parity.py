@@ -61,7 +61,7 @@ def test_forward_fp32_matches_reference_golden(case):
     assert torch.allclose(ys.sum(1), torch.ones_like(ys.sum(1)), atol=1e-4)
 
 
-@pytest.mark.parametrize("case", ["wavenet_tiny", "wavenet_tiny_k2", "wavenet_vqwae"])
+@pytest.mark.parametrize("case", ["wavenet_tiny", "wavenet_tiny_k2", "wavenet_vqwae", "wavenet_inwae"])
 def test_forward_bf16_matches_reference_golden(case):
     g, cfg, m, x, c, spk = _inputs(case)
     m.precision = "bf16"
@@ -91,6 +91,31 @@ def test_forward_bf16_fused_last_upsample_stage(case):
         m.precision = "bf16"
         y16 = m(x2, c, spk)
     assert rel_err(y16.cpu().numpy(), y32.cpu().numpy()) < TOL_BF16
+
+
+@pytest.mark.parametrize("G", [40, 296, 368, 512])
+def test_forward_bf16_gate_padding_and_two_pass(G):
+    """Gate widths the tcgen05 layer kernel pads (H % 16 != 0) or splits into two accumulator passes (G > 256; IN-WAE has
+    G = 368), against the numpy oracle on a small stack."""
+    cfg = dict(T.CONFIGS["tiny"], residual_channels=64, gate_channels=G, skip_out_channels=64, layers=4, stacks=2,
+               upsample_conditional_features=False)
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    torch.manual_seed(0)
+    m = WaveNet(**cfg).eval()
+    m.load_state_dict(T.synth_state_dict(m, 5))
+    p = wo.extract_params({k: v.numpy() for k, v in m.state_dict().items()}, cfg["layers"], cfg["stacks"])
+    m = m.cuda()
+    rs = np.random.RandomState(G)
+    B, Tn = 3, 300
+    idx = rs.randint(0, cfg["out_channels"], size=(B, Tn))
+    x = np.eye(cfg["out_channels"], dtype=np.float32)[idx].transpose(0, 2, 1).copy()
+    c = rs.normal(size=(B, cfg["cin_channels"], Tn)).astype(np.float32)
+    spk = rs.randint(0, cfg["n_speakers"], size=(B, 1))
+    ref = wo.forward(p, x, c, spk)
+    m.precision = "bf16"
+    with torch.no_grad():
+        y = m(torch.tensor(x).cuda(), torch.tensor(c).cuda(), torch.tensor(spk).cuda())
+    assert rel_err(y.cpu().numpy(), ref) < TOL_BF16, G
 
 
 def test_forward_ragged_tail_and_dense_input_fp32_bf16():

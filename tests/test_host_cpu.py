@@ -112,11 +112,20 @@ def test_packing_layouts(cfg_name):
     np.testing.assert_allclose(w1[1 * R + 7, 8 * q + i], lay["w"][4 * q + i, 7, 1], rtol=1e-6)           # tanh ch, tap 1
     np.testing.assert_allclose(w1[kw * R + 3, 8 * q + 4 + i], lay["wc"][H + 4 * q + i, 3], rtol=1e-6)   # sigmoid ch, cond row
     np.testing.assert_allclose(pf.t["w2"][0].numpy()[9, R + 11], p["layers"][0]["ws"][11, 9], rtol=1e-6)
-    # bf16 pack: K-major [G][K1p]
+    # bf16 pack: K-major [2*Hh][K1p]; gate halves padded to Hh = round16(H), split into two passes beyond 128 channels
     pb = packing.pack_bf16(m)
     w1b = pb.t["w1"][L - 1].float().numpy()
-    assert w1b.shape[1] % 64 == 0 and w1b.shape[0] == sh.G
-    np.testing.assert_allclose(w1b[H + 3, 2 * R + 5] if kw == 3 else w1b[H + 3, 1 * R + 5], lay["w"][H + 3, 5, kw - 1], rtol=1e-2)
+    Hh = -(-H // 16) * 16
+    Ha = min(Hh, 128)
+    assert w1b.shape[1] % 64 == 0 and w1b.shape[0] == 2 * Hh
+
+    def gate_row(half, ch):          # row of tanh (0) / sigmoid (1) channel ch
+        return half * Ha + ch if ch < Ha else 2 * Ha + half * (Hh - Ha) + (ch - Ha)
+    for ch in {3, H - 1}:
+        for half in (0, 1):
+            np.testing.assert_allclose(w1b[gate_row(half, ch), (kw - 1) * R + 5], lay["w"][half * H + ch, 5, kw - 1], rtol=1e-2)
+    if Hh > H:
+        assert float(np.abs(w1b[gate_row(0, H):gate_row(0, Hh - 1) + 1]).sum()) == 0                       # padded channels are zero
     assert float(np.abs(w1b[:, kw * R + sh.C:]).sum()) == 0                                                # K padding is zero
     np.testing.assert_allclose(pb.t["bs_sum"].numpy(), sum(l["bs"] for l in p["layers"]), rtol=1e-5, atol=1e-6)
     # AR pack: per-(stage, rank) row slices

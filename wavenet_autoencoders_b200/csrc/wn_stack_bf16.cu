@@ -213,17 +213,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __gr
 // ---------------------------------------------------------------------------------------------
 // prep kernels
 // ---------------------------------------------------------------------------------------------
-// gb[l][b][:] = b1[l] + wg[l]^T gemb[b]   (natural column order)
+// gb[l][b][:] = b1[l] + wg[l]^T gemb[b], stored as [tanh half | sigmoid half], each half zero padded from H = G/2 to Hh
+// channels (Hh = H rounded up to 16: the epilogues read 16-channel chunks)
 __global__ void __launch_bounds__(256)
 gbias_bf16_kernel(const float* __restrict__ b1, const float* __restrict__ wg, const float* __restrict__ gemb, int L,
-                  int B, int G, int Gi, float* __restrict__ gb) {
-    const int l = blockIdx.x / B, b = blockIdx.x % B;
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-        float acc = 0.f;
-        if (wg != nullptr && gemb != nullptr)
-            for (int i = 0; i < Gi; ++i)
-                acc = fmaf(__ldg(&wg[((size_t)l * Gi + i) * G + g]), __ldg(&gemb[(size_t)b * Gi + i]), acc);
-        gb[((size_t)l * B + b) * G + g] = __ldg(&b1[(size_t)l * G + g]) + acc;
+                  int B, int G, int Gi, int Hh, float* __restrict__ gb) {
+    const int l = blockIdx.x / B, b = blockIdx.x % B, H = G / 2;
+    for (int o = threadIdx.x; o < 2 * Hh; o += blockDim.x) {
+        const int half = o >= Hh, ch = o - half * Hh;
+        float v = 0.f;
+        if (ch < H) {
+            const int g = half * H + ch;
+            float acc = 0.f;
+            if (wg != nullptr && gemb != nullptr)
+                for (int i = 0; i < Gi; ++i)
+                    acc = fmaf(__ldg(&wg[((size_t)l * Gi + i) * G + g]), __ldg(&gemb[(size_t)b * Gi + i]), acc);
+            v = __ldg(&b1[(size_t)l * G + g]) + acc;
+        }
+        gb[((size_t)l * B + b) * 2 * Hh + o] = v;
     }
 }
 
@@ -378,16 +385,18 @@ cond_stage_cl_kernel(const float* __restrict__ in, int C, int Cp, int Tin, int s
 struct LayerArgs {
     CUtensorMap tm_x;    // layer input  [B][T][R]   box {64, 128}
     CUtensorMap tm_c;    // conditioning [B][T][Cp]  box {64, 128}
+    CUtensorMap tm_w1b;  // second gate pass (G > 256, version-2 kernel only): box {64, 2 * Hb} at weight row 2 * Ha
     CUtensorMap tm_w1;   // [L][G][K1p]              box {64, G / cluster}: every CTA of a cluster loads one row slice
     CUtensorMap tm_wo;   // [L][R][Hp]               box {64, R / cluster}  and multicasts it to all of them
     CUtensorMap tm_hst;  // h_all viewed as [L*B][T][Hp], box {64, 128}: TMA store of the gated activations
     CUtensorMap tm_xout; // layer output [B][T][R], box {64, 128}: TMA store of x' (version-2 kernel)
-    const float* gb;     // [B][G]  conv bias + g term of this layer
+    const float* gb;     // [B][G]  conv bias + g term of this layer, [tanh half | sigmoid half]
     const float* bo;     // [R]
     const __nv_bfloat16* x_in;   // [B][T][R]
     __nv_bfloat16* x_out;        // [B][T][R] or null (last layer: residual output is dead)
     __nv_bfloat16* h_out;        // [B][T][Hp] plane of this layer
-    int B, T, R, G, Hp, Cp, kw, dil, layer, tiles_per_utt;
+    int B, T, R, G, Hp, Cp, kw, dil, layer, tiles_per_utt;   // G = 2 * Hh: gate rows incl. the zero padding of each half
+    int Ha, Hb;          // h channels produced by gate pass A (min(Hh, 128)) and pass B (Hh - Ha; 0 = single pass)
     long long* prof;     // optional [gridDim.x][16] cycle counters (debug), or null
 };
 
@@ -734,9 +743,10 @@ constexpr int V2_STAGES = 3;
 template <int kDummy>
 __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles, uint32_t tmem_acc1, uint32_t tmem_acc2, uint8_t* hx,
                                                   float* sb_bo, uint64_t* acc1_full, uint64_t* acc2_full, uint64_t* epi1_done,
-                                                  uint64_t* epi2_done) {
+                                                  uint64_t* epi2_done, uint64_t* epi1a_done) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int H = a.G / 2;
+    const int Hh = a.G / 2;
+    uint32_t n_acc1 = 0;                              // completions of acc1_full seen so far (1 or 2 per tile)
     const bool has_out = (a.x_out != nullptr);
     const int q = warp & 3;
     const int cg = (warp - 2) >> 2;
@@ -750,40 +760,55 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
         const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
         const float* gbp = a.gb + (size_t)b * a.G;
 
-        // ---- EPI1: gate ----
-        mbar_wait(acc1_full, it & 1);
+        // ---- EPI1: gate.  Pass A gives h channels [0, Ha) from accumulator columns [0, Ha) (tanh) and [Ha, 2 Ha) (sigmoid);
+        // with more than 256 gate rows a second pass over the same columns gives channels [Ha, Ha + Hb) ----
+        auto gate_chunks = [&](int c_lo, int c_hi, int col_a, int col_b) {
+            for (int c0 = c_lo + cg * 16; c0 < c_hi; c0 += LAYER_NCG * 16) {
+                uint32_t packed[8];
+                if (c0 < Hh) {
+                    float va[16], vb[16];
+                    tmem_ld16(tmem_acc1 + lane_base + col_a + (c0 - c_lo), va);
+                    tmem_ld16(tmem_acc1 + lane_base + col_b + (c0 - c_lo), vb);
+                    float ba[16], bb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
+                        *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + Hh + c0 + i));
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
+                        const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
+                        packed[i >> 1] = pack_bf16x2(h0, h1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = 0u;
+                }
+                const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                const uint32_t base = hx_addr + kb * A_TILE_BYTES;
+                st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+            }
+        };
+        mbar_wait(acc1_full, n_acc1 & 1);
+        ++n_acc1;
         tc_fence_after();
         if (it > 0) {   // the TMA stores of the previous tile (h and x') must have finished READING the staging tiles
             if (threadIdx.x == 64) tma_store_wait_read();
             asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
         }
-        for (int c0 = cg * 16; c0 < a.Hp; c0 += LAYER_NCG * 16) {
-            uint32_t packed[8];
-            if (c0 < H) {
-                float va[16], vb[16];
-                tmem_ld16(tmem_acc1 + lane_base + c0, va);
-                tmem_ld16(tmem_acc1 + lane_base + H + c0, vb);
-                float ba[16], bb[16];
-#pragma unroll
-                for (int i = 0; i < 16; i += 4) {
-                    *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
-                    *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + H + c0 + i));
-                }
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
-                    const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
-                    packed[i >> 1] = pack_bf16x2(h0, h1);
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) packed[i] = 0u;
-            }
-            const int kb = c0 / BK, c16 = (c0 % BK) / 8;
-            const uint32_t base = hx_addr + kb * A_TILE_BYTES;
-            st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
-            st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+        if (a.Hb == 0) {
+            gate_chunks(0, a.Hp, 0, a.Ha);
+        } else {
+            gate_chunks(0, a.Ha, 0, a.Ha);
+            tc_fence_before();
+            mbar_arrive(epi1a_done);               // the accumulator columns are free for pass B
+            mbar_wait(acc1_full, n_acc1 & 1);
+            ++n_acc1;
+            tc_fence_after();
+            gate_chunks(a.Ha, a.Hp, 0, a.Hb);
         }
         tc_fence_before();
         fence_proxy_async_smem();
@@ -850,7 +875,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
     uint64_t* epi1_done = acc1_full + 1;
     uint64_t* acc2_full = acc1_full + 2;
     uint64_t* epi2_done = acc1_full + 3;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
+    uint64_t* epi1a_done = acc1_full + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 5);
 
     const int warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
@@ -859,10 +885,12 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
         mbar_init(epi1_done, 32 * LAYER_EPI_WARPS);
         mbar_init(acc2_full, 1);
         mbar_init(epi2_done, 32 * LAYER_EPI_WARPS);
+        mbar_init(epi1a_done, 32 * LAYER_EPI_WARPS);
         fence_mbar_init();
         tma_prefetch_desc(&a.tm_x);
         tma_prefetch_desc(&a.tm_c);
         tma_prefetch_desc(&a.tm_w1);
+        if (a.Hb > 0) tma_prefetch_desc(&a.tm_w1b);
         tma_prefetch_desc(&a.tm_wo);
         tma_prefetch_desc(&a.tm_hst);
         tma_prefetch_desc(&a.tm_xout);
@@ -889,7 +917,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
     const int nk_c = a.Cp / BK;
     const int nk1 = nk_old + nk_c + rk;          // + the newest tap, walked LAST (its A tiles also feed the residual MMAs)
     const bool has_out = (a.x_out != nullptr);
-    const int w1_bytes = a.G * BK * 2, wo_bytes = a.R * BK * 2;
+    const int w1_bytes = 2 * a.Ha * BK * 2, w1b_bytes = 2 * a.Hb * BK * 2, wo_bytes = a.R * BK * 2;
+    const int npass = (a.Hb > 0) ? 2 : 1;        // gate rows beyond 256 (one UMMA N / the 256 accumulator columns) take a second pass
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -897,10 +926,11 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
             Ring ring(V2_STAGES);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+                for (int pass = 0; pass < npass; ++pass)
                 for (int kb = 0; kb < nk1; ++kb) {
                     mbar_wait(&empty[ring.stage], ring.phase ^ 1);
                     uint8_t* sa = smem + ring.stage * STAGE_BYTES;
-                    mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + w1_bytes);
+                    mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + (pass == 0 ? w1_bytes : w1b_bytes));
                     int kcol;
                     if (kb < nk_old) {
                         const int tap = kb / rk, r0 = (kb % rk) * BK;
@@ -915,7 +945,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
                         tma_load_3d(&a.tm_x, &full[ring.stage], sa, r0, t0, b);
                         kcol = (a.kw - 1) * a.R + r0;
                     }
-                    tma_load_3d(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES, kcol, 0, a.layer);
+                    if (pass == 0) tma_load_3d(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES, kcol, 0, a.layer);
+                    else tma_load_3d(&a.tm_w1b, &full[ring.stage], sa + A_TILE_BYTES, kcol, 2 * a.Ha, a.layer);
                     ring.advance();
                 }
                 if (has_out) {
@@ -933,7 +964,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
         // ================= MMA issuer =================
         if (elect_one()) {
             Ring ring(V2_STAGES);
-            const uint32_t idesc1 = umma_idesc_bf16(BM, a.G);
+            const uint32_t idesc1 = umma_idesc_bf16(BM, 2 * a.Ha);
+            const uint32_t idesc1b = umma_idesc_bf16(BM, a.Hb > 0 ? 2 * a.Hb : 16);
             const uint32_t idesc2 = umma_idesc_bf16(BM, a.R);
             const uint32_t idesc_id = umma_idesc_bf16(BM, 64);
             const uint64_t id_desc = umma_desc_sw128(smem_u32(ident));
@@ -958,6 +990,20 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
                     ring.advance();
                 }
                 umma_commit(acc1_full);
+                if (npass == 2) {
+                    // pass B: gate rows [2 Ha, 2 Ha + 2 Hb) into the same accumulator columns, once EPI1 has drained pass A
+                    mbar_wait(epi1a_done, it & 1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < nk1; ++kb) {
+                        mbar_wait(&full[ring.stage], ring.phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                        issue_kblock(tmem_acc1, sa, sa + A_TILE_BYTES, idesc1b, kb == 0);
+                        umma_commit(&empty[ring.stage]);
+                        ring.advance();
+                    }
+                    umma_commit(acc1_full);
+                }
                 if (has_out) {
                     mbar_wait(epi1_done, it & 1);  // h is in shared memory, acc1 drained
                     tc_fence_after();
@@ -975,7 +1021,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
         }
     } else {
         layer_epilogue_v2<0>(a, ntiles, tmem_acc1, tmem_acc2, hx, reinterpret_cast<float*>(bars) + 64, acc1_full, acc2_full,
-                             epi1_done, epi2_done);
+                             epi1_done, epi2_done, epi1a_done);
     }
     tc_fence_before();
     __syncthreads();
@@ -1382,7 +1428,8 @@ Bf16Workspace carve(const wae_stack_dims& d, int B, int T, void* base) {
     w.xb = reinterpret_cast<__nv_bfloat16*>(take(bt * d.R * 2));
     w.ccl = reinterpret_cast<__nv_bfloat16*>(take(bt * (Cp > 0 ? Cp : 1) * 2));
     w.hall = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.layers * bt * Hp * 2));
-    w.gb = reinterpret_cast<float*>(take((size_t)d.layers * B * d.G * 4));
+    const int Hh = (d.G / 2 + 15) / 16 * 16;
+    w.gb = reinterpret_cast<float*>(take((size_t)d.layers * B * 2 * Hh * 4));
     w.total = off;
     return w;
 }
@@ -1459,9 +1506,14 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     const int H = d.G / 2;
     WAE_REQUIRE(B > 0 && T > 0 && B <= 65535, "wae_stack_forward_bf16: B=%d T=%d", B, T);
     WAE_REQUIRE(d.layers >= 1 && d.layers <= WAE_MAX_LAYERS && d.kernel_size >= 1, "bad layers/kernel_size");
-    WAE_REQUIRE(d.R % BK == 0 && d.R <= 256 && d.S % BK == 0 && d.S <= 256 && d.G % 32 == 0 && d.G <= 256 && d.O <= 256,
-                "wae_stack_forward_bf16: this build supports R,S in {64,128,192,256}, G%%32==0, G<=256, O<=256 "
+    WAE_REQUIRE(d.R % BK == 0 && d.R <= 256 && d.S % BK == 0 && d.S <= 256 && d.G % 2 == 0 && d.G >= 2 && d.G <= 512 && d.O <= 256,
+                "wae_stack_forward_bf16: this build supports R,S in {64,128,192,256}, even G<=512, O<=256 "
                 "(R=%d G=%d S=%d O=%d); use the fp32 stack for other shapes", d.R, d.G, d.S, d.O);
+    // gate rows as the kernels see them: [tanh half | sigmoid half], each padded to Hh = H rounded up to 16; more than 128
+    // channels per half (256 rows = one UMMA N = the accumulator's 256 TMEM columns) are split into two passes:
+    // rows [a(0:Ha) | b(0:Ha) | a(Ha:Hh) | b(Ha:Hh)] (packing.pack_bf16 writes W1 in this order)
+    const int Hh = (H + 15) / 16 * 16, Gp = 2 * Hh;
+    const int Ha = Hh < 128 ? Hh : 128, Hb = Hh - Ha;
     WAE_REQUIRE((d.C == 0) == (c == nullptr), "wae_stack_forward_bf16: c must be given iff C>0");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0)
         return wae::set_error(WAE_ERR_ALIGN, "wae_stack_forward_bf16: workspace must be 256-byte aligned");
@@ -1481,7 +1533,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     // ---- prep: g bias, first conv, conditioning layout ----
     {
     ProfScope prof(0, stream);
-    gbias_bf16_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, gemb, d.layers, B, d.G, d.Gi, ws.gb);
+    gbias_bf16_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, gemb, d.layers, B, d.G, d.Gi, Hh, ws.gb);
     WAE_CHECK_LAUNCH();
     {
         const int vec_ok = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
@@ -1503,8 +1555,10 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
 
     // ---- layers ----
     const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 256 + 1024;
-    WAE_REQUIRE(smem_layer <= 232448, "wae_stack_forward_bf16: layer kernel shared memory %zu too large", smem_layer);
-    WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
+    if (g_layer_mode != 2 && Hb == 0) {
+        WAE_REQUIRE(smem_layer <= 232448, "wae_stack_forward_bf16: layer kernel shared memory %zu too large", smem_layer);
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
+    }
 
     LayerArgs la;
     CUtensorMap tm_xa, tm_xb;
@@ -1516,11 +1570,16 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         la.tm_c = tm_xa;  // never used (nk_c == 0)
     }
     // Layer-kernel variant: CTA pairs (cta_group::2, default) or the 1-CTA kernel in clusters of 1/2/4 with weight multicast.
-    const bool pair = (g_layer_mode == 0) && d.G % 32 == 0 && d.R % 32 == 0;
-    const bool v2 = (g_layer_mode == 2);
+    const bool v2 = (g_layer_mode == 2) || Hb > 0;           // only the version-2 kernel has the second gate pass
+    const bool pair = !v2 && (g_layer_mode == 0) && Gp % 32 == 0 && d.R % 32 == 0;
     int cs = pair ? 2 : (v2 ? 1 : g_layer_cluster);
-    while (!pair && cs > 1 && (d.G % (8 * cs) != 0 || d.R % (8 * cs) != 0)) cs >>= 1;
-    if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, d.G, d.layers, K1p, (uint64_t)d.G * K1p, BK, d.G / cs)) return rc;
+    while (!pair && cs > 1 && (Gp % (8 * cs) != 0 || d.R % (8 * cs) != 0)) cs >>= 1;
+    if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, Gp, d.layers, K1p, (uint64_t)Gp * K1p, BK, v2 ? 2 * Ha : Gp / cs)) return rc;
+    if (Hb > 0) {
+        if (int rc = make_tmap(&la.tm_w1b, w->w1, K1p, Gp, d.layers, K1p, (uint64_t)Gp * K1p, BK, 2 * Hb)) return rc;
+    } else {
+        la.tm_w1b = la.tm_w1;
+    }
     if (int rc = make_tmap(&la.tm_wo, w->wo, Hp, d.R, d.layers, Hp, (uint64_t)d.R * Hp, BK, d.R / cs)) return rc;
     const int nsuper = (ntiles + cs - 1) / cs;
     int nclusters = num_sms() / cs;
@@ -1536,14 +1595,14 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
     }
     if (int rc = make_tmap(&la.tm_hst, ws.hall, Hp, T, (uint64_t)d.layers * B, Hp, (uint64_t)T * Hp, BK, BM)) return rc;
-    la.B = B; la.T = T; la.R = d.R; la.G = d.G; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
+    la.B = B; la.T = T; la.R = d.R; la.G = Gp; la.Ha = Ha; la.Hb = Hb; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
     la.tiles_per_utt = tiles_per_utt;
     __nv_bfloat16* cur = ws.xa;
     __nv_bfloat16* nxt = ws.xb;
     for (int l = 0; l < d.layers; ++l) {
         la.tm_x = (cur == ws.xa) ? tm_xa : tm_xb;
         la.tm_xout = (cur == ws.xa) ? tm_xb : tm_xa;
-        la.gb = ws.gb + (size_t)l * B * d.G;
+        la.gb = ws.gb + (size_t)l * B * Gp;
         la.bo = w->bo + (size_t)l * d.R;
         la.x_in = cur;
         la.x_out = (l + 1 < d.layers) ? nxt : nullptr;

@@ -110,6 +110,20 @@ def _w1_kmajor(m, sh: StackShape, cpad: int) -> torch.Tensor:
     return torch.cat(parts, dim=1).contiguous()
 
 
+def _gate_rows_bf16(w1: torch.Tensor, H: int) -> torch.Tensor:
+    """(G, K) natural gate rows [tanh(0:H); sigmoid(0:H)] -> the row order of the tcgen05 layer kernels: each half zero
+    padded to Hh = H rounded up to 16, and, when a half exceeds 128 channels (more than one UMMA N of 256 rows), split into
+    two passes: [a(0:Ha); b(0:Ha); a(Ha:Hh); b(Ha:Hh)] with Ha = min(Hh, 128)  (include/wae_b200.h, wae_stack_bf16)."""
+    Hh = _ru(H, 16)
+    Ha = min(Hh, 128)
+    a = torch.nn.functional.pad(w1[:H], (0, 0, 0, Hh - H))
+    b = torch.nn.functional.pad(w1[H:2 * H], (0, 0, 0, Hh - H))
+    blocks = [a[:Ha], b[:Ha]]
+    if Hh > Ha:
+        blocks += [a[Ha:], b[Ha:]]
+    return torch.cat(blocks, dim=0)
+
+
 class Packed:
     """Holds the packed tensors (keeps them alive) and the ctypes struct pointing at them."""
 
@@ -165,7 +179,7 @@ def pack_bf16(wn) -> Packed:
     p = Packed()
     p.shape = sh
     t = p.t
-    t["w1"] = torch.stack([_w1_kmajor(m, sh, Cp) for m in mats]).to(bf).contiguous()                              # [L][G][K1p]
+    t["w1"] = torch.stack([_gate_rows_bf16(_w1_kmajor(m, sh, Cp), H) for m in mats]).to(bf).contiguous()         # [L][2*Hh][K1p]
     t["wo"] = torch.stack([torch.nn.functional.pad(m["wo"], (0, Hp - H)) for m in mats]).to(bf).contiguous()     # [L][R][Hp]
     t["ws"] = torch.stack([torch.nn.functional.pad(m["ws"], (0, Hp - H)) for m in mats]).to(bf).contiguous()     # [L][S][Hp]
     l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
