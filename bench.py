@@ -329,6 +329,42 @@ def main():
             extras[f"vq_vectors_per_s_N{N}"] = N / sec
             extras[f"vq_hbm_frac_N{N}"] = N * (64 * 4 * 2 + 8) / sec / 1e9 / peak_hbm
         model.wavenet.precision = "bf16"
+        # configs[4]: IN-WAE decoder (G = 368) teacher-forced forward, 64 x 2 s per GPU, bf16 tensor-core stack
+        # (full B x T sweep: tools/inwae_sweep.py -> profiles/)
+        from wavenet_autoencoders_b200 import testing as T
+        from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet as _WN
+        for name in ("inwae", "inwae_30x3"):
+            cfg = T.CONFIGS[name]
+            torch.manual_seed(0)
+            wn5 = _WN(**cfg).eval()
+            wn5.load_state_dict(T.synth_state_dict(wn5, 1))
+            wn5 = wn5.to(dev)
+            wn5.precision = "bf16"
+            hop5 = T.hop(cfg)
+            B5, T5 = 64, 32000 // hop5 * hop5
+            i5 = torch.randint(0, 256, (B5, T5), device=dev)
+            x5 = torch.zeros(B5, 256, T5, device=dev).scatter_(1, i5[:, None, :], 1.0)
+            c5 = torch.randn(B5, 64, T5 // hop5, device=dev)
+            g5 = torch.randint(0, 153, (B5, 1), device=dev)
+            with torch.no_grad():
+                for _ in range(2):
+                    y5 = wn5(x5, c5, g5)
+                    del y5
+                barrier()
+                e0.record()
+                for _ in range(3):
+                    y5 = wn5(x5, c5, g5)
+                    del y5
+                e1.record()
+                barrier()
+            sec = max_over_ranks(e0.elapsed_time(e1)) * 1e-3 / 3
+            H5, L5 = cfg["gate_channels"] // 2, cfg["layers"]
+            fl5 = L5 * (2 * 3 * 256 * 2 * H5 + 2 * 64 * 2 * H5 + 2 * H5 * 256 + 2 * H5 * 256) + 2 * 256 * 256 + 2 * 256 * 256
+            extras[f"{name}_fwd_samples_per_s"] = world * B5 * T5 / sec
+            extras[f"{name}_fwd_frac_of_bf16_peak"] = B5 * T5 * fl5 / sec / 1e12 / peak_tf
+            del wn5, x5, c5, i5
+            torch.cuda.empty_cache()
+        extras["inwae_config"] = "decoder only, 64 utt/GPU x 32000 samples, bf16 tcgen05 stack (gate rows in two accumulator passes)"
 
     cpu = None
     if rank == 0 and world == 1:
