@@ -364,6 +364,63 @@ def main():
             extras[f"{name}_fwd_frac_of_bf16_peak"] = B5 * T5 * fl5 / sec / 1e12 / peak_tf
             del wn5, x5, c5, i5
             torch.cuda.empty_cache()
+        # configs[2]: data-parallel VQ-WAE training step, 8 utterances x 7680-sample windows per GPU (8000 is not a multiple
+        # of the encoder's stride x hop), bf16 tcgen05 forward + GEMM backward, fp32 master weights, Adam
+        from wavenet_autoencoders_b200 import train_step as TS
+        torch.backends.cudnn.benchmark = True            # the (out-of-scope, cuDNN) encoder's default wgrad algorithm is 3 x 1.8 ms
+        tm = build_vqvae(dev).train()
+        tm.wavenet.precision = "bf16"
+        opt = TS.make_optimizer(tm, capturable=True)
+        rs = np.random.RandomState(7 + rank)
+        Bt, Tt = 8, 7680
+        ti = torch.tensor(rs.randint(0, 256, size=(Bt, Tt)), dtype=torch.long, device=dev)
+        tmf = torch.tensor(rs.normal(size=(Bt, 39, Tt // 160)), dtype=torch.float32, device=dev)
+        tg = torch.tensor(rs.randint(0, 153, size=(Bt, 1)), dtype=torch.long, device=dev)
+        nt = 5
+        # eager launches (about 3000 small kernels per step: host-bound) ...
+        for _ in range(3):
+            TS.train_step(tm, opt, ti, tmf, tg, world=world)
+        barrier()
+        e0.record()
+        for _ in range(nt):
+            TS.train_step(tm, opt, ti, tmf, tg, world=world)
+        e1.record()
+        barrier()
+        extras["train_eager_ms_per_step"] = max_over_ranks(e0.elapsed_time(e1)) / nt
+        # ... and the same step (all-reduce included) captured into one CUDA graph
+        gstep = TS.GraphedTrainStep(tm, opt, ti, tmf, tg, world=world)
+        for _ in range(2):
+            gstep(ti, tmf, tg)
+        barrier()
+        e0.record()
+        for _ in range(nt):
+            tloss = gstep(ti, tmf, tg)
+        e1.record()
+        barrier()
+        t_ms = max_over_ranks(e0.elapsed_time(e1)) / nt
+        extras["train_samples_per_s"] = world * Bt * Tt / (t_ms * 1e-3)
+        extras["train_ms_per_step"] = t_ms
+        extras["train_loss_after_steps"] = float(tloss)
+        if world > 1:            # all-reduce alone, same flat buffer size (7.6 M fp32 gradients), device-timed
+            import torch.distributed as _d
+            flat = torch.zeros(sum(p.numel() for p in tm.parameters()), device=dev)
+            for _ in range(3):
+                _d.all_reduce(flat)
+            barrier()
+            e0.record()
+            for _ in range(10):
+                _d.all_reduce(flat)
+            e1.record()
+            barrier()
+            extras["train_allreduce_ms"] = max_over_ranks(e0.elapsed_time(e1)) / 10
+            extras["train_allreduce_bytes"] = flat.numel() * 4
+        del gstep
+        extras["train_config"] = ("VQ-WAE step: 8 utt/GPU x 7680 samples, tcgen05 bf16 forward + bf16 GEMM backward with fused "
+                                  "gather/gate kernels, fp32 master weights, Adam, grad-clip 100, one flat NCCL all-reduce "
+                                  "when N > 1; the step is replayed as one CUDA graph")
+        del tm, opt
+        torch.backends.cudnn.benchmark = False
+        torch.cuda.empty_cache()
         extras["inwae_config"] = "decoder only, 64 utt/GPU x 32000 samples, bf16 tcgen05 stack (gate rows in two accumulator passes)"
 
     cpu = None

@@ -155,6 +155,34 @@ int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const flo
                               const float* up_filter, const float* gemb, int B, int T, float* logits,
                               void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Training forward: the same kernels, but every layer input, the gated activations and the channels-last conditioning are
+ * written to caller-owned buffers (all bf16) that the backward pass reads (modules.py:115-163 under autograd).  The
+ * version-2 layer kernel is used regardless of wae_set_layer_cluster.
+ */
+typedef struct wae_stack_saved {
+    void* x_all;   /* [L][B][T][R]   x_all[l] = input of residual layer l (x_all[0] = first conv output) */
+    void* h_all;   /* [L][B][T][Hp]  tanh * sigmoid of every layer, Hp = G/2 rounded up to 64 (padding channels are 0) */
+    void* c_cl;    /* [B][T][Cp]     conditioning, Cp = C rounded up to 64; NULL iff C == 0 */
+} wae_stack_saved;
+int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B, int T,
+                                float* logits, const wae_stack_saved* save, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
+/*
+ * Gather / element-wise kernels between the GEMMs of the stack's backward pass (wavenet_autoencoders_b200/training.py;
+ * modules.py:115-163 differentiated by hand).  bf16 channels-last activations, fp32 statistics.
+ *   wae_train_im2col    out[b][t] = [x[t-(kw-1)d] | .. | x[t] | c[t]]   (B,T,kw*R+Cp); zeros before the start of an utterance
+ *   wae_train_gate_bwd  z (B,T,2H) pre-activations without bias, gb (B,2H) [tanh | sigmoid] biases, dh = dh_a (row stride
+ *                       dh_a_stride elements) + dh_b (optional, (B,T,H))  ->  dz (B,T,2H), dgb (B,2H) += sum_t dz (caller zeroes)
+ *   wae_train_dx_accum  dx[t] = (dxo[t] + sum_j dxcat[t+(kw-1-j)d][j*R:(j+1)*R]) * scale;  dC (B,T,C) fp32 += dxcat[t][kw*R:kw*R+C]
+ */
+int wae_train_im2col(const void* x, const void* c, int B, int T, int R, int Cp, int kw, int dil, void* out, void* stream);
+int wae_train_gate_bwd(const void* z, const float* gb, const void* dh_a, long long dh_a_stride, const void* dh_b, int B, int T,
+                       int H, void* dz, float* dgb, void* stream);
+int wae_train_dx_accum(const void* dxcat, const void* dxo, int B, int T, int R, int C, int Cp, int kw, int dil, float scale,
+                       void* dx, float* dC, void* stream);
+
 /* Variant of the bf16 residual-layer kernel: -1 (default) = version-2 kernel (residual added by an identity MMA, x' and h
  * stored by TMA from shared memory); 0 = CTA-pair kernel (tcgen05 cta_group::2, M = 256 per MMA, each CTA
  * holds half of every weight k-block); 1, 2 or 4 = the 1-CTA kernel in clusters of that size, the CTAs of a cluster sharing

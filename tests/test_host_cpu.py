@@ -160,3 +160,63 @@ def test_vq_module_api():
         assert set(m.state_dict()) == names
     m = vqm.SlicedVectorQuantize(16, 8, K1=4)
     assert m.embedding2.weight.shape == (4, 4) and float(m.embedding1.weight.abs().max()) <= 1 / 16
+
+
+@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_k2"])
+def test_hand_derived_stack_backward_matches_autograd_float64(cfg_name):
+    """training.stack_backward (what the GPU training path runs in bf16 on the activations its tcgen05 forward saves) in
+    float64 against torch autograd over the same layer equations: every weight, bias, the conditioning and the speaker vector."""
+    import math
+    from wavenet_autoencoders_b200 import packing, training
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    cfg = T.CONFIGS[cfg_name]
+    torch.manual_seed(0)
+    m = WaveNet(**cfg).train()
+    m.load_state_dict(T.synth_state_dict(m, 4))
+    sh = packing.stack_shape(m)
+    L, R, H, C, kw = sh.layers, sh.R, sh.H, sh.C, sh.kernel_size
+    B, Tn = 2, 96
+    x, idx, c, spk = T.synth_inputs(cfg, B, Tn, 5)
+    D = torch.float64
+    with torch.no_grad():
+        c_up0 = m.upsample_net(c).to(D)
+        g0 = m._speaker_vectors(spk, B).to(D)
+        y_mod = m._forward_autograd(x, c_up0.float(), g0.float(), False)
+    ws = [None if w is None else w.detach().to(D).requires_grad_(True) for w in training.live_weights(m)]
+    c_up, gv = c_up0.clone().requires_grad_(True), g0.clone().requires_grad_(True)
+    P = training.PER_LAYER
+    Hp, Cp = -(-H // 64) * 64, -(-C // 64) * 64
+    base = L * P
+    xs, hs = [], []
+    cur = (ws[base][:, :, 0] @ x.to(D)).transpose(1, 2) + ws[base + 1]                 # (B,T,R) channels-last
+    ccl = c_up.transpose(1, 2)
+    skips = 0
+    for l in range(L):
+        W1, b1, Wc, Wg, Wo, bo, Ws, bs = ws[l * P: l * P + P]
+        xs.append(cur)
+        z = sum(training._shift(cur, (kw - 1 - j) * sh.dilations[l]) @ W1[:, :, j].t() for j in range(kw)) + b1
+        z = z + ccl @ Wc[:, :, 0].t() + (gv @ Wg[:, :, 0].t())[:, None, :]
+        h = torch.tanh(z[..., :H]) * torch.sigmoid(z[..., H:])
+        hs.append(h)
+        skips = skips + h @ Ws[:, :, 0].t() + bs
+        cur = (h @ Wo[:, :, 0].t() + bo + cur) * math.sqrt(0.5)
+    s = torch.relu(skips * math.sqrt(1.0 / L))
+    s = torch.relu(s @ ws[base + 2][:, :, 0].t() + ws[base + 3])
+    logits = (s @ ws[base + 4][:, :, 0].t() + ws[base + 5]).transpose(1, 2)            # (B,O,T)
+    assert rel_err(logits.detach().float().numpy(), y_mod.numpy()) < 1e-5                # the same function as the module
+    cot = torch.randn_like(logits)
+    ins = [w for w in ws if w is not None] + [c_up, gv]
+    ref = torch.autograd.grad((logits * cot).sum(), ins, allow_unused=True)
+    x_all = torch.stack([t.detach() for t in xs])
+    h_all = torch.nn.functional.pad(torch.stack([t.detach() for t in hs]), (0, Hp - H))
+    c_cl = torch.nn.functional.pad(ccl.detach(), (0, Cp - C))
+    _, dc, dg, grads = training.stack_backward(sh, list(sh.dilations), x.to(D), gv.detach(), x_all, h_all, c_cl,
+                                               [None if w is None else w.detach() for w in ws], cot, cdt=D, adt=D)
+    got = [g for g, w in zip(grads, ws) if w is not None] + [dc, dg]
+    names = [i for i, w in enumerate(ws) if w is not None] + ["c", "g"]
+    for n, a, b in zip(names, ref, got):
+        if a is None:                                   # the last layer's residual 1x1: no gradient under autograd either
+            assert b is None or float(b.abs().max()) == 0, n
+            continue
+        assert b is not None, n
+        assert rel_err(b.numpy(), a.numpy()) < 1e-9, (n, rel_err(b.numpy(), a.numpy()))

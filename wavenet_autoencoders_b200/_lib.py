@@ -41,6 +41,10 @@ class StackBF16(C.Structure):
                                     ("w1", "wo", "ws", "w3", "w4", "b1", "wg", "bo", "bs_sum", "b3", "b4", "wf", "bf")]
 
 
+class StackSaved(C.Structure):
+    _fields_ = [("x_all", C.c_void_p), ("h_all", C.c_void_p), ("c_cl", C.c_void_p)]
+
+
 class ArWeights(C.Structure):
     _fields_ = [
         ("d", StackDims),
@@ -70,6 +74,13 @@ SIGNATURES = {
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "wae_stack_forward_bf16_up": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wae_stack_forward_bf16_save": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                              C.c_void_p, C.POINTER(StackSaved), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wae_train_im2col": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "wae_train_gate_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wae_train_dx_accum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
+                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     "wae_set_layer_cluster": (C.c_int, [C.c_int]),
     "wae_layer_set_profile_buffer": (None, [C.c_void_p]),
     "wae_profile_enable": (None, [C.c_int]),

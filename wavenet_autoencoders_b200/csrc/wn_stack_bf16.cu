@@ -1498,8 +1498,8 @@ size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T) {
 }
 
 static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, const float* c, int up_s, const float* up_w,
-                                   const float* gemb, int B, int T, float* logits, void* workspace,
-                                   size_t workspace_bytes, void* stream_) {
+                                   const float* gemb, int B, int T, float* logits, const wae_stack_saved* save,
+                                   void* workspace, size_t workspace_bytes, void* stream_) {
     if (int rc = wae::require_sm100()) return rc;
     WAE_REQUIRE(w && x && logits && workspace, "wae_stack_forward_bf16: null pointer");
     const wae_stack_dims& d = w->d;
@@ -1521,6 +1521,15 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     if (workspace_bytes < ws.total)
         return wae::set_error(WAE_ERR_WORKSPACE, "wae_stack_forward_bf16: workspace %zu < %zu", workspace_bytes, ws.total);
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (save != nullptr) {
+        // training: the caller keeps every layer input, the gated activations and the conditioning for the backward pass
+        WAE_REQUIRE(save->x_all && save->h_all && ((d.C == 0) || save->c_cl), "wae_stack_forward_bf16_save: null buffer");
+        WAE_REQUIRE(((reinterpret_cast<uintptr_t>(save->x_all) | reinterpret_cast<uintptr_t>(save->h_all) |
+                      reinterpret_cast<uintptr_t>(save->c_cl)) & 127) == 0, "wae_stack_forward_bf16_save: buffers must be 128-byte aligned");
+        ws.hall = static_cast<__nv_bfloat16*>(save->h_all);
+        if (d.C > 0) ws.ccl = static_cast<__nv_bfloat16*>(save->c_cl);
+        ws.xa = static_cast<__nv_bfloat16*>(save->x_all);
+    }
 
     const int Hp = (H + BK - 1) / BK * BK;
     const int Cp = (d.C + BK - 1) / BK * BK;
@@ -1555,7 +1564,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
 
     // ---- layers ----
     const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 256 + 1024;
-    if (g_layer_mode != 2 && Hb == 0) {
+    if (g_layer_mode != 2 && Hb == 0 && save == nullptr) {
         WAE_REQUIRE(smem_layer <= 232448, "wae_stack_forward_bf16: layer kernel shared memory %zu too large", smem_layer);
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
     }
@@ -1570,7 +1579,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         la.tm_c = tm_xa;  // never used (nk_c == 0)
     }
     // Layer-kernel variant: CTA pairs (cta_group::2, default) or the 1-CTA kernel in clusters of 1/2/4 with weight multicast.
-    const bool v2 = (g_layer_mode == 2) || Hb > 0;           // only the version-2 kernel has the second gate pass
+    const bool v2 = (g_layer_mode == 2) || Hb > 0 || save != nullptr;           // only the version-2 kernel has the second gate pass
     const bool pair = !v2 && (g_layer_mode == 0) && Gp % 32 == 0 && d.R % 32 == 0;
     int cs = pair ? 2 : (v2 ? 1 : g_layer_cluster);
     while (!pair && cs > 1 && (Gp % (8 * cs) != 0 || d.R % (8 * cs) != 0)) cs >>= 1;
@@ -1598,10 +1607,16 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     la.B = B; la.T = T; la.R = d.R; la.G = Gp; la.Ha = Ha; la.Hb = Hb; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
     la.tiles_per_utt = tiles_per_utt;
     __nv_bfloat16* cur = ws.xa;
-    __nv_bfloat16* nxt = ws.xb;
+    __nv_bfloat16* nxt = (save != nullptr) ? ws.xa + (size_t)B * T * d.R : ws.xb;
     for (int l = 0; l < d.layers; ++l) {
-        la.tm_x = (cur == ws.xa) ? tm_xa : tm_xb;
-        la.tm_xout = (cur == ws.xa) ? tm_xb : tm_xa;
+        if (save != nullptr) {        // layer l reads x_all[l] and writes x_all[l + 1]
+            if (l == 0) la.tm_x = tm_xa; else la.tm_x = la.tm_xout;
+            if (l + 1 < d.layers)
+                if (int rc = make_tmap(&la.tm_xout, nxt, d.R, T, B, d.R, (uint64_t)T * d.R, BK, BM)) return rc;
+        } else {
+            la.tm_x = (cur == ws.xa) ? tm_xa : tm_xb;
+            la.tm_xout = (cur == ws.xa) ? tm_xb : tm_xa;
+        }
         la.gb = ws.gb + (size_t)l * B * Gp;
         la.bo = w->bo + (size_t)l * d.R;
         la.x_in = cur;
@@ -1629,7 +1644,8 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
             else WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_kernel, la));
         }
         WAE_CHECK_LAUNCH();
-        __nv_bfloat16* t = cur; cur = nxt; nxt = t;
+        if (save != nullptr) { cur = nxt; nxt = nxt + (size_t)B * T * d.R; }
+        else { __nv_bfloat16* t = cur; cur = nxt; nxt = t; }
     }
 
     // ---- head ----
@@ -1653,7 +1669,14 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
 
 int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,
                            int T, float* logits, void* workspace, size_t workspace_bytes, void* stream) {
-    return stack_forward_bf16_impl(w, x, c, 0, nullptr, gemb, B, T, logits, workspace, workspace_bytes, stream);
+    return stack_forward_bf16_impl(w, x, c, 0, nullptr, gemb, B, T, logits, nullptr, workspace, workspace_bytes, stream);
+}
+
+int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,
+                                int T, float* logits, const wae_stack_saved* save, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    WAE_REQUIRE(save != nullptr, "wae_stack_forward_bf16_save: null save descriptor");
+    return stack_forward_bf16_impl(w, x, c, 0, nullptr, gemb, B, T, logits, save, workspace, workspace_bytes, stream);
 }
 
 int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const float* c_frames, int Tc, int up_scale,
@@ -1663,7 +1686,7 @@ int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const flo
     WAE_REQUIRE(w->d.C > 0, "wae_stack_forward_bf16_up: the stack has no local conditioning (C = 0)");
     WAE_REQUIRE(up_scale >= 1 && Tc >= 1 && (long long)Tc * up_scale == T,
                 "wae_stack_forward_bf16_up: %d frames x scale %d != T = %d", Tc, up_scale, T);
-    return stack_forward_bf16_impl(w, x, c_frames, up_scale, up_filter, gemb, B, T, logits, workspace, workspace_bytes, stream);
+    return stack_forward_bf16_impl(w, x, c_frames, up_scale, up_filter, gemb, B, T, logits, nullptr, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -1,0 +1,194 @@
+// Element-wise / gather kernels of the decoder stack's backward pass (training.py): everything between the GEMMs.
+// All activations are bf16 channels-last [B][T][channels]; these kernels are pure HBM streams (16-byte accesses).
+//
+//   wae_train_im2col     Xcat[b][t] = [x[t-(kw-1)d] | ... | x[t-d] | x[t] | c[t]]      operand of z = Xcat W1cat^T and of dW1cat = dz^T Xcat
+//   wae_train_gate_bwd   dz = [dh sig (1 - tanh^2) | dh tanh sig (1 - sig)],  dgb[b] += sum_t dz      (modules.py:138,154 differentiated)
+//   wae_train_dx_accum   dx[t] = (dxo[t] + sum_j dXcat[t + (kw-1-j)d][tap j]) * scale,  dC[t] += dXcat[t][c part]
+#include "wae_common.cuh"
+
+#include <cuda_bf16.h>
+
+#include "../../include/wae_b200.h"
+
+namespace {
+
+using wae::ptx::pack_bf16x2;
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 v;
+    v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]);
+    v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    return v;
+}
+
+// one thread per 16-byte chunk of the output row [kw*R + Cp]
+__global__ void __launch_bounds__(256)
+im2col_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ c, int T, int R, int Cp, int kw, int dil,
+              __nv_bfloat16* __restrict__ out, long long rows) {
+    const int K8 = (kw * R + Cp) >> 3, R8 = R >> 3;
+    const long long total = rows * K8;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / K8;                 // b * T + t
+        const int k8 = (int)(e - row * K8);
+        const int t = (int)(row % T);
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (k8 < kw * R8) {
+            const int j = k8 / R8, r8 = k8 - j * R8, s = (kw - 1 - j) * dil;
+            if (t - s >= 0) v = __ldg(reinterpret_cast<const uint4*>(x + (row - s) * R) + r8);
+        } else {
+            v = __ldg(reinterpret_cast<const uint4*>(c + row * Cp) + (k8 - kw * R8));
+        }
+        reinterpret_cast<uint4*>(out)[e] = v;
+    }
+}
+
+// block = 64 time steps of one utterance x all H channels (8 per thread); dgb partial sums via shared memory + atomics
+constexpr int GB_T = 64;
+__global__ void __launch_bounds__(256)
+gate_bwd_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ gb, const __nv_bfloat16* __restrict__ dh_a,
+                long long dh_a_stride, const __nv_bfloat16* __restrict__ dh_b, int T, int H, __nv_bfloat16* __restrict__ dz,
+                float* __restrict__ dgb) {
+    extern __shared__ float s_dgb[];                  // [2 * H]
+    const int b = blockIdx.y, t0 = blockIdx.x * GB_T, G = 2 * H, H8 = H >> 3;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) s_dgb[i] = 0.f;
+    __syncthreads();
+    // thread -> fixed channel group (so its partial sums stay in registers), strided over time
+    const int per_t = H8;                             // threads per time step
+    const int tl = threadIdx.x / per_t, c8 = threadIdx.x - tl * per_t, tstep = blockDim.x / per_t;
+    if (tl < tstep) {
+        float ga[8], gbv[8], sa[8], sb[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            ga[i] = __ldg(&gb[(size_t)b * G + c8 * 8 + i]);
+            gbv[i] = __ldg(&gb[(size_t)b * G + H + c8 * 8 + i]);
+            sa[i] = sb[i] = 0.f;
+        }
+        for (int tt = tl; tt < GB_T && t0 + tt < T; tt += tstep) {
+            const size_t row = (size_t)b * T + t0 + tt;
+            float za[8], zb[8], dh[8], tmp[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(z + row * G) + c8), za);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(z + row * G + H) + c8), zb);
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dh_a + row * dh_a_stride) + c8), dh);
+            if (dh_b != nullptr) {
+                unpack8(__ldg(reinterpret_cast<const uint4*>(dh_b + row * H) + c8), tmp);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dh[i] += tmp[i];
+            }
+            float da[8], db[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float th = tanhf(za[i] + ga[i]);
+                const float sg = 1.f / (1.f + __expf(-(zb[i] + gbv[i])));
+                da[i] = dh[i] * sg * (1.f - th * th);
+                db[i] = dh[i] * th * sg * (1.f - sg);
+                sa[i] += da[i];
+                sb[i] += db[i];
+            }
+            reinterpret_cast<uint4*>(dz + row * G)[c8] = pack8(da);
+            reinterpret_cast<uint4*>(dz + row * G + H)[c8] = pack8(db);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            atomicAdd(&s_dgb[c8 * 8 + i], sa[i]);
+            atomicAdd(&s_dgb[H + c8 * 8 + i], sb[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G; i += blockDim.x) atomicAdd(&dgb[(size_t)b * G + i], s_dgb[i]);
+}
+
+__global__ void __launch_bounds__(256)
+dx_accum_kernel(const __nv_bfloat16* __restrict__ dxcat, const __nv_bfloat16* __restrict__ dxo, int T, int R, int C, int Cp, int kw,
+                int dil, float scale, __nv_bfloat16* __restrict__ dx, float* __restrict__ dC, long long rows) {
+    const int R8 = R >> 3, C8 = (C + 7) >> 3, K = kw * R + Cp, W8 = R8 + C8;
+    const long long total = rows * W8;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / W8;
+        const int w8 = (int)(e - row * W8);
+        const int t = (int)(row % T);
+        if (w8 < R8) {
+            float acc[8], tmp[8];
+            if (dxo != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(dxo + row * R) + w8), acc);
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+            }
+            for (int j = 0; j < kw; ++j) {
+                const int s = (kw - 1 - j) * dil;
+                if (t + s < T) {
+                    unpack8(__ldg(reinterpret_cast<const uint4*>(dxcat + (row + s) * K + j * R) + w8), tmp);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] += tmp[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] *= scale;
+            reinterpret_cast<uint4*>(dx + row * R)[w8] = pack8(acc);
+        } else {
+            const int c8 = w8 - R8;
+            float tmp[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(dxcat + row * K + kw * R) + c8), tmp);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (c8 * 8 + i < C) dC[row * C + c8 * 8 + i] += tmp[i];
+        }
+    }
+}
+
+inline unsigned grid_for(long long items) {
+    long long b = (items + 255) / 256;
+    if (b > 148 * 32) b = 148 * 32;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+
+extern "C" {
+
+int wae_train_im2col(const void* x, const void* c, int B, int T, int R, int Cp, int kw, int dil, void* out, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(x && out && (Cp == 0 || c), "wae_train_im2col: null pointer");
+    WAE_REQUIRE(B > 0 && T > 0 && R % 8 == 0 && Cp % 8 == 0 && kw >= 1 && dil >= 1, "wae_train_im2col: bad sizes");
+    const long long rows = (long long)B * T;
+    im2col_kernel<<<grid_for(rows * ((kw * R + Cp) / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(c), T, R, Cp, kw, dil,
+        static_cast<__nv_bfloat16*>(out), rows);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+int wae_train_gate_bwd(const void* z, const float* gb, const void* dh_a, long long dh_a_stride, const void* dh_b, int B, int T,
+                       int H, void* dz, float* dgb, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(z && gb && dh_a && dz && dgb, "wae_train_gate_bwd: null pointer");
+    WAE_REQUIRE(B > 0 && B <= 65535 && T > 0 && H % 8 == 0 && H >= 8 && H <= 2048 && dh_a_stride % 8 == 0,
+                "wae_train_gate_bwd: needs H %% 8 == 0, 8 <= H <= 2048 (H=%d)", H);
+    gate_bwd_kernel<<<dim3((T + GB_T - 1) / GB_T, B), 256, 2 * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(z), gb, static_cast<const __nv_bfloat16*>(dh_a), dh_a_stride,
+        static_cast<const __nv_bfloat16*>(dh_b), T, H, static_cast<__nv_bfloat16*>(dz), dgb);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+int wae_train_dx_accum(const void* dxcat, const void* dxo, int B, int T, int R, int C, int Cp, int kw, int dil, float scale,
+                       void* dx, float* dC, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(dxcat && dx && (C == 0 || dC), "wae_train_dx_accum: null pointer");
+    WAE_REQUIRE(B > 0 && T > 0 && R % 8 == 0 && Cp % 8 == 0 && C <= Cp && kw >= 1, "wae_train_dx_accum: bad sizes");
+    const long long rows = (long long)B * T;
+    dx_accum_kernel<<<grid_for(rows * (R / 8 + (C + 7) / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dxcat), static_cast<const __nv_bfloat16*>(dxo), T, R, C, Cp, kw, dil, scale,
+        static_cast<__nv_bfloat16*>(dx), dC, rows);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,254 @@
+"""Training path of the decoder stack (BASELINE configs[2], SURVEY 8(b) "autograd-differentiable forward").
+
+Forward: the same tcgen05 kernels as inference (``wae_stack_forward_bf16_save``), which additionally keep every layer
+input ``x_all``, the gated activations ``h_all`` and the channels-last conditioning for the backward pass.
+
+Backward: the layer equations of ``ResidualConv1dGLU._forward`` (modules.py:115-163) differentiated by hand on those saved
+bf16 channels-last tensors.  Every contraction is a plain dense GEMM (library bf16 matmuls with fp32 accumulation; the
+hand-written dgrad/wgrad tcgen05 kernels are the next step), organised so that a layer costs five GEMMs:
+
+    Xcat = [x(t-2d) | x(t-d) | x(t) | c(t)]                 (B,T,kw*R+Cp)   gathered once per layer
+    z    = Xcat W1cat^T + gb            (recomputed: only h = tanh*sigmoid was stored, 256 B/sample/layer instead of 768)
+    dh   = dS Ws + (dx' sqrt(.5)) Wo                        skip term for all layers comes from ONE GEMM over K = L*H
+    dz   = [dh sig (1-tanh^2) | dh tanh sig (1-sig)]
+    dW1cat = dz^T Xcat ,  dXcat = dz W1cat  ->  dx (taps shifted back) , dc
+    dWo  = (dx' sqrt(.5))^T h
+
+The result is a custom ``torch.autograd.Function`` whose inputs are the weight-norm-folded weights, so the gradients flow on
+to ``weight_g`` / ``weight_v``, the speaker embedding and the upsampling network through ordinary autograd.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch.nn import functional as F
+
+from . import _lib, packing
+
+BF = torch.bfloat16
+
+
+def _fw(m):
+    """Weight-norm folded weight WITH autograd history (packing.folded_weight is the detached twin)."""
+    if hasattr(m, "weight_g") and hasattr(m, "weight_v"):
+        return torch._weight_norm(m.weight_v, m.weight_g, 0)
+    return m.weight
+
+
+def live_weights(wn):
+    """Flat list of the stack's folded weights and biases, fixed order (None where a conv has no bias / is absent)."""
+    out = []
+    for f in wn.conv_layers:
+        out += [_fw(f.conv), f.conv.bias,
+                _fw(f.conv1x1c) if f.conv1x1c is not None else None,
+                _fw(f.conv1x1g) if f.conv1x1g is not None else None,
+                _fw(f.conv1x1_out), f.conv1x1_out.bias, _fw(f.conv1x1_skip), f.conv1x1_skip.bias]
+    l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
+    out += [_fw(wn.first_conv), wn.first_conv.bias, _fw(l1), l1.bias, _fw(l3), l3.bias]
+    return out
+
+
+PER_LAYER = 8
+
+
+def _shift(x, s):
+    """x[b, t - s] with zeros for t < s (the causal left padding, modules.py:80-85)."""
+    return x if s == 0 else F.pad(x, (0, 0, s, 0))[:, : x.shape[1]]
+
+
+def _unshift(y, s):
+    """adjoint of _shift: y[b, t + s], zeros past the end."""
+    return y if s == 0 else F.pad(y, (0, 0, 0, s))[:, s:]
+
+
+def _colsum(t, adt=torch.float32):
+    return t.to(adt).sum(dim=tuple(range(t.dim() - 1)))
+
+
+def _wgrad(dy, x, adt=torch.float32):
+    """dy (B,T,N), x (B,T,K) -> dy^T x (N,K), one GEMM over K = B*T."""
+    return (dy.reshape(-1, dy.shape[-1]).t() @ x.reshape(-1, x.shape[-1])).to(adt)
+
+
+class StackTrainFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wn, x, c_up, gvec, *weights):
+        sh = packing.stack_shape(wn)
+        B, _, T = x.shape
+        dev = x.device
+        L, R, H = sh.layers, sh.R, sh.H
+        Hp, Cp = packing._ru(H, 64), (packing._ru(sh.C, 64) if sh.C else 0)
+        pk = packing.pack_bf16(wn)
+        lib = _lib.lib()
+        xf = x.detach().float().contiguous()
+        cf = None if c_up is None else c_up.detach().float().contiguous()
+        gf = None if gvec is None else gvec.detach().float().contiguous()
+        logits = torch.empty(B, sh.O, T, dtype=torch.float32, device=dev)
+        x_all = torch.empty(L, B, T, R, dtype=BF, device=dev)
+        h_all = torch.empty(L, B, T, Hp, dtype=BF, device=dev)
+        c_cl = torch.empty(B, T, Cp, dtype=BF, device=dev) if sh.C else None
+        save = _lib.StackSaved(_lib.ptr(x_all), _lib.ptr(h_all), _lib.ptr(c_cl))
+        n = lib.wae_stack_workspace_bf16(pk.struct.d, B, T)
+        ws = wn._ws.get(n, dev)
+        _lib.check(lib.wae_stack_forward_bf16_save(pk.struct, _lib.ptr(xf), _lib.ptr(cf), _lib.ptr(gf), B, T, _lib.ptr(logits),
+                                                   save, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                   "wae_stack_forward_bf16_save")
+        ctx.sh, ctx.dil = sh, list(sh.dilations)
+        ctx.x_needs_grad = x.requires_grad
+        ctx.c_present, ctx.g_present = c_up is not None, gvec is not None
+        ctx.save_for_backward(xf, gf, x_all, h_all, c_cl, *[None if w is None else w.detach() for w in weights])
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        xf, gf, x_all, h_all, c_cl, *weights = ctx.saved_tensors
+        dxin, dc_up, dgvec, grads = stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, ctx.x_needs_grad)
+        return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, *grads)
+
+
+def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_needs_grad=False, cdt=BF, adt=torch.float32):
+    """Hand-derived backward of the decoder stack on saved channels-last activations.  cdt: GEMM operand dtype (bf16 on the
+    GPU), adt: accumulation / element-wise dtype.  tests/test_host_cpu.py runs it in float64 against torch autograd."""
+    if True:
+        L, R, G, H, S, C, O, kw = sh.layers, sh.R, sh.G, sh.H, sh.S, sh.C, sh.O, sh.kernel_size
+        _, B, T, _ = x_all.shape
+        Hp = h_all.shape[-1]
+        Cp = c_cl.shape[-1] if c_cl is not None else 0
+        scale = math.sqrt(1.0 / L)
+        rs = math.sqrt(0.5)
+        grads = [None] * len(weights)
+
+        def lw(l, k):
+            return weights[l * PER_LAYER + k]
+
+        base = L * PER_LAYER
+        Wf, W3, W4 = weights[base], weights[base + 2], weights[base + 4]
+        b3 = weights[base + 3]
+
+        # ---- head: logits = W4 relu(W3 relu(s) + b3) + b4,  s = (sum_l Ws_l h_l + bs_l) * sqrt(1/L) ----
+        dY = dlogits.transpose(1, 2).to(cdt).contiguous()                                  # (B,T,O)
+        Hcat = h_all.permute(1, 2, 0, 3).reshape(B, T, L * Hp)                            # (B,T,L*Hp)
+        Wscat = torch.cat([F.pad(lw(l, 6)[:, :, 0], (0, Hp - H)) for l in range(L)], dim=1).to(cdt)   # (S, L*Hp)
+        bs_sum = torch.zeros(S, dtype=adt, device=dY.device)
+        for l in range(L):
+            if lw(l, 7) is not None:
+                bs_sum = bs_sum + lw(l, 7).to(adt)
+        s = ((Hcat @ Wscat.t()).to(adt) + bs_sum) * scale
+        r1 = torch.relu(s).to(cdt)
+        p2 = (r1 @ W3[:, :, 0].to(cdt).t()).to(adt) + (b3.to(adt) if b3 is not None else 0.0)
+        r2 = torch.relu(p2).to(cdt)
+        grads[base + 4] = _wgrad(dY, r2, adt).unsqueeze(-1)
+        if weights[base + 5] is not None:
+            grads[base + 5] = _colsum(dY, adt)
+        dp2 = ((dY @ W4[:, :, 0].to(cdt)).to(adt) * (p2 > 0)).to(cdt)
+        grads[base + 2] = _wgrad(dp2, r1, adt).unsqueeze(-1)
+        if b3 is not None:
+            grads[base + 3] = _colsum(dp2, adt)
+        dS = ((dp2 @ W3[:, :, 0].to(cdt)).to(adt) * (s > 0) * scale).to(cdt)               # d loss / d (skip sum), the same for every layer
+        del s, r1, p2, r2, dp2
+        dWscat = _wgrad(dS, Hcat, adt)                                                         # (S, L*Hp): every layer's skip wgrad in one GEMM
+        dbs = _colsum(dS, adt)
+        dHskip = dS @ Wscat                                                               # (B,T,L*Hp)
+        del Hcat
+
+        # ---- residual layers, last to first ----
+        # On the GPU (bf16) the gathers and element-wise chains between the GEMMs are three CUDA kernels (csrc/wn_train.cu);
+        # the float64 CPU check of the same derivation runs them as torch expressions.
+        fused = (cdt == BF and x_all.is_cuda)
+        lib = _lib.lib() if fused else None
+        st = _lib.stream_ptr(x_all.device) if fused else None
+        dev = dS.device
+        dx = None                                    # fused: bf16 d loss / d x_{l+1} ALREADY scaled by sqrt(.5) (= dxo); else unscaled, adt
+        dC = torch.zeros(B, T, C, dtype=adt, device=dev) if C else None
+        dgvec = torch.zeros_like(gf, dtype=adt) if gf is not None else None
+        K = kw * R + Cp
+        for l in reversed(range(L)):
+            d = dil[l]
+            W1, b1, Wc, Wg, Wo = lw(l, 0), lw(l, 1), lw(l, 2), lw(l, 3), lw(l, 4)
+            grads[l * PER_LAYER + 6] = dWscat[:, l * Hp: l * Hp + H].unsqueeze(-1).contiguous()
+            if lw(l, 7) is not None:
+                grads[l * PER_LAYER + 7] = dbs
+            dh_skip = dHskip[..., l * Hp: l * Hp + H]                       # view, row stride L*Hp
+            h_l = h_all[l][..., :H]
+            dh_res = None
+            if dx is not None:
+                dxo = dx if fused else (dx * rs).to(cdt)
+                dh_res = dxo @ Wo[:, :, 0].to(cdt)                          # (B,T,H)
+                grads[l * PER_LAYER + 4] = _wgrad(dxo, h_l, adt).unsqueeze(-1)
+                if lw(l, 5) is not None:
+                    grads[l * PER_LAYER + 5] = _colsum(dxo, adt)
+            else:                         # last layer: its residual branch is dead -- no gradient, as under autograd in the reference
+                dxo = None
+            wparts = [W1[:, :, j] for j in range(kw)]
+            if C:
+                wparts.append(F.pad(Wc[:, :, 0], (0, Cp - C)))
+            W1cat = torch.cat(wparts, dim=1).to(cdt)                        # (G,K)
+            gb = b1.to(adt) if b1 is not None else torch.zeros(G, dtype=adt, device=dev)
+            gb = gb[None, :].expand(B, G)
+            if Wg is not None and gf is not None:
+                gb = gb + gf.to(adt) @ Wg[:, :, 0].to(adt).t()
+            # recompute the gate pre-activations from the saved layer input
+            X = x_all[l]
+            if fused:
+                Xcat = torch.empty(B, T, K, dtype=BF, device=dev)
+                _lib.check(lib.wae_train_im2col(_lib.ptr(X), _lib.ptr(c_cl), B, T, R, Cp, kw, d, _lib.ptr(Xcat), st), "wae_train_im2col")
+                z = Xcat @ W1cat.t()                                        # (B,T,G) bf16, bias added inside the gate kernel
+                dz = torch.empty(B, T, G, dtype=BF, device=dev)
+                dgb = torch.zeros(B, G, dtype=torch.float32, device=dev)
+                gbc = gb.float().contiguous()
+                _lib.check(lib.wae_train_gate_bwd(_lib.ptr(z), _lib.ptr(gbc), dh_skip.data_ptr(), L * Hp, _lib.ptr(dh_res), B, T, H,
+                                                  _lib.ptr(dz), _lib.ptr(dgb), st), "wae_train_gate_bwd")
+                del z
+            else:
+                parts = [_shift(X, (kw - 1 - j) * d) for j in range(kw)] + ([c_cl] if C else [])
+                Xcat = torch.cat(parts, dim=-1)                             # (B,T,K)
+                z = (Xcat @ W1cat.t()).to(adt) + gb[:, None, :]
+                th, sg = torch.tanh(z[..., :H]), torch.sigmoid(z[..., H:])
+                dhf = dh_skip.to(adt) + (dh_res.to(adt) if dh_res is not None else 0.0)
+                dz = torch.cat([dhf * sg * (1 - th * th), dhf * th * sg * (1 - sg)], dim=-1)
+                del z, th, sg, dhf
+                dgb = dz.sum(1)                                             # (B,G)
+                dz = dz.to(cdt)
+            if b1 is not None:
+                grads[l * PER_LAYER + 1] = dgb.sum(0)
+            if Wg is not None and gf is not None:
+                grads[l * PER_LAYER + 3] = (dgb.to(adt).t() @ gf.to(adt)).unsqueeze(-1)
+                dgvec += dgb.to(adt) @ Wg[:, :, 0].to(adt)
+            dW1cat = _wgrad(dz, Xcat, adt)                                  # (G,K)
+            grads[l * PER_LAYER + 0] = torch.stack([dW1cat[:, j * R:(j + 1) * R] for j in range(kw)], dim=-1)
+            if C:
+                grads[l * PER_LAYER + 2] = dW1cat[:, kw * R: kw * R + C].unsqueeze(-1).contiguous()
+            dXcat = dz @ W1cat                                              # (B,T,K)
+            del Xcat, dz
+            if fused:
+                dxn = torch.empty(B, T, R, dtype=BF, device=dev)
+                _lib.check(lib.wae_train_dx_accum(_lib.ptr(dXcat), _lib.ptr(dxo), B, T, R, C, Cp, kw, d, rs if l > 0 else 1.0,
+                                                  _lib.ptr(dxn), _lib.ptr(dC), st), "wae_train_dx_accum")
+            else:
+                dxn = dxo.to(adt) if dxo is not None else 0.0
+                for j in range(kw):
+                    dxn = dxn + _unshift(dXcat[..., j * R:(j + 1) * R], (kw - 1 - j) * d).to(adt)
+                if C:
+                    dC += dXcat[..., kw * R: kw * R + C].to(adt)
+            dx = dxn
+            del dXcat
+
+        # ---- first conv: x0 = Wf x + bf ----
+        dx0 = dx.to(cdt)
+        xb = xf.to(cdt)                                                                    # (B,Oin,T); exact for one-hot input
+        grads[base] = torch.bmm(xb, dx0).to(adt).sum(0).t().unsqueeze(-1).contiguous()    # (R,Oin,1)
+        if weights[base + 1] is not None:
+            grads[base + 1] = _colsum(dx0, adt)
+        dxin = None
+        if x_needs_grad:
+            dxin = (dx0 @ Wf[:, :, 0].to(cdt)).to(adt).transpose(1, 2).contiguous()
+        dc_up = dC.transpose(1, 2).contiguous() if C else None
+        grads = [g if g is None or w is None else g.to(w.dtype).reshape(w.shape) for g, w in zip(grads, weights)]
+        return dxin, dc_up, dgvec, grads
+
+
+def stack_forward_train(wn, x, c_up, gvec):
+    """(B,O,T) logits with autograd through the tcgen05 forward + GEMM backward.  x one-hot / dense (B,Oin,T); c_up
+    (B,C,T) already upsampled; gvec (B,Gi) speaker vectors (with autograd history back to the embedding)."""
+    return StackTrainFunction.apply(wn, x, c_up, gvec, *live_weights(wn))

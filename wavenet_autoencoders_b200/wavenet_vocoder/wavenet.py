@@ -80,6 +80,7 @@ class WaveNet(nn.Module):
         self.ar_cluster = None            # None -> 16 CTAs for fp32 weights, 8 for bf16
         self.ar_utts_per_cluster = None   # None -> 8 for the tensor-core AR kernel, 2 for the SIMT kernel
         self.ar_impl = "mma"               # "mma" | "simt" (bf16 precision only)
+        self.train_impl = "kernels"        # "kernels": tcgen05 forward + GEMM backward (bf16, CUDA) | "autograd": torch ops
         self.last_sampled_indices = None  # (B,T) int32 of the last categorical incremental_forward
         self._packs = {}
         self._ws = packing.WorkspaceCache()
@@ -161,6 +162,11 @@ class WaveNet(nn.Module):
                 print(f"c {c.size() } x {x.size()}")
                 raise Exception
         if autograd:
+            if self.precision == "bf16" and x.is_cuda and self.train_impl == "kernels":
+                # tcgen05 forward that keeps its activations + hand-derived backward on them (training.py)
+                from .. import training
+                out = training.stack_forward_train(self, x, c, gvec)
+                return F.softmax(out, dim=1) if softmax else out
             return self._forward_autograd(x, c, gvec, softmax)
         with torch.no_grad():
             out = self.stack_forward(x, c, gvec, last_stage=last_stage)
