@@ -377,17 +377,9 @@ def main():
         tmf = torch.tensor(rs.normal(size=(Bt, 39, Tt // 160)), dtype=torch.float32, device=dev)
         tg = torch.tensor(rs.randint(0, 153, size=(Bt, 1)), dtype=torch.long, device=dev)
         nt = 5
-        # eager launches (about 3000 small kernels per step: host-bound) ...
-        for _ in range(3):
-            TS.train_step(tm, opt, ti, tmf, tg, world=world)
-        barrier()
-        e0.record()
-        for _ in range(nt):
-            TS.train_step(tm, opt, ti, tmf, tg, world=world)
-        e1.record()
-        barrier()
-        extras["train_eager_ms_per_step"] = max_over_ranks(e0.elapsed_time(e1)) / nt
-        # ... and the same step (all-reduce included) captured into one CUDA graph
+        # the whole step (all-reduce included) captured into one CUDA graph -- captured BEFORE any eager training step of this
+        # model: autograd binds the parameters' gradient accumulators to the stream of their first use, and the legacy
+        # default stream cannot take part in a capture
         gstep = TS.GraphedTrainStep(tm, opt, ti, tmf, tg, world=world)
         for _ in range(2):
             gstep(ti, tmf, tg)
@@ -401,6 +393,16 @@ def main():
         extras["train_samples_per_s"] = world * Bt * Tt / (t_ms * 1e-3)
         extras["train_ms_per_step"] = t_ms
         extras["train_loss_after_steps"] = float(tloss)
+        # eager launches of the same step (about 3000 small kernels: host-bound)
+        for _ in range(2):
+            TS.train_step(tm, opt, ti, tmf, tg, world=world)
+        barrier()
+        e0.record()
+        for _ in range(nt):
+            TS.train_step(tm, opt, ti, tmf, tg, world=world)
+        e1.record()
+        barrier()
+        extras["train_eager_ms_per_step"] = max_over_ranks(e0.elapsed_time(e1)) / nt
         if world > 1:            # all-reduce alone, same flat buffer size (7.6 M fp32 gradients), device-timed
             import torch.distributed as _d
             flat = torch.zeros(sum(p.numel() for p in tm.parameters()), device=dev)

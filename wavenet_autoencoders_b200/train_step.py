@@ -49,7 +49,8 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # thread_local: other threads of the process (the NCCL watchdog, a profiler) may touch the legacy stream meanwhile
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = train_step(model, opt, self.idx, self.mfcc, self.g, clip, world)
 
     def __call__(self, idx, mfcc, g):
