@@ -189,6 +189,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version banner would otherwise share stdout with the JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     from wavenet_autoencoders_b200 import _lib
