@@ -156,6 +156,22 @@ int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const flo
                               void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same forward from CLASS INDICES x_idx (B, T) int64 instead of the (B, O, T) fp32 one-hot tensor the reference's
+ * collate builds (vqwae_train.py:509-520; 262 MB at BASELINE config 2): the first conv is a row gather.  up_scale = 0:
+ * c is the (B, C, T) conditioning; up_scale > 0: c holds the (B, C, Tc) frames before the last upsampler stage, as in
+ * wae_stack_forward_bf16_up.
+ */
+int wae_stack_forward_bf16_idx(const wae_stack_bf16* w, const int64_t* x_idx, const float* c, int Tc, int up_scale,
+                               const float* up_filter, const float* gemb, int B, int T, float* logits, void* workspace,
+                               size_t workspace_bytes, void* stream);
+/*
+ * Teacher-forced negative log-likelihood summed over b and t < T - shift, straight from the logits:
+ * *out_sum += sum logsumexp_o(logits[b][:][t]) - logits[b][target[b][t+shift]][t]   (vqwae_train.py:760-766, mask of ones).
+ * One pass over the logits; the caller zeroes out_sum and divides by B * (T - shift).
+ */
+int wae_nll_sum(const float* logits, const int64_t* target, int B, int O, int T, int shift, double* out_sum, void* stream);
+
+/*
  * Training forward: the same kernels, but every layer input, the gated activations and the channels-last conditioning are
  * written to caller-owned buffers (all bf16) that the backward pass reads (modules.py:115-163 under autograd).  The
  * version-2 layer kernel is used regardless of wae_set_layer_cluster.

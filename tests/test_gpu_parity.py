@@ -119,6 +119,25 @@ def test_forward_bf16_gate_padding_and_two_pass(G):
     assert rel_err(y.cpu().numpy(), ref) < TOL_BF16, G
 
 
+def test_forward_bf16_from_class_indices_and_fused_nll():
+    """Additive fast paths: (B,T) integer classes instead of the one-hot tensor (identical logits: the same row gather), and
+    the one-pass teacher-forced NLL against torch's cross_entropy on the shifted slices (vqwae_train.py:760-766)."""
+    from wavenet_autoencoders_b200.losses import teacher_forced_nll
+    g, cfg, m, x, c, spk = _inputs("wavenet_tiny")
+    m.precision = "bf16"
+    idx = x.argmax(1)
+    with torch.no_grad():
+        y_onehot = m(x, c, spk)
+        y_idx = m(idx, c, spk)
+    assert torch.equal(y_onehot, y_idx)
+    ref = torch.nn.functional.cross_entropy(y_idx[:, :, :-1], idx[:, 1:])
+    got = teacher_forced_nll(y_idx, idx)
+    assert abs(float(got) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    m.precision = "fp32"                       # no index kernel there: expanded to one-hot on the host side
+    with torch.no_grad():
+        assert torch.equal(m(idx, c, spk), m(x, c, spk))
+
+
 def test_forward_ragged_tail_and_dense_input_fp32_bf16():
     """T not a multiple of any tile size; dense (non one-hot) x exercises the first-conv GEMV path."""
     cfg = dict(T.CONFIGS["tiny"], upsample_conditional_features=False)

@@ -314,6 +314,31 @@ first_conv_bf16_kernel(const float* __restrict__ x, const float* __restrict__ wf
     }
 }
 
+// first_conv on class indices (the mu-law input as the data pipeline holds it, before any one-hot expansion):
+// x0[b][t][:] = wf[idx[b][t]][:] + bf.  Out-of-range classes give the bias alone (an all-zero one-hot column).
+__global__ void __launch_bounds__(256)
+first_conv_idx_kernel(const long long* __restrict__ idx, const float* __restrict__ wf, const float* __restrict__ bf, long long rows,
+                      int Oin, int R, __nv_bfloat16* __restrict__ x0) {
+    const int r8n = R >> 3;
+    const long long total = rows * r8n;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / r8n;
+        const int r = (int)(e - row * r8n) * 8;
+        const long long h = __ldg(&idx[row]);
+        float4 a0 = __ldg(reinterpret_cast<const float4*>(bf + r)), a1 = __ldg(reinterpret_cast<const float4*>(bf + r + 4));
+        if (h >= 0 && h < Oin) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(wf + (size_t)h * R + r));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(wf + (size_t)h * R + r + 4));
+            a0.x += w0.x; a0.y += w0.y; a0.z += w0.z; a0.w += w0.w;
+            a1.x += w1.x; a1.y += w1.y; a1.z += w1.z; a1.w += w1.w;
+        }
+        uint4 o4;
+        o4.x = pack_bf16x2(a0.x, a0.y); o4.y = pack_bf16x2(a0.z, a0.w);
+        o4.z = pack_bf16x2(a1.x, a1.y); o4.w = pack_bf16x2(a1.z, a1.w);
+        *reinterpret_cast<uint4*>(x0 + row * R + r) = o4;
+    }
+}
+
 // (B,C,T) fp32 -> [B][T][Cp] bf16, zero padded channels
 __global__ void __launch_bounds__(256)
 cond_to_cl_kernel(const float* __restrict__ c, int T, int C, int Cp, __nv_bfloat16* __restrict__ out) {
@@ -1497,11 +1522,11 @@ size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T) {
     return carve(*d, B, T, nullptr).total;
 }
 
-static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, const float* c, int up_s, const float* up_w,
+static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, const int64_t* x_idx, const float* c, int up_s, const float* up_w,
                                    const float* gemb, int B, int T, float* logits, const wae_stack_saved* save,
                                    void* workspace, size_t workspace_bytes, void* stream_) {
     if (int rc = wae::require_sm100()) return rc;
-    WAE_REQUIRE(w && x && logits && workspace, "wae_stack_forward_bf16: null pointer");
+    WAE_REQUIRE(w && (x || x_idx) && logits && workspace, "wae_stack_forward_bf16: null pointer");
     const wae_stack_dims& d = w->d;
     const int H = d.G / 2;
     WAE_REQUIRE(B > 0 && T > 0 && B <= 65535, "wae_stack_forward_bf16: B=%d T=%d", B, T);
@@ -1544,7 +1569,14 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     ProfScope prof(0, stream);
     gbias_bf16_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, gemb, d.layers, B, d.G, d.Gi, Hh, ws.gb);
     WAE_CHECK_LAUNCH();
-    {
+    if (x_idx != nullptr) {
+        const long long rows = (long long)B * T;
+        long long blocks = (rows * (d.R / 8) + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        first_conv_idx_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const long long*>(x_idx), w->wf, w->bf, rows, d.Oin,
+                                                                    d.R, ws.xa);
+        WAE_CHECK_LAUNCH();
+    } else {
         const int vec_ok = (T % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
         first_conv_bf16_kernel<<<dim3((T + FC_T - 1) / FC_T, B), 256, 0, stream>>>(x, w->wf, w->bf, T, d.Oin, d.R, vec_ok, ws.xa);
         WAE_CHECK_LAUNCH();
@@ -1669,14 +1701,14 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
 
 int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,
                            int T, float* logits, void* workspace, size_t workspace_bytes, void* stream) {
-    return stack_forward_bf16_impl(w, x, c, 0, nullptr, gemb, B, T, logits, nullptr, workspace, workspace_bytes, stream);
+    return stack_forward_bf16_impl(w, x, nullptr, c, 0, nullptr, gemb, B, T, logits, nullptr, workspace, workspace_bytes, stream);
 }
 
 int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,
                                 int T, float* logits, const wae_stack_saved* save, void* workspace, size_t workspace_bytes,
                                 void* stream) {
     WAE_REQUIRE(save != nullptr, "wae_stack_forward_bf16_save: null save descriptor");
-    return stack_forward_bf16_impl(w, x, c, 0, nullptr, gemb, B, T, logits, save, workspace, workspace_bytes, stream);
+    return stack_forward_bf16_impl(w, x, nullptr, c, 0, nullptr, gemb, B, T, logits, save, workspace, workspace_bytes, stream);
 }
 
 int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const float* c_frames, int Tc, int up_scale,
@@ -1686,7 +1718,20 @@ int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const flo
     WAE_REQUIRE(w->d.C > 0, "wae_stack_forward_bf16_up: the stack has no local conditioning (C = 0)");
     WAE_REQUIRE(up_scale >= 1 && Tc >= 1 && (long long)Tc * up_scale == T,
                 "wae_stack_forward_bf16_up: %d frames x scale %d != T = %d", Tc, up_scale, T);
-    return stack_forward_bf16_impl(w, x, c_frames, up_scale, up_filter, gemb, B, T, logits, nullptr, workspace, workspace_bytes, stream);
+    return stack_forward_bf16_impl(w, x, nullptr, c_frames, up_scale, up_filter, gemb, B, T, logits, nullptr, workspace, workspace_bytes, stream);
+}
+
+int wae_stack_forward_bf16_idx(const wae_stack_bf16* w, const int64_t* x_idx, const float* c, int Tc, int up_scale,
+                               const float* up_filter, const float* gemb, int B, int T, float* logits, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+    WAE_REQUIRE(w && x_idx, "wae_stack_forward_bf16_idx: null pointer");
+    WAE_REQUIRE(w->d.Oin > 1, "wae_stack_forward_bf16_idx: class indices need a one-hot-input model (Oin > 1)");
+    if (up_scale > 0) {
+        WAE_REQUIRE(c && up_filter && w->d.C > 0 && Tc >= 1 && (long long)Tc * up_scale == T,
+                    "wae_stack_forward_bf16_idx: %d frames x scale %d != T = %d", Tc, up_scale, T);
+    }
+    return stack_forward_bf16_impl(w, nullptr, x_idx, c, up_scale > 0 ? up_scale : 0, up_scale > 0 ? up_filter : nullptr, gemb, B, T,
+                                   logits, nullptr, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

@@ -143,6 +143,35 @@ dx_accum_kernel(const __nv_bfloat16* __restrict__ dxcat, const __nv_bfloat16* __
     }
 }
 
+// Teacher-forced negative log-likelihood straight from the (B,O,T) logits: sum over b, t < T - shift of
+// logsumexp_o(logits[b][:][t]) - logits[b][target[b][t + shift]][t]   (vqwae_train.py:760-766 with an all-ones mask).
+// One thread per time step: for a fixed class the threads of a warp read consecutive t (coalesced); online max/sum.
+__global__ void __launch_bounds__(128)
+nll_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int O, int T, int shift, double* __restrict__ out) {
+    const int b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    float loss = 0.f;
+    if (t < T - shift) {
+        const float* p = logits + (size_t)b * O * T + t;
+        float m = -INFINITY, s = 0.f;
+#pragma unroll 4
+        for (int o = 0; o < O; ++o) {
+            const float v = __ldg(p + (size_t)o * T);
+            const float mn = fmaxf(m, v);
+            s = s * __expf(m - mn) + __expf(v - mn);
+            m = mn;
+        }
+        const long long y = __ldg(&target[(size_t)b * T + t + shift]);
+        const float ly = (y >= 0 && y < O) ? __ldg(p + (size_t)y * T) : 0.f;
+        loss = m + __logf(s) - ly;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) loss += __shfl_xor_sync(0xffffffffu, loss, off);
+    __shared__ float part[4];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = loss;
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(out, (double)(part[0] + part[1] + part[2] + part[3]));
+}
+
 inline unsigned grid_for(long long items) {
     long long b = (items + 255) / 256;
     if (b > 148 * 32) b = 148 * 32;
@@ -187,6 +216,16 @@ int wae_train_dx_accum(const void* dxcat, const void* dxo, int B, int T, int R, 
     dx_accum_kernel<<<grid_for(rows * (R / 8 + (C + 7) / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __nv_bfloat16*>(dxcat), static_cast<const __nv_bfloat16*>(dxo), T, R, C, Cp, kw, dil, scale,
         static_cast<__nv_bfloat16*>(dx), dC, rows);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+int wae_nll_sum(const float* logits, const int64_t* target, int B, int O, int T, int shift, double* out_sum, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(logits && target && out_sum, "wae_nll_sum: null pointer");
+    WAE_REQUIRE(B > 0 && B <= 65535 && O > 0 && T > 0 && shift >= 0 && shift < T, "wae_nll_sum: bad sizes");
+    nll_kernel<<<dim3((T + 127) / 128, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        logits, reinterpret_cast<const long long*>(target), O, T, shift, out_sum);
     WAE_CHECK_LAUNCH();
     return WAE_OK;
 }

@@ -143,10 +143,18 @@ class WaveNet(nn.Module):
 
     # ------------------------------------------------------------------ teacher-forced forward
     def forward(self, x, c=None, g=None, softmax=False):
-        """x (B,O,T) one-hot / (B,1,T) scalar; c (B,C,Tc); g ids or (B,Gi[,1])  ->  (B,O,T) (wavenet.py:164-216)."""
-        B, _, T = x.size()
-        gvec = self._speaker_vectors(g, B)
+        """x (B,O,T) one-hot / (B,1,T) scalar; c (B,C,Tc); g ids or (B,Gi[,1])  ->  (B,O,T) (wavenet.py:164-216).
+        Additive: x may also be the (B,T) integer mu-law classes themselves (what the one-hot tensor is built from); the
+        bf16 inference path then gathers first-conv rows by index and never materialises the (B,O,T) one-hot."""
         autograd = self.training and torch.is_grad_enabled()
+        x_idx = None
+        if not torch.is_floating_point(x) and x.dim() == 2 and not self.scalar_input:
+            if autograd or self.precision != "bf16" or not x.is_cuda:
+                x = F.one_hot(x.long(), self.out_channels).float().transpose(1, 2)
+            else:
+                x_idx = x.long().contiguous()
+        B, T = x.size(0), x.size(-1)
+        gvec = self._speaker_vectors(g, B)
         last_stage = None
         if c is not None and self.upsample_net is not None:
             if not autograd and self.precision == "bf16" and x.is_cuda and isinstance(self.upsample_net, (upsample.UpsampleNetwork, upsample.ConvInUpsampleNetwork)):
@@ -169,18 +177,19 @@ class WaveNet(nn.Module):
                 return F.softmax(out, dim=1) if softmax else out
             return self._forward_autograd(x, c, gvec, softmax)
         with torch.no_grad():
-            out = self.stack_forward(x, c, gvec, last_stage=last_stage)
+            out = self.stack_forward(x, c, gvec, last_stage=last_stage, x_is_index=x_idx is not None)
         return F.softmax(out, dim=1) if softmax else out
 
-    def stack_forward(self, x, c_up, gvec, precision=None, last_stage=None):
+    def stack_forward(self, x, c_up, gvec, precision=None, last_stage=None, x_is_index=False):
         """The hot path proper: first_conv + residual stack + head on already-upsampled conditioning (or, with
-        ``last_stage=(filter, scale)``, on the frames entering the last upsampler stage; bf16 only)."""
+        ``last_stage=(filter, scale)``, on the frames entering the last upsampler stage; bf16 only).  ``x_is_index``: x is
+        the (B,T) int64 class tensor (bf16 only)."""
         self._require_cuda(x, "WaveNet.forward")
         precision = precision or self.precision
-        if last_stage is not None and precision != "bf16":
-            raise ValueError("last_stage fusion exists for precision='bf16' only")
-        B, _, T = x.shape
-        x = x.detach().float().contiguous()
+        if (last_stage is not None or x_is_index) and precision != "bf16":
+            raise ValueError("last_stage fusion / index input exist for precision='bf16' only")
+        B, T = x.shape[0], x.shape[-1]
+        x = x.detach().contiguous() if x_is_index else x.detach().float().contiguous()
         c_up = None if c_up is None else c_up.detach().float().contiguous()
         gvec = None if gvec is None else gvec.detach().float().contiguous()
         logits = torch.empty(B, self.out_channels, T, dtype=torch.float32, device=x.device)
@@ -196,7 +205,13 @@ class WaveNet(nn.Module):
             pk = self._pack("bf16")
             n = L.wae_stack_workspace_bf16(pk.struct.d, B, T)
             ws = self._ws.get(n, x.device)
-            if last_stage is not None:
+            if x_is_index:
+                up_w, up_s = last_stage if last_stage is not None else (None, 0)
+                up_w = None if up_w is None else up_w.detach().float().contiguous()
+                _lib.check(L.wae_stack_forward_bf16_idx(pk.struct, _lib.ptr(x), _lib.ptr(c_up), 0 if c_up is None else c_up.shape[-1],
+                                                        int(up_s), _lib.ptr(up_w), _lib.ptr(gvec), B, T, _lib.ptr(logits),
+                                                        _lib.ptr(ws), ws.numel(), st), "wae_stack_forward_bf16_idx")
+            elif last_stage is not None:
                 up_w, up_s = last_stage
                 up_w = up_w.detach().float().contiguous()
                 _lib.check(L.wae_stack_forward_bf16_up(pk.struct, _lib.ptr(x), _lib.ptr(c_up), c_up.shape[-1], int(up_s),
