@@ -200,9 +200,9 @@ int wae_train_dx_accum(const void* dxcat, const void* dxo, int B, int T, int R, 
                        void* dx, float* dC, void* stream);
 
 /* Variant of the bf16 residual-layer kernel: -1 (default) = version-2 kernel (residual added by an identity MMA, x' and h
- * stored by TMA from shared memory); 0 = CTA-pair kernel (tcgen05 cta_group::2, M = 256 per MMA, each CTA
- * holds half of every weight k-block); 1, 2 or 4 = the 1-CTA kernel in clusters of that size, the CTAs of a cluster sharing
- * every weight k-block through TMA multicast. */
+ * stored by TMA from shared memory); -2 = version 2 on CTA pairs (tcgen05 cta_group::2: each CTA stages half of every weight
+ * k-block); 0 = first CTA-pair kernel; 1, 2 or 4 = the first 1-CTA kernel in clusters of that size, the CTAs of a cluster
+ * sharing every weight k-block through TMA multicast.  Gate widths above 256 and the training forward always use -1. */
 int wae_set_layer_cluster(int cs);
 /* Debug: per-CTA cycle counters of the 1-CTA residual-layer kernel's three roles (16 int64 per CTA), or NULL to disable. */
 void wae_layer_set_profile_buffer(int64_t* dev_buf);

@@ -10,7 +10,7 @@ idx, mfcc, g = bench.synth_batch(16, 1000)
 idx, mfcc, g = idx.cuda(), mfcc.cuda(), g.cuda()
 x = torch.nn.functional.one_hot(idx, 256).float().transpose(1, 2).contiguous()
 ref = None
-for cs in (1, -1, 0):   # -1 = version-2 kernel (default); 0 = CTA-pair kernel (cta_group::2); 1 = first 1-CTA kernel
+for cs in (-1, -2, 0):   # -1 = version-2 kernel; -2 = version 2 on CTA pairs; 0 = first CTA-pair kernel; 1 = first 1-CTA kernel
     _lib.check(L.wae_set_layer_cluster(cs), "set cluster")
     with torch.no_grad():
         for _ in range(3):

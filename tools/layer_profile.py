@@ -9,7 +9,7 @@ m = bench.build_vqvae("cuda"); m.wavenet.precision = "bf16"
 idx, mfcc, g = bench.synth_batch(16, 1000)
 idx, mfcc, g = idx.cuda(), mfcc.cuda(), g.cuda()
 x = torch.nn.functional.one_hot(idx, 256).float().transpose(1, 2).contiguous()
-_lib.check(L.wae_set_layer_cluster(1), "mode")
+_lib.check(L.wae_set_layer_cluster(int(sys.argv[1]) if len(sys.argv) > 1 else -1), "mode")
 with torch.no_grad():
     for _ in range(2):
         m(x, mfcc, g)

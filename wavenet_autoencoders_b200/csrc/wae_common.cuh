@@ -122,6 +122,12 @@ __device__ __forceinline__ void tc_fence_after() {
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
 }
+// L2 prefetch of a tensor box (no shared memory, no barrier): hides the HBM latency of a tile that is loaded later
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* desc, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(desc)), "r"(c0),
+                 "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(const void* desc, uint64_t* bar, void* smem_dst,
                                             int32_t c0, int32_t c1, int32_t c2) {
     asm volatile(

@@ -765,10 +765,15 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_kernel(const __gr
 // Shared memory: 3 stages x 48 KB, the h / x' staging tiles (x' reuses the h tiles once GEMM2 is done), the identity tile.
 constexpr int V2_STAGES = 3;
 
-template <int kDummy>
+// kPair: the CTA-pair variant (layer_bf16_pair2_kernel) -- CTA `crank` of cluster `unit0` handles tile 2*u + crank of every
+// super-tile u, and the "done" arrivals go to the LEADER's barriers (the MMA issuer lives there).
+template <bool kPair>
 __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles, uint32_t tmem_acc1, uint32_t tmem_acc2, uint8_t* hx,
                                                   float* sb_bo, uint64_t* acc1_full, uint64_t* acc2_full, uint64_t* epi1_done,
-                                                  uint64_t* epi2_done, uint64_t* epi1a_done) {
+                                                  uint64_t* epi2_done, uint64_t* epi1a_done, int crank, int unit0, int nunits,
+                                                  int unit_stride) {
+    const uint32_t epi1_remote = kPair ? mapa(smem_u32(epi1_done), 0) : 0u;
+    const uint32_t epi2_remote = kPair ? mapa(smem_u32(epi2_done), 0) : 0u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Hh = a.G / 2;
     uint32_t n_acc1 = 0;                              // completions of acc1_full seen so far (1 or 2 per tile)
@@ -781,9 +786,12 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
     for (int i = threadIdx.x - 64; i < a.R; i += 32 * LAYER_EPI_WARPS) sb_bo[i] = __ldg(a.bo + i);
     asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
     int it = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0; const long long e_t0 = clock64(); LPROF_BEGIN();
+    for (int unit = unit0; unit < nunits; unit += unit_stride, ++it) {
+        const int tile = kPair ? unit * 2 + crank : unit;
+        const bool valid = tile < ntiles;                      // a pair's odd tail: computed on zero-filled input, never stored
         const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
-        const float* gbp = a.gb + (size_t)b * a.G;
+        const float* gbp = a.gb + (size_t)(valid ? b : 0) * a.G;
 
         // ---- EPI1: gate.  Pass A gives h channels [0, Ha) from accumulator columns [0, Ha) (tanh) and [Ha, 2 Ha) (sigmoid);
         // with more than 256 gate rows a second pass over the same columns gives channels [Ha, Ha + Hb) ----
@@ -817,7 +825,9 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
                 st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
             }
         };
+        LPROF(e_e2);
         mbar_wait(acc1_full, n_acc1 & 1);
+        LPROF(e_w1);
         ++n_acc1;
         tc_fence_after();
         if (it > 0) {   // the TMA stores of the previous tile (h and x') must have finished READING the staging tiles
@@ -829,7 +839,8 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
         } else {
             gate_chunks(0, a.Ha, 0, a.Ha);
             tc_fence_before();
-            mbar_arrive(epi1a_done);               // the accumulator columns are free for pass B
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+            if (threadIdx.x == 64) mbar_arrive(epi1a_done);   // the accumulator columns are free for pass B
             mbar_wait(acc1_full, n_acc1 & 1);
             ++n_acc1;
             tc_fence_after();
@@ -839,14 +850,19 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
         if (threadIdx.x == 64) {
-            for (int kb = 0; kb < a.Hp / BK; ++kb) tma_store_3d(&a.tm_hst, hx + kb * A_TILE_BYTES, kb * BK, t0, a.layer * a.B + b);
+            if (valid)
+                for (int kb = 0; kb < a.Hp / BK; ++kb) tma_store_3d(&a.tm_hst, hx + kb * A_TILE_BYTES, kb * BK, t0, a.layer * a.B + b);
             tma_store_commit();
+            // ONE arrival per CTA (all epilogue threads fenced and met at the bar.sync above): 512 arrivals per phase -- 512
+            // remote ones in the pair kernel -- cost more than the barrier they replace
+            if (kPair) mbar_arrive_cluster(epi1_remote); else mbar_arrive(epi1_done);
         }
-        mbar_arrive(epi1_done);
 
         // ---- EPI2: x' = (acc2 + bo) * sqrt(.5)   (acc2 already holds Wo*h + x) ----
         if (has_out) {
+            LPROF(e_e1);
             mbar_wait(acc2_full, it & 1);
+            LPROF(e_w2);
             tc_fence_after();
             // GEMM2 has finished reading the h tiles; the h TMA store must have finished reading them too before x' overwrites them
             if (threadIdx.x == 64) tma_store_wait_read();
@@ -873,15 +889,20 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
             }
             tc_fence_before();
             fence_proxy_async_smem();
-            mbar_arrive(epi2_done);     // acc2 is drained: the MMA warp may start the next tile's residual MMAs
             asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
             if (threadIdx.x == 64) {
-                for (int kb = 0; kb < a.R / BK; ++kb) tma_store_3d(&a.tm_xout, hx + kb * A_TILE_BYTES, kb * BK, t0, b);
+                if (kPair) mbar_arrive_cluster(epi2_remote); else mbar_arrive(epi2_done);   // acc2 is drained: the next tile's residual MMAs may start
+                if (valid)
+                    for (int kb = 0; kb < a.R / BK; ++kb) tma_store_3d(&a.tm_xout, hx + kb * A_TILE_BYTES, kb * BK, t0, b);
                 tma_store_commit();
             }
         }
     }
     if (threadIdx.x == 64) tma_store_wait_all();
+    if (LPROF_ON && a.prof && threadIdx.x == 64) {
+        long long* pp = a.prof + blockIdx.x * 16;
+        pp[8] = e_w1; pp[9] = e_e1; pp[10] = e_w2; pp[11] = e_e2; pp[12] = 0; pp[13] = clock64() - e_t0;
+    }
 }
 
 __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const __grid_constant__ LayerArgs a) {
@@ -907,10 +928,10 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
     if (threadIdx.x == 0) {
         for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         mbar_init(acc1_full, 1);
-        mbar_init(epi1_done, 32 * LAYER_EPI_WARPS);
+        mbar_init(epi1_done, 1);             // one elected epilogue thread arrives, after the epilogue warps' bar.sync
         mbar_init(acc2_full, 1);
-        mbar_init(epi2_done, 32 * LAYER_EPI_WARPS);
-        mbar_init(epi1a_done, 32 * LAYER_EPI_WARPS);
+        mbar_init(epi2_done, 1);
+        mbar_init(epi1a_done, 1);
         fence_mbar_init();
         tma_prefetch_desc(&a.tm_x);
         tma_prefetch_desc(&a.tm_c);
@@ -995,17 +1016,22 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
             const uint32_t idesc_id = umma_idesc_bf16(BM, 64);
             const uint64_t id_desc = umma_desc_sw128(smem_u32(ident));
             int it = 0;
+            long long m_full = 0, m_e1 = 0, m_e2 = 0, m_iss = 0; const long long m_t0 = clock64(); LPROF_BEGIN();
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
                 if (!has_out && it > 0) { mbar_wait(epi1_done, (it - 1) & 1); tc_fence_after(); }
                 for (int kb = 0; kb < nk1; ++kb) {
+                    LPROF(m_iss);
                     mbar_wait(&full[ring.stage], ring.phase);
+                    LPROF(m_full);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
                     issue_kblock(tmem_acc1, sa, sa + A_TILE_BYTES, idesc1, kb == 0);
                     if (has_out && kb >= nk_old + nk_c) {
                         // residual: acc2[:, 64j .. 64j+63] = x tile (A) x I^T  -- needs acc2 drained by the previous tile's EPI2
                         const int j = kb - nk_old - nk_c;
+                        LPROF(m_iss);
                         if (j == 0 && it > 0) { mbar_wait(epi2_done, (it - 1) & 1); tc_fence_after(); }
+                        LPROF(m_e2);
                         const uint64_t ad = umma_desc_sw128(sa);
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
@@ -1030,10 +1056,14 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
                     umma_commit(acc1_full);
                 }
                 if (has_out) {
+                    LPROF(m_iss);
                     mbar_wait(epi1_done, it & 1);  // h is in shared memory, acc1 drained
+                    LPROF(m_e1);
                     tc_fence_after();
                     for (int kb = 0; kb < nkh; ++kb) {
+                        LPROF(m_iss);
                         mbar_wait(&full[ring.stage], ring.phase);
+                        LPROF(m_full);
                         tc_fence_after();
                         const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
                         issue_kblock(tmem_acc2, smem_u32(hx + kb * A_TILE_BYTES), sb, idesc2, false);   // accumulate on top of x
@@ -1043,10 +1073,14 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
                     umma_commit(acc2_full);
                 }
             }
+            if (LPROF_ON && a.prof) {
+                long long* pp = a.prof + blockIdx.x * 16;
+                pp[2] = m_full; pp[3] = m_e1; pp[4] = m_e2; pp[5] = m_iss; pp[6] = clock64() - m_t0; pp[7] = it;
+            }
         }
     } else {
-        layer_epilogue_v2<0>(a, ntiles, tmem_acc1, tmem_acc2, hx, reinterpret_cast<float*>(bars) + 64, acc1_full, acc2_full,
-                             epi1_done, epi2_done, epi1a_done);
+        layer_epilogue_v2<false>(a, ntiles, tmem_acc1, tmem_acc2, hx, reinterpret_cast<float*>(bars) + 64, acc1_full, acc2_full,
+                                 epi1_done, epi2_done, epi1a_done, 0, (int)blockIdx.x, ntiles, (int)gridDim.x);
     }
     tc_fence_before();
     __syncthreads();
@@ -1197,6 +1231,198 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_pair_kernel(const
         // ================= epilogue warps (both CTAs, own 128 TMEM lanes) =================
         layer_epilogue<true>(a, 2, crank, cluster_id, ncluster, nsuper, ntiles, tmem_acc1, tmem_acc2, hbuf,
                              reinterpret_cast<float*>(bars) + 64, acc1_full, acc2_full, epi1_done, epi2_done);
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 1) tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// version 2 on CTA pairs: the L2 -> shared-memory stream is what bounds version 2
+// ---------------------------------------------------------------------------------------------
+// What bounds version 2 is SHARED-MEMORY bandwidth (128 B/cycle/SM): per 64-deep k-block TMA writes 48 KB (A 16 + W 32) and
+// the tensor core reads the same 48 KB back, 96 KB per 512 cycles of MMA math = 750 cycles at 128 B/cycle; with GEMM2, the
+// identity MMAs and the epilogues' staging a 128-sample tile moves ~1.76 MB through shared memory = 13.8k cycles, and the
+// kernel runs at 17.5k (role counters: MMA warp 7.0k issuing, 5.9k waiting for operands, 4.4k waiting for the gate epilogue).
+// It also sits at 86 % of the L2 -> SM delivery rate (ncu: 1.41 GB of TMA loads per launch, 5.4 KB/cycle chip-wide; an L2
+// prefetch of the next tile's activations changed nothing, so it is not HBM latency).
+// tcgen05 cta_group::2 attacks both: a pair of CTAs computes 256 samples per MMA and each CTA stages only HALF of every weight
+// k-block (the instruction reads B from both CTAs' shared memory): 32 KB written + 48 KB read per k-block and CTA, 480 KB
+// instead of 752 KB from L2 per 128 samples.  Everything else is version 2 (residual by identity MMA -- each CTA holds 32 of
+// the identity's 64 rows --, x' and h by TMA store, k-blocks ordered old taps, conditioning, newest tap); roles and barriers
+// as in layer_bf16_pair_kernel.  Single gate pass only.  MEASURED: 154 us vs 144.5 us -- bit-identical output, but the pair's
+// epilogues run ~40 % slower (E1 6.1k vs 4.2k cycles) and the operand wait does not shrink (6.1k per 256 samples), so the
+// single-CTA kernel stays the default; selectable with wae_set_layer_cluster(-2).
+constexpr int PAIR2_STAGES = 4;
+
+__global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_pair2_kernel(const __grid_constant__ LayerArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGE_BYTES = A_TILE_BYTES + PAIR_B_BYTES;
+    const int nkh = a.Hp / BK, nkr = a.R / BK;
+    const int hx_tiles = nkh > nkr ? nkh : nkr;
+    uint8_t* hx = smem + PAIR2_STAGES * STAGE_BYTES;
+    uint8_t* ident = hx + hx_tiles * A_TILE_BYTES;               // this CTA's 32 x 64 half of the identity (4 KB)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(ident + 32 * BK * 2);
+    uint64_t* full = bars;                       // [PAIR2_STAGES]  used in the leader only
+    uint64_t* empty = bars + PAIR2_STAGES;       // [PAIR2_STAGES]  one per CTA (commit is multicast)
+    uint64_t* acc1_full = bars + 2 * PAIR2_STAGES;
+    uint64_t* epi1_done = acc1_full + 1;         // leader only, 2 arrivals
+    uint64_t* acc2_full = acc1_full + 2;
+    uint64_t* epi2_done = acc1_full + 3;         // leader only
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int crank = (int)cluster_ctarank();    // 0 = leader
+    const bool leader = (crank == 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PAIR2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc1_full, 1);
+        mbar_init(epi1_done, 2);             // one elected epilogue thread per CTA
+        mbar_init(acc2_full, 1);
+        mbar_init(epi2_done, 2);
+        fence_mbar_init();
+        tma_prefetch_desc(&a.tm_x);
+        tma_prefetch_desc(&a.tm_c);
+        tma_prefetch_desc(&a.tm_w1);
+        tma_prefetch_desc(&a.tm_wo);
+        tma_prefetch_desc(&a.tm_hst);
+        tma_prefetch_desc(&a.tm_xout);
+    }
+    // identity half: local row nl is identity row n = 32 * crank + nl; element (nl, k) = (n == k)
+    for (int e = threadIdx.x; e < 32 * 8; e += LAYER_THREADS) {
+        const int nl = e >> 3, c16 = e & 7, n = 32 * crank + nl;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if ((n >> 3) == c16) w[(n & 7) >> 1] = (n & 1) ? 0x3F800000u : 0x00003F80u;
+        st_shared_v4(smem_u32(ident) + sw128_off(nl, c16), w[0], w[1], w[2], w[3]);
+    }
+    fence_proxy_async_smem();
+    if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_acc1 = tmem_base;        // columns [0, G)
+    const uint32_t tmem_acc2 = tmem_base + 256;  // columns [256, 256+R)
+
+    const int ntiles = a.B * a.tiles_per_utt;
+    const int nsuper = (ntiles + 1) / 2;
+    const int ncluster = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+    const int rk = a.R / BK;
+    const int nk_old = (a.kw - 1) * rk, nk_c = a.Cp / BK, nk1 = nk_old + nk_c + rk;
+    const bool has_out = (a.x_out != nullptr);
+    const int w1_rows = a.G / 2, wo_rows = a.R / 2;       // weight rows held by this CTA
+    const uint32_t w1_half = (uint32_t)w1_rows * BK * 2, wo_half = (uint32_t)wo_rows * BK * 2;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (elect_one()) {
+            Ring ring(PAIR2_STAGES);
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster) {
+                const int tile = sup * 2 + crank;
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
+                for (int kb = 0; kb < nk1; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
+                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + w1_half));
+                    int kcol;
+                    if (kb < nk_old) {
+                        const int tap = kb / rk, r0 = (kb % rk) * BK;
+                        tma_load_3d_2cta(&a.tm_x, fb, sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
+                        kcol = tap * a.R + r0;
+                    } else if (kb < nk_old + nk_c) {
+                        const int c0 = (kb - nk_old) * BK;
+                        tma_load_3d_2cta(&a.tm_c, fb, sa, c0, t0, b);
+                        kcol = a.kw * a.R + c0;
+                    } else {
+                        const int r0 = (kb - nk_old - nk_c) * BK;
+                        tma_load_3d_2cta(&a.tm_x, fb, sa, r0, t0, b);
+                        kcol = (a.kw - 1) * a.R + r0;
+                    }
+                    tma_load_3d_2cta(&a.tm_w1, fb, sa + A_TILE_BYTES, kcol, crank * w1_rows, a.layer);
+                    ring.advance();
+                }
+                if (has_out) {
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                        uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                        const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
+                        if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * wo_half);
+                        tma_load_3d_2cta(&a.tm_wo, fb, sa + A_TILE_BYTES, kb * BK, crank * wo_rows, a.layer);
+                        ring.advance();
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && elect_one()) {
+            Ring ring(PAIR2_STAGES);
+            const uint32_t idesc1 = umma_idesc_bf16(2 * BM, a.G);
+            const uint32_t idesc2 = umma_idesc_bf16(2 * BM, a.R);
+            const uint32_t idesc_id = umma_idesc_bf16(2 * BM, 64);
+            const uint64_t id_desc = umma_desc_sw128(smem_u32(ident));
+            int it = 0;
+            long long m_full = 0, m_e1 = 0, m_e2 = 0, m_iss = 0; const long long m_t0 = clock64(); LPROF_BEGIN();
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+                if (!has_out && it > 0) { mbar_wait_cluster(epi1_done, (it - 1) & 1); tc_fence_after(); }
+                for (int kb = 0; kb < nk1; ++kb) {
+                    LPROF(m_iss);
+                    mbar_wait_cluster(&full[ring.stage], ring.phase);
+                    LPROF(m_full);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_2cta(tmem_acc1, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc1, (kb == 0 && k == 0) ? 0u : 1u);
+                    if (has_out && kb >= nk_old + nk_c) {
+                        // residual: acc2[:, 64j .. 64j+63] = x tile (A, both CTAs' rows) x I^T
+                        const int j = kb - nk_old - nk_c;
+                        LPROF(m_iss);
+                        if (j == 0 && it > 0) { mbar_wait_cluster(epi2_done, (it - 1) & 1); tc_fence_after(); }
+                        LPROF(m_e2);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_2cta(tmem_acc2 + 64 * j, ad + (uint64_t)(2 * k), id_desc + (uint64_t)(2 * k), idesc_id, k == 0 ? 0u : 1u);
+                    }
+                    umma_commit_2cta(&empty[ring.stage], 3);
+                    ring.advance();
+                }
+                umma_commit_2cta(acc1_full, 3);
+                if (has_out) {
+                    LPROF(m_iss);
+                    mbar_wait_cluster(epi1_done, it & 1);  // h of BOTH CTAs is in shared memory, acc1 drained
+                    LPROF(m_e1);
+                    tc_fence_after();
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        LPROF(m_iss);
+                        mbar_wait_cluster(&full[ring.stage], ring.phase);
+                        LPROF(m_full);
+                        tc_fence_after();
+                        const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                        const uint64_t ad = umma_desc_sw128(smem_u32(hx + kb * A_TILE_BYTES)), bd = umma_desc_sw128(sb);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_2cta(tmem_acc2, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc2, 1u);   // on top of x
+                        umma_commit_2cta(&empty[ring.stage], 3);
+                        ring.advance();
+                    }
+                    umma_commit_2cta(acc2_full, 3);
+                }
+            }
+            if (LPROF_ON && a.prof) {
+                long long* pp = a.prof + blockIdx.x * 16;
+                pp[2] = m_full; pp[3] = m_e1; pp[4] = m_e2; pp[5] = m_iss; pp[6] = clock64() - m_t0; pp[7] = it;
+            }
+        }
+    } else {
+        // ================= epilogue warps (both CTAs, own 128 TMEM lanes) =================
+        layer_epilogue_v2<true>(a, ntiles, tmem_acc1, tmem_acc2, hx, reinterpret_cast<float*>(bars) + 64, acc1_full, acc2_full,
+                                epi1_done, epi2_done, nullptr, crank, cluster_id, nsuper, ncluster);
     }
     tc_fence_before();
     __syncthreads();
@@ -1487,9 +1713,10 @@ void wae_profile_enable(int on) { g_prof.on = (on != 0); }
 void wae_layer_set_profile_buffer(int64_t* dev_buf) { g_layer_prof = reinterpret_cast<long long*>(dev_buf); }
 
 int wae_set_layer_cluster(int cs) {
-    if (cs == -1) { g_layer_mode = 2; return WAE_OK; }    // version-2 kernel (default)
+    if (cs == -1) { g_layer_mode = 2; return WAE_OK; }    // version-2 kernel, one CTA per tile
+    if (cs == -2) { g_layer_mode = 3; return WAE_OK; }    // version-2 kernel on CTA pairs
     if (cs == 0) { g_layer_mode = 0; return WAE_OK; }     // CTA-pair kernel
-    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be -1, 0, 1, 2 or 4");
+    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be -2, -1, 0, 1, 2 or 4");
     g_layer_mode = 1;
     g_layer_cluster = cs;
     return WAE_OK;
@@ -1596,7 +1823,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
 
     // ---- layers ----
     const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 256 + 1024;
-    if (g_layer_mode != 2 && Hb == 0 && save == nullptr) {
+    if (g_layer_mode != 2 && g_layer_mode != 3 && Hb == 0 && save == nullptr) {
         WAE_REQUIRE(smem_layer <= 232448, "wae_stack_forward_bf16: layer kernel shared memory %zu too large", smem_layer);
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
     }
@@ -1611,11 +1838,15 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         la.tm_c = tm_xa;  // never used (nk_c == 0)
     }
     // Layer-kernel variant: CTA pairs (cta_group::2, default) or the 1-CTA kernel in clusters of 1/2/4 with weight multicast.
-    const bool v2 = (g_layer_mode == 2) || Hb > 0 || save != nullptr;           // only the version-2 kernel has the second gate pass
-    const bool pair = !v2 && (g_layer_mode == 0) && Gp % 32 == 0 && d.R % 32 == 0;
+    // version 2 on CTA pairs: single gate pass, weight halves must stay multiples of 16 rows
+    const bool pair2 = (g_layer_mode == 3) && Hb == 0 && Gp % 32 == 0 && d.R % 32 == 0;
+    const bool v2 = !pair2 && ((g_layer_mode == 2) || (g_layer_mode == 3) || Hb > 0 || save != nullptr);   // only the 1-CTA version 2 has the second gate pass
+    const bool pair = pair2 || (!v2 && (g_layer_mode == 0) && Gp % 32 == 0 && d.R % 32 == 0);
     int cs = pair ? 2 : (v2 ? 1 : g_layer_cluster);
     while (!pair && cs > 1 && (Gp % (8 * cs) != 0 || d.R % (8 * cs) != 0)) cs >>= 1;
     if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, Gp, d.layers, K1p, (uint64_t)Gp * K1p, BK, v2 ? 2 * Ha : Gp / cs)) return rc;
+    // pair kernels: CTA r stages weight rows [r * N/2, (r+1) * N/2) (the MMA's B operand is split over the pair's shared
+    // memories); both CTAs' accumulators still hold all N columns for their own 128 rows
     if (Hb > 0) {
         if (int rc = make_tmap(&la.tm_w1b, w->w1, K1p, Gp, d.layers, K1p, (uint64_t)Gp * K1p, BK, 2 * Hb)) return rc;
     } else {
@@ -1627,9 +1858,14 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     if (cs == 4) nclusters = 33;   // 132 SMs: 4-CTA clusters cannot use all 148 (GPC granularity); more would queue a 2nd wave
     if (nclusters > nsuper) nclusters = nsuper;
     const int grid_layer = nclusters * cs;
-    if (pair)
+    if (pair && !pair2)
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
     const int hx_tiles = (Hp / BK) > (d.R / BK) ? (Hp / BK) : (d.R / BK);
+    const size_t smem_pair2 = 1024 + (size_t)PAIR2_STAGES * (A_TILE_BYTES + PAIR_B_BYTES) + (size_t)hx_tiles * A_TILE_BYTES + 32 * BK * 2 + 256 + 1024;
+    if (pair2) {
+        WAE_REQUIRE(smem_pair2 <= 232448, "wae_stack_forward_bf16: layer kernel (pair v2) shared memory %zu too large", smem_pair2);
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_pair2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pair2));
+    }
     const size_t smem_v2 = 1024 + (size_t)V2_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)hx_tiles * A_TILE_BYTES + 64 * BK * 2 + 256 + 1024;
     if (v2) {
         WAE_REQUIRE(smem_v2 <= 232448, "wae_stack_forward_bf16: layer kernel (v2) shared memory %zu too large", smem_v2);
@@ -1662,7 +1898,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)grid_layer);
             cfg.blockDim = dim3(LAYER_THREADS);
-            cfg.dynamicSmemBytes = v2 ? smem_v2 : smem_layer;
+            cfg.dynamicSmemBytes = pair2 ? smem_pair2 : (v2 ? smem_v2 : smem_layer);
             cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1671,7 +1907,8 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            if (v2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v2_kernel, la));
+            if (pair2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair2_kernel, la));
+            else if (v2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v2_kernel, la));
             else if (pair) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair_kernel, la));
             else WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_kernel, la));
         }
