@@ -394,3 +394,46 @@ def test_training_backward_matches_autograd(cfg_name):
         print(f"{e:.3e}  {n}")
     # bf16 forward activations + bf16 backward operands against an fp32 forward/backward: max-norm relative error per tensor
     assert max(errs.values()) < TOL_BF16_GRAD, max(errs.items(), key=lambda kv: kv[1])
+
+
+def test_training_kernels_match_torch():
+    """The gather / element-wise kernels of the backward pass (csrc/wn_train.cu) against their torch expressions."""
+    from wavenet_autoencoders_b200 import training
+    L = _lib.lib()
+    st = _lib.stream_ptr()
+    B, Tn, R, C, Cp, kw, H = 3, 200, 64, 16, 64, 3, 184        # H = 184: the IN-WAE gate half (23 chunks of 8)
+    bf = torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(B, Tn, R, device="cuda", generator=g).to(bf)
+    c = torch.nn.functional.pad(torch.randn(B, Tn, C, device="cuda", generator=g), (0, Cp - C)).to(bf)
+    for d in (1, 7, 64, 512):                                  # dilation beyond T: every tap but the newest is zero padding
+        out = torch.empty(B, Tn, kw * R + Cp, dtype=bf, device="cuda")
+        _lib.check(L.wae_train_im2col(_lib.ptr(x), _lib.ptr(c), B, Tn, R, Cp, kw, d, _lib.ptr(out), st), "im2col")
+        ref = torch.cat([training._shift(x, (kw - 1 - j) * d) for j in range(kw)] + [c], dim=-1)
+        assert torch.equal(out, ref), d
+        dxcat = torch.randn(B, Tn, kw * R + Cp, device="cuda", generator=g).to(bf)
+        dxo = torch.randn(B, Tn, R, device="cuda", generator=g).to(bf)
+        dC = torch.ones(B, Tn, C, device="cuda")
+        dx = torch.empty(B, Tn, R, dtype=bf, device="cuda")
+        _lib.check(L.wae_train_dx_accum(_lib.ptr(dxcat), _lib.ptr(dxo), B, Tn, R, C, Cp, kw, d, 0.5, _lib.ptr(dx), _lib.ptr(dC), st),
+                   "dx_accum")
+        want = dxo.float()
+        for j in range(kw):
+            want = want + training._unshift(dxcat[..., j * R:(j + 1) * R], (kw - 1 - j) * d).float()
+        assert rel_err(dx.float().cpu().numpy(), (want * 0.5).cpu().numpy()) < 1e-2
+        assert torch.allclose(dC, 1.0 + dxcat[..., kw * R: kw * R + C].float())
+    z = torch.randn(B, Tn, 2 * H, device="cuda", generator=g).to(bf)
+    gb = torch.randn(B, 2 * H, device="cuda", generator=g)
+    wide = torch.randn(B, Tn, 3 * 192, device="cuda", generator=g).to(bf)          # dh_a is a strided view, like dHskip[..., l*Hp:]
+    dh_a = wide[..., 192: 192 + H]
+    dh_b = torch.randn(B, Tn, H, device="cuda", generator=g).to(bf)
+    dz = torch.empty(B, Tn, 2 * H, dtype=bf, device="cuda")
+    dgb = torch.zeros(B, 2 * H, device="cuda")
+    _lib.check(L.wae_train_gate_bwd(_lib.ptr(z), _lib.ptr(gb), dh_a.data_ptr(), 3 * 192, _lib.ptr(dh_b), B, Tn, H, _lib.ptr(dz),
+                                    _lib.ptr(dgb), st), "gate_bwd")
+    zz = z.float() + gb[:, None, :]
+    th, sg = torch.tanh(zz[..., :H]), torch.sigmoid(zz[..., H:])
+    dh = dh_a.float() + dh_b.float()
+    want = torch.cat([dh * sg * (1 - th * th), dh * th * sg * (1 - sg)], dim=-1)
+    assert rel_err(dz.float().cpu().numpy(), want.cpu().numpy()) < 1e-2
+    assert rel_err(dgb.cpu().numpy(), want.sum(1).cpu().numpy()) < 1e-3
