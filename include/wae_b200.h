@@ -84,6 +84,16 @@ int wae_vq_ema_stats(const float* x, int B, int D, int T, int d0, int sub_d,
  */
 int wae_upsample_stage(const float* in, int rows, int Tin, int s, const float* w, float* out, void* stream);
 
+/* ---- frame-rate encoder layer ------------------------- */
+/*
+ * out (B, Cout, Tout) = [relu](conv1d(x (B, Cin, T), w, stride, padding = k/2) + bias) [+ x], fp32, Tout = (T-1)/stride + 1;
+ * w is the conv weight (Cout, Cin, k) TRANSPOSED to (Cin, k, Cout) by the host (output channels contiguous):
+ * one ConvReLURes block of vqvae_model.py:9-21 (relu = residual = 1 where stride == 1 and Cin == Cout), or, with k = 1 and
+ * relu = residual = 0, the encoder's final Linear (vqvae_model.py:47-51).  Odd k, any stride.
+ */
+int wae_conv1d_relu_res(const float* x, const float* w, const float* bias, int B, int Cin, int T, int Cout, int k, int stride,
+                        int relu, int residual, float* out, void* stream);
+
 /* ---- WaveNet decoder stack: shared description -------------------------- */
 typedef struct wae_stack_dims {
     int32_t layers;       /* L */

@@ -437,3 +437,26 @@ def test_training_kernels_match_torch():
     want = torch.cat([dh * sg * (1 - th * th), dh * th * sg * (1 - sg)], dim=-1)
     assert rel_err(dz.float().cpu().numpy(), want.cpu().numpy()) < 1e-2
     assert rel_err(dgb.cpu().numpy(), want.sum(1).cpu().numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("frames", [100, 37, 1])
+def test_encoder_kernels_match_torch_convs(frames):
+    """wae_conv1d_relu_res (one launch per ConvReLURes block + the final Linear) against the torch/cuDNN fp32 path of the same
+    module (vqvae_model.py:9-51): strides 1 and 2, kernel sizes 1/3/5, residual and non-residual blocks, ragged lengths."""
+    from wavenet_autoencoders_b200.vqvae_model import Encoder
+    torch.manual_seed(0)
+    enc = Encoder(hid=256, c_in=39, c_out=64).cuda().eval()
+    x = torch.randn(3, 39, frames, device="cuda")
+    with torch.no_grad():
+        got = enc(x)                                        # kernels (inference, CUDA)
+        assert enc._kernels_ok(x)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            ref = enc.lin(enc.net(x).permute(0, 2, 1)).permute(0, 2, 1)
+    assert got.shape == ref.shape
+    assert rel_err(got.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+    w0 = enc.net[0].conv.weight
+    with torch.no_grad():
+        w0.mul_(2.0)                                        # in-place parameter update: the transposed-weight cache must notice
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            ref2 = enc.lin(enc.net(x).permute(0, 2, 1)).permute(0, 2, 1)
+        assert rel_err(enc(x).cpu().numpy(), ref2.cpu().numpy()) < 1e-5

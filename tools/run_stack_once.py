@@ -11,5 +11,9 @@ x = torch.nn.functional.one_hot(idx, 256).float().transpose(1, 2).contiguous()
 with torch.no_grad():
     for _ in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
         y = m(x, mfcc, g)[0]
-torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()          # ncu --profile-from-start off: exactly one steady-state forward
+    y = m(x, mfcc, g)[0]
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
 print("ok", float(y.abs().mean()))

@@ -288,3 +288,126 @@ int wae_upsample_stage(const float* in, int rows, int Tin, int s, const float* w
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Frame-rate encoder layer (vqvae_model.py:12-21): out = relu(conv1d(x, w, stride, padding = k/2) + bias) [+ x], fp32.
+// The encoder runs at 1/640 of the sample rate (16 x 100 frames at BASELINE config 2): a dozen tiny convolutions for which
+// cuDNN's heuristics pick a 45-90 us implicit-GEMM kernel each (0.46 ms of the 4.3 ms forward step).  Here a layer is one
+// SGEMM  out[co][n] = sum_kidx wt[kidx][co] * im2col[kidx][n],  kidx = (ci, tap), n = (utterance, frame) flattened:
+// 64 x 64 tiles, 256 threads, 4 x 4 register tiles, the next k-chunk prefetched into registers while the current one is
+// multiplied (the im2col gather happens in that prefetch).
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int EG_M = 64, EG_N = 64, EG_K = 32;      // 32-deep k-chunks: two rows per thread in flight (the layers are latency-bound)
+
+__global__ void __launch_bounds__(256)
+enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Cin*k][Cout] */, const float* __restrict__ bias, int Cin,
+                int T, int Cout, int k, int s, int Tout, int N, int relu, int residual, float* __restrict__ out) {
+    __shared__ __align__(16) float As[2][EG_K][EG_M];
+    __shared__ __align__(16) float Bs[2][EG_K][EG_N];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int co0 = blockIdx.y * EG_M, n0 = blockIdx.x * EG_N;
+    const int K = Cin * k, pad = k / 2;
+    // this thread's 4 output columns (also the 4 im2col columns it gathers): n -> (utterance, frame)
+    int cb[4], ct[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int n = n0 + tx * 4 + j;
+        cb[j] = (n < N) ? n / Tout : -1;
+        ct[j] = (n < N) ? n - cb[j] * Tout : 0;
+    }
+    const bool a_vec = ((Cout & 3) == 0);
+    float4 ra[2];
+    float rb[2][4];
+    auto fetch = [&](int k0) {                       // global -> registers: rows `ty` and `ty + 16` of the k-chunk
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int kidx = k0 + ty + 16 * h;
+            ra[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rb[h][0] = rb[h][1] = rb[h][2] = rb[h][3] = 0.f;
+            if (kidx < K) {
+                const int co = co0 + tx * 4;
+                const float* wr = wt + (size_t)kidx * Cout + co;
+                if (a_vec && co + 3 < Cout) ra[h] = __ldg(reinterpret_cast<const float4*>(wr));
+                else {
+                    if (co < Cout) ra[h].x = __ldg(wr);
+                    if (co + 1 < Cout) ra[h].y = __ldg(wr + 1);
+                    if (co + 2 < Cout) ra[h].z = __ldg(wr + 2);
+                    if (co + 3 < Cout) ra[h].w = __ldg(wr + 3);
+                }
+                const int ci = kidx / k, kk = kidx - ci * k;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int t = ct[j] * s + kk - pad;
+                    if (cb[j] >= 0 && t >= 0 && t < T) rb[h][j] = __ldg(&x[((size_t)cb[j] * Cin + ci) * T + t]);
+                }
+            }
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            *reinterpret_cast<float4*>(&As[buf][ty + 16 * h][tx * 4]) = ra[h];
+            *reinterpret_cast<float4*>(&Bs[buf][ty + 16 * h][tx * 4]) = make_float4(rb[h][0], rb[h][1], rb[h][2], rb[h][3]);
+        }
+    };
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < K; k0 += EG_K) {
+        const bool more = k0 + EG_K < K;
+        if (more) fetch(k0 + EG_K);
+#pragma unroll
+        for (int kk = 0; kk < EG_K; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+        }
+        if (more) {
+            stash(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= Cout) continue;
+        const float bv = bias ? __ldg(&bias[co]) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (cb[j] < 0) continue;
+            float v = acc[i][j] + bv;
+            if (relu) v = fmaxf(v, 0.f);
+            if (residual) v += __ldg(&x[((size_t)cb[j] * Cin + co) * T + ct[j]]);      // stride 1, Cin == Cout: same indexing
+            out[((size_t)cb[j] * Cout + co) * Tout + ct[j]] = v;
+        }
+    }
+}
+}  // namespace
+
+extern "C" int wae_conv1d_relu_res(const float* x, const float* w, const float* bias, int B, int Cin, int T, int Cout, int k, int stride,
+                                   int relu, int residual, float* out, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(x && w && out, "wae_conv1d_relu_res: null pointer");
+    WAE_REQUIRE(B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && T > 0, "wae_conv1d_relu_res: bad sizes");
+    WAE_REQUIRE((k & 1) == 1 && k >= 1 && stride >= 1, "wae_conv1d_relu_res: odd k, stride >= 1 (k=%d stride=%d)", k, stride);
+    WAE_REQUIRE(!residual || (stride == 1 && Cin == Cout), "wae_conv1d_relu_res: the residual needs stride 1 and Cin == Cout");
+    const int Tout = (T - 1) / stride + 1;
+    const long long N = (long long)B * Tout;
+    WAE_REQUIRE(N < (1ll << 31) && (long long)Cin * k < (1ll << 31), "wae_conv1d_relu_res: sizes too large");
+    enc_conv_kernel<<<dim3((unsigned)((N + EG_N - 1) / EG_N), (Cout + EG_M - 1) / EG_M), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        x, w, bias, Cin, T, Cout, k, stride, Tout, (int)N, relu, residual, out);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
