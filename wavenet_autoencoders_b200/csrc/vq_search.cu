@@ -363,11 +363,20 @@ enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Ci
     for (int k0 = 0; k0 < K; k0 += EG_K) {
         const bool more = k0 + EG_K < K;
         if (more) fetch(k0 + EG_K);
+        // operands of step kk + 2 are loaded while step kk is multiplied (ncu: short-scoreboard stalls on these LDS dominated)
+        float4 av[3], bv[3];
+        av[0] = *reinterpret_cast<const float4*>(&As[buf][0][ty * 4]);
+        bv[0] = *reinterpret_cast<const float4*>(&Bs[buf][0][tx * 4]);
+        av[1] = *reinterpret_cast<const float4*>(&As[buf][1][ty * 4]);
+        bv[1] = *reinterpret_cast<const float4*>(&Bs[buf][1][tx * 4]);
 #pragma unroll
         for (int kk = 0; kk < EG_K; ++kk) {
-            const float4 av = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
-            const float4 bv = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
-            const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+            if (kk + 2 < EG_K) {
+                av[(kk + 2) % 3] = *reinterpret_cast<const float4*>(&As[buf][kk + 2][ty * 4]);
+                bv[(kk + 2) % 3] = *reinterpret_cast<const float4*>(&Bs[buf][kk + 2][tx * 4]);
+            }
+            const float4 a = av[kk % 3], b = bv[kk % 3];
+            const float a4[4] = {a.x, a.y, a.z, a.w}, b4[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
