@@ -856,6 +856,25 @@ __device__ __noinline__ void allgather_bf16_async(const __nv_bfloat16* src, int 
         }
     }
 }
+// fp32 variant (the logits): 16-byte chunks when the slice allows, single words otherwise
+__device__ __noinline__ void allgather_f32_async(const float* src, int spitch, float* dst, int dpitch, int off, int n, int cs, int tid,
+                                                 uint64_t* bar) {
+    const uint32_t bar_local = smem_u32(bar);
+    if (((n | off | spitch | dpitch) & 3) == 0) {
+        const int nv = n >> 2, per = UC * nv;
+        for (int e = tid; e < cs * per; e += AR_THREADS) {
+            const int r = e / per, w = e - r * per, u = w / nv, i = w - u * nv;
+            const uint4 v = *reinterpret_cast<const uint4*>(src + u * spitch + 4 * i);
+            st_async_v4u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + 4 * i), (uint32_t)r), v, mapa(bar_local, (uint32_t)r));
+        }
+        return;
+    }
+    const int per = UC * n;
+    for (int e = tid; e < cs * per; e += AR_THREADS) {
+        const int r = e / per, w = e - r * per, u = w / n, i = w - u * n;
+        st_async_u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + i), (uint32_t)r), __float_as_uint(src[u * spitch + i]), mapa(bar_local, (uint32_t)r));
+    }
+}
 __device__ __noinline__ void allgather_f32(const float* src, int spitch, float* dst, int dpitch, int off, int n, int cs, int tid) {
     const int per = UC * n;
     for (int e = tid; e < cs * per; e += AR_THREADS) {
@@ -1078,7 +1097,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     int* cur_idx = reinterpret_cast<int*>(bars + 4);             // [UC]
     uint64_t* h_full = bars + 62;                                // all-gather barriers (end of the 512-byte misc region)
     uint64_t* x_full = bars + 63;
+    uint64_t* s2_full = bars + 60;                               // head: second hidden layer / logits all-gathers
+    uint64_t* lg_full = bars + 61;
     const uint32_t h_bytes = (uint32_t)(UC * H * 2), x_bytes = (uint32_t)(UC * R * 2);
+    const uint32_t s2_bytes = (uint32_t)(UC * S * 2), lg_bytes = (uint32_t)(UC * O * 4);
 
     const int p0 = part(H, rank, cs), np = part(H, rank + 1, cs) - p0;
     const int ro0 = part(R, rank, cs), nres = part(R, rank + 1, cs) - ro0;
@@ -1114,10 +1136,12 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     if (tid == 0) {
         mbar_init(&w1_full[0], 1); mbar_init(&w1_full[1], 1);
         mbar_init(&w2_full[0], 1); mbar_init(&w2_full[1], 1);
-        mbar_init(h_full, 1); mbar_init(x_full, 1);
+        mbar_init(h_full, 1); mbar_init(x_full, 1); mbar_init(s2_full, 1); mbar_init(lg_full, 1);
         fence_mbar_init();
-        mbar_arrive_expect_tx(h_full, h_bytes);   // arm phase 0 of both exchanges (peers start after the cluster_sync below)
+        mbar_arrive_expect_tx(h_full, h_bytes);   // arm phase 0 of every exchange (peers start after the cluster_sync below)
         mbar_arrive_expect_tx(x_full, x_bytes);
+        mbar_arrive_expect_tx(s2_full, s2_bytes);
+        mbar_arrive_expect_tx(lg_full, lg_bytes);
     }
     for (int e = tid; e < (sl.off_boff - sl.off_xin) / 4; e += AR_THREADS) reinterpret_cast<uint32_t*>(smem + sl.off_xin)[e] = 0u;
     __syncthreads();
@@ -1462,13 +1486,14 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             stgx[u * STX + i] = __float2bfloat16_rn(fmaxf(red_sum(red, sl.rows3p, i, u) + b3c[i], 0.f));
         }
         __syncthreads();
-        allgather_bf16(stgx, STX, s2buf, SS, so0, nsk, cs, tid);
+        // The first head exchange above keeps its cluster barrier (it orders this step's ring rows for the whole cluster and
+        // fences the reuse of s2buf / lgbuf across steps); the other two are st.async all-gathers like the layers'.
+        allgather_bf16_async(stgx, STX, s2buf, SS, so0, nsk, cs, tid, s2_full);
         ++j2;
-        cluster_arrive();
+        if (tid == 0) issue_w2(j2 + 1, 0);      // the slot of head matrix 3 is free (every warp passed the barrier after its mat-vec)
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
-        cluster_wait();
-        if (tid == 0) issue_w2(j2 + 1, 0);      // the slot of head matrix 3 is free: first layer of the next step
-        __syncwarp();
+        mbar_wait(s2_full, (uint32_t)(t & 1));
+        if (tid == 0) mbar_arrive_expect_tx(s2_full, s2_bytes);
         gemv_ksplit(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt4, W3S, S / 16, smem_u32(s2buf), (uint32_t)(SS * 2), S / 16, 0u, 0u, red,
                     sl.rows4p);
         __syncthreads();
@@ -1479,12 +1504,11 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             stgl[u * STL + i] = red_sum(red, sl.rows4p, i, u) + b4c[i];
         }
         __syncthreads();
-        allgather_f32(stgl, STL, lgbuf, O, oo0, nout, cs, tid);
+        allgather_f32_async(stgl, STL, lgbuf, O, oo0, nout, cs, tid, lg_full);
         ++j2;
-        cluster_arrive();
-        cluster_wait();
         if (tid == 0) issue_w2(j2 + 1, 1);
-        __syncwarp();
+        mbar_wait(lg_full, (uint32_t)(t & 1));
+        if (tid == 0) mbar_arrive_expect_tx(lg_full, lg_bytes);
 
         AR_PROF(10);
         // ---- output / sampling (categorical or none; scalar-input models use the SIMT kernel) ----
