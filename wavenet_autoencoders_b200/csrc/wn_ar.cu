@@ -9,18 +9,25 @@
 //  * every layer's two mat-vecs are split by OUTPUT ROW across the CTAs of the cluster; each CTA
 //    streams only its row slice of the weights (bf16 or fp32) from L2 into shared memory with
 //    cp.async.bulk + mbarrier, two layers ahead of use (11.5 MB of weights do not fit 8 x 227 KB);
-//  * partial results are exchanged through DISTRIBUTED SHARED MEMORY (st.shared::cluster) and
-//    hardware cluster barriers -- no global-memory flags, no grid-wide sync, nothing that can
-//    dead-lock if clusters are scheduled in waves;
+//  * partial results are exchanged through DISTRIBUTED SHARED MEMORY -- no global-memory flags, no grid-wide sync,
+//    nothing that can dead-lock if clusters are scheduled in waves.  The SIMT kernel (ar_kernel) pushes with
+//    st.shared::cluster and synchronises with hardware cluster barriers; the tensor-core kernel (ar_mma_kernel)
+//    pushes with st.async, which counts the bytes on an mbarrier of the RECEIVING CTA, so a layer's two exchanges need
+//    no barrier at all (one cluster barrier per step remains, in the head: it orders the history ring);
 //  * the dilation history is a ring in global memory ([kw-1]*d+1 rows per layer, the reference's own
 //    buffer length, conv.py:35) that is only ever touched at 3 rows per layer per step; the rows for
 //    the next layers are prefetched with cp.async while the current layer computes;
-//  * dot products: lanes split K, warp-shuffle reduce; tanh*sigmoid, residual, skip accumulation,
-//    the ReLU/1x1 head, softmax and the sampling (inverse-CDF categorical with caller-supplied
-//    uniforms, mixture of logistics, mixture of gaussians -- mixture.py:118-156, :221-270) are fused.
+//  * ar_kernel: lanes split K, warp-shuffle reduce (fp32 or bf16 weights, any sampler);
+//    ar_mma_kernel: every mat-vec is mma.sync.m16n8k16 with up to 8 utterances of the cluster as the n columns
+//    (bf16 weights, categorical / no sampling);
+//  * tanh*sigmoid, residual, skip accumulation, the ReLU/1x1 head, softmax and the sampling (inverse-CDF
+//    categorical with caller-supplied uniforms, mixture of logistics, mixture of gaussians -- mixture.py:118-156,
+//    :221-270) are fused.
 //
 // Numerics: fp32 accumulate everywhere; with fp32 weights the per-step logits match the reference
-// to ~1e-6 relative (tests/test_ar_gpu.py), with bf16 weights to ~1e-2.
+// to ~1e-6 relative (tests/test_gpu_parity.py), with bf16 weights to ~1e-2.
+// Measured (vqwae shape, B200): fp32 SIMT 366 us per sample; bf16 tensor-core 53-57 us per sample for 8 utterances per
+// cluster = 1.1-1.2 x real time per utterance; history of the optimisation in profiles/ar_phase_r1.txt.
 #include "wae_common.cuh"
 
 using namespace wae::ptx;

@@ -20,8 +20,14 @@
 // sqrt(1/L), ReLU, the S->S 1x1, ReLU and the S->O 1x1 (wavenet.py:208-212): three chained tcgen05
 // GEMMs whose intermediate activations never leave shared memory / TMEM.
 //
-// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA
-// issuer (one elected lane), warps 2..5 = epilogue (each owns the 32 TMEM lanes of its warp_id % 4).
+// Warp roles (576 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator + MMA
+// issuer (one elected lane), warps 2..17 = epilogue (4 column groups x the 4 TMEM lane quadrants).
+//
+// Kernel variants in this file (wae_set_layer_cluster): layer_bf16_v2_kernel (DEFAULT: residual added by identity
+// MMAs, x' and h leave through shared memory + TMA stores, gate widths up to 512 in two accumulator passes),
+// layer_bf16_pair2_kernel (the same on CTA pairs, tcgen05 cta_group::2), and the two first-generation kernels
+// layer_bf16_kernel / layer_bf16_pair_kernel kept as measured evidence.  Measured numbers, role counters and the
+// shared-memory roofline that bounds the default kernel: DESIGN.md section 3 and profiles/.
 #include "wae_common.cuh"
 #include <vector>
 #include <utility>
