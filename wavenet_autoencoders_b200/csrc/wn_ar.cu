@@ -365,6 +365,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             nz = __reduce_add_sync(0xffffffffu, nz);
             pos = __reduce_max_sync(0xffffffffu, pos);
             const bool ok = __all_sync(0xffffffffu, is_one);
+            __syncwarp();                       // every lane has read cur_idx[warp] (the condition above) before lane 0 rewrites it
             if (lane == 0 && nz == 1 && ok) cur_idx[warp] = pos;
         }
         __syncthreads();
@@ -1303,6 +1304,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             nz = __reduce_add_sync(0xffffffffu, nz);
             pos = __reduce_max_sync(0xffffffffu, pos);
             const bool ok = __all_sync(0xffffffffu, is_one);
+            __syncwarp();                       // every lane has read cur_idx[warp] (the condition above) before lane 0 rewrites it
             if (lane == 0 && nz == 1 && ok) cur_idx[warp] = pos;
         }
         __syncthreads();
