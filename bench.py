@@ -386,7 +386,7 @@ def main():
         torch.backends.cudnn.benchmark = True            # the (out-of-scope, cuDNN) encoder's default wgrad algorithm is 3 x 1.8 ms
         tm = build_vqvae(dev).train()
         tm.wavenet.precision = "bf16"
-        opt = TS.make_optimizer(tm, capturable=True)
+        opt = TS.FlatAdam(tm, lr=4e-4, clip=100.0)       # clip + Adam on one flat buffer (f4); the all-reduce works on it directly
         rs = np.random.RandomState(7 + rank)
         Bt, Tt = 8, 7680
         ti = torch.tensor(rs.randint(0, 256, size=(Bt, Tt)), dtype=torch.long, device=dev)

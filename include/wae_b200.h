@@ -209,6 +209,17 @@ int wae_train_gate_bwd(const void* z, const float* gb, const void* dh_a, long lo
 int wae_train_dx_accum(const void* dxcat, const void* dxo, int B, int T, int R, int C, int Cp, int kw, int dil, float scale,
                        void* dx, float* dC, void* stream);
 
+/*
+ * Optimiser tail on one flat fp32 parameter / gradient buffer (the buffer the data-parallel all-reduce works on):
+ *   wae_sumsq      *out += sum g[i]^2  (caller zeroes; the global gradient norm of torch.nn.utils.clip_grad_norm_)
+ *   wae_adam_step  g' = g * min(1, max_norm / (sqrt(*sumsq) + 1e-6)) (max_norm <= 0: no clipping), then torch.optim.Adam's update
+ *                  (no amsgrad, no weight decay; hps/vqwae.json:50-55, vqwae_train.py:339-350,779-780).  The step count lives on
+ *                  the device (*step_out = *step_in + 1; two different buffers) so the call can sit in a CUDA graph.
+ */
+int wae_sumsq(const float* g, long long n, double* out, void* stream);
+int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                  float max_norm, const double* sumsq, const float* step_in, float* step_out, void* stream);
+
 /* Variant of the bf16 residual-layer kernel: -1 (default) = version-2 kernel (residual added by an identity MMA, x' and h
  * stored by TMA from shared memory); -2 = version 2 on CTA pairs (tcgen05 cta_group::2: each CTA stages half of every weight
  * k-block); 0 = first CTA-pair kernel; 1, 2 or 4 = the first 1-CTA kernel in clusters of that size, the CTAs of a cluster

@@ -460,3 +460,27 @@ def test_encoder_kernels_match_torch_convs(frames):
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             ref2 = enc.lin(enc.net(x).permute(0, 2, 1)).permute(0, 2, 1)
         assert rel_err(enc(x).cpu().numpy(), ref2.cpu().numpy()) < 1e-5
+
+
+def test_flat_adam_matches_torch_adam_with_clipping():
+    """train_step.FlatAdam (wae_sumsq + wae_adam_step on one flat buffer) against clip_grad_norm_ + torch.optim.Adam."""
+    from wavenet_autoencoders_b200.train_step import FlatAdam
+    torch.manual_seed(0)
+
+    def make():
+        torch.manual_seed(1)
+        return torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Tanh(), torch.nn.Linear(53, 11)).cuda()
+    ma, mb = make(), make()
+    oa = torch.optim.Adam(ma.parameters(), lr=4e-4, betas=(0.9, 0.999), eps=1e-8)
+    ob = FlatAdam(mb, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, clip=0.05)
+    for step in range(5):
+        x = torch.randn(64, 37, device="cuda") * (10.0 if step % 2 else 0.1)      # steps that clip and steps that do not
+        for m_, o_ in ((ma, oa), (mb, ob)):
+            o_.zero_grad()
+            m_(x).square().mean().backward()
+        torch.nn.utils.clip_grad_norm_(ma.parameters(), 0.05)
+        oa.step()
+        ob.step()
+        for pa, pb in zip(ma.parameters(), mb.parameters()):
+            assert torch.allclose(pa, pb, rtol=2e-5, atol=1e-7), step
+    assert float(ob.step_a) == 5.0

@@ -11,7 +11,7 @@ torch.backends.cudnn.benchmark = True
 tm = bench.build_vqvae(dev).train()
 tm.wavenet.precision = "bf16"
 tm.wavenet.train_impl = impl
-opt = TS.make_optimizer(tm)
+opt = TS.FlatAdam(tm) if impl == "kernels" else TS.make_optimizer(tm)
 rs = np.random.RandomState(7)
 Bt, Tt = 8, 7680
 ti = torch.tensor(rs.randint(0, 256, size=(Bt, Tt)), dtype=torch.long, device=dev)
@@ -35,7 +35,7 @@ tot = sum(e.self_device_time_total for e in ev) / 1e3
 n = sum(e.count for e in ev if e.self_device_time_total > 0)
 print(f"CUDA kernel time {tot:.2f} ms over {n} launches")
 if impl == "kernels":
-    opt2 = TS.make_optimizer(tm, capturable=True)
+    opt2 = TS.FlatAdam(tm)
     gs = TS.GraphedTrainStep(tm, opt2, ti, tmf, tg)
     for _ in range(2):
         gs(ti, tmf, tg)

@@ -231,3 +231,79 @@ int wae_nll_sum(const float* logits, const int64_t* target, int B, int O, int T,
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Optimiser tail on ONE flat fp32 buffer: gradient clipping by global norm (vqwae_train.py:779-780,
+// torch.nn.utils.clip_grad_norm_) and the Adam update (hps/vqwae.json:50-55, vqwae_train.py:339-350) for all 7.6 M
+// parameters in two launches -- the buffer the data-parallel all-reduce already works on.  torch's foreach Adam + clip over
+// ~300 tensors costs 2.5 ms of a 17 ms step; this is two HBM passes (~0.25 GB).
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out) {
+    float s = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float v = __ldg(&g[i]);
+        s = fmaf(v, v, s);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    __shared__ float part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += (double)part[w];
+        atomicAdd(out, t);
+    }
+}
+
+// state[0] = step count (incremented by thread 0 of block 0 AFTER every block has read it: see the grid-stride loop),
+// sumsq = sum of squared gradients (the clip coefficient is derived per thread, no host round trip)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
+            float b1, float b2, float eps, float max_norm, const double* __restrict__ sumsq, const float* __restrict__ step_in,
+            float* __restrict__ step_out) {
+    const float step = __ldg(step_in) + 1.f;
+    float coef = 1.f;
+    if (max_norm > 0.f) {
+        const float norm = (float)sqrt(__ldg(sumsq));
+        coef = fminf(max_norm / (norm + 1e-6f), 1.f);                       // torch.nn.utils.clip_grad_norm_
+    }
+    const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+    const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = __ldg(&g[i]) * coef;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);          // torch.optim.Adam (no amsgrad, no weight decay)
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *step_out = step;
+}
+
+}  // namespace
+
+extern "C" int wae_sumsq(const float* g, long long n, double* out, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(g && out && n >= 0, "wae_sumsq: bad arguments");
+    if (n == 0) return WAE_OK;
+    sumsq_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+
+extern "C" int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                             float max_norm, const double* sumsq, const float* step_in, float* step_out, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(p && g && m && v && step_in && step_out && n >= 0, "wae_adam_step: null pointer");
+    WAE_REQUIRE(max_norm <= 0.f || sumsq != nullptr, "wae_adam_step: clipping needs the squared gradient norm");
+    WAE_REQUIRE(step_in != step_out, "wae_adam_step: step_in and step_out must be different buffers (ping-pong)");
+    if (n == 0) return WAE_OK;
+    adam_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, max_norm, sumsq, step_in,
+                                                                             step_out);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}

@@ -15,6 +15,57 @@ def make_optimizer(model, lr=4e-4, capturable=False):
     return torch.optim.Adam(model.parameters(), lr=lr, betas=(0.9, 0.999), eps=1e-8, capturable=capturable)
 
 
+class FlatAdam:
+    """Adam + global-norm gradient clipping on ONE flat fp32 buffer (wae_sumsq / wae_adam_step).
+
+    Every parameter becomes a view into ``flat_p`` and every ``.grad`` a view into ``flat_g`` (autograd accumulates into them
+    in place), so the data-parallel exchange is a single all-reduce of ``flat_g`` with no gather/scatter copies, and the
+    clip + update of all tensors is two kernel launches.  Same update rule as ``torch.optim.Adam`` (no amsgrad, no weight decay)
+    after ``clip_grad_norm_`` -- tests/test_gpu_parity.py.  Parameters that never receive a gradient (the last layer's
+    ``conv1x1_out``) see zeros and do not move, like parameters torch's Adam skips."""
+
+    def __init__(self, model, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, clip=100.0):
+        from . import _lib
+        self._lib = _lib
+        self.params = [p for p in model.parameters() if p.requires_grad]
+        dev = self.params[0].device
+        n = sum(p.numel() for p in self.params)
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m, self.v = torch.zeros_like(self.flat_p), torch.zeros_like(self.flat_p)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            p.grad = self.flat_g[off:off + k].view_as(p)
+            off += k
+        self.lr, self.betas, self.eps, self.clip = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(clip or 0.0)
+        self.step_a = torch.zeros(1, dtype=torch.float32, device=dev)       # step count lives on the device (CUDA-graph safe)
+        self.step_b = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_g.zero_()
+
+    def allreduce(self, world):
+        import torch.distributed as dist
+        dist.all_reduce(self.flat_g)
+        self.flat_g.div_(world)
+
+    def step(self):
+        L, ptr = self._lib.lib(), self._lib.ptr
+        st = self._lib.stream_ptr(self.flat_p.device)
+        n = self.flat_p.numel()
+        if self.clip > 0:
+            self.sumsq.zero_()
+            self._lib.check(L.wae_sumsq(ptr(self.flat_g), n, ptr(self.sumsq), st), "wae_sumsq")
+        self._lib.check(L.wae_adam_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), n, self.lr, self.betas[0],
+                                        self.betas[1], self.eps, self.clip, ptr(self.sumsq), ptr(self.step_a), ptr(self.step_b), st),
+                        "wae_adam_step")
+        self.step_a.copy_(self.step_b)
+
+
 def train_step(model, opt, idx, mfcc, g, clip=100.0, world=1, timers=None):
     """idx (B,T) int64 mu-law classes; mfcc (B,39,frames); g (B,1) speaker ids.  Returns the loss tensor (no sync)."""
     x = F.one_hot(idx, 256).float().transpose(1, 2)                        # the collate's one-hot input (vqwae_train.py:509-520)
@@ -23,13 +74,18 @@ def train_step(model, opt, idx, mfcc, g, clip=100.0, world=1, timers=None):
     # vqwae_train.py:760-766: y_hat[:, :, :-1] predicts y[:, 1:]; full-length synthetic windows -> the mask is all ones
     loss = F.cross_entropy(y_hat[:, :, :-1], idx[:, 1:]) + vq_loss
     loss.backward()
+    flat = isinstance(opt, FlatAdam)
     if world > 1:
         if timers is not None:
             timers[0].record()
-        parallel.allreduce_gradients(model)                                # replaces replicate/gather (vqwae_train.py:698-706)
+        if flat:
+            opt.allreduce(world)                                           # one all-reduce of the flat gradient buffer, no copies
+        else:
+            parallel.allreduce_gradients(model)                            # replaces replicate/gather (vqwae_train.py:698-706)
         if timers is not None:
             timers[1].record()
-    torch.nn.utils.clip_grad_norm_(model.parameters(), clip)               # hps/vqwae.json:63, vqwae_train.py:779-780
+    if not flat:                                                           # FlatAdam clips inside its update (opt.clip)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), clip)           # hps/vqwae.json:63, vqwae_train.py:779-780
     opt.step()
     return loss.detach()
 

@@ -63,7 +63,7 @@ def _unshift(y, s):
 
 
 def _colsum(t, adt=torch.float32):
-    return t.to(adt).sum(dim=tuple(range(t.dim() - 1)))
+    return t.sum(dim=tuple(range(t.dim() - 1)), dtype=adt)          # accumulates in adt without materialising a converted copy
 
 
 def _wgrad(dy, x, adt=torch.float32):
@@ -127,7 +127,8 @@ def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_need
         b3 = weights[base + 3]
 
         # ---- head: logits = W4 relu(W3 relu(s) + b3) + b4,  s = (sum_l Ws_l h_l + bs_l) * sqrt(1/L) ----
-        dY = dlogits.transpose(1, 2).to(cdt).contiguous()                                  # (B,T,O)
+        dY = torch.empty(dlogits.shape[0], dlogits.shape[2], dlogits.shape[1], dtype=cdt, device=dlogits.device)
+        dY.copy_(dlogits.transpose(1, 2))                                                  # (B,T,O): transpose + cast in one pass
         Hcat = h_all.permute(1, 2, 0, 3).reshape(B, T, L * Hp)                            # (B,T,L*Hp)
         Wscat = torch.cat([F.pad(lw(l, 6)[:, :, 0], (0, Hp - H)) for l in range(L)], dim=1).to(cdt)   # (S, L*Hp)
         bs_sum = torch.zeros(S, dtype=adt, device=dY.device)
