@@ -92,7 +92,10 @@ int wae_upsample_stage(const float* in, int rows, int Tin, int s, const float* w
  * relu = residual = 0, the encoder's final Linear (vqvae_model.py:47-51).  Odd k, any stride.
  */
 int wae_conv1d_relu_res(const float* x, const float* w, const float* bias, int B, int Cin, int T, int Cout, int k, int stride,
-                        int relu, int residual, float* out, void* stream);
+                        int relu, int residual, float* out, int splits, float* partial, void* stream);
+/* splits > 1: the reduction over (channel, tap) is cut into `splits` slices computed by different blocks (these layers are a few
+ * dozen 64 x 64 tiles with a long serial reduction); `partial` holds splits x B x Cout x Tout floats, summed in a fixed order by
+ * a second launch that also applies bias / ReLU / residual. */
 
 /* ---- WaveNet decoder stack: shared description -------------------------- */
 typedef struct wae_stack_dims {

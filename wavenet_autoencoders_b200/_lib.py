@@ -67,7 +67,7 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p]),
     "wae_upsample_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "wae_conv1d_relu_res": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+                                      C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wae_stack_workspace_f32": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),
     "wae_stack_forward_f32": (C.c_int, [C.POINTER(StackF32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -308,14 +308,18 @@ constexpr int EG_M = 64, EG_N = 64, EG_K = 32, EG_THREADS = 512;
 
 __global__ void __launch_bounds__(EG_THREADS)
 enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Cin*k][Cout] */, const float* __restrict__ bias, int Cin,
-                int T, int Cout, int k, int s, int Tout, int N, int relu, int residual, float* __restrict__ out) {
+                int T, int Cout, int k, int s, int Tout, int N, int relu, int residual, float* __restrict__ out, int k_per_split,
+                float* __restrict__ partial) {
     __shared__ __align__(16) float As[2][EG_K][EG_M];
     __shared__ __align__(16) float Bs[2][EG_K][EG_N];
     const int tid = threadIdx.x;
     const int tx = tid & 31, ty = tid >> 5;           // compute: 32 column pairs x 16 row quads
     const int fr = tid >> 4, fc = (tid & 15) * 4;     // fetch: k-row fr, columns fc .. fc+3
     const int co0 = blockIdx.y * EG_M, n0 = blockIdx.x * EG_N;
-    const int K = Cin * k, pad = k / 2;
+    const int pad = k / 2;
+    // split-K: block z handles reduction indices [k_begin, K) of its slice and leaves raw partial sums for enc_reduce_kernel
+    const int k_begin = blockIdx.z * k_per_split;
+    const int K = min(Cin * k, k_begin + k_per_split);
     int fb[4], ft[4];                                 // the 4 im2col columns this thread gathers: n -> (utterance, frame)
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -355,11 +359,11 @@ enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Ci
     float acc[4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
-    fetch(0);
+    fetch(k_begin);
     stash(0);
     __syncthreads();
     int buf = 0;
-    for (int k0 = 0; k0 < K; k0 += EG_K) {
+    for (int k0 = k_begin; k0 < K; k0 += EG_K) {
         const bool more = k0 + EG_K < K;
         if (more) fetch(k0 + EG_K);
 #pragma unroll
@@ -388,6 +392,10 @@ enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Ci
         for (int i = 0; i < 4; ++i) {
             const int co = co0 + ty * 4 + i;
             if (co >= Cout) continue;
+            if (partial != nullptr) {                 // [split][utterance][channel][frame]
+                partial[(((size_t)blockIdx.z * (N / Tout) + ob) * Cout + co) * Tout + ot] = acc[i][j];
+                continue;
+            }
             float v = acc[i][j] + (bias ? __ldg(&bias[co]) : 0.f);
             if (relu) v = fmaxf(v, 0.f);
             if (residual) v += __ldg(&x[((size_t)ob * Cin + co) * T + ot]);            // stride 1, Cin == Cout: same indexing
@@ -395,20 +403,52 @@ enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Ci
         }
     }
 }
+// second pass of a split-K layer: sum the partial planes in a fixed order, then bias / ReLU / residual
+__global__ void __launch_bounds__(256)
+enc_reduce_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ x, const float* __restrict__ bias, int Cin, int T,
+                  int Cout, int Tout, long long total, int relu, int residual, float* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        for (int z = 0; z < splits; ++z) v += __ldg(&partial[(size_t)z * total + e]);
+        const int t = (int)(e % Tout);
+        const long long r = e / Tout;
+        const int co = (int)(r % Cout);
+        const long long b = r / Cout;
+        v += bias ? __ldg(&bias[co]) : 0.f;
+        if (relu) v = fmaxf(v, 0.f);
+        if (residual) v += __ldg(&x[((size_t)b * Cin + co) * T + t]);
+        out[e] = v;
+    }
+}
 }  // namespace
 
 extern "C" int wae_conv1d_relu_res(const float* x, const float* w, const float* bias, int B, int Cin, int T, int Cout, int k, int stride,
-                                   int relu, int residual, float* out, void* stream) {
+                                   int relu, int residual, float* out, int splits, float* partial, void* stream) {
     if (int rc = wae::require_sm100()) return rc;
     WAE_REQUIRE(x && w && out, "wae_conv1d_relu_res: null pointer");
     WAE_REQUIRE(B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && T > 0, "wae_conv1d_relu_res: bad sizes");
     WAE_REQUIRE((k & 1) == 1 && k >= 1 && stride >= 1, "wae_conv1d_relu_res: odd k, stride >= 1 (k=%d stride=%d)", k, stride);
     WAE_REQUIRE(!residual || (stride == 1 && Cin == Cout), "wae_conv1d_relu_res: the residual needs stride 1 and Cin == Cout");
+    WAE_REQUIRE(splits >= 1 && splits <= 64 && (splits == 1 || partial != nullptr), "wae_conv1d_relu_res: splits=%d needs a partial-sum buffer",
+                splits);
     const int Tout = (T - 1) / stride + 1;
     const long long N = (long long)B * Tout;
     WAE_REQUIRE(N < (1ll << 31) && (long long)Cin * k < (1ll << 31), "wae_conv1d_relu_res: sizes too large");
-    enc_conv_kernel<<<dim3((unsigned)((N + EG_N - 1) / EG_N), (Cout + EG_M - 1) / EG_M), EG_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
-        x, w, bias, Cin, T, Cout, k, stride, Tout, (int)N, relu, residual, out);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int K = Cin * k;
+    const int chunks = (K + EG_K - 1) / EG_K;
+    if (splits > chunks) splits = chunks;
+    const int k_per_split = (chunks + splits - 1) / splits * EG_K;           // whole k-chunks per split
+    splits = (K + k_per_split - 1) / k_per_split;
+    enc_conv_kernel<<<dim3((unsigned)((N + EG_N - 1) / EG_N), (Cout + EG_M - 1) / EG_M, splits), EG_THREADS, 0, st>>>(
+        x, w, bias, Cin, T, Cout, k, stride, Tout, (int)N, relu, residual, out, k_per_split, splits > 1 ? partial : nullptr);
     WAE_CHECK_LAUNCH();
+    if (splits > 1) {
+        const long long total = N * Cout;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        enc_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, splits, x, bias, Cin, T, Cout, Tout, total, relu, residual, out);
+        WAE_CHECK_LAUNCH();
+    }
     return WAE_OK;
 }

@@ -36,6 +36,23 @@ class Encoder(nn.Module):
         L, st = _lib.lib(), _lib.stream_ptr(x.device)
         cur = x.detach().float().contiguous()
         B = cur.shape[0]
+
+        def run(inp, w, b, cin, T, cout, k, s, relu, res, out):
+            # a layer is a few dozen 64 x 64 output tiles with a serial reduction of Cin*k/32 chunks (~1.9 us each): cut the
+            # reduction into slices until there are enough blocks for the GPU or a slice is only 4 chunks long
+            tiles = -(-(B * out.shape[-1]) // 64) * -(-cout // 64)
+            chunks = -(-(cin * k) // 32)
+            splits = max(1, min(chunks // 4, -(-148 // tiles), 8))
+            part = None
+            if splits > 1:
+                need = splits * out.numel()
+                part = self.__dict__.get("_partial")
+                if part is None or part.numel() < need or part.device != out.device:
+                    part = torch.empty(need, dtype=torch.float32, device=out.device)
+                    self.__dict__["_partial"] = part
+            _lib.check(L.wae_conv1d_relu_res(_lib.ptr(inp), _lib.ptr(w), _lib.ptr(b), B, cin, T, cout, k, s, relu, res, _lib.ptr(out),
+                                             splits, _lib.ptr(part), st), "wae_conv1d_relu_res")
+
         for m in self.net:
             conv = m.conv
             k, s = conv.kernel_size[0], conv.stride[0]
@@ -43,14 +60,12 @@ class Encoder(nn.Module):
             T = cur.shape[-1]
             out = torch.empty(B, m.dim_out, (T - 1) // s + 1, dtype=torch.float32, device=cur.device)
             w, b = self._wt(conv.weight), conv.bias.detach().float().contiguous()
-            _lib.check(L.wae_conv1d_relu_res(_lib.ptr(cur), _lib.ptr(w), _lib.ptr(b), B, m.dim_in, T, m.dim_out, k, s, 1, res,
-                                             _lib.ptr(out), st), "wae_conv1d_relu_res")
+            run(cur, w, b, m.dim_in, T, m.dim_out, k, s, 1, res, out)
             cur = out
         T = cur.shape[-1]
         out = torch.empty(B, self.lin.out_features, T, dtype=torch.float32, device=cur.device)
         w, b = self._wt(self.lin.weight), self.lin.bias.detach().float().contiguous()
-        _lib.check(L.wae_conv1d_relu_res(_lib.ptr(cur), _lib.ptr(w), _lib.ptr(b), B, self.lin.in_features, T, self.lin.out_features,
-                                         1, 1, 0, 0, _lib.ptr(out), st), "wae_conv1d_relu_res")
+        run(cur, w, b, self.lin.in_features, T, self.lin.out_features, 1, 1, 0, 0, out)
         return out
 
     def _wt(self, weight):
