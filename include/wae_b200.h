@@ -76,6 +76,15 @@ int wae_vq_search(const float* x, int B, int D, int T, int d0, int sub_d,
 int wae_vq_ema_stats(const float* x, int B, int D, int T, int d0, int sub_d,
                      const int64_t* idx, int K, float* dw, void* stream);
 
+/*
+ * Statistics of an inference-time VQ forward from wae_vq_search's by-products, one launch: out2[0] = sum(sqerr[0..nslices)) /
+ * n_elements (the mean squared quantisation error: both loss terms of vector_quantization.py:41-43 / :114-118 when nothing is
+ * detached), out2[1] = sum over slices of exp(-sum_k p log(p + 1e-10)), p = counts[slice][k] / n_vectors (:47-48, :122-127).
+ * All slices must have the same codebook size K.
+ */
+int wae_vq_stats(const double* sqerr, const int32_t* counts, int nslices, int K, long long n_vectors, long long n_elements,
+                 float* out2, void* stream);
+
 /* ---- conditioning upsampler (one stage) -------------------------------- */
 /*
  * out[b][c][u] = sum_{j=0..2s} w[j] * in[b][c][ floor((u + j - s) / s) ]   (zero outside [0, Tin*s))

@@ -289,6 +289,39 @@ int wae_upsample_stage(const float* in, int rows, int Tin, int s, const float* w
 
 }  // extern "C"
 
+// Inference-time statistics of a VQ forward in one launch: out[0] = mean squared quantisation error (both loss terms of
+// vector_quantization.py:41-43 reduce to it when nothing is detached), out[1] = sum over the slices of the code perplexity
+// exp(-sum_k p_k log(p_k + 1e-10)), p = counts / N (vector_quantization.py:47-48, :122-127).  Replaces ~15 element-wise launches.
+__global__ void __launch_bounds__(256)
+vq_stats_kernel(const double* __restrict__ sqerr, const int* __restrict__ counts, int nslices, int K, double n_vec, double n_elem,
+                float* __restrict__ out) {
+    __shared__ float part[8];
+    float perp = 0.f;
+    for (int sidx = 0; sidx < nslices; ++sidx) {
+        float h = 0.f;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            const float p = (float)counts[sidx * K + k] / (float)n_vec;
+            h += p * logf(p + 1e-10f);
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) h += __shfl_xor_sync(0xffffffffu, h, off);
+        if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t += part[w];
+            perp += expf(-t);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        double e = 0.0;
+        for (int sidx = 0; sidx < nslices; ++sidx) e += sqerr[sidx];
+        out[0] = (float)(e / n_elem);
+        out[1] = perp;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Frame-rate encoder layer (vqvae_model.py:12-21): out = relu(conv1d(x, w, stride, padding = k/2) + bias) [+ x], fp32.
 // The encoder runs at 1/640 of the sample rate (16 x 100 frames at BASELINE config 2): a dozen tiny convolutions for which
@@ -450,5 +483,14 @@ extern "C" int wae_conv1d_relu_res(const float* x, const float* w, const float* 
         enc_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, splits, x, bias, Cin, T, Cout, Tout, total, relu, residual, out);
         WAE_CHECK_LAUNCH();
     }
+    return WAE_OK;
+}
+
+extern "C" int wae_vq_stats(const double* sqerr, const int32_t* counts, int nslices, int K, long long n_vectors, long long n_elements,
+                            float* out2, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(sqerr && counts && out2 && nslices >= 1 && K >= 1 && n_vectors > 0 && n_elements > 0, "wae_vq_stats: bad arguments");
+    vq_stats_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(sqerr, counts, nslices, K, (double)n_vectors, (double)n_elements, out2);
+    WAE_CHECK_LAUNCH();
     return WAE_OK;
 }

@@ -21,7 +21,7 @@ from . import _lib
 
 
 def _search(x: torch.Tensor, codebook: torch.Tensor, d0: int, sub_d: int, quant: torch.Tensor | None,
-            want_stats: bool):
+            want_stats: bool, sqerr: torch.Tensor | None = None, counts: torch.Tensor | None = None):
     """x (B,D,T) fp32 cuda contiguous -> idx (B*T,) int64 [, sqerr (1,) f64, counts (K,) i32]; fills quant rows."""
     if not x.is_cuda:
         raise _lib.WaeError(f"vector quantization input is on {x.device}; wavenet_autoencoders_b200 runs on CUDA "
@@ -30,8 +30,9 @@ def _search(x: torch.Tensor, codebook: torch.Tensor, d0: int, sub_d: int, quant:
     K = codebook.shape[0]
     cb = codebook.detach().float().contiguous()
     idx = torch.empty(B * T, dtype=torch.int64, device=x.device)
-    sqerr = torch.zeros(1, dtype=torch.float64, device=x.device) if want_stats else None
-    counts = torch.zeros(K, dtype=torch.int32, device=x.device) if want_stats else None
+    if want_stats and sqerr is None:               # else: zeroed views into the caller's per-slice buffers
+        sqerr = torch.zeros(1, dtype=torch.float64, device=x.device)
+        counts = torch.zeros(K, dtype=torch.int32, device=x.device)
     _lib.check(_lib.lib().wae_vq_search(_lib.ptr(x), B, D, T, d0, sub_d, _lib.ptr(cb), K, _lib.ptr(idx),
                                         _lib.ptr(quant), _lib.ptr(sqerr), _lib.ptr(counts),
                                         _lib.stream_ptr(x.device)), "wae_vq_search")
@@ -68,8 +69,15 @@ class _VQBase(nn.Module):
         grad = _needs_grad(x, *[emb.weight for _, _, emb in self._slices()])
         quant = torch.empty_like(xin)
         idxs, counts, sqerr_total = [], [], 0.0
-        for d0, sd, emb in self._slices():
-            idx, sqerr, cnt = _search(xin, emb.weight, d0, sd, None if (grad or training_hook) else quant, True)
+        slices = self._slices()
+        Ks = [emb.weight.shape[0] for _, _, emb in slices]
+        fused_stats = not (grad or training_hook) and len(set(Ks)) == 1     # one statistics launch instead of ~15 tiny ones
+        if fused_stats:
+            sq_all = torch.zeros(len(slices), dtype=torch.float64, device=xin.device)
+            cn_all = torch.zeros(len(slices), Ks[0], dtype=torch.int32, device=xin.device)
+        for si, (d0, sd, emb) in enumerate(slices):
+            idx, sqerr, cnt = _search(xin, emb.weight, d0, sd, None if (grad or training_hook) else quant, True,
+                                      sq_all[si:si + 1] if fused_stats else None, cn_all[si] if fused_stats else None)
             idxs.append(idx)
             counts.append(cnt)
             sqerr_total = sqerr_total + sqerr
@@ -81,10 +89,17 @@ class _VQBase(nn.Module):
             xt = x.permute(0, 2, 1)
             vq_loss = loss_fn(torch.mean((q.detach() - xt) ** 2), torch.mean((q - xt.detach()) ** 2))
             quant = (xt + (q - xt).detach()).permute(0, 2, 1)
+            perp = sum(_perplexity(c, N) for c in counts)
+        elif fused_stats:
+            out2 = torch.empty(2, dtype=torch.float32, device=xin.device)
+            _lib.check(_lib.lib().wae_vq_stats(_lib.ptr(sq_all), _lib.ptr(cn_all), len(slices), Ks[0], N, N * D, _lib.ptr(out2),
+                                               _lib.stream_ptr(xin.device)), "wae_vq_stats")
+            vq_loss = loss_fn(out2[0], out2[0])
+            perp = out2[1]
         else:
             mse = (sqerr_total / float(N * D)).float().squeeze(0)
             vq_loss = loss_fn(mse, mse)
-        perp = sum(_perplexity(c, N) for c in counts)
+            perp = sum(_perplexity(c, N) for c in counts)
         codes = [i.view(B, T) for i in idxs]
         self.last_codes = codes[0] if len(codes) == 1 else torch.stack(codes, dim=-1)
         return quant, vq_loss, perp
