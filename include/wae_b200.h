@@ -230,7 +230,9 @@ int wae_train_dx_accum(const void* dxcat, const void* dxo, int B, int T, int R, 
  */
 int wae_sumsq(const float* g, long long n, double* out, void* stream);
 int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                  float max_norm, const double* sumsq, const float* step_in, float* step_out, void* stream);
+                  float max_norm, const double* sumsq, const float* step_in, float* step_out, float* ema, float ema_decay,
+                  void* stream);
+/* ema (optional, NULL = none): the reference's shadow parameters, ema -= (1 - ema_decay) * (ema - p_new)  (vqwae_train.py:337-350,782-787) */
 
 /* Variant of the bf16 residual-layer kernel: -1 (default) = version-2 kernel (residual added by an identity MMA, x' and h
  * stored by TMA from shared memory); -2 = version 2 on CTA pairs (tcgen05 cta_group::2: each CTA stages half of every weight

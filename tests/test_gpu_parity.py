@@ -472,7 +472,8 @@ def test_flat_adam_matches_torch_adam_with_clipping():
         return torch.nn.Sequential(torch.nn.Linear(37, 53), torch.nn.Tanh(), torch.nn.Linear(53, 11)).cuda()
     ma, mb = make(), make()
     oa = torch.optim.Adam(ma.parameters(), lr=4e-4, betas=(0.9, 0.999), eps=1e-8)
-    ob = FlatAdam(mb, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, clip=0.05)
+    ob = FlatAdam(mb, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, clip=0.05, ema_decay=0.9)
+    shadow = [p.detach().clone() for p in ma.parameters()]
     for step in range(5):
         x = torch.randn(64, 37, device="cuda") * (10.0 if step % 2 else 0.1)      # steps that clip and steps that do not
         for m_, o_ in ((ma, oa), (mb, ob)):
@@ -483,4 +484,8 @@ def test_flat_adam_matches_torch_adam_with_clipping():
         ob.step()
         for pa, pb in zip(ma.parameters(), mb.parameters()):
             assert torch.allclose(pa, pb, rtol=2e-5, atol=1e-7), step
+        for sh, pa in zip(shadow, ma.parameters()):                   # vqwae_train.py:346-350
+            sh -= (1.0 - 0.9) * (sh - pa.detach())
+        for sh, (pb, eb) in zip(shadow, ob.ema_state().items()):
+            assert torch.allclose(sh, eb, rtol=2e-5, atol=1e-7), step
     assert float(ob.step_a) == 5.0

@@ -264,7 +264,7 @@ sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
             float b1, float b2, float eps, float max_norm, const double* __restrict__ sumsq, const float* __restrict__ step_in,
-            float* __restrict__ step_out) {
+            float* __restrict__ step_out, float* __restrict__ ema, float ema_decay) {
     const float step = __ldg(step_in) + 1.f;
     float coef = 1.f;
     if (max_norm > 0.f) {
@@ -279,7 +279,12 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi;
         v[i] = vi;
-        p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);          // torch.optim.Adam (no amsgrad, no weight decay)
+        const float pi = p[i] - step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);   // torch.optim.Adam (no amsgrad, no weight decay)
+        p[i] = pi;
+        if (ema != nullptr) {                                               // shadow -= (1 - decay) * (shadow - p)   (vqwae_train.py:346-350)
+            const float sh = ema[i];
+            ema[i] = sh - (1.f - ema_decay) * (sh - pi);
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) *step_out = step;
 }
@@ -296,14 +301,15 @@ extern "C" int wae_sumsq(const float* g, long long n, double* out, void* stream)
 }
 
 extern "C" int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                             float max_norm, const double* sumsq, const float* step_in, float* step_out, void* stream) {
+                             float max_norm, const double* sumsq, const float* step_in, float* step_out, float* ema, float ema_decay,
+                             void* stream) {
     if (int rc = wae::require_sm100()) return rc;
     WAE_REQUIRE(p && g && m && v && step_in && step_out && n >= 0, "wae_adam_step: null pointer");
     WAE_REQUIRE(max_norm <= 0.f || sumsq != nullptr, "wae_adam_step: clipping needs the squared gradient norm");
     WAE_REQUIRE(step_in != step_out, "wae_adam_step: step_in and step_out must be different buffers (ping-pong)");
     if (n == 0) return WAE_OK;
     adam_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, max_norm, sumsq, step_in,
-                                                                             step_out);
+                                                                             step_out, ema, ema_decay);
     WAE_CHECK_LAUNCH();
     return WAE_OK;
 }

@@ -24,7 +24,7 @@ class FlatAdam:
     after ``clip_grad_norm_`` -- tests/test_gpu_parity.py.  Parameters that never receive a gradient (the last layer's
     ``conv1x1_out``) see zeros and do not move, like parameters torch's Adam skips."""
 
-    def __init__(self, model, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, clip=100.0):
+    def __init__(self, model, lr=4e-4, betas=(0.9, 0.999), eps=1e-8, clip=100.0, ema_decay=None):
         from . import _lib
         self._lib = _lib
         self.params = [p for p in model.parameters() if p.requires_grad]
@@ -44,6 +44,17 @@ class FlatAdam:
         self.step_a = torch.zeros(1, dtype=torch.float32, device=dev)       # step count lives on the device (CUDA-graph safe)
         self.step_b = torch.zeros(1, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+        # the reference's ExponentialMovingAverage shadow of every parameter (vqwae_train.py:337-350), updated in the same pass
+        self.ema_decay = None if ema_decay is None else float(ema_decay)
+        self.ema = self.flat_p.clone() if ema_decay is not None else None
+
+    def ema_state(self):
+        """{parameter: shadow tensor} views into the flat shadow buffer (what clone_as_averaged_model copies, :353-360)."""
+        out, off = {}, 0
+        for p in self.params:
+            out[p] = self.ema[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        return out
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
@@ -61,7 +72,8 @@ class FlatAdam:
             self.sumsq.zero_()
             self._lib.check(L.wae_sumsq(ptr(self.flat_g), n, ptr(self.sumsq), st), "wae_sumsq")
         self._lib.check(L.wae_adam_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), n, self.lr, self.betas[0],
-                                        self.betas[1], self.eps, self.clip, ptr(self.sumsq), ptr(self.step_a), ptr(self.step_b), st),
+                                        self.betas[1], self.eps, self.clip, ptr(self.sumsq), ptr(self.step_a), ptr(self.step_b),
+                                        ptr(self.ema), self.ema_decay or 0.0, st),
                         "wae_adam_step")
         self.step_a.copy_(self.step_b)
 
