@@ -1454,7 +1454,9 @@ struct HeadArgs {
 
 constexpr int HEAD_STAGES = 3;
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) head_bf16_kernel(const __grid_constant__ HeadArgs a) {
+// 16 epilogue warps like the layer kernels (4 TMEM lane quadrants x 4 column groups): with 4 warps the three serial epilogues of
+// a tile (scale+ReLU, ReLU, logits) cost ~20k cycles between the GEMMs.
+__global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_kernel(const __grid_constant__ HeadArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int B_BYTES = 256 * BK * 2;
@@ -1475,9 +1477,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bf16_kernel(const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int s = 0; s < HEAD_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(accs_full, 1); mbar_init(epis_done, 128);
-        mbar_init(acc3_full, 1); mbar_init(epi3_done, 128);
-        mbar_init(acc4_full, 1); mbar_init(epi4_done, 128);
+        mbar_init(accs_full, 1); mbar_init(epis_done, 32 * LAYER_EPI_WARPS);
+        mbar_init(acc3_full, 1); mbar_init(epi3_done, 32 * LAYER_EPI_WARPS);
+        mbar_init(acc4_full, 1); mbar_init(epi4_done, 32 * LAYER_EPI_WARPS);
         fence_mbar_init();
         tma_prefetch_desc(&a.tm_h);
         tma_prefetch_desc(&a.tm_ws);
@@ -1569,6 +1571,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bf16_kernel(const __grid_
         }
     } else {
         const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;                 // column group of this warp: 16-column chunks cg, cg + 4, ...
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t act_addr = smem_u32(act);
@@ -1580,7 +1583,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bf16_kernel(const __grid_
 
             // relu(scale * (acc + bias)) / relu(acc + bias) -> bf16 -> `act` (A operand of the next GEMM)
             auto relu_to_act = [&](uint32_t tmem_acc, const float* bias, float scale) {
-                for (int c0 = 0; c0 < a.S; c0 += 16) {
+                for (int c0 = cg * 16; c0 < a.S; c0 += LAYER_NCG * 16) {
                     float v[16];
                     tmem_ld16(tmem_acc + lane_base + c0, v);
                     tmem_ld_wait();
@@ -1613,7 +1616,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) head_bf16_kernel(const __grid_
 
             mbar_wait(acc4_full, it & 1);
             tc_fence_after();
-            for (int c0 = 0; c0 < a.Op; c0 += 16) {
+            for (int c0 = cg * 16; c0 < a.Op; c0 += LAYER_NCG * 16) {
                 float v[16];
                 tmem_ld16(tmem_34 + lane_base + c0, v);
                 tmem_ld_wait();
@@ -1936,7 +1939,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
     {
         ProfScope prof(2, stream);
-        head_bf16_kernel<<<grid, NUM_THREADS, smem_head, stream>>>(ha);
+        head_bf16_kernel<<<grid, LAYER_THREADS, smem_head, stream>>>(ha);
     }
     WAE_CHECK_LAUNCH();
     return WAE_OK;
