@@ -359,14 +359,14 @@ def test_vqvae_forward_matches_reference_golden():
 
 
 # ------------------------------------------------------------------ training: tcgen05 forward + GEMM backward
-@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_k2"])
+@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_k2", "vqwae"])
 def test_training_backward_matches_autograd(cfg_name):
     """Gradients of the teacher-forced NLL through training.StackTrainFunction (bf16 kernels forward, hand-derived backward)
     against torch autograd over the fp32 composite of the same layer equations (itself pinned to the oracle by
     tests/test_host_cpu.py) -- every parameter, the conditioning input and the speaker embedding."""
     cfg = T.CONFIGS[cfg_name]
     m = build_model(cfg_name, 3, "cuda").train()
-    B, Tn = 3, 320
+    B, Tn = (3, 320) if cfg_name != "vqwae" else (2, 1280)      # vqwae: the real 20-layer shape, two latent frames
     x, idx, c, spk = T.synth_inputs(cfg, B, Tn, 11)
     x, idx, spk = x.cuda(), idx.cuda(), spk.cuda()
     m.precision = "bf16"
@@ -375,9 +375,12 @@ def test_training_backward_matches_autograd(cfg_name):
         m.train_impl = impl
         m.zero_grad(set_to_none=True)
         cc = c.cuda().clone().requires_grad_(True)
-        y = m(x, cc, spk)
-        loss = torch.nn.functional.cross_entropy(y[:, :, :-1], idx[:, 1:])
-        loss.backward()
+        # the reference side in true fp32: cuDNN's default TF32 convolutions put ~1e-3 of noise on every activation, which
+        # swamps the small residual-path gradients (|g| ~ 3e-5 next to 1e-3 on the skip path) of the 20-layer model
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            y = m(x, cc, spk)
+            loss = torch.nn.functional.cross_entropy(y[:, :, :-1], idx[:, 1:])
+            loss.backward()
         out[impl] = (float(loss), cc.grad.clone(), {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None})
     l0, dc0, g0 = out["autograd"]
     l1, dc1, g1 = out["kernels"]

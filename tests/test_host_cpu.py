@@ -162,7 +162,7 @@ def test_vq_module_api():
     assert m.embedding2.weight.shape == (4, 4) and float(m.embedding1.weight.abs().max()) <= 1 / 16
 
 
-@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_k2"])
+@pytest.mark.parametrize("cfg_name", ["tiny", "tiny_k2", "vqwae"])
 def test_hand_derived_stack_backward_matches_autograd_float64(cfg_name):
     """training.stack_backward (what the GPU training path runs in bf16 on the activations its tcgen05 forward saves) in
     float64 against torch autograd over the same layer equations: every weight, bias, the conditioning and the speaker vector."""
@@ -175,7 +175,7 @@ def test_hand_derived_stack_backward_matches_autograd_float64(cfg_name):
     m.load_state_dict(T.synth_state_dict(m, 4))
     sh = packing.stack_shape(m)
     L, R, H, C, kw = sh.layers, sh.R, sh.H, sh.C, sh.kernel_size
-    B, Tn = 2, 96
+    B, Tn = (2, 96) if cfg_name != "vqwae" else (1, 1280)      # vqwae: all 20 layers, dilations up to 512 against T = 1280
     x, idx, c, spk = T.synth_inputs(cfg, B, Tn, 5)
     D = torch.float64
     with torch.no_grad():
