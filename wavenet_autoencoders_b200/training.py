@@ -62,6 +62,19 @@ def _unshift(y, s):
     return y if s == 0 else F.pad(y, (0, 0, 0, s))[:, s:]
 
 
+def _mm_acc(a, b, adt):
+    """a (..., K) @ b (K, N) with the result kept in the accumulation dtype: the ReLU masks of the recomputed head must be
+    decided on the fp32 sums the forward kernel saw in TMEM, not on sums rounded to bf16 first."""
+    if a.dtype == adt:
+        return a @ b
+    a2 = a.reshape(-1, a.shape[-1])
+    try:
+        out = torch.mm(a2, b, out_dtype=adt)
+    except (TypeError, RuntimeError, NotImplementedError):
+        out = (a2 @ b).to(adt)
+    return out.reshape(*a.shape[:-1], b.shape[-1])
+
+
 def _colsum(t, adt=torch.float32):
     return t.sum(dim=tuple(range(t.dim() - 1)), dtype=adt)          # accumulates in adt without materialising a converted copy
 
@@ -135,9 +148,9 @@ def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_need
         for l in range(L):
             if lw(l, 7) is not None:
                 bs_sum = bs_sum + lw(l, 7).to(adt)
-        s = ((Hcat @ Wscat.t()).to(adt) + bs_sum) * scale
+        s = (_mm_acc(Hcat, Wscat.t(), adt) + bs_sum) * scale
         r1 = torch.relu(s).to(cdt)
-        p2 = (r1 @ W3[:, :, 0].to(cdt).t()).to(adt) + (b3.to(adt) if b3 is not None else 0.0)
+        p2 = _mm_acc(r1, W3[:, :, 0].to(cdt).t(), adt) + (b3.to(adt) if b3 is not None else 0.0)
         r2 = torch.relu(p2).to(cdt)
         grads[base + 4] = _wgrad(dY, r2, adt).unsqueeze(-1)
         if weights[base + 5] is not None:
