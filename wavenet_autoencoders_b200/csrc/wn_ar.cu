@@ -1424,16 +1424,13 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             if (tid == 0) issue_w2(j2 + 2, l + 2);     // stages L, L+1 are the two head matrices
             ++j2;
             AR_PROF(7);
-            for (int e = tid; e < n2 * UC; e += AR_THREADS) {
-                const int i = e >> 3, u = e & 7;
-                const float o = red_sum_n(red, sl.rows2p, i, u, nparts2) + b2c[(size_t)l * sl.max_n2 + i];
-                if (i < nres) {
-                    if (!last) {
-                        const float xo = (o + __bfloat162float(xl[(size_t)u * XS + (kw - 1) * R + ro0 + i])) * 0.70710678118654752440f;
-                        stgx[u * STX + i] = __float2bfloat16_rn(xo);
-                    }
-                } else {
-                    skipacc[u * (nsk + 1) + (i - nres)] += o;
+            // residual rows first: the x exchange is on the critical path, the skip accumulation (below) hides behind it
+            if (!last) {
+                for (int e = tid; e < nres * UC; e += AR_THREADS) {
+                    const int i = e >> 3, u = e & 7;
+                    const float o = red_sum_n(red, sl.rows2p, i, u, nparts2) + b2c[(size_t)l * sl.max_n2 + i];
+                    const float xo = (o + __bfloat162float(xl[(size_t)u * XS + (kw - 1) * R + ro0 + i])) * 0.70710678118654752440f;
+                    stgx[u * STX + i] = __float2bfloat16_rn(xo);
                 }
             }
             if (!last) {
@@ -1459,6 +1456,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                                 *reinterpret_cast<const uint32_t*>(stgx + u * STX + 2 * i);
                     }
                 }
+            }
+            for (int e = nres * UC + tid; e < n2 * UC; e += AR_THREADS) {     // skip rows: skips += Ws h + bs (wavenet.py:207)
+                const int i = e >> 3, u = e & 7;
+                skipacc[u * (nsk + 1) + (i - nres)] += red_sum_n(red, sl.rows2p, i, u, nparts2) + b2c[(size_t)l * sl.max_n2 + i];
             }
             AR_PROF(8);
             cp_async_wait<NPF_M - 2>();
