@@ -1347,16 +1347,6 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         const bf16* cl = cbuf + (size_t)(t & 1) * UC * CSd;
         const size_t gb_layer = (size_t)a.B * G;
         for (int l = 0; l < L; ++l) {
-            {
-                // the first layers of the NEXT step are fetched in the head, behind its cluster barrier (their newest tap can be
-                // a ring row written earlier in this step by another CTA); keep one commit group per layer here
-                const int lp = l + NPF_M - 1;
-                if (lp < L) {
-                    if (pf_fast) prefetch_taps_fast(t, lp, false, slot_add(slot, NPF_M - 1)); else prefetch_taps(t, lp, false);
-                } else {
-                    cp_async_commit();
-                }
-            }
             const bf16* xl = xin + (size_t)slot * UC * XS;
             // gate biases of this thread's (pair, utterance) items: issue the loads now, use them after the mma loop
             float gba[2] = {0.f, 0.f}, gbb[2] = {0.f, 0.f};
@@ -1405,6 +1395,18 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 }
             } else {
                 allgather_bf16_async(stgh, STH, hbuf, HS, p0, np, cs, tid, h_full);
+            }
+            // while the peers' h slices are in flight: prefetch the taps of the layer after next (slot (slot + 2) % 3 was last
+            // read by the previous layer)
+            {
+                // the first layers of the NEXT step are fetched in the head, behind its cluster barrier (their newest tap can be
+                // a ring row written earlier in this step by another CTA); keep one commit group per layer here
+                const int lp = l + NPF_M - 1;
+                if (lp < L) {
+                    if (pf_fast) prefetch_taps_fast(t, lp, false, slot_add(slot, NPF_M - 1)); else prefetch_taps(t, lp, false);
+                } else {
+                    cp_async_commit();
+                }
             }
             AR_PROF(5);
             mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
