@@ -1370,7 +1370,6 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 else gemv_ksplit_t<4>(a_lane, W1S, K1p / 16, xb, KX / 16, cb, redp, mt1, warp);
             }
             __syncthreads();
-            if (tid == 0) issue_w1(j1 + 2, l + 2 >= L ? l + 2 - L : l + 2);   // every warp is done with this layer's W1 slice: refill its slot
             ++j1;
             AR_PROF(3);
 #pragma unroll
@@ -1396,8 +1395,9 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
             } else {
                 allgather_bf16_async(stgh, STH, hbuf, HS, p0, np, cs, tid, h_full);
             }
-            // while the peers' h slices are in flight: prefetch the taps of the layer after next (slot (slot + 2) % 3 was last
-            // read by the previous layer)
+            // while the peers' h slices are in flight: refill the W1 slot this layer's mat-vec has released (every warp passed the
+            // barrier after it) and prefetch the taps of the layer after next (slot (slot + 2) % 3 was last read by the previous layer)
+            if (tid == 0) issue_w1(j1 + 1, l + 2 >= L ? l + 2 - L : l + 2);
             {
                 // the first layers of the NEXT step are fetched in the head, behind its cluster barrier (their newest tap can be
                 // a ring row written earlier in this step by another CTA); keep one commit group per layer here
@@ -1423,7 +1423,6 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 gemv_msplit_t(a_lane, xb, g2_part, Hp / 16, nparts2, red + ((size_t)g2_part * sl.rows2p + g2_m * 16) * UC + l_red);
             }
             __syncthreads();
-            if (tid == 0) issue_w2(j2 + 2, l + 2);     // stages L, L+1 are the two head matrices
             ++j2;
             AR_PROF(7);
             // residual rows first: the x exchange is on the critical path, the skip accumulation (below) hides behind it
@@ -1459,6 +1458,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                     }
                 }
             }
+            if (tid == 0) issue_w2(j2 + 1, l + 2);     // refill the W2 slot released above; stages L, L+1 are the two head matrices
             for (int e = nres * UC + tid; e < n2 * UC; e += AR_THREADS) {     // skip rows: skips += Ws h + bs (wavenet.py:207)
                 const int i = e >> 3, u = e & 7;
                 skipacc[u * (nsk + 1) + (i - nres)] += red_sum_n(red, sl.rows2p, i, u, nparts2) + b2c[(size_t)l * sl.max_n2 + i];
