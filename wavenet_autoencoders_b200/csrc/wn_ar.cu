@@ -1346,10 +1346,9 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         // ---- residual layers ----
         const bf16* cl = cbuf + (size_t)(t & 1) * UC * CSd;
         const size_t gb_layer = (size_t)a.B * G;
-        for (int l = 0; l < L; ++l) {
-            const bf16* xl = xin + (size_t)slot * UC * XS;
-            // gate biases of this thread's (pair, utterance) items: issue the loads now, use them after the mma loop
-            float gba[2] = {0.f, 0.f}, gbb[2] = {0.f, 0.f};
+        // gate biases of this thread's (pair, utterance) items of a layer: loaded one layer ahead, inside the x-exchange wait
+        float gba[2] = {0.f, 0.f}, gbb[2] = {0.f, 0.f};
+        auto load_gb = [&](int l) {
 #pragma unroll
             for (int q = 0; q < 2; ++q) {
                 if (gb_off[q] >= 0) {
@@ -1358,6 +1357,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                     gbb[q] = __ldg(gp + H);
                 }
             }
+        };
+        load_gb(0);
+        for (int l = 0; l < L; ++l) {
+            const bf16* xl = xin + (size_t)slot * UC * XS;
             AR_PROF(1);
             mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
             AR_PROF(2);
@@ -1459,6 +1462,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 }
             }
             if (tid == 0) issue_w2(j2 + 1, l + 2);     // refill the W2 slot released above; stages L, L+1 are the two head matrices
+            if (!last) load_gb(l + 1);
             for (int e = nres * UC + tid; e < n2 * UC; e += AR_THREADS) {     // skip rows: skips += Ws h + bs (wavenet.py:207)
                 const int i = e >> 3, u = e & 7;
                 skipacc[u * (nsk + 1) + (i - nres)] += red_sum_n(red, sl.rows2p, i, u, nparts2) + b2c[(size_t)l * sl.max_n2 + i];
