@@ -1494,8 +1494,14 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         for (int l2 = 0; l2 < NPF_M - 1; ++l2) {
             if (pf_fast) prefetch_taps_fast(t + 1, l2, true, slot_add(slot, (uint32_t)l2)); else prefetch_taps(t + 1, l2, true);
         }
-        gemv_ksplit(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt3, W3S, S / 16, smem_u32(s1buf), (uint32_t)(SS * 2), S / 16, 0u, 0u, red,
-                    sl.rows3p);
+        {   // the two head mat-vecs through the same specialised inline loops as the layers'
+            const uint32_t a_lane = smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot) + (uint32_t)(l_arow * W3S + l_acol2);
+            const uint32_t xb = smem_u32(s1buf) + (uint32_t)(l_brow * SS * 2 + l_bcol2);
+            float* redp = red + (size_t)warp * sl.rows3p * UC + l_red;
+            if (mt3 == 2) gemv_ksplit_t<2>(a_lane, W3S, S / 16, xb, S / 16, 0u, redp, mt3, warp);
+            else if (mt3 == 1) gemv_ksplit_t<1>(a_lane, W3S, S / 16, xb, S / 16, 0u, redp, mt3, warp);
+            else gemv_ksplit_t<4>(a_lane, W3S, S / 16, xb, S / 16, 0u, redp, mt3, warp);
+        }
         __syncthreads();
         for (int e = tid; e < nsk * UC; e += AR_THREADS) {
             const int i = e >> 3, u = e & 7;
@@ -1510,8 +1516,14 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         mbar_wait(&w2_full[j2 & 1], (uint32_t)((j2 >> 1) & 1));
         mbar_wait(s2_full, (uint32_t)(t & 1));
         if (tid == 0) mbar_arrive_expect_tx(s2_full, s2_bytes);
-        gemv_ksplit(smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot), mt4, W3S, S / 16, smem_u32(s2buf), (uint32_t)(SS * 2), S / 16, 0u, 0u, red,
-                    sl.rows4p);
+        {
+            const uint32_t a_lane = smem_u32(w2buf + (size_t)(j2 & 1) * sl.w2_slot) + (uint32_t)(l_arow * W3S + l_acol2);
+            const uint32_t xb = smem_u32(s2buf) + (uint32_t)(l_brow * SS * 2 + l_bcol2);
+            float* redp = red + (size_t)warp * sl.rows4p * UC + l_red;
+            if (mt4 == 2) gemv_ksplit_t<2>(a_lane, W3S, S / 16, xb, S / 16, 0u, redp, mt4, warp);
+            else if (mt4 == 1) gemv_ksplit_t<1>(a_lane, W3S, S / 16, xb, S / 16, 0u, redp, mt4, warp);
+            else gemv_ksplit_t<4>(a_lane, W3S, S / 16, xb, S / 16, 0u, redp, mt4, warp);
+        }
         __syncthreads();
         float* stgl = reinterpret_cast<float*>(stgx);       // fp32 logits staging [UC][max_n4 + 8]
         const int STL = sl.max_n4 + 8;
