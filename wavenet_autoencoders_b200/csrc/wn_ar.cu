@@ -68,16 +68,6 @@ struct ArArgs {
 
 __host__ __device__ inline int part(int n, int r, int cs) { return (n * r) / cs; }   // n*r < 2^31 (n <= 1024 rows, r <= 16)
 
-template <typename WT> struct WLoad;
-template <> struct WLoad<float> {
-    static __device__ __forceinline__ float2 ld2(const float* row, int k) { return *reinterpret_cast<const float2*>(row + k); }
-};
-template <> struct WLoad<__nv_bfloat16> {
-    static __device__ __forceinline__ float2 ld2(const __nv_bfloat16* row, int k) {
-        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + k));
-    }
-};
-
 template <typename WT> struct WLoad4;
 template <> struct WLoad4<float> {
     static __device__ __forceinline__ float4 ld(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -91,11 +81,6 @@ template <> struct WLoad4<__nv_bfloat16> {
     }
 };
 
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-    return v;
-}
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
@@ -883,14 +868,6 @@ __device__ __noinline__ void allgather_f32_async(const float* src, int spitch, f
         st_async_u32(mapa(smem_u32(dst + (size_t)u * dpitch + off + i), (uint32_t)r), __float_as_uint(src[u * spitch + i]), mapa(bar_local, (uint32_t)r));
     }
 }
-__device__ __noinline__ void allgather_f32(const float* src, int spitch, float* dst, int dpitch, int off, int n, int cs, int tid) {
-    const int per = UC * n;
-    for (int e = tid; e < cs * per; e += AR_THREADS) {
-        const int r = e / per, w = e - r * per, u = w / n, i = w - u * n;
-        st_cluster_f32(mapa(smem_u32(dst + (size_t)u * dpitch + off + i), (uint32_t)r), src[u * spitch + i]);
-    }
-}
-
 // ---- inline fast paths of ar_mma_kernel -------------------------------------------------------------------------
 // ncu on the first tensor-core version: 2 warps per scheduler, an instruction issued every ~7 cycles per warp (fixed-latency
 // "wait" stalls dominate), ~1300 instructions per warp per layer of which the mma work itself is ~60.  These variants keep
@@ -946,86 +923,8 @@ __device__ __forceinline__ void gemv_msplit_t(uint32_t a_lane, uint32_t xb, int 
 }
 
 // ---- out-of-line building blocks of ar_mma_kernel ------------------------------------------------------------------
-// The kernel runs ~10^5 cycles of mostly straight-line code per sample; with everything inlined its SASS was 211 KB and
-// adding 13 KB made every phase ~8% slower, 60 KB made it 1.8x slower (instruction-cache misses; profiles/ar_phase_r1.txt).
-// So: one copy of each building block, called; cold fallbacks kept out of the hot path.
-
-// partial[warp][row][u] = sum over this warp's k-steps of W[row][k] * X[u][k];   W: [mt*16][wstride] bf16 in smem (mt <= 4).
-// X: k-steps below nkx come from xaddr (row stride xstride bytes), the rest from caddr (conditioning rows).
-__device__ __noinline__ void gemv_ksplit(uint32_t w_addr, int mt, int wstride_bytes, int nk, uint32_t xaddr, uint32_t xstride, int nkx,
-                                         uint32_t caddr, uint32_t cstride, float* red, int rows_pad) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float acc[4][4];
-#pragma unroll
-    for (int m = 0; m < 4; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
-    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;    // ldmatrix.x4 lane -> (row, k) of its 8x8 matrix
-    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
-    const uint32_t a_lane = w_addr + (uint32_t)(arow * wstride_bytes + acol * 2);
-    const uint32_t xb = xaddr + brow * xstride + bcol * 2, cb = caddr + brow * cstride + bcol * 2;
-    // two k-steps per round: the ldmatrix of the round are issued before its first mma, so their latencies overlap
-    for (int ks0 = warp; ks0 < nk; ks0 += 2 * AR_WARPS) {
-        uint32_t bq[2][2], aq[2][4][4];
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int ks = ks0 + j * AR_WARPS;
-            if (ks < nk) {
-                ldsm_x2(ks < nkx ? xb + ks * 32 : cb + (ks - nkx) * 32, bq[j][0], bq[j][1]);
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    if (m < mt) ldsm_x4(a_lane + (uint32_t)(m * 16 * wstride_bytes + ks * 32), aq[j][m][0], aq[j][m][1], aq[j][m][2], aq[j][m][3]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            if (ks0 + j * AR_WARPS < nk) {
-#pragma unroll
-                for (int m = 0; m < 4; ++m)
-                    if (m < mt) mma_bf16_16816(acc[m], aq[j][m][0], aq[j][m][1], aq[j][m][2], aq[j][m][3], bq[j][0], bq[j][1]);
-            }
-        }
-    }
-    const int g = lane >> 2, t2 = (lane & 3) * 2;
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-        if (m < mt) {
-            float* p = red + ((size_t)warp * rows_pad + m * 16 + g) * UC + t2;
-            *reinterpret_cast<float2*>(p) = make_float2(acc[m][0], acc[m][1]);
-            *reinterpret_cast<float2*>(p + 8 * UC) = make_float2(acc[m][2], acc[m][3]);
-        }
-    }
-}
-
-// Variant for short reductions (K <= 256) and up to AR_WARPS m-tiles: warps are dealt (m-tile, k-part) pairs, so only
-// nparts = AR_WARPS / mt partial tiles have to be summed afterwards (warps beyond mt * nparts idle).
-__device__ __noinline__ void gemv_msplit(uint32_t w_addr, int mt, int wstride_bytes, int nk, uint32_t xaddr, uint32_t xstride, float* red,
-                                         int rows_pad) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nparts = AR_WARPS / mt, m = warp % mt, part_ = warp / mt;
-    if (part_ >= nparts) return;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const int arow = (lane & 7) + ((lane >> 3) & 1) * 8, acol = (lane >> 4) * 8;
-    const int brow = lane & 7, bcol = ((lane >> 3) & 1) * 8;
-    const uint32_t a_lane = w_addr + (uint32_t)((m * 16 + arow) * wstride_bytes + acol * 2);
-    const uint32_t xb = xaddr + brow * xstride + bcol * 2;
-    for (int ks0 = part_; ks0 < nk; ks0 += nparts * 4) {
-        uint32_t bq[4][2], aq[4][4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int ks = ks0 + j * nparts;
-            if (ks < nk) {
-                ldsm_x2(xb + ks * 32, bq[j][0], bq[j][1]);
-                ldsm_x4(a_lane + ks * 32, aq[j][0], aq[j][1], aq[j][2], aq[j][3]);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (ks0 + j * nparts < nk) mma_bf16_16816(acc, aq[j][0], aq[j][1], aq[j][2], aq[j][3], bq[j][0], bq[j][1]);
-    }
-    const int g = lane >> 2, t2 = (lane & 3) * 2;
-    float* p = red + ((size_t)part_ * rows_pad + m * 16 + g) * UC + t2;
-    *reinterpret_cast<float2*>(p) = make_float2(acc[0], acc[1]);
-    *reinterpret_cast<float2*>(p + 8 * UC) = make_float2(acc[2], acc[3]);
-}
+// Cold fallbacks (shapes the per-thread fast paths do not cover, dense first-conv input) are kept out of the hot path:
+// the kernel is issue-bound, and every instruction in the per-layer loop costs ~7 cycles per warp.
 
 // dense (not one-hot) input of the first conv: dot product of one weight column with the step's input vector
 __device__ __noinline__ float first_conv_dense(const float* __restrict__ wf, const float* inrow, int Oin, int R, int r) {

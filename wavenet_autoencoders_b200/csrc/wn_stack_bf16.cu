@@ -41,7 +41,6 @@ constexpr int BM = 128;                 // samples per tile (UMMA M)
 constexpr int BK = 64;                  // bf16 per k-block = one 128-byte swizzle row
 constexpr int A_TILE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int NUM_THREADS = 192;
-constexpr int EPI_WARP0 = 2;
 constexpr int TMEM_COLS = 512;
 constexpr float kSqrtHalf = 0.70710678118654752440f;
 
@@ -603,7 +602,7 @@ __device__ __forceinline__ void layer_epilogue(const LayerArgs& a, int cs, int c
 __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int H = a.G / 2;
+
     const int B_BYTES = 256 * BK * 2;  // stage B slot sized for N = 256
     const int STAGE_BYTES = A_TILE_BYTES + B_BYTES;
     uint8_t* hbuf = smem + LAYER_STAGES * STAGE_BYTES;
@@ -617,7 +616,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_kernel(const __gr
     uint64_t* epi2_done = acc1_full + 3;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int cs = (int)cluster_nctarank();              // 1, 2 or 4
     const int crank = (int)cluster_ctarank();
     const uint16_t cmask = (uint16_t)((1u << cs) - 1);
@@ -1113,7 +1112,7 @@ constexpr int PAIR_B_BYTES = 128 * BK * 2;   // half of an N = 256 weight k-bloc
 __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_pair_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int H = a.G / 2;
+
     const int STAGE_BYTES = A_TILE_BYTES + PAIR_B_BYTES;
     uint8_t* hbuf = smem + PAIR_STAGES * STAGE_BYTES;
     const int nkh = a.Hp / BK;
@@ -1126,7 +1125,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_pair_kernel(const
     uint64_t* epi2_done = acc1_full + 3;         // leader only, 256 arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
     const int crank = (int)cluster_ctarank();    // 0 = leader
     const bool leader = (crank == 0);
     if (threadIdx.x == 0) {
