@@ -42,17 +42,16 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
     const long long n0 = (long long)blockIdx.x * VQ_VT;
     const int tid = threadIdx.x;
 
-    // ---- stage the x tile: xs[j][v] ----
-    for (int e = tid; e < sub_d * VQ_VT; e += VQ_THREADS) {
-        int j = e / VQ_VT, v = e % VQ_VT;
-        long long n = n0 + v;
-        float val = 0.f;
-        if (n < N) {
-            long long b = n / T, t = n % T;
-            val = x[(b * D + d0 + j) * (long long)T + t];
-        }
-        xs[j * VQ_VT + v] = val;
-    }
+    // ---- stage the x tile: xs[j][v].  A thread keeps its vector v = tid % VQ_VT for the whole loop, so the (utterance, frame)
+    // split -- a 64-bit division -- is done once per thread, not once per element (it dominated the N = 400 launch) ----
+    static_assert(VQ_THREADS % VQ_VT == 0, "vector index must be loop-invariant per thread");
+    const int my_v = tid % VQ_VT, my_j0 = tid / VQ_VT;
+    const long long my_n = n0 + my_v;
+    const bool my_ok = my_n < N;
+    const long long my_b = my_ok ? my_n / T : 0, my_t = my_ok ? my_n - my_b * T : 0;
+    const size_t my_base = ((size_t)my_b * D + d0) * (size_t)T + (size_t)my_t;         // element (b, d0, t); + j * T per dimension
+    for (int j = my_j0; j < sub_d; j += VQ_THREADS / VQ_VT)
+        xs[j * VQ_VT + my_v] = my_ok ? x[my_base + (size_t)j * T] : 0.f;
     __syncthreads();
     if (tid < VQ_VT) {
         float s = 0.f;
@@ -144,20 +143,16 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
     }
     double local_err = 0.0;
     if (quant_out != nullptr || sqerr_out != nullptr) {
-        for (int e = tid; e < sub_d * VQ_VT; e += VQ_THREADS) {
-            int j = e / VQ_VT, v = e % VQ_VT;
-            long long n = n0 + v;
-            if (n >= N) continue;
-            int k = bidx[v];
+        if (my_ok) {
+            int k = bidx[my_v];
             if (k == 0x7fffffff) k = 0;
-            const float xv = xs[j * VQ_VT + v];
-            const float q = __ldg(&cb[(size_t)k * sub_d + j]);
-            const float diff = __fsub_rn(q, xv);
-            if (quant_out) {
-                long long b = n / T, t = n % T;
-                quant_out[(b * D + d0 + j) * (long long)T + t] = __fadd_rn(xv, diff);
+            for (int j = my_j0; j < sub_d; j += VQ_THREADS / VQ_VT) {
+                const float xv = xs[j * VQ_VT + my_v];
+                const float q = __ldg(&cb[(size_t)k * sub_d + j]);
+                const float diff = __fsub_rn(q, xv);
+                if (quant_out) quant_out[my_base + (size_t)j * T] = __fadd_rn(xv, diff);
+                local_err += (double)diff * (double)diff;
             }
-            local_err += (double)diff * (double)diff;
         }
     }
     if (sqerr_out) {
