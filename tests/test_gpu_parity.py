@@ -516,3 +516,21 @@ def test_flat_adam_matches_torch_adam_with_clipping():
         for sh, (pb, eb) in zip(shadow, ob.ema_state().items()):
             assert torch.allclose(sh, eb, rtol=2e-5, atol=1e-7), step
     assert float(ob.step_a) == 5.0
+
+
+def test_vq_codebook_view_at_unaligned_offset():
+    """Codebooks that are views into a flat parameter buffer (train_step.FlatAdam) may start at any 4-byte offset."""
+    torch.manual_seed(0)
+    K, D, B, Tn = 64, 32, 2, 37
+    flat = torch.randn(K * D + 3, device="cuda")
+    x = torch.randn(B, D, Tn, device="cuda")
+    outs = []
+    for off in (0, 1, 3):
+        cb = flat[off:off + K * D].view(K, D)
+        cb.copy_(flat[:K * D].view(K, D).clone() if off else cb)
+        idx = torch.empty(B * Tn, dtype=torch.int64, device="cuda")
+        _lib.check(_lib.lib().wae_vq_search(_lib.ptr(x), B, D, Tn, 0, D, cb.data_ptr(), K, _lib.ptr(idx), None, None, None,
+                                            _lib.stream_ptr()), "wae_vq_search")
+        ref = torch.cdist(x.permute(0, 2, 1).reshape(-1, D), cb).argmin(1)
+        assert (idx == ref).float().mean() > 0.99                      # cdist's arithmetic differs in the last ulp on near-ties
+        outs.append(idx)

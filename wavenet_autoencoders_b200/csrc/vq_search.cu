@@ -21,16 +21,19 @@
 namespace {
 
 constexpr int VQ_THREADS = 256;
-constexpr int VQ_VT = 64;    // vectors per block
 constexpr int VQ_KC = 128;   // codes per shared-memory chunk (16 lanes x 8 codes)
 constexpr int VQ_EP = VQ_KC + 4;  // es row pitch: keeps float4 alignment, cuts transpose-store conflicts to 4-way
 
 // dynamic smem: xs[sub_d][VQ_VT] | es[sub_d][VQ_EP] | e2s[VQ_KC] | x2s[VQ_VT] | best_idx[VQ_VT]
+// VPT vectors per thread: 4 (64 vectors per block) for throughput; 1 (16 per block) when there are so few vectors that 64 per
+// block would leave most SMs idle (N = 400 at BASELINE config 2: 7 blocks vs 25).
+template <int VPT>
 __global__ void __launch_bounds__(VQ_THREADS)
 vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int sub_d,
                  const float* __restrict__ cb, int K,
                  long long* __restrict__ idx_out, float* __restrict__ quant_out,
                  double* __restrict__ sqerr_out, int* __restrict__ counts_out) {
+    constexpr int VQ_VT = 16 * VPT;     // vectors per block
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                         // [sub_d][VQ_VT]
     float* es = xs + (size_t)sub_d * VQ_VT;   // [sub_d][VQ_KC]
@@ -50,8 +53,9 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
     const bool my_ok = my_n < N;
     const long long my_b = my_ok ? my_n / T : 0, my_t = my_ok ? my_n - my_b * T : 0;
     const size_t my_base = ((size_t)my_b * D + d0) * (size_t)T + (size_t)my_t;         // element (b, d0, t); + j * T per dimension
+#pragma unroll 4
     for (int j = my_j0; j < sub_d; j += VQ_THREADS / VQ_VT)
-        xs[j * VQ_VT + my_v] = my_ok ? x[my_base + (size_t)j * T] : 0.f;
+        xs[j * VQ_VT + my_v] = my_ok ? __ldg(&x[my_base + (size_t)j * T]) : 0.f;
     __syncthreads();
     if (tid < VQ_VT) {
         float s = 0.f;
@@ -63,18 +67,29 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
     }
 
     const int kx = tid & 15;   // code lane: codes kx*8 .. kx*8+7 of the chunk
-    const int vy = tid >> 4;   // vector group: vectors vy*4 .. vy*4+3
-    float best[4];
-    int besti[4];
+    const int vy = tid >> 4;   // vector group: vectors vy*VPT .. vy*VPT+VPT-1
+    float best[VPT];
+    int besti[VPT];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { best[i] = INFINITY; besti[i] = 0x7fffffff; }
+    for (int i = 0; i < VPT; ++i) { best[i] = INFINITY; besti[i] = 0x7fffffff; }
 
     for (int k0 = 0; k0 < K; k0 += VQ_KC) {
         __syncthreads();  // previous chunk fully consumed (and x2s visible on first pass)
-        for (int e = tid; e < sub_d * VQ_KC; e += VQ_THREADS) {
-            int kk = e / sub_d, j = e % sub_d;  // coalesced read of codebook rows
-            int k = k0 + kk;
-            es[j * VQ_EP + kk] = (k < K) ? cb[(size_t)k * sub_d + j] : 0.f;
+        // coalesced read of the chunk's codebook rows, several loads in flight per thread (one load per loop trip left the
+        // launch waiting on ~32 serial L2 round trips per chunk: 26 of the 29 us at N = 400)
+        if ((sub_d & 3) == 0 && (reinterpret_cast<uintptr_t>(cb) & 15) == 0) {
+#pragma unroll 4
+            for (int e4 = tid; e4 < sub_d * VQ_KC / 4; e4 += VQ_THREADS) {
+                const int e = e4 * 4, kk = e / sub_d, j = e - kk * sub_d, k = k0 + kk;
+                const float4 v = (k < K) ? __ldg(reinterpret_cast<const float4*>(cb + (size_t)k * sub_d + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                es[j * VQ_EP + kk] = v.x; es[(j + 1) * VQ_EP + kk] = v.y; es[(j + 2) * VQ_EP + kk] = v.z; es[(j + 3) * VQ_EP + kk] = v.w;
+            }
+        } else {
+#pragma unroll 4
+            for (int e = tid; e < sub_d * VQ_KC; e += VQ_THREADS) {
+                const int kk = e / sub_d, j = e - kk * sub_d, k = k0 + kk;
+                es[j * VQ_EP + kk] = (k < K) ? __ldg(&cb[(size_t)k * sub_d + j]) : 0.f;
+            }
         }
         __syncthreads();
         if (tid < VQ_KC) {  // ||e_k||^2 of this chunk, sequential fp32 (conflict-free column walk)
@@ -87,26 +102,33 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
         }
         __syncthreads();
 
-        float acc[4][8];
+        float acc[VPT][8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < VPT; ++i)
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-        for (int d = 0; d < sub_d; ++d) {
-            const float4 xv = *reinterpret_cast<const float4*>(&xs[d * VQ_VT + vy * 4]);
+#pragma unroll 4
+        for (int d = 0; d < sub_d; ++d) {      // one FMA chain per (vector, code) over d in order: the reference's summation order
+            float xr[VPT];
+            if (VPT == 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[d * VQ_VT + vy * 4]);
+                xr[0] = xv.x; xr[VPT > 1 ? 1 : 0] = xv.y; xr[VPT > 2 ? 2 : 0] = xv.z; xr[VPT > 3 ? 3 : 0] = xv.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < VPT; ++i) xr[i] = xs[d * VQ_VT + vy * VPT + i];
+            }
             const float4 ea = *reinterpret_cast<const float4*>(&es[d * VQ_EP + kx * 8]);
             const float4 eb = *reinterpret_cast<const float4*>(&es[d * VQ_EP + kx * 8 + 4]);
-            const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
             const float er[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < VPT; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(xr[i], er[j], acc[i][j]);
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float x2 = x2s[vy * 4 + i];
+        for (int i = 0; i < VPT; ++i) {
+            const float x2 = x2s[vy * VPT + i];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = k0 + kx * 8 + j;
@@ -120,14 +142,14 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
 
     // ---- argmin across the 16 code lanes (lexicographic on (dist, idx) = first minimum) ----
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < VPT; ++i) {
 #pragma unroll
         for (int off = 8; off >= 1; off >>= 1) {
             float od = __shfl_xor_sync(0xffffffffu, best[i], off);
             int oi = __shfl_xor_sync(0xffffffffu, besti[i], off);
             if (od < best[i] || (od == best[i] && oi < besti[i])) { best[i] = od; besti[i] = oi; }
         }
-        if (kx == 0) bidx[vy * 4 + i] = besti[i];
+        if (kx == 0) bidx[vy * VPT + i] = besti[i];
     }
     __syncthreads();
 
@@ -146,6 +168,7 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
         if (my_ok) {
             int k = bidx[my_v];
             if (k == 0x7fffffff) k = 0;
+#pragma unroll 4
             for (int j = my_j0; j < sub_d; j += VQ_THREADS / VQ_VT) {
                 const float xv = xs[j * VQ_VT + my_v];
                 const float q = __ldg(&cb[(size_t)k * sub_d + j]);
@@ -232,18 +255,23 @@ int wae_vq_search(const float* x, int B, int D, int T, int d0, int sub_d, const 
     const long long N = (long long)B * T;
     if (N == 0) return WAE_OK;
 
-    const size_t smem = ((size_t)sub_d * (VQ_VT + VQ_EP) + VQ_KC + VQ_VT) * sizeof(float) + VQ_VT * sizeof(int);
+    const int vpt = (N <= 148 * 64 / 2) ? 1 : 4;       // few vectors: 16 per block so that the launch covers more SMs
+    const int VT = 16 * vpt;
+    const size_t smem = ((size_t)sub_d * (VT + VQ_EP) + VQ_KC + VT) * sizeof(float) + VT * sizeof(int);
     static bool attr_set = false;
     if (!attr_set) {
-        WAE_CHECK_CUDA(cudaFuncSetAttribute(vq_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            200 * 1024));
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(vq_search_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(vq_search_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr_set = true;
     }
-    const long long blocks = (N + VQ_VT - 1) / VQ_VT;
+    const long long blocks = (N + VT - 1) / VT;
     WAE_REQUIRE(blocks <= 0x7fffffffLL, "wae_vq_search: too many vectors");
-    vq_search_kernel<<<(unsigned)blocks, VQ_THREADS, smem, stream>>>(
-        x, B, D, T, d0, sub_d, codebook, K, reinterpret_cast<long long*>(idx_out), quant_out, sqerr_out,
-        counts_out);
+    if (vpt == 4)
+        vq_search_kernel<4><<<(unsigned)blocks, VQ_THREADS, smem, stream>>>(x, B, D, T, d0, sub_d, codebook, K, reinterpret_cast<long long*>(idx_out),
+                                                                           quant_out, sqerr_out, counts_out);
+    else
+        vq_search_kernel<1><<<(unsigned)blocks, VQ_THREADS, smem, stream>>>(x, B, D, T, d0, sub_d, codebook, K, reinterpret_cast<long long*>(idx_out),
+                                                                           quant_out, sqerr_out, counts_out);
     WAE_CHECK_LAUNCH();
     return WAE_OK;
 }

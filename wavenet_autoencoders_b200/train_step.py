@@ -29,17 +29,20 @@ class FlatAdam:
         self._lib = _lib
         self.params = [p for p in model.parameters() if p.requires_grad]
         dev = self.params[0].device
-        n = sum(p.numel() for p in self.params)
-        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        ALIGN = 64                                   # floats: every parameter view starts 256-byte aligned (kernels use 16-byte loads)
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += -(-p.numel() // ALIGN) * ALIGN
+        self.offsets = offs
+        self.flat_p = torch.zeros(n, dtype=torch.float32, device=dev)
         self.flat_g = torch.zeros(n, dtype=torch.float32, device=dev)
         self.m, self.v = torch.zeros_like(self.flat_p), torch.zeros_like(self.flat_p)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, offs):
             k = p.numel()
             self.flat_p[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + k].view_as(p)
             p.grad = self.flat_g[off:off + k].view_as(p)
-            off += k
         self.lr, self.betas, self.eps, self.clip = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(clip or 0.0)
         self.step_a = torch.zeros(1, dtype=torch.float32, device=dev)       # step count lives on the device (CUDA-graph safe)
         self.step_b = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -50,11 +53,7 @@ class FlatAdam:
 
     def ema_state(self):
         """{parameter: shadow tensor} views into the flat shadow buffer (what clone_as_averaged_model copies, :353-360)."""
-        out, off = {}, 0
-        for p in self.params:
-            out[p] = self.ema[off:off + p.numel()].view_as(p)
-            off += p.numel()
-        return out
+        return {p: self.ema[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)}
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
