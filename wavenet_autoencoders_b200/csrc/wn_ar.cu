@@ -1511,6 +1511,7 @@ ar_gbias_kernel(const float* __restrict__ b1, const float* __restrict__ wg, cons
     for (int g = threadIdx.x; g < G; g += blockDim.x) {
         float acc = 0.f;
         if (wg != nullptr && gemb != nullptr)
+#pragma unroll 8
             for (int i = 0; i < Gi; ++i)
                 acc = fmaf(__ldg(&wg[((size_t)l * Gi + i) * G + g]), __ldg(&gemb[(size_t)b * Gi + i]), acc);
         gb[((size_t)l * B + b) * G + g] = __ldg(&b1[(size_t)l * G + g]) + acc;

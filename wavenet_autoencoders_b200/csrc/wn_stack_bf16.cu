@@ -230,9 +230,11 @@ gbias_bf16_kernel(const float* __restrict__ b1, const float* __restrict__ wg, co
         if (ch < H) {
             const int g = half * H + ch;
             float acc = 0.f;
-            if (wg != nullptr && gemb != nullptr)
-                for (int i = 0; i < Gi; ++i)
+            if (wg != nullptr && gemb != nullptr) {
+#pragma unroll 8
+                for (int i = 0; i < Gi; ++i)       // unrolled: the loads of 8 trips are in flight together (same FMA order)
                     acc = fmaf(__ldg(&wg[((size_t)l * Gi + i) * G + g]), __ldg(&gemb[(size_t)b * Gi + i]), acc);
+            }
             v = __ldg(&b1[(size_t)l * G + g]) + acc;
         }
         gb[((size_t)l * B + b) * 2 * Hh + o] = v;
