@@ -37,6 +37,7 @@ METRIC = "WaveNet-decoder samples/s (teacher-forced forward)"
 UNIT = "samples/s"
 B_PER_GPU, T_SAMPLES, FRAMES = 16, 16000, 100          # configs[1]: 16 x 1 s; 100 MFCC frames -> 25 latents -> 16000
 FLOP_PER_SAMPLE_LAYER = 557056                         # 2kRG + 2CG + 2HR + 2HS at hps/vqwae.json
+FLOP_PER_SAMPLE_SKIP = 2 * 128 * 256                   # the layer's skip 1x1 (2HS), executed inside the head kernel's K = L*H GEMM
 FLOP_PER_SAMPLE_TOTAL = 11403264                       # 20 layers + head (first conv on one-hot input = gather)
 
 
@@ -299,14 +300,23 @@ def main():
     layer_launches = max(int(n_kind[1]), 1)
     layer_ms = float(ms_kind[1]) / layer_launches
     n_layers = 20
-    flops_per_launch = B * T_SAMPLES * (FLOP_PER_SAMPLE_LAYER - 2 * 128 * 256 / n_layers)   # last layer has no residual 1x1
+    # FLOPs one layer launch EXECUTES: the layer's 2kRG + 2CG + 2HR.  Its skip 1x1 (2HS = 65,536 of SURVEY 8(d)'s 557,056 per
+    # sample per layer) runs in head_bf16_kernel as part of the K = L*H skip GEMM and is credited there, not here; the last
+    # layer has no residual 1x1.
+    flops_per_launch = B * T_SAMPLES * (FLOP_PER_SAMPLE_LAYER - FLOP_PER_SAMPLE_SKIP - 2 * 128 * 256 / n_layers)
+    head_flops = B * T_SAMPLES * (n_layers * FLOP_PER_SAMPLE_SKIP + 2 * 256 * 256 + 2 * 256 * 256)
     peak_tf, peak_hbm, peak_src = _peaks()
     achieved = flops_per_launch / (layer_ms * 1e-3) / 1e12
     roofline = {"kernel": "layer_bf16_v2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
                 "avg_launch_ms": layer_ms, "share_of_step": float(ms_kind[1]) / prof_total,
                 "head_share_of_step": float(ms_kind[2]) / prof_total, "prep_share_of_step": float(ms_kind[0]) / prof_total,
-                "step_frac_of_peak": value / world * FLOP_PER_SAMPLE_TOTAL / 1e12 / peak_tf}
+                "step_frac_of_peak": value / world * FLOP_PER_SAMPLE_TOTAL / 1e12 / peak_tf,
+                "flops_counted": "per launch: B*T*(2kRG + 2CG + 2HR) = 491,520/sample; the layer's skip 1x1 (65,536/sample) is "
+                                 "executed by and credited to the head kernel",
+                "head_frac": head_flops / (float(ms_kind[2]) / max(int(n_kind[2]), 1) * 1e-3) / 1e12 / peak_tf,
+                "stack_frac": B * T_SAMPLES * FLOP_PER_SAMPLE_TOTAL * prof_steps
+                              / ((float(ms_kind[0]) + float(ms_kind[1]) + float(ms_kind[2])) * 1e-3) / 1e12 / peak_tf}
     try:
         roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
