@@ -69,6 +69,11 @@ int wae_vq_search(const float* x, int B, int D, int T, int d0, int sub_d,
                   int64_t* idx_out, float* quant_out, double* sqerr_out, int32_t* counts_out,
                   void* stream);
 
+/* Kernel choice of wae_vq_search: 0 = automatic (default: a codebook-resident persistent kernel for many vectors when the slice
+ * fits shared memory, the chunked kernel otherwise), 1 = always the chunked kernel.  Both are bit-identical; the switch exists
+ * for the parity tests and the bench. */
+int wae_vq_set_variant(int variant);
+
 /*
  * EMA statistics for the *EMA VQ variants: dw[k][j] += sum_{n: idx[n]==k} x[n][d0+j]
  * (the reference's encodings.t() @ flat_in).  dw: (K, sub_d) fp32, caller zeroes.

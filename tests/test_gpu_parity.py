@@ -534,3 +534,46 @@ def test_vq_codebook_view_at_unaligned_offset():
         ref = torch.cdist(x.permute(0, 2, 1).reshape(-1, D), cb).argmin(1)
         assert (idx == ref).float().mean() > 0.99                      # cdist's arithmetic differs in the last ulp on near-ties
         outs.append(idx)
+
+
+def test_vq_resident_kernel_bit_exact_vs_oracle_and_chunked():
+    """Many vectors: wae_vq_search switches to the codebook-resident persistent kernel.  Codes and quantised values must equal
+    the oracle's AND the chunked kernel's bit for bit, for ragged tiles, K off the 128-code chunk, odd / wide slices (sub_d
+    not a multiple of 4, sub_d > 64: no register prefetch) and a codebook too large to stay resident (falls back)."""
+    rs = np.random.RandomState(3)
+    L = _lib.lib()
+    try:
+        for B, D, Tn, K in [(3, 64, 2001, 300), (2, 24, 3000, 100), (2, 7, 3000, 3), (2, 132, 2500, 64), (1, 64, 5000, 1024)]:
+            x = (rs.normal(size=(B, D, Tn)) * 0.5).astype(np.float32)
+            cb = (rs.normal(size=(K, D)) * 0.5).astype(np.float32)
+            oq, ol, op, oi = vq_oracle.vq_forward(x, cb)
+            mod = vqm.VectorQuantize(K, D).cuda()
+            outs = []
+            for variant in (0, 1):
+                _lib.check(L.wae_vq_set_variant(variant), "wae_vq_set_variant")
+                with torch.no_grad():
+                    mod.embedding.weight.copy_(torch.tensor(cb))
+                    q, loss, perp = mod(torch.tensor(x).cuda())
+                np.testing.assert_array_equal(mod.last_codes.cpu().numpy(), oi)
+                np.testing.assert_array_equal(q.cpu().numpy(), oq)
+                assert abs(float(loss) - float(ol)) <= 1e-5 * abs(float(ol))
+                assert abs(float(perp) - float(op)) <= 1e-4 * abs(float(op))
+                outs.append((mod.last_codes.clone(), q.clone()))
+            assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+        # sliced module (two 32-wide halves of a 64-channel latent), many vectors
+        x = (rs.normal(size=(4, 64, 2500)) * 0.5).astype(np.float32)
+        cb1 = (rs.normal(size=(256, 32)) * 0.5).astype(np.float32)
+        cb2 = (rs.normal(size=(256, 32)) * 0.5).astype(np.float32)
+        _lib.check(L.wae_vq_set_variant(0), "wae_vq_set_variant")
+        mod = vqm.SlicedVectorQuantize(256, 64).cuda()
+        with torch.no_grad():
+            mod.embedding1.weight.copy_(torch.tensor(cb1))
+            mod.embedding2.weight.copy_(torch.tensor(cb2))
+            q, loss, perp = mod(torch.tensor(x).cuda())
+        i1, _, _ = vq_oracle.search(x, cb1, 0, 32)
+        i2, _, _ = vq_oracle.search(x, cb2, 32, 32)
+        codes = mod.last_codes.cpu().numpy().reshape(-1, 2)
+        np.testing.assert_array_equal(codes[:, 0], np.asarray(i1).reshape(-1))
+        np.testing.assert_array_equal(codes[:, 1], np.asarray(i2).reshape(-1))
+    finally:
+        L.wae_vq_set_variant(0)

@@ -15,7 +15,8 @@
 // Layout: x is (B, D, T) -- consecutive vectors are consecutive in memory for a fixed feature row,
 // so a tile of 64 vectors loads/stores 256-byte coalesced runs per feature row.  The codebook chunk
 // is staged in shared memory transposed ([d][k]) so the 16 code-lanes of a half-warp read
-// conflict-free float4s; each thread keeps a 4-vector x 8-code register tile.
+// conflict-free float4s (lane kx owns codes 4kx..4kx+3 and 64+4kx..: contiguous 256-byte runs per read);
+// each thread keeps a 4-vector x 8-code register tile.
 #include "wae_common.cuh"
 
 namespace {
@@ -66,7 +67,10 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
         x2s[tid] = s;
     }
 
-    const int kx = tid & 15;   // code lane: codes kx*8 .. kx*8+7 of the chunk
+    // code lane: codes kx*4 .. kx*4+3 and 64 + kx*4 .. of the chunk.  The 16 lanes' float4 reads of a code row are then two
+    // contiguous 256-byte runs (conflict-free); 8 consecutive codes per lane put the lanes 32 bytes apart and made every such
+    // read a 2-way bank conflict -- ncu: 93 % of the shared-memory wavefront peak, 43 % of the wavefronts conflicts.
+    const int kx = tid & 15;
     const int vy = tid >> 4;   // vector group: vectors vy*VPT .. vy*VPT+VPT-1
     float best[VPT];
     int besti[VPT];
@@ -118,8 +122,8 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
 #pragma unroll
                 for (int i = 0; i < VPT; ++i) xr[i] = xs[d * VQ_VT + vy * VPT + i];
             }
-            const float4 ea = *reinterpret_cast<const float4*>(&es[d * VQ_EP + kx * 8]);
-            const float4 eb = *reinterpret_cast<const float4*>(&es[d * VQ_EP + kx * 8 + 4]);
+            const float4 ea = *reinterpret_cast<const float4*>(&es[d * VQ_EP + kx * 4]);
+            const float4 eb = *reinterpret_cast<const float4*>(&es[d * VQ_EP + 64 + kx * 4]);
             const float er[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
 #pragma unroll
             for (int i = 0; i < VPT; ++i)
@@ -131,8 +135,8 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
             const float x2 = x2s[vy * VPT + i];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int k = k0 + kx * 8 + j;
-                const float s = __fadd_rn(e2s[kx * 8 + j], x2);
+                const int kk = (j < 4) ? kx * 4 + j : 64 + kx * 4 + (j - 4), k = k0 + kk;
+                const float s = __fadd_rn(e2s[kk], x2);
                 const float dist = __fmaf_rn(-2.0f, acc[i][j], s);
                 // ascending k within a thread: strict '<' keeps the first minimum
                 if (k < K && dist < best[i]) { best[i] = dist; besti[i] = k; }
@@ -192,6 +196,185 @@ vq_search_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int s
     }
 }
 
+// Large-N variant: the WHOLE codebook slice stays in shared memory (transposed, with its norms) for the life of the block, and
+// the block walks 64-vector tiles persistently (grid = a multiple of the SM count).  The chunked kernel above re-stages and
+// re-norms 128 codes for every 64 vectors -- three block-wide barriers and a 32 KB transposing copy per 2048 FMAs per thread;
+// here a tile costs two barriers, the next tile's vectors are fetched into registers while the current one is searched, and
+// the gather of the winning codeword reads shared memory.  Same arithmetic, same order: bit-identical outputs.
+// dynamic smem: es[sub_d][KP] | e2s[Kpad] | xs[sub_d][64] | x2s[64] | bidx[64],  KP = Kpad + 4, Kpad = K rounded up to 128.
+constexpr int VQ_PT = 64;             // vectors per tile (16 vector groups x 4)
+constexpr int VQ_MAX_XPF = 16;        // prefetch registers per thread: sub_d <= 64 prefetches in registers, larger slices reload
+
+__global__ void __launch_bounds__(VQ_THREADS, 2)
+vq_search_resident_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int sub_d,
+                          const float* __restrict__ cb, int K, int Kpad,
+                          long long* __restrict__ idx_out, float* __restrict__ quant_out,
+                          double* __restrict__ sqerr_out, int* __restrict__ counts_out) {
+    extern __shared__ __align__(16) float smem[];
+    const int KP = Kpad + 4;
+    float* es = smem;                               // [sub_d][KP]
+    float* e2s = es + (size_t)sub_d * KP;           // [Kpad]
+    float* xs = e2s + Kpad;                         // [sub_d][VQ_PT]
+    float* x2s = xs + (size_t)sub_d * VQ_PT;        // [VQ_PT]
+    int* bidx = reinterpret_cast<int*>(x2s + VQ_PT);
+    __shared__ double werr[VQ_THREADS / 32];
+
+    const long long N = (long long)B * T;
+    const long long ntiles = (N + VQ_PT - 1) / VQ_PT;
+    const int tid = threadIdx.x;
+
+    // ---- codebook slice -> es[j][k] (zero rows for k >= K), then the norms: once per block ----
+    if ((sub_d & 3) == 0 && (reinterpret_cast<uintptr_t>(cb) & 15) == 0) {
+#pragma unroll 4
+        for (int e4 = tid; e4 < sub_d * Kpad / 4; e4 += VQ_THREADS) {
+            const int e = e4 * 4, k = e / sub_d, j = e - k * sub_d;
+            const float4 v = (k < K) ? __ldg(reinterpret_cast<const float4*>(cb + (size_t)k * sub_d + j)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            es[j * KP + k] = v.x; es[(j + 1) * KP + k] = v.y; es[(j + 2) * KP + k] = v.z; es[(j + 3) * KP + k] = v.w;
+        }
+    } else {
+#pragma unroll 4
+        for (int e = tid; e < sub_d * Kpad; e += VQ_THREADS) {
+            const int k = e / sub_d, j = e - k * sub_d;
+            es[j * KP + k] = (k < K) ? __ldg(&cb[(size_t)k * sub_d + j]) : 0.f;
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < Kpad; k += VQ_THREADS) {
+        float s = 0.f;
+        for (int j = 0; j < sub_d; ++j) {
+            const float v = es[j * KP + k];
+            s = __fadd_rn(s, __fmul_rn(v, v));
+        }
+        e2s[k] = s;
+    }
+
+    const int my_v = tid & (VQ_PT - 1), my_j0 = tid / VQ_PT;      // staging / output role: vector my_v, rows my_j0, my_j0 + 4, ...
+    const int kx = tid & 15, vy = tid >> 4;                        // search role: codes kx*4.. and 64+kx*4.. of each 128-chunk, vectors vy*4..
+    const bool pf_regs = sub_d <= 4 * VQ_MAX_XPF;
+    float xpf[VQ_MAX_XPF];
+    auto fetch = [&](long long tile, size_t& base, bool& ok) {     // global -> registers (or just the address when sub_d is large)
+        const long long n = tile * VQ_PT + my_v;
+        ok = tile < ntiles && n < N;
+        const long long b = ok ? n / T : 0, t = ok ? n - b * T : 0;
+        base = ((size_t)b * D + d0) * (size_t)T + (size_t)t;
+        if (pf_regs) {
+#pragma unroll
+            for (int i = 0; i < VQ_MAX_XPF; ++i) {
+                const int j = my_j0 + 4 * i;
+                xpf[i] = (ok && j < sub_d) ? __ldg(&x[base + (size_t)j * T]) : 0.f;
+            }
+        }
+    };
+    size_t base_next; bool ok_next;
+    fetch(blockIdx.x, base_next, ok_next);
+    double local_err = 0.0;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const size_t my_base = base_next;
+        const bool my_ok = ok_next;
+        __syncthreads();                    // previous tile's readers of xs / bidx are done (first trip: e2s visible)
+        if (pf_regs) {
+#pragma unroll
+            for (int i = 0; i < VQ_MAX_XPF; ++i) {
+                const int j = my_j0 + 4 * i;
+                if (j < sub_d) xs[j * VQ_PT + my_v] = xpf[i];
+            }
+        } else {
+            for (int j = my_j0; j < sub_d; j += 4) xs[j * VQ_PT + my_v] = my_ok ? __ldg(&x[my_base + (size_t)j * T]) : 0.f;
+        }
+        __syncthreads();
+        fetch(tile + gridDim.x, base_next, ok_next);               // in flight behind the search below
+        if (tid < VQ_PT) {
+            float s = 0.f;
+            for (int j = 0; j < sub_d; ++j) {
+                const float v = xs[j * VQ_PT + tid];
+                s = __fadd_rn(s, __fmul_rn(v, v));
+            }
+            x2s[tid] = s;
+        }
+        __syncthreads();
+
+        float best[4];
+        int besti[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { best[i] = INFINITY; besti[i] = 0x7fffffff; }
+        for (int k0 = 0; k0 < Kpad; k0 += VQ_KC) {
+            float acc[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            const float* ep = es + k0 + kx * 4;
+#pragma unroll 4
+            for (int d = 0; d < sub_d; ++d) {          // one FMA chain per (vector, code) over d in order: the reference's summation order
+                const float4 xv = *reinterpret_cast<const float4*>(&xs[d * VQ_PT + vy * 4]);
+                const float4 ea = *reinterpret_cast<const float4*>(&ep[d * KP]);
+                const float4 eb = *reinterpret_cast<const float4*>(&ep[d * KP + 64]);
+                const float xr[4] = {xv.x, xv.y, xv.z, xv.w};
+                const float er[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = __fmaf_rn(xr[i], er[j], acc[i][j]);
+            }
+            float e2r[8];
+            *reinterpret_cast<float4*>(&e2r[0]) = *reinterpret_cast<const float4*>(&e2s[k0 + kx * 4]);
+            *reinterpret_cast<float4*>(&e2r[4]) = *reinterpret_cast<const float4*>(&e2s[k0 + 64 + kx * 4]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float x2 = x2s[vy * 4 + i];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = k0 + ((j < 4) ? kx * 4 + j : 64 + kx * 4 + (j - 4));
+                    const float dist = __fmaf_rn(-2.0f, acc[i][j], __fadd_rn(e2r[j], x2));
+                    if (k < K && dist < best[i]) { best[i] = dist; besti[i] = k; }     // ascending k, strict '<': first minimum
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int off = 8; off >= 1; off >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, best[i], off);
+                const int oi = __shfl_xor_sync(0xffffffffu, besti[i], off);
+                if (od < best[i] || (od == best[i] && oi < besti[i])) { best[i] = od; besti[i] = oi; }
+            }
+            if (kx == 0) bidx[vy * 4 + i] = besti[i];
+        }
+        __syncthreads();
+
+        if (my_ok) {
+            int k = bidx[my_v];
+            if (k == 0x7fffffff) k = 0;         // all-NaN row (see the chunked kernel)
+            if (my_j0 == 0) {
+                const long long n = tile * VQ_PT + my_v;
+                if (idx_out) idx_out[n] = k;
+                if (counts_out) atomicAdd(&counts_out[k], 1);
+            }
+            if (quant_out != nullptr || sqerr_out != nullptr) {
+#pragma unroll 4
+                for (int j = my_j0; j < sub_d; j += 4) {
+                    const float xv = xs[j * VQ_PT + my_v];
+                    const float diff = __fsub_rn(es[j * KP + k], xv);
+                    if (quant_out) quant_out[my_base + (size_t)j * T] = __fadd_rn(xv, diff);
+                    local_err += (double)diff * (double)diff;
+                }
+            }
+        }
+    }
+    if (sqerr_out) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) local_err += __shfl_xor_sync(0xffffffffu, local_err, off);
+        if ((tid & 31) == 0) werr[tid >> 5] = local_err;
+        __syncthreads();
+        if (tid == 0) {
+            double s = 0.0;
+            for (int w = 0; w < VQ_THREADS / 32; ++w) s += werr[w];
+            atomicAdd(sqerr_out, s);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 vq_ema_stats_kernel(const float* __restrict__ x, int B, int D, int T, int d0, int sub_d,
                     const long long* __restrict__ idx, int K, float* __restrict__ dw) {
@@ -240,7 +423,25 @@ upsample_stage_kernel(const float* __restrict__ in, int rows, int Tin, int s, co
 
 }  // namespace
 
+static int vq_num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+static int g_vq_variant = 0;   // 0 = automatic, 1 = always the chunked kernel (wae_vq_set_variant; used by tests and the bench)
+
 extern "C" {
+
+int wae_vq_set_variant(int v) {
+    if (v != 0 && v != 1) return wae::set_error(WAE_ERR_ARG, "wae_vq_set_variant: 0 (automatic) or 1 (chunked kernel)");
+    g_vq_variant = v;
+    return WAE_OK;
+}
 
 int wae_vq_search(const float* x, int B, int D, int T, int d0, int sub_d, const float* codebook, int K,
                   int64_t* idx_out, float* quant_out, double* sqerr_out, int32_t* counts_out,
@@ -266,6 +467,22 @@ int wae_vq_search(const float* x, int B, int D, int T, int d0, int sub_d, const 
     }
     const long long blocks = (N + VT - 1) / VT;
     WAE_REQUIRE(blocks <= 0x7fffffffLL, "wae_vq_search: too many vectors");
+    // many vectors and a codebook slice that fits shared memory twice per SM: the persistent, codebook-resident kernel
+    const int Kpad = (K + VQ_KC - 1) / VQ_KC * VQ_KC;
+    const size_t smem_res = ((size_t)sub_d * (Kpad + 4) + Kpad + (size_t)sub_d * VQ_PT + VQ_PT) * sizeof(float) + VQ_PT * sizeof(int);
+    if (vpt == 4 && smem_res <= 110 * 1024 && g_vq_variant != 1) {
+        static bool res_attr_set = false;
+        if (!res_attr_set) {
+            WAE_CHECK_CUDA(cudaFuncSetAttribute(vq_search_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+            res_attr_set = true;
+        }
+        const long long ntiles = (N + VQ_PT - 1) / VQ_PT;
+        const long long grid = ntiles < 2LL * vq_num_sms() ? ntiles : 2LL * vq_num_sms();
+        vq_search_resident_kernel<<<(unsigned)grid, VQ_THREADS, smem_res, stream>>>(x, B, D, T, d0, sub_d, codebook, K, Kpad,
+                                                                                     reinterpret_cast<long long*>(idx_out), quant_out, sqerr_out, counts_out);
+        WAE_CHECK_LAUNCH();
+        return WAE_OK;
+    }
     if (vpt == 4)
         vq_search_kernel<4><<<(unsigned)blocks, VQ_THREADS, smem, stream>>>(x, B, D, T, d0, sub_d, codebook, K, reinterpret_cast<long long*>(idx_out),
                                                                            quant_out, sqerr_out, counts_out);
