@@ -139,7 +139,11 @@ __device__ __forceinline__ void load_w_chunk(float* Ws, const float* __restrict_
         const int kk = e / (PW / 4), c4 = (e % (PW / 4)) * 4;
         const bool ok = (k0 + kk < K) && (col0 + c4 < ncols);  // ncols % 4 == 0
         const float* src = ok ? &W[(size_t)(k0 + kk) * ld + col0 + c4] : W;
-        cp_async16(&Ws[kk * PW + c4], src, ok);
+        // Shared layout: thread tx of mma_chunk owns columns 8 tx .. 8 tx + 7; its first four live at [4 tx], its last four at
+        // [PW/2 + 4 tx], so that the 32 lanes' float4 reads of a row are two contiguous 512-byte runs.  (Stored at [8 tx] and
+        // [8 tx + 4] the lanes were 32 bytes apart and every read was a 2-way bank conflict -- the same pattern ncu showed at
+        // 93 % of the shared-memory wavefront peak in the VQ search, profiles/r1_vq_resident_ncu.txt.)
+        cp_async16(&Ws[kk * PW + ((c4 >> 2) & 1) * (PW / 2) + (c4 >> 3) * 4], src, ok);
     }
 }
 
@@ -148,8 +152,8 @@ __device__ __forceinline__ void mma_chunk(float (&acc)[8][8], const float* As, c
     for (int kk = 0; kk < KC; ++kk) {
         const float4 a0 = *reinterpret_cast<const float4*>(&As[kk * AP + ty * 8]);
         const float4 a1 = *reinterpret_cast<const float4*>(&As[kk * AP + ty * 8 + 4]);
-        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk * PW + tx * 8]);
-        const float4 w1 = *reinterpret_cast<const float4*>(&Ws[kk * PW + tx * 8 + 4]);
+        const float4 w0 = *reinterpret_cast<const float4*>(&Ws[kk * PW + tx * 4]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&Ws[kk * PW + PW / 2 + tx * 4]);
         const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
         const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
