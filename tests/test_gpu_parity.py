@@ -577,3 +577,40 @@ def test_vq_resident_kernel_bit_exact_vs_oracle_and_chunked():
         np.testing.assert_array_equal(codes[:, 1], np.asarray(i2).reshape(-1))
     finally:
         L.wae_vq_set_variant(0)
+
+
+def test_graphed_forward_matches_eager():
+    """GraphedForward (the inference forward + NLL captured as one CUDA graph) returns what the eager call returns, also after
+    new inputs are copied into the captured buffers (pinned host tensors included)."""
+    from wavenet_autoencoders_b200.graphed import GraphedForward
+    from wavenet_autoencoders_b200.losses import teacher_forced_nll
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    cfg = T.CONFIGS["tiny"]
+    torch.manual_seed(0)
+    m = VQVAE(c_in=39, hid=cfg["cin_channels"], K=32, wavenet=WaveNet(**cfg), encoder_hid=48).eval()
+    m.load_state_dict(T.synth_state_dict(m, 5))
+    m = m.cuda()
+    m.wavenet.precision = "bf16"
+    g0 = load_golden("vqvae_tiny")
+    idx = torch.tensor(g0["idx"]).cuda()
+    mfcc = torch.tensor(g0["mfcc"]).cuda()
+    spk = torch.tensor(g0["g"]).cuda()
+    gf = GraphedForward(m, idx, mfcc, spk)
+    assert gf.launches and gf.launches > 0
+    gen = torch.Generator().manual_seed(7)
+    for trial in range(3):
+        if trial:
+            idx_h = torch.randint(0, cfg["out_channels"], idx.shape, generator=gen).pin_memory()
+            mfcc_h = torch.randn(mfcc.shape, generator=gen).pin_memory()
+            spk_h = torch.randint(0, cfg["n_speakers"], spk.shape, generator=gen).pin_memory()
+        else:
+            idx_h, mfcc_h, spk_h = idx, mfcc, spk
+        logits, vq_loss, perp, nll = gf(idx_h, mfcc_h, spk_h)
+        with torch.no_grad():
+            y, vl, pp = m(idx_h.cuda(), mfcc_h.cuda(), spk_h.cuda())
+            ref_nll = teacher_forced_nll(y, idx_h.cuda())
+        assert torch.equal(logits, y)
+        assert abs(float(nll) - float(ref_nll)) <= 1e-6 * max(1.0, abs(float(ref_nll)))
+        assert abs(float(vq_loss) - float(vl)) <= 1e-6 * max(1.0, abs(float(vl)))
+        assert abs(float(perp) - float(pp)) <= 1e-5 * max(1.0, abs(float(pp)))

@@ -1,0 +1,61 @@
+"""Inference forward replayed as one CUDA graph (additive API; the reference has no counterpart).
+
+A teacher-forced forward of the VQ-WAE is ~75 launches (11 encoder layers, the VQ search, 3 upsampler stages, the prep kernels,
+20 residual layers, the head, the NLL).  Launched eagerly from Python after a host synchronisation -- which every evaluation
+step has, to read its loss -- the short frame-rate kernels at the front are issued more slowly than they execute and the GPU
+idles between them.  Shapes are static per model and batch, so the whole forward is captured once and replayed; inputs are
+copied into the captured buffers (from pinned host memory or from the device).  Same kernels, same results as the eager call.
+Weights are read through the packed copies made at capture time: re-capture after changing parameters.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .losses import teacher_forced_nll
+
+
+class GraphedForward:
+    """``GraphedForward(model, idx, mfcc, g)`` captures ``model(idx, mfcc, g)`` (+ the teacher-forced NLL of vqwae_train.py:760-766)
+    for the shapes of the example inputs; calling it with new inputs of the same shapes copies them in, replays the graph and
+    returns ``(logits, vq_loss, perplexity, nll)`` -- tensors owned by the graph, overwritten by the next call.
+
+    ``model`` is a ``vqvae_model.VQVAE`` (or any module with the same ``forward(x, c, g)``) in eval mode on a CUDA sm_100 device;
+    ``idx`` are the (B,T) int64 mu-law classes (or the (B,O,T) one-hot tensor), ``mfcc`` the encoder input, ``g`` speaker ids."""
+
+    def __init__(self, model, idx, mfcc, g, with_nll: bool = True, warmup: int = 2):
+        if not (idx.is_cuda and mfcc.is_cuda and g.is_cuda):
+            raise _lib.WaeError("GraphedForward: example inputs must be CUDA tensors (no CPU fallback)")
+        if model.training:
+            raise RuntimeError("GraphedForward captures the inference forward: call model.eval() first")
+        self.model = model
+        self.idx, self.mfcc, self.g = idx.clone(), mfcc.clone(), g.clone()
+        classes = self.idx if not torch.is_floating_point(self.idx) else None
+        self.with_nll = bool(with_nll and classes is not None)
+
+        def run():
+            with torch.no_grad():
+                logits, vq_loss, perp = model(self.idx, self.mfcc, self.g)
+                nll = teacher_forced_nll(logits, classes) if self.with_nll else None
+            return logits, vq_loss, perp, nll
+
+        side = torch.cuda.Stream(device=idx.device)
+        side.wait_stream(torch.cuda.current_stream(idx.device))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):              # weight packing, workspace and allocator warm-up outside the capture
+                run()
+        torch.cuda.current_stream(idx.device).wait_stream(side)
+        torch.cuda.synchronize(idx.device)
+        self.launches = None
+        n0 = _lib.launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.logits, self.vq_loss, self.perp, self.nll = run()
+        self.launches = _lib.launch_count() - n0          # this library's kernels inside one replay
+
+    def __call__(self, idx, mfcc, g):
+        self.idx.copy_(idx, non_blocking=True)
+        self.mfcc.copy_(mfcc, non_blocking=True)
+        self.g.copy_(g, non_blocking=True)
+        self.graph.replay()
+        return self.logits, self.vq_loss, self.perp, self.nll
