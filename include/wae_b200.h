@@ -305,6 +305,19 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
                     int32_t* out_idx, float* out_dense,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Waveform post-processing after autoregressive synthesis, one launch (replaces synthesis.py:382-394: argmax of the one-hot
+ * output on the host, nnmnkwii P.inv_mulaw_quantize / P.inv_mulaw, audio.inv_preemphasis = lfilter([1], [1, -coef]), division by
+ * hparams.global_gain_scale).
+ *   in      : in_kind 0: (B,T) int64 sampled classes (what wae_ar_generate returns); 1: (B,T) fp32 mu-law companded samples in
+ *             [-1,1] (input_type "mulaw"); 2: (B,T) fp32 raw samples
+ *   mu      : the value the reference passes as `mu` (hparams.quantize_channels, synthesis.py:384,386)
+ *   preemphasis_coef : 0 = no inverse pre-emphasis;  gain : <= 0 = no division
+ *   out     : (B,T) fp32
+ */
+int wae_synth_postprocess(const void* in, int in_kind, int B, int T, int mu, float preemphasis_coef, float gain,
+                          float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -614,3 +614,33 @@ def test_graphed_forward_matches_eager():
         assert abs(float(nll) - float(ref_nll)) <= 1e-6 * max(1.0, abs(float(ref_nll)))
         assert abs(float(vq_loss) - float(vl)) <= 1e-6 * max(1.0, abs(float(vl)))
         assert abs(float(perp) - float(pp)) <= 1e-5 * max(1.0, abs(float(pp)))
+
+
+def test_synthesis_postprocess_matches_oracle():
+    """wae_synth_postprocess (inverse mu-law + inverse pre-emphasis + gain, synthesis.py:382-394) against the float64 numpy /
+    scipy restatement: all three input types, ragged T (shorter than the 256 segments, not a multiple of them), T = 48000."""
+    from oracle import postprocess_oracle as po
+    from wavenet_autoencoders_b200.postprocess import waveform_from_synthesis
+    rs = np.random.RandomState(11)
+    for B, Tn in [(1, 1), (3, 100), (2, 1000), (4, 48000)]:
+        idx = rs.randint(0, 256, size=(B, Tn))
+        for post, coef, gain in [(None, 0.85, 0.0), ("inv_preemphasis", 0.85, 0.0), ("inv_preemphasis", 0.97, 0.55)]:
+            got = waveform_from_synthesis(torch.tensor(idx).cuda(), "mulaw-quantize", 256, post, coef, gain).cpu().numpy()
+            ref = po.waveform(idx, "mulaw-quantize", 256, post, coef, gain)
+            assert got.shape == (B, Tn) and got.dtype == np.float32
+            np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5 * max(1.0, float(np.abs(ref).max())))
+            if post is None and gain == 0.0:
+                np.testing.assert_array_equal(got, ref.astype(np.float32))          # the table is exact to fp32 rounding
+        y = rs.uniform(-1, 1, size=(B, Tn)).astype(np.float32)
+        for kind in ("mulaw", "raw"):
+            got = waveform_from_synthesis(torch.tensor(y).cuda()[:, None, :], kind, 256, "inv_preemphasis", 0.85, 2.0).cpu().numpy()
+            ref = po.waveform(y, kind, 256, "inv_preemphasis", 0.85, 2.0)
+            np.testing.assert_allclose(got, ref, rtol=0, atol=2e-5 * max(1.0, float(np.abs(ref).max())))
+    # one-hot input takes the argmax like the reference (synthesis.py:383)
+    idx = rs.randint(0, 256, size=(2, 50))
+    onehot = torch.nn.functional.one_hot(torch.tensor(idx), 256).float().transpose(1, 2).cuda()
+    a = waveform_from_synthesis(onehot, "mulaw-quantize", 256)
+    b = waveform_from_synthesis(torch.tensor(idx).cuda(), "mulaw-quantize", 256)
+    assert torch.equal(a, b)
+    with pytest.raises(_lib.WaeError):
+        waveform_from_synthesis(torch.tensor(idx), "mulaw-quantize", 256)             # CPU tensor: no fallback

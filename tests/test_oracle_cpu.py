@@ -171,3 +171,25 @@ def test_oracle_vqvae_composition():
     x = np.eye(cfg["out_channels"], dtype=np.float32)[g["idx"]].transpose(0, 2, 1)
     y = wo.forward(p, x, quant, g["g"])
     assert rel_err(y, g["logits"]) < 2e-5
+
+
+def test_postprocess_oracle_known_values():
+    """The restated mu-law inverse (nnmnkwii's published formula; parity unpinned) at values derivable by hand, its consistency
+    with the forward companding of the same library, and the IIR against a direct recurrence."""
+    from oracle import postprocess_oracle as po
+    mu = 256
+    assert po.inv_mulaw(0.0, mu) == 0.0
+    assert abs(po.inv_mulaw(1.0, mu) - 1.0) < 1e-12 and abs(po.inv_mulaw(-1.0, mu) + 1.0) < 1e-12
+    assert abs(po.inv_mulaw_quantize(mu, mu) - 1.0) < 1e-12 and abs(po.inv_mulaw_quantize(0, mu) + 1.0) < 1e-12
+    assert po.inv_mulaw_quantize(128, mu) == 0.0                        # 2 * 128 / 256 - 1 = 0
+    x = np.linspace(-1, 1, 1001)
+    y = np.sign(x) * np.log1p(mu * np.abs(x)) / np.log1p(mu)            # mulaw(x, mu)
+    np.testing.assert_allclose(po.inv_mulaw(y, mu), x, atol=1e-12)
+    # silence maps to class 127 under mulaw_quantize = int((y + 1) / 2 * mu) (wavenet.py:288, audio.py:96) and decodes to ~0
+    assert int((0.0 + 1) / 2 * mu * (1 - 1e-9)) == 127 and abs(po.inv_mulaw_quantize(127, mu)) < 2e-4
+    rs = np.random.RandomState(0)
+    v = rs.normal(size=(2, 300))
+    w = np.zeros_like(v)
+    for t in range(300):
+        w[:, t] = v[:, t] + 0.85 * (w[:, t - 1] if t else 0.0)
+    np.testing.assert_allclose(po.inv_preemphasis(v, 0.85), w, atol=1e-12)
