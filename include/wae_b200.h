@@ -221,6 +221,8 @@ int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const f
  *   wae_train_dx_accum  dx[t] = (dxo[t] + sum_j dxcat[t+(kw-1-j)d][j*R:(j+1)*R]) * scale;  dC (B,T,C) fp32 += dxcat[t][kw*R:kw*R+C]
  */
 int wae_train_im2col(const void* x, const void* c, int B, int T, int R, int Cp, int kw, int dil, void* out, void* stream);
+/* (B,O,T) fp32 gradient of the logits -> (B,T,O) bf16 (transposing cast feeding the head's backward GEMMs; O even). */
+int wae_train_transpose_cast(const float* in, int B, int O, int T, void* out, void* stream);
 int wae_train_gate_bwd(const void* z, const float* gb, const void* dh_a, long long dh_a_stride, const void* dh_b, int B, int T,
                        int H, void* dz, float* dgb, void* stream);
 int wae_train_dx_accum(const void* dxcat, const void* dxo, int B, int T, int R, int C, int Cp, int kw, int dil, float scale,

@@ -644,3 +644,16 @@ def test_synthesis_postprocess_matches_oracle():
     assert torch.equal(a, b)
     with pytest.raises(_lib.WaeError):
         waveform_from_synthesis(torch.tensor(idx), "mulaw-quantize", 256)             # CPU tensor: no fallback
+
+
+def test_training_transpose_cast_matches_torch():
+    """wae_train_transpose_cast: (B,O,T) fp32 -> (B,T,O) bf16, bit-identical to torch's transposing copy (round to nearest even),
+    ragged tiles included."""
+    for B, O, Tn in [(1, 2, 1), (3, 30, 77), (2, 256, 1000), (2, 66, 33)]:
+        torch.manual_seed(B + O + Tn)
+        x = torch.randn(B, O, Tn, device="cuda")
+        out = torch.full((B, Tn, O), float("nan"), dtype=torch.bfloat16, device="cuda")
+        _lib.check(_lib.lib().wae_train_transpose_cast(_lib.ptr(x), B, O, Tn, _lib.ptr(out), _lib.stream_ptr()), "wae_train_transpose_cast")
+        ref = torch.empty(B, Tn, O, dtype=torch.bfloat16, device="cuda")
+        ref.copy_(x.transpose(1, 2))
+        assert torch.equal(out, ref)

@@ -313,3 +313,42 @@ extern "C" int wae_adam_step(float* p, const float* g, float* m, float* v, long 
     WAE_CHECK_LAUNCH();
     return WAE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// d logits (B,O,T) fp32 (what autograd hands the backward) -> (B,T,O) bf16, the row-major operand of the head's backward GEMMs.
+// torch's strided copy_ does this transposing cast in 385 us at 8 x 256 x 7680 (tools/train_profile.py); a 32 (time) x 64
+// (channel) shared-memory tile reads 128-byte runs along T and writes 128-byte runs along O: two HBM passes (94 MB).
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+transpose_cast_kernel(const float* __restrict__ in, int O, int T, __nv_bfloat16* __restrict__ out) {
+    __shared__ float tile[64][33];
+    const int b = blockIdx.z, t0 = blockIdx.x * 32, o0 = blockIdx.y * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float* src = in + (size_t)b * O * T;
+    __nv_bfloat16* dst = out + (size_t)b * T * O;
+#pragma unroll
+    for (int j = ty; j < 64; j += 8) {
+        const int o = o0 + j, t = t0 + tx;
+        tile[j][tx] = (o < O && t < T) ? __ldg(&src[(size_t)o * T + t]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = ty; j < 32; j += 8) {
+        const int t = t0 + j, o = o0 + 2 * tx;
+        if (t < T && o + 1 < O)
+            *reinterpret_cast<__nv_bfloat162*>(&dst[(size_t)t * O + o]) = __floats2bfloat162_rn(tile[2 * tx][j], tile[2 * tx + 1][j]);
+    }
+}
+}  // namespace
+
+extern "C" int wae_train_transpose_cast(const float* in, int B, int O, int T, void* out, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(in && out, "wae_train_transpose_cast: null pointer");
+    WAE_REQUIRE(B > 0 && B <= 65535 && O > 0 && O % 2 == 0 && T > 0, "wae_train_transpose_cast: need 0 < B <= 65535, even O (B=%d O=%d T=%d)", B, O, T);
+    WAE_REQUIRE((O + 63) / 64 <= 65535, "wae_train_transpose_cast: O too large");
+    transpose_cast_kernel<<<dim3((unsigned)((T + 31) / 32), (unsigned)((O + 63) / 64), (unsigned)B), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        in, O, T, static_cast<__nv_bfloat16*>(out));
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}

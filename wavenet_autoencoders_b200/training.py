@@ -158,7 +158,12 @@ def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_need
 
         # ---- head: logits = W4 relu(W3 relu(s) + b3) + b4,  s = (sum_l Ws_l h_l + bs_l) * sqrt(1/L) ----
         dY = torch.empty(dlogits.shape[0], dlogits.shape[2], dlogits.shape[1], dtype=cdt, device=dlogits.device)
-        dY.copy_(dlogits.transpose(1, 2))                                                  # (B,T,O): transpose + cast in one pass
+        if cdt == BF and dlogits.is_cuda and dlogits.dtype == torch.float32 and O % 2 == 0 and dlogits.shape[0] <= 65535:
+            dl = dlogits.contiguous()                                                      # (B,T,O): tiled transpose + cast, one launch
+            _lib.check(_lib.lib().wae_train_transpose_cast(_lib.ptr(dl), dl.shape[0], O, dl.shape[2], _lib.ptr(dY),
+                                                           _lib.stream_ptr(dl.device)), "wae_train_transpose_cast")
+        else:
+            dY.copy_(dlogits.transpose(1, 2))                                              # (B,T,O): transpose + cast in one pass
         Hcat = h_all.permute(1, 2, 0, 3).reshape(B, T, L * Hp)                            # (B,T,L*Hp)
         Wscat = torch.cat([F.pad(lw(l, 6)[:, :, 0], (0, Hp - H)) for l in range(L)], dim=1).to(cdt)   # (S, L*Hp)
         bs_sum = torch.zeros(S, dtype=adt, device=dY.device)
