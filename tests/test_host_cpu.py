@@ -39,6 +39,22 @@ def test_no_cpu_fallback():
         vqm.VectorQuantize(8, 4)(torch.zeros(1, 4, 3))
     with pytest.raises(_lib.WaeError):
         vqm.SlicedVectorQuantize(8, 4).encode_indices(torch.zeros(1, 4, 3))
+    # the additive entry points added later obey the same rule: CUDA tensors or a loud error, never a CPU path
+    from wavenet_autoencoders_b200.graphed import GraphedForward
+    from wavenet_autoencoders_b200.losses import teacher_forced_nll
+    from wavenet_autoencoders_b200.postprocess import waveform_from_synthesis
+    with pytest.raises(_lib.WaeError):
+        waveform_from_synthesis(torch.zeros(1, 8, dtype=torch.long))
+    with pytest.raises(_lib.WaeError):
+        teacher_forced_nll(torch.zeros(1, 4, 8), torch.zeros(1, 8, dtype=torch.long))
+    with pytest.raises(_lib.WaeError):
+        GraphedForward(m, torch.zeros(1, 32, dtype=torch.long), torch.zeros(1, 39, 4), torch.zeros(1, 1, dtype=torch.long))
+    # ... and no GPU is touched before the arguments are validated
+    with pytest.raises(ValueError):
+        waveform_from_synthesis(torch.zeros(1, 8, dtype=torch.long), input_type="alaw")
+    assert lib.wae_synth_postprocess(None, 0, 1, 8, 256, 0.0, 0.0, None, None) != 0           # rejected (no sm_100 device / null)
+    assert lib.wae_vq_set_variant(2) != 0 and b"wae_vq_set_variant" in lib.wae_last_error()
+    assert lib.wae_vq_set_variant(0) == 0
 
 
 def test_state_dict_layout_matches_reference():
