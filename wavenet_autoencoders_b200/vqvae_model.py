@@ -111,11 +111,13 @@ class VQVAE(nn.Module):
         quant, vq_loss, perp = self.vq(self.encoder(c))
         return self.wavenet(x, quant, g, softmax), vq_loss, perp
 
-    def incremental_forward(self, initial_input, c, g, T, softmax, quantize, tqdm, log_scale_min):
+    def incremental_forward(self, initial_input, c, g, T, softmax, quantize, tqdm, log_scale_min, **extra):
+        """vqvae_model.py:74-80.  ``extra``: the additive keywords of ``WaveNet.incremental_forward`` (``uniforms``,
+        ``generator``, ``return_indices``), passed through."""
         with torch.no_grad():
             quant, _, _ = self.vq(self.encoder(c))
             return self.wavenet.incremental_forward(initial_input, c=quant, g=g, T=T, softmax=softmax,
-                                                    quantize=quantize, tqdm=tqdm, log_scale_min=log_scale_min)
+                                                    quantize=quantize, tqdm=tqdm, log_scale_min=log_scale_min, **extra)
 
     def encode(self, x):
         with torch.no_grad():
