@@ -290,6 +290,12 @@ def main():
         graphed, graphed_err = None, f"{type(e).__name__}: {e}"[:300]
         torch.cuda.synchronize()
 
+    if dist is not None:                                         # every rank must take the same branch: timed() holds collectives
+        flag = torch.tensor([1 if graphed is not None else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and graphed is not None:
+            graphed, graphed_err = None, "graph capture failed on another rank"
+
     def step_e2e_graphed():
         return float(graphed(idx_p, mfcc_p, g_p)[3].item())      # H2D copies into the captured buffers, replay, D2H of the loss
 
