@@ -1,4 +1,10 @@
-"""Role-level cycle breakdown of layer_bf16_kernel (1-CTA variant). GPU box only."""
+"""Role-level cycle breakdown of the residual-layer kernels (needs a WAE_LAYER_PROF=1 build).  GPU box only.
+
+    WAE_LAYER_PROF=1 python -m wavenet_autoencoders_b200.build --force; python tools/layer_profile.py [-1 | -2 | 0 | 1 | 2 | 4]
+
+The argument is wae_set_layer_cluster's: -1 version 2 (default kernel), -2 version 2 on CTA pairs (per 256-sample super-tile).
+For the version-2 kernels E1 is also split: a = waiting for the previous tile's TMA stores + barrier, b = TMEM loads + gate math +
+st.shared, rest = fences, barrier, TMA store issue, barrier arrival."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -20,8 +26,8 @@ with torch.no_grad():
     L.wae_layer_set_profile_buffer(None)
 p = buf.view(148, 16).double().cpu()
 names = ["prod wait-empty", "prod total", "mma wait-full", "mma wait-epi1", "mma wait-epi2", "mma issue", "mma total", "tiles",
-         "epi wait-acc1", "epi E1", "epi wait-acc2", "epi E2", "epi prefetch", "epi total"]
+         "epi wait-acc1", "epi E1", "epi wait-acc2", "epi E2", "epi prefetch", "epi total", "epi E1 a (store wait)", "epi E1 b (gate)"]
 tiles = p[:, 7].clamp(min=1)
 print("counters of layer 5 (dilation 32), cycles")
 for i, n in enumerate(names):
-    print(f"{n:18s} mean {p[:, i].mean().item():10.0f}  per tile {(p[:, i] / tiles).mean().item():9.0f}")
+    print(f"{n:22s} mean {p[:, i].mean().item():10.0f}  per tile {(p[:, i] / tiles).mean().item():9.0f}")

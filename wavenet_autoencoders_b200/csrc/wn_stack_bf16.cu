@@ -793,7 +793,7 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
     for (int i = threadIdx.x - 64; i < a.R; i += 32 * LAYER_EPI_WARPS) sb_bo[i] = __ldg(a.bo + i);
     asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
     int it = 0;
-    long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0; const long long e_t0 = clock64(); LPROF_BEGIN();
+    long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0, e_e1a = 0, e_e1b = 0; const long long e_t0 = clock64(); LPROF_BEGIN();
     for (int unit = unit0; unit < nunits; unit += unit_stride, ++it) {
         const int tile = kPair ? unit * 2 + crank : unit;
         const bool valid = tile < ntiles;                      // a pair's odd tail: computed on zero-filled input, never stored
@@ -841,6 +841,7 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
             if (threadIdx.x == 64) tma_store_wait_read();
             asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
         }
+        LPROF(e_e1a);                                          // E1 segment a: wait for the previous tile's TMA stores + barrier
         if (a.Hb == 0) {
             gate_chunks(0, a.Hp, 0, a.Ha);
         } else {
@@ -853,6 +854,7 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
             tc_fence_after();
             gate_chunks(a.Ha, a.Hp, 0, a.Hb);
         }
+        LPROF(e_e1b);                                          // E1 segment b: TMEM loads, gate math, st.shared (the rest of E1: fences, barrier, TMA store issue, arrival)
         tc_fence_before();
         fence_proxy_async_smem();
         asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
@@ -908,7 +910,8 @@ __device__ __forceinline__ void layer_epilogue_v2(const LayerArgs& a, int ntiles
     if (threadIdx.x == 64) tma_store_wait_all();
     if (LPROF_ON && a.prof && threadIdx.x == 64) {
         long long* pp = a.prof + blockIdx.x * 16;
-        pp[8] = e_w1; pp[9] = e_e1; pp[10] = e_w2; pp[11] = e_e2; pp[12] = 0; pp[13] = clock64() - e_t0;
+        pp[8] = e_w1; pp[9] = e_e1 + e_e1a + e_e1b; pp[10] = e_w2; pp[11] = e_e2; pp[12] = 0; pp[13] = clock64() - e_t0;
+        pp[14] = e_e1a; pp[15] = e_e1b;
     }
 }
 
