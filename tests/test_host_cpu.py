@@ -236,3 +236,24 @@ def test_hand_derived_stack_backward_matches_autograd_float64(cfg_name):
             continue
         assert b is not None, n
         assert rel_err(b.numpy(), a.numpy()) < 1e-9, (n, rel_err(b.numpy(), a.numpy()))
+
+
+def test_library_sass_contains_tcgen05_tma_and_cluster_instructions():
+    """The built library really is sm_100a tensor-core / TMA code: cuobjdump's SASS of libwae_b200.so holds the tcgen05 MMA
+    (UTCHMMA, also .2CTA), TMEM loads (LDTM), tcgen05.commit (UTCBAR), TMA tensor loads / stores (UTMALDG / UTMASTG), bulk
+    copies (UBLKCP, the AR kernel's weight stream) and the AR kernel's mma.sync (HMMA.16816.F32.BF16) -- the mnemonics
+    /opt/skills/guides/B200_PROFILING.md names as proof.  Skipped where cuobjdump is not installed."""
+    import re
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or ("/usr/local/cuda/bin/cuobjdump" if os.path.exists("/usr/local/cuda/bin/cuobjdump") else None)
+    if exe is None:
+        pytest.skip("cuobjdump not available")
+    so = os.path.join(ROOT, "wavenet_autoencoders_b200", "libwae_b200.so")
+    r = subprocess.run([exe, "-sass", so], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert "sm_100a" in r.stdout
+    counts = {m: len(re.findall(r"\b" + re.escape(m), r.stdout))
+              for m in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA.16816.F32.BF16")}
+    missing = [m for m, n in counts.items() if n == 0]
+    assert not missing, f"SASS lacks {missing}: {counts}"
