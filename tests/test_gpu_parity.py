@@ -657,3 +657,190 @@ def test_training_transpose_cast_matches_torch():
         ref = torch.empty(B, Tn, O, dtype=torch.bfloat16, device="cuda")
         ref.copy_(x.transpose(1, 2))
         assert torch.equal(out, ref)
+
+
+# ------------------------------------------------------------------ round 2: the benchmarked shapes, pinned to the reference
+def _b3(t):
+    """(2, ...) -> ragged batch of 3: [u0, u1, u0] (utterance 2 must reproduce utterance 0 exactly)."""
+    return torch.cat([t, t[:1]], dim=0).contiguous()
+
+
+# measured on B200 (GPUTEST r2): the bf16 tensor-core AR kernel is within 1.0e-2 (vqwae) / 1.2e-2 (inwae) of the reference's
+# fp32 logits over all 2560 steps; asserted at ~2x that
+TOL_AR_BF16 = 2.5e-2
+
+
+@pytest.mark.parametrize("case,prec,cluster,upc,tol", [
+    ("wavenet_vqwae_b2", "bf16", 8, 8, TOL_AR_BF16), ("wavenet_vqwae_b2", "bf16", 16, 8, TOL_AR_BF16),
+    ("wavenet_vqwae_b2", "bf16", 16, 2, TOL_AR_BF16), ("wavenet_vqwae_b2", "fp32", 16, 2, 1e-4),
+    ("wavenet_vqwae_b2", "bf16-simt", 8, 2, TOL_AR_BF16),
+    ("wavenet_inwae_b2", "bf16", 8, 8, TOL_AR_BF16), ("wavenet_inwae_b2", "fp32", 16, 2, 1e-4)])
+def test_incremental_logits_at_benchmarked_shapes(case, prec, cluster, upc, tol):
+    """L1 at the shapes bench.py times (hps/vqwae.json, hps/inae_hp.json; 20 layers, R = 256, dilations to 512), against
+    the REFERENCE's incremental_forward output (golden `inc_logits`): T = 2560 so that the 1025-row history of the d = 512
+    layers wraps twice and the t-1024 taps are live, B = 3 ragged ([u0, u1, u0]: a partially filled utterance group / a
+    second cluster with one utterance).  "bf16": ar_mma_kernel (the 226.5 KB shared layout, cp.async.bulk weight rings,
+    history rings in global memory); "fp32" / "bf16-simt": ar_kernel<float/bf16>."""
+    g, cfg, m, x, c, spk = _inputs(case)
+    if prec.endswith("-simt"):
+        prec, m.ar_impl = "bf16", "simt"
+    m.precision, m.ar_cluster, m.ar_utts_per_cluster = prec, cluster, upc
+    x3, c3, s3 = _b3(x), _b3(c), _b3(spk)
+    Tn, s = int(g["T"]), int(g["stride"])
+    y = m.incremental_forward(initial_input=x3[:, :, :1], c=c3, g=s3, T=Tn, test_inputs=x3, softmax=False, quantize=False)
+    want_kernel = "fp32" if prec == "fp32" else ("bf16" if m.ar_impl == "simt" else "bf16mma")
+    if case == "wavenet_inwae_b2" and prec == "bf16":
+        want_kernel = "bf16"       # H = 184 over 8 CTAs gives odd slice boundaries: the model falls to ar_kernel<bf16> (wavenet.py)
+    assert m.last_ar_variant[0] == want_kernel and m.last_ar_variant[1] == cluster, m.last_ar_variant
+    assert y.shape == (3, cfg["out_channels"], Tn)
+    assert torch.equal(y[2], y[0])                                    # same utterance in another slot / cluster: bit-identical
+    err = rel_err(y[:2, :, ::s].cpu().numpy(), g["inc_logits"])
+    late = rel_err(y[:2, :, 2048::s].cpu().numpy(), g["inc_logits"][:, :, 2048 // s:])     # after both ring wraps
+    print(f"{case} {prec} cluster {cluster} upc {upc}: rel err {err:.3e} (t >= 2048: {late:.3e})")
+    assert err < tol and late < tol, (err, late)
+
+
+def test_incremental_free_running_vqwae_first_divergence():
+    """L3 at the benchmarked shape: free-running categorical synthesis, 2 utterances x 2560 steps on the golden's uniform
+    stream.  The reference was driven by the same inverse-CDF sampler (tools/make_golden.py sampled_free_run), so the fp32
+    kernel's classes must equal the reference's for the whole run (first divergence-free window = T).  The bf16 tensor-core
+    kernel's window is REPORTED (its logits differ at the 1e-2 level, so it leaves the reference's trajectory early; north
+    star: "identical sampled samples ... for the first divergence-free window")."""
+    g, cfg, m, x, c, spk = _inputs("wavenet_vqwae_b2")
+    Tn, B = int(g["T"]), int(g["B"])
+    u = torch.rand(Tn, B, generator=torch.Generator().manual_seed(int(g["sampled_seed"]))).cuda()
+    want = g["sampled"].astype(np.int64)
+
+    def first_div(got):
+        ne = (got != want).any(0)
+        return int(np.argmax(ne)) if ne.any() else Tn
+    m.precision, m.ar_cluster = "fp32", 16
+    out = m.incremental_forward(initial_input=x[:, :, :1], c=c, g=spk, T=Tn, softmax=True, quantize=True, uniforms=u,
+                                return_indices=True)
+    d32 = first_div(out.cpu().numpy())
+    m.precision, m.ar_cluster = "bf16", None
+    out = m.incremental_forward(initial_input=x[:, :, :1], c=c, g=spk, T=Tn, softmax=True, quantize=True, uniforms=u,
+                                return_indices=True)
+    d16 = first_div(out.cpu().numpy())
+    print(f"first divergence from the reference's sampled classes: fp32 kernel {d32} / {Tn}, bf16 mma kernel {d16} / {Tn}")
+    assert d32 == Tn, f"fp32 AR kernel left the reference trajectory at step {d32}"
+    assert d16 >= 1
+
+
+@pytest.mark.parametrize("case,cfg_name", [("wavenet_tiny_mol_ar", "tiny_mol"), ("wavenet_tiny_gauss_ar", "tiny_gauss")])
+def test_incremental_scalar_samplers_match_reference(case, cfg_name):
+    """Scalar-input synthesis with the fused mixture-of-logistics (mixture.py:118-156) and mixture-of-Gaussians
+    (mixture.py:221-270) samplers against the reference's incremental_forward fed the same draws (uniform_ / Normal.sample
+    patched in tools/make_golden.py)."""
+    g = load_golden(case)
+    cfg = T.CONFIGS[cfg_name]
+    m = build_model(cfg_name, int(g["seed"]), "cuda")
+    B, Tn = int(g["B"]), int(g["T"])
+    _, _, c, spk = T.synth_inputs(cfg, B, Tn, int(g["in_seed"]))
+    for prec, atol in (("fp32", 2e-4), ("bf16", None)):
+        m.precision, m.ar_cluster = prec, 8
+        y = m.incremental_forward(initial_input=None, c=c.cuda(), g=spk.cuda(), T=Tn, uniforms=torch.tensor(g["u"]).cuda(),
+                                  log_scale_min=-7.0)
+        assert y.shape == (B, 1, Tn) and float(y.abs().max()) <= 1.0
+        if atol is not None:
+            np.testing.assert_allclose(y[:, 0].cpu().numpy(), g["samples"], atol=atol)
+        else:       # bf16 weights: same trajectory until rounding flips a mixture indicator; the first steps must agree closely
+            np.testing.assert_allclose(y[:, 0, :8].cpu().numpy(), g["samples"][:, :8], atol=5e-2)
+
+
+@pytest.mark.parametrize("case", ["vq_ema_plain", "vq_ema_sliced"])
+def test_vq_ema_modules_match_reference(case):
+    """VectorQuantizeEMA / SlicedVectorQuantizeEMA (vector_quantization.py:156-235, :257-306) in training mode for three steps
+    and one eval step against the REFERENCE classes' own outputs and state (golden): codes via wae_vq_search, per-code sums
+    via wae_vq_ema_stats, the codebook overwritten before the gather."""
+    g = load_golden(case)
+    K, D, steps = int(g["K"]), int(g["D"]), int(g["steps"])
+    mod = getattr(vqm, str(g["kind"]))(K, D).cuda().train()
+    with torch.no_grad():
+        for n, p_ in mod.named_parameters():
+            p_.copy_(torch.tensor(g["param_" + n.replace(".", "__")]))
+    for s in range(steps + 1):
+        if s == steps:
+            mod.eval()
+        with torch.no_grad():
+            q, loss, perp = mod(torch.tensor(g[f"x{s}"]).cuda())
+        np.testing.assert_allclose(q.cpu().numpy(), g[f"quant{s}"], rtol=2e-5, atol=1e-6)
+        assert abs(float(loss) - float(g[f"vq_loss{s}"])) <= 1e-5 * float(g[f"vq_loss{s}"])
+        assert abs(float(perp) - float(g[f"perp{s}"])) <= 1e-5 * float(g[f"perp{s}"])
+        state = dict(mod.named_parameters())
+        state.update(dict(mod.named_buffers()))
+        for n, t in state.items():
+            np.testing.assert_allclose(t.detach().cpu().numpy(), g[f"after{s}_" + n.replace(".", "__")], rtol=2e-5, atol=1e-7,
+                                       err_msg=f"{n} after step {s}")
+
+
+def test_vqvae_forward_at_config2_shape_matches_reference():
+    """BASELINE configs[1] at its real shape -- VQVAE(WaveNet(**vqwae), c_in=39, hid=64, K=256, encoder_hid=256), 100 MFCC frames
+    -> 25 latents -> T = 16000 -- against the reference's own forward (golden): VQ codes BIT-IDENTICAL to the reference's argmin,
+    latents / quantised latents, vq_loss, perplexity, fp32 logits <= 1e-3 (north star), bf16 logits within the stated bound."""
+    g = load_golden("vqvae_vqwae")
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    cfg = T.CONFIGS["vqwae"]
+    torch.manual_seed(0)
+    m = VQVAE(c_in=39, hid=cfg["cin_channels"], K=256, wavenet=WaveNet(**cfg), encoder_hid=256).eval()
+    m.load_state_dict(T.synth_state_dict(m, int(g["seed"])))
+    m = m.cuda()
+    idx = torch.tensor(g["idx"].astype(np.int64)).cuda()
+    x = torch.nn.functional.one_hot(idx, cfg["out_channels"]).float().transpose(1, 2).contiguous()
+    mfcc, spk = torch.tensor(g["mfcc"]).cuda(), torch.tensor(g["g"]).cuda()
+    s = int(g["stride"])
+    with torch.no_grad():
+        lat = m.encoder(mfcc)
+        assert rel_err(lat.cpu().numpy(), g["latents"]) < 1e-5
+        y, vq_loss, perp = m(x, mfcc, spk)
+        np.testing.assert_array_equal(m.vq.last_codes.cpu().numpy(), g["codes"])          # bit-identical code indices
+        quant = m.encode(mfcc)
+        assert rel_err(quant.cpu().numpy(), g["quant"]) < 1e-5
+        assert rel_err(y[:, :, ::s].cpu().numpy(), g["logits"]) < 1e-4
+        assert abs(float(y.double().sum()) - float(g["logits_sum"])) < 1e-4 * abs(float(g["logits_sum"])) + 1.0
+        assert abs(vq_loss.item() - float(g["vq_loss"])) < 1e-5 * float(g["vq_loss"])
+        assert abs(perp.item() - float(g["perp"])) < 1e-5 * float(g["perp"])
+        m.wavenet.precision = "bf16"
+        y16, _, _ = m(idx, mfcc, spk)
+        np.testing.assert_array_equal(m.vq.last_codes.cpu().numpy(), g["codes"])
+        err = rel_err(y16[:, :, ::s].cpu().numpy(), g["logits"])
+        print(f"vqvae_vqwae bf16 rel err {err:.3e}")
+        assert err < TOL_BF16, err
+
+
+def test_packed_weights_follow_raw_pointer_optimizer_updates():
+    """FlatAdam / a replayed training graph rewrite parameters through raw pointers (no _version bump, same
+    data_ptr); the packed-weight caches of WaveNet.forward / incremental_forward and the encoder's transposed weights must
+    still notice.  eval -> optimiser step -> eval must change the logits, and equal a freshly built model's on the new weights."""
+    from wavenet_autoencoders_b200.train_step import FlatAdam
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    cfg = T.CONFIGS["tiny"]
+
+    def make():
+        torch.manual_seed(0)
+        mm = VQVAE(c_in=39, hid=cfg["cin_channels"], K=32, wavenet=WaveNet(**cfg), encoder_hid=48).eval()
+        mm.load_state_dict(T.synth_state_dict(mm, 5))
+        return mm.cuda()
+    m = make()
+    g0 = load_golden("vqvae_tiny")
+    idx, mfcc, spk = torch.tensor(g0["idx"]).cuda(), torch.tensor(g0["mfcc"]).cuda(), torch.tensor(g0["g"]).cuda()
+    x = torch.nn.functional.one_hot(idx, cfg["out_channels"]).float().transpose(1, 2).contiguous()
+    opt = FlatAdam(m, lr=1e-2, clip=0.0)
+    for prec in ("fp32", "bf16"):
+        m.wavenet.precision = prec
+        with torch.no_grad():
+            y0 = m(x, mfcc, spk)[0].clone()
+            lat0 = m.encoder(mfcc).clone()
+        opt.flat_g.normal_(0, 1.0)                      # a gradient for every parameter; step() writes through raw pointers
+        opt.step()
+        with torch.no_grad():
+            y1 = m(x, mfcc, spk)[0]
+            lat1 = m.encoder(mfcc)
+        assert not torch.allclose(lat0, lat1) and not torch.allclose(y0, y1), prec
+        fresh = make()
+        fresh.load_state_dict(m.state_dict())
+        fresh.wavenet.precision = prec
+        with torch.no_grad():
+            assert torch.equal(fresh(x, mfcc, spk)[0], y1), prec

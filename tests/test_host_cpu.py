@@ -88,7 +88,8 @@ def test_api_errors_match_reference():
     m = build_model("tiny", 1)
     x, _, c, g = T.synth_inputs(T.CONFIGS["tiny"], 1, 32, 0)
     with pytest.raises(Exception):                      # upsampled c length != T (wavenet.py:196-200)
-        m(x[:, :, :31], c, g)
+        with torch.no_grad():
+            m(x[:, :, :31], c, g)
     m.train()
     with pytest.raises(RuntimeError):                   # conv.py:19-20
         m.incremental_forward(c=c, g=g, T=32)
@@ -99,6 +100,14 @@ def test_training_path_is_differentiable_and_matches_oracle():
     cfg = T.CONFIGS["tiny"]
     m = build_model("tiny", int(g["seed"])).train()
     x, _, c, spk = T.synth_inputs(cfg, int(g["B"]), int(g["T"]), int(g["in_seed"]))
+    # default train_impl="kernels": a gradient request that the CUDA kernels cannot serve (CPU tensors, fp32) fails loudly, in
+    # train and in eval mode -- no silent torch-op fallback; the composite is an explicit opt-in (test infrastructure)
+    for mode in (m.train, m.eval):
+        mode()
+        with pytest.raises(_lib.WaeError, match="no silent fallback"):
+            m(x, c, spk)
+    m.train()
+    m.train_impl = "autograd"
     y = m(x, c, spk)
     assert rel_err(y.detach().numpy(), g["logits"]) < 2e-5
     y.square().mean().backward()

@@ -8,7 +8,8 @@ from oracle import sampling, torch_port, vq_oracle
 from oracle import wavenet_oracle as wo
 from wavenet_autoencoders_b200 import testing as T
 
-WAVENET_CASES = ["wavenet_tiny", "wavenet_tiny_k2", "wavenet_tiny_mol", "wavenet_vqwae", "wavenet_inwae"]
+WAVENET_CASES = ["wavenet_tiny", "wavenet_tiny_k2", "wavenet_tiny_mol", "wavenet_vqwae", "wavenet_inwae", "wavenet_vqwae_b2",
+                 "wavenet_inwae_b2"]
 
 
 def _setup(case):
@@ -46,13 +47,33 @@ def test_torch_port_forward_matches_reference(case):
     assert rel_err(y[:, :, ::s], g["logits"]) < 2e-5
 
 
-@pytest.mark.parametrize("case", ["wavenet_tiny", "wavenet_tiny_k2"])
+@pytest.mark.parametrize("case", ["wavenet_tiny", "wavenet_tiny_k2", "wavenet_vqwae_b2", "wavenet_inwae_b2"])
 def test_oracle_incremental_matches_reference(case):
+    """*_b2: the benchmarked 20-layer shapes, two utterances, T = 2560 -- the d = 512 history (1025 rows) wraps and the
+    taps at t-1024 are live (conv.py:34-46)."""
     g, cfg, p, x, c, spk = _setup(case)
     Tn = int(g["T"])
+    s = int(g["stride"])
     forced = np.ascontiguousarray(x.transpose(0, 2, 1))
     y = wo.incremental_forward(p, Tn, c=c, g=spk, initial_input=forced[:, 0], test_inputs=forced)   # (B,T,O)
-    assert rel_err(y.transpose(0, 2, 1), g["inc_logits"]) < 2e-5
+    assert rel_err(y.transpose(0, 2, 1)[:, :, ::s], g["inc_logits"]) < 2e-5
+    if "sampled" in g:
+        # L3: free-running categorical synthesis on the golden's uniform stream; the reference was driven by the same
+        # inverse-CDF sampler, so the classes must agree for the whole run (first divergence-free window = T)
+        u = torch.rand(Tn, int(g["B"]), generator=torch.Generator().manual_seed(int(g["sampled_seed"]))).numpy()
+        O = cfg["out_channels"]
+        picks = []
+
+        def sampler(t, logits):
+            k = np.array([sampling.categorical_from_uniform(logits[b], float(u[t, b])) for b in range(logits.shape[0])])
+            picks.append(k)
+            return np.eye(O, dtype=np.float32)[k]
+        wo.incremental_forward(p, Tn, c=c, g=spk, initial_input=forced[:, 0], test_inputs=forced[:, :1], sampler=sampler)
+        got = np.stack(picks, 1)
+        first_div = int(np.argmax((got != g["sampled"]).any(0))) if (got != g["sampled"]).any() else Tn
+        assert first_div == Tn, f"first divergence at step {first_div}"
+    if "free_probs" not in g:
+        return
     # free-running with softmax feedback (softmax=True, quantize=False): probabilities fed back as the next input
     Tf = int(g["Tfree"])
     probs = wo.incremental_forward(
@@ -193,3 +214,66 @@ def test_postprocess_oracle_known_values():
     for t in range(300):
         w[:, t] = v[:, t] + 0.85 * (w[:, t - 1] if t else 0.0)
     np.testing.assert_allclose(po.inv_preemphasis(v, 0.85), w, atol=1e-12)
+
+
+# ------------------------------------------------------------------ round-2 pins: Gaussian sampler, scalar-input AR, EMA VQ
+def test_gauss_sampler_matches_reference():
+    """oracle/sampling.gauss_from_draws against mixture.py:221-270 run with its uniform_/Normal.sample draws supplied."""
+    g = load_golden("sampler_gauss")
+    for tag in ("mix", "c2", "c3"):
+        got = np.array([sampling.gauss_from_draws(y, u) for y, u in zip(g[f"y_{tag}"], g[f"u_{tag}"])], np.float32)
+        np.testing.assert_allclose(got, g[f"x_{tag}"], rtol=2e-6, atol=2e-7, err_msg=tag)
+        assert np.abs(g[f"x_{tag}"]).max() <= 1.0 and (np.abs(g[f"x_{tag}"]) < 1.0).any()
+
+
+@pytest.mark.parametrize("case,fn", [("wavenet_tiny_mol_ar", "mol_from_uniform"), ("wavenet_tiny_gauss_ar", "gauss_from_draws")])
+def test_oracle_scalar_ar_matches_reference(case, fn):
+    """Free-running synthesis of scalar-input models: the oracle loop + oracle sampler against the reference's
+    incremental_forward fed the same draws (wavenet.py:324-331)."""
+    g = load_golden(case)
+    cfg = T.CONFIGS[str(g["cfg"])]
+    m = build_model(str(g["cfg"]), int(g["seed"]))
+    p = wo.extract_params({k: v.numpy() for k, v in m.state_dict().items()}, cfg["layers"], cfg["stacks"])
+    B, Tn = int(g["B"]), int(g["T"])
+    _, _, c, spk = T.synth_inputs(cfg, B, Tn, int(g["in_seed"]))
+    u = g["u"]
+    draw = getattr(sampling, fn)
+    y = wo.incremental_forward(p, Tn, c=c.numpy(), g=spk.numpy(), initial_input=np.zeros((B, 1), np.float32),
+                               test_inputs=np.zeros((B, 1, 1), np.float32),
+                               sampler=lambda t, lg: np.array([[draw(lg[b], u[t, b])] for b in range(B)], np.float32))
+    np.testing.assert_allclose(y[:, :, 0], g["samples"], atol=5e-5)
+
+
+@pytest.mark.parametrize("case", ["vq_ema_plain", "vq_ema_sliced"])
+def test_vq_ema_oracle_matches_reference(case):
+    """vq_oracle.ema_update (+ search) against the reference's EMA classes run in training mode for several steps
+    (vector_quantization.py:156-235, :257-306; run on the CPU through a harness-side `.cuda()` shim, tools/make_golden.py):
+    cluster sizes, per-code sums, the codebook overwritten BEFORE the gather, commitment-only loss."""
+    g = load_golden(case)
+    K, D, steps = int(g["K"]), int(g["D"]), int(g["steps"])
+    sliced = str(g["kind"]).startswith("Sliced")
+    names = ["1", "2"] if sliced else [""]
+    sd = D // len(names)
+    cbs = [g[f"param_embedding{n}__weight"].copy() for n in names]
+    sizes = [np.zeros(K, np.float32) for _ in names]
+    ws = [np.zeros((K, sd), np.float32) for _ in names]
+    for s in range(steps + 1):
+        x = g[f"x{s}"]
+        B, _, Tn = x.shape
+        flat = x.transpose(0, 2, 1).reshape(-1, D)
+        q = np.empty((B * Tn, D), np.float32)
+        perp = 0.0
+        for i, n in enumerate(names):
+            idx, _, _ = vq_oracle.search(x, cbs[i], i * sd, sd)
+            if s < steps:                                    # training-mode forward
+                sizes[i], ws[i], cbs[i] = vq_oracle.ema_update(flat[:, i * sd:(i + 1) * sd], idx, K, sizes[i], ws[i], 0.99)
+            q[:, i * sd:(i + 1) * sd] = cbs[i][idx]
+            perp += float(vq_oracle.perplexity(idx, K))
+            np.testing.assert_allclose(cbs[i], g[f"after{s}_embedding{n}__weight"], rtol=2e-5, atol=1e-7)
+            np.testing.assert_allclose(sizes[i], g[f"after{s}_ema_cluster_size{n}"], rtol=2e-5, atol=1e-9)
+            np.testing.assert_allclose(ws[i], g[f"after{s}_ema_w{n}"], rtol=2e-5, atol=1e-7)
+        quant = (flat + (q - flat)).reshape(B, Tn, D).transpose(0, 2, 1)
+        np.testing.assert_allclose(quant, g[f"quant{s}"], rtol=2e-5, atol=1e-6)
+        loss = 0.25 * np.mean((q.astype(np.float64) - flat) ** 2)
+        assert abs(loss - float(g[f"vq_loss{s}"])) <= 1e-5 * float(g[f"vq_loss{s}"])
+        assert abs(perp - float(g[f"perp{s}"])) <= 1e-5 * float(g[f"perp{s}"])

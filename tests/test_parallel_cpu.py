@@ -26,6 +26,7 @@ def _worker(rank, world, port, q):
         torch.manual_seed(0)
         m = WaveNet(**T.CONFIGS["tiny"]).train()
         m.load_state_dict(T.synth_state_dict(m, 1))
+        m.train_impl = "autograd"        # CPU / gloo: the torch-op composite, opted into explicitly (host logic under test)
         # each rank: its own utterance shard of a global batch of 4
         ids = parallel.shard_utterances(4, world, rank)
         x, _, c, g = T.synth_inputs(T.CONFIGS["tiny"], 4, 64, 0)
@@ -58,6 +59,7 @@ def test_dp_allreduce_and_sharding_world2():
     torch.manual_seed(0)
     m = WaveNet(**T.CONFIGS["tiny"]).train()
     m.load_state_dict(T.synth_state_dict(m, 1))
+    m.train_impl = "autograd"
     x, _, c, g = T.synth_inputs(T.CONFIGS["tiny"], 4, 64, 0)
     y = m(x, c, g)
     (y.square().sum() / (4 * y[0].numel())).backward()

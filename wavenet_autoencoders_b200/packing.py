@@ -74,9 +74,25 @@ def stack_shape(wn) -> StackShape:
     return StackShape(len(dil), kw, R, G, S, C, Gi, O, Oin, dil)
 
 
+_generation = 0
+
+
+def bump_generation() -> None:
+    """Parameters were rewritten behind autograd's back (through raw pointers, by a kernel or a CUDA-graph replay:
+    train_step.FlatAdam.step, GraphedTrainStep.__call__) -- neither ``data_ptr`` nor ``_version`` moves then, so every cache of
+    packed / transposed weights keys on this counter as well."""
+    global _generation
+    _generation += 1
+
+
+def generation() -> int:
+    return _generation
+
+
 def params_fingerprint(wn) -> tuple:
-    """Changes whenever any parameter of the module is modified in place or replaced."""
-    return tuple((p.data_ptr(), p._version) for p in wn.parameters())
+    """Changes whenever any parameter of the module is modified in place, replaced, or rewritten through raw pointers by this
+    package's optimiser (bump_generation)."""
+    return (_generation,) + tuple((p.data_ptr(), p._version) for p in wn.parameters())
 
 
 def _ru(x, m):

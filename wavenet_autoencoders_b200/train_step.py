@@ -7,7 +7,7 @@ from __future__ import annotations
 import torch
 from torch.nn import functional as F
 
-from . import parallel
+from . import packing, parallel
 
 
 def make_optimizer(model, lr=4e-4, capturable=False):
@@ -75,6 +75,7 @@ class FlatAdam:
                                         ptr(self.ema), self.ema_decay or 0.0, st),
                         "wae_adam_step")
         self.step_a.copy_(self.step_b)
+        packing.bump_generation()        # parameters changed through raw pointers: packed-weight caches must re-pack
 
 
 def train_step(model, opt, idx, mfcc, g, clip=100.0, world=1, timers=None):
@@ -125,4 +126,5 @@ class GraphedTrainStep:
         self.mfcc.copy_(mfcc, non_blocking=True)
         self.g.copy_(g, non_blocking=True)
         self.graph.replay()
+        packing.bump_generation()        # the replayed optimiser kernels rewrote every parameter in place
         return self.loss

@@ -70,16 +70,18 @@ class Encoder(nn.Module):
 
     def _wt(self, weight):
         """(Cout, Cin[, k]) -> (Cin, k, Cout) fp32 for the kernel, cached until the parameter is modified in place or replaced."""
+        from . import packing
         cache = self.__dict__.setdefault("_wt_cache", {})
         key = id(weight)
         hit = cache.get(key)
-        if hit is not None and hit[0] == weight._version and hit[1].device == weight.device and hit[2] is weight:
+        ver = (weight._version, weight.data_ptr(), packing.generation())   # generation: raw-pointer updates (FlatAdam, graph replay)
+        if hit is not None and hit[0] == ver and hit[1].device == weight.device and hit[2] is weight:
             return hit[1]
         w3 = weight.detach().float()
         if w3.dim() == 2:
             w3 = w3.unsqueeze(-1)
         wt = w3.permute(1, 2, 0).contiguous()
-        cache[key] = (weight._version, wt, weight)
+        cache[key] = (ver, wt, weight)
         return wt
 
     def _kernels_ok(self, x):

@@ -54,10 +54,10 @@ class ResidualConv1dGLU(nn.Module):
         self.conv1x1_skip = Conv1d1x1(gate_out_channels, skip_out_channels, bias=bias)
 
     def forward(self, x, c=None, g=None):
-        """Differentiable single-layer evaluation (torch autograd ops).
+        """Differentiable single-layer evaluation with torch ops: the reference composite (modules.py:115-163).
 
-        Only the TRAINING path uses this (backward kernels are not native yet, DESIGN.md "C3");
-        inference goes through WaveNet.forward -> libwae_b200 and never reaches this method.
+        Test infrastructure / fp32 debugging only -- reached solely through ``WaveNet.train_impl = "autograd"``.  Inference and
+        the default training path go through WaveNet.forward -> libwae_b200 (wn_stack_*.cu, wn_bwd.cu) and never get here.
         """
         T = x.size(-1)
         z = self.conv(F.dropout(x, p=self.dropout, training=self.training))

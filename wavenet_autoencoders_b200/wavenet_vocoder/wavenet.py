@@ -6,7 +6,12 @@ What differs is where the arithmetic runs:
 
 * ``forward`` (no autograd)        -> wae_stack_forward_f32 / wae_stack_forward_bf16: one fused kernel per layer
 * ``incremental_forward``          -> wae_ar_generate: ONE persistent cluster kernel for all T steps
-* ``forward`` while training       -> torch autograd ops (backward kernels are the next row)
+* ``forward`` when a gradient is needed (grad mode on and any of x, c, g or the parameters requires it, in train OR eval
+  mode like the reference) -> ``training.stack_forward_train``: the tcgen05 forward that keeps its activations + the
+  hand-derived backward on this library's kernels (``precision="bf16"``, CUDA).  The torch-op composite
+  (``_forward_autograd``) is test infrastructure / an fp32 debugging aid and runs only when ``train_impl="autograd"`` is
+  set explicitly; with the default ``train_impl="kernels"`` a gradient request on a CPU tensor or with
+  ``precision="fp32"`` raises instead of silently taking another path.
 
 ``precision`` ("fp32" | "bf16", default from $WAE_B200_PRECISION or "fp32") selects the fp32-faithful
 CUDA-core kernels (reference parity to ~1e-5) or the tcgen05 tensor-core kernels.
@@ -82,6 +87,7 @@ class WaveNet(nn.Module):
         self.ar_impl = "mma"               # "mma" | "simt" (bf16 precision only)
         self.train_impl = "kernels"        # "kernels": tcgen05 forward + GEMM backward (bf16, CUDA) | "autograd": torch ops
         self.last_sampled_indices = None  # (B,T) int32 of the last categorical incremental_forward
+        self.last_ar_variant = None       # (weight type, cluster size, utterances per cluster) the last synthesis ran with
         self._packs = {}
         self._ws = packing.WorkspaceCache()
 
@@ -146,7 +152,11 @@ class WaveNet(nn.Module):
         """x (B,O,T) one-hot / (B,1,T) scalar; c (B,C,Tc); g ids or (B,Gi[,1])  ->  (B,O,T) (wavenet.py:164-216).
         Additive: x may also be the (B,T) integer mu-law classes themselves (what the one-hot tensor is built from); the
         bf16 inference path then gathers first-conv rows by index and never materialises the (B,O,T) one-hot."""
-        autograd = self.training and torch.is_grad_enabled()
+        # the reference stays differentiable in eval mode too: pick the path by who needs a gradient, not by self.training
+        autograd = torch.is_grad_enabled() and (
+            (torch.is_floating_point(x) and x.requires_grad) or (c is not None and c.requires_grad)
+            or (g is not None and torch.is_floating_point(g) and g.requires_grad)
+            or any(p.requires_grad for p in self.parameters()))
         x_idx = None
         if not torch.is_floating_point(x) and x.dim() == 2 and not self.scalar_input:
             if autograd or self.precision != "bf16" or not x.is_cuda:
@@ -170,12 +180,25 @@ class WaveNet(nn.Module):
                 print(f"c {c.size() } x {x.size()}")
                 raise Exception
         if autograd:
-            if self.precision == "bf16" and x.is_cuda and self.train_impl == "kernels":
-                # tcgen05 forward that keeps its activations + hand-derived backward on them (training.py)
-                from .. import training
-                out = training.stack_forward_train(self, x, c, gvec)
-                return F.softmax(out, dim=1) if softmax else out
-            return self._forward_autograd(x, c, gvec, softmax)
+            if self.train_impl == "autograd":        # explicit opt-in only: torch-op composite (tests, fp32 debugging)
+                return self._forward_autograd(x, c, gvec, softmax)
+            if self.train_impl != "kernels":
+                raise ValueError(f"train_impl must be 'kernels' or 'autograd', got {self.train_impl!r}")
+            if not x.is_cuda or self.precision != "bf16":
+                raise _lib.WaeError(
+                    "WaveNet.forward: a gradient is required (grad mode is on and an input or parameter requires grad) but the "
+                    f"differentiable kernels need CUDA tensors and precision='bf16' (got {x.device}, precision={self.precision!r}). "
+                    "Wrap inference in torch.no_grad(), set model.precision='bf16', or opt into the torch-op composite "
+                    "with model.train_impl='autograd' -- there is no silent fallback.")
+            if self.training and any(f.dropout > 0 for f in self.conv_layers):
+                raise _lib.WaeError(
+                    "WaveNet.forward: training with dropout > 0 (modules.py:128) is not implemented in the kernel path "
+                    "(every hps/*.json preset uses dropout 0.0); construct the model with dropout=0.0 or set "
+                    "model.train_impl='autograd'")
+            # tcgen05 forward that keeps its activations + hand-derived backward on them (training.py)
+            from .. import training
+            out = training.stack_forward_train(self, x, c, gvec)
+            return F.softmax(out, dim=1) if softmax else out
         with torch.no_grad():
             out = self.stack_forward(x, c, gvec, last_stage=last_stage, x_is_index=x_idx is not None)
         return F.softmax(out, dim=1) if softmax else out
@@ -268,9 +291,16 @@ class WaveNet(nn.Module):
                 if self.upsample_net is not None:
                     c = self.upsample_net(c)
                     assert c.size(-1) == T, f"c {c.size()} != T {T}"
-                if c.size(-1) == T:
+                if c.dim() != 3 or c.size(0) != B:
+                    raise ValueError(f"incremental_forward: c must be (B={B}, C, T) or (B, T, C), got {tuple(c.shape)}")
+                if c.size(-1) == T:                  # (B,C,T) -> (B,T,C)   (wavenet.py:276-280)
                     c = c.transpose(1, 2)
-                c_btc = c.float().contiguous()
+                if c.size(1) < T:
+                    raise ValueError(f"incremental_forward: conditioning covers {c.size(1)} steps but T = {T}")
+                # the reference indexes c[:, t] and so tolerates a longer c; the kernel's rows are exactly (B,T,C)
+                c_btc = c[:, :T].float().contiguous()
+                if self.cin_channels > 0 and c_btc.size(2) != self.cin_channels:
+                    raise ValueError(f"incremental_forward: c has {c_btc.size(2)} channels, the model expects {self.cin_channels}")
                 self._require_cuda(c_btc, "WaveNet.incremental_forward")
             if initial_input is None:
                 init = torch.zeros(B, Oin, device=dev)
@@ -283,6 +313,10 @@ class WaveNet(nn.Module):
                         init = init.transpose(1, 2)
                     init = init[:, -1, :]
                 init = init.to(dev).float().contiguous()
+            if tuple(init.shape) != (B, Oin):
+                raise ValueError(f"incremental_forward: initial_input must reduce to (B={B}, {Oin}), got {tuple(init.shape)}")
+            if gvec is not None and gvec.shape[0] != B:
+                raise ValueError(f"incremental_forward: g has batch {gvec.shape[0]}, expected {B}")
             if dev.type != "cuda":
                 raise _lib.WaeError("WaveNet.incremental_forward: parameters are not on a CUDA device (no CPU fallback)")
 
@@ -302,6 +336,9 @@ class WaveNet(nn.Module):
             else:
                 mode = _lib.AR_SAMPLE_NONE
             if uniforms is not None:
+                want = (T, B, nmix + 1) if self.scalar_input else (T, B)
+                if tuple(uniforms.shape) != want:
+                    raise ValueError(f"incremental_forward: uniforms must have shape {want}, got {tuple(uniforms.shape)}")
                 uniforms = uniforms.to(dev).float().contiguous()
 
             # fp32 weights -> SIMT kernel (reference parity); bf16 -> tensor-core (mma.sync) kernel with up to 8 utterances
@@ -330,7 +367,10 @@ class WaveNet(nn.Module):
             n = L.wae_ar_workspace(pk.struct, B, T)
             ws = self._ws.get(n, dev)
             forced = None if test_inputs is None else test_inputs.to(dev).float().contiguous()
+            if forced is not None and (forced.dim() != 3 or forced.size(0) != B or forced.size(2) != Oin):
+                raise ValueError(f"incremental_forward: test_inputs must be (B={B}, T, {Oin}) or (B, {Oin}, T), got {tuple(forced.shape)}")
             Tf = 0 if forced is None else forced.size(1)
+            self.last_ar_variant = (wtype, cluster, upc)
             out_idx = torch.empty(B, T, dtype=torch.int32, device=dev) if mode == _lib.AR_SAMPLE_CATEGORICAL else None
             if mode == _lib.AR_SAMPLE_NONE:
                 out_dense = torch.empty(B, T, self.out_channels, dtype=torch.float32, device=dev)
