@@ -29,6 +29,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+if "--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"] or "--impl=reference" in sys.argv:
+    # the reference arm times the reference's CPU path: with no visible device its modules take their CPU branches unmodified
+    # (vector_quantization.py:33 moves the one-hot matrix to CUDA whenever torch.cuda.is_available())
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
@@ -41,22 +45,34 @@ FLOP_PER_SAMPLE_SKIP = 2 * 128 * 256                   # the layer's skip 1x1 (2
 FLOP_PER_SAMPLE_TOTAL = 11403264                       # 20 layers + head (first conv on one-hot input = gather)
 
 
+def LAYER_KERNEL_NAME(L):
+    try:
+        return L.wae_layer_kernel_name().decode()
+    except Exception:
+        return "layer_bf16_v2_kernel"
+
+
 def workload_config(world):
     return {"workload": "VQ-WAE hps/vqwae.json encoder->VQ->WaveNet decoder teacher-forced forward (BASELINE configs[1])",
             "batch_per_gpu": B_PER_GPU, "samples_per_utt": T_SAMPLES, "global_batch": world * B_PER_GPU,
             "parallelism": f"utterance-sharded x{world}, no data-path collective",
             "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no explicit flush",
             "weights": "synthetic seeded (testing.synth_state_dict)",
+            "reference_arm": "--impl reference / cpu_baseline: the unmodified reference modules (baseline/_ref) on the host cores, the "
+                             "same VQVAE.forward + teacher-forced NLL on ONE utterance per step (1/16 of the per-GPU batch; "
+                             "decoder-only port of the same ATen calls if baseline/_ref is absent) -- see cpu_baseline.sample",
             "value_input": "reference-shaped call, eager launches: one-hot (B,256,T) fp32 + mfcc + speaker ids resident in HBM; "
                            "e2e goes through the class-index input and GraphedForward (see e2e.what)"}
 
 
 def _peaks():
+    """(burst bf16 TFLOP/s, sustained bf16 TFLOP/s, HBM GB/s, source).  The layer kernel is timed in windows of tens of ms at
+    full clocks, so its roofline denominator is the BURST figure (B200_PROFILING.md); the sustained one is reported beside it."""
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, sustained bf16)"
+        return float(p["bf16_tflops"]), float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json, burst bf16)"
     except Exception:
-        return 1400.0, 6650.0, "fallback (B200_PROFILING.md: ~1.4 PF sustained, 6.65 TB/s)"
+        return 1590.0, 1400.0, 6650.0, "fallback (B200_PROFILING.md: 1.59 PF burst, ~1.4 PF sustained, 6.65 TB/s)"
 
 
 class ClockSampler:
@@ -121,6 +137,57 @@ def synth_batch(B, seed):
     return idx, mfcc, g
 
 
+def load_reference_modules():
+    """The UNMODIFIED reference modules staged in git-ignored baseline/_ref/ by __graft_entry__.build() (they travel to the GPU
+    box with the snapshot).  Returns (VQVAE, WaveNet) or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "wavenet_vocoder")):
+        return None
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    import warnings
+    warnings.filterwarnings("ignore")
+    try:
+        import vqvae_model as ref_vqvae
+        from wavenet_vocoder import WaveNet as RefWaveNet
+    except Exception:
+        return None
+    return ref_vqvae.VQVAE, RefWaveNet
+
+
+def build_reference_vqvae(device):
+    """The reference's own VQVAE (vqvae_model.py:54-71 around wavenet_vocoder.WaveNet) with the weights of build_vqvae."""
+    mods = load_reference_modules()
+    if mods is None:
+        return None
+    from wavenet_autoencoders_b200 import testing as T
+    RefVQVAE, RefWaveNet = mods
+    torch.manual_seed(0)
+    m = RefVQVAE(c_in=39, hid=64, K=256, wavenet=RefWaveNet(**T.VQWAE), encoder_hid=256).eval()
+    m.load_state_dict(T.synth_state_dict(m, 1))
+    return m.to(device)
+
+
+def cpu_reference_setup():
+    """One step of the reference arm: the workload of the GPU arm's e2e (VQVAE.forward -> teacher-forced NLL,
+    vqwae_train.py:760-766) on ONE utterance (1/16 of the per-GPU batch), on the host cores.  kind "reference": the real
+    modules from baseline/_ref; kind "port": oracle/torch_port.py, decoder only (when baseline/_ref is absent)."""
+    m = build_reference_vqvae("cpu")
+    if m is None:
+        return cpu_port_setup(), "port", ("decoder teacher-forced forward only (no encoder / VQ / loss), B=1 x T=%d per step "
+                                          "(1/16 of the per-GPU batch), oracle/torch_port.py, fp32" % T_SAMPLES)
+    idx, mfcc, g = synth_batch(1, 100)
+    x = torch.nn.functional.one_hot(idx, 256).float().transpose(1, 2).contiguous()
+
+    def step():
+        with torch.no_grad():
+            y, vq_loss, perp = m(x, mfcc, g)
+            return float(torch.nn.functional.cross_entropy(y[:, :, :-1], idx[:, 1:]))
+    return step, "reference", ("unmodified reference modules (baseline/_ref): VQVAE.forward (encoder -> VQ -> WaveNet decoder, "
+                               "one-hot input) + cross_entropy, B=1 x T=%d per step (1/16 of the per-GPU batch), fp32, torch %s CPU"
+                               % (T_SAMPLES, torch.__version__))
+
+
 def cpu_port_setup():
     """Decoder of the same model on the host cores through oracle/torch_port.py (kind "port")."""
     from oracle import torch_port
@@ -143,11 +210,57 @@ def cpu_port_setup():
     return step
 
 
+def library_baseline(dev, x, idx, mfcc, g):
+    """The unmodified reference modules (baseline/_ref) moved to the GPU: eager PyTorch, cuDNN convolutions + cuBLAS, fp32 with
+    TF32 off and on.  Same weights and the same tensors as the headline step (16 x 16000, one-hot input) + cross_entropy."""
+    m = build_reference_vqvae(dev)
+    if m is None:
+        return {"unavailable": "baseline/_ref not staged (run __graft_entry__.build() where /root/reference exists)"}
+    out = {"what": "reference VQVAE.forward(one-hot x, mfcc, g) + F.cross_entropy on the B200, eager launches, B=16 x T=16000",
+           "torch": torch.__version__}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for tf32 in (False, True):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=tf32, benchmark=True), torch.no_grad():
+            for _ in range(2):
+                y = m(x, mfcc, g)[0]
+                loss = torch.nn.functional.cross_entropy(y[:, :, :-1], idx[:, 1:])
+            torch.cuda.synchronize()
+            n = 5
+            e0.record()
+            for _ in range(n):
+                y = m(x, mfcc, g)[0]
+                loss = torch.nn.functional.cross_entropy(y[:, :, :-1], idx[:, 1:])
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        key = "tf32" if tf32 else "fp32"
+        out[f"{key}_ms_per_step"] = ms
+        out[f"{key}_samples_per_s"] = x.shape[0] * x.shape[2] / (ms * 1e-3)
+        out[f"{key}_loss"] = float(loss)
+        del y
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return out
+
+
+def cpu_baseline_subprocess():
+    """The cpu_baseline leg = the reference arm itself, run as a child process with the GPU hidden (the unmodified reference
+    picks its device by torch.cuda.is_available()).  About 10-30 s of CPU work."""
+    try:
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "12", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=900, env={k: v for k, v in os.environ.items()
+                                                                             if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]
+        return json.loads(line)["cpu_baseline"]
+    except Exception as e:
+        return {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "unavailable", "sample": f"{type(e).__name__}: {e}"[:200]}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    step = cpu_port_setup()
+    step, kind, sample = cpu_reference_setup()
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -155,13 +268,13 @@ def run_reference(args, rank):
         step()
     dt = time.perf_counter() - t0
     v = args.steps * T_SAMPLES / dt
-    sample = f"decoder teacher-forced forward, B=1 x T={T_SAMPLES} per step (1/16 of the per-GPU batch), fp32, torch {torch.__version__} CPU"
+    cfg = workload_config(args.gpus)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -172,7 +285,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--ar-steps", type=int, default=2400, help="AR extra: samples per utterance (config 4 uses 48000)")
+    ap.add_argument("--ar-steps", type=int, default=48000, help="AR extra: samples per utterance (configs[3]: 48000 = 3 s)")
+    ap.add_argument("--ar-fp32-steps", type=int, default=2560, help="AR extra, fp32-faithful SIMT kernel: samples per utterance (truncated)")
     ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -301,6 +415,22 @@ def main():
 
     ms_e2e = timed(step_e2e_graphed, args.steps, args.warmup) if graphed is not None else ms_e2e_eager
     e2e_value = world * B * T_SAMPLES * args.steps / (ms_e2e * 1e-3)
+
+    # the same step when the caller wants the LOGITS back (262 MB fp32 per step): D2H into pinned host memory inside the timing
+    logits_host = torch.empty(B, 256, T_SAMPLES, dtype=torch.float32).pin_memory()
+
+    def step_e2e_logits():
+        if graphed is not None:
+            out = graphed(idx_p, mfcc_p, g_p)
+            logits_host.copy_(out[0], non_blocking=True)
+            return float(out[3].item())
+        with torch.no_grad():
+            i_d = idx_p.to(dev, non_blocking=True)
+            y = model(i_d, mfcc_p.to(dev, non_blocking=True), g_p.to(dev, non_blocking=True))[0]
+            logits_host.copy_(y, non_blocking=True)
+            return float(teacher_forced_nll(y, i_d).item())
+    n_lg = max(3, args.steps // 4)
+    ms_e2e_logits = timed(step_e2e_logits, n_lg, 2) / n_lg
     ms_e2e_onehot = timed(step_e2e_onehot, args.steps, args.warmup)
     h2d = idx_p.numel() * 8 + mfcc_p.numel() * 4 + g_p.numel() * 8
 
@@ -331,10 +461,11 @@ def main():
     # layer has no residual 1x1.
     flops_per_launch = B * T_SAMPLES * (FLOP_PER_SAMPLE_LAYER - FLOP_PER_SAMPLE_SKIP - 2 * 128 * 256 / n_layers)
     head_flops = B * T_SAMPLES * (n_layers * FLOP_PER_SAMPLE_SKIP + 2 * 256 * 256 + 2 * 256 * 256)
-    peak_tf, peak_hbm, peak_src = _peaks()
+    peak_tf, peak_tf_sust, peak_hbm, peak_src = _peaks()
     achieved = flops_per_launch / (layer_ms * 1e-3) / 1e12
-    roofline = {"kernel": "layer_bf16_v2_kernel", "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+    roofline = {"kernel": LAYER_KERNEL_NAME(L), "bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved / peak_tf, "traffic": None, "peak_source": peak_src,
+                "frac_of_sustained_peak": achieved / peak_tf_sust, "sustained_peak": peak_tf_sust,
                 "avg_launch_ms": layer_ms, "share_of_step": float(ms_kind[1]) / prof_total,
                 "head_share_of_step": float(ms_kind[2]) / prof_total, "prep_share_of_step": float(ms_kind[0]) / prof_total,
                 "step_frac_of_peak": value / world * FLOP_PER_SAMPLE_TOTAL / 1e12 / peak_tf,
@@ -354,25 +485,46 @@ def main():
         model.wavenet.precision = "fp32"
         ms32 = timed(step_device, max(2, args.steps // 5), 1)
         extras["fp32_stack_samples_per_s"] = world * B * T_SAMPLES * max(2, args.steps // 5) / (ms32 * 1e-3)
-        # autoregressive synthesis, configs[3] shape per GPU (32 utterances), truncated to --ar-steps samples
+        # autoregressive synthesis, configs[3] AS STATED: 32 utterances per GPU (256 over 8 GPUs) x 48000 samples (3 s),
+        # categorical sampling on supplied uniforms, bf16 tensor-core cluster kernel; the fp32-faithful SIMT kernel is ~8x
+        # slower and timed on a truncated run (stated)
         wn = model.wavenet
-        Tar = (args.ar_steps // 640) * 640
-        lat = torch.randn(32, 64, Tar // 640, device=dev)
         gar = torch.randint(0, 153, (32, 1), device=dev)
-        for prec in ("bf16", "fp32"):
+        for prec, Tar in (("bf16", (args.ar_steps // 640) * 640), ("fp32", (args.ar_fp32_steps // 640) * 640)):
+            if Tar <= 0:
+                continue
             wn.precision = prec
+            lat = torch.randn(32, 64, Tar // 640, device=dev)
             u = torch.rand(Tar, 32, device=dev)
             wn.incremental_forward(c=lat[:, :, :1], g=gar, T=640, uniforms=u[:640], return_indices=True)   # warm-up / packing
             barrier()
             e0.record()
-            wn.incremental_forward(c=lat, g=gar, T=Tar, uniforms=u, return_indices=True)
+            out_ar = wn.incremental_forward(c=lat, g=gar, T=Tar, uniforms=u, return_indices=True)
             e1.record()
             barrier()
             t_ar = max_over_ranks(e0.elapsed_time(e1)) * 1e-3
             extras[f"ar_{prec}_samples_per_s"] = world * 32 * Tar / t_ar
             extras[f"ar_{prec}_realtime_factor_per_utt"] = Tar / t_ar / 16000.0
             extras[f"ar_{prec}_us_per_step"] = 1e6 * t_ar / Tar
-        extras["ar_config"] = f"32 utt/GPU x {Tar} samples (configs[3] is 48000), categorical sampling, cluster kernel"
+            extras[f"ar_{prec}_samples_per_utt"] = Tar
+            extras[f"ar_{prec}_kernel"] = "/".join(str(v) for v in wn.last_ar_variant)       # weight type / cluster size / utterances per cluster
+            if prec == "bf16":
+                # "roofline" of a latency-bound kernel: every step streams the cluster's whole weight set (11.53 MB bf16) L2 -> SM once,
+                # and walks 2 dependent DSMEM exchanges per layer + 3 in the head
+                wt, cs, upc = wn.last_ar_variant
+                n_clusters = -(-32 // upc)
+                w_bytes = 20 * (256 * 832 + 512 * 128) * 2 + (256 * 256 + 256 * 256) * 2
+                extras["ar_roofline"] = {"bound": "latency (2L+3 dependent cluster exchanges per step) / L2->SM weight stream",
+                                         "us_per_step": 1e6 * t_ar / Tar, "realtime_us_per_step": 62.5,
+                                         "clusters": n_clusters, "ctas": n_clusters * cs,
+                                         "l2_to_sm_gbs": n_clusters * w_bytes / (t_ar / Tar) / 1e9,
+                                         "l2_cap_gbs_B300_MICROARCH": 6300 * 1.965,
+                                         "dependent_exchanges_per_step": 2 * 20 + 3,
+                                         "ns_per_exchange_if_latency_bound": 1e9 * t_ar / Tar / (2 * 20 + 3)}
+                assert out_ar.shape == (32, Tar)
+            del lat, u, out_ar
+        extras["ar_config"] = (f"32 utt/GPU x {(args.ar_steps // 640) * 640} samples bf16 (configs[3]: 256 utterances x 48000 over 8 GPUs); "
+                               f"fp32 SIMT kernel truncated to {(args.ar_fp32_steps // 640) * 640} samples; categorical sampling, cluster kernels")
         # VQ search throughput, N sweep (HBM roofline: 4D read + 4D write + 8 B index per vector)
         from wavenet_autoencoders_b200.vector_quantization import VectorQuantize
         vq = VectorQuantize(256, 64).to(dev)
@@ -487,19 +639,17 @@ def main():
         torch.cuda.empty_cache()
         extras["inwae_config"] = "decoder only, 64 utt/GPU x 32000 samples, bf16 tcgen05 stack (gate rows in two accumulator passes)"
 
+    # ---- the reference's own eager PyTorch path on this GPU (cuDNN / cuBLAS), BASELINE.md section 4: same weights, same tensors ----
+    if not args.no_extras and rank == 0:
+        try:
+            extras["library_baseline"] = library_baseline(dev, x, idx, mfcc, g)
+        except Exception as e:
+            extras["library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
     cpu = None
     if rank == 0 and world == 1:
-        torch.set_num_threads(os.cpu_count() or 1)
-        step = cpu_port_setup()
-        step()
-        reps, t0 = 0, time.perf_counter()
-        while reps < 3 or (time.perf_counter() - t0 < 10 and reps < 20):
-            step()
-            reps += 1
-        dtc = time.perf_counter() - t0
-        cpu = {"value": reps * T_SAMPLES / dtc, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": f"decoder teacher-forced forward B=1 x T={T_SAMPLES}, {reps} reps, oracle/torch_port.py (reference's ATen calls), fp32"}
-
+        cpu = cpu_baseline_subprocess()
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -508,6 +658,9 @@ def main():
             "config": workload_config(world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps,
+                    "with_logits_to_host": {"value": world * B * T_SAMPLES / (ms_e2e_logits * 1e-3), "ms_per_step": ms_e2e_logits,
+                                            "d2h_bytes_per_step": 4 + logits_host.numel() * 4,
+                                            "what": "same step, plus the (16,256,16000) fp32 logits copied to pinned host memory"},
                     "what": "pinned host class indices/mfcc/speaker -> H2D -> VQVAE.forward(indices) -> one-pass teacher-forced NLL -> D2H loss"
                             + (", replayed as one CUDA graph (GraphedForward)" if graphed is not None else ", eager launches"),
                     "eager_api_value": world * B * T_SAMPLES * args.steps / (ms_e2e_eager * 1e-3),

@@ -57,7 +57,10 @@ def test_forward_fp32_matches_reference_golden(case):
     assert y.shape == (int(g["B"]), cfg["out_channels"], int(g["T"]))
     assert rel_err(y[:, :, ::s].cpu().numpy(), g["logits"]) < TOL_FP32
     assert rel_err(y[:, :, ::s].cpu().numpy(), g["logits"]) < 1e-4   # what the fp32 kernels actually achieve
-    ys = m(x, c, spk, softmax=True)
+    with torch.no_grad():
+        ys = m(x, c, spk, softmax=True)
+    with pytest.raises(_lib.WaeError, match="no silent fallback"):     # grad mode + fp32 kernels: fails loudly (no torch-op fallback)
+        m(x, c, spk)
     assert torch.allclose(ys.sum(1), torch.ones_like(ys.sum(1)), atol=1e-4)
 
 

@@ -45,6 +45,7 @@ struct ArArgs {
     wae_stack_dims d;
     int wtype, cluster, B, T, Tf, sample_mode, apply_softmax, nmix;
     int utts;                        // utterances per cluster (tensor-core variant; the SIMT kernel has it as a template parameter)
+    int w1_slots;                    // SIMT kernel: shared-memory slots of the gate-weight ring (2; 1 when two do not fit, e.g. G = 368)
     int Hp, Cp, K1p;                 // padded reduction lengths (multiples of 64)
     int ring_rows;                   // rows per utterance in the ring
     int ring_off[WAE_MAX_LAYERS];    // first ring row of each layer
@@ -115,7 +116,8 @@ struct ArSmem {
     int n_bias;                // floats in the bias cache
 };
 
-__host__ __device__ inline ArSmem ar_smem_layout(const wae_stack_dims& d, int cs, int U, int wbytes, int Hp, int Cp, int K1p) {
+__host__ __device__ inline ArSmem ar_smem_layout(const wae_stack_dims& d, int cs, int U, int wbytes, int Hp, int Cp, int K1p,
+                                                 int w1_slots = 2) {
     ArSmem s;
     const int H = d.G / 2;
     int max_np = 0, max_n2 = 0, max_n3 = 0, max_n4 = 0;
@@ -134,7 +136,7 @@ __host__ __device__ inline ArSmem ar_smem_layout(const wae_stack_dims& d, int cs
     int w2 = max_n2 * Hp * wbytes, w3 = max_n3 * d.S * wbytes, w4 = max_n4 * d.S * wbytes;
     s.w2_slot = up(w2 > w3 ? (w2 > w4 ? w2 : w4) : (w3 > w4 ? w3 : w4));
     int off = 0;
-    s.off_w1 = off; off += 2 * s.w1_slot;
+    s.off_w1 = off; off += w1_slots * s.w1_slot;
     s.off_w2 = off; off += 2 * s.w2_slot;
     s.off_xin = off; off += up(NPF * U * d.kernel_size * d.R * 4);
     s.off_c = off; off += up(2 * U * (Cp > 0 ? Cp : 16) * 4);
@@ -178,7 +180,8 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     const int KX = kw * R;  // taps + current sample part of the GEMV1 input
     const int nm1 = K1p / 64, nm2 = Hp / 64, nms = S / 64;
 
-    const ArSmem sl = ar_smem_layout(d, cs, U, (int)sizeof(WT), Hp, Cp, K1p);
+    const ArSmem sl = ar_smem_layout(d, cs, U, (int)sizeof(WT), Hp, Cp, K1p, a.w1_slots);
+    const bool w1_single = (a.w1_slots == 1);       // one gate-weight slot: the next layer's slice is fetched behind GEMV2 instead of a layer ahead
     uint8_t* w1buf = smem + sl.off_w1;
     uint8_t* w2buf = smem + sl.off_w2;
     float* xin = reinterpret_cast<float*>(smem + sl.off_xin);      // [NPF][U][KX]
@@ -229,7 +232,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
     const unsigned n1_total = (unsigned)a.T * L, n2_total = (unsigned)a.T * (L + 2);   // host checks T*(L+2) < 2^31
     auto issue_w1 = [&](unsigned j) {
         if (j >= n1_total) return;
-        const int l = (int)(j % L), slot = (int)(j & 1);
+        const int l = (int)(j % L), slot = w1_single ? 0 : (int)(j & 1);
         const uint32_t bytes = w1_bytes();
         if (bytes == 0) { mbar_arrive(&w1_full[slot]); return; }  // empty slice: just complete the phase
         mbar_arrive_expect_tx(&w1_full[slot], bytes);
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
         inbuf[e] = (b < a.B) ? a.init[(size_t)b * Oin + o] : 0.f;
     }
     __syncthreads();
-    if (tid == 0) { issue_w1(0); issue_w1(1); issue_w2(0); issue_w2(1); }
+    if (tid == 0) { issue_w1(0); if (!w1_single) issue_w1(1); issue_w2(0); issue_w2(1); }
     cluster_sync();  // also: every CTA of the cluster is running before any DSMEM traffic
 
     const int pf_r4 = R / 4;
@@ -395,10 +398,11 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             // 32-lane-per-row split.  Weights are packed [K/32][row][32] (4 elements per lane) so the 32 lanes of a warp read 32
             // consecutive words of shared memory (conflict free); the input vector is a broadcast read.
             AR_PROF(1);
-            mbar_wait(&w1_full[j1 & 1], (uint32_t)((j1 >> 1) & 1));
+            const unsigned s1 = w1_single ? 0u : (j1 & 1u);
+            mbar_wait(&w1_full[s1], w1_single ? (j1 & 1u) : ((j1 >> 1) & 1u));
             AR_PROF(2);
             {
-                const WT* w1s = reinterpret_cast<const WT*>(w1buf + (size_t)(j1 & 1) * sl.w1_slot);
+                const WT* w1s = reinterpret_cast<const WT*>(w1buf + (size_t)s1 * sl.w1_slot);
                 const int rows1 = 2 * np, grp = lane >> 3, s8 = lane & 7;
                 for (int r0 = warp * 4; r0 < rows1; r0 += AR_WARPS * 4) {
                     const int row = r0 + grp;
@@ -453,7 +457,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
             // Refill the W1 slot just consumed (blob j1+1 has the parity of j1-1).  Every warp of this CTA
             // finished reading it before arriving at the cluster barrier we just passed, so the
             // asynchronous overwrite cannot race with a reader.
-            if (tid == 0) issue_w1(j1 + 1);
+            if (tid == 0) issue_w1(w1_single ? j1 : j1 + 1);
             __syncwarp();
 
             // ---- GEMV2: residual + skip rows of this rank (4 lanes per row, 8 rows per warp and pass) ----
@@ -1668,7 +1672,12 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
         return WAE_OK;
     }
     const int wbytes = (w->wtype == 0) ? 4 : 2;
-    const ArSmem sl = ar_smem_layout(d, a.cluster, U, wbytes, a.Hp, a.Cp, a.K1p);
+    a.w1_slots = 2;
+    ArSmem sl = ar_smem_layout(d, a.cluster, U, wbytes, a.Hp, a.Cp, a.K1p, 2);
+    if (sl.total > 232448) {      // wide gates (IN-WAE: G = 368): keep one gate-weight slot, refilled behind the layer's second mat-vec
+        a.w1_slots = 1;
+        sl = ar_smem_layout(d, a.cluster, U, wbytes, a.Hp, a.Cp, a.K1p, 1);
+    }
     WAE_REQUIRE(sl.total <= 232448, "wae_ar_generate: shared memory %d B exceeds 227 KB (use a larger cluster or bf16 weights)", sl.total);
     const int clusters = (B + U - 1) / U;
     if (w->wtype == 0) {
