@@ -241,11 +241,14 @@ int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
                   void* stream);
 /* ema (optional, NULL = none): the reference's shadow parameters, ema -= (1 - ema_decay) * (ema - p_new)  (vqwae_train.py:337-350,782-787) */
 
-/* Variant of the bf16 residual-layer kernel: -1 (default) = version-2 kernel (residual added by an identity MMA, x' and h
- * stored by TMA from shared memory); -2 = version 2 on CTA pairs (tcgen05 cta_group::2: each CTA stages half of every weight
+/* Variant of the bf16 residual-layer kernel: -3 (default) = version-3 kernel (version 2 with the accumulators ping-ponged
+ * in TMEM: GEMM1 of tile i+1 runs while the epilogues drain tile i; gate widths up to 256); -1 = version-2 kernel (residual
+ * added by an identity MMA, x' and h stored by TMA from shared memory); -2 = version 2 on CTA pairs (tcgen05 cta_group::2: each CTA stages half of every weight
  * k-block); 0 = first CTA-pair kernel; 1, 2 or 4 = the first 1-CTA kernel in clusters of that size, the CTAs of a cluster
- * sharing every weight k-block through TMA multicast.  Gate widths above 256 and the training forward always use -1. */
+ * sharing every weight k-block through TMA multicast.  Gate widths above 256 always use -1. */
 int wae_set_layer_cluster(int cs);
+/* Name of the residual-layer kernel the last wae_stack_forward_bf16* call launched (for bench.py's roofline entry). */
+const char* wae_layer_kernel_name(void);
 /* Debug: per-CTA cycle counters of the 1-CTA residual-layer kernel's three roles (16 int64 per CTA), or NULL to disable. */
 void wae_layer_set_profile_buffer(int64_t* dev_buf);
 

@@ -30,4 +30,7 @@ names = ["prod wait-empty", "prod total", "mma wait-full", "mma wait-epi1", "mma
 tiles = p[:, 7].clamp(min=1)
 print("counters of layer 5 (dilation 32), cycles")
 for i, n in enumerate(names):
-    print(f"{n:22s} mean {p[:, i].mean().item():10.0f}  per tile {(p[:, i] / tiles).mean().item():9.0f}")
+    col = p[:, i][p[:, 13] > 0] if i < 8 and (p[:, 6] > 0).sum() < 148 else p[:, i]   # pair kernels: MMA counters exist in leaders only
+    colt = col if len(col) == 148 else p[:, i][p[:, 6] > 0]
+    tl = tiles if len(colt) == 148 else tiles[p[:, 6] > 0]
+    print(f"{n:22s} mean {colt.mean().item():10.0f}  max {colt.max().item():10.0f}  per tile {(colt / tl).mean().item():9.0f}")

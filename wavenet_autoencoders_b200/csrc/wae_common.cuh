@@ -298,15 +298,18 @@ __device__ __forceinline__ void tma_load_3d_2cta(const void* desc, uint32_t bar_
           "r"(c2)
         : "memory");
 }
-// arrive (release at cluster scope) on an mbarrier addressed in the shared::cluster window
+// arrive on an mbarrier addressed in the shared::cluster window (the peer CTA's barrier).  Default semantics (release.cta):
+// the .release.cluster form compiles to MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive (checked in SASS) and cost
+// the CTA-pair kernels ~1.8k cycles per epilogue (profiles/r2_layer_roles.txt).  What the arrival orders here is shared-memory
+// data read by the ASYNC proxy (tcgen05.mma / TMA), published by fence.proxy.async + the CTA barrier in front of the arrive.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"   // .acquire.cluster adds a CCTL.IVALL (L1 flush) per wait
         "selp.u32 %0, 1, 0, P;\n\t}\n"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)

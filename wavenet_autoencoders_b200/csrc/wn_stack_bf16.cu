@@ -1098,6 +1098,288 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
 }
 
 // ---------------------------------------------------------------------------------------------
+// version 3 (DEFAULT for G <= 256): version 2 with the accumulators PING-PONGED in TMEM
+// ---------------------------------------------------------------------------------------------
+// Version 2's MMA warp idles ~4.4k of its 17.5k cycles per tile while the gate epilogue drains the one gate accumulator
+// (gate 256 + output 256 columns fill TMEM; profiles/layer_roles_r1.txt).  Here a tile owns ONE 256-column buffer for its whole
+// life -- GEMM1 writes z into it, EPI1 drains it (h -> shared memory), GEMM2 writes Wo*h back into the SAME columns, EPI2 drains
+// it again -- and consecutive tiles alternate between the two buffers, so the tensor core runs GEMM1 of tile i+1 while the
+// epilogue warps work on tile i.  The short GEMM2 of tile i is issued in the MIDDLE of GEMM1(i+1) (after KSPLIT k-blocks, when
+// EPI1(i) has delivered h), which leaves EPI2(i) the rest of GEMM1(i+1) to free the buffer for GEMM1(i+2).
+// The residual can no longer ride on identity MMAs (the buffer holds z while the x tile is in the ring), so EPI2 adds x from
+// global memory, loaded into registers at the start of EPI1 (one L2 round trip, hidden behind the gate math).
+//   MMA warp order:  G1(i)[0..KSPLIT)  G2(i-1)  G1(i)[KSPLIT..nk1)  ->  the TMA producer feeds the ring in exactly that order
+//   epilogue order:  EPI1(i)  EPI2(i)   (EPI2(i) waits for G2(i), i.e. runs during the second part of G1(i+1))
+__global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v3_kernel(const __grid_constant__ LayerArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int B_BYTES = 256 * BK * 2;
+    const int STAGE_BYTES = A_TILE_BYTES + B_BYTES;
+    const int nkh = a.Hp / BK, nkr = a.R / BK;
+    const int hx_tiles = nkh > nkr ? nkh : nkr;
+    uint8_t* hx = smem + V2_STAGES * STAGE_BYTES;                 // h tiles (GEMM2 A operand), later the x' staging tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hx + hx_tiles * A_TILE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + V2_STAGES;
+    uint64_t* acc1_full = bars + 2 * V2_STAGES;   // [2]  GEMM1 of the tile in buffer b is complete
+    uint64_t* epi1_done = acc1_full + 2;           // [2]  h is in shared memory, buffer b drained
+    uint64_t* acc2_full = acc1_full + 4;           // [2]  GEMM2 of the tile in buffer b is complete
+    uint64_t* epi2_done = acc1_full + 6;           // [2]  buffer b drained for good: the tile after next may use it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 8);
+    float* sb_bo = reinterpret_cast<float*>(bars) + 64;
+
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < V2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 8; ++i) mbar_init(&acc1_full[i], 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&a.tm_x);
+        tma_prefetch_desc(&a.tm_c);
+        tma_prefetch_desc(&a.tm_w1);
+        tma_prefetch_desc(&a.tm_wo);
+        tma_prefetch_desc(&a.tm_hst);
+        tma_prefetch_desc(&a.tm_xout);
+    }
+    if (warp == 1) tmem_alloc<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ntiles = a.B * a.tiles_per_utt;
+    const int rk = a.R / BK;
+    const int nk_x = a.kw * rk;                  // tap k-blocks, oldest tap first
+    const int nk_c = a.Cp / BK;
+    const int nk1 = nk_x + nk_c;
+    const int ksplit = (nk1 * 5) / 8;            // GEMM2 of the previous tile is issued after this many k-blocks of GEMM1
+    const bool has_out = (a.x_out != nullptr);
+    const int w1_bytes = a.G * BK * 2, wo_bytes = a.R * BK * 2;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (elect_one()) {
+            Ring ring(V2_STAGES);
+            auto load_g1 = [&](int b, int t0, int kb) {
+                mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + w1_bytes);
+                if (kb < nk_x) {
+                    const int tap = kb / rk, r0 = (kb % rk) * BK;
+                    tma_load_3d(&a.tm_x, &full[ring.stage], sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
+                } else {
+                    tma_load_3d(&a.tm_c, &full[ring.stage], sa, (kb - nk_x) * BK, t0, b);
+                }
+                tma_load_3d(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, a.layer);
+                ring.advance();
+            };
+            auto load_wo = [&]() {
+                for (int kb = 0; kb < nkh; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    mbar_arrive_expect_tx(&full[ring.stage], wo_bytes);
+                    tma_load_3d(&a.tm_wo, &full[ring.stage], sa + A_TILE_BYTES, kb * BK, 0, a.layer);
+                    ring.advance();
+                }
+            };
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+                for (int kb = 0; kb < ksplit; ++kb) load_g1(b, t0, kb);
+                if (has_out && it > 0) load_wo();
+                for (int kb = ksplit; kb < nk1; ++kb) load_g1(b, t0, kb);
+            }
+            if (has_out && it > 0) load_wo();
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (elect_one()) {
+            Ring ring(V2_STAGES);
+            const uint32_t idesc1 = umma_idesc_bf16(BM, a.G);
+            const uint32_t idesc2 = umma_idesc_bf16(BM, a.R);
+            long long m_full = 0, m_e1 = 0, m_e2 = 0, m_iss = 0; const long long m_t0 = clock64(); LPROF_BEGIN();
+            auto gemm2 = [&](int jt) {       // tile number jt (per-CTA count) -> its own buffer, on top of nothing (zero-init)
+                const uint32_t buf = tmem_base + (uint32_t)((jt & 1) * 256);
+                LPROF(m_iss);
+                mbar_wait(&epi1_done[jt & 1], (uint32_t)((jt >> 1) & 1));     // h(jt) is in shared memory, the buffer is drained
+                LPROF(m_e1);
+                tc_fence_after();
+                for (int kb = 0; kb < nkh; ++kb) {
+                    LPROF(m_iss);
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    LPROF(m_full);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                    issue_kblock(buf, smem_u32(hx + kb * A_TILE_BYTES), sb, idesc2, kb == 0);
+                    umma_commit(&empty[ring.stage]);
+                    ring.advance();
+                }
+                umma_commit(&acc2_full[jt & 1]);
+            };
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+                const uint32_t buf = tmem_base + (uint32_t)((it & 1) * 256);
+                if (it >= 2) {               // the buffer's previous tenant (tile it-2) must be fully drained
+                    LPROF(m_iss);
+                    mbar_wait(has_out ? &epi2_done[it & 1] : &epi1_done[it & 1], (uint32_t)(((it - 2) >> 1) & 1));
+                    LPROF(m_e2);
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < nk1; ++kb) {
+                    if (kb == ksplit && has_out && it > 0) gemm2(it - 1);
+                    LPROF(m_iss);
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    LPROF(m_full);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    issue_kblock(buf, sa, sa + A_TILE_BYTES, idesc1, kb == 0);
+                    umma_commit(&empty[ring.stage]);
+                    ring.advance();
+                }
+                umma_commit(&acc1_full[it & 1]);
+            }
+            if (has_out && it > 0) gemm2(it - 1);
+            if (LPROF_ON && a.prof) {
+                long long* pp = a.prof + blockIdx.x * 16;
+                pp[2] = m_full; pp[3] = m_e1; pp[4] = m_e2; pp[5] = m_iss; pp[6] = clock64() - m_t0; pp[7] = it;
+            }
+        }
+    } else {
+        // ================= epilogue warps =================
+        const int lane = threadIdx.x & 31;
+        const int Hh = a.G / 2;
+        const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t hx_addr = smem_u32(hx);
+        for (int i = threadIdx.x - 64; i < a.R; i += 32 * LAYER_EPI_WARPS) sb_bo[i] = __ldg(a.bo + i);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+        long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0; const long long e_t0 = clock64(); LPROF_BEGIN();
+        int it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+            const uint32_t buf = tmem_base + (uint32_t)((it & 1) * 256);
+            const uint32_t par = (uint32_t)((it >> 1) & 1);
+            const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+            const int t = t0 + row;
+            const bool live = t < a.T;
+            const float* gbp = a.gb + (size_t)b * a.G;
+            // residual channels of this thread (its column group's chunks of its row): requested now, consumed in EPI2
+            uint4 res[8];
+            if (has_out && live) {
+                const __nv_bfloat16* xin = a.x_in + ((size_t)b * a.T + t) * a.R;
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c0 = (cg + LAYER_NCG * jj) * 16;
+                    if (c0 < a.R) {
+                        res[2 * jj] = __ldg(reinterpret_cast<const uint4*>(xin + c0));
+                        res[2 * jj + 1] = __ldg(reinterpret_cast<const uint4*>(xin + c0 + 8));
+                    }
+                }
+            }
+            // ---- EPI1: gate ----
+            LPROF(e_e2);
+            mbar_wait(&acc1_full[it & 1], par);
+            LPROF(e_w1);
+            tc_fence_after();
+            if (it > 0) {   // the TMA stores of the previous tile (h and x') must have finished READING the staging tiles
+                if (threadIdx.x == 64) tma_store_wait_read();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+            }
+            for (int c0 = cg * 16; c0 < a.Hp; c0 += LAYER_NCG * 16) {
+                uint32_t packed[8];
+                if (c0 < Hh) {
+                    float va[16], vb[16];
+                    tmem_ld16(buf + lane_base + c0, va);
+                    tmem_ld16(buf + lane_base + Hh + c0, vb);
+                    float ba[16], bb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
+                        *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + Hh + c0 + i));
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
+                        const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
+                        packed[i >> 1] = pack_bf16x2(h0, h1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = 0u;
+                }
+                const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                const uint32_t base = hx_addr + kb * A_TILE_BYTES;
+                st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+            if (threadIdx.x == 64) {
+                for (int kb = 0; kb < a.Hp / BK; ++kb) tma_store_3d(&a.tm_hst, hx + kb * A_TILE_BYTES, kb * BK, t0, a.layer * a.B + b);
+                tma_store_commit();
+                mbar_arrive(&epi1_done[it & 1]);
+            }
+            LPROF(e_e1);
+            // ---- EPI2: x' = (Wo h + bo + x) * sqrt(.5) ----
+            if (has_out) {
+                mbar_wait(&acc2_full[it & 1], par);
+                LPROF(e_w2);
+                tc_fence_after();
+                // GEMM2 has finished reading the h tiles; their TMA store must have finished reading them too before x' overwrites them
+                if (threadIdx.x == 64) tma_store_wait_read();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c0 = (cg + LAYER_NCG * jj) * 16;
+                    if (c0 < a.R) {
+                        float v[16];
+                        tmem_ld16(buf + lane_base + c0, v);
+                        float bo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bo[i]) = *reinterpret_cast<const float4*>(sb_bo + c0 + i);
+                        tmem_ld_wait();
+                        uint32_t rr[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                        if (live) {
+                            const uint4 r0 = res[2 * jj], r1 = res[2 * jj + 1];
+                            rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+                        }
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                            packed[i] = pack_bf16x2(((v[2 * i] + bo[2 * i]) + __low2float(rv)) * kSqrtHalf,
+                                                    ((v[2 * i + 1] + bo[2 * i + 1]) + __high2float(rv)) * kSqrtHalf);
+                        }
+                        const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                        const uint32_t base = hx_addr + kb * A_TILE_BYTES;
+                        st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                        st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+                if (threadIdx.x == 64) {
+                    mbar_arrive(&epi2_done[it & 1]);
+                    for (int kb = 0; kb < a.R / BK; ++kb) tma_store_3d(&a.tm_xout, hx + kb * A_TILE_BYTES, kb * BK, t0, b);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (threadIdx.x == 64) tma_store_wait_all();
+        if (LPROF_ON && a.prof && threadIdx.x == 64) {
+            long long* pp = a.prof + blockIdx.x * 16;
+            pp[8] = e_w1; pp[9] = e_e1; pp[10] = e_w2; pp[11] = e_e2; pp[12] = 0; pp[13] = clock64() - e_t0; pp[14] = 0; pp[15] = 0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
 // the fused residual layer on CTA PAIRS (tcgen05 cta_group::2)
 // ---------------------------------------------------------------------------------------------
 // Same maths and the same warp roles as layer_bf16_kernel, but two CTAs (one cluster of 2 = one TPC) execute every
@@ -1441,6 +1723,311 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_pair2_kernel(cons
 }
 
 // ---------------------------------------------------------------------------------------------
+// version 4 (DEFAULT for G <= 256): CTA pairs (tcgen05 cta_group::2) + accumulators ping-ponged in TMEM
+// ---------------------------------------------------------------------------------------------
+// Measured state before this kernel (profiles/r2_layer_roles.txt): the 1-CTA kernels wait for OPERANDS -- version 3 spends 7.8k of
+// its 18.0k cycles per tile in full-barrier waits while pulling 688 KB per 128 samples from L2 (~40 B/cycle/SM, the chip-wide
+// L2 -> SM rate); the pair kernel (version 2 on cta_group::2) halves the weight bytes per CTA but still serialises GEMM1 -> gate
+// epilogue -> GEMM2 (5.6k cycles of MMA idle per 256-sample super-tile).  This kernel combines the two:
+//   * cta_group::2: a pair computes 256 samples per MMA, each CTA stages its own 128 sample rows (A) and HALF of every weight
+//     k-block (B): 32 KB per k-block and CTA instead of 48 KB, 4 ring stages;
+//   * TMEM ping-pong as in version 3: a tile owns one 256-column buffer for its whole life (GEMM1 -> z, EPI1 drains it, GEMM2
+//     writes Wo*h into the same columns, EPI2 drains it again) and consecutive tiles alternate buffers, so GEMM1 of tile i+1 runs
+//     under both epilogues of tile i; GEMM2(i) is issued after KSPLIT k-blocks of GEMM1(i+1);
+//   * the residual: version 3 fetched x with per-thread global loads (one sample row per thread = 32 cache lines per warp
+//     instruction) and its EPI2 grew from 2.7k to 7.9k cycles.  Here one thread TMA-loads the 128 x R tile of x into a staging
+//     region at the start of EPI1 (64 KB more from L2 per tile, hidden behind the gate math); EPI2 reads its own row from there,
+//     adds, and writes x' IN PLACE (same thread, same 16 bytes); the TMA store leaves from the same region.
+// Shared memory per CTA: 4 x 32 KB ring + h tiles (Hp/64 x 16 KB) + x/x' tiles (R/64 x 16 KB) = 224 KB at the vqwae shape.
+// Barriers: full[] in the leader (both CTAs' TMA loads signal it), empty[] per CTA (multicast commit), acc*_full[2] per CTA
+// (multicast commit), epi*_done[2] in the leader (one arrival per CTA, remote for the peer), xres_full per CTA.
+constexpr int V4_STAGES = 4;
+
+__global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const __grid_constant__ LayerArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGE_BYTES = A_TILE_BYTES + PAIR_B_BYTES;
+    const int nkh = a.Hp / BK, nkr = a.R / BK;
+    uint8_t* hbuf = smem + V4_STAGES * STAGE_BYTES;               // h tiles: GEMM2 A operand + TMA store source
+    uint8_t* xres = hbuf + nkh * A_TILE_BYTES;                    // x tile (residual) in, x' out, TMA store source
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xres + nkr * A_TILE_BYTES);
+    uint64_t* full = bars;                        // [V4_STAGES]  used in the leader only
+    uint64_t* empty = bars + V4_STAGES;           // [V4_STAGES]  one per CTA (commit is multicast)
+    uint64_t* acc1_full = bars + 2 * V4_STAGES;   // [2]  GEMM1 of the tile in buffer b is complete
+    uint64_t* epi1_done = acc1_full + 2;          // [2]  leader only, 2 arrivals: h of both CTAs is in shared memory, buffer b drained
+    uint64_t* acc2_full = acc1_full + 4;          // [2]  GEMM2 of the tile in buffer b is complete
+    uint64_t* epi2_done = acc1_full + 6;          // [2]  leader only, 2 arrivals: buffer b drained for good
+    uint64_t* xres_full = acc1_full + 8;          // x tile of the current tile has landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 9);
+    float* sb_bo = reinterpret_cast<float*>(bars) + 64;
+
+    const int warp = threadIdx.x >> 5;
+    const int crank = (int)cluster_ctarank();    // 0 = leader
+    const bool leader = (crank == 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < V4_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&acc1_full[i], 1);
+            mbar_init(&epi1_done[i], 2);         // one elected epilogue thread per CTA
+            mbar_init(&acc2_full[i], 1);
+            mbar_init(&epi2_done[i], 2);
+        }
+        mbar_init(xres_full, 1);
+        fence_mbar_init();
+        tma_prefetch_desc(&a.tm_x);
+        tma_prefetch_desc(&a.tm_c);
+        tma_prefetch_desc(&a.tm_w1);
+        tma_prefetch_desc(&a.tm_wo);
+        tma_prefetch_desc(&a.tm_hst);
+        tma_prefetch_desc(&a.tm_xout);
+    }
+    if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int ntiles = a.B * a.tiles_per_utt;
+    const int nsuper = (ntiles + 1) / 2;
+    const int ncluster = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+    const int rk = a.R / BK;
+    const int nk_x = a.kw * rk;                  // tap k-blocks, oldest tap first
+    const int nk_c = a.Cp / BK;
+    const int nk1 = nk_x + nk_c;
+    const int ksplit = (nk1 * 5) / 8;            // GEMM2 of the previous tile is issued after this many k-blocks of GEMM1
+    const bool has_out = (a.x_out != nullptr);
+    const int w1_rows = a.G / 2, wo_rows = a.R / 2;       // weight rows held by this CTA
+    const uint32_t w1_half = (uint32_t)w1_rows * BK * 2, wo_half = (uint32_t)wo_rows * BK * 2;
+
+    if (warp == 0) {
+        // ================= TMA producer (both CTAs) =================
+        if (elect_one()) {
+            Ring ring(V4_STAGES);
+            auto load_g1 = [&](int b, int t0, int kb) {
+                mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
+                if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + w1_half));
+                if (kb < nk_x) {
+                    const int tap = kb / rk, r0 = (kb % rk) * BK;
+                    tma_load_3d_2cta(&a.tm_x, fb, sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
+                } else {
+                    tma_load_3d_2cta(&a.tm_c, fb, sa, (kb - nk_x) * BK, t0, b);
+                }
+                tma_load_3d_2cta(&a.tm_w1, fb, sa + A_TILE_BYTES, kb * BK, crank * w1_rows, a.layer);
+                ring.advance();
+            };
+            auto load_wo = [&]() {
+                for (int kb = 0; kb < nkh; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
+                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * wo_half);
+                    tma_load_3d_2cta(&a.tm_wo, fb, sa + A_TILE_BYTES, kb * BK, crank * wo_rows, a.layer);
+                    ring.advance();
+                }
+            };
+            int it = 0;
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+                const int tile = sup * 2 + crank;
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
+                for (int kb = 0; kb < ksplit; ++kb) load_g1(b, t0, kb);
+                if (has_out && it > 0) load_wo();
+                for (int kb = ksplit; kb < nk1; ++kb) load_g1(b, t0, kb);
+            }
+            if (has_out && it > 0) load_wo();
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (leader && elect_one()) {
+            Ring ring(V4_STAGES);
+            const uint32_t idesc1 = umma_idesc_bf16(2 * BM, a.G);
+            const uint32_t idesc2 = umma_idesc_bf16(2 * BM, a.R);
+            long long m_full = 0, m_e1 = 0, m_e2 = 0, m_iss = 0; const long long m_t0 = clock64(); LPROF_BEGIN();
+            auto gemm2 = [&](int jt) {       // tile number jt (per-cluster count) -> its own buffer, zero-initialised
+                const uint32_t buf = tmem_base + (uint32_t)((jt & 1) * 256);
+                LPROF(m_iss);
+                mbar_wait(&epi1_done[jt & 1], (uint32_t)((jt >> 1) & 1));     // h(jt) of BOTH CTAs is in shared memory, the buffers are drained
+                LPROF(m_e1);
+                tc_fence_after();
+                for (int kb = 0; kb < nkh; ++kb) {
+                    LPROF(m_iss);
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    LPROF(m_full);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                    const uint64_t ad = umma_desc_sw128(smem_u32(hbuf + kb * A_TILE_BYTES)), bd = umma_desc_sw128(sb);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_2cta(buf, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc2, (kb == 0 && k == 0) ? 0u : 1u);
+                    umma_commit_2cta(&empty[ring.stage], 3);
+                    ring.advance();
+                }
+                umma_commit_2cta(&acc2_full[jt & 1], 3);
+            };
+            int it = 0;
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+                const uint32_t buf = tmem_base + (uint32_t)((it & 1) * 256);
+                if (it >= 2) {               // the buffer's previous tenant (tile it-2) must be fully drained in both CTAs
+                    LPROF(m_iss);
+                    mbar_wait(has_out ? &epi2_done[it & 1] : &epi1_done[it & 1], (uint32_t)(((it - 2) >> 1) & 1));
+                    LPROF(m_e2);
+                    tc_fence_after();
+                }
+                for (int kb = 0; kb < nk1; ++kb) {
+                    if (kb == ksplit && has_out && it > 0) gemm2(it - 1);
+                    LPROF(m_iss);
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    LPROF(m_full);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_2cta(buf, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc1, (kb == 0 && k == 0) ? 0u : 1u);
+                    umma_commit_2cta(&empty[ring.stage], 3);
+                    ring.advance();
+                }
+                umma_commit_2cta(&acc1_full[it & 1], 3);
+            }
+            if (has_out && it > 0) gemm2(it - 1);
+            if (LPROF_ON && a.prof) {
+                long long* pp = a.prof + blockIdx.x * 16;
+                pp[2] = m_full; pp[3] = m_e1; pp[4] = m_e2; pp[5] = m_iss; pp[6] = clock64() - m_t0; pp[7] = it;
+            }
+        }
+    } else {
+        // ================= epilogue warps (both CTAs, own 128 TMEM lanes) =================
+        const int lane = threadIdx.x & 31;
+        const int Hh = a.G / 2;
+        const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t h_addr = smem_u32(hbuf), x_addr = smem_u32(xres);
+        const uint32_t epi1_remote0 = mapa(smem_u32(&epi1_done[0]), 0), epi2_remote0 = mapa(smem_u32(&epi2_done[0]), 0);
+        for (int i = threadIdx.x - 64; i < a.R; i += 32 * LAYER_EPI_WARPS) sb_bo[i] = __ldg(a.bo + i);
+        asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+        long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0, e_wx = 0; const long long e_t0 = clock64(); LPROF_BEGIN();
+        int it = 0;
+        for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+            const uint32_t buf = tmem_base + (uint32_t)((it & 1) * 256);
+            const uint32_t par = (uint32_t)((it >> 1) & 1);
+            const int tile = sup * 2 + crank;
+            const bool valid = tile < ntiles;                  // a pair's odd tail: computed on zero-filled input, never stored
+            const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+            const float* gbp = a.gb + (size_t)(valid ? b : 0) * a.G;
+            // ---- EPI1: gate ----
+            LPROF(e_e2);
+            mbar_wait(&acc1_full[it & 1], par);
+            LPROF(e_w1);
+            tc_fence_after();
+            if (threadIdx.x == 64) {
+                // the TMA stores of the previous tile (h and x') must have finished READING the staging tiles; then the x tile of
+                // this one is fetched into the x/x' region (consumed by EPI2, several thousand cycles from now)
+                if (it > 0) tma_store_wait_read();
+                if (has_out) {
+                    mbar_arrive_expect_tx(xres_full, (uint32_t)(nkr * A_TILE_BYTES));
+                    for (int j = 0; j < nkr; ++j) tma_load_3d(&a.tm_x, xres_full, xres + j * A_TILE_BYTES, j * BK, t0, b);
+                }
+            }
+            if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+            for (int c0 = cg * 16; c0 < a.Hp; c0 += LAYER_NCG * 16) {
+                uint32_t packed[8];
+                if (c0 < Hh) {
+                    float va[16], vb[16];
+                    tmem_ld16(buf + lane_base + c0, va);
+                    tmem_ld16(buf + lane_base + Hh + c0, vb);
+                    float ba[16], bb[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        *reinterpret_cast<float4*>(&ba[i]) = __ldg(reinterpret_cast<const float4*>(gbp + c0 + i));
+                        *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + Hh + c0 + i));
+                    }
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
+                        const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
+                        packed[i >> 1] = pack_bf16x2(h0, h1);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) packed[i] = 0u;
+                }
+                const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                const uint32_t base = h_addr + kb * A_TILE_BYTES;
+                st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+            if (threadIdx.x == 64) {
+                if (valid)
+                    for (int kb = 0; kb < nkh; ++kb) tma_store_3d(&a.tm_hst, hbuf + kb * A_TILE_BYTES, kb * BK, t0, a.layer * a.B + b);
+                tma_store_commit();
+                mbar_arrive_cluster(epi1_remote0 + (uint32_t)((it & 1) * 8));
+            }
+            LPROF(e_e1);
+            // ---- EPI2: x' = (Wo h + bo + x) * sqrt(.5), in place over the staged x tile ----
+            if (has_out) {
+                mbar_wait(xres_full, (uint32_t)(it & 1));
+                LPROF(e_wx);
+                mbar_wait(&acc2_full[it & 1], par);
+                LPROF(e_w2);
+                tc_fence_after();
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int c0 = (cg + LAYER_NCG * jj) * 16;
+                    if (c0 < a.R) {
+                        float v[16];
+                        tmem_ld16(buf + lane_base + c0, v);
+                        const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                        const uint32_t p0 = x_addr + kb * A_TILE_BYTES + sw128_off(row, c16), p1 = x_addr + kb * A_TILE_BYTES + sw128_off(row, c16 + 1);
+                        uint32_t rr[8];
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]) : "r"(p0) : "memory");
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]) : "r"(p1) : "memory");
+                        float bo[16];
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(&bo[i]) = *reinterpret_cast<const float4*>(sb_bo + c0 + i);
+                        tmem_ld_wait();
+                        uint32_t packed[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const __nv_bfloat162 rv = *reinterpret_cast<const __nv_bfloat162*>(&rr[i]);
+                            packed[i] = pack_bf16x2(((v[2 * i] + bo[2 * i]) + __low2float(rv)) * kSqrtHalf,
+                                                    ((v[2 * i + 1] + bo[2 * i + 1]) + __high2float(rv)) * kSqrtHalf);
+                        }
+                        st_shared_v4(p0, packed[0], packed[1], packed[2], packed[3]);
+                        st_shared_v4(p1, packed[4], packed[5], packed[6], packed[7]);
+                    }
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+                if (threadIdx.x == 64) {
+                    mbar_arrive_cluster(epi2_remote0 + (uint32_t)((it & 1) * 8));
+                    if (valid)
+                        for (int kb = 0; kb < nkr; ++kb) tma_store_3d(&a.tm_xout, xres + kb * A_TILE_BYTES, kb * BK, t0, b);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (threadIdx.x == 64) tma_store_wait_all();
+        if (LPROF_ON && a.prof && threadIdx.x == 64) {
+            long long* pp = a.prof + blockIdx.x * 16;
+            pp[8] = e_w1; pp[9] = e_e1; pp[10] = e_w2; pp[11] = e_e2; pp[12] = e_wx; pp[13] = clock64() - e_t0; pp[14] = 0; pp[15] = 0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 1) tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
 // the head: skip GEMM over all layers + ReLU + 1x1 + ReLU + 1x1
 // ---------------------------------------------------------------------------------------------
 struct HeadArgs {
@@ -1664,7 +2251,10 @@ struct Profiler {
 };
 Profiler g_prof;
 long long* g_layer_prof = nullptr;
-int g_layer_mode = 2;      // 2 = version-2 1-CTA kernel (default), 0 = CTA-pair kernel (cta_group::2), 1 = first 1-CTA kernel
+int g_layer_mode = 5;      // 5 = version 4 (CTA pairs + TMEM ping-pong; default, G <= 256; other shapes fall to version 3 / 2),
+                           // 4 = version 3 (1-CTA TMEM ping-pong), 2 = version-2 1-CTA kernel,
+                           // 3 = version 2 on CTA pairs, 0 = first CTA-pair kernel (cta_group::2), 1 = first 1-CTA kernel
+const char* g_layer_kernel_name = "layer_bf16_v4_kernel";
 int g_layer_cluster = 1;   // 1-CTA kernel only: 1, 2 or 4 CTAs share every weight k-block via TMA multicast
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a, b; bool on;
@@ -1725,11 +2315,15 @@ void wae_profile_enable(int on) { g_prof.on = (on != 0); }
 
 void wae_layer_set_profile_buffer(int64_t* dev_buf) { g_layer_prof = reinterpret_cast<long long*>(dev_buf); }
 
+const char* wae_layer_kernel_name() { return g_layer_kernel_name; }   // the residual-layer kernel the last forward launched
+
 int wae_set_layer_cluster(int cs) {
+    if (cs == -4) { g_layer_mode = 5; return WAE_OK; }    // version-4 kernel (default)
+    if (cs == -3) { g_layer_mode = 4; return WAE_OK; }    // version-3 kernel
     if (cs == -1) { g_layer_mode = 2; return WAE_OK; }    // version-2 kernel, one CTA per tile
     if (cs == -2) { g_layer_mode = 3; return WAE_OK; }    // version-2 kernel on CTA pairs
     if (cs == 0) { g_layer_mode = 0; return WAE_OK; }     // CTA-pair kernel
-    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be -2, -1, 0, 1, 2 or 4");
+    if (cs != 1 && cs != 2 && cs != 4) return wae::set_error(WAE_ERR_ARG, "wae_set_layer_cluster: cs must be -4, -3, -2, -1, 0, 1, 2 or 4");
     g_layer_mode = 1;
     g_layer_cluster = cs;
     return WAE_OK;
@@ -1836,7 +2430,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
 
     // ---- layers ----
     const size_t smem_layer = 1024 + (size_t)LAYER_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(Hp / BK) * A_TILE_BYTES + 256 + 1024;
-    if (g_layer_mode != 2 && g_layer_mode != 3 && Hb == 0 && save == nullptr) {
+    if (g_layer_mode != 2 && g_layer_mode != 3 && g_layer_mode != 4 && g_layer_mode != 5 && Hb == 0 && save == nullptr) {
         WAE_REQUIRE(smem_layer <= 232448, "wae_stack_forward_bf16: layer kernel shared memory %zu too large", smem_layer);
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
     }
@@ -1853,11 +2447,16 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     // Layer-kernel variant: CTA pairs (cta_group::2, default) or the 1-CTA kernel in clusters of 1/2/4 with weight multicast.
     // version 2 on CTA pairs: single gate pass, weight halves must stay multiples of 16 rows
     const bool pair2 = (g_layer_mode == 3) && Hb == 0 && Gp % 32 == 0 && d.R % 32 == 0;
-    const bool v2 = !pair2 && ((g_layer_mode == 2) || (g_layer_mode == 3) || Hb > 0 || save != nullptr);   // only the 1-CTA version 2 has the second gate pass
-    const bool pair = pair2 || (!v2 && (g_layer_mode == 0) && Gp % 32 == 0 && d.R % 32 == 0);
-    int cs = pair ? 2 : (v2 ? 1 : g_layer_cluster);
+    const size_t smem_v4 = 1024 + (size_t)V4_STAGES * (A_TILE_BYTES + PAIR_B_BYTES) + (size_t)(Hp / BK + d.R / BK) * A_TILE_BYTES + 256 + 1024;
+    const bool v4 = (g_layer_mode == 5) && Hb == 0 && Gp % 32 == 0 && d.R % 32 == 0 && smem_v4 <= 232448;    // CTA pairs + TMEM ping-pong
+    const bool v3 = !v4 && (g_layer_mode == 4 || g_layer_mode == 5) && Hb == 0;                            // TMEM ping-pong (single gate pass only)
+    const bool v2 = !v4 && !v3 && !pair2 && ((g_layer_mode == 2) || (g_layer_mode == 3) || (g_layer_mode == 4) || (g_layer_mode == 5) || Hb > 0 || save != nullptr);   // only the 1-CTA version 2 has the second gate pass
+    const bool pair = v4 || pair2 || (!v2 && !v3 && (g_layer_mode == 0) && Gp % 32 == 0 && d.R % 32 == 0);
+    int cs = pair ? 2 : ((v2 || v3) ? 1 : g_layer_cluster);
+    g_layer_kernel_name = v4 ? "layer_bf16_v4_kernel" : v3 ? "layer_bf16_v3_kernel" : pair2 ? "layer_bf16_pair2_kernel" : v2 ? "layer_bf16_v2_kernel"
+                          : pair ? "layer_bf16_pair_kernel" : "layer_bf16_kernel";
     while (!pair && cs > 1 && (Gp % (8 * cs) != 0 || d.R % (8 * cs) != 0)) cs >>= 1;
-    if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, Gp, d.layers, K1p, (uint64_t)Gp * K1p, BK, v2 ? 2 * Ha : Gp / cs)) return rc;
+    if (int rc = make_tmap(&la.tm_w1, w->w1, K1p, Gp, d.layers, K1p, (uint64_t)Gp * K1p, BK, (v2 || v3) ? 2 * Ha : Gp / cs)) return rc;
     // pair kernels: CTA r stages weight rows [r * N/2, (r+1) * N/2) (the MMA's B operand is split over the pair's shared
     // memories); both CTAs' accumulators still hold all N columns for their own 128 rows
     if (Hb > 0) {
@@ -1871,7 +2470,8 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     if (cs == 4) nclusters = 33;   // 132 SMs: 4-CTA clusters cannot use all 148 (GPC granularity); more would queue a 2nd wave
     if (nclusters > nsuper) nclusters = nsuper;
     const int grid_layer = nclusters * cs;
-    if (pair && !pair2)
+    if (v4) WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v4));
+    if (pair && !pair2 && !v4)
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
     const int hx_tiles = (Hp / BK) > (d.R / BK) ? (Hp / BK) : (d.R / BK);
     const size_t smem_pair2 = 1024 + (size_t)PAIR2_STAGES * (A_TILE_BYTES + PAIR_B_BYTES) + (size_t)hx_tiles * A_TILE_BYTES + 32 * BK * 2 + 256 + 1024;
@@ -1883,6 +2483,11 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     if (v2) {
         WAE_REQUIRE(smem_v2 <= 232448, "wae_stack_forward_bf16: layer kernel (v2) shared memory %zu too large", smem_v2);
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v2));
+    }
+    const size_t smem_v3 = 1024 + (size_t)V2_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)hx_tiles * A_TILE_BYTES + 256 + 1024;
+    if (v3) {
+        WAE_REQUIRE(smem_v3 <= 232448, "wae_stack_forward_bf16: layer kernel (v3) shared memory %zu too large", smem_v3);
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v3));
     }
     if (int rc = make_tmap(&la.tm_hst, ws.hall, Hp, T, (uint64_t)d.layers * B, Hp, (uint64_t)T * Hp, BK, BM)) return rc;
     la.B = B; la.T = T; la.R = d.R; la.G = Gp; la.Ha = Ha; la.Hb = Hb; la.Hp = Hp; la.Cp = (d.C > 0) ? Cp : 0; la.kw = d.kernel_size;
@@ -1911,7 +2516,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)grid_layer);
             cfg.blockDim = dim3(LAYER_THREADS);
-            cfg.dynamicSmemBytes = pair2 ? smem_pair2 : (v2 ? smem_v2 : smem_layer);
+            cfg.dynamicSmemBytes = v4 ? smem_v4 : v3 ? smem_v3 : pair2 ? smem_pair2 : (v2 ? smem_v2 : smem_layer);
             cfg.stream = stream;
             cudaLaunchAttribute attr[1];
             attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1920,7 +2525,9 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            if (pair2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair2_kernel, la));
+            if (v4) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v4_kernel, la));
+            else if (v3) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v3_kernel, la));
+            else if (pair2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair2_kernel, la));
             else if (v2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v2_kernel, la));
             else if (pair) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair_kernel, la));
             else WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_kernel, la));
