@@ -201,7 +201,7 @@ int wae_nll_sum(const float* logits, const int64_t* target, int B, int O, int T,
 /*
  * Training forward: the same kernels, but every layer input, the gated activations and the channels-last conditioning are
  * written to caller-owned buffers (all bf16) that the backward pass reads (modules.py:115-163 under autograd).  The
- * version-2 layer kernel is used regardless of wae_set_layer_cluster.
+ * default layer kernel is used (the variant chosen by wae_set_layer_cluster).
  */
 typedef struct wae_stack_saved {
     void* x_all;   /* [L][B][T][R]   x_all[l] = input of residual layer l (x_all[0] = first conv output) */
@@ -241,11 +241,12 @@ int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
                   void* stream);
 /* ema (optional, NULL = none): the reference's shadow parameters, ema -= (1 - ema_decay) * (ema - p_new)  (vqwae_train.py:337-350,782-787) */
 
-/* Variant of the bf16 residual-layer kernel: -3 (default) = version-3 kernel (version 2 with the accumulators ping-ponged
- * in TMEM: GEMM1 of tile i+1 runs while the epilogues drain tile i; gate widths up to 256); -1 = version-2 kernel (residual
- * added by an identity MMA, x' and h stored by TMA from shared memory); -2 = version 2 on CTA pairs (tcgen05 cta_group::2: each CTA stages half of every weight
- * k-block); 0 = first CTA-pair kernel; 1, 2 or 4 = the first 1-CTA kernel in clusters of that size, the CTAs of a cluster
- * sharing every weight k-block through TMA multicast.  Gate widths above 256 always use -1. */
+/* Variant of the bf16 residual-layer kernel: -4 (default) = version-4 kernel (CTA pairs, tcgen05 cta_group::2: each CTA stages
+ * half of every weight k-block; accumulators ping-ponged in TMEM so that GEMM1 of tile i+1 runs under both epilogues of tile i;
+ * residual tile staged by TMA; gate widths up to 256); -3 = version 3 (the same ping-pong on single CTAs, residual by per-thread
+ * loads); -1 = version 2 (residual added by an identity MMA, x' and h stored by TMA from shared memory; the only one with the
+ * second gate pass for widths above 256); -2 = version 2 on CTA pairs; 0 = first CTA-pair kernel; 1, 2 or 4 = the first 1-CTA
+ * kernel in clusters of that size with TMA weight multicast.  Shapes a variant does not cover fall back: -4 -> -3 -> -1. */
 int wae_set_layer_cluster(int cs);
 /* Name of the residual-layer kernel the last wae_stack_forward_bf16* call launched (for bench.py's roofline entry). */
 const char* wae_layer_kernel_name(void);

@@ -10,7 +10,7 @@ idx, mfcc, g = bench.synth_batch(16, 1000)
 idx, mfcc, g = idx.cuda(), mfcc.cuda(), g.cuda()
 x = torch.nn.functional.one_hot(idx, 256).float().transpose(1, 2).contiguous()
 ref = None
-for cs in (-1, -4, -3, -2):   # -3 = version-3 kernel (TMEM ping-pong, default); -1 = version-2 kernel; -2 = version 2 on CTA pairs; 0 = first CTA-pair kernel; 1 = first 1-CTA kernel
+for cs in ([int(a) for a in sys.argv[1:]] or (-1, -4, -3, -2)):   # -3 = version-3 kernel (TMEM ping-pong, default); -1 = version-2 kernel; -2 = version 2 on CTA pairs; 0 = first CTA-pair kernel; 1 = first 1-CTA kernel
     _lib.check(L.wae_set_layer_cluster(cs), "set cluster")
     with torch.no_grad():
         for _ in range(3):

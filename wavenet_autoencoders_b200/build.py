@@ -36,6 +36,8 @@ def _extra_flags() -> list:
         flags.append("-DWAE_LAYER_PROF")      # role counters of the residual-layer kernels (tools/layer_profile.py)
     if os.environ.get("WAE_AR_PROF") == "1":
         flags.append("-DWAE_AR_PROF")         # phase counters of the autoregressive kernels (tools/ar_profile.py)
+    for d in os.environ.get("WAE_NVCC_DEFS", "").split():
+        flags.append("-D" + d)                # experiment switches (e.g. WAE_V4_STAGES=3), never set in a shipped build
     return flags
 
 

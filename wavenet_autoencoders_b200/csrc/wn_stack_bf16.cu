@@ -1741,7 +1741,10 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_pair2_kernel(cons
 // Shared memory per CTA: 4 x 32 KB ring + h tiles (Hp/64 x 16 KB) + x/x' tiles (R/64 x 16 KB) = 224 KB at the vqwae shape.
 // Barriers: full[] in the leader (both CTAs' TMA loads signal it), empty[] per CTA (multicast commit), acc*_full[2] per CTA
 // (multicast commit), epi*_done[2] in the leader (one arrival per CTA, remote for the peer), xres_full per CTA.
-constexpr int V4_STAGES = 4;
+#ifndef WAE_V4_STAGES
+#define WAE_V4_STAGES 4
+#endif
+constexpr int V4_STAGES = WAE_V4_STAGES;
 
 __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -1760,6 +1763,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
     uint64_t* xres_full = acc1_full + 8;          // x tile of the current tile has landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc1_full + 9);
     float* sb_bo = reinterpret_cast<float*>(bars) + 64;
+    volatile long long* t_issue = reinterpret_cast<volatile long long*>(bars) + 24;   // [V4_STAGES] producer issue clocks (profiling builds)
 
     const int warp = threadIdx.x >> 5;
     const int crank = (int)cluster_ctarank();    // 0 = leader
@@ -1804,8 +1808,12 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
         // ================= TMA producer (both CTAs) =================
         if (elect_one()) {
             Ring ring(V4_STAGES);
+            long long p_we = 0, p_iss = 0; const long long p_t0 = clock64(); LPROF_BEGIN();
             auto load_g1 = [&](int b, int t0, int kb) {
+                LPROF(p_iss);
                 mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                LPROF(p_we);
+                if (LPROF_ON) t_issue[ring.stage] = clock64();
                 uint8_t* sa = smem + ring.stage * STAGE_BYTES;
                 const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
                 if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + w1_half));
@@ -1820,7 +1828,10 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
             };
             auto load_wo = [&]() {
                 for (int kb = 0; kb < nkh; ++kb) {
+                    LPROF(p_iss);
                     mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    LPROF(p_we);
+                    if (LPROF_ON) t_issue[ring.stage] = clock64();
                     uint8_t* sa = smem + ring.stage * STAGE_BYTES;
                     const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
                     if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * wo_half);
@@ -1837,6 +1848,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                 for (int kb = ksplit; kb < nk1; ++kb) load_g1(b, t0, kb);
             }
             if (has_out && it > 0) load_wo();
+            if (LPROF_ON && a.prof) { long long* pp = a.prof + blockIdx.x * 16; pp[0] = p_we; pp[1] = clock64() - p_t0; }
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
@@ -1844,7 +1856,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
             Ring ring(V4_STAGES);
             const uint32_t idesc1 = umma_idesc_bf16(2 * BM, a.G);
             const uint32_t idesc2 = umma_idesc_bf16(2 * BM, a.R);
-            long long m_full = 0, m_e1 = 0, m_e2 = 0, m_iss = 0; const long long m_t0 = clock64(); LPROF_BEGIN();
+            long long m_full = 0, m_e1 = 0, m_e2 = 0, m_iss = 0, m_lat = 0; const long long m_t0 = clock64(); LPROF_BEGIN();
             auto gemm2 = [&](int jt) {       // tile number jt (per-cluster count) -> its own buffer, zero-initialised
                 const uint32_t buf = tmem_base + (uint32_t)((jt & 1) * 256);
                 LPROF(m_iss);
@@ -1855,6 +1867,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                     LPROF(m_iss);
                     mbar_wait(&full[ring.stage], ring.phase);
                     LPROF(m_full);
+                    if (LPROF_ON) m_lat += clock64() - t_issue[ring.stage];
                     tc_fence_after();
                     const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
                     const uint64_t ad = umma_desc_sw128(smem_u32(hbuf + kb * A_TILE_BYTES)), bd = umma_desc_sw128(sb);
@@ -1880,6 +1893,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                     LPROF(m_iss);
                     mbar_wait(&full[ring.stage], ring.phase);
                     LPROF(m_full);
+                    if (LPROF_ON) m_lat += clock64() - t_issue[ring.stage];
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
                     const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_TILE_BYTES);
@@ -1894,7 +1908,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
             if (has_out && it > 0) gemm2(it - 1);
             if (LPROF_ON && a.prof) {
                 long long* pp = a.prof + blockIdx.x * 16;
-                pp[2] = m_full; pp[3] = m_e1; pp[4] = m_e2; pp[5] = m_iss; pp[6] = clock64() - m_t0; pp[7] = it;
+                pp[2] = m_full; pp[3] = m_e1; pp[4] = m_e2; pp[5] = m_iss; pp[6] = clock64() - m_t0; pp[7] = it; pp[14] = m_lat;
             }
         }
     } else {
@@ -1923,16 +1937,15 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
             mbar_wait(&acc1_full[it & 1], par);
             LPROF(e_w1);
             tc_fence_after();
-            if (threadIdx.x == 64) {
-                // the TMA stores of the previous tile (h and x') must have finished READING the staging tiles; then the x tile of
-                // this one is fetched into the x/x' region (consumed by EPI2, several thousand cycles from now)
-                if (it > 0) tma_store_wait_read();
-                if (has_out) {
-                    mbar_arrive_expect_tx(xres_full, (uint32_t)(nkr * A_TILE_BYTES));
-                    for (int j = 0; j < nkr; ++j) tma_load_3d(&a.tm_x, xres_full, xres + j * A_TILE_BYTES, j * BK, t0, b);
-                }
+            // The h store of the previous tile must have finished READING the h tiles before they are overwritten.  Its x' store
+            // (committed last, 64 KB, still in flight when the next accumulator is already waiting) only guards the x/x' region:
+            // thread 64 waits for it after its first gate chunk and then fetches this tile's x there (consumed by EPI2, several
+            // thousand cycles from now) -- waiting for both groups here held all 16 warps at the barrier (E1 6.5k cycles vs 3.9k).
+            if (it > 0) {
+                if (threadIdx.x == 64) { if (has_out) tma_store_wait_read_1(); else tma_store_wait_read(); }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
             }
-            if (it > 0) asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+            bool xres_pending = has_out;
             for (int c0 = cg * 16; c0 < a.Hp; c0 += LAYER_NCG * 16) {
                 uint32_t packed[8];
                 if (c0 < Hh) {
@@ -1960,6 +1973,16 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                 const uint32_t base = h_addr + kb * A_TILE_BYTES;
                 st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
                 st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+                if (xres_pending && threadIdx.x == 64) {
+                    tma_store_wait_read();
+#ifdef WAE_V4_NOXRES   // timing experiment only (wrong residual)
+                    mbar_arrive(xres_full);
+#else
+                    mbar_arrive_expect_tx(xres_full, (uint32_t)(nkr * A_TILE_BYTES));
+                    for (int j = 0; j < nkr; ++j) tma_load_3d(&a.tm_x, xres_full, xres + j * A_TILE_BYTES, j * BK, t0, b);
+#endif
+                }
+                xres_pending = false;
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -2018,7 +2041,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
         if (threadIdx.x == 64) tma_store_wait_all();
         if (LPROF_ON && a.prof && threadIdx.x == 64) {
             long long* pp = a.prof + blockIdx.x * 16;
-            pp[8] = e_w1; pp[9] = e_e1; pp[10] = e_w2; pp[11] = e_e2; pp[12] = e_wx; pp[13] = clock64() - e_t0; pp[14] = 0; pp[15] = 0;
+            pp[8] = e_w1; pp[9] = e_e1; pp[10] = e_w2; pp[11] = e_e2; pp[12] = e_wx; pp[13] = clock64() - e_t0; pp[15] = 0;
         }
     }
     tc_fence_before();
