@@ -207,10 +207,44 @@ typedef struct wae_stack_saved {
     void* x_all;   /* [L][B][T][R]   x_all[l] = input of residual layer l (x_all[0] = first conv output) */
     void* h_all;   /* [L][B][T][Hp]  tanh * sigmoid of every layer, Hp = G/2 rounded up to 64 (padding channels are 0) */
     void* c_cl;    /* [B][T][Cp]     conditioning, Cp = C rounded up to 64; NULL iff C == 0 */
+    void* r1;      /* [B][T][S]      relu(skip sum * sqrt(1/L)): first hidden activation of the head (NULL: not kept) */
+    void* r2;      /* [B][T][S]      relu(W3 r1 + b3): second hidden activation of the head (NULL: not kept) */
 } wae_stack_saved;
 int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B, int T,
                                 float* logits, const wae_stack_saved* save, void* workspace, size_t workspace_bytes,
                                 void* stream);
+
+/*
+ * The whole backward of the decoder stack on the tensor cores (modules.py:115-163 and wavenet.py:203-212 differentiated by
+ * hand; the reference gets it from autograd, vqwae_train.py:768-782).  Reads what wae_stack_forward_bf16_save kept, recomputes
+ * the gate pre-activations, and produces fp32 gradients in the PACKED layouts of the forward's weight struct; the Python side
+ * scatters them back to the parameters.  `wae_stack_bwd` additionally carries the weights in the transposed K-major forms the dgrad GEMMs need
+ * (packed per step, bf16):
+ *   wdh [L][Hp][S+R]     row h: [Ws_l[:,h] | Wo_l[:,h]]            dh_l = dS Ws_l + dxo_l Wo_l
+ *   wdx [L][R][kw*Gq]    Wdx[r][j*Gq + g] = W1_l[g][r][j], g in the packed gate-row order, Gq = 2*Hh rounded up to 64
+ *   wct [Cp][L*Gq]       Wc_l[g][c] at column l*Gq + g                dC = sum_l dz_l Wc_l
+ *   w4t [S][O], w3t [S][S]   transposes of the head's 1x1 convs
+ * Outputs (fp32, zeroed by the call): dw1 [L][2*Hh][K1p], dwo [L][R][Hp], dws [S][L*Hp], dw3 [S][S], dw4 [O][S],
+ * dgb [L][B][2*Hh] (sum over time of dz per utterance: gives the conv-bias, conv1x1g and speaker-vector gradients),
+ * dbo [L][R], dbs [S], db3 [S], db4 [O], dc [B][T][Cp] (gradient of the upsampled conditioning), dx0 [B][T][R] bf16 (gradient of
+ * the first conv's output).  Shapes: R, S multiples of 64 up to 256, G <= 256, O a multiple of 16.
+ */
+typedef struct wae_stack_bwd {
+    const void *wdh, *wdx, *wct, *w4t, *w3t;                      /* bf16, packed per step */
+    const void *x_all, *h_all, *c_cl, *r1, *r2;                   /* saved by wae_stack_forward_bf16_save */
+    const float* gemb;                                            /* (B, Gi) speaker vectors or NULL */
+    float *dw1, *dwo, *dws, *dw3, *dw4, *dgb, *dbo, *dbs, *db3, *db4, *dc;
+    void* dx0;
+} wae_stack_bwd;
+size_t wae_stack_backward_workspace_bf16(const wae_stack_dims* d, int B, int T);
+int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* Unit-test entries of the two backward kernel families: C[M][N] fp32 += A^T B (A [K][M], B [K][N] bf16, MN-major operands,
+ * split-K), and out[M][N] bf16 = (A[M][K] W[N][K]^T) * alpha. */
+int wae_gemm_bf16_nt(const void* A, const void* B, float* C, int M, int N, int K, void* stream);
+/* out[plane (per_plane) or 0][n] += sum_t src[plane][t][n]: bias gradients; src (planes, T, N) bf16, N % 8 == 0, N <= 256 */
+int wae_colsum_bf16(const void* src, int planes, int T, int N, int per_plane, float* out, void* stream);
+int wae_gemm_bf16_tn_bf16out(const void* A, const void* W, void* out, int M, int N, int K, float alpha, void* stream);
 
 /*
  * Gather / element-wise kernels between the GEMMs of the stack's backward pass (wavenet_autoencoders_b200/training.py;

@@ -372,8 +372,8 @@ def test_training_backward_matches_autograd(cfg_name):
     """Gradients of the teacher-forced NLL through training.StackTrainFunction (bf16 kernels forward, hand-derived backward).
     The derivation itself is checked in float64 against autograd on the CPU (tests/test_host_cpu.py, < 1e-9, also at this
     20-layer shape).  Here, on the GPU:
-      (a) the bf16 backward (library GEMMs + csrc/wn_train.cu) against the SAME function evaluated in fp32 on the SAME saved
-          activations -- isolates the backward's bf16 arithmetic;
+      (a) the bf16 backward on the tensor-core kernels (wae_stack_backward_bf16, csrc/wn_bwd.cu) against the SAME derivation
+          evaluated as fp32 torch expressions on the SAME saved activations -- isolates the kernels' bf16 arithmetic;
       (b) end to end against torch autograd over the fp32 composite (true fp32: no TF32) -- additionally contains the bf16
           forward, whose ReLU masks / gate saturations differ slightly from the fp32 forward's.
     Gradients of bias-like quantities are heavily cancelling sums over time, so bf16 rounding noise is visible on them;
@@ -413,10 +413,11 @@ def test_training_backward_matches_autograd(cfg_name):
     logits = training.StackTrainFunction.forward(ctx, m, x, c_up, gv, *training.live_weights(m))
     lg = logits.clone().requires_grad_(True)
     torch.nn.functional.cross_entropy(lg[:, :, :-1], idx[:, 1:]).backward()
-    xf, gf, x_all, h_all, c_cl, *wts = ctx.saved
+    xf, gf, x_all, h_all, c_cl, r1, r2, *wts = ctx.saved
     f32 = lambda t: None if t is None else t.float()
+    assert training.tc_backward_supported(ctx.sh)                  # (a) exercises wae_stack_backward_bf16, not the library composite
     with torch.no_grad():
-        ra = training.stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, wts, lg.grad)
+        ra = training.stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, wts, lg.grad, r1=r1, r2=r2, pk=ctx.pk)
         rb = training.stack_backward(ctx.sh, ctx.dil, xf, gf, f32(x_all), f32(h_all), f32(c_cl), wts, lg.grad, cdt=torch.float32)
     keep = [i for i, w in enumerate(wts) if w is not None and ra[3][i] is not None]
     cos_a, l2_a = _flat_stats([rb[3][i] for i in keep] + [rb[1], rb[2]], [ra[3][i] for i in keep] + [ra[1], ra[2]])

@@ -2064,6 +2064,9 @@ struct HeadArgs {
     float* logits;       // (B, O, T)
     float scale;         // sqrt(1/L)
     int B, T, L, S, O, Op, Hp, tiles_per_utt;
+    int save;            // training forward: the two ReLU outputs (the head's hidden activations) are kept for the backward
+    CUtensorMap tm_r1;   // [B][T][S] bf16, box {64, 128}: relu(skip sum * sqrt(1/L))
+    CUtensorMap tm_r2;   // [B][T][S] bf16: relu(W3 r1 + b3)
 };
 
 constexpr int HEAD_STAGES = 3;
@@ -2196,7 +2199,11 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_kernel(const __gri
             const bool live = (t < a.T);
 
             // relu(scale * (acc + bias)) / relu(acc + bias) -> bf16 -> `act` (A operand of the next GEMM)
-            auto relu_to_act = [&](uint32_t tmem_acc, const float* bias, float scale) {
+            auto relu_to_act = [&](uint32_t tmem_acc, const float* bias, float scale, const CUtensorMap* tm_save) {
+                if (a.save) {   // the TMA store of the previous hidden activation must have finished reading `act`
+                    if (threadIdx.x == 64) tma_store_wait_read();
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+                }
                 for (int c0 = cg * 16; c0 < a.S; c0 += LAYER_NCG * 16) {
                     float v[16];
                     tmem_ld16(tmem_acc + lane_base + c0, v);
@@ -2216,16 +2223,23 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_kernel(const __gri
                 }
                 tc_fence_before();
                 fence_proxy_async_smem();
+                if (a.save) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+                    if (threadIdx.x == 64) {
+                        for (int kb = 0; kb < a.S / BK; ++kb) tma_store_3d(tm_save, act + kb * A_TILE_BYTES, kb * BK, t0, b);
+                        tma_store_commit();
+                    }
+                }
             };
 
             mbar_wait(accs_full, it & 1);
             tc_fence_after();
-            relu_to_act(tmem_s, a.bs_sum, a.scale);
+            relu_to_act(tmem_s, a.bs_sum, a.scale, &a.tm_r1);
             mbar_arrive(epis_done);
 
             mbar_wait(acc3_full, it & 1);
             tc_fence_after();
-            relu_to_act(tmem_34, a.b3, 1.0f);
+            relu_to_act(tmem_34, a.b3, 1.0f, &a.tm_r2);
             mbar_arrive(epi3_done);
 
             mbar_wait(acc4_full, it & 1);
@@ -2244,6 +2258,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_kernel(const __gri
             tc_fence_before();
             mbar_arrive(epi4_done);
         }
+        if (a.save && threadIdx.x == 64) tma_store_wait_all();
     }
     tc_fence_before();
     __syncthreads();
@@ -2312,6 +2327,15 @@ Bf16Workspace carve(const wae_stack_dims& d, int B, int T, void* base) {
 }
 
 }  // namespace
+
+namespace wae {
+// per-(layer, utterance) gate bias of the tcgen05 kernels (conv bias + speaker term), shared with the backward (wn_bwd.cu)
+int launch_gbias_bf16(const float* b1, const float* wg, const float* gemb, int L, int B, int G, int Gi, int Hh, float* gb, cudaStream_t st) {
+    gbias_bf16_kernel<<<L * B, 256, 0, st>>>(b1, wg, gemb, L, B, G, Gi, Hh, gb);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}
+}  // namespace wae
 
 extern "C" {
 
@@ -2569,6 +2593,13 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     ha.bs_sum = w->bs_sum; ha.b3 = w->b3; ha.b4 = w->b4; ha.logits = logits;
     ha.scale = (float)sqrt(1.0 / (double)d.layers);
     ha.B = B; ha.T = T; ha.L = d.layers; ha.S = d.S; ha.O = d.O; ha.Op = Op; ha.Hp = Hp; ha.tiles_per_utt = tiles_per_utt;
+    ha.save = (save != nullptr && save->r1 != nullptr && save->r2 != nullptr) ? 1 : 0;
+    ha.tm_r1 = ha.tm_h; ha.tm_r2 = ha.tm_h;
+    if (ha.save) {
+        WAE_REQUIRE(((reinterpret_cast<uintptr_t>(save->r1) | reinterpret_cast<uintptr_t>(save->r2)) & 127) == 0, "wae_stack_forward_bf16_save: r1/r2 must be 128-byte aligned");
+        if (int rc = make_tmap(&ha.tm_r1, save->r1, d.S, T, B, d.S, (uint64_t)T * d.S, BK, BM)) return rc;
+        if (int rc = make_tmap(&ha.tm_r2, save->r2, d.S, T, B, d.S, (uint64_t)T * d.S, BK, BM)) return rc;
+    }
     const size_t smem_head = 1024 + (size_t)HEAD_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(d.S / BK) * A_TILE_BYTES + 256;
     WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
     {

@@ -4,8 +4,11 @@ Forward: the same tcgen05 kernels as inference (``wae_stack_forward_bf16_save``)
 input ``x_all``, the gated activations ``h_all`` and the channels-last conditioning for the backward pass.
 
 Backward: the layer equations of ``ResidualConv1dGLU._forward`` (modules.py:115-163) differentiated by hand on those saved
-bf16 channels-last tensors.  Every contraction is a plain dense GEMM (library bf16 matmuls with fp32 accumulation; the
-hand-written dgrad/wgrad tcgen05 kernels are the next step), organised so that a layer costs five GEMMs:
+bf16 channels-last tensors.  On the GPU every contraction runs on this library's tcgen05 kernels (``wae_stack_backward_bf16``,
+csrc/wn_bwd.cu: dgrad-shaped GEMMs with the dilated taps as TMA boxes and the gate derivative / residual / ReLU masks fused in
+the epilogues, MN-major split-K wgrads) -- ``_stack_backward_tc`` below only packs the transposed weights and scatters the
+fp32 gradients back to the parameters.  ``stack_backward`` keeps the same derivation as torch expressions: it is what the
+float64 CPU test differentiates against autograd, and the fp32 twin the GPU test compares the kernels with.  Per layer:
 
     Xcat = [x(t-2d) | x(t-d) | x(t) | c(t)]                 (B,T,kw*R+Cp)   gathered once per layer
     z    = Xcat W1cat^T + gb            (recomputed: only h = tanh*sigmoid was stored, 256 B/sample/layer instead of 768)
@@ -118,7 +121,9 @@ class StackTrainFunction(torch.autograd.Function):
         x_all = torch.empty(L, B, T, R, dtype=BF, device=dev)
         h_all = torch.empty(L, B, T, Hp, dtype=BF, device=dev)
         c_cl = torch.empty(B, T, Cp, dtype=BF, device=dev) if sh.C else None
-        save = _lib.StackSaved(_lib.ptr(x_all), _lib.ptr(h_all), _lib.ptr(c_cl))
+        r1 = torch.empty(B, T, sh.S, dtype=BF, device=dev)           # the head's two hidden activations (ReLU outputs)
+        r2 = torch.empty(B, T, sh.S, dtype=BF, device=dev)
+        save = _lib.StackSaved(_lib.ptr(x_all), _lib.ptr(h_all), _lib.ptr(c_cl), _lib.ptr(r1), _lib.ptr(r2))
         n = lib.wae_stack_workspace_bf16(pk.struct.d, B, T)
         ws = wn._ws.get(n, dev)
         _lib.check(lib.wae_stack_forward_bf16_save(pk.struct, _lib.ptr(xf), _lib.ptr(cf), _lib.ptr(gf), B, T, _lib.ptr(logits),
@@ -127,19 +132,154 @@ class StackTrainFunction(torch.autograd.Function):
         ctx.sh, ctx.dil = sh, list(sh.dilations)
         ctx.x_needs_grad = x.requires_grad
         ctx.c_present, ctx.g_present = c_up is not None, gvec is not None
-        ctx.save_for_backward(xf, gf, x_all, h_all, c_cl, *[None if w is None else w.detach() for w in weights])
+        if not hasattr(wn, "_ws_bwd"):
+            wn._ws_bwd = packing.WorkspaceCache()
+        ctx.pk, ctx.ws_cache = pk, wn._ws_bwd
+        ctx.save_for_backward(xf, gf, x_all, h_all, c_cl, r1, r2, *[None if w is None else w.detach() for w in weights])
         return logits
 
     @staticmethod
     def backward(ctx, dlogits):
-        xf, gf, x_all, h_all, c_cl, *weights = ctx.saved_tensors
-        dxin, dc_up, dgvec, grads = stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, ctx.x_needs_grad)
+        xf, gf, x_all, h_all, c_cl, r1, r2, *weights = ctx.saved_tensors
+        dxin, dc_up, dgvec, grads = stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, ctx.x_needs_grad,
+                                                   r1=r1, r2=r2, pk=ctx.pk, ws_cache=ctx.ws_cache)
         return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, *grads)
 
 
-def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_needs_grad=False, cdt=BF, adt=torch.float32):
+def tc_backward_supported(sh) -> bool:
+    """Shapes wae_stack_backward_bf16 covers (include/wae_b200.h): every preset of the reference with G <= 256."""
+    return (sh.R % 64 == 0 and sh.R <= 256 and sh.S % 64 == 0 and sh.S <= 256 and _ru(sh.H, 16) <= 128 and sh.O % 16 == 0
+            and sh.O <= 256 and 1 <= sh.kernel_size <= 5)
+
+
+def _ru(x, m):
+    return (x + m - 1) // m * m
+
+
+def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache):
+    """The backward on the tensor cores: pack the transposed weights, one call of wae_stack_backward_bf16, scatter the packed
+    fp32 gradients to the parameter shapes.  Same return value as stack_backward."""
+    lib = _lib.lib()
+    L, R, G, H, S, C, O, kw, Gi = sh.layers, sh.R, sh.G, sh.H, sh.S, sh.C, sh.O, sh.kernel_size, sh.Gi
+    _, B, T, _ = x_all.shape
+    dev = x_all.device
+    Hh, Hp, Cp = _ru(H, 16), _ru(H, 64), (_ru(C, 64) if C else 0)
+    Gp = 2 * Hh
+    Gq, K1p = _ru(Gp, 64), kw * R + Cp
+    f32 = torch.float32
+
+    def lw(l, k):
+        return weights[l * PER_LAYER + k]
+
+    base = L * PER_LAYER
+    Wf, W3, W4 = weights[base], weights[base + 2], weights[base + 4]
+    rows = torch.cat([torch.arange(H, device=dev), Hh + torch.arange(H, device=dev)])     # natural gate row -> packed row
+    # ---- weights in the transposed K-major forms of the dgrad GEMMs (tiny tensors, a handful of launches for all layers) ----
+    W1 = torch.stack([lw(l, 0) for l in range(L)]).float()                                  # (L,G,R,kw)
+    wdx = torch.zeros(L, R, kw, Gq, dtype=f32, device=dev)
+    wdx[:, :, :, rows] = W1.permute(0, 2, 3, 1)
+    wdx = wdx.reshape(L, R, kw * Gq).to(BF).contiguous()
+    Ws = torch.stack([lw(l, 6)[:, :, 0] for l in range(L)]).float()                         # (L,S,H)
+    Wo = torch.stack([lw(l, 4)[:, :, 0] for l in range(L)]).float()                         # (L,R,H)
+    wdh = torch.zeros(L, Hp, S + R, dtype=f32, device=dev)
+    wdh[:, :H, :S] = Ws.transpose(1, 2)
+    wdh[:, :H, S:] = Wo.transpose(1, 2)
+    wdh = wdh.to(BF).contiguous()
+    wct = None
+    if C:
+        Wc = torch.stack([lw(l, 2)[:, :, 0] for l in range(L)]).float()                     # (L,G,C)
+        wct = torch.zeros(Cp, L, Gq, dtype=f32, device=dev)
+        wct[:C][:, :, rows] = Wc.permute(2, 0, 1)
+        wct = wct.reshape(Cp, L * Gq).to(BF).contiguous()
+    w4t = W4[:, :, 0].float().t().to(BF).contiguous()                                        # (S,O)
+    w3t = W3[:, :, 0].float().t().to(BF).contiguous()                                        # (S,S)
+    # ---- outputs ----
+    sizes = dict(dw1=L * Gp * K1p, dwo=L * R * Hp, dws=S * L * Hp, dw3=S * S, dw4=O * S, dgb=L * B * Gp, dbo=L * R, dbs=S, db3=S, db4=O)
+    flat = torch.empty(sum(sizes.values()), dtype=f32, device=dev)                          # zeroed by the call
+    o, off = {}, 0
+    for k, n in sizes.items():
+        o[k] = flat[off:off + n]
+        off += n
+    dc = torch.empty(B, T, Cp, dtype=f32, device=dev) if C else None
+    dx0 = torch.empty(B, T, R, dtype=BF, device=dev)
+    bw = _lib.StackBwd()
+    for name, t in (("wdh", wdh), ("wdx", wdx), ("wct", wct), ("w4t", w4t), ("w3t", w3t), ("x_all", x_all), ("h_all", h_all),
+                    ("c_cl", c_cl), ("r1", r1), ("r2", r2), ("gemb", gf if (Gi and gf is not None) else None), ("dc", dc), ("dx0", dx0)):
+        setattr(bw, name, _lib.ptr(t))
+    for k in sizes:
+        setattr(bw, k, o[k].data_ptr())
+    dl = dlogits.float().contiguous()
+    n = lib.wae_stack_backward_workspace_bf16(pk.struct.d, B, T)
+    ws = ws_cache.get(n, dev) if ws_cache is not None else torch.empty(n, dtype=torch.uint8, device=dev)
+    _lib.check(lib.wae_stack_backward_bf16(pk.struct, bw, _lib.ptr(dl), B, T, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+               "wae_stack_backward_bf16")
+    # ---- scatter to the parameter shapes ----
+    grads = [None] * len(weights)
+    dw1 = o["dw1"].view(L, Gp, K1p)[:, rows]                                                # (L,G,K1p) natural gate rows
+    dW1 = dw1[:, :, :kw * R].reshape(L, G, kw, R).permute(0, 1, 3, 2)                       # (L,G,R,kw)
+    dWc = dw1[:, :, kw * R: kw * R + C] if C else None
+    dgb = o["dgb"].view(L, B, Gp)[:, :, rows]                                               # (L,B,G)
+    dwo, dws = o["dwo"].view(L, R, Hp), o["dws"].view(S, L, Hp)
+    dgvec = torch.zeros_like(gf, dtype=f32) if gf is not None else None
+    if Gi and gf is not None:
+        Wg = torch.stack([lw(l, 3)[:, :, 0] for l in range(L)]).float()                     # (L,G,Gi)
+        dWg = (dgb.unsqueeze(-1) * gf.float()[None, :, None, :]).sum(1)                     # (L,G,Gi): tiny, element-wise
+        dgvec = (dgb.unsqueeze(-1) * Wg.unsqueeze(1)).sum(2).sum(0)                         # (B,Gi)
+    db1 = dgb.sum(1)
+    for l in range(L):
+        k = l * PER_LAYER
+        grads[k + 0] = dW1[l]
+        if lw(l, 1) is not None:
+            grads[k + 1] = db1[l]
+        if C:
+            grads[k + 2] = dWc[l].unsqueeze(-1)
+        if Gi and gf is not None and lw(l, 3) is not None:
+            grads[k + 3] = dWg[l].unsqueeze(-1)
+        if l < L - 1:                       # the last layer's residual branch is dead: no gradient, as under autograd in the reference
+            grads[k + 4] = dwo[l, :, :H].unsqueeze(-1)
+            if lw(l, 5) is not None:
+                grads[k + 5] = o["dbo"].view(L, R)[l]
+        grads[k + 6] = dws[:, l, :H].unsqueeze(-1)
+        if lw(l, 7) is not None:
+            grads[k + 7] = o["dbs"]
+    grads[base + 2] = o["dw3"].view(S, S).unsqueeze(-1)
+    if weights[base + 3] is not None:
+        grads[base + 3] = o["db3"]
+    grads[base + 4] = o["dw4"].view(O, S).unsqueeze(-1)
+    if weights[base + 5] is not None:
+        grads[base + 5] = o["db4"]
+    # ---- first conv: x0 = Wf x + bf.  dWf = dx0^T x^T as one more MN-major wgrad over the transposed-cast input ----
+    Oin = xf.shape[1]
+    st = _lib.stream_ptr(dev)
+    dWf = torch.zeros(R, _ru(Oin, 16), dtype=f32, device=dev)
+    if Oin % 16 == 0 and B <= 65535:
+        xT = torch.empty(B, T, Oin, dtype=BF, device=dev)                                   # exact for the one-hot input of every preset
+        _lib.check(lib.wae_train_transpose_cast(_lib.ptr(xf), B, Oin, T, _lib.ptr(xT), st), "wae_train_transpose_cast")
+        _lib.check(lib.wae_gemm_bf16_nt(_lib.ptr(dx0), _lib.ptr(xT), _lib.ptr(dWf), R, Oin, B * T, st), "wae_gemm_bf16_nt")
+        grads[base] = dWf[:, :Oin].unsqueeze(-1)
+    else:                                                                                    # scalar input (Oin = 1): a weighted column sum
+        grads[base] = (dx0.float() * xf.transpose(1, 2).float()).sum((0, 1)).reshape(R, Oin, 1) if Oin == 1 else \
+            torch.einsum("btr,bot->ro", dx0.float(), xf.float()).unsqueeze(-1)
+    if weights[base + 1] is not None:
+        dbf = torch.zeros(R, dtype=f32, device=dev)
+        _lib.check(lib.wae_colsum_bf16(_lib.ptr(dx0), B, T, R, 0, _lib.ptr(dbf), st), "wae_colsum_bf16")
+        grads[base + 1] = dbf
+    dxin = None
+    if x_needs_grad:
+        dxin = (dx0.float() @ Wf[:, :, 0].float()).transpose(1, 2).contiguous()
+    dc_up = dc[..., :C].transpose(1, 2).contiguous() if C else None
+    grads = [g if g is None or w is None else g.to(w.dtype).reshape(w.shape) for g, w in zip(grads, weights)]
+    return dxin, dc_up, dgvec, grads
+
+
+def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_needs_grad=False, cdt=BF, adt=torch.float32,
+                   r1=None, r2=None, pk=None, ws_cache=None):
     """Hand-derived backward of the decoder stack on saved channels-last activations.  cdt: GEMM operand dtype (bf16 on the
-    GPU), adt: accumulation / element-wise dtype.  tests/test_host_cpu.py runs it in float64 against torch autograd."""
+    GPU), adt: accumulation / element-wise dtype.  tests/test_host_cpu.py runs it in float64 against torch autograd.  With
+    bf16 CUDA tensors, the head's saved hidden activations (r1, r2) and the packed forward weights (pk) it runs on the
+    tensor-core kernels (_stack_backward_tc); shapes those do not cover keep the library-GEMM composite below."""
+    if cdt == BF and x_all.is_cuda and r1 is not None and r2 is not None and pk is not None and tc_backward_supported(sh):
+        return _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache)
     if True:
         L, R, G, H, S, C, O, kw = sh.layers, sh.R, sh.G, sh.H, sh.S, sh.C, sh.O, sh.kernel_size
         _, B, T, _ = x_all.shape
