@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_kernel(const __grid_const
 // ---------------------------------------------------------------------------------------------
 // column sums (bias gradients): out[plane or 0][n] += sum_t src[plane][t][n]
 // ---------------------------------------------------------------------------------------------
-constexpr int CSUM_ROWS = 512;
+constexpr int CSUM_ROWS = 128;     // rows per block: 8 row lanes x 16 rows, 4 independent 16-byte loads in flight per thread
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int T, int N, int per_plane, float* __restrict__ out) {
     __shared__ float red[8][256 + 8];
     const int plane = blockIdx.y, t0 = blockIdx.x * CSUM_ROWS;
@@ -421,11 +421,20 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (c8 < n8) {
         const __nv_bfloat16* base = src + ((size_t)plane * T) * N;
-        for (int t = t0 + rl; t < t0 + CSUM_ROWS && t < T; t += 8) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(base + (size_t)t * N) + c8);
-            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { acc[2 * i] += bf_lo(w[i]); acc[2 * i + 1] += bf_hi(w[i]); }
+        for (int pass = 0; pass < CSUM_ROWS / 32; ++pass) {
+            uint4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int t = t0 + rl + 8 * (4 * pass + u);
+                v[u] = (t < T) ? __ldg(reinterpret_cast<const uint4*>(base + (size_t)t * N) + c8) : make_uint4(0u, 0u, 0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { acc[2 * i] += bf_lo(w[i]); acc[2 * i + 1] += bf_hi(w[i]); }
+            }
         }
     }
 #pragma unroll
