@@ -235,10 +235,18 @@ typedef struct wae_stack_bwd {
     const float* gemb;                                            /* (B, Gi) speaker vectors or NULL */
     float *dw1, *dwo, *dws, *dw3, *dw4, *dgb, *dbo, *dbs, *db3, *db4, *dc;
     void* dx0;
+    const void* dy;   /* optional: d loss / d logits already as (B,T,O) bf16 (wae_train_ce_grad); then dlogits may be NULL */
 } wae_stack_bwd;
 size_t wae_stack_backward_workspace_bf16(const wae_stack_dims* d, int B, int T);
 int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
                             size_t workspace_bytes, void* stream);
+/*
+ * Gradient of the teacher-forced cross-entropy (vqwae_train.py:760-766, mask of ones; the loss itself: wae_nll_sum) written
+ * straight into the backward's operand: dY[b][t][o] = (softmax_o(logits[b][:][t]) - [o == target[b][t+shift]]) * g * inv_n for
+ * t < T - shift, 0 after; (B,T,O) bf16.  g = *gscale (device scalar: the upstream gradient of the loss) or 1 if NULL.
+ */
+int wae_train_ce_grad(const float* logits, const int64_t* target, int B, int O, int T, int shift, const float* gscale, float inv_n,
+                      void* dY, void* stream);
 /* Unit-test entries of the two backward kernel families: C[M][N] fp32 += A^T B (A [K][M], B [K][N] bf16, MN-major operands,
  * split-K), and out[M][N] bf16 = (A[M][K] W[N][K]^T) * alpha. */
 int wae_gemm_bf16_nt(const void* A, const void* B, float* C, int M, int N, int K, void* stream);

@@ -47,7 +47,7 @@ class StackSaved(C.Structure):
 
 class StackBwd(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("wdh", "wdx", "wct", "w4t", "w3t", "x_all", "h_all", "c_cl", "r1", "r2", "gemb",
-                                           "dw1", "dwo", "dws", "dw3", "dw4", "dgb", "dbo", "dbs", "db3", "db4", "dc", "dx0")]
+                                           "dw1", "dwo", "dws", "dw3", "dw4", "dgb", "dbo", "dbs", "db3", "db4", "dc", "dx0", "dy")]
 
 
 class ArWeights(C.Structure):
@@ -107,6 +107,7 @@ SIGNATURES = {
     "wae_stack_backward_workspace_bf16": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),
     "wae_stack_backward_bf16": (C.c_int, [C.POINTER(StackBF16), C.POINTER(StackBwd), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                           C.c_void_p]),
+    "wae_train_ce_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "wae_colsum_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wae_gemm_bf16_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wae_gemm_bf16_tn_bf16out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),

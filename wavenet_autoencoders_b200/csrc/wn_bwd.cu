@@ -596,7 +596,7 @@ size_t wae_stack_backward_workspace_bf16(const wae_stack_dims* d, int B, int T) 
 int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
                             size_t workspace_bytes, void* stream_) {
     if (int rc = wae::require_sm100()) return rc;
-    WAE_REQUIRE(w && bw && dlogits && workspace, "wae_stack_backward_bf16: null pointer");
+    WAE_REQUIRE(w && bw && (dlogits || bw->dy) && workspace, "wae_stack_backward_bf16: null pointer");
     const wae_stack_dims& d = w->d;
     const int L = d.layers, R = d.R, S = d.S, C = d.C, O = d.O, kw = d.kernel_size, H = d.G / 2;
     const int Hh = (H + 15) / 16 * 16, Gp = 2 * Hh, Gq = (Gp + 63) / 64 * 64, Hp = (H + 63) / 64 * 64;
@@ -626,7 +626,12 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
     WAE_CHECK_CUDA(cudaMemsetAsync(bw->db3, 0, (size_t)S * 4, st));
     WAE_CHECK_CUDA(cudaMemsetAsync(bw->db4, 0, (size_t)Op * 4, st));
     if (int rc = wae::launch_gbias_bf16(w->b1, w->wg, bw->gemb, L, B, d.G, (w->wg && bw->gemb) ? d.Gi : 0, Hh, ws.gb, st)) return rc;
-    if (int rc = wae_train_transpose_cast(dlogits, B, O, T, ws.dY, stream_)) return rc;
+    if (bw->dy != nullptr) {
+        WAE_REQUIRE((reinterpret_cast<uintptr_t>(bw->dy) & 127) == 0, "wae_stack_backward_bf16: dy must be 128-byte aligned");
+        ws.dY = static_cast<__nv_bfloat16*>(const_cast<void*>(bw->dy));
+    } else if (int rc = wae_train_transpose_cast(dlogits, B, O, T, ws.dY, stream_)) {
+        return rc;
+    }
 
     // ---- tensor maps: every activation tensor once with 128-row boxes (GEMM rows) and once with 64-row boxes (wgrad k-blocks) ----
     CUtensorMap m_dY, m_dY64, m_r1, m_r1_64, m_r2, m_r2_64, m_dp2, m_dp2_64, m_dS, m_dS64, m_h64, m_x, m_x64, m_c, m_c64, m_dz, m_dz64;

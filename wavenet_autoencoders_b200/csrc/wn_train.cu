@@ -352,3 +352,76 @@ extern "C" int wae_train_transpose_cast(const float* in, int B, int O, int T, vo
     WAE_CHECK_LAUNCH();
     return WAE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// gradient of the teacher-forced cross-entropy, straight into the backward's (B,T,O) bf16 operand
+// ---------------------------------------------------------------------------------------------
+// loss = 1/N sum_{b, t < T-shift} [ logsumexp_o logits[b][:][t] - logits[b][target[b][t+shift]][t] ]   (vqwae_train.py:760-766 with a
+// mask of ones).  d loss / d logits[b][o][t] = (softmax_o - [o == target]) * g / N for t < T - shift, 0 after; written transposed and
+// cast: one pass over the fp32 logits replaces log_softmax backward + the (B,O,T) -> (B,T,O) transposing cast.  g is read from
+// device memory (the upstream gradient of the scalar loss) so that nothing syncs and the launch can sit in a CUDA graph.
+namespace {
+constexpr int CE_T = 64;
+__global__ void __launch_bounds__(256)
+ce_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ target, int O, int T, int shift, const float* __restrict__ gscale,
+               float inv_n, __nv_bfloat16* __restrict__ dY) {
+    extern __shared__ float ce_tile[];            // [O][CE_T + 1]
+    __shared__ float s_max[CE_T], s_inv[CE_T];
+    __shared__ int s_tgt[CE_T];
+    const int b = blockIdx.y, t0 = blockIdx.x * CE_T, tid = threadIdx.x;
+    const float* src = logits + (size_t)b * O * T;
+    for (int e = tid; e < O * CE_T; e += 256) {
+        const int o = e / CE_T, tt = e - o * CE_T, t = t0 + tt;
+        ce_tile[o * (CE_T + 1) + tt] = (t < T) ? __ldg(&src[(size_t)o * T + t]) : 0.f;
+    }
+    if (tid < CE_T) {
+        const int t = t0 + tid;
+        s_tgt[tid] = (t + shift < T) ? (int)__ldg(&target[(size_t)b * T + t + shift]) : -1;
+    }
+    __syncthreads();
+    {   // 4 threads per time step: max, then sum of exp
+        const int tt = tid >> 2, part = tid & 3;
+        float m = -INFINITY;
+        for (int o = part; o < O; o += 4) m = fmaxf(m, ce_tile[o * (CE_T + 1) + tt]);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        float sum = 0.f;
+        for (int o = part; o < O; o += 4) sum += __expf(ce_tile[o * (CE_T + 1) + tt] - m);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (part == 0) { s_max[tt] = m; s_inv[tt] = 1.f / sum; }
+    }
+    __syncthreads();
+    const float g = (gscale != nullptr ? __ldg(gscale) : 1.f) * inv_n;
+    const int o8n = O >> 3;
+    for (int e = tid; e < CE_T * o8n; e += 256) {
+        const int tt = e / o8n, o0 = (e - tt * o8n) * 8, t = t0 + tt;
+        if (t >= T) break;
+        const int tg = s_tgt[tt];
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float p = __expf(ce_tile[(o0 + i) * (CE_T + 1) + tt] - s_max[tt]) * s_inv[tt];
+            v[i] = (tg >= 0) ? (p - ((o0 + i) == tg ? 1.f : 0.f)) * g : 0.f;
+        }
+        *reinterpret_cast<uint4*>(dY + ((size_t)b * T + t) * O + o0) = pack8(v);
+    }
+}
+}  // namespace
+
+extern "C" int wae_train_ce_grad(const float* logits, const int64_t* target, int B, int O, int T, int shift, const float* gscale, float inv_n,
+                                 void* dY, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(logits && target && dY, "wae_train_ce_grad: null pointer");
+    WAE_REQUIRE(B > 0 && B <= 65535 && O >= 8 && O % 8 == 0 && O <= 512 && T > 0 && shift >= 0 && shift < T, "wae_train_ce_grad: B=%d O=%d T=%d shift=%d", B, O, T, shift);
+    const size_t smem = (size_t)O * (CE_T + 1) * sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(ce_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * (CE_T + 1) * 4));
+        attr_set = true;
+    }
+    ce_grad_kernel<<<dim3((unsigned)((T + CE_T - 1) / CE_T), (unsigned)B), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+        logits, reinterpret_cast<const long long*>(target), O, T, shift, gscale, inv_n, static_cast<__nv_bfloat16*>(dY));
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}

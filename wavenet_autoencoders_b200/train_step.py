@@ -78,13 +78,17 @@ class FlatAdam:
         packing.bump_generation()        # parameters changed through raw pointers: packed-weight caches must re-pack
 
 
-def train_step(model, opt, idx, mfcc, g, clip=100.0, world=1, timers=None):
+def train_step(model, opt, idx, mfcc, g, clip=100.0, world=1, timers=None, fused_loss=True):
     """idx (B,T) int64 mu-law classes; mfcc (B,39,frames); g (B,1) speaker ids.  Returns the loss tensor (no sync)."""
     x = F.one_hot(idx, 256).float().transpose(1, 2)                        # the collate's one-hot input (vqwae_train.py:509-520)
     opt.zero_grad(set_to_none=True)
-    y_hat, vq_loss, _ = model(x, mfcc, g)                                  # vqvae_model.py:64-71
     # vqwae_train.py:760-766: y_hat[:, :, :-1] predicts y[:, 1:]; full-length synthetic windows -> the mask is all ones
-    loss = F.cross_entropy(y_hat[:, :, :-1], idx[:, 1:]) + vq_loss
+    if fused_loss and hasattr(model, "forward_nll"):
+        nll, vq_loss, _ = model.forward_nll(x, mfcc, g, idx, 1)            # decoder loss + backward fused (training.StackNLLFunction)
+        loss = nll + vq_loss
+    else:
+        y_hat, vq_loss, _ = model(x, mfcc, g)                              # vqvae_model.py:64-71
+        loss = F.cross_entropy(y_hat[:, :, :-1], idx[:, 1:]) + vq_loss
     loss.backward()
     flat = isinstance(opt, FlatAdam)
     if world > 1:

@@ -146,6 +146,44 @@ class StackTrainFunction(torch.autograd.Function):
         return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, *grads)
 
 
+class StackNLLFunction(torch.autograd.Function):
+    """Decoder stack + teacher-forced cross-entropy in one autograd node (training side): the forward returns
+    the scalar loss of vqwae_train.py:760-766 (mask of ones) from one pass over the logits (wae_nll_sum); the backward writes
+    softmax - onehot straight into the (B,T,O) bf16 operand of the tensor-core backward (wae_train_ce_grad) -- no log_softmax
+    forward / backward kernels, no (B,O,T) gradient tensor, no transposing cast."""
+
+    @staticmethod
+    def forward(ctx, wn, x, c_up, gvec, target, shift, *weights):
+        logits = StackTrainFunction.forward(ctx, wn, x, c_up, gvec, *weights)
+        B, O, T = logits.shape
+        tgt = target.detach().long().contiguous()
+        out = torch.zeros(1, dtype=torch.float64, device=logits.device)
+        _lib.check(_lib.lib().wae_nll_sum(_lib.ptr(logits), _lib.ptr(tgt), B, O, T, int(shift), _lib.ptr(out), _lib.stream_ptr(logits.device)),
+                   "wae_nll_sum")
+        ctx.logits, ctx.target, ctx.shift = logits, tgt, int(shift)
+        return (out[0] / float(B * (T - shift))).float()
+
+    @staticmethod
+    def backward(ctx, dloss):
+        xf, gf, x_all, h_all, c_cl, r1, r2, *weights = ctx.saved_tensors
+        logits, B, O, T = ctx.logits, *ctx.logits.shape
+        if not tc_backward_supported(ctx.sh):
+            raise _lib.WaeError("forward_nll needs the tensor-core backward (R, S multiples of 64, G <= 256, O % 16 == 0)")
+        dy = torch.empty(B, T, O, dtype=BF, device=logits.device)
+        gs = dloss.detach().float().reshape(1).contiguous()
+        _lib.check(_lib.lib().wae_train_ce_grad(_lib.ptr(logits), _lib.ptr(ctx.target), B, O, T, ctx.shift, _lib.ptr(gs),
+                                                1.0 / float(B * (T - ctx.shift)), _lib.ptr(dy), _lib.stream_ptr(logits.device)),
+                   "wae_train_ce_grad")
+        dxin, dc_up, dgvec, grads = _stack_backward_tc(ctx.sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, None, ctx.x_needs_grad,
+                                                       ctx.pk, ctx.ws_cache, dy=dy)
+        return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, None, None, *grads)
+
+
+def stack_nll_train(wn, x, c_up, gvec, target, shift=1):
+    """Scalar teacher-forced NLL with autograd through the tcgen05 forward / backward (StackNLLFunction)."""
+    return StackNLLFunction.apply(wn, x, c_up, gvec, target, shift, *live_weights(wn))
+
+
 def tc_backward_supported(sh) -> bool:
     """Shapes wae_stack_backward_bf16 covers (include/wae_b200.h): every preset of the reference with G <= 256."""
     return (sh.R % 64 == 0 and sh.R <= 256 and sh.S % 64 == 0 and sh.S <= 256 and _ru(sh.H, 16) <= 128 and sh.O % 16 == 0
@@ -156,7 +194,7 @@ def _ru(x, m):
     return (x + m - 1) // m * m
 
 
-def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache):
+def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, dy=None):
     """The backward on the tensor cores: pack the transposed weights, one call of wae_stack_backward_bf16, scatter the packed
     fp32 gradients to the parameter shapes.  Same return value as stack_backward."""
     lib = _lib.lib()
@@ -208,7 +246,8 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
         setattr(bw, name, _lib.ptr(t))
     for k in sizes:
         setattr(bw, k, o[k].data_ptr())
-    dl = dlogits.float().contiguous()
+    bw.dy = _lib.ptr(dy)                                 # (B,T,O) bf16 from wae_train_ce_grad, or None: transpose-cast dlogits
+    dl = None if dy is not None else dlogits.float().contiguous()
     n = lib.wae_stack_backward_workspace_bf16(pk.struct.d, B, T)
     ws = ws_cache.get(n, dev) if ws_cache is not None else torch.empty(n, dtype=torch.uint8, device=dev)
     _lib.check(lib.wae_stack_backward_bf16(pk.struct, bw, _lib.ptr(dl), B, T, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),

@@ -113,6 +113,12 @@ class VQVAE(nn.Module):
         quant, vq_loss, perp = self.vq(self.encoder(c))
         return self.wavenet(x, quant, g, softmax), vq_loss, perp
 
+    def forward_nll(self, x, c, g, target, shift=1):
+        """Additive: (teacher-forced NLL of the decoder, vq_loss, perplexity) -- the three quantities the reference's training
+        step combines (vqwae_train.py:752-766) -- with loss and backward of the decoder fused (WaveNet.forward_nll)."""
+        quant, vq_loss, perp = self.vq(self.encoder(c))
+        return self.wavenet.forward_nll(x, quant, g, target, shift), vq_loss, perp
+
     def incremental_forward(self, initial_input, c, g, T, softmax, quantize, tqdm, log_scale_min, **extra):
         """vqvae_model.py:74-80.  ``extra``: the additive keywords of ``WaveNet.incremental_forward`` (``uniforms``,
         ``generator``, ``return_indices``), passed through."""

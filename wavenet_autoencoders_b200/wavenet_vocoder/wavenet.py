@@ -203,6 +203,32 @@ class WaveNet(nn.Module):
             out = self.stack_forward(x, c, gvec, last_stage=last_stage, x_is_index=x_idx is not None)
         return F.softmax(out, dim=1) if softmax else out
 
+    def forward_nll(self, x, c=None, g=None, target=None, shift=1):
+        """Additive: the reference's training criterion in one call -- mean over b, t < T - shift of the cross-entropy between
+        ``forward(x, c, g)[:, :, t]`` and ``target[:, t + shift]`` (vqwae_train.py:760-766 with a mask of ones) -- as a 0-dim
+        tensor.  With gradients required (bf16 kernels) loss and backward run fused (training.StackNLLFunction): the
+        (B,O,T) log-softmax and its gradient are never materialised.  Without, it is ``losses.teacher_forced_nll``."""
+        from .. import losses, training
+        needs_grad = torch.is_grad_enabled() and ((c is not None and c.requires_grad) or any(p.requires_grad for p in self.parameters()))
+        fused = (needs_grad and self.train_impl == "kernels" and self.precision == "bf16" and x.is_cuda
+                 and training.tc_backward_supported(packing.stack_shape(self))
+                 and not (self.training and any(f.dropout > 0 for f in self.conv_layers)))
+        if not fused:
+            y = self.forward(x, c, g)
+            if needs_grad:
+                return F.cross_entropy(y[:, :, :y.size(-1) - shift], target[:, shift:])
+            return losses.teacher_forced_nll(y, target, shift)
+        if not torch.is_floating_point(x) and x.dim() == 2 and not self.scalar_input:
+            x = F.one_hot(x.long(), self.out_channels).float().transpose(1, 2)
+        B = x.size(0)
+        gvec = self._speaker_vectors(g, B)
+        if c is not None and self.upsample_net is not None:
+            c = self.upsample_net(c)
+            if c.size(-1) != x.size(-1):
+                print(f"c {c.size() } x {x.size()}")
+                raise Exception
+        return training.stack_nll_train(self, x, c, gvec, target, shift)
+
     def stack_forward(self, x, c_up, gvec, precision=None, last_stage=None, x_is_index=False):
         """The hot path proper: first_conv + residual stack + head on already-upsampled conditioning (or, with
         ``last_stage=(filter, scale)``, on the frames entering the last upsampler stage; bf16 only).  ``x_is_index``: x is
