@@ -192,6 +192,15 @@ int wae_stack_forward_bf16_idx(const wae_stack_bf16* w, const int64_t* x_idx, co
                                const float* up_filter, const float* gemb, int B, int T, float* logits, void* workspace,
                                size_t workspace_bytes, void* stream);
 /*
+ * Forward from class indices with the teacher-forced NLL taken straight from the head kernel's logits accumulator in TMEM
+ * (SURVEY 8 row f2): *out_sum += sum over b, t < T - shift of logsumexp_o(logits[b][:][t]) - logits[b][target[b][t+shift]][t]
+ * (vqwae_train.py:760-766, mask of ones; the caller zeroes out_sum and divides by B * (T - shift)).  logits may be NULL: then the
+ * (B,O,T) fp32 tensor (262 MB at BASELINE config 2) is neither written nor read.  Other arguments as wae_stack_forward_bf16_idx.
+ */
+int wae_stack_nll_bf16_idx(const wae_stack_bf16* w, const int64_t* x_idx, const float* c, int Tc, int up_scale, const float* up_filter,
+                           const float* gemb, int B, int T, const int64_t* target, int shift, double* out_sum, float* logits,
+                           void* workspace, size_t workspace_bytes, void* stream);
+/*
  * Teacher-forced negative log-likelihood summed over b and t < T - shift, straight from the logits:
  * *out_sum += sum logsumexp_o(logits[b][:][t]) - logits[b][target[b][t+shift]][t]   (vqwae_train.py:760-766, mask of ones).
  * One pass over the logits; the caller zeroes out_sum and divides by B * (T - shift).

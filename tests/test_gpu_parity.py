@@ -135,9 +135,32 @@ def test_forward_bf16_from_class_indices_and_fused_nll():
     ref = torch.nn.functional.cross_entropy(y_idx[:, :, :-1], idx[:, 1:])
     got = teacher_forced_nll(y_idx, idx)
     assert abs(float(got) - float(ref)) < 1e-5 * max(1.0, abs(float(ref)))
+    # NLL from the head kernel's accumulator, logits never written (wae_stack_nll_bf16_idx): row f2
+    with torch.no_grad():
+        fused = m.forward_nll(idx, c, spk, idx, 1)
+    assert abs(float(fused) - float(ref)) < 1e-6 * max(1.0, abs(float(ref))), (float(fused), float(ref))
     m.precision = "fp32"                       # no index kernel there: expanded to one-hot on the host side
     with torch.no_grad():
         assert torch.equal(m(idx, c, spk), m(x, c, spk))
+
+
+def test_head_fused_nll_at_benchmark_shape():
+    """wae_stack_nll_bf16_idx at the vqwae shape (ragged T, several utterances): loss from the TMEM accumulator == F.cross_entropy on
+    the logits the same kernels write; with logits_out the written logits are bit-identical to the plain forward's."""
+    cfg = T.CONFIGS["vqwae"]
+    m = build_model("vqwae", 1, "cuda")
+    m.precision = "bf16"
+    x, idx, c, spk = T.synth_inputs(cfg, 3, 1920, 5)
+    idx, c, spk = idx.cuda(), c.cuda(), spk.cuda()
+    with torch.no_grad():
+        y = m(idx, c, spk)
+        ref = torch.nn.functional.cross_entropy(y[:, :, :-1].double(), idx[:, 1:])
+        got = m.forward_nll(idx, c, spk, idx, 1)
+        lg = torch.empty_like(y)
+        got2 = m._nll_from_indices(idx, c, spk, idx, 1, logits_out=lg)
+    assert abs(float(got) - float(ref)) < 1e-6 * max(1.0, abs(float(ref))), (float(got), float(ref))
+    assert float(got) == float(got2) or abs(float(got) - float(got2)) < 1e-6
+    assert torch.equal(lg, y)
 
 
 def test_forward_ragged_tail_and_dense_input_fp32_bf16():

@@ -2064,6 +2064,9 @@ struct HeadArgs {
     float* logits;       // (B, O, T)
     float scale;         // sqrt(1/L)
     int B, T, L, S, O, Op, Hp, tiles_per_utt;
+    const long long* target;  // optional (B,T) classes: teacher-forced NLL straight from the logits accumulator (vqwae_train.py:760-766)
+    double* nll_sum;          // += sum over b, t < T - shift of logsumexp_o(logits[b][:][t]) - logits[b][target[b][t+shift]][t]
+    int shift;
     int save;            // training forward: the two ReLU outputs (the head's hidden activations) are kept for the backward
     CUtensorMap tm_r1;   // [B][T][S] bf16, box {64, 128}: relu(skip sum * sqrt(1/L))
     CUtensorMap tm_r2;   // [B][T][S] bf16: relu(W3 r1 + b3)
@@ -2192,6 +2195,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_kernel(const __gri
         const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t act_addr = smem_u32(act);
+        float* nll_red = reinterpret_cast<float*>(bars) + 64;        // [LAYER_NCG][3][BM] floats behind the barriers
+        double nll_acc = 0.0;
         int it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
             const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
@@ -2244,20 +2249,58 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_kernel(const __gri
 
             mbar_wait(acc4_full, it & 1);
             tc_fence_after();
+            // loss straight from the accumulator: every thread holds 1/4 of the classes of its time step --
+            // running max / sum of exponentials / the target's logit per thread, merged over the four column groups below
+            const bool want_nll = (a.target != nullptr);
+            const int tgt = (want_nll && live && t + a.shift < a.T) ? (int)__ldg(a.target + (size_t)b * a.T + t + a.shift) : -1;
+            float r_max = -INFINITY, r_sum = 0.f, r_tgt = 0.f;
             for (int c0 = cg * 16; c0 < a.Op; c0 += LAYER_NCG * 16) {
                 float v[16];
                 tmem_ld16(tmem_34 + lane_base + c0, v);
                 tmem_ld_wait();
-                if (live) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += __ldg(a.b4 + c0 + i);
+                if (live && a.logits != nullptr) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
                         if (c0 + i < a.O)  // lanes of a warp = consecutive samples -> 128-byte coalesced rows
-                            a.logits[((size_t)b * a.O + c0 + i) * a.T + t] = v[i] + __ldg(a.b4 + c0 + i);
+                            a.logits[((size_t)b * a.O + c0 + i) * a.T + t] = v[i];
+                }
+                if (want_nll) {
+                    float m = r_max;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.O) m = fmaxf(m, v[i]);
+                    float s = r_sum * expf(r_max - m);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.O) { s += expf(v[i] - m); if (c0 + i == tgt) r_tgt = v[i]; }
+                    r_max = m; r_sum = s;
                 }
             }
             tc_fence_before();
             mbar_arrive(epi4_done);
+            if (want_nll) {
+                float* red = nll_red + (size_t)cg * 3 * BM;       // [column group][max | sum | target logit][row]
+                red[row] = r_max; red[BM + row] = r_sum; red[2 * BM + row] = r_tgt;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+                if (cg == 0) {
+                    float m = r_max, lt = r_tgt;
+                    for (int k = 1; k < LAYER_NCG; ++k) m = fmaxf(m, nll_red[(size_t)k * 3 * BM + row]);
+                    float ssum = r_sum * expf(r_max - m);
+                    for (int k = 1; k < LAYER_NCG; ++k) {
+                        ssum += nll_red[(size_t)k * 3 * BM + BM + row] * expf(nll_red[(size_t)k * 3 * BM + row] - m);
+                        lt += nll_red[(size_t)k * 3 * BM + 2 * BM + row];
+                    }
+                    float nll = (tgt >= 0) ? (m + logf(ssum)) - lt : 0.f;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) nll += __shfl_xor_sync(0xffffffffu, nll, off);
+                    if (lane == 0) nll_acc += (double)nll;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");   // nll_red is reused by the next tile
+            }
         }
+        if (a.target != nullptr && cg == 0 && lane == 0) atomicAdd(a.nll_sum, nll_acc);
         if (a.save && threadIdx.x == 64) tma_store_wait_all();
     }
     tc_fence_before();
@@ -2403,11 +2446,13 @@ size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T) {
     return carve(*d, B, T, nullptr).total;
 }
 
+struct NllRequest { const int64_t* target; int shift; double* out_sum; };
+
 static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, const int64_t* x_idx, const float* c, int up_s, const float* up_w,
                                    const float* gemb, int B, int T, float* logits, const wae_stack_saved* save,
-                                   void* workspace, size_t workspace_bytes, void* stream_) {
+                                   void* workspace, size_t workspace_bytes, void* stream_, const NllRequest* nll = nullptr) {
     if (int rc = wae::require_sm100()) return rc;
-    WAE_REQUIRE(w && (x || x_idx) && logits && workspace, "wae_stack_forward_bf16: null pointer");
+    WAE_REQUIRE(w && (x || x_idx) && (logits || nll) && workspace, "wae_stack_forward_bf16: null pointer");
     const wae_stack_dims& d = w->d;
     const int H = d.G / 2;
     WAE_REQUIRE(B > 0 && T > 0 && B <= 65535, "wae_stack_forward_bf16: B=%d T=%d", B, T);
@@ -2593,6 +2638,9 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     ha.bs_sum = w->bs_sum; ha.b3 = w->b3; ha.b4 = w->b4; ha.logits = logits;
     ha.scale = (float)sqrt(1.0 / (double)d.layers);
     ha.B = B; ha.T = T; ha.L = d.layers; ha.S = d.S; ha.O = d.O; ha.Op = Op; ha.Hp = Hp; ha.tiles_per_utt = tiles_per_utt;
+    ha.target = nll ? reinterpret_cast<const long long*>(nll->target) : nullptr;
+    ha.nll_sum = nll ? nll->out_sum : nullptr;
+    ha.shift = nll ? nll->shift : 0;
     ha.save = (save != nullptr && save->r1 != nullptr && save->r2 != nullptr) ? 1 : 0;
     ha.tm_r1 = ha.tm_h; ha.tm_r2 = ha.tm_h;
     if (ha.save) {
@@ -2600,7 +2648,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         if (int rc = make_tmap(&ha.tm_r1, save->r1, d.S, T, B, d.S, (uint64_t)T * d.S, BK, BM)) return rc;
         if (int rc = make_tmap(&ha.tm_r2, save->r2, d.S, T, B, d.S, (uint64_t)T * d.S, BK, BM)) return rc;
     }
-    const size_t smem_head = 1024 + (size_t)HEAD_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(d.S / BK) * A_TILE_BYTES + 256;
+    const size_t smem_head = 1024 + (size_t)HEAD_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(d.S / BK) * A_TILE_BYTES + 256 + LAYER_NCG * 3 * BM * 4;
     WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
     {
         ProfScope prof(2, stream);
@@ -2643,6 +2691,21 @@ int wae_stack_forward_bf16_idx(const wae_stack_bf16* w, const int64_t* x_idx, co
     }
     return stack_forward_bf16_impl(w, nullptr, x_idx, c, up_scale > 0 ? up_scale : 0, up_scale > 0 ? up_filter : nullptr, gemb, B, T,
                                    logits, nullptr, workspace, workspace_bytes, stream);
+}
+
+int wae_stack_nll_bf16_idx(const wae_stack_bf16* w, const int64_t* x_idx, const float* c, int Tc, int up_scale, const float* up_filter,
+                           const float* gemb, int B, int T, const int64_t* target, int shift, double* out_sum, float* logits,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    WAE_REQUIRE(w && x_idx && target && out_sum, "wae_stack_nll_bf16_idx: null pointer");
+    WAE_REQUIRE(w->d.Oin > 1, "wae_stack_nll_bf16_idx: class indices need a one-hot-input model (Oin > 1)");
+    WAE_REQUIRE(shift >= 0 && shift < T, "wae_stack_nll_bf16_idx: shift %d", shift);
+    if (up_scale > 0) {
+        WAE_REQUIRE(c && up_filter && w->d.C > 0 && Tc >= 1 && (long long)Tc * up_scale == T,
+                    "wae_stack_nll_bf16_idx: %d frames x scale %d != T = %d", Tc, up_scale, T);
+    }
+    NllRequest rq{target, shift, out_sum};
+    return stack_forward_bf16_impl(w, nullptr, x_idx, c, up_scale > 0 ? up_scale : 0, up_scale > 0 ? up_filter : nullptr, gemb, B, T,
+                                   logits, nullptr, workspace, workspace_bytes, stream, &rq);
 }
 
 }  // extern "C"

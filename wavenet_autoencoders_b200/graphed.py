@@ -18,12 +18,14 @@ from .losses import teacher_forced_nll
 class GraphedForward:
     """``GraphedForward(model, idx, mfcc, g)`` captures ``model(idx, mfcc, g)`` (+ the teacher-forced NLL of vqwae_train.py:760-766)
     for the shapes of the example inputs; calling it with new inputs of the same shapes copies them in, replays the graph and
-    returns ``(logits, vq_loss, perplexity, nll)`` -- tensors owned by the graph, overwritten by the next call.
+    returns ``(logits, vq_loss, perplexity, nll)`` -- tensors owned by the graph, overwritten by the next call.  With
+    ``with_logits=False`` (loss-only evaluation) the NLL is taken from the head kernel's accumulator, the logits are never
+    materialised and ``logits`` is None.
 
     ``model`` is a ``vqvae_model.VQVAE`` (or any module with the same ``forward(x, c, g)``) in eval mode on a CUDA sm_100 device;
     ``idx`` are the (B,T) int64 mu-law classes (or the (B,O,T) one-hot tensor), ``mfcc`` the encoder input, ``g`` speaker ids."""
 
-    def __init__(self, model, idx, mfcc, g, with_nll: bool = True, warmup: int = 2):
+    def __init__(self, model, idx, mfcc, g, with_nll: bool = True, warmup: int = 2, with_logits: bool = True):
         if not (idx.is_cuda and mfcc.is_cuda and g.is_cuda):
             raise _lib.WaeError("GraphedForward: example inputs must be CUDA tensors (no CPU fallback)")
         if model.training:
@@ -32,9 +34,14 @@ class GraphedForward:
         self.idx, self.mfcc, self.g = idx.clone(), mfcc.clone(), g.clone()
         classes = self.idx if not torch.is_floating_point(self.idx) else None
         self.with_nll = bool(with_nll and classes is not None)
+        # loss-only evaluation: the NLL comes out of the head kernel's accumulator and the (B,O,T) logits are never written
+        self.loss_only = bool(self.with_nll and not with_logits and hasattr(model, "forward_nll"))
 
         def run():
             with torch.no_grad():
+                if self.loss_only:
+                    nll, vq_loss, perp = model.forward_nll(self.idx, self.mfcc, self.g, classes, 1)
+                    return None, vq_loss, perp, nll
                 logits, vq_loss, perp = model(self.idx, self.mfcc, self.g)
                 nll = teacher_forced_nll(logits, classes) if self.with_nll else None
             return logits, vq_loss, perp, nll

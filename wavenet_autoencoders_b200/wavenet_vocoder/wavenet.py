@@ -214,6 +214,9 @@ class WaveNet(nn.Module):
                  and training.tc_backward_supported(packing.stack_shape(self))
                  and not (self.training and any(f.dropout > 0 for f in self.conv_layers)))
         if not fused:
+            if (not needs_grad and self.precision == "bf16" and x.is_cuda and not torch.is_floating_point(x) and x.dim() == 2
+                    and not self.scalar_input):
+                return self._nll_from_indices(x, c, g, target, shift)
             y = self.forward(x, c, g)
             if needs_grad:
                 return F.cross_entropy(y[:, :, :y.size(-1) - shift], target[:, shift:])
@@ -228,6 +231,39 @@ class WaveNet(nn.Module):
                 print(f"c {c.size() } x {x.size()}")
                 raise Exception
         return training.stack_nll_train(self, x, c, gvec, target, shift)
+
+    def _nll_from_indices(self, x_idx, c, g, target, shift, logits_out=None):
+        """Inference, bf16, class-index input: the NLL comes out of the head kernel's accumulator (wae_stack_nll_bf16_idx);
+        the (B,O,T) logits are written only if ``logits_out`` is given."""
+        B, T = x_idx.shape
+        gvec = self._speaker_vectors(g, B)
+        up_w, up_s = None, 0
+        with torch.no_grad():
+            if c is not None and self.upsample_net is not None:
+                deferred = None
+                if isinstance(self.upsample_net, (upsample.UpsampleNetwork, upsample.ConvInUpsampleNetwork)):
+                    deferred = self.upsample_net(c, defer_last=True)
+                if deferred is not None:
+                    c, up_w, up_s = deferred
+                else:
+                    c = self.upsample_net(c)
+                if c.size(-1) * (up_s if up_s else 1) != T:
+                    print(f"c {c.size() } x {x_idx.size()}")
+                    raise Exception
+            xi = x_idx.detach().long().contiguous()
+            tg = target.detach().long().contiguous()
+            cf = None if c is None else c.detach().float().contiguous()
+            gv = None if gvec is None else gvec.detach().float().contiguous()
+            uw = None if up_w is None else up_w.detach().float().contiguous()
+            L, st = _lib.lib(), _lib.stream_ptr(xi.device)
+            pk = self._pack("bf16")
+            n = L.wae_stack_workspace_bf16(pk.struct.d, B, T)
+            ws = self._ws.get(n, xi.device)
+            out = torch.zeros(1, dtype=torch.float64, device=xi.device)
+            _lib.check(L.wae_stack_nll_bf16_idx(pk.struct, _lib.ptr(xi), _lib.ptr(cf), 0 if cf is None else cf.shape[-1], int(up_s), _lib.ptr(uw),
+                                                _lib.ptr(gv), B, T, _lib.ptr(tg), int(shift), _lib.ptr(out), _lib.ptr(logits_out), _lib.ptr(ws),
+                                                ws.numel(), st), "wae_stack_nll_bf16_idx")
+            return (out[0] / float(B * (T - shift))).float()
 
     def stack_forward(self, x, c_up, gvec, precision=None, last_stage=None, x_is_index=False):
         """The hot path proper: first_conv + residual stack + head on already-upsampled conditioning (or, with
