@@ -764,10 +764,13 @@ def test_incremental_scalar_samplers_match_reference(case, cfg_name):
     m = build_model(cfg_name, int(g["seed"]), "cuda")
     B, Tn = int(g["B"]), int(g["T"])
     _, _, c, spk = T.synth_inputs(cfg, B, Tn, int(g["in_seed"]))
-    for prec, atol in (("fp32", 2e-4), ("bf16", None)):
-        m.precision, m.ar_cluster = prec, 8
+    for prec, atol in (("fp32", 2e-4), ("bf16", None), ("bf16-simt", None)):
+        m.ar_impl = "simt" if prec.endswith("-simt") else "auto"
+        m.precision, m.ar_cluster = prec.split("-")[0], 8
         y = m.incremental_forward(initial_input=None, c=c.cuda(), g=spk.cuda(), T=Tn, uniforms=torch.tensor(g["u"]).cuda(),
                                   log_scale_min=-7.0)
+        # bf16: the tensor-core (mma.sync) kernel now carries the mixture samplers too; "-simt": ar_kernel<bf16>
+        assert m.last_ar_variant[0] == {"fp32": "fp32", "bf16": "bf16mma", "bf16-simt": "bf16"}[prec], m.last_ar_variant
         assert y.shape == (B, 1, Tn) and float(y.abs().max()) <= 1.0
         if atol is not None:
             np.testing.assert_allclose(y[:, 0].cpu().numpy(), g["samples"], atol=atol)

@@ -1442,8 +1442,49 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
         if (tid == 0) mbar_arrive_expect_tx(lg_full, lg_bytes);
 
         AR_PROF(10);
-        // ---- output / sampling (categorical or none; scalar-input models use the SIMT kernel) ----
-        if (warp < U) {
+        // ---- output / sampling: categorical / none, or the mixture samplers of scalar-input models (mixture.py:118-156,221-270) ----
+        if (warp < U && (a.sample_mode == WAE_AR_SAMPLE_MOL || a.sample_mode == WAE_AR_SAMPLE_GAUSS)) {
+            const int u = warp, b = cid * U + u;
+            const bool writer = (rank == 0 && b < a.B);
+            const float* lg = lgbuf + (size_t)u * O;
+            // O = 3*nmix (or 2 for a single gaussian): [logit | mean | log_scale]; same arithmetic as the SIMT kernel
+            const int nmix = a.nmix;
+            float best = -INFINITY;
+            int bi = 0x7fffffff;
+            if (nmix > 1 || a.sample_mode == WAE_AR_SAMPLE_MOL) {
+                if (lane < nmix) {   // gumbel-max over mixture logits (mixture.py:138-140); lane i holds uniform i
+                    const float uq = 1e-5f + u_pref * (1.0f - 2e-5f);
+                    best = lg[lane] - logf(-logf(uq));
+                    bi = lane;
+                }
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+                }
+            } else {
+                bi = 0;
+            }
+            float xs;
+            if (a.sample_mode == WAE_AR_SAMPLE_MOL) {
+                const float mean = lg[nmix + bi], ls = lg[2 * nmix + bi];
+                const float uq = 1e-5f + __shfl_sync(0xffffffffu, u_pref, nmix) * (1.0f - 2e-5f);
+                xs = mean + expf(ls) * (logf(uq) - logf(1.f - uq));     // mixture.py:151-152
+            } else {
+                float mean, ls;
+                if (O == 2) { mean = lg[0]; ls = lg[1]; }
+                else if (nmix == 1) { mean = lg[1]; ls = lg[2]; }
+                else { mean = lg[nmix + bi]; ls = lg[2 * nmix + bi]; }
+                xs = mean + expf(ls) * __shfl_sync(0xffffffffu, u_pref, nmix);                 // Normal(mean, exp(ls)).sample() with a supplied N(0,1) draw
+            }
+            xs = fminf(fmaxf(xs, -1.f), 1.f);
+            if (lane == 0) {
+                inbuf[u * Oin] = xs;
+                cur_idx[u] = -1;
+                if (writer && a.out_dense) a.out_dense[(size_t)b * a.T + t] = xs;
+            }
+        } else if (warp < U) {
             const int u = warp, b = cid * U + u;
             const bool writer = (rank == 0 && b < a.B);
             const float* lg = lgbuf + (size_t)u * O;
@@ -1639,8 +1680,6 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
     const int U = w->utts_per_cluster;
     if (w->wtype == 2) {
         // tensor-core variant: bf16 weights in the [rows%16][K+8] layout, bf16 conditioning / ring
-        WAE_REQUIRE(sample_mode == WAE_AR_SAMPLE_CATEGORICAL || sample_mode == WAE_AR_SAMPLE_NONE,
-                    "wae_ar_generate: the tensor-core variant samples categorical / none only (scalar-input models: wtype 0/1)");
         WAE_REQUIRE(U >= 1 && U <= UC, "wae_ar_generate: utts_per_cluster must be 1..8 for the tensor-core variant");
         WAE_REQUIRE(d.C % 8 == 0 && d.R % 16 == 0 && d.layers >= NPF_M, "wae_ar_generate: tensor-core variant needs C%%8==0, R%%16==0");
         a.utts = U;

@@ -404,11 +404,11 @@ class WaveNet(nn.Module):
                 uniforms = uniforms.to(dev).float().contiguous()
 
             # fp32 weights -> SIMT kernel (reference parity); bf16 -> tensor-core (mma.sync) kernel with up to 8 utterances
-            # per cluster, except for scalar-input models whose mixture samplers live in the SIMT kernel only
+            # per cluster (categorical, mixture-of-logistics and Gaussian samplers alike)
             if self.precision == "fp32":
                 wtype = "fp32"
             else:
-                wtype = "bf16" if (self.scalar_input or self.ar_impl == "simt") else "bf16mma"
+                wtype = "bf16" if self.ar_impl == "simt" else "bf16mma"
             cluster = self.ar_cluster or (16 if wtype == "fp32" else 8)
             if wtype == "bf16mma":
                 sh = packing.stack_shape(self)     # the tensor-core kernel exchanges bf16 pairs: slice boundaries must be even
