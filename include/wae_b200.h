@@ -299,6 +299,8 @@ int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, flo
  * second gate pass for widths above 256); -2 = version 2 on CTA pairs; 0 = first CTA-pair kernel; 1, 2 or 4 = the first 1-CTA
  * kernel in clusters of that size with TMA weight multicast.  Shapes a variant does not cover fall back: -4 -> -3 -> -1. */
 int wae_set_layer_cluster(int cs);
+/* Head kernel variant: 1 (default) = CTA pairs (cta_group::2, each CTA stages half of every weight k-block), 0 = 1-CTA kernel. */
+int wae_set_head_pair(int on);
 /* Name of the residual-layer kernel the last wae_stack_forward_bf16* call launched (for bench.py's roofline entry). */
 const char* wae_layer_kernel_name(void);
 /* Debug: per-CTA cycle counters of the 1-CTA residual-layer kernel's three roles (16 int64 per CTA), or NULL to disable. */

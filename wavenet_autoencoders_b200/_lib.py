@@ -102,6 +102,7 @@ SIGNATURES = {
                                 C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "wae_set_layer_cluster": (C.c_int, [C.c_int]),
     "wae_layer_kernel_name": (C.c_char_p, []),
+    "wae_set_head_pair": (C.c_int, [C.c_int]),
     "wae_layer_set_profile_buffer": (None, [C.c_void_p]),
     "wae_profile_enable": (None, [C.c_int]),
     "wae_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),

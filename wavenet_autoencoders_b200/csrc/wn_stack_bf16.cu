@@ -2308,6 +2308,269 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_kernel(const __gri
     if (warp == 1) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------
+// the head on CTA pairs (tcgen05 cta_group::2), DEFAULT when S and O allow it
+// ---------------------------------------------------------------------------------------------
+// ncu of the 1-CTA head (profiles/r2_head_ncu.txt): 4.46 GB of TMA loads per launch -- 2.2 MB per 128-sample tile, of which
+// 1.4 MB are WEIGHTS (Ws of every layer, W3, W4) streamed again for every tile -- i.e. ~250 us at the 62.6 B/cycle/SM a TMA
+// engine delivers (profiles/r2_tma_l2_bw.txt) against 175 us of tensor-pipe work: the kernel (421 us) is bound by operand delivery.
+// On CTA pairs each CTA stages its own 128 sample rows and HALF of every weight k-block (32 KB stages instead of 48 KB, 4 of
+// them), so a tile pulls 1.4 MB instead of 2.2 MB.  Roles, barriers and epilogues as in head_bf16_kernel; the "done" arrivals
+// are one per CTA into the leader's barriers.
+constexpr int HEADP_STAGES = 4;
+
+__global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const __grid_constant__ HeadArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int STAGE_BYTES = A_TILE_BYTES + PAIR_B_BYTES;
+    uint8_t* act = smem + HEADP_STAGES * STAGE_BYTES;   // [S/64][128 x 64] bf16 swizzled
+    const int nks = a.S / BK, nkh = a.Hp / BK;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(act + nks * A_TILE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + HEADP_STAGES;
+    uint64_t* accs_full = bars + 2 * HEADP_STAGES;
+    uint64_t* epis_done = accs_full + 1;
+    uint64_t* acc3_full = accs_full + 2;
+    uint64_t* epi3_done = accs_full + 3;
+    uint64_t* acc4_full = accs_full + 4;
+    uint64_t* epi4_done = accs_full + 5;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accs_full + 6);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int crank = (int)cluster_ctarank();
+    const bool leader = (crank == 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < HEADP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(accs_full, 1); mbar_init(epis_done, 2);       // one elected epilogue thread per CTA
+        mbar_init(acc3_full, 1); mbar_init(epi3_done, 2);
+        mbar_init(acc4_full, 1); mbar_init(epi4_done, 2);
+        fence_mbar_init();
+        tma_prefetch_desc(&a.tm_h);
+        tma_prefetch_desc(&a.tm_ws);
+        tma_prefetch_desc(&a.tm_w3);
+        tma_prefetch_desc(&a.tm_w4);
+    }
+    if (warp == 1) tmem_alloc_2cta<TMEM_COLS>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_s = tmem_base;          // skip accumulator, columns [0, S)
+    const uint32_t tmem_34 = tmem_base + 256;   // GEMM3 then GEMM4 accumulator, columns [256, 512)
+
+    const int ntiles = a.B * a.tiles_per_utt;
+    const int nsuper = (ntiles + 1) / 2;
+    const int ncluster = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+    const int ws_rows = a.S / 2, w4_rows = a.Op / 2;             // weight rows staged by this CTA
+    const uint32_t ws_half = (uint32_t)ws_rows * BK * 2, w4_half = (uint32_t)w4_rows * BK * 2;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            Ring ring(HEADP_STAGES);
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster) {
+                const int tile = sup * 2 + crank;
+                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
+                const bool valid = tile < ntiles;
+                for (int l = 0; l < a.L; ++l)
+                    for (int kb = 0; kb < nkh; ++kb) {
+                        mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                        uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                        const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
+                        if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + ws_half));
+                        // past the last tile (odd tail) the plane coordinate leaves the tensor: TMA zero-fills the box
+                        tma_load_3d_2cta(&a.tm_h, fb, sa, kb * BK, t0, valid ? l * a.B + b : a.L * a.B);
+                        tma_load_3d_2cta(&a.tm_ws, fb, sa + A_TILE_BYTES, kb * BK, crank * ws_rows, l);
+                        ring.advance();
+                    }
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
+                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * ws_half);
+                    tma_load_3d_2cta(&a.tm_w3, fb, sa + A_TILE_BYTES, kb * BK, crank * ws_rows, 0);
+                    ring.advance();
+                }
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
+                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * w4_half);
+                    tma_load_3d_2cta(&a.tm_w4, fb, sa + A_TILE_BYTES, kb * BK, crank * w4_rows, 0);
+                    ring.advance();
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && elect_one()) {
+            Ring ring(HEADP_STAGES);
+            const uint32_t idesc_s = umma_idesc_bf16(2 * BM, a.S);
+            const uint32_t idesc_4 = umma_idesc_bf16(2 * BM, a.Op);
+            auto issue2 = [&](uint32_t tmem_d, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool zero_init) {
+                const uint64_t ad = umma_desc_sw128(a_addr), bd = umma_desc_sw128(b_addr);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16_2cta(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (zero_init && k == 0) ? 0u : 1u);
+            };
+            int it = 0;
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+                // skip accumulator region was drained by EPI_S of the previous tile (waited below, before GEMM3)
+                for (int kb = 0; kb < a.L * nkh; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
+                    issue2(tmem_s, sa, sa + A_TILE_BYTES, idesc_s, kb == 0);
+                    umma_commit_2cta(&empty[ring.stage], 3);
+                    ring.advance();
+                }
+                umma_commit_2cta(accs_full, 3);
+                mbar_wait(epis_done, it & 1);
+                tc_fence_after();
+                if (it > 0) { mbar_wait(epi4_done, (it - 1) & 1); tc_fence_after(); }
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                    issue2(tmem_34, smem_u32(act + kb * A_TILE_BYTES), sb, idesc_s, kb == 0);
+                    umma_commit_2cta(&empty[ring.stage], 3);
+                    ring.advance();
+                }
+                umma_commit_2cta(acc3_full, 3);
+                mbar_wait(epi3_done, it & 1);
+                tc_fence_after();
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                    issue2(tmem_34, smem_u32(act + kb * A_TILE_BYTES), sb, idesc_4, kb == 0);
+                    umma_commit_2cta(&empty[ring.stage], 3);
+                    ring.advance();
+                }
+                umma_commit_2cta(acc4_full, 3);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int cg = (warp - 2) >> 2;                 // column group of this warp: 16-column chunks cg, cg + 4, ...
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t act_addr = smem_u32(act);
+        float* nll_red = reinterpret_cast<float*>(bars) + 64;        // [LAYER_NCG][3][BM] floats behind the barriers
+        double nll_acc = 0.0;
+        const uint32_t epis_remote = mapa(smem_u32(epis_done), 0), epi3_remote = mapa(smem_u32(epi3_done), 0), epi4_remote = mapa(smem_u32(epi4_done), 0);
+        int it = 0;
+        for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+            const int tile = sup * 2 + crank;
+            const bool valid = tile < ntiles;                  // a pair's odd tail: computed on zero-filled input, never stored
+            const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
+            const int t = t0 + row;
+            const bool live = valid && (t < a.T);
+
+            // relu(scale * (acc + bias)) / relu(acc + bias) -> bf16 -> `act` (A operand of the next GEMM)
+            auto relu_to_act = [&](uint32_t tmem_acc, const float* bias, float scale, const CUtensorMap* tm_save) {
+                if (a.save) {   // the TMA store of the previous hidden activation must have finished reading `act`
+                    if (threadIdx.x == 64) tma_store_wait_read();
+                    asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+                }
+                for (int c0 = cg * 16; c0 < a.S; c0 += LAYER_NCG * 16) {
+                    float v[16];
+                    tmem_ld16(tmem_acc + lane_base + c0, v);
+                    tmem_ld_wait();
+                    uint32_t packed[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 b2 = __ldg(reinterpret_cast<const float2*>(bias + c0 + 2 * i));
+                        const float o0 = fmaxf((v[2 * i] + b2.x) * scale, 0.f);
+                        const float o1 = fmaxf((v[2 * i + 1] + b2.y) * scale, 0.f);
+                        packed[i] = pack_bf16x2(o0, o1);
+                    }
+                    const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                    const uint32_t base = act_addr + kb * A_TILE_BYTES;
+                    st_shared_v4(base + sw128_off(row, c16), packed[0], packed[1], packed[2], packed[3]);
+                    st_shared_v4(base + sw128_off(row, c16 + 1), packed[4], packed[5], packed[6], packed[7]);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+                if (a.save && valid && threadIdx.x == 64) {
+                    for (int kb = 0; kb < a.S / BK; ++kb) tma_store_3d(tm_save, act + kb * A_TILE_BYTES, kb * BK, t0, b);
+                    tma_store_commit();
+                }
+            };
+
+            mbar_wait(accs_full, it & 1);
+            tc_fence_after();
+            relu_to_act(tmem_s, a.bs_sum, a.scale, &a.tm_r1);
+            if (threadIdx.x == 64) mbar_arrive_cluster(epis_remote);
+
+            mbar_wait(acc3_full, it & 1);
+            tc_fence_after();
+            relu_to_act(tmem_34, a.b3, 1.0f, &a.tm_r2);
+            if (threadIdx.x == 64) mbar_arrive_cluster(epi3_remote);
+
+            mbar_wait(acc4_full, it & 1);
+            tc_fence_after();
+            // loss straight from the accumulator: every thread holds 1/4 of the classes of its time step --
+            // running max / sum of exponentials / the target's logit per thread, merged over the four column groups below
+            const bool want_nll = (a.target != nullptr);
+            const int tgt = (want_nll && live && t + a.shift < a.T) ? (int)__ldg(a.target + (size_t)b * a.T + t + a.shift) : -1;
+            float r_max = -INFINITY, r_sum = 0.f, r_tgt = 0.f;
+            for (int c0 = cg * 16; c0 < a.Op; c0 += LAYER_NCG * 16) {
+                float v[16];
+                tmem_ld16(tmem_34 + lane_base + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] += __ldg(a.b4 + c0 + i);
+                if (live && a.logits != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.O)  // lanes of a warp = consecutive samples -> 128-byte coalesced rows
+                            a.logits[((size_t)b * a.O + c0 + i) * a.T + t] = v[i];
+                }
+                if (want_nll) {
+                    float m = r_max;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.O) m = fmaxf(m, v[i]);
+                    float s = r_sum * expf(r_max - m);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (c0 + i < a.O) { s += expf(v[i] - m); if (c0 + i == tgt) r_tgt = v[i]; }
+                    r_max = m; r_sum = s;
+                }
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+            if (threadIdx.x == 64) mbar_arrive_cluster(epi4_remote);
+            if (want_nll) {
+                float* red = nll_red + (size_t)cg * 3 * BM;       // [column group][max | sum | target logit][row]
+                red[row] = r_max; red[BM + row] = r_sum; red[2 * BM + row] = r_tgt;
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
+                if (cg == 0) {
+                    float m = r_max, lt = r_tgt;
+                    for (int k = 1; k < LAYER_NCG; ++k) m = fmaxf(m, nll_red[(size_t)k * 3 * BM + row]);
+                    float ssum = r_sum * expf(r_max - m);
+                    for (int k = 1; k < LAYER_NCG; ++k) {
+                        ssum += nll_red[(size_t)k * 3 * BM + BM + row] * expf(nll_red[(size_t)k * 3 * BM + row] - m);
+                        lt += nll_red[(size_t)k * 3 * BM + 2 * BM + row];
+                    }
+                    float nll = (tgt >= 0) ? (m + logf(ssum)) - lt : 0.f;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) nll += __shfl_xor_sync(0xffffffffu, nll, off);
+                    if (lane == 0) nll_acc += (double)nll;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");   // nll_red is reused by the next tile
+            }
+        }
+        if (a.target != nullptr && cg == 0 && lane == 0) atomicAdd(a.nll_sum, nll_acc);
+        if (a.save && threadIdx.x == 64) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync();
+    if (warp == 1) tmem_dealloc_2cta<TMEM_COLS>(tmem_base);
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -2337,6 +2600,7 @@ int g_layer_mode = 5;      // 5 = version 4 (CTA pairs + TMEM ping-pong; default
                            // 3 = version 2 on CTA pairs, 0 = first CTA-pair kernel (cta_group::2), 1 = first 1-CTA kernel
 const char* g_layer_kernel_name = "layer_bf16_v4_kernel";
 int g_layer_cluster = 1;   // 1-CTA kernel only: 1, 2 or 4 CTAs share every weight k-block via TMA multicast
+int g_head_pair = 1;       // head on CTA pairs (default) or the 1-CTA head kernel (wae_set_head_pair)
 struct ProfScope {
     int kind; cudaStream_t st; cudaEvent_t a, b; bool on;
     ProfScope(int k, cudaStream_t s) : kind(k), st(s), on(g_prof.on) {
@@ -2404,6 +2668,8 @@ int wae_gemm_bf16_tn(const void* A, const void* Bm, float* Cout, int M, int N, i
 void wae_profile_enable(int on) { g_prof.on = (on != 0); }
 
 void wae_layer_set_profile_buffer(int64_t* dev_buf) { g_layer_prof = reinterpret_cast<long long*>(dev_buf); }
+
+int wae_set_head_pair(int on) { g_head_pair = on ? 1 : 0; return WAE_OK; }   // 1 (default): head kernel on CTA pairs; 0: 1-CTA head
 
 const char* wae_layer_kernel_name() { return g_layer_kernel_name; }   // the residual-layer kernel the last forward launched
 
@@ -2649,8 +2915,30 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         if (int rc = make_tmap(&ha.tm_r2, save->r2, d.S, T, B, d.S, (uint64_t)T * d.S, BK, BM)) return rc;
     }
     const size_t smem_head = 1024 + (size_t)HEAD_STAGES * (A_TILE_BYTES + 256 * BK * 2) + (size_t)(d.S / BK) * A_TILE_BYTES + 256 + LAYER_NCG * 3 * BM * 4;
-    WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
-    {
+    const size_t smem_headp = 1024 + (size_t)HEADP_STAGES * (A_TILE_BYTES + PAIR_B_BYTES) + (size_t)(d.S / BK) * A_TILE_BYTES + 256 + LAYER_NCG * 3 * BM * 4;
+    const bool head_pair = g_head_pair && d.S % 32 == 0 && Op % 32 == 0 && smem_headp <= 232448 && ntiles >= 2;
+    if (head_pair) {
+        // the weight boxes of a pair are half matrices: rows [r * N/2, (r+1) * N/2) for CTA r
+        if (int rc = make_tmap(&ha.tm_ws, w->ws, Hp, d.S, d.layers, Hp, (uint64_t)d.S * Hp, BK, d.S / 2)) return rc;
+        if (int rc = make_tmap(&ha.tm_w3, w->w3, d.S, d.S, 1, d.S, (uint64_t)d.S * d.S, BK, d.S / 2)) return rc;
+        if (int rc = make_tmap(&ha.tm_w4, w->w4, d.S, Op, 1, d.S, (uint64_t)Op * d.S, BK, Op / 2)) return rc;
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_headp));
+        int nclusters = num_sms() / 2;
+        if (nclusters > (ntiles + 1) / 2) nclusters = (ntiles + 1) / 2;
+        ProfScope prof(2, stream);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(nclusters * 2));
+        cfg.blockDim = dim3(LAYER_THREADS);
+        cfg.dynamicSmemBytes = smem_headp;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, head_bf16_pair_kernel, ha));
+    } else {
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
         ProfScope prof(2, stream);
         head_bf16_kernel<<<grid, LAYER_THREADS, smem_head, stream>>>(ha);
     }
