@@ -306,6 +306,12 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # which algorithm / protocol NCCL picks for the gradient all-reduce: its INFO log goes to a file that rank 0 summarises
+        # into extras.nccl (the stdout of this process must carry the one JSON line only)
+        nccl_log = f"/tmp/wae_nccl_{os.getpid()}.log"
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ["NCCL_DEBUG_SUBSYS"] = "INIT,TUNING,COLL" if os.environ.get("WAE_NCCL_COLL") else "INIT,TUNING"
+        os.environ["NCCL_DEBUG_FILE"] = nccl_log
         # NCCL prints its version banner on stdout when the communicator is created; stdout must carry the one JSON line only
         sys.stdout.flush()
         saved_out = os.dup(1)
@@ -586,6 +592,8 @@ def main():
         tm = build_vqvae(dev).train()
         tm.wavenet.precision = "bf16"
         opt = TS.FlatAdam(tm, lr=4e-4, clip=100.0)       # clip + Adam on one flat buffer (f4); the all-reduce works on it directly
+        if world > 1:                                    # decoder bucket all-reduced under the upsampler / VQ / encoder backward
+            opt.enable_overlap(tm)
         rs = np.random.RandomState(7 + rank)
         Bt, Tt = 8, 7680
         ti = torch.tensor(rs.randint(0, 256, size=(Bt, Tt)), dtype=torch.long, device=dev)
@@ -631,10 +639,23 @@ def main():
             barrier()
             extras["train_allreduce_ms"] = max_over_ranks(e0.elapsed_time(e1)) / 10
             extras["train_allreduce_bytes"] = flat.numel() * 4
+            br = getattr(opt, "bucketed", None)
+            if br is not None:
+                extras["train_allreduce_buckets"] = [int(sl.numel()) * 4 for sl in br.slices]
+                extras["train_allreduce_buckets_started_inside_backward"] = int(br.overlapped)
+            try:                                         # NCCL's own account of what it runs (INIT / TUNING lines of its INFO log)
+                lines = open(os.environ.get("NCCL_DEBUG_FILE", "")).read().splitlines()
+                keep = [ln.split("NCCL INFO ", 1)[-1][:160] for ln in lines
+                        if any(k in ln for k in ("NVLS", "Connected all", "AllReduce", "Algo", "nRanks", "channels"))]
+                extras["nccl"] = keep[:6] + (["..."] if len(keep) > 12 else []) + keep[-6:]
+            except OSError as e:
+                extras["nccl"] = [f"no NCCL log: {e}"]
         del gstep
-        extras["train_config"] = ("VQ-WAE step: 8 utt/GPU x 7680 samples, tcgen05 bf16 forward + bf16 GEMM backward with fused "
-                                  "gather/gate kernels, fp32 master weights, Adam, grad-clip 100, one flat NCCL all-reduce "
-                                  "when N > 1; the step is replayed as one CUDA graph")
+        extras["train_config"] = ("VQ-WAE step: 8 utt/GPU x 7680 samples, tcgen05 bf16 forward, tcgen05 backward (wae_stack_backward_bf16: "
+                                  "dgrad GEMMs with the dilated taps as TMA boxes and fused gate / residual / ReLU epilogues, MN-major "
+                                  "split-K wgrads), loss + softmax gradient fused (forward_nll), fp32 master weights, Adam, grad-clip 100; "
+                                  "N > 1: flat gradient all-reduced in two buckets, the decoder's (80 % of the bytes) under the rest of the "
+                                  "backward; the step is replayed as one CUDA graph")
         del tm, opt
         torch.backends.cudnn.benchmark = False
         torch.cuda.empty_cache()

@@ -77,3 +77,63 @@ def test_shard_utterances_is_a_partition():
     for n, w in [(256, 8), (7, 4), (3, 8), (0, 2)]:
         got = [i for r in range(w) for i in parallel.shard_utterances(n, w, r)]
         assert got == list(range(n))
+
+
+def _bucket_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+        dead = torch.nn.Parameter(torch.zeros(7))                      # never receives a gradient (like the last layer's conv1x1_out)
+        params = list(net[4].parameters()) + [dead] + list(net[2].parameters()) + list(net[0].parameters())   # backward order
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += -(-p.numel() // 4) * 4
+        flat = torch.zeros(n)
+        for p, o in zip(params, offs):
+            p.grad = flat[o:o + p.numel()].view_as(p)
+        br = parallel.BucketedAllReduce(params, flat, offs, [0, 3, 5, len(params)])
+        outs = []
+        for step in range(3):
+            flat.zero_()
+            br.start_step()
+            x = torch.randn(8, 6, generator=torch.Generator().manual_seed(100 * step + rank))
+            net(x).square().mean().backward()
+            br.finish()
+            outs.append((flat.clone().numpy(), br.overlapped))
+        q.put((rank, outs))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_overlaps_and_matches_flat_world2():
+    """parallel.BucketedAllReduce: the first step calibrates (no overlap), later steps start a bucket's all-reduce from the
+    hook of its last gradient (all but the last bucket start INSIDE the backward); the result equals the average of the two
+    ranks' gradients, the dead parameter's slot stays zero."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucket_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    import numpy as np
+    for step in range(3):
+        np.testing.assert_allclose(res[0][step][0], res[1][step][0], rtol=1e-6, atol=1e-7)       # replicas agree
+    assert res[0][0][1] == 0 and res[0][1][1] == 3 and res[0][2][1] == 3                            # calibration, then every bucket from its hook
+    # reference: average of the per-rank gradients computed locally
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 4), torch.nn.Tanh(), torch.nn.Linear(4, 3))
+    want = None
+    for rank in range(world):
+        net.zero_grad()
+        x = torch.randn(8, 6, generator=torch.Generator().manual_seed(100 * 2 + rank))
+        net(x).square().mean().backward()
+        g = torch.cat([p.grad.reshape(-1) for p in net[4].parameters()])
+        want = g if want is None else want + g
+    np.testing.assert_allclose(res[0][2][0][:want.numel()], (want / world).numpy(), rtol=1e-5, atol=1e-7)

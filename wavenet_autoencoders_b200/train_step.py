@@ -58,7 +58,26 @@ class FlatAdam:
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
 
+    def enable_overlap(self, model=None, bounds=None, group=None):
+        """Bucketed all-reduce overlapped with the backward (parallel.BucketedAllReduce).  Default buckets: [the WaveNet
+        decoder's parameters | everything else] when ``model`` has a ``wavenet`` whose parameters come first -- the decoder's
+        gradients are complete when its backward node finishes, before the upsampler / VQ / encoder backward runs."""
+        from . import parallel
+        if bounds is None:
+            n_dec = 0
+            dec = getattr(model, "wavenet", None)
+            if dec is not None:
+                ids = {id(p) for p in dec.parameters()}
+                while n_dec < len(self.params) and id(self.params[n_dec]) in ids:
+                    n_dec += 1
+            bounds = [0, n_dec, len(self.params)] if 0 < n_dec < len(self.params) else [0, len(self.params)]
+        self.bucketed = parallel.BucketedAllReduce(self.params, self.flat_g, self.offsets, bounds, group)
+        return self.bucketed
+
     def allreduce(self, world):
+        if getattr(self, "bucketed", None) is not None:
+            self.bucketed.finish()
+            return
         import torch.distributed as dist
         dist.all_reduce(self.flat_g)
         self.flat_g.div_(world)
@@ -82,6 +101,8 @@ def train_step(model, opt, idx, mfcc, g, clip=100.0, world=1, timers=None, fused
     """idx (B,T) int64 mu-law classes; mfcc (B,39,frames); g (B,1) speaker ids.  Returns the loss tensor (no sync)."""
     x = F.one_hot(idx, 256).float().transpose(1, 2)                        # the collate's one-hot input (vqwae_train.py:509-520)
     opt.zero_grad(set_to_none=True)
+    if world > 1 and getattr(opt, "bucketed", None) is not None:
+        opt.bucketed.start_step()
     # vqwae_train.py:760-766: y_hat[:, :, :-1] predicts y[:, 1:]; full-length synthetic windows -> the mask is all ones
     if fused_loss and hasattr(model, "forward_nll"):
         nll, vq_loss, _ = model.forward_nll(x, mfcc, g, idx, 1)            # decoder loss + backward fused (training.StackNLLFunction)
