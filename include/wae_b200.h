@@ -201,6 +201,29 @@ int wae_stack_nll_bf16_idx(const wae_stack_bf16* w, const int64_t* x_idx, const 
                            const float* gemb, int B, int T, const int64_t* target, int shift, double* out_sum, float* logits,
                            void* workspace, size_t workspace_bytes, void* stream);
 /*
+ * The conditioning front-end of the decoder: wavenet_vocoder/upsample.py:69-85 (ConvInUpsampleNetwork:
+ * conv_in 1x1 without bias, then every UpsampleNetwork stage = nearest stretch by scale[i] + the 1 x (2*scale[i]+1) smoothing
+ * filter, upsample.py:37-49), as plain arrays.  conv_in_w_t: the (C, C) conv_in weight TRANSPOSED to [in][out] fp32, or NULL
+ * for a plain UpsampleNetwork; filter[i]: (2*scale[i]+1) fp32, weight norm folded.
+ */
+typedef struct wae_cond_frontend {
+    const float* conv_in_w_t;
+    int n_stages;              /* 1..8 */
+    int scale[8];
+    const float* filter[8];
+} wae_cond_frontend;
+/*
+ * Teacher-forced forward straight from the LATENT frames lat (B, C, F) fp32 (the VQ output, F * prod(scale) == T): ONE kernel
+ * evaluates conv_in and the whole upsampler pyramid per 128-sample block in shared memory and writes the stack's channels-last
+ * bf16 conditioning; nothing at an intermediate rate is materialised and no library GEMM runs.  Bit-identical to running
+ * wae_upsample_stage per stage.  Input: x (B, Oin, T) fp32 or, if x_idx != NULL, the (B, T) int64 classes.  Outputs: logits
+ * (B, O, T) fp32 (may be NULL when the NLL is requested) and/or, with target != NULL, the teacher-forced NLL sum as in
+ * wae_stack_nll_bf16_idx (target and nll_sum both NULL: forward only).
+ */
+int wae_stack_forward_bf16_lat(const wae_stack_bf16* w, const float* x, const int64_t* x_idx, const float* lat, int F,
+                               const wae_cond_frontend* fe, const float* gemb, int B, int T, float* logits, const int64_t* target,
+                               int shift, double* nll_sum, void* workspace, size_t workspace_bytes, void* stream);
+/*
  * Teacher-forced negative log-likelihood summed over b and t < T - shift, straight from the logits:
  * *out_sum += sum logsumexp_o(logits[b][:][t]) - logits[b][target[b][t+shift]][t]   (vqwae_train.py:760-766, mask of ones).
  * One pass over the logits; the caller zeroes out_sum and divides by B * (T - shift).

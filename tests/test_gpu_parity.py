@@ -81,6 +81,7 @@ def test_forward_bf16_fused_last_upsample_stage(case):
     materialised (B,C,T) conditioning, and the mixed one-hot / dense first-conv path inside one block."""
     g, cfg, m, x, c, spk = _inputs(case)
     m.precision = "bf16"
+    m.fuse_frontend = False        # the whole-front-end kernel (next test) would take over otherwise
     with torch.no_grad():
         assert m.upsample_net(c, defer_last=True) is not None          # the fused path is the one forward() takes
         y_fused = m(x, c, spk)
@@ -94,6 +95,49 @@ def test_forward_bf16_fused_last_upsample_stage(case):
         m.precision = "bf16"
         y16 = m(x2, c, spk)
     assert rel_err(y16.cpu().numpy(), y32.cpu().numpy()) < TOL_BF16
+
+
+@pytest.mark.parametrize("case", ["wavenet_tiny", "wavenet_vqwae", "wavenet_inwae"])
+def test_forward_bf16_fused_conditioning_frontend(case):
+    """wae_stack_forward_bf16_lat: conv_in + every upsampler stage evaluated per 128-sample block inside the
+    stack's conditioning kernel, from the latent frames.  (a) without conv_in the stage pyramid repeats the staged kernels'
+    arithmetic: logits BIT-identical to the staged path; (b) with conv_in (an fp32 dot product in another summation order than
+    the library matmul) the bf16 conditioning may differ in its last bit: logits within 2e-3; (c) reference golden; (d) the
+    class-index input and the fused NLL go through the same front-end."""
+    g, cfg, m, x, c, spk = _inputs(case)
+    m.precision = "bf16"
+    B, T = x.shape[0], x.shape[-1]
+    idx = x.argmax(1)
+    with torch.no_grad():
+        assert m._pack("fe") is not None
+        n0 = _lib.launch_count()
+        y_fe = m(x, c, spk)
+        n_fe = _lib.launch_count() - n0
+        m.fuse_frontend = False
+        n0 = _lib.launch_count()
+        y_st = m(x, c, spk)
+        n_st = _lib.launch_count() - n0
+        assert n_fe == n_st - (len(m.upsample_net.upsample.scales) - 1), (n_fe, n_st)      # the stage launches are gone
+        assert rel_err(y_fe.cpu().numpy(), y_st.cpu().numpy()) < 2e-3
+        s = int(g["stride"])
+        assert rel_err(y_fe[:, :, ::s].cpu().numpy(), g["logits"]) < TOL_BF16
+        # (a) no conv_in: feed the staged path the conv_in output, the fused one an identity conv_in
+        c_in = torch.matmul(m.upsample_net.conv_in.weight[:, :, 0], c)
+        y_a = m.stack_forward(x, m.upsample_net.upsample(c_in), m._speaker_vectors(spk, B))
+        m.fuse_frontend = True
+        w_keep = m.upsample_net.conv_in.weight.detach().clone()
+        m.upsample_net.conv_in.weight.copy_(torch.eye(w_keep.shape[0], device=w_keep.device).unsqueeze(-1))   # in place: bumps _version
+        y_b = m(x, c_in, spk)
+        m.upsample_net.conv_in.weight.copy_(w_keep)
+        assert torch.equal(y_a, y_b)
+        # (d) class indices + NLL from the head kernel
+        y_idx = m(idx, c, spk)
+        assert torch.equal(y_idx, m(x, c, spk))
+        nll = m.forward_nll(idx, c, spk, idx, 1)
+        ref = torch.nn.functional.cross_entropy(y_idx[:, :, :-1].double(), idx[:, 1:])
+        assert abs(float(nll) - float(ref)) < 2e-5 * max(1.0, abs(float(ref)))
+        with pytest.raises(Exception):
+            m(x[:, :, :-cfg["upsample_params"]["upsample_scales"][-1]], c, spk)       # c does not cover T: same failure as the reference
 
 
 @pytest.mark.parametrize("G", [40, 296, 368, 512])

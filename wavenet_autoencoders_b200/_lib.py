@@ -50,6 +50,10 @@ class StackBwd(C.Structure):
                                            "dw1", "dwo", "dws", "dw3", "dw4", "dgb", "dbo", "dbs", "db3", "db4", "dc", "dx0", "dy")]
 
 
+class CondFrontend(C.Structure):
+    _fields_ = [("conv_in_w_t", C.c_void_p), ("n_stages", C.c_int32), ("scale", C.c_int32 * 8), ("filter", C.c_void_p * 8)]
+
+
 class ArWeights(C.Structure):
     _fields_ = [
         ("d", StackDims),
@@ -96,6 +100,9 @@ SIGNATURES = {
                                              C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "wae_stack_nll_bf16_idx": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                          C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wae_stack_forward_bf16_lat": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(CondFrontend),
+                                             C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_size_t, C.c_void_p]),
     "wae_nll_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wae_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "wae_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,

@@ -411,6 +411,123 @@ cond_stage_cl_kernel(const float* __restrict__ in, int C, int Cp, int Tin, int s
     }
 }
 
+// The WHOLE conditioning front-end in one launch: latent frames (B,C,F) fp32 -> conv_in (1x1, no bias,
+// upsample.py:78) -> every upsampler stage (nearest stretch by s_i + (2 s_i + 1)-tap smoothing, upsample.py:37-49) ->
+// [B][T][Cp] bf16 channels-last.  A block owns CF_T output samples of one utterance and evaluates the stage pyramid locally in
+// shared memory: the last stage needs CF_T / s + 3 positions of the stage before it, that one a quarter of those + 3, ... down
+// to a handful of latent frames, on which conv_in is applied first.  Every stage uses the 3-coefficient form and the FMA order of
+// upsample_stage_kernel / cond_stage_cl_kernel (positions outside [0, len) are zero: the reference's zero padding per stage), so
+// the result equals the staged path bit for bit; nothing at an intermediate rate ever goes to global memory.
+constexpr int CF_T = 128;        // samples per block
+constexpr int CF_PITCH = 133;    // >= CF_T + 3 positions (a stage of scale 1), odd
+constexpr int CF_MAX_STAGES = 8;
+struct CondFrontArgs {
+    const float* lat;            // (B, C, F)
+    const float* win_t;          // (C, C) conv_in weight transposed to [in][out], or null
+    const float* filt[CF_MAX_STAGES];
+    int scale[CF_MAX_STAGES];
+    int ns, C, Cp, F, T;
+    __nv_bfloat16* out;          // [B][T][Cp]
+};
+
+__global__ void __launch_bounds__(256)
+cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
+    extern __shared__ float cf_sm[];
+    // coefficient tables of all stages [3][s_i], then two position buffers [Cp][CF_PITCH]
+    int coef_off[CF_MAX_STAGES], lo[CF_MAX_STAGES + 1], hi[CF_MAX_STAGES + 1], len[CF_MAX_STAGES + 1];
+    int ctot = 0;
+    for (int i = 0; i < a.ns; ++i) { coef_off[i] = ctot; ctot += 3 * a.scale[i]; }
+    float* coef = cf_sm;
+    float* buf0 = cf_sm + ((ctot + 3) & ~3);
+    float* buf1 = buf0 + a.Cp * CF_PITCH;
+    const int b = blockIdx.y, t0 = blockIdx.x * CF_T, tid = threadIdx.x;
+    // position ranges, top down: level ns = output samples, level i = input of stage i (level 0 = latent frames)
+    len[0] = a.F;
+    for (int i = 0; i < a.ns; ++i) len[i + 1] = len[i] * a.scale[i];
+    lo[a.ns] = t0; hi[a.ns] = min(t0 + CF_T, a.T) - 1;
+    for (int i = a.ns - 1; i >= 0; --i) {
+        // floor division that also works for lo = -1 (positions left of the signal are zeros computed from zeros)
+        const int s = a.scale[i];
+        lo[i] = (lo[i + 1] >= 0 ? lo[i + 1] / s : -1) - 1;
+        hi[i] = (hi[i + 1] >= 0 ? hi[i + 1] / s : -1) + 1;
+    }
+    for (int i = 0; i < a.ns; ++i) {
+        const int s = a.scale[i];
+        const float* w = a.filt[i];
+        float* cf = coef + coef_off[i];
+        for (int p = tid; p < s; p += 256) {
+            float x = 0.f, y = 0.f, z = 0.f;
+            for (int j = 0; j < s - p; ++j) x += __ldg(&w[j]);
+            for (int j = s - p; j < 2 * s - p; ++j) y += __ldg(&w[j]);
+            for (int j = 2 * s - p; j <= 2 * s; ++j) z += __ldg(&w[j]);
+            cf[p] = x; cf[s + p] = y; cf[2 * s + p] = z;
+        }
+    }
+    // level 0: latent frames [lo0, hi0] (zeros outside [0, F)), conv_in applied
+    const int n0 = hi[0] - lo[0] + 1;
+    {
+        float* raw = a.win_t ? buf1 : buf0;
+        for (int e = tid; e < a.Cp * n0; e += 256) {
+            const int ch = e / n0, k = e - ch * n0, f = lo[0] + k;
+            raw[ch * CF_PITCH + k] = (ch < a.C && f >= 0 && f < a.F) ? __ldg(&a.lat[((size_t)b * a.C + ch) * a.F + f]) : 0.f;
+        }
+        __syncthreads();
+        if (a.win_t) {
+            for (int e = tid; e < a.Cp * n0; e += 256) {
+                const int k = e / a.Cp, co = e - k * a.Cp;      // consecutive threads: consecutive output channels
+                float acc = 0.f;
+                if (co < a.C) {
+#pragma unroll 8
+                    for (int ci = 0; ci < a.C; ++ci) acc = fmaf(__ldg(&a.win_t[(size_t)ci * a.C + co]), buf1[ci * CF_PITCH + k], acc);
+                }
+                buf0[co * CF_PITCH + k] = acc;
+            }
+            __syncthreads();
+        }
+    }
+    // stages 0 .. ns-2: level i (in `cur`, origin lo[i]) -> level i+1 positions [lo[i+1], hi[i+1]]
+    float* cur = buf0;
+    float* nxt = buf1;
+    for (int i = 0; i + 1 < a.ns; ++i) {
+        const int s = a.scale[i], n1 = hi[i + 1] - lo[i + 1] + 1, L1 = len[i + 1];
+        const float* cf = coef + coef_off[i];
+        for (int e = tid; e < a.Cp * n1; e += 256) {
+            const int ch = e / n1, k = e - ch * n1, u = lo[i + 1] + k;
+            float v = 0.f;
+            if (u >= 0 && u < L1) {
+                const int f = u / s, p = u - f * s;
+                const float* xr = cur + ch * CF_PITCH + (f - lo[i]);
+                v = fmaf(cf[2 * s + p], xr[1], fmaf(cf[s + p], xr[0], cf[p] * xr[-1]));
+            }
+            nxt[ch * CF_PITCH + k] = v;
+        }
+        __syncthreads();
+        float* t = cur; cur = nxt; nxt = t;
+    }
+    // last stage + layout change
+    {
+        const int i = a.ns - 1, s = a.scale[i];
+        const float* cf = coef + coef_off[i];
+        const int c8n = a.Cp >> 3;
+        for (int e = tid; e < CF_T * c8n; e += 256) {
+            const int tt = e / c8n, c8 = (e - tt * c8n) * 8, t = t0 + tt;
+            if (t >= a.T) break;
+            const int f = t / s, p = t - f * s, k = f - lo[i];
+            const float ca = cf[p], cb = cf[s + p], cc = cf[2 * s + p];
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float* xr = cur + (c8 + j) * CF_PITCH + k;
+                v[j] = fmaf(cc, xr[1], fmaf(cb, xr[0], ca * xr[-1]));
+            }
+            uint4 o4;
+            o4.x = pack_bf16x2(v[0], v[1]); o4.y = pack_bf16x2(v[2], v[3]);
+            o4.z = pack_bf16x2(v[4], v[5]); o4.w = pack_bf16x2(v[6], v[7]);
+            *reinterpret_cast<uint4*>(a.out + ((size_t)b * a.T + t) * a.Cp + c8) = o4;
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // the fused residual layer
 // ---------------------------------------------------------------------------------------------
@@ -2716,7 +2833,8 @@ struct NllRequest { const int64_t* target; int shift; double* out_sum; };
 
 static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, const int64_t* x_idx, const float* c, int up_s, const float* up_w,
                                    const float* gemb, int B, int T, float* logits, const wae_stack_saved* save,
-                                   void* workspace, size_t workspace_bytes, void* stream_, const NllRequest* nll = nullptr) {
+                                   void* workspace, size_t workspace_bytes, void* stream_, const NllRequest* nll = nullptr,
+                                   const wae_cond_frontend* fe = nullptr, int fe_frames = 0) {
     if (int rc = wae::require_sm100()) return rc;
     WAE_REQUIRE(w && (x || x_idx) && (logits || nll) && workspace, "wae_stack_forward_bf16: null pointer");
     const wae_stack_dims& d = w->d;
@@ -2773,7 +2891,29 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         first_conv_bf16_kernel<<<dim3((T + FC_T - 1) / FC_T, B), 256, 0, stream>>>(x, w->wf, w->bf, T, d.Oin, d.R, vec_ok, ws.xa);
         WAE_CHECK_LAUNCH();
     }
-    if (d.C > 0 && up_s > 0) {
+    if (d.C > 0 && fe != nullptr) {
+        // c holds the LATENT frames: conv_in + every upsampler stage + layout change in one launch (row f1)
+        CondFrontArgs ca;
+        long long total = fe_frames;
+        int ctot = 0, worst = CF_T;
+        WAE_REQUIRE(fe->n_stages >= 1 && fe->n_stages <= CF_MAX_STAGES && fe_frames >= 1, "wae_stack_forward_bf16_lat: %d stages, %d frames", fe->n_stages, fe_frames);
+        for (int i = 0; i < fe->n_stages; ++i) {
+            WAE_REQUIRE(fe->scale[i] >= 1 && fe->filter[i] != nullptr, "wae_stack_forward_bf16_lat: stage %d: scale %d", i, fe->scale[i]);
+            ca.scale[i] = fe->scale[i]; ca.filt[i] = fe->filter[i];
+            total *= fe->scale[i]; ctot += 3 * fe->scale[i];
+        }
+        for (int i = fe->n_stages - 1; i >= 0; --i) {      // positions a block needs at the input of stage i
+            worst = (worst + fe->scale[i] - 1) / fe->scale[i] + 3;
+            WAE_REQUIRE(worst <= CF_PITCH - 1, "wae_stack_forward_bf16_lat: upsampler scales need %d positions per block at stage %d (max %d)", worst, i, CF_PITCH - 1);
+        }
+        WAE_REQUIRE(total == T, "wae_stack_forward_bf16_lat: %d frames x scales = %lld != T = %d", fe_frames, total, T);
+        ca.lat = c; ca.win_t = fe->conv_in_w_t; ca.ns = fe->n_stages; ca.C = d.C; ca.Cp = Cp; ca.F = fe_frames; ca.T = T; ca.out = ws.ccl;
+        const size_t sm = ((size_t)((ctot + 3) & ~3) + (size_t)2 * Cp * CF_PITCH) * sizeof(float);
+        WAE_REQUIRE(sm <= 200 * 1024, "wae_stack_forward_bf16_lat: C=%d needs %zu bytes of shared memory", d.C, sm);
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(cond_frontend_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        cond_frontend_cl_kernel<<<dim3((T + CF_T - 1) / CF_T, B), 256, sm, stream>>>(ca);
+        WAE_CHECK_LAUNCH();
+    } else if (d.C > 0 && up_s > 0) {
         // c holds the frames before the last upsampler stage: stretch + smooth + layout change in one pass
         const size_t sm = ((size_t)3 * up_s + (size_t)Cp * CS_PITCH) * sizeof(float);
         WAE_REQUIRE(sm <= 200 * 1024, "wae_stack_forward_bf16_up: C=%d / scale %d need %zu bytes of shared memory", d.C, up_s, sm);
@@ -2994,6 +3134,24 @@ int wae_stack_nll_bf16_idx(const wae_stack_bf16* w, const int64_t* x_idx, const 
     NllRequest rq{target, shift, out_sum};
     return stack_forward_bf16_impl(w, nullptr, x_idx, c, up_scale > 0 ? up_scale : 0, up_scale > 0 ? up_filter : nullptr, gemb, B, T,
                                    logits, nullptr, workspace, workspace_bytes, stream, &rq);
+}
+
+int wae_stack_forward_bf16_lat(const wae_stack_bf16* w, const float* x, const int64_t* x_idx, const float* lat, int F,
+                               const wae_cond_frontend* fe, const float* gemb, int B, int T, float* logits, const int64_t* target,
+                               int shift, double* nll_sum, void* workspace, size_t workspace_bytes, void* stream) {
+    WAE_REQUIRE(w && (x || x_idx) && lat && fe, "wae_stack_forward_bf16_lat: null pointer");
+    WAE_REQUIRE(w->d.C > 0, "wae_stack_forward_bf16_lat: the stack has no local conditioning (C = 0)");
+    WAE_REQUIRE(!x_idx || w->d.Oin > 1, "wae_stack_forward_bf16_lat: class indices need a one-hot-input model (Oin > 1)");
+    WAE_REQUIRE((target == nullptr) == (nll_sum == nullptr), "wae_stack_forward_bf16_lat: target and nll_sum go together");
+    WAE_REQUIRE(logits || target, "wae_stack_forward_bf16_lat: nothing to compute (no logits, no NLL)");
+    if (target) {
+        WAE_REQUIRE(shift >= 0 && shift < T, "wae_stack_forward_bf16_lat: shift %d", shift);
+        NllRequest rq{target, shift, nll_sum};
+        return stack_forward_bf16_impl(w, x_idx ? nullptr : x, x_idx, lat, 0, nullptr, gemb, B, T, logits, nullptr, workspace, workspace_bytes,
+                                       stream, &rq, fe, F);
+    }
+    return stack_forward_bf16_impl(w, x_idx ? nullptr : x, x_idx, lat, 0, nullptr, gemb, B, T, logits, nullptr, workspace, workspace_bytes,
+                                   stream, nullptr, fe, F);
 }
 
 }  // extern "C"

@@ -95,6 +95,52 @@ def params_fingerprint(wn) -> tuple:
     return (_generation,) + tuple((p.data_ptr(), p._version) for p in wn.parameters())
 
 
+@dataclass
+class FrontendPack:
+    struct: "_lib.CondFrontend"
+    total_scale: int
+    keep: list
+
+
+def pack_frontend(wn):
+    """The conditioning front-end as plain arrays for wae_stack_forward_bf16_lat (upsample.py:29-85): conv_in weight transposed
+    to [in][out], one folded (2s+1)-tap filter per stage.  None when the upsampler is not expressible that way (activation,
+    frequency-axis kernel, cin_pad > 0, another interpolation mode): the caller then runs the stages one by one."""
+    from .wavenet_vocoder import upsample as U
+    net = wn.upsample_net
+    conv_in = None
+    if isinstance(net, U.ConvInUpsampleNetwork):
+        conv_in, up = net.conv_in, net.upsample
+    elif isinstance(net, U.UpsampleNetwork):
+        up = net
+    else:
+        return None
+    if (up.freq_axis_kernel_size != 1 or up.has_activation or up.mode != "nearest" or up.indent != 0
+            or not 1 <= len(up.scales) <= 8):
+        return None
+    if conv_in is not None and (conv_in.kernel_size[0] != 1 or conv_in.bias is not None or conv_in.weight.shape[0] != conv_in.weight.shape[1]):
+        return None
+    fe = _lib.CondFrontend()
+    keep = []
+    if conv_in is not None:
+        wt = folded_weight(conv_in).float()[:, :, 0].t().contiguous()      # (in, out)
+        keep.append(wt)
+        fe.conv_in_w_t = wt.data_ptr()
+    else:
+        fe.conv_in_w_t = None
+    convs = [m for m in up.up_layers if isinstance(m, torch.nn.Conv2d)]
+    fe.n_stages = len(up.scales)
+    total = 1
+    for i, (s, conv) in enumerate(zip(up.scales, convs)):
+        w = folded_weight(conv).float().reshape(-1).contiguous()
+        assert w.numel() == 2 * s + 1
+        keep.append(w)
+        fe.scale[i] = int(s)
+        fe.filter[i] = w.data_ptr()
+        total *= int(s)
+    return FrontendPack(fe, total, keep)
+
+
 def _ru(x, m):
     return (x + m - 1) // m * m
 

@@ -85,6 +85,7 @@ class WaveNet(nn.Module):
         self.ar_cluster = None            # None -> 16 CTAs for fp32 weights, 8 for bf16
         self.ar_utts_per_cluster = None   # None -> 8 for the tensor-core AR kernel, 2 for the SIMT kernel
         self.ar_impl = "mma"               # "mma" | "simt" (bf16 precision only)
+        self.fuse_frontend = True          # bf16 inference: conv_in + all upsampler stages inside the stack's conditioning kernel
         self.train_impl = "kernels"        # "kernels": tcgen05 forward + GEMM backward (bf16, CUDA) | "autograd": torch ops
         self.last_sampled_indices = None  # (B,T) int32 of the last categorical incremental_forward
         self.last_ar_variant = None       # (weight type, cluster size, utterances per cluster) the last synthesis ran with
@@ -136,7 +137,7 @@ class WaveNet(nn.Module):
         fp = packing.params_fingerprint(self)
         hit = self._packs.get(key)
         if hit is None or hit[0] != fp:
-            fn = {"f32": packing.pack_f32, "bf16": packing.pack_bf16, "ar": packing.pack_ar}[kind]
+            fn = {"f32": packing.pack_f32, "bf16": packing.pack_bf16, "ar": packing.pack_ar, "fe": packing.pack_frontend}[kind]
             with torch.no_grad():
                 hit = (fp, fn(self, **kw))
             self._packs[key] = hit
@@ -162,10 +163,21 @@ class WaveNet(nn.Module):
             if autograd or self.precision != "bf16" or not x.is_cuda:
                 x = F.one_hot(x.long(), self.out_channels).float().transpose(1, 2)
             else:
-                x_idx = x.long().contiguous()
+                x_idx = x = x.long().contiguous()     # the kernels read int64 classes
         B, T = x.size(0), x.size(-1)
         gvec = self._speaker_vectors(g, B)
         last_stage = None
+        if (c is not None and self.upsample_net is not None and not autograd and self.precision == "bf16" and x.is_cuda
+                and self.fuse_frontend and c.is_cuda and c.dim() == 3):
+            fe = self._pack("fe")
+            if fe is not None:
+                # inference: conv_in + the whole upsampler are evaluated inside the stack's conditioning pass (row f1)
+                if c.size(-1) * fe.total_scale != x.size(-1):
+                    print(f"c {c.size() } x {x.size()}")
+                    raise Exception
+                with torch.no_grad():
+                    out = self.stack_forward(x, c, gvec, frontend=fe, x_is_index=x_idx is not None)
+                return F.softmax(out, dim=1) if softmax else out
         if c is not None and self.upsample_net is not None:
             if not autograd and self.precision == "bf16" and x.is_cuda and isinstance(self.upsample_net, (upsample.UpsampleNetwork, upsample.ConvInUpsampleNetwork)):
                 # inference: the last upsampler stage is fused into the stack's conditioning pass
@@ -238,7 +250,24 @@ class WaveNet(nn.Module):
         B, T = x_idx.shape
         gvec = self._speaker_vectors(g, B)
         up_w, up_s = None, 0
+        fe = self._pack("fe") if (c is not None and self.upsample_net is not None and self.fuse_frontend and c.dim() == 3) else None
         with torch.no_grad():
+            if fe is not None:
+                if c.size(-1) * fe.total_scale != T:
+                    print(f"c {c.size() } x {x_idx.size()}")
+                    raise Exception
+                xi = x_idx.detach().long().contiguous()
+                tg = target.detach().long().contiguous()
+                lat = c.detach().float().contiguous()
+                gv = None if gvec is None else gvec.detach().float().contiguous()
+                L, st = _lib.lib(), _lib.stream_ptr(xi.device)
+                pk = self._pack("bf16")
+                ws = self._ws.get(L.wae_stack_workspace_bf16(pk.struct.d, B, T), xi.device)
+                out = torch.zeros(1, dtype=torch.float64, device=xi.device)
+                _lib.check(L.wae_stack_forward_bf16_lat(pk.struct, None, _lib.ptr(xi), _lib.ptr(lat), lat.shape[-1], fe.struct, _lib.ptr(gv), B, T,
+                                                        _lib.ptr(logits_out), _lib.ptr(tg), int(shift), _lib.ptr(out), _lib.ptr(ws),
+                                                        ws.numel(), st), "wae_stack_forward_bf16_lat")
+                return (out[0] / float(B * (T - shift))).float()
             if c is not None and self.upsample_net is not None:
                 deferred = None
                 if isinstance(self.upsample_net, (upsample.UpsampleNetwork, upsample.ConvInUpsampleNetwork)):
@@ -265,14 +294,14 @@ class WaveNet(nn.Module):
                                                 ws.numel(), st), "wae_stack_nll_bf16_idx")
             return (out[0] / float(B * (T - shift))).float()
 
-    def stack_forward(self, x, c_up, gvec, precision=None, last_stage=None, x_is_index=False):
+    def stack_forward(self, x, c_up, gvec, precision=None, last_stage=None, x_is_index=False, frontend=None):
         """The hot path proper: first_conv + residual stack + head on already-upsampled conditioning (or, with
         ``last_stage=(filter, scale)``, on the frames entering the last upsampler stage; bf16 only).  ``x_is_index``: x is
         the (B,T) int64 class tensor (bf16 only)."""
         self._require_cuda(x, "WaveNet.forward")
         precision = precision or self.precision
-        if (last_stage is not None or x_is_index) and precision != "bf16":
-            raise ValueError("last_stage fusion / index input exist for precision='bf16' only")
+        if (last_stage is not None or x_is_index or frontend is not None) and precision != "bf16":
+            raise ValueError("front-end / last_stage fusion / index input exist for precision='bf16' only")
         B, T = x.shape[0], x.shape[-1]
         x = x.detach().contiguous() if x_is_index else x.detach().float().contiguous()
         c_up = None if c_up is None else c_up.detach().float().contiguous()
@@ -290,7 +319,13 @@ class WaveNet(nn.Module):
             pk = self._pack("bf16")
             n = L.wae_stack_workspace_bf16(pk.struct.d, B, T)
             ws = self._ws.get(n, x.device)
-            if x_is_index:
+            if frontend is not None:
+                # c_up holds the LATENT frames (B, C, F); ``frontend``: packing.FrontendPack
+                _lib.check(L.wae_stack_forward_bf16_lat(pk.struct, None if x_is_index else _lib.ptr(x), _lib.ptr(x) if x_is_index else None,
+                                                        _lib.ptr(c_up), c_up.shape[-1], frontend.struct, _lib.ptr(gvec), B, T,
+                                                        _lib.ptr(logits), None, 0, None, _lib.ptr(ws), ws.numel(), st),
+                           "wae_stack_forward_bf16_lat")
+            elif x_is_index:
                 up_w, up_s = last_stage if last_stage is not None else (None, 0)
                 up_w = None if up_w is None else up_w.detach().float().contiguous()
                 _lib.check(L.wae_stack_forward_bf16_idx(pk.struct, _lib.ptr(x), _lib.ptr(c_up), 0 if c_up is None else c_up.shape[-1],
