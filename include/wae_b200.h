@@ -111,6 +111,55 @@ int wae_conv1d_relu_res(const float* x, const float* w, const float* bias, int B
  * dozen 64 x 64 tiles with a long serial reduction); `partial` holds splits x B x Cout x Tout floats, summed in a fixed order by
  * a second launch that also applies bias / ReLU / residual. */
 
+/* ---- encoder + Linear + VQ search in one launch ------- */
+/*
+ * The inference-time encoder of vqvae_model.py:25-51 (ConvReLURes blocks, then Linear hid -> D) followed by the nearest-codeword
+ * search of vector_quantization.py:21-49 (one slice) / :75-128 (two slices), as ONE persistent kernel: a group of 8 co-resident
+ * CTAs per (utterance, block of latents), each CTA computes an eighth of every layer's output channels, the layer activations
+ * are exchanged through an L2-resident scratch with one group barrier per layer; the latent vectors exist only on chip unless
+ * lat_out is given.
+ *   layer[l].w    conv weight (Cout, Cin, k) TRANSPOSED to (Cin, k, Cout) fp32, as for wae_conv1d_relu_res
+ *   lin_w_t       Linear weight (D, hid) TRANSPOSED to (hid, D); lin_b (D) or NULL
+ * Supported (wae_encoder_vq_supported() == 1): Cout % 32 == 0, channels <= 256, (k, stride) in {(1,1), (3,1), (5,2)},
+ * exactly two stride-2 layers, receptive field <= +-16 input frames -- every configuration the reference's Encoder produces with
+ * encoder_hid <= 256.  Anything else: run the layers with wae_conv1d_relu_res and the search with wae_vq_search.
+ * x (B, Cin, F) fp32; outputs in the reference layout: lat_out / quant_out (B, D, F4), F4 = frames after the two stride-2
+ * layers; per slice idx_out (B*F4) int64, counts_out (K) int32 and sqerr_out (1) double as in wae_vq_search (caller zeroes the
+ * accumulators; any of them may be NULL).  Arithmetic of the search: bit-identical to wae_vq_search on the same latents.
+ */
+typedef struct wae_enc_layer {
+    const float* w;
+    const float* bias;         /* (Cout) or NULL */
+    int cin, cout, k, stride, relu, residual;
+} wae_enc_layer;
+typedef struct wae_encoder {
+    int n_layers;              /* <= 16 */
+    wae_enc_layer layer[16];
+    const float* lin_w_t;
+    const float* lin_b;
+    int hid, D;
+} wae_encoder;
+typedef struct wae_vq_slice {
+    const float* codebook;     /* (K, sub_d) fp32 */
+    int K, d0, sub_d;
+    int64_t* idx_out;
+    int32_t* counts_out;
+    double* sqerr_out;
+} wae_vq_slice;
+int wae_encoder_vq_supported(const wae_encoder* enc);
+/* Scratch bytes for (B, F): group barrier counters + two L2-resident activation buffers per concurrently processed item. */
+size_t wae_encoder_vq_workspace(int B, int F);
+/* Debug builds (-DWAE_EV_PROF) only: the 64 phase clocks CTA 0 recorded during the last launch (tools/enc_profile.py). */
+int wae_encoder_vq_profile(long long* out64);
+/* lengths: (B) int32 valid frames per utterance (<= F) for ragged batches -- utterance b is encoded exactly as if run alone with
+ * F = lengths[b] (zero padding from ITS last frame; latents beyond its own F4 are not written and not counted) -- or NULL. */
+int wae_encoder_vq_forward(const wae_encoder* enc, const float* x, const int32_t* lengths, int B, int F, int n_slices,
+                           const wae_vq_slice* slices, float* lat_out, float* quant_out, void* workspace, size_t workspace_bytes,
+                           void* stream);
+/* inference_2019.py:262 np.savetxt(path, rep, fmt='%.6f'): writes the (rows, cols) fp32 HOST matrix as text, byte-identical to
+ * numpy's output for fmt = "%.<decimals>f" (values formatted through double, single spaces, one row per line).  Host-only. */
+int wae_dump_text(const char* path, const float* data, long long rows, int cols, int decimals);
+
 /* ---- WaveNet decoder stack: shared description -------------------------- */
 typedef struct wae_stack_dims {
     int32_t layers;       /* L */

@@ -560,6 +560,71 @@ def test_encoder_kernels_match_torch_convs(frames):
         assert rel_err(enc(x).cpu().numpy(), ref2.cpu().numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("frames,B,sliced", [(100, 16, False), (37, 3, True), (1, 2, False), (128, 2, False), (129, 2, False), (300, 3, True), (1000, 1, False)])
+def test_encoder_vq_fused_kernel(frames, B, sliced):
+    """wae_encoder_vq_forward (encoder + Linear + VQ search in one launch, cluster of 8 CTAs per item) against
+    (a) the torch/cuDNN fp32 encoder (latents <= 1e-5 relative; another summation order), (b) the standalone search kernel
+    wae_vq_search run on the fused kernel's own latents: codes, quantised values, loss and perplexity BIT-identical -- the
+    search arithmetic is the same; (c) utterances longer than 128 frames (24-latent blocks with a recomputed halo)."""
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    torch.manual_seed(0)
+    m = VQVAE(c_in=39, hid=64, K=256, wavenet=None, encoder_hid=256).eval()
+    if sliced:
+        m.vq = vqm.SlicedVectorQuantize(256, 64)
+    m.load_state_dict(T.synth_state_dict(m, 3))
+    m = m.cuda()
+    x = torch.randn(B, 39, frames, device="cuda")
+    with torch.no_grad():
+        enc = m.encoder.fused_struct()
+        assert enc is not None and m.vq._fusable(x)
+        n0 = _lib.launch_count()
+        quant, loss, perp = m._encode_quantize(x)
+        assert _lib.launch_count() - n0 == 2                 # the fused kernel + the statistics finaliser
+        codes = m.vq.last_codes.clone()
+        F4 = m.encoder.out_frames(frames)
+        q2, l2, p2 = m.vq._forward_fused(enc, x, F4, want_latents=True)
+        lat = m.vq.last_latents
+        assert torch.equal(q2, quant) and torch.equal(m.vq.last_codes, codes)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            ref = m.encoder.lin(m.encoder.net(x).permute(0, 2, 1)).permute(0, 2, 1)
+        assert lat.shape == ref.shape
+        assert rel_err(lat.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+        qs, ls, ps = m.vq(lat)                               # standalone search kernel on the same latents
+        assert torch.equal(m.vq.last_codes, codes)
+        assert torch.equal(qs.contiguous(), quant)
+        assert abs(float(ls) - float(loss)) <= 1e-6 * abs(float(ls)) and abs(float(ps) - float(perp)) <= 1e-6 * abs(float(ps))
+        m.fuse_encoder = False                               # module by module: same codes unless a latent sits on a near-tie
+        qu, lu, pu = m._encode_quantize(x)
+        agree = float((m.vq.last_codes == codes).float().mean())
+        assert agree > 0.995, agree
+
+
+def test_encode_batch_ragged_matches_per_utterance_encode(tmp_path):
+    """VQVAE.encode_batch (inference_2019.py:225-262 batched): utterances of different lengths in ONE launch (per-utterance
+    lengths inside the fused kernel) == encode() utterance by utterance, bit for bit; the text dump equals np.savetxt('%.6f')."""
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    torch.manual_seed(0)
+    m = VQVAE(c_in=39, hid=64, K=256, wavenet=None, encoder_hid=256).eval()
+    m.load_state_dict(T.synth_state_dict(m, 3))
+    m = m.cuda()
+    rs = np.random.RandomState(5)
+    lens = [100, 37, 1, 128, 64, 99, 5]
+    feats = [rs.normal(size=(n, 39)).astype(np.float32) for n in lens]
+    n0 = _lib.launch_count()
+    reps = m.encode_batch(feats)
+    assert _lib.launch_count() - n0 == 2
+    for f, rep in zip(feats, reps):
+        one = m.encode(torch.tensor(f.T[None]).cuda())[0].t().cpu().numpy()          # (T', D), the reference's per-utterance call
+        assert rep.shape == one.shape
+        np.testing.assert_array_equal(rep, one)
+    long_feats = [rs.normal(size=(n, 39)).astype(np.float32) for n in (300, 131, 700)]    # > 128 frames: tiled items, ragged
+    for f, rep in zip(long_feats, m.encode_batch(long_feats)):
+        np.testing.assert_array_equal(rep, m.encode(torch.tensor(f.T[None]).cuda())[0].t().cpu().numpy())
+    m.dump_representation(tmp_path / "rep.txt", reps[0])
+    np.savetxt(tmp_path / "ref.txt", reps[0], fmt="%.6f")
+    assert (tmp_path / "rep.txt").read_bytes() == (tmp_path / "ref.txt").read_bytes()
+
+
 def test_flat_adam_matches_torch_adam_with_clipping():
     """train_step.FlatAdam (wae_sumsq + wae_adam_step on one flat buffer) against clip_grad_norm_ + torch.optim.Adam."""
     from wavenet_autoencoders_b200.train_step import FlatAdam

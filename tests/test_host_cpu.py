@@ -266,3 +266,19 @@ def test_library_sass_contains_tcgen05_tma_and_cluster_instructions():
               for m in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTCBAR", "UTMALDG", "UTMASTG", "UBLKCP", "HMMA.16816.F32.BF16")}
     missing = [m for m, n in counts.items() if n == 0]
     assert not missing, f"SASS lacks {missing}: {counts}"
+
+
+def test_representation_text_dump_matches_numpy_savetxt(tmp_path):
+    """wae_dump_text (host-only entry point of the C ABI) == np.savetxt(fmt='%.6f'), the ABX feature dump of
+    inference_2019.py:262: byte-identical incl. negative zero, tiny and large values."""
+    import numpy as np
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    rs = np.random.RandomState(0)
+    a = (rs.randn(211, 64) * np.exp(rs.randn(211, 64) * 4)).astype(np.float32)
+    a[0, :6] = [0.0, -0.0, 1e-7, -5e-7, 123456.789, 0.4999995]
+    VQVAE.dump_representation(tmp_path / "a.txt", a)
+    np.savetxt(tmp_path / "b.txt", a, fmt="%.6f")
+    assert (tmp_path / "a.txt").read_bytes() == (tmp_path / "b.txt").read_bytes()
+    VQVAE.dump_representation(tmp_path / "c.txt", a[:3, :1], decimals=3)
+    np.savetxt(tmp_path / "d.txt", a[:3, :1], fmt="%.3f")
+    assert (tmp_path / "c.txt").read_bytes() == (tmp_path / "d.txt").read_bytes()

@@ -54,6 +54,20 @@ class CondFrontend(C.Structure):
     _fields_ = [("conv_in_w_t", C.c_void_p), ("n_stages", C.c_int32), ("scale", C.c_int32 * 8), ("filter", C.c_void_p * 8)]
 
 
+class EncLayer(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("bias", C.c_void_p)] + [(n, C.c_int32) for n in ("cin", "cout", "k", "stride", "relu", "residual")]
+
+
+class Encoder(C.Structure):
+    _fields_ = [("n_layers", C.c_int32), ("layer", EncLayer * 16), ("lin_w_t", C.c_void_p), ("lin_b", C.c_void_p),
+                ("hid", C.c_int32), ("D", C.c_int32)]
+
+
+class VqSlice(C.Structure):
+    _fields_ = [("codebook", C.c_void_p), ("K", C.c_int32), ("d0", C.c_int32), ("sub_d", C.c_int32),
+                ("idx_out", C.c_void_p), ("counts_out", C.c_void_p), ("sqerr_out", C.c_void_p)]
+
+
 class ArWeights(C.Structure):
     _fields_ = [
         ("d", StackDims),
@@ -103,6 +117,12 @@ SIGNATURES = {
     "wae_stack_forward_bf16_lat": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(CondFrontend),
                                              C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
                                              C.c_size_t, C.c_void_p]),
+    "wae_encoder_vq_supported": (C.c_int, [C.POINTER(Encoder)]),
+    "wae_encoder_vq_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "wae_encoder_vq_profile": (C.c_int, [C.c_void_p]),
+    "wae_encoder_vq_forward": (C.c_int, [C.POINTER(Encoder), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(VqSlice), C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wae_dump_text": (C.c_int, [C.c_char_p, C.c_void_p, C.c_longlong, C.c_int, C.c_int]),
     "wae_nll_sum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wae_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "wae_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,

@@ -20,7 +20,7 @@ CSRC = PKG / "csrc"
 LIB = PKG / "libwae_b200.so"
 OBJ = PKG / "build"
 
-SOURCES = ["wae_lib.cu", "vq_search.cu", "wn_stack_f32.cu", "wn_stack_bf16.cu", "wn_ar.cu", "wn_train.cu", "wn_bwd.cu", "synth_post.cu"]
+SOURCES = ["wae_lib.cu", "vq_search.cu", "wn_stack_f32.cu", "wn_stack_bf16.cu", "wn_ar.cu", "wn_train.cu", "wn_bwd.cu", "synth_post.cu", "enc_vq_fused.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -418,112 +418,184 @@ cond_stage_cl_kernel(const float* __restrict__ in, int C, int Cp, int Tin, int s
 // to a handful of latent frames, on which conv_in is applied first.  Every stage uses the 3-coefficient form and the FMA order of
 // upsample_stage_kernel / cond_stage_cl_kernel (positions outside [0, len) are zero: the reference's zero padding per stage), so
 // the result equals the staged path bit for bit; nothing at an intermediate rate ever goes to global memory.
-constexpr int CF_T = 128;        // samples per block
+constexpr int CF_T = 128;        // samples per tile
+constexpr int CF_NT = 5;         // consecutive tiles per block: conv_in and the coefficient tables are set up once for all of them
 constexpr int CF_PITCH = 133;    // >= CF_T + 3 positions (a stage of scale 1), odd
+constexpr int CF_F0 = 24;        // latent frames a block may need (host-checked)
 constexpr int CF_MAX_STAGES = 8;
 struct CondFrontArgs {
     const float* lat;            // (B, C, F)
     const float* win_t;          // (C, C) conv_in weight transposed to [in][out], or null
     const float* filt[CF_MAX_STAGES];
     int scale[CF_MAX_STAGES];
-    int ns, C, Cp, F, T;
+    int ns, C, Cp, F, T, nt;     // nt: tiles per block (<= CF_NT, host-chosen so that a block needs <= CF_F0 latent frames)
     __nv_bfloat16* out;          // [B][T][Cp]
 };
 
 __global__ void __launch_bounds__(256)
 cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
     extern __shared__ float cf_sm[];
-    // coefficient tables of all stages [3][s_i], then two position buffers [Cp][CF_PITCH]
-    int coef_off[CF_MAX_STAGES], lo[CF_MAX_STAGES + 1], hi[CF_MAX_STAGES + 1], len[CF_MAX_STAGES + 1];
+    // coefficient tables of all stages [3][s_i] | y0 [Cp][CF_F0 + 1] latent frames after conv_in | two position buffers [Cp][CF_PITCH]
+    // | position table [CF_PITCH] (frame offset | phase << 16) of the stage being evaluated
+    __shared__ int s_coef_off[CF_MAX_STAGES], s_len[CF_MAX_STAGES + 1];
+    __shared__ int s_lo[CF_MAX_STAGES + 1], s_hi[CF_MAX_STAGES + 1];
     int ctot = 0;
-    for (int i = 0; i < a.ns; ++i) { coef_off[i] = ctot; ctot += 3 * a.scale[i]; }
+    for (int i = 0; i < a.ns; ++i) ctot += 3 * a.scale[i];
     float* coef = cf_sm;
-    float* buf0 = cf_sm + ((ctot + 3) & ~3);
+    float* y0 = cf_sm + ((ctot + 3) & ~3);
+    float* buf0 = y0 + a.Cp * (CF_F0 + 1);
     float* buf1 = buf0 + a.Cp * CF_PITCH;
-    const int b = blockIdx.y, t0 = blockIdx.x * CF_T, tid = threadIdx.x;
-    // position ranges, top down: level ns = output samples, level i = input of stage i (level 0 = latent frames)
-    len[0] = a.F;
-    for (int i = 0; i < a.ns; ++i) len[i + 1] = len[i] * a.scale[i];
-    lo[a.ns] = t0; hi[a.ns] = min(t0 + CF_T, a.T) - 1;
-    for (int i = a.ns - 1; i >= 0; --i) {
-        // floor division that also works for lo = -1 (positions left of the signal are zeros computed from zeros)
-        const int s = a.scale[i];
-        lo[i] = (lo[i + 1] >= 0 ? lo[i + 1] / s : -1) - 1;
-        hi[i] = (hi[i + 1] >= 0 ? hi[i + 1] / s : -1) + 1;
+    int* ptab = reinterpret_cast<int*>(buf1 + a.Cp * CF_PITCH);
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int tile0 = blockIdx.x * a.nt;
+    const int ntiles = (a.T + CF_T - 1) / CF_T;
+    const int tile1 = min(tile0 + a.nt, ntiles);
+
+    if (tid == 0) {
+        int off = 0, len = a.F;
+        for (int i = 0; i < a.ns; ++i) { s_coef_off[i] = off; off += 3 * a.scale[i]; s_len[i] = len; len *= a.scale[i]; }
+        s_len[a.ns] = len;
     }
-    for (int i = 0; i < a.ns; ++i) {
-        const int s = a.scale[i];
-        const float* w = a.filt[i];
-        float* cf = coef + coef_off[i];
-        for (int p = tid; p < s; p += 256) {
-            float x = 0.f, y = 0.f, z = 0.f;
-            for (int j = 0; j < s - p; ++j) x += __ldg(&w[j]);
-            for (int j = s - p; j < 2 * s - p; ++j) y += __ldg(&w[j]);
-            for (int j = 2 * s - p; j <= 2 * s; ++j) z += __ldg(&w[j]);
-            cf[p] = x; cf[s + p] = y; cf[2 * s + p] = z;
+    // partial tap sums per phase (as upsample_stage_kernel): out[f*s+p] = A[p] in[f-1] + B[p] in[f] + C[p] in[f+1]
+    {
+        int off = 0;
+        for (int i = 0; i < a.ns; ++i) {
+            const int s = a.scale[i];
+            const float* w = a.filt[i];
+            for (int p = tid; p < s; p += 256) {
+                float x = 0.f, y = 0.f, z = 0.f;
+                for (int j = 0; j < s - p; ++j) x += __ldg(&w[j]);
+                for (int j = s - p; j < 2 * s - p; ++j) y += __ldg(&w[j]);
+                for (int j = 2 * s - p; j <= 2 * s; ++j) z += __ldg(&w[j]);
+                coef[off + p] = x; coef[off + s + p] = y; coef[off + 2 * s + p] = z;
+            }
+            off += 3 * s;
         }
     }
-    // level 0: latent frames [lo0, hi0] (zeros outside [0, F)), conv_in applied
-    const int n0 = hi[0] - lo[0] + 1;
+    // latent frames the block's tiles can touch: [F0, F0 + n0), conv_in applied once
+    int F0, n0;
     {
-        float* raw = a.win_t ? buf1 : buf0;
+        int lo = tile0 * CF_T, hi = min(tile1 * CF_T, a.T) - 1;
+        for (int i = a.ns - 1; i >= 0; --i) {         // the per-tile recursion below, applied to the block's first / last sample
+            lo = (lo >= 0 ? lo / a.scale[i] : -1) - 1;
+            hi = (hi >= 0 ? hi / a.scale[i] : -1) + 1;
+        }
+        F0 = lo; n0 = hi - lo + 1;
+    }
+    {
+        float* raw = a.win_t ? buf0 : y0;                      // raw frames [C][n0] (pitch CF_F0 + 1 in y0, n0 in the scratch)
+        const int rp = a.win_t ? n0 : CF_F0 + 1;
         for (int e = tid; e < a.Cp * n0; e += 256) {
-            const int ch = e / n0, k = e - ch * n0, f = lo[0] + k;
-            raw[ch * CF_PITCH + k] = (ch < a.C && f >= 0 && f < a.F) ? __ldg(&a.lat[((size_t)b * a.C + ch) * a.F + f]) : 0.f;
+            const int ch = e / n0, k = e - ch * n0, f = F0 + k;
+            raw[ch * rp + k] = (ch < a.C && f >= 0 && f < a.F) ? __ldg(&a.lat[((size_t)b * a.C + ch) * a.F + f]) : 0.f;
         }
         __syncthreads();
         if (a.win_t) {
-            for (int e = tid; e < a.Cp * n0; e += 256) {
-                const int k = e / a.Cp, co = e - k * a.Cp;      // consecutive threads: consecutive output channels
-                float acc = 0.f;
-                if (co < a.C) {
+            // thread = (output channel, frame lane): the weight column is read once per thread and reused for its frames
+            const int co = tid % a.Cp, kl = tid / a.Cp, nkl = 256 / a.Cp;     // Cp divides 256 for Cp in {64, 128, 256}
+            if (nkl >= 1) {
+                for (int k = kl; k < n0; k += nkl) {
+                    float acc = 0.f;
+                    if (co < a.C) {
 #pragma unroll 8
-                    for (int ci = 0; ci < a.C; ++ci) acc = fmaf(__ldg(&a.win_t[(size_t)ci * a.C + co]), buf1[ci * CF_PITCH + k], acc);
+                        for (int ci = 0; ci < a.C; ++ci) acc = fmaf(__ldg(&a.win_t[(size_t)ci * a.C + co]), buf0[ci * n0 + k], acc);
+                    }
+                    y0[co * (CF_F0 + 1) + k] = acc;
                 }
-                buf0[co * CF_PITCH + k] = acc;
+            } else {
+                for (int e = tid; e < a.Cp * n0; e += 256) {
+                    const int k = e / a.Cp, co2 = e - k * a.Cp;
+                    float acc = 0.f;
+                    if (co2 < a.C)
+                        for (int ci = 0; ci < a.C; ++ci) acc = fmaf(__ldg(&a.win_t[(size_t)ci * a.C + co2]), buf0[ci * n0 + k], acc);
+                    y0[co2 * (CF_F0 + 1) + k] = acc;
+                }
             }
-            __syncthreads();
-        }
-    }
-    // stages 0 .. ns-2: level i (in `cur`, origin lo[i]) -> level i+1 positions [lo[i+1], hi[i+1]]
-    float* cur = buf0;
-    float* nxt = buf1;
-    for (int i = 0; i + 1 < a.ns; ++i) {
-        const int s = a.scale[i], n1 = hi[i + 1] - lo[i + 1] + 1, L1 = len[i + 1];
-        const float* cf = coef + coef_off[i];
-        for (int e = tid; e < a.Cp * n1; e += 256) {
-            const int ch = e / n1, k = e - ch * n1, u = lo[i + 1] + k;
-            float v = 0.f;
-            if (u >= 0 && u < L1) {
-                const int f = u / s, p = u - f * s;
-                const float* xr = cur + ch * CF_PITCH + (f - lo[i]);
-                v = fmaf(cf[2 * s + p], xr[1], fmaf(cf[s + p], xr[0], cf[p] * xr[-1]));
-            }
-            nxt[ch * CF_PITCH + k] = v;
         }
         __syncthreads();
-        float* t = cur; cur = nxt; nxt = t;
     }
-    // last stage + layout change
-    {
-        const int i = a.ns - 1, s = a.scale[i];
-        const float* cf = coef + coef_off[i];
-        const int c8n = a.Cp >> 3;
-        for (int e = tid; e < CF_T * c8n; e += 256) {
-            const int tt = e / c8n, c8 = (e - tt * c8n) * 8, t = t0 + tt;
-            if (t >= a.T) break;
-            const int f = t / s, p = t - f * s, k = f - lo[i];
-            const float ca = cf[p], cb = cf[s + p], cc = cf[2 * s + p];
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float* xr = cur + (c8 + j) * CF_PITCH + k;
-                v[j] = fmaf(cc, xr[1], fmaf(cb, xr[0], ca * xr[-1]));
+
+    const int chn = tid % a.Cp;                 // fixed channel per thread in the stage loops (Cp | 256), else strided fallback
+    const bool fixed_ch = (256 % a.Cp) == 0;
+    const int c8n = a.Cp >> 3;
+    for (int tile = tile0; tile < tile1; ++tile) {
+        const int t0 = tile * CF_T;
+        if (tid == 0) {
+            s_lo[a.ns] = t0; s_hi[a.ns] = min(t0 + CF_T, a.T) - 1;
+            for (int i = a.ns - 1; i >= 0; --i) {
+                const int s = a.scale[i];
+                s_lo[i] = (s_lo[i + 1] >= 0 ? s_lo[i + 1] / s : -1) - 1;
+                s_hi[i] = (s_hi[i + 1] >= 0 ? s_hi[i + 1] / s : -1) + 1;
             }
-            uint4 o4;
-            o4.x = pack_bf16x2(v[0], v[1]); o4.y = pack_bf16x2(v[2], v[3]);
-            o4.z = pack_bf16x2(v[4], v[5]); o4.w = pack_bf16x2(v[6], v[7]);
-            *reinterpret_cast<uint4*>(a.out + ((size_t)b * a.T + t) * a.Cp + c8) = o4;
+        }
+        __syncthreads();
+        // level 0 of this tile: a window of y0
+        const float* cur = y0 + (s_lo[0] - F0);
+        int cur_pitch = CF_F0 + 1;
+        float* nxt = buf0;
+        for (int i = 0; i + 1 < a.ns; ++i) {
+            const int s = a.scale[i], lo1 = s_lo[i + 1], n1 = s_hi[i + 1] - lo1 + 1, L1 = s_len[i + 1], lo_in = s_lo[i];
+            const float* cf = coef + s_coef_off[i];
+            for (int k = tid; k < n1; k += 256) {
+                const int u = lo1 + k;
+                int v = -1;
+                if (u >= 0 && u < L1) { const int f = u / s; v = (f - lo_in) | ((u - f * s) << 16); }
+                ptab[k] = v;
+            }
+            __syncthreads();
+            if (fixed_ch) {
+                for (int k = tid / a.Cp; k < n1; k += 256 / a.Cp) {
+                    const int pt = ptab[k];
+                    float v = 0.f;
+                    if (pt >= 0) {
+                        const int fo = pt & 0xffff, p = pt >> 16;
+                        const float* xr = cur + chn * cur_pitch + fo;
+                        v = fmaf(cf[2 * s + p], xr[1], fmaf(cf[s + p], xr[0], cf[p] * xr[-1]));
+                    }
+                    nxt[chn * CF_PITCH + k] = v;
+                }
+            } else {
+                for (int e = tid; e < a.Cp * n1; e += 256) {
+                    const int ch = e / n1, k = e - ch * n1, pt = ptab[k];
+                    float v = 0.f;
+                    if (pt >= 0) {
+                        const int fo = pt & 0xffff, p = pt >> 16;
+                        const float* xr = cur + ch * cur_pitch + fo;
+                        v = fmaf(cf[2 * s + p], xr[1], fmaf(cf[s + p], xr[0], cf[p] * xr[-1]));
+                    }
+                    nxt[ch * CF_PITCH + k] = v;
+                }
+            }
+            __syncthreads();
+            cur = nxt; cur_pitch = CF_PITCH;
+            nxt = (nxt == buf0) ? buf1 : buf0;
+        }
+        // last stage + layout change
+        {
+            const int i = a.ns - 1, s = a.scale[i], lo_in = s_lo[i];
+            const float* cf = coef + s_coef_off[i];
+            const int nt = min(CF_T, a.T - t0);
+            for (int k = tid; k < nt; k += 256) { const int t = t0 + k, f = t / s; ptab[k] = (f - lo_in) | ((t - f * s) << 16); }
+            __syncthreads();
+            const int tt0 = tid / c8n, c8 = (tid - tt0 * c8n) * 8, tstep = 256 / c8n;
+            const bool reg = (256 % c8n) == 0;
+            for (int e = tid; e < nt * c8n; e += 256) {
+                const int tt = reg ? tt0 + (e / 256) * tstep : e / c8n;
+                const int cc8 = reg ? c8 : (e - tt * c8n) * 8;
+                const int pt = ptab[tt], fo = pt & 0xffff, p = pt >> 16;
+                const float ca = cf[p], cb = cf[s + p], cc = cf[2 * s + p];
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float* xr = cur + (cc8 + j) * cur_pitch + fo;
+                    v[j] = fmaf(cc, xr[1], fmaf(cb, xr[0], ca * xr[-1]));
+                }
+                uint4 o4;
+                o4.x = pack_bf16x2(v[0], v[1]); o4.y = pack_bf16x2(v[2], v[3]);
+                o4.z = pack_bf16x2(v[4], v[5]); o4.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(a.out + ((size_t)b * a.T + t0 + tt) * a.Cp + cc8) = o4;
+            }
+            __syncthreads();      // ptab / buffers are reused by the next tile
         }
     }
 }
@@ -2908,10 +2980,19 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         }
         WAE_REQUIRE(total == T, "wae_stack_forward_bf16_lat: %d frames x scales = %lld != T = %d", fe_frames, total, T);
         ca.lat = c; ca.win_t = fe->conv_in_w_t; ca.ns = fe->n_stages; ca.C = d.C; ca.Cp = Cp; ca.F = fe_frames; ca.T = T; ca.out = ws.ccl;
-        const size_t sm = ((size_t)((ctot + 3) & ~3) + (size_t)2 * Cp * CF_PITCH) * sizeof(float);
+        int nt = CF_NT;
+        for (;; --nt) {   // latent frames one block of nt tiles can touch (+ 2: blocks that do not start at a frame boundary)
+            long long lo = 0, hi = (long long)nt * CF_T - 1;
+            for (int i = fe->n_stages - 1; i >= 0; --i) { lo = (lo >= 0 ? lo / fe->scale[i] : -1) - 1; hi = hi / fe->scale[i] + 1; }
+            if (hi - lo + 1 + 2 <= CF_F0) break;
+            WAE_REQUIRE(nt > 1, "wae_stack_forward_bf16_lat: total upsampling factor too small (%lld latent frames per 128-sample tile, max %d)",
+                        hi - lo + 1 + 2, CF_F0);
+        }
+        ca.nt = nt;
+        const size_t sm = ((size_t)((ctot + 3) & ~3) + (size_t)Cp * (CF_F0 + 1) + (size_t)2 * Cp * CF_PITCH + CF_PITCH + 3) * sizeof(float);
         WAE_REQUIRE(sm <= 200 * 1024, "wae_stack_forward_bf16_lat: C=%d needs %zu bytes of shared memory", d.C, sm);
         WAE_CHECK_CUDA(cudaFuncSetAttribute(cond_frontend_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        cond_frontend_cl_kernel<<<dim3((T + CF_T - 1) / CF_T, B), 256, sm, stream>>>(ca);
+        cond_frontend_cl_kernel<<<dim3(((T + CF_T - 1) / CF_T + nt - 1) / nt, B), 256, sm, stream>>>(ca);
         WAE_CHECK_LAUNCH();
     } else if (d.C > 0 && up_s > 0) {
         // c holds the frames before the last upsampler stage: stretch + smooth + layout change in one pass

@@ -120,6 +120,11 @@ def pack_frontend(wn):
         return None
     if conv_in is not None and (conv_in.kernel_size[0] != 1 or conv_in.bias is not None or conv_in.weight.shape[0] != conv_in.weight.shape[1]):
         return None
+    lo, hi = 0, 127           # latent frames one 128-sample tile touches (the kernel's recursion): its frame buffer holds 24
+    for sc in reversed(up.scales):
+        lo, hi = (lo // sc if lo >= 0 else -1) - 1, hi // sc + 1
+    if hi - lo + 1 + 2 > 24:
+        return None
     fe = _lib.CondFrontend()
     keep = []
     if conv_in is not None:

@@ -62,6 +62,58 @@ class _VQBase(nn.Module):
             cols = [_search(xin, emb.weight, d0, sd, None, False)[0].view(B, T) for d0, sd, emb in self._slices()]
         return cols[0] if len(cols) == 1 else torch.stack(cols, dim=-1)
 
+    def _fusable(self, c):
+        """True when this module's forward on the encoder output of ``c`` can run inside wae_encoder_vq_forward: inference only
+        (no gradient, no EMA codebook update), one or two slices with one codebook size."""
+        slices = self._slices()
+        is_ema = hasattr(self, "_ema_update")
+        return (not _needs_grad(c, *[emb.weight for _, _, emb in slices]) and not (is_ema and self.training)
+                and len(slices) <= 2 and len({emb.weight.shape[0] for _, _, emb in slices}) == 1)
+
+    def _forward_fused(self, enc_struct, c, F4, want_latents=False, lengths=None):
+        """Encoder + Linear + search in one launch: same (quant, vq_loss, perplexity) as
+        ``self(encoder(c))``; the latents stay on chip unless ``want_latents``."""
+        cin = c.detach().float().contiguous()
+        B, _, F = cin.shape
+        slices = self._slices()
+        D = sum(sd for _, sd, _ in slices)
+        K = slices[0][2].weight.shape[0]
+        dev = cin.device
+        alloc = torch.zeros if lengths is not None else torch.empty      # ragged: latents past an utterance's end stay 0
+        quant = alloc(B, D, F4, dtype=torch.float32, device=dev)
+        lat = alloc(B, D, F4, dtype=torch.float32, device=dev) if want_latents else None
+        if lengths is not None:
+            lengths = lengths.to(device=dev, dtype=torch.int32).contiguous()
+            assert lengths.numel() == B
+        idx = (torch.full((len(slices), B * F4), -1, dtype=torch.int64, device=dev) if lengths is not None
+               else torch.empty(len(slices), B * F4, dtype=torch.int64, device=dev))
+        sq_all = torch.zeros(len(slices), dtype=torch.float64, device=dev)
+        cn_all = torch.zeros(len(slices), K, dtype=torch.int32, device=dev)
+        arr = (_lib.VqSlice * len(slices))()
+        keep = []
+        for si, (d0, sd, emb) in enumerate(slices):
+            cb = emb.weight.detach().float().contiguous()
+            keep.append(cb)
+            arr[si].codebook, arr[si].K, arr[si].d0, arr[si].sub_d = cb.data_ptr(), K, d0, sd
+            arr[si].idx_out = idx[si].data_ptr()
+            arr[si].counts_out = cn_all[si].data_ptr()
+            arr[si].sqerr_out = sq_all[si:si + 1].data_ptr()
+        L, st = _lib.lib(), _lib.stream_ptr(dev)
+        from .packing import WorkspaceCache
+        if self.__dict__.get("_fused_ws") is None:
+            self.__dict__["_fused_ws"] = WorkspaceCache()
+        ws = self.__dict__["_fused_ws"].get(L.wae_encoder_vq_workspace(B, F), dev)
+        _lib.check(L.wae_encoder_vq_forward(enc_struct, _lib.ptr(cin), _lib.ptr(lengths), B, F, len(slices), arr, _lib.ptr(lat),
+                                            _lib.ptr(quant), _lib.ptr(ws), ws.numel(), st), "wae_encoder_vq_forward")
+        out2 = torch.empty(2, dtype=torch.float32, device=dev)
+        N = B * F4 if lengths is None else int(cn_all[0].sum().item())      # ragged: vectors actually quantised
+        _lib.check(L.wae_vq_stats(_lib.ptr(sq_all), _lib.ptr(cn_all), len(slices), K, max(N, 1), max(N, 1) * D, _lib.ptr(out2), st),
+                   "wae_vq_stats")
+        codes = [idx[si].view(B, F4) for si in range(len(slices))]
+        self.last_codes = codes[0] if len(codes) == 1 else torch.stack(codes, dim=-1)
+        self.last_latents = lat
+        return quant, self._loss(out2[0], out2[0]), out2[1]
+
     def _forward_common(self, x, loss_fn, training_hook=None):
         xin = x.detach().float().contiguous()
         B, D, T = xin.shape
@@ -118,8 +170,11 @@ class VectorQuantize(_VQBase):
     def _slices(self):
         return [(0, self.D, self.embedding)]
 
+    def _loss(self, e, c):
+        return self.beta * e + c          # vector_quantization.py:41-43
+
     def forward(self, inputs):
-        quant, loss, perp = self._forward_common(inputs, lambda e, c: self.beta * e + c)
+        quant, loss, perp = self._forward_common(inputs, self._loss)
         return quant.contiguous(), loss, perp
 
 
@@ -142,9 +197,12 @@ class SlicedVectorQuantize(_VQBase):
     def _slices(self):
         return [(0, self.sub_D, self.embedding1), (self.sub_D, self.D - self.sub_D, self.embedding2)]
 
+    def _loss(self, e, c):
+        return e + self.beta * c          # vector_quantization.py:114-118 (beta on the other term)
+
     def forward(self, x):
         assert x.size(1) == self.D
-        return self._forward_common(x, lambda e, c: e + self.beta * c)
+        return self._forward_common(x, self._loss)
 
 
 class _EMAMixin:
@@ -194,7 +252,10 @@ class SlicedVectorQuantizeEMA(_VQBase, _EMAMixin):
                 for n, ((d0, sd, emb), idx, cnt) in enumerate(zip(self._slices(), idxs, counts), start=1):
                     self._ema_update(xin, idx, cnt, d0, sd, emb, f"ema_cluster_size{n}", f"ema_w{n}")
 
-        return self._forward_common(x, lambda e, c: self.beta * e, hook if self.training else None)
+        return self._forward_common(x, self._loss, hook if self.training else None)
+
+    def _loss(self, e, c):
+        return self.beta * e              # vector_quantization.py:224 (commitment term only)
 
 
 class VectorQuantizeEMA(_VQBase, _EMAMixin):
@@ -220,4 +281,7 @@ class VectorQuantizeEMA(_VQBase, _EMAMixin):
             with torch.no_grad():
                 self._ema_update(xin, idxs[0], counts[0], 0, self.D, self.embedding, "ema_cluster_size", "ema_w")
 
-        return self._forward_common(x, lambda e, c: self.beta * e, hook if self.training else None)
+        return self._forward_common(x, self._loss, hook if self.training else None)
+
+    def _loss(self, e, c):
+        return self.beta * e              # vector_quantization.py:298

@@ -1,7 +1,8 @@
 """Encoder -> VQ -> WaveNet composition with the reference's names (vqvae_model.py:9-84).
 
-The encoder is ordinary frame-rate convolution (1/640 of the sample rate, <2 % of the FLOPs) and stays
-in PyTorch; the VQ search and the WaveNet decoder are the B200 kernels of this package.
+Inference: encoder, its final Linear and the VQ search are ONE kernel (wae_encoder_vq_forward, a cluster of 8 CTAs per
+utterance with the activations in shared memory); the decoder is the tcgen05 stack.  Under autograd the encoder is
+the torch modules (frame rate, < 2 % of the FLOPs).
 """
 import torch
 from torch import nn
@@ -68,6 +69,41 @@ class Encoder(nn.Module):
         run(cur, w, b, self.lin.in_features, T, self.lin.out_features, 1, 1, 0, 0, out)
         return out
 
+    def out_frames(self, F):
+        """Frames after the stride-2 blocks (SURVEY 9: F -> (F-1)//2+1 per block)."""
+        for m in self.net:
+            s = m.conv.stride[0]
+            F = (F - 1) // s + 1
+        return F
+
+    def fused_struct(self):
+        """The layer list as the plain-array struct wae_encoder_vq_forward takes, or None if that kernel does not support this
+        encoder (then every block is its own launch, ``_forward_kernels``).  Weights come from the ``_wt`` cache."""
+        from . import _lib
+        if len(self.net) > 16 or not all(m.conv.kernel_size[0] // 2 == m.conv.padding[0] and m.conv.dilation[0] == 1 and m.conv.groups == 1
+                                         for m in self.net):
+            return None
+        enc = _lib.Encoder()
+        keep = []
+        enc.n_layers = len(self.net)
+        for i, m in enumerate(self.net):
+            w = self._wt(m.conv.weight)
+            b = None if m.conv.bias is None else m.conv.bias.detach().float().contiguous()
+            keep += [w, b]
+            ly = enc.layer[i]
+            ly.w, ly.bias = w.data_ptr(), (None if b is None else b.data_ptr())
+            ly.cin, ly.cout, ly.k, ly.stride = m.dim_in, m.dim_out, m.conv.kernel_size[0], m.conv.stride[0]
+            ly.relu, ly.residual = 1, int(m.stride == 1 and m.dim_in == m.dim_out)
+        wl = self._wt(self.lin.weight)[:, 0, :]                      # (hid, 1, D) -> (hid, D)
+        bl = None if self.lin.bias is None else self.lin.bias.detach().float().contiguous()
+        keep += [wl, bl]
+        enc.lin_w_t, enc.lin_b = wl.data_ptr(), (None if bl is None else bl.data_ptr())
+        enc.hid, enc.D = self.lin.in_features, self.lin.out_features
+        if not _lib.lib().wae_encoder_vq_supported(enc):
+            return None
+        enc._keep = keep
+        return enc
+
     def _wt(self, weight):
         """(Cout, Cin[, k]) -> (Cin, k, Cout) fp32 for the kernel, cached until the parameter is modified in place or replaced."""
         from . import packing
@@ -108,26 +144,73 @@ class VQVAE(nn.Module):
         self.wavenet = wavenet
         self.encoder = Encoder(c_in=c_in, c_out=hid, hid=encoder_hid)
         self.vq = VectorQuantize(K=K, D=hid)
+        self.fuse_encoder = True       # inference: encoder + Linear + VQ search as one launch (wae_encoder_vq_forward)
+
+    def _encode_quantize(self, c):
+        """(quant, vq_loss, perplexity) of ``vq(encoder(c))`` (vqvae_model.py:66-69).  Inference on CUDA: ONE launch for the
+        encoder, its Linear and the nearest-codeword search; otherwise module by module."""
+        if (self.fuse_encoder and c.is_cuda and c.dim() == 3 and self.encoder._kernels_ok(c) and hasattr(self.vq, "_fusable")
+                and self.vq._fusable(c)):
+            enc = self.encoder.fused_struct()
+            if enc is not None:
+                with torch.no_grad():
+                    return self.vq._forward_fused(enc, c, self.encoder.out_frames(c.shape[-1]))
+        return self.vq(self.encoder(c))
 
     def forward(self, x, c, g, softmax=False):
-        quant, vq_loss, perp = self.vq(self.encoder(c))
+        quant, vq_loss, perp = self._encode_quantize(c)
         return self.wavenet(x, quant, g, softmax), vq_loss, perp
 
     def forward_nll(self, x, c, g, target, shift=1):
         """Additive: (teacher-forced NLL of the decoder, vq_loss, perplexity) -- the three quantities the reference's training
         step combines (vqwae_train.py:752-766) -- with loss and backward of the decoder fused (WaveNet.forward_nll)."""
-        quant, vq_loss, perp = self.vq(self.encoder(c))
+        quant, vq_loss, perp = self._encode_quantize(c)
         return self.wavenet.forward_nll(x, quant, g, target, shift), vq_loss, perp
 
     def incremental_forward(self, initial_input, c, g, T, softmax, quantize, tqdm, log_scale_min, **extra):
         """vqvae_model.py:74-80.  ``extra``: the additive keywords of ``WaveNet.incremental_forward`` (``uniforms``,
         ``generator``, ``return_indices``), passed through."""
         with torch.no_grad():
-            quant, _, _ = self.vq(self.encoder(c))
+            quant, _, _ = self._encode_quantize(c)
             return self.wavenet.incremental_forward(initial_input, c=quant, g=g, T=T, softmax=softmax,
                                                     quantize=quantize, tqdm=tqdm, log_scale_min=log_scale_min, **extra)
 
+    def encode_batch(self, feats):
+        """Additive (inference_2019.py:225-262 batched): ``feats`` is a list of (n_frames_i, n_feat) arrays /
+        tensors, one per utterance, of ANY lengths; returns the list of (T'_i, D) float32 numpy arrays ``encode`` would give
+        utterance by utterance (``rep_tensor.cpu().numpy()[0].transpose()``) -- from ONE launch of the fused encoder + VQ kernel
+        over the zero-padded batch with per-utterance lengths."""
+        import numpy as np
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            from . import _lib
+            raise _lib.WaeError("VQVAE.encode_batch: parameters are not on a CUDA device (no CPU fallback)")
+        lens = [int(f.shape[0]) for f in feats]
+        Fmax, nfeat = max(lens), int(feats[0].shape[1])
+        x = torch.zeros(len(feats), nfeat, Fmax, dtype=torch.float32)
+        for i, f in enumerate(feats):
+            x[i, :, :lens[i]] = torch.as_tensor(np.asarray(f), dtype=torch.float32).t()
+        x = x.to(dev)
+        with torch.no_grad():
+            enc = self.encoder.fused_struct() if (self.fuse_encoder and hasattr(self.vq, "_fusable") and self.vq._fusable(x)
+                                                  and self.encoder._kernels_ok(x)) else None
+            if enc is None:      # encoder the fused kernel does not cover: utterance by utterance, as the reference
+                return [self.encode(x[i:i + 1, :, :n])[0].t().contiguous().cpu().numpy() for i, n in enumerate(lens)]
+            quant, _, _ = self.vq._forward_fused(enc, x, self.encoder.out_frames(Fmax), lengths=torch.tensor(lens, dtype=torch.int32))
+            q = quant.permute(0, 2, 1).contiguous().cpu().numpy()
+        return [q[i, :self.encoder.out_frames(n)] for i, n in enumerate(lens)]
+
+    @staticmethod
+    def dump_representation(path, rep, decimals=6):
+        """``np.savetxt(path, rep, fmt='%.6f')`` (inference_2019.py:262), byte-identical, written by the library."""
+        import numpy as np
+        from . import _lib
+        a = np.ascontiguousarray(rep, dtype=np.float32)
+        if a.ndim != 2:
+            raise ValueError(f"dump_representation: expected a (frames, D) matrix, got shape {a.shape}")
+        _lib.check(_lib.lib().wae_dump_text(str(path).encode(), a.ctypes.data, a.shape[0], a.shape[1], int(decimals)), "wae_dump_text")
+
     def encode(self, x):
         with torch.no_grad():
-            quant, _, _ = self.vq(self.encoder(x))
+            quant, _, _ = self._encode_quantize(x)
         return quant
