@@ -1984,6 +1984,13 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
     const int ntiles = a.B * a.tiles_per_utt;
     const int nsuper = (ntiles + 1) / 2;
     const int ncluster = (int)gridDim.x / 2, cluster_id = (int)blockIdx.x / 2;
+    // odd layers walk the tiles backwards: a layer then starts on the tiles the previous layer wrote LAST, i.e. the part of x
+    // (131 MB at config 2, against 126 MB of L2) that is still L2-resident, instead of the part evicted longest ago
+#ifdef WAE_V4_NOREV
+    const bool rev = false;
+#else
+    const bool rev = (a.layer & 1) != 0;
+#endif
     const int rk = a.R / BK;
     const int nk_x = a.kw * rk;                  // tap k-blocks, oldest tap first
     const int nk_c = a.Cp / BK;
@@ -2005,7 +2012,14 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                 if (LPROF_ON) t_issue[ring.stage] = clock64();
                 uint8_t* sa = smem + ring.stage * STAGE_BYTES;
                 const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
+#ifdef WAE_V4_FAKESHARE   // timing experiment only (wrong numerics): what would sharing one staged x window between the taps be worth?
+                const bool skip_a = (kb < nk_x) && (kb / rk < a.kw - 1) && (a.dil <= WAE_V4_FAKESHARE);
+                if (leader) mbar_arrive_expect_tx(&full[ring.stage], skip_a ? 2 * w1_half : 2 * (A_TILE_BYTES + w1_half));
+                if (skip_a) {
+                } else
+#else
                 if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + w1_half));
+#endif
                 if (kb < nk_x) {
                     const int tap = kb / rk, r0 = (kb % rk) * BK;
                     tma_load_3d_2cta(&a.tm_x, fb, sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
@@ -2029,7 +2043,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                 }
             };
             int it = 0;
-            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+            for (int s0 = cluster_id; s0 < nsuper; s0 += ncluster, ++it) {
+                const int sup = rev ? nsuper - 1 - s0 : s0;
                 const int tile = sup * 2 + crank;
                 const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
                 for (int kb = 0; kb < ksplit; ++kb) load_g1(b, t0, kb);
@@ -2069,7 +2084,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                 umma_commit_2cta(&acc2_full[jt & 1], 3);
             };
             int it = 0;
-            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+            for (int s0 = cluster_id; s0 < nsuper; s0 += ncluster, ++it) {
+                const int sup = rev ? nsuper - 1 - s0 : s0;
                 const uint32_t buf = tmem_base + (uint32_t)((it & 1) * 256);
                 if (it >= 2) {               // the buffer's previous tenant (tile it-2) must be fully drained in both CTAs
                     LPROF(m_iss);
@@ -2114,7 +2130,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
         asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
         long long e_w1 = 0, e_e1 = 0, e_w2 = 0, e_e2 = 0, e_wx = 0; const long long e_t0 = clock64(); LPROF_BEGIN();
         int it = 0;
-        for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
+        for (int s0 = cluster_id; s0 < nsuper; s0 += ncluster, ++it) {
+            const int sup = rev ? nsuper - 1 - s0 : s0;
             const uint32_t buf = tmem_base + (uint32_t)((it & 1) * 256);
             const uint32_t par = (uint32_t)((it >> 1) & 1);
             const int tile = sup * 2 + crank;
