@@ -362,6 +362,11 @@ int wae_sumsq(const float* g, long long n, double* out, void* stream);
 int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                   float max_norm, const double* sumsq, const float* step_in, float* step_out, float* ema, float ema_decay,
                   void* stream);
+/* The same with the learning rate read from device memory at run time (*lr_dev): a scheduled rate (vqwae_train.py:730-735 writes
+ * param_group['lr'] every step) then works inside a replayed CUDA graph. */
+int wae_adam_step_dlr(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, float beta1, float beta2, float eps,
+                      float max_norm, const double* sumsq, const float* step_in, float* step_out, float* ema, float ema_decay,
+                      void* stream);
 /* ema (optional, NULL = none): the reference's shadow parameters, ema -= (1 - ema_decay) * (ema - p_new)  (vqwae_train.py:337-350,782-787) */
 
 /* Variant of the bf16 residual-layer kernel: -4 (default) = version-4 kernel (CTA pairs, tcgen05 cta_group::2: each CTA stages

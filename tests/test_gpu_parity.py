@@ -16,7 +16,9 @@ pytestmark = pytest.mark.gpu
 
 # stated tolerances (max|diff| / max|ref|)
 TOL_FP32 = 1e-3     # BASELINE north_star: "decoder logits within 1e-3 relative in fp32" (we see ~1e-5)
-TOL_BF16 = 6e-2     # bf16 operands + bf16 residual stream through 20 layers; fp32 accumulate (stated looser bound)
+TOL_BF16 = 3.5e-2   # bf16 operands + bf16 residual stream through 20 layers, fp32 accumulate: the "stated looser bound" = 2x the
+                    # largest error measured on any golden (1.6e-2, tools/measure_tolerances.py); per golden below
+TOL_BF16_CASE = {"wavenet_tiny": 1.3e-2, "wavenet_tiny_k2": 1.3e-2, "wavenet_vqwae": 2.6e-2, "wavenet_inwae": 3.3e-2}   # 2x measured
 
 
 def _inputs(case):
@@ -72,7 +74,7 @@ def test_forward_bf16_matches_reference_golden(case):
         y = m(x, c, spk)
     s = int(g["stride"])
     err = rel_err(y[:, :, ::s].cpu().numpy(), g["logits"])
-    assert err < TOL_BF16, err
+    assert err < TOL_BF16_CASE[case], err
 
 
 @pytest.mark.parametrize("case", ["wavenet_tiny", "wavenet_vqwae"])
@@ -434,6 +436,20 @@ def _flat_stats(ref, got):
     return float((fa * fb).sum() / (fa.norm() * fb.norm())), float((fb - fa).norm() / fa.norm())
 
 
+def _per_tensor_stats(ref, got):
+    """(lowest cosine, highest relative L2 error) over the tensors, each compared on its own: a wrong gradient of ONE small
+    tensor (a bias, a weight_g) cannot hide inside the norm of the whole gradient vector."""
+    cos, l2 = 1.0, 0.0
+    for a, b in zip(ref, got):
+        a, b = a.double().flatten(), b.double().flatten()
+        if float(a.norm()) == 0.0:
+            assert float(b.norm()) == 0.0
+            continue
+        cos = min(cos, float((a @ b) / (a.norm() * b.norm())))
+        l2 = max(l2, float((a - b).norm() / a.norm()))
+    return cos, l2
+
+
 @pytest.mark.parametrize("cfg_name", ["tiny", "tiny_k2", "vqwae"])
 def test_training_backward_matches_autograd(cfg_name):
     """Gradients of the teacher-forced NLL through training.StackTrainFunction (bf16 kernels forward, hand-derived backward).
@@ -468,6 +484,7 @@ def test_training_backward_matches_autograd(cfg_name):
     assert set(g0) == set(g1), set(g0) ^ set(g1)
     names = sorted(g0)
     cos_b, l2_b = _flat_stats([g0[n] for n in names] + [dc0], [g1[n] for n in names] + [dc1])
+    pcos_b, pl2_b = _per_tensor_stats([g0[n] for n in names] + [dc0], [g1[n] for n in names] + [dc1])
 
     # (a): same saved activations, bf16 kernels vs fp32 torch expressions
     with torch.no_grad():
@@ -488,10 +505,16 @@ def test_training_backward_matches_autograd(cfg_name):
         rb = training.stack_backward(ctx.sh, ctx.dil, xf, gf, f32(x_all), f32(h_all), f32(c_cl), wts, lg.grad, cdt=torch.float32)
     keep = [i for i, w in enumerate(wts) if w is not None and ra[3][i] is not None]
     cos_a, l2_a = _flat_stats([rb[3][i] for i in keep] + [rb[1], rb[2]], [ra[3][i] for i in keep] + [ra[1], ra[2]])
-    print(f"{cfg_name}: (a) bf16 vs fp32 backward on the same activations: cosine {cos_a:.5f} rel L2 {l2_a:.3e};  "
-          f"(b) vs fp32 autograd end to end: cosine {cos_b:.5f} rel L2 {l2_b:.3e}")
-    assert cos_a > 0.995 and l2_a < 0.10, (cos_a, l2_a)
-    assert cos_b > 0.98 and l2_b < 0.20, (cos_b, l2_b)
+    pcos_a, pl2_a = _per_tensor_stats([rb[3][i] for i in keep] + [rb[1], rb[2]], [ra[3][i] for i in keep] + [ra[1], ra[2]])
+    print(f"{cfg_name}: (a) bf16 vs fp32 backward on the same activations: cosine {cos_a:.5f} rel L2 {l2_a:.3e}, worst tensor "
+          f"{pcos_a:.5f} / {pl2_a:.3e};  (b) vs fp32 autograd end to end: cosine {cos_b:.5f} rel L2 {l2_b:.3e}, worst tensor "
+          f"{pcos_b:.5f} / {pl2_b:.3e}")
+    # bounds = 2x the measured deviations (tools/measure_tolerances.py; whole vector and worst single tensor)
+    bound = {"tiny": dict(a=(0.9990, 0.05), pa=(0.995, 0.10), b=(0.994, 0.11), pb=(0.988, 0.23)),
+             "tiny_k2": dict(a=(0.9990, 0.05), pa=(0.995, 0.10), b=(0.994, 0.11), pb=(0.988, 0.23)),
+             "vqwae": dict(a=(0.994, 0.16), pa=(0.97, 0.30), b=(0.978, 0.30), pb=(0.94, 0.50))}[cfg_name]
+    for (c_, l_), key in (((cos_a, l2_a), "a"), ((pcos_a, pl2_a), "pa"), ((cos_b, l2_b), "b"), ((pcos_b, pl2_b), "pb")):
+        assert c_ > bound[key][0] and l_ < bound[key][1], (key, c_, l_, bound[key])
 
 
 def test_training_kernels_match_torch():
@@ -652,6 +675,29 @@ def test_flat_adam_matches_torch_adam_with_clipping():
         for sh, (pb, eb) in zip(shadow, ob.ema_state().items()):
             assert torch.allclose(sh, eb, rtol=2e-5, atol=1e-7), step
     assert float(ob.step_a) == 5.0
+    # the torch.optim surface the reference's loop uses: a scheduled rate written into param_groups every step
+    # (vqwae_train.py:730-735), model.zero_grad() detaching .grad, state_dict round trip for checkpoints
+    sd = ob.state_dict()
+    mc = make()
+    with torch.no_grad():
+        for pc, pb in zip(mc.parameters(), mb.parameters()):
+            pc.copy_(pb)
+    oc = FlatAdam(mc, lr=1.0, betas=(0.9, 0.999), eps=1e-8, clip=0.05, ema_decay=0.9)
+    oc.load_state_dict(sd)
+    for step in range(5, 8):
+        lr = 4e-4 * 0.5 ** (step - 4)
+        for g_ in oa.param_groups + ob.param_groups + oc.param_groups:
+            g_["lr"] = lr
+        x = torch.randn(64, 37, device="cuda")
+        for m_ in (ma, mb, mc):
+            m_.zero_grad()                                           # set_to_none: FlatAdam must pick the fresh .grad tensors up
+            m_(x).square().mean().backward()
+        torch.nn.utils.clip_grad_norm_(ma.parameters(), 0.05)
+        oa.step(); ob.step(); oc.step()
+        for pa, pb, pc in zip(ma.parameters(), mb.parameters(), mc.parameters()):
+            assert torch.allclose(pa, pb, rtol=2e-5, atol=1e-7), step
+            assert torch.equal(pb, pc), step                         # resumed optimiser == the one that kept running
+            assert pb.grad.data_ptr() >= ob.flat_g.data_ptr()        # views restored
 
 
 def test_vq_codebook_view_at_unaligned_offset():

@@ -127,6 +127,8 @@ SIGNATURES = {
     "wae_sumsq": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "wae_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_float, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
+    "wae_adam_step_dlr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_float, C.c_float,
+                                    C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p]),
     "wae_set_layer_cluster": (C.c_int, [C.c_int]),
     "wae_layer_kernel_name": (C.c_char_p, []),
     "wae_set_head_pair": (C.c_int, [C.c_int]),

@@ -264,7 +264,8 @@ sumsq_kernel(const float* __restrict__ g, long long n, double* __restrict__ out)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
             float b1, float b2, float eps, float max_norm, const double* __restrict__ sumsq, const float* __restrict__ step_in,
-            float* __restrict__ step_out, float* __restrict__ ema, float ema_decay) {
+            float* __restrict__ step_out, float* __restrict__ ema, float ema_decay, const float* __restrict__ lr_dev) {
+    if (lr_dev != nullptr) lr = __ldg(lr_dev);                              // scheduled learning rate read at run time (CUDA-graph replay)
     const float step = __ldg(step_in) + 1.f;
     float coef = 1.f;
     if (max_norm > 0.f) {
@@ -300,18 +301,31 @@ extern "C" int wae_sumsq(const float* g, long long n, double* out, void* stream)
     return WAE_OK;
 }
 
-extern "C" int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                             float max_norm, const double* sumsq, const float* step_in, float* step_out, float* ema, float ema_decay,
-                             void* stream) {
+static int adam_step_impl(float* p, const float* g, float* m, float* v, long long n, float lr, const float* lr_dev, float beta1, float beta2,
+                          float eps, float max_norm, const double* sumsq, const float* step_in, float* step_out, float* ema,
+                          float ema_decay, void* stream) {
     if (int rc = wae::require_sm100()) return rc;
-    WAE_REQUIRE(p && g && m && v && step_in && step_out && n >= 0, "wae_adam_step: null pointer");
+    WAE_REQUIRE(p && g && m && v && step_in && step_out && n >= 0, "wae_adam_step: bad arguments");
     WAE_REQUIRE(max_norm <= 0.f || sumsq != nullptr, "wae_adam_step: clipping needs the squared gradient norm");
     WAE_REQUIRE(step_in != step_out, "wae_adam_step: step_in and step_out must be different buffers (ping-pong)");
     if (n == 0) return WAE_OK;
     adam_kernel<<<grid_for(n), 256, 0, static_cast<cudaStream_t>(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps, max_norm, sumsq, step_in,
-                                                                             step_out, ema, ema_decay);
+                                                                             step_out, ema, ema_decay, lr_dev);
     WAE_CHECK_LAUNCH();
     return WAE_OK;
+}
+
+extern "C" int wae_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                             float max_norm, const double* sumsq, const float* step_in, float* step_out, float* ema, float ema_decay,
+                             void* stream) {
+    return adam_step_impl(p, g, m, v, n, lr, nullptr, beta1, beta2, eps, max_norm, sumsq, step_in, step_out, ema, ema_decay, stream);
+}
+
+extern "C" int wae_adam_step_dlr(float* p, const float* g, float* m, float* v, long long n, const float* lr_dev, float beta1, float beta2,
+                                 float eps, float max_norm, const double* sumsq, const float* step_in, float* step_out, float* ema,
+                                 float ema_decay, void* stream) {
+    WAE_REQUIRE(lr_dev != nullptr, "wae_adam_step_dlr: null learning-rate pointer");
+    return adam_step_impl(p, g, m, v, n, 0.f, lr_dev, beta1, beta2, eps, max_norm, sumsq, step_in, step_out, ema, ema_decay, stream);
 }
 
 // ---------------------------------------------------------------------------------------------

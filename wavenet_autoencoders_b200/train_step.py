@@ -43,7 +43,12 @@ class FlatAdam:
             self.flat_p[off:off + k].copy_(p.data.reshape(-1))
             p.data = self.flat_p[off:off + k].view_as(p)
             p.grad = self.flat_g[off:off + k].view_as(p)
-        self.lr, self.betas, self.eps, self.clip = float(lr), (float(betas[0]), float(betas[1])), float(eps), float(clip or 0.0)
+        self.betas, self.eps, self.clip = (float(betas[0]), float(betas[1])), float(eps), float(clip or 0.0)
+        # torch.optim surface the reference's loop touches: it writes the scheduled rate into param_group['lr'] every step
+        # (vqwae_train.py:730-735) and saves / restores optimizer.state_dict() (save_checkpoint / load_checkpoint)
+        self.param_groups = [{"params": self.params, "lr": float(lr), "betas": self.betas, "eps": self.eps}]
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)     # what the kernel reads (graph replay safe)
+        self._lr_on_dev = float(lr)
         self.step_a = torch.zeros(1, dtype=torch.float32, device=dev)       # step count lives on the device (CUDA-graph safe)
         self.step_b = torch.zeros(1, dtype=torch.float32, device=dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
@@ -55,8 +60,53 @@ class FlatAdam:
         """{parameter: shadow tensor} views into the flat shadow buffer (what clone_as_averaged_model copies, :353-360)."""
         return {p: self.ema[off:off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)}
 
+    @property
+    def lr(self):
+        return self.param_groups[0]["lr"]
+
+    @lr.setter
+    def lr(self, value):
+        self.param_groups[0]["lr"] = float(value)
+
+    def sync_lr(self):
+        """Copy param_groups[0]['lr'] to the device scalar the update kernel reads (a no-op while it is unchanged).  ``step()``
+        calls it; with ``GraphedTrainStep`` it runs before every replay, so a scheduled learning rate takes effect."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_on_dev:
+            self.lr_dev.fill_(lr)
+            self._lr_on_dev = lr
+
     def zero_grad(self, set_to_none=False):
+        """Zeroes the flat gradient buffer; ``.grad`` stays a view into it whatever ``set_to_none`` says."""
         self.flat_g.zero_()
+
+    def _reattach_grads(self):
+        """``model.zero_grad()`` (set_to_none) or a fresh ``.grad`` tensor detaches a parameter from ``flat_g``; the update reads
+        ``flat_g``, so bring stray gradients back (copy) and restore the views."""
+        for p, off in zip(self.params, self.offsets):
+            view = self.flat_g[off:off + p.numel()]
+            if p.grad is None:
+                view.zero_()
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad.reshape(-1))
+            else:
+                continue
+            p.grad = view.view_as(p)
+
+    def state_dict(self):
+        """Adam moments, step count, EMA shadow and learning rate (what a checkpoint needs to resume: vqwae_train.py save_checkpoint)."""
+        return {"m": self.m.clone(), "v": self.v.clone(), "step": self.step_a.clone(), "ema": None if self.ema is None else self.ema.clone(),
+                "lr": float(self.param_groups[0]["lr"]), "betas": self.betas, "eps": self.eps, "clip": self.clip,
+                "ema_decay": self.ema_decay, "numel": int(self.flat_p.numel())}
+
+    def load_state_dict(self, sd):
+        if int(sd["numel"]) != int(self.flat_p.numel()):
+            raise ValueError(f"FlatAdam.load_state_dict: {sd['numel']} elements in the checkpoint, {self.flat_p.numel()} here")
+        self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.step_a.copy_(sd["step"]); self.step_b.copy_(sd["step"])
+        if self.ema is not None and sd.get("ema") is not None:
+            self.ema.copy_(sd["ema"])
+        self.param_groups[0]["lr"] = float(sd["lr"])
+        self.sync_lr()
 
     def enable_overlap(self, model=None, bounds=None, group=None):
         """Bucketed all-reduce overlapped with the backward (parallel.BucketedAllReduce).  Default buckets: [the WaveNet
@@ -86,13 +136,16 @@ class FlatAdam:
         L, ptr = self._lib.lib(), self._lib.ptr
         st = self._lib.stream_ptr(self.flat_p.device)
         n = self.flat_p.numel()
+        if not torch.cuda.is_current_stream_capturing():
+            self._reattach_grads()
+            self.sync_lr()
         if self.clip > 0:
             self.sumsq.zero_()
             self._lib.check(L.wae_sumsq(ptr(self.flat_g), n, ptr(self.sumsq), st), "wae_sumsq")
-        self._lib.check(L.wae_adam_step(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), n, self.lr, self.betas[0],
-                                        self.betas[1], self.eps, self.clip, ptr(self.sumsq), ptr(self.step_a), ptr(self.step_b),
-                                        ptr(self.ema), self.ema_decay or 0.0, st),
-                        "wae_adam_step")
+        self._lib.check(L.wae_adam_step_dlr(ptr(self.flat_p), ptr(self.flat_g), ptr(self.m), ptr(self.v), n, ptr(self.lr_dev), self.betas[0],
+                                            self.betas[1], self.eps, self.clip, ptr(self.sumsq), ptr(self.step_a), ptr(self.step_b),
+                                            ptr(self.ema), self.ema_decay or 0.0, st),
+                        "wae_adam_step_dlr")
         self.step_a.copy_(self.step_b)
         packing.bump_generation()        # parameters changed through raw pointers: packed-weight caches must re-pack
 
@@ -134,6 +187,7 @@ class GraphedTrainStep:
 
     def __init__(self, model, opt, idx, mfcc, g, clip=100.0, world=1, warmup=3):
         self.idx, self.mfcc, self.g = idx.clone(), mfcc.clone(), g.clone()
+        self.opt = opt
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -150,6 +204,8 @@ class GraphedTrainStep:
         self.idx.copy_(idx, non_blocking=True)
         self.mfcc.copy_(mfcc, non_blocking=True)
         self.g.copy_(g, non_blocking=True)
+        if hasattr(self.opt, "sync_lr"):
+            self.opt.sync_lr()           # a scheduled learning rate (opt.param_groups[0]['lr']) reaches the captured update kernel
         self.graph.replay()
         packing.bump_generation()        # the replayed optimiser kernels rewrote every parameter in place
         return self.loss
