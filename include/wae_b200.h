@@ -260,12 +260,17 @@ typedef struct wae_cond_frontend {
     int n_stages;              /* 1..8 */
     int scale[8];
     const float* filter[8];
+    /* optional (all three or none): the speaker embedding lookup of wavenet.py:186-191 done by the library -- speaker_ids (B)
+     * int64, speaker_table (n_speakers, Gi) fp32 = embed_speakers.weight; then pass gemb = NULL */
+    const int64_t* speaker_ids;
+    const float* speaker_table;
+    int n_speakers;
 } wae_cond_frontend;
 /*
  * Teacher-forced forward straight from the LATENT frames lat (B, C, F) fp32 (the VQ output, F * prod(scale) == T): ONE kernel
  * evaluates conv_in and the whole upsampler pyramid per 128-sample block in shared memory and writes the stack's channels-last
  * bf16 conditioning; nothing at an intermediate rate is materialised and no library GEMM runs.  Bit-identical to running
- * wae_upsample_stage per stage.  Input: x (B, Oin, T) fp32 or, if x_idx != NULL, the (B, T) int64 classes.  Outputs: logits
+ * wae_upsample_stage per stage.  With class indices the same kernel also gathers the first-conv rows of its samples.  Input: x (B, Oin, T) fp32 or, if x_idx != NULL, the (B, T) int64 classes.  Outputs: logits
  * (B, O, T) fp32 (may be NULL when the NLL is requested) and/or, with target != NULL, the teacher-forced NLL sum as in
  * wae_stack_nll_bf16_idx (target and nll_sum both NULL: forward only).
  */

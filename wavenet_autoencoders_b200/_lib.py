@@ -51,7 +51,8 @@ class StackBwd(C.Structure):
 
 
 class CondFrontend(C.Structure):
-    _fields_ = [("conv_in_w_t", C.c_void_p), ("n_stages", C.c_int32), ("scale", C.c_int32 * 8), ("filter", C.c_void_p * 8)]
+    _fields_ = [("conv_in_w_t", C.c_void_p), ("n_stages", C.c_int32), ("scale", C.c_int32 * 8), ("filter", C.c_void_p * 8),
+                ("speaker_ids", C.c_void_p), ("speaker_table", C.c_void_p), ("n_speakers", C.c_int32)]
 
 
 class EncLayer(C.Structure):

@@ -222,8 +222,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) gemm_bf16_tn_kernel(const __gr
 // channels (Hh = H rounded up to 16: the epilogues read 16-channel chunks)
 __global__ void __launch_bounds__(256)
 gbias_bf16_kernel(const float* __restrict__ b1, const float* __restrict__ wg, const float* __restrict__ gemb, int L,
-                  int B, int G, int Gi, int Hh, float* __restrict__ gb) {
+                  int B, int G, int Gi, int Hh, float* __restrict__ gb, const long long* __restrict__ spk_ids = nullptr,
+                  const float* __restrict__ spk_table = nullptr, int n_spk = 0) {
     const int l = blockIdx.x / B, b = blockIdx.x % B, H = G / 2;
+    if (spk_ids != nullptr) {       // the speaker embedding row (wavenet.py:186-191) is looked up here: gemb = table[ids[b]]
+        long long id = __ldg(&spk_ids[b]);
+        id = id < 0 ? 0 : (id >= n_spk ? n_spk - 1 : id);
+        gemb = spk_table + (size_t)id * Gi - (size_t)b * Gi;
+    }
     for (int o = threadIdx.x; o < 2 * Hh; o += blockDim.x) {
         const int half = o >= Hh, ch = o - half * Hh;
         float v = 0.f;
@@ -430,6 +436,12 @@ struct CondFrontArgs {
     int scale[CF_MAX_STAGES];
     int ns, C, Cp, F, T, nt;     // nt: tiles per block (<= CF_NT, host-chosen so that a block needs <= CF_F0 latent frames)
     __nv_bfloat16* out;          // [B][T][Cp]
+    // optional: the first conv on class indices for the same samples (x0[b][t][:] = wf[idx[b][t]][:] + bf), one launch less
+    const long long* x_idx;      // (B, T) or null
+    const float* wf;             // [Oin][R]
+    const float* bf;             // [R]
+    int Oin, R;
+    __nv_bfloat16* x0;           // [B][T][R]
 };
 
 __global__ void __launch_bounds__(256)
@@ -594,6 +606,26 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
                 o4.x = pack_bf16x2(v[0], v[1]); o4.y = pack_bf16x2(v[2], v[3]);
                 o4.z = pack_bf16x2(v[4], v[5]); o4.w = pack_bf16x2(v[6], v[7]);
                 *reinterpret_cast<uint4*>(a.out + ((size_t)b * a.T + t0 + tt) * a.Cp + cc8) = o4;
+            }
+            if (a.x_idx != nullptr) {
+                // first conv of the tile's samples: a row gather from the [Oin][R] table (out-of-range classes: bias alone)
+                const int r8n = a.R >> 3;
+                const long long row0 = (long long)b * a.T + t0;
+                for (int e = tid; e < nt * r8n; e += 256) {
+                    const int tt = e / r8n, r = (e - tt * r8n) * 8;
+                    const long long h = __ldg(&a.x_idx[row0 + tt]);
+                    float4 a0 = __ldg(reinterpret_cast<const float4*>(a.bf + r)), a1 = __ldg(reinterpret_cast<const float4*>(a.bf + r + 4));
+                    if (h >= 0 && h < a.Oin) {
+                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.wf + (size_t)h * a.R + r));
+                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.wf + (size_t)h * a.R + r + 4));
+                        a0.x += w0.x; a0.y += w0.y; a0.z += w0.z; a0.w += w0.w;
+                        a1.x += w1.x; a1.y += w1.y; a1.z += w1.z; a1.w += w1.w;
+                    }
+                    uint4 o4;
+                    o4.x = pack_bf16x2(a0.x, a0.y); o4.y = pack_bf16x2(a0.z, a0.w);
+                    o4.z = pack_bf16x2(a1.x, a1.y); o4.w = pack_bf16x2(a1.z, a1.w);
+                    *reinterpret_cast<uint4*>(a.x0 + (size_t)(row0 + tt) * a.R + r) = o4;
+                }
             }
             __syncthreads();      // ptab / buffers are reused by the next tile
         }
@@ -2966,9 +2998,15 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     // ---- prep: g bias, first conv, conditioning layout ----
     {
     ProfScope prof(0, stream);
-    gbias_bf16_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, gemb, d.layers, B, d.G, d.Gi, Hh, ws.gb);
+    const bool spk_lookup = fe != nullptr && fe->speaker_ids != nullptr && fe->speaker_table != nullptr && d.Gi > 0;
+    if (spk_lookup) WAE_REQUIRE(fe->n_speakers >= 1 && gemb == nullptr, "wae_stack_forward_bf16_lat: speaker ids OR embedded vectors, not both");
+    gbias_bf16_kernel<<<d.layers * B, 256, 0, stream>>>(w->b1, w->wg, spk_lookup ? fe->speaker_table : gemb, d.layers, B, d.G, d.Gi, Hh, ws.gb,
+                                                        spk_lookup ? reinterpret_cast<const long long*>(fe->speaker_ids) : nullptr,
+                                                        spk_lookup ? fe->speaker_table : nullptr, spk_lookup ? fe->n_speakers : 0);
     WAE_CHECK_LAUNCH();
-    if (x_idx != nullptr) {
+    const bool fc_fused = (x_idx != nullptr) && (fe != nullptr) && d.C > 0;    // the front-end kernel gathers the first-conv rows too
+    if (fc_fused) {
+    } else if (x_idx != nullptr) {
         const long long rows = (long long)B * T;
         long long blocks = (rows * (d.R / 8) + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
@@ -2997,6 +3035,8 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         }
         WAE_REQUIRE(total == T, "wae_stack_forward_bf16_lat: %d frames x scales = %lld != T = %d", fe_frames, total, T);
         ca.lat = c; ca.win_t = fe->conv_in_w_t; ca.ns = fe->n_stages; ca.C = d.C; ca.Cp = Cp; ca.F = fe_frames; ca.T = T; ca.out = ws.ccl;
+        ca.x_idx = fc_fused ? reinterpret_cast<const long long*>(x_idx) : nullptr;
+        ca.wf = w->wf; ca.bf = w->bf; ca.Oin = d.Oin; ca.R = d.R; ca.x0 = ws.xa;
         int nt = CF_NT;
         for (;; --nt) {   // latent frames one block of nt tiles can touch (+ 2: blocks that do not start at a frame boundary)
             long long lo = 0, hi = (long long)nt * CF_T - 1;

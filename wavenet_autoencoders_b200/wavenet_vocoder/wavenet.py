@@ -132,6 +132,19 @@ class WaveNet(nn.Module):
             g = g[:, :, 0]
         return g
 
+    def _fe_with_speakers(self, fe, g, B):
+        """(front-end struct for this call, gvec): integer speaker ids with ``embed_speakers`` are looked up by the kernel that
+        builds the per-utterance gate bias (no index_select / transpose launches); anything else goes through
+        ``_speaker_vectors``."""
+        if g is not None and self.embed_speakers is not None and not torch.is_floating_point(g) and g.is_cuda and g.numel() == B:
+            st = type(fe.struct).from_buffer_copy(fe.struct)
+            ids = g.detach().reshape(B).long().contiguous()
+            tab = self.embed_speakers.weight.detach().float().contiguous()
+            st.speaker_ids, st.speaker_table, st.n_speakers = ids.data_ptr(), tab.data_ptr(), tab.shape[0]
+            st._keep = (ids, tab, fe)
+            return st, None
+        return fe.struct, self._speaker_vectors(g, B)
+
     def _pack(self, kind, **kw):
         key = (kind,) + tuple(sorted(kw.items()))
         fp = packing.params_fingerprint(self)
@@ -165,7 +178,6 @@ class WaveNet(nn.Module):
             else:
                 x_idx = x = x.long().contiguous()     # the kernels read int64 classes
         B, T = x.size(0), x.size(-1)
-        gvec = self._speaker_vectors(g, B)
         last_stage = None
         if (c is not None and self.upsample_net is not None and not autograd and self.precision == "bf16" and x.is_cuda
                 and self.fuse_frontend and c.is_cuda and c.dim() == 3):
@@ -176,8 +188,10 @@ class WaveNet(nn.Module):
                     print(f"c {c.size() } x {x.size()}")
                     raise Exception
                 with torch.no_grad():
-                    out = self.stack_forward(x, c, gvec, frontend=fe, x_is_index=x_idx is not None)
+                    fe_struct, gvec = self._fe_with_speakers(fe, g, B)
+                    out = self.stack_forward(x, c, gvec, frontend=fe_struct, x_is_index=x_idx is not None)
                 return F.softmax(out, dim=1) if softmax else out
+        gvec = self._speaker_vectors(g, B)
         if c is not None and self.upsample_net is not None:
             if not autograd and self.precision == "bf16" and x.is_cuda and isinstance(self.upsample_net, (upsample.UpsampleNetwork, upsample.ConvInUpsampleNetwork)):
                 # inference: the last upsampler stage is fused into the stack's conditioning pass
@@ -248,11 +262,12 @@ class WaveNet(nn.Module):
         """Inference, bf16, class-index input: the NLL comes out of the head kernel's accumulator (wae_stack_nll_bf16_idx);
         the (B,O,T) logits are written only if ``logits_out`` is given."""
         B, T = x_idx.shape
-        gvec = self._speaker_vectors(g, B)
         up_w, up_s = None, 0
         fe = self._pack("fe") if (c is not None and self.upsample_net is not None and self.fuse_frontend and c.dim() == 3) else None
+        gvec = None if fe is not None else self._speaker_vectors(g, B)
         with torch.no_grad():
             if fe is not None:
+                fe_struct, gvec = self._fe_with_speakers(fe, g, B)
                 if c.size(-1) * fe.total_scale != T:
                     print(f"c {c.size() } x {x_idx.size()}")
                     raise Exception
@@ -264,7 +279,7 @@ class WaveNet(nn.Module):
                 pk = self._pack("bf16")
                 ws = self._ws.get(L.wae_stack_workspace_bf16(pk.struct.d, B, T), xi.device)
                 out = torch.zeros(1, dtype=torch.float64, device=xi.device)
-                _lib.check(L.wae_stack_forward_bf16_lat(pk.struct, None, _lib.ptr(xi), _lib.ptr(lat), lat.shape[-1], fe.struct, _lib.ptr(gv), B, T,
+                _lib.check(L.wae_stack_forward_bf16_lat(pk.struct, None, _lib.ptr(xi), _lib.ptr(lat), lat.shape[-1], fe_struct, _lib.ptr(gv), B, T,
                                                         _lib.ptr(logits_out), _lib.ptr(tg), int(shift), _lib.ptr(out), _lib.ptr(ws),
                                                         ws.numel(), st), "wae_stack_forward_bf16_lat")
                 return (out[0] / float(B * (T - shift))).float()
@@ -320,9 +335,9 @@ class WaveNet(nn.Module):
             n = L.wae_stack_workspace_bf16(pk.struct.d, B, T)
             ws = self._ws.get(n, x.device)
             if frontend is not None:
-                # c_up holds the LATENT frames (B, C, F); ``frontend``: packing.FrontendPack
+                # c_up holds the LATENT frames (B, C, F); ``frontend``: the _lib.CondFrontend struct of this call
                 _lib.check(L.wae_stack_forward_bf16_lat(pk.struct, None if x_is_index else _lib.ptr(x), _lib.ptr(x) if x_is_index else None,
-                                                        _lib.ptr(c_up), c_up.shape[-1], frontend.struct, _lib.ptr(gvec), B, T,
+                                                        _lib.ptr(c_up), c_up.shape[-1], frontend, _lib.ptr(gvec), B, T,
                                                         _lib.ptr(logits), None, 0, None, _lib.ptr(ws), ws.numel(), st),
                            "wae_stack_forward_bf16_lat")
             elif x_is_index:
