@@ -451,6 +451,7 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
     // | position table [CF_PITCH] (frame offset | phase << 16) of the stage being evaluated
     __shared__ int s_coef_off[CF_MAX_STAGES], s_len[CF_MAX_STAGES + 1];
     __shared__ int s_lo[CF_MAX_STAGES + 1], s_hi[CF_MAX_STAGES + 1];
+    __shared__ int s_cls[CF_T];
     int ctot = 0;
     for (int i = 0; i < a.ns; ++i) ctot += 3 * a.scale[i];
     float* coef = cf_sm;
@@ -532,6 +533,11 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
     const int c8n = a.Cp >> 3;
     for (int tile = tile0; tile < tile1; ++tile) {
         const int t0 = tile * CF_T;
+        if (a.x_idx != nullptr && tid < CF_T) {          // classes of the tile's samples (consumed after the pyramid: latency hidden)
+            const int t = t0 + tid;
+            long long h = (t < a.T) ? __ldg(&a.x_idx[(long long)b * a.T + t]) : -1;
+            s_cls[tid] = (h < 0 || h > 0x7fffffff) ? -1 : (int)h;
+        }
         if (tid == 0) {
             s_lo[a.ns] = t0; s_hi[a.ns] = min(t0 + CF_T, a.T) - 1;
             for (int i = a.ns - 1; i >= 0; --i) {
@@ -608,23 +614,38 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
                 *reinterpret_cast<uint4*>(a.out + ((size_t)b * a.T + t0 + tt) * a.Cp + cc8) = o4;
             }
             if (a.x_idx != nullptr) {
-                // first conv of the tile's samples: a row gather from the [Oin][R] table (out-of-range classes: bias alone)
+                // first conv of the tile's samples: a row gather from the [Oin][R] table (out-of-range classes: bias alone).
+                // The classes were staged in shared memory at the start of the tile; four rows are in flight per thread.
                 const int r8n = a.R >> 3;
                 const long long row0 = (long long)b * a.T + t0;
-                for (int e = tid; e < nt * r8n; e += 256) {
-                    const int tt = e / r8n, r = (e - tt * r8n) * 8;
-                    const long long h = __ldg(&a.x_idx[row0 + tt]);
-                    float4 a0 = __ldg(reinterpret_cast<const float4*>(a.bf + r)), a1 = __ldg(reinterpret_cast<const float4*>(a.bf + r + 4));
-                    if (h >= 0 && h < a.Oin) {
-                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(a.wf + (size_t)h * a.R + r));
-                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(a.wf + (size_t)h * a.R + r + 4));
-                        a0.x += w0.x; a0.y += w0.y; a0.z += w0.z; a0.w += w0.w;
-                        a1.x += w1.x; a1.y += w1.y; a1.z += w1.z; a1.w += w1.w;
+                const int n_it = nt * r8n;
+                for (int e0 = tid; e0 < n_it; e0 += 256 * 4) {
+                    float4 w0[4], w1[4];
+                    int tts[4], rs[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int e = e0 + u * 256;
+                        const int tt = e / r8n, r = (e - tt * r8n) * 8;
+                        tts[u] = tt; rs[u] = r;
+                        w0[u] = make_float4(0.f, 0.f, 0.f, 0.f); w1[u] = w0[u];
+                        if (e < n_it) {
+                            const int h = s_cls[tt];
+                            if (h >= 0 && h < a.Oin) {
+                                w0[u] = __ldg(reinterpret_cast<const float4*>(a.wf + (size_t)h * a.R + r));
+                                w1[u] = __ldg(reinterpret_cast<const float4*>(a.wf + (size_t)h * a.R + r + 4));
+                            }
+                        }
                     }
-                    uint4 o4;
-                    o4.x = pack_bf16x2(a0.x, a0.y); o4.y = pack_bf16x2(a0.z, a0.w);
-                    o4.z = pack_bf16x2(a1.x, a1.y); o4.w = pack_bf16x2(a1.z, a1.w);
-                    *reinterpret_cast<uint4*>(a.x0 + (size_t)(row0 + tt) * a.R + r) = o4;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (e0 + u * 256 < n_it) {
+                            const float4 a0 = __ldg(reinterpret_cast<const float4*>(a.bf + rs[u])), a1 = __ldg(reinterpret_cast<const float4*>(a.bf + rs[u] + 4));
+                            uint4 o4;
+                            o4.x = pack_bf16x2(a0.x + w0[u].x, a0.y + w0[u].y); o4.y = pack_bf16x2(a0.z + w0[u].z, a0.w + w0[u].w);
+                            o4.z = pack_bf16x2(a1.x + w1[u].x, a1.y + w1[u].y); o4.w = pack_bf16x2(a1.z + w1[u].z, a1.w + w1[u].w);
+                            *reinterpret_cast<uint4*>(a.x0 + (size_t)(row0 + tts[u]) * a.R + rs[u]) = o4;
+                        }
+                    }
                 }
             }
             __syncthreads();      // ptab / buffers are reused by the next tile
