@@ -7,15 +7,19 @@ One "step" = one pass of the hot path over one batch of the workload BASELINE.js
 (configs[1]): VQ-WAE (hps/vqwae.json) encoder -> VQ -> WaveNet decoder teacher-forced forward, 16 utterances x 1 s
 of synthetic 16 kHz audio per GPU, with synthetic MFCC conditioning and random-init weights.
 
-  value     device-timed samples/s, inputs resident in HBM, tcgen05 bf16 kernels (weak scaling: 16 utt per GPU)
-  e2e       the same through the public module API from pinned HOST buffers: H2D of the mu-law class indices, MFCCs
-            and speaker ids, on-device one-hot, forward, teacher-forced NLL, D2H of the loss -- all inside the timing
-  roofline  the residual-layer kernel (layer_bf16_v2_kernel): algorithmic FLOPs / CUDA-event time vs the measured bf16 peak
-  cpu_baseline   oracle/torch_port.py (the reference's ATen calls, folded weights) on the host cores, bounded sample
-  extras    fp32-faithful stack, autoregressive synthesis (config 4 shape, truncated T), VQ search throughput
+  value     device-timed samples/s of the reference-shaped call (one-hot input resident in HBM, eager launches, logits
+            written), tcgen05 bf16 kernels (weak scaling: 16 utt per GPU)
+  e2e       the same metric through the public module API from pinned HOST buffers: H2D of the mu-law class indices, MFCCs
+            and speaker ids, VQVAE.forward_nll (fused encoder+VQ kernel, front-end kernel, 20 layer kernels, head kernel
+            with the NLL from its accumulator), D2H of the loss -- all inside the timing, replayed as one CUDA graph
+  roofline  the residual-layer kernel (layer_bf16_v4_kernel): algorithmic FLOPs / CUDA-event time vs the measured BURST bf16 peak
+  cpu_baseline   the UNMODIFIED reference modules (baseline/_ref, staged by __graft_entry__.build()) on the host cores, bounded
+            sample (one utterance per step); the torch port of the same ATen calls if baseline/_ref is absent
+  extras    fp32-faithful stack, autoregressive synthesis (config 4 per-GPU shard: 32 x 48000), IN-WAE forward, VQ search
+            throughput, the data-parallel training step, the reference on the same GPU (eager cuDNN / cuBLAS)
 
---impl reference times the CPU port alone (the reference is pure Python/PyTorch and /root/reference does not exist
-on the GPU box; see DESIGN.md "Measurement").
+--impl reference times the reference's CPU path alone (its modules are pure Python/PyTorch; /root/reference does not exist
+on the GPU box, baseline/_ref travels with the snapshot; see DESIGN.md "Measurement").
 """
 from __future__ import annotations
 

@@ -31,8 +31,9 @@ using namespace wae::ptx;
 namespace {
 
 constexpr int EV_GROUP = 8;
-constexpr int EV_THREADS = 512;                   // two halves of 256: same output tiles, each half takes 8 of a chunk's 16 input channels
-constexpr int EV_HALF = 256;
+constexpr int EV_THREADS = 512;
+constexpr int EV_TP = 8;                           // positions per thread (register tile: 4 channels x 8 positions)
+constexpr int EV_RED_FLOATS = 16384;               // K-split partial sums: KS x (channels per CTA) x (positions per item) <= 512 x 32
 constexpr int EV_PADL = 4;                         // zero margin left of local position 0
 constexpr int EV_NPOS = 128;                       // positions per item at the input rate
 constexpr int EV_PITCH = EV_PADL + EV_NPOS + 4;    // floats per channel row (4 zeros right of the last position)
@@ -95,16 +96,6 @@ __device__ __forceinline__ void ev_group_barrier(unsigned* cnt, unsigned target)
     __syncthreads();
 }
 
-// Chunk geometry per kernel variant.  Layers at the latent rate (P == 1 with 32 output channels per CTA: <= 32 output positions,
-// <= 64 input positions) are overhead-bound -- a 32-channel chunk of a k = 1 layer is 250 FMAs per thread behind a barrier, a
-// cp.async wait and the issue loops -- so they stage short rows and take up to 96 input channels per chunk.
-template <int P, int KW, int CS>
-struct EvCfg {
-    static constexpr bool SMALL = (CS == 32 && P == 1);
-    static constexpr int XP = SMALL ? (KW == 5 ? 72 : 40) : EV_PITCH;                      // floats per staged activation row
-    static constexpr int CIC = SMALL ? (KW == 1 ? 96 : 32) : EV_CI;                            // input channels per chunk
-    static_assert(CIC * KW * EV_MAXCS <= EV_W_FLOATS && CIC * XP <= EV_CI * EV_PITCH && CIC % 32 == 0, "chunk does not fit its stage");
-};
 constexpr int EV_XJ = 3;     // activation float4s a thread copies per chunk (<= 34 * 32 / 512 rounded up)
 
 // weight chunk (nci input channels from ci0) of this CTA's output-channel slice -> stage
@@ -119,53 +110,62 @@ __device__ __forceinline__ void ev_issue_w(const EvLayer& ly, int ci0, int nci, 
         cp_async16(dst + (uint32_t)(row * cs + q * 4) * 4u, src + (size_t)row * ly.cout + q * 4);
     }
 }
-// the first chunks of a layer, issued ahead of the barrier that publishes its input; the layer's variant is not known to the
-// caller's template, so the chunk size is looked up here (same rule as EvCfg)
-__device__ __forceinline__ int ev_chunk_ci(const EvLayer& ly, int n_out) {
-    const int cs = ly.cout / EV_GROUP;
-    const bool small = (cs == 32) && (n_out <= EV_HALF / (cs >> 2));
-    return small ? (ly.k == 1 ? 96 : 32) : EV_CI;
-}
-__device__ __forceinline__ void ev_preissue_w(const EvLayer& ly, int n_out, int rank, float* stages) {
-    const int cic = ev_chunk_ci(ly, n_out);
+// the first chunks of a layer, issued ahead of the barrier that publishes its input
+// k = 1 layers at the latent rate (<= 32 positions) are overhead-bound per chunk (64 FMAs per thread behind a barrier, a cp.async
+// wait and the issue loops): they stage 40-float rows and take 96 input channels per chunk.  A function of the layer only.
+constexpr int EV_CI_SMALL = 96, EV_XP_SMALL = 40;
+__device__ __forceinline__ bool ev_small(const EvLayer& ly, int rate_out) { return ly.k == 1 && rate_out >= 4; }
+__device__ __forceinline__ void ev_preissue_w(const EvLayer& ly, int rate_out, int rank, float* stages) {
+    const int cic = ev_small(ly, rate_out) ? EV_CI_SMALL : EV_CI;
 #pragma unroll
     for (int i = 0; i < EV_NPRE; ++i)
-        if (ly.cin > i * cic) ev_issue_w<0>(ly, i * cic, min(cic, ly.cin - i * cic), rank, stages + (size_t)i * EV_STAGE_FLOATS);
+        if (ly.cin > i * cic) {
+            if (ly.cout == 32 * EV_GROUP) ev_issue_w<32>(ly, i * cic, min(cic, ly.cin - i * cic), rank, stages + (size_t)i * EV_STAGE_FLOATS);
+            else ev_issue_w<0>(ly, i * cic, min(cic, ly.cin - i * cic), rank, stages + (size_t)i * EV_STAGE_FLOATS);
+        }
 }
 
-// one chunk: acc[c][p] += W[ci][j][co + c] * X[ci][stride * (p0 + p) + j - pad] for this reduction half's input channels of the
-// chunk: half h owns the channels whose 16-block index (ci / 16) has parity h -- a rule that does not depend on the chunk size,
-// so every output is the same sequence of roundings whatever variant (P, chunk size) a batch shape selects.
-// CS > 0: output channels per CTA known at compile time (every weight load is base + immediate); CS == 0: runtime `cs`.
-template <int P, int KW, int STRIDE, int CS>
-__device__ __forceinline__ void ev_compute_chunk(const float* __restrict__ stage, int half, int nci, int cs_rt, int cg, int p0, float (&acc)[4][P]) {
-    constexpr int WIN = (P - 1) * STRIDE + KW;
-    constexpr int XP = EvCfg<P, KW, CS>::XP, CIC = EvCfg<P, KW, CS>::CIC;
+// Register tile 4 output channels x 8 positions: per input channel a thread reads 8 + KW - 1 (stride 1) or 19 (k = 5, stride 2)
+// activations and KW x 4 weights for KW x 32 FMAs -- 0.23 floats delivered to registers per FMA, under the 0.25 the shared-memory
+// pipe (128 B/cycle/SM) can feed the FMA pipe (128/cycle/SM).  (The first version's 4 x 4 / 4 x 1 tiles needed 0.38 / 1.25 and
+// ran at half / an eighth of the FMA rate: profiles/r2_enc_vq_group_ncu.txt, tools/enc_profile.py.)
+// acc[c][p] += W[ci][j][co + c] * X[ci][stride * (p0 + p) + j - pad] for the chunk's input channels cl0 .. cl1.
+template <int KW, int STRIDE, int CS, int XP>
+__device__ __forceinline__ void ev_compute_chunk(const float* __restrict__ stage, int cl0, int cl1, int cs_rt, int cg, int p0, float (&acc)[4][EV_TP]) {
+    constexpr int WIN = (EV_TP - 1) * STRIDE + KW;
     const int cs = CS > 0 ? CS : cs_rt;
-    const float* xr = stage + EV_W_FLOATS + EV_PADL + p0 * STRIDE - KW / 2;
-    const float* wr = stage + 4 * cg;
-    auto step = [&](int cl) {
+    const float* xx = stage + EV_W_FLOATS + cl0 * XP + EV_PADL + p0 * STRIDE - KW / 2;
+    const float* wr = stage + cl0 * KW * cs + 4 * cg;
+#pragma unroll 2
+    for (int cl = cl0; cl < cl1; ++cl) {
         float win[WIN];
-        const float* xx = xr + cl * XP;
-        if (P == 4 && STRIDE == 1 && (KW == 3 || KW == 1)) {
-            // positions p0 - 1 .. p0 + 4: one aligned 16-byte load for p0 .. p0 + 3 and the two neighbours
-            const float4 m = *reinterpret_cast<const float4*>(xx + KW / 2);
-            if (KW == 3) { win[0] = xx[0]; win[WIN - 1] = xx[WIN - 1]; }
-            win[KW / 2] = m.x; win[(KW / 2 + 1) % WIN] = m.y; win[(KW / 2 + 2) % WIN] = m.z; win[(KW / 2 + 3) % WIN] = m.w;
-        } else if (P == 2 && STRIDE == 2 && KW == 5) {
-            // positions 2 p0 - 2 .. 2 p0 + 4 (p0 even): 8-byte, 16-byte and 4-byte loads
+        if (STRIDE == 1) {
+            // positions p0 - KW/2 .. p0 + 7 + KW/2 (p0 a multiple of 8): two aligned 16-byte loads + the neighbours
+            const float4 m0 = *reinterpret_cast<const float4*>(xx + KW / 2);
+            const float4 m1 = *reinterpret_cast<const float4*>(xx + KW / 2 + 4);
+#pragma unroll
+            for (int i = 0; i < KW / 2; ++i) { win[i] = xx[i]; win[WIN - 1 - i] = xx[WIN - 1 - i]; }
+            win[KW / 2] = m0.x; win[KW / 2 + 1] = m0.y; win[KW / 2 + 2] = m0.z; win[KW / 2 + 3] = m0.w;
+            win[KW / 2 + 4] = m1.x; win[KW / 2 + 5] = m1.y; win[KW / 2 + 6] = m1.z; win[KW / 2 + 7] = m1.w;
+        } else if (STRIDE == 2 && KW == 5) {
+            // positions 2 p0 - 2 .. 2 p0 + 16 (2 p0 a multiple of 16): 8-byte + four 16-byte + one 4-byte load
             const float2 lo = *reinterpret_cast<const float2*>(xx);
-            const float4 m = *reinterpret_cast<const float4*>(xx + 2);
-            win[0] = lo.x; win[1 % WIN] = lo.y; win[2 % WIN] = m.x; win[3 % WIN] = m.y; win[4 % WIN] = m.z; win[5 % WIN] = m.w; win[6 % WIN] = xx[6];
+            win[0] = lo.x; win[1] = lo.y;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 m = *reinterpret_cast<const float4*>(xx + 2 + 4 * q);
+                win[(2 + 4 * q) % WIN] = m.x; win[(3 + 4 * q) % WIN] = m.y; win[(4 + 4 * q) % WIN] = m.z; win[(5 + 4 * q) % WIN] = m.w;
+            }
+            win[18 % WIN] = xx[18];
         } else {
 #pragma unroll
             for (int i = 0; i < WIN; ++i) win[i] = xx[i];
         }
 #pragma unroll
         for (int j = 0; j < KW; ++j) {
-            const float4 w = *reinterpret_cast<const float4*>(wr + (cl * KW + j) * cs);
+            const float4 w = *reinterpret_cast<const float4*>(wr + j * cs);
 #pragma unroll
-            for (int p = 0; p < P; ++p) {
+            for (int p = 0; p < EV_TP; ++p) {
                 const float xv = win[p * STRIDE + j];
                 acc[0][p] = fmaf(w.x, xv, acc[0][p]);
                 acc[1][p] = fmaf(w.y, xv, acc[1][p]);
@@ -173,31 +173,30 @@ __device__ __forceinline__ void ev_compute_chunk(const float* __restrict__ stage
                 acc[3][p] = fmaf(w.w, xv, acc[3][p]);
             }
         }
-    };
-    if (CS > 0 && nci == CIC) {
-        xr += half * 16 * XP;            // rebased: the unrolled steps address with immediates
-        wr += half * 16 * KW * cs;
-#pragma unroll
-        for (int b2 = 0; b2 < CIC / 32; ++b2) {
-#pragma unroll 8
-            for (int cl = 0; cl < 16; ++cl) step(b2 * 32 + cl);
-        }
-    } else {
-#pragma unroll 1
-        for (int cl = half * 16; cl < nci; cl += ((cl & 15) == 15) ? 17 : 1) step(cl);
+        xx += XP;
+        wr += KW * cs;
     }
 }
 
-template <int P, int KW, int STRIDE, int CS>
+// One layer.  `npos` = positions of the item at the layer's OUTPUT rate (128 / 64 / 32 for cumulative stride 1 / 2 / 4): it fixes
+// the thread layout -- (cs / 4) channel groups x (npos / 8) position groups = one K-group, KS = 512 / that (a power of two <= 16)
+// K-groups, K-group k takes input channels [k, k + 1) * 32 / KS of every 32-channel chunk -- as a function of the LAYER only, so
+// an output is the same sequence of roundings whatever the batch shape (ragged batches and tiled utterances stay bit-identical).
+template <int KW, int STRIDE, int CS, bool SMALL>
 __device__ __forceinline__ void ev_layer(const EvArgs& a, int l, const float* act_in, float* act_out, float* stages, float* red, int rank,
-                                         int n_in, int n_out, int g_out, int len_out, unsigned* bar, unsigned& bar_target) {
+                                         int npos, int rate_out, int n_in, int n_out, int g_out, int len_out, unsigned* bar, unsigned& bar_target) {
+    constexpr int CIC = SMALL ? EV_CI_SMALL : EV_CI, XP = SMALL ? EV_XP_SMALL : EV_PITCH;
+    static_assert(CIC * KW * EV_MAXCS <= EV_W_FLOATS && CIC * XP <= EV_CI * EV_PITCH, "chunk does not fit its stage");
     const EvLayer& ly = a.layer[l];
     const int cs = CS > 0 ? CS : ly.cout / EV_GROUP, ncg = cs >> 2;
-    const int half = threadIdx.x / EV_HALF, lt = threadIdx.x - half * EV_HALF;    // reduction half, thread within the half
+    const int tg = ncg * (npos / EV_TP);                     // threads of one K-group
+    int ks = 1;
+    while (ks < 16 && 2 * ks * tg <= EV_THREADS) ks *= 2;
+    const int kgroup = threadIdx.x / tg, lt = threadIdx.x - kgroup * tg;
     const int cg = lt % ncg, pg = lt / ncg;
-    const int p0 = pg * P;
-    const bool active = p0 < n_out;
-    constexpr int XP = EvCfg<P, KW, CS>::XP, CIC = EvCfg<P, KW, CS>::CIC;
+    const int p0 = pg * EV_TP;
+    const bool active = kgroup < ks && p0 < n_out;
+    const int cpk = CIC / ks;                                 // input channels of a chunk per K-group
     const int nq = (EV_PADL + n_in + 4 + 3) / 4;             // float4s per activation row that the taps can touch
     const int nch = (ly.cin + CIC - 1) / CIC;
     // this thread's share of a chunk's activation copy, worked out once per layer: float4 j is (row, q) -> offsets in floats
@@ -222,11 +221,11 @@ __device__ __forceinline__ void ev_layer(const EvArgs& a, int l, const float* ac
         if (i < nch) issue_x(i * CIC, stages + (size_t)i * EV_STAGE_FLOATS);
         cp_async_commit();
     }
-    float acc[4][P];
+    float acc[4][EV_TP];
 #pragma unroll
     for (int c = 0; c < 4; ++c)
 #pragma unroll
-        for (int p = 0; p < P; ++p) acc[c][p] = 0.f;
+        for (int p = 0; p < EV_TP; ++p) acc[c][p] = 0.f;
     if (l == 7 || l == 1) EVPROF(l == 7 ? 42 : 52);
     for (int c = 0; c < nch; ++c) {
         cp_async_wait<EV_STAGES - 2>();
@@ -240,52 +239,74 @@ __device__ __forceinline__ void ev_layer(const EvArgs& a, int l, const float* ac
         }
         cp_async_commit();
         if (active) {
-            ev_compute_chunk<P, KW, STRIDE, CS>(stages + (size_t)(c % EV_STAGES) * EV_STAGE_FLOATS, half, min(CIC, ly.cin - c * CIC), cs, cg, p0, acc);
+            const int nci = min(CIC, ly.cin - c * CIC);
+            ev_compute_chunk<KW, STRIDE, CS, XP>(stages + (size_t)(c % EV_STAGES) * EV_STAGE_FLOATS, min(nci, kgroup * cpk),
+                                             min(nci, (kgroup + 1) * cpk), cs, cg, p0, acc);
         }
     }
     if (l == 7 || l == 1) EVPROF(l == 7 ? 46 : 56);
-    // the upper half hands its partial sums over (fixed order: lower + upper)
-    if (half == 1 && active) {
+    // K-group partial sums -> shared memory [kgroup][position group][position][channel]: a warp's 16-byte stores cover whole
+    // 128-byte rows (conflict-free); the reducer below reads them channel-fastest, likewise
+    const int npg = npos / EV_TP;
+    if (active) {
+        float* r = red + ((size_t)(kgroup * npg + pg) * EV_TP) * cs + 4 * cg;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int p = 0; p < P; ++p) red[(c * P + p) * EV_HALF + lt] = acc[c][p];
+        for (int p = 0; p < EV_TP; ++p)
+            *reinterpret_cast<float4*>(r + p * cs) = make_float4(acc[0][p], acc[1][p], acc[2][p], acc[3][p]);
     }
-    __syncthreads();                 // partial sums visible; every warp has finished reading the ring: the next layer's first weight chunks may land
-    if (half == 0 && active) {
+    // the epilogue's global operands (bias, residual input) of this thread's outputs: requested now, consumed three barriers later
+    const int npos_w = (n_out + EV_TP - 1) / EV_TP * EV_TP;          // positions the K-groups wrote
+    float e_bias[8], e_res[8];
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-#pragma unroll
-            for (int p = 0; p < P; ++p) acc[c][p] += red[(c * P + p) * EV_HALF + lt];
-    }
-    if (l + 1 < a.nl) ev_preissue_w(a.layer[l + 1], a.layer[l + 1].stride == 2 ? (n_out - 1) / 2 + 1 : n_out, rank, stages);
-    // epilogue in registers: bias, ReLU, residual (vqvae_model.py:17-21), zero outside the utterance; own channel slice -> act_out
-    if (l == 7 || l == 1) EVPROF(l == 7 ? 47 : 57);
-    const int co = rank * cs + 4 * cg;
-    if (active && half == 0) {
-        const float4 b4 = ly.bias ? __ldg(reinterpret_cast<const float4*>(ly.bias + co)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            float* orow = act_out + (size_t)(co + c) * EV_PITCH + EV_PADL + p0;
-            const float* rrow = act_in + (size_t)(co + c) * EV_PITCH + EV_PADL + p0;
-            float v[P];
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                float t = acc[c][p] + bb[c];
-                if (ly.relu) t = fmaxf(t, 0.f);
-                if (ly.res) t += __ldcg(rrow + p);
-                const int gp = g_out + p0 + p;
-                v[p] = (p0 + p < n_out && gp >= 0 && gp < len_out) ? t : 0.f;
-            }
-            if (P == 4) *reinterpret_cast<float4*>(orow) = make_float4(v[0], v[1 % P], v[2 % P], v[3 % P]);
-            else if (P == 2) *reinterpret_cast<float2*>(orow) = make_float2(v[0], v[1 % P]);
-            else orow[0] = v[0];
+    for (int j = 0; j < 8; ++j) {
+        const int o = threadIdx.x + j * EV_THREADS;
+        e_bias[j] = 0.f; e_res[j] = 0.f;
+        if (o < cs * npos_w) {
+            const int c = o / npos_w, q = o - c * npos_w, co = rank * cs + c;
+            if (ly.bias) e_bias[j] = __ldg(ly.bias + co);
+            if (ly.res) e_res[j] = __ldcg(act_in + (size_t)co * EV_PITCH + EV_PADL + q);
         }
     }
-    // positions [ceil(n_out / P) * P, + 4) right of the written ones must read as zeros for the next layer's taps
+    __syncthreads();                 // partial sums visible; every warp has finished reading the ring: the next layer's first weight chunks may land
+    if (l + 1 < a.nl) ev_preissue_w(a.layer[l + 1], rate_out * a.layer[l + 1].stride, rank, stages);
+    if (l == 7 || l == 1) EVPROF(l == 7 ? 47 : 57);
+    // reduction over the K-groups in the fixed order 0, 1, ...: thread -> (channel = tid % cs, positions tid / cs + j * (512 / cs))
+    const int ch = threadIdx.x % cs, pstep = EV_THREADS / cs;
+    float sum[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int pos = threadIdx.x / cs + j * pstep;
+        float t = 0.f;
+        if (pos < npos_w) {
+            const float* r = red + (size_t)pos * cs + ch;             // (pos / 8, pos % 8) flattened
+            for (int k = 0; k < ks; ++k) t += r[(size_t)k * npos * cs];
+        }
+        sum[j] = t;
+    }
+    __syncthreads();                 // everybody has read the partial sums: their region becomes the [channel][position] tile
+    constexpr int TPITCH = EV_NPOS + 1;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int pos = threadIdx.x / cs + j * pstep;
+        if (pos < npos_w) red[ch * TPITCH + pos] = sum[j];
+    }
+    __syncthreads();
+    // bias, ReLU, residual (vqvae_model.py:17-21), zero outside the utterance; own channel slice -> act_out, position-fastest
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int o = threadIdx.x + j * EV_THREADS;
+        if (o < cs * npos_w) {
+            const int c = o / npos_w, q = o - c * npos_w, co = rank * cs + c;
+            float t = red[c * TPITCH + q] + e_bias[j];
+            if (ly.relu) t = fmaxf(t, 0.f);
+            t += e_res[j];
+            const int gp = g_out + q;
+            act_out[(size_t)co * EV_PITCH + EV_PADL + q] = (q < n_out && gp >= 0 && gp < len_out) ? t : 0.f;
+        }
+    }
+    // positions [ceil(n_out / 8) * 8, + 4) right of the written ones must read as zeros for the next layer's taps
     {
-        const int z0 = (n_out + P - 1) / P * P;
+        const int z0 = (n_out + EV_TP - 1) / EV_TP * EV_TP;
         for (int e = threadIdx.x; e < cs * 4; e += EV_THREADS) {
             const int c = e >> 2, z = z0 + (e & 3);
             if (z < EV_NPOS + 4) act_out[(size_t)(rank * cs + c) * EV_PITCH + EV_PADL + z] = 0.f;
@@ -300,8 +321,9 @@ __global__ void __launch_bounds__(EV_THREADS, 1)
 enc_vq_group_kernel(const __grid_constant__ EvArgs a) {
     extern __shared__ __align__(16) float ev_sm[];
     float* stages = ev_sm;                                           // [EV_STAGES][EV_STAGE_FLOATS]
-    float* red = stages + (size_t)EV_STAGES * EV_STAGE_FLOATS;       // [16][EV_HALF] partial sums of the upper reduction half
-    float* sxh = red + 16 * EV_HALF;                                 // [EV_VPC][EV_MAXC] last hidden activations of this CTA's positions
+    float* red = stages + (size_t)EV_STAGES * EV_STAGE_FLOATS;       // [KS][channels per CTA][positions] K-split partial sums (64 KB)
+    float* sxh = red;                                                // the tail's arrays reuse that region: [EV_VPC][EV_MAXC] last hidden
+                                                                     // activations of this CTA's positions
     float* spart = sxh + EV_VPC * EV_MAXC;                           // [4 K-parts][EV_VPC][EV_MAXC] Linear partial sums
     float* slat = spart + 4 * EV_VPC * EV_MAXC;                      // [EV_VPC][EV_MAXC] latent vectors
     float* sx2 = slat + EV_VPC * EV_MAXC;                            // [EV_VPC]
@@ -337,7 +359,7 @@ enc_vq_group_kernel(const __grid_constant__ EvArgs a) {
         }
         if (q_count <= 0) continue;                          // the whole group skips the item: barrier counts stay in step
         // weights of the first layer do not depend on anything: in flight during the set-up
-        ev_preissue_w(a.layer[0], a.layer[0].stride == 2 ? (n - 1) / 2 + 1 : n, rank, stages);
+        ev_preissue_w(a.layer[0], a.layer[0].stride, rank, stages);
         // this CTA's channel rows of both scratch buffers: zeros, then the input frames into buffer A
         {
             constexpr int ROWS = EV_MAXC / EV_GROUP;
@@ -359,19 +381,18 @@ enc_vq_group_kernel(const __grid_constant__ EvArgs a) {
 
         float* cur = actA;
         float* nxt = actB;
+        int rate = 1;
         for (int l = 0; l < a.nl; ++l) {
             const EvLayer& ly = a.layer[l];
             int n_out = n, g_out = g, len_out = len;
             if (ly.stride == 2) { n_out = (n - 1) / 2 + 1; g_out = g / 2; len_out = (len - 1) / 2 + 1; }
-            // positions per thread: the smallest of 1, 2, 4 that covers n_out positions with the block's threads
-            const int ncg = ly.cout / EV_GROUP / 4;
-            const int pgs = EV_HALF / ncg;
-            const int P = (n_out <= pgs) ? 1 : (n_out <= 2 * pgs) ? 2 : 4;
-#define EV_CALL(PP, KK, SS) do { if (ly.cout == 256) ev_layer<PP, KK, SS, 32>(a, l, cur, nxt, stages, red, rank, n, n_out, g_out, len_out, bar, bar_target); \
-                                 else ev_layer<PP, KK, SS, 0>(a, l, cur, nxt, stages, red, rank, n, n_out, g_out, len_out, bar, bar_target); } while (0)
-            if (ly.k == 1)      { if (P == 1) EV_CALL(1, 1, 1); else if (P == 2) EV_CALL(2, 1, 1); else EV_CALL(4, 1, 1); }
-            else if (ly.k == 3) { if (P == 1) EV_CALL(1, 3, 1); else if (P == 2) EV_CALL(2, 3, 1); else EV_CALL(4, 3, 1); }
-            else                { if (P == 1) EV_CALL(1, 5, 2); else if (P == 2) EV_CALL(2, 5, 2); else EV_CALL(4, 5, 2); }
+            rate *= ly.stride;
+            const int npos = EV_NPOS / rate;                 // thread layout by the layer's rate class, not by the batch's length
+#define EV_CALL(KK, SS, SM) do { if (ly.cout == 256) ev_layer<KK, SS, 32, SM>(a, l, cur, nxt, stages, red, rank, npos, rate, n, n_out, g_out, len_out, bar, bar_target); \
+                                 else ev_layer<KK, SS, 0, SM>(a, l, cur, nxt, stages, red, rank, npos, rate, n, n_out, g_out, len_out, bar, bar_target); } while (0)
+            if (ly.k == 1) { if (ev_small(ly, rate)) EV_CALL(1, 1, true); else EV_CALL(1, 1, false); }
+            else if (ly.k == 3) EV_CALL(3, 1, false);
+            else EV_CALL(5, 2, false);
 #undef EV_CALL
             n = n_out; g = g_out; len = len_out;
             float* t = cur; cur = nxt; nxt = t;
@@ -384,10 +405,41 @@ enc_vq_group_kernel(const __grid_constant__ EvArgs a) {
         const int D = a.D;
         int nv = 0;
         for (int i = 0; i < EV_VPC; ++i) if (rank + EV_GROUP * i < q_count) nv = i + 1;
+        // the idle stage ring takes the Linear weight and the codebook(s) (rows padded by 4 floats: conflict-free 16-byte reads
+        // with one code per thread) while the hidden activations arrive: the tail then never waits on L2 inside its loops
+        const float* lin_w = a.lin_w_t;
+        const float* cbp[2] = {a.slice[0].cb, a.slice[a.nslices > 1 ? 1 : 0].cb};
+        int cb_pitch[2] = {a.slice[0].sub_d, a.slice[a.nslices > 1 ? 1 : 0].sub_d};
+        {
+            size_t need = (size_t)a.hid * D;
+            bool ok = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.lin_w_t) & 15) == 0);
+            for (int s2 = 0; s2 < a.nslices; ++s2) {
+                need += (size_t)a.slice[s2].K * (a.slice[s2].sub_d + 4);
+                ok = ok && (a.slice[s2].sub_d % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.slice[s2].cb) & 15) == 0);
+            }
+            if (ok && need <= (size_t)EV_STAGES * EV_STAGE_FLOATS) {
+                const uint32_t dstw = smem_u32(stages);
+                for (int e = tid; e < a.hid * D / 4; e += EV_THREADS) cp_async16(dstw + (uint32_t)e * 16u, a.lin_w_t + (size_t)e * 4);
+                lin_w = stages;
+                float* dst = stages + (size_t)a.hid * D;
+                for (int s2 = 0; s2 < a.nslices; ++s2) {
+                    const int sd = a.slice[s2].sub_d, sd4 = sd >> 2, pitch = sd + 4;
+                    const uint32_t dc = smem_u32(dst);
+                    for (int e = tid; e < a.slice[s2].K * sd4; e += EV_THREADS) {
+                        const int row = e / sd4, q = e - row * sd4;
+                        cp_async16(dc + (uint32_t)(row * pitch + q * 4) * 4u, a.slice[s2].cb + (size_t)row * sd + q * 4);
+                    }
+                    cbp[s2] = dst; cb_pitch[s2] = pitch;
+                    dst += (size_t)a.slice[s2].K * pitch;
+                }
+            }
+            cp_async_commit();
+        }
         for (int e = tid; e < EV_VPC * a.hid; e += EV_THREADS) {
             const int i = e / a.hid, c = e - i * a.hid;
             sxh[i * EV_MAXC + c] = (i < nv) ? __ldcg(cur + (size_t)c * EV_PITCH + EV_PADL + (q_first + rank + EV_GROUP * i - g)) : 0.f;
         }
+        cp_async_wait<0>();
         __syncthreads();
         {   // Linear: 4 K-parts x D outputs, every thread accumulates its K-part for all EV_VPC positions (weights read once)
             const int kq = (a.hid + 3) / 4;
@@ -399,7 +451,7 @@ enc_vq_group_kernel(const __grid_constant__ EvArgs a) {
                 const int c1 = min(a.hid, (part + 1) * kq);
 #pragma unroll 8
                 for (int c = part * kq; c < c1; ++c) {
-                    const float w = __ldg(&a.lin_w_t[(size_t)c * D + d]);
+                    const float w = lin_w[(size_t)c * D + d];
 #pragma unroll
                     for (int i = 0; i < EV_VPC; ++i) acc[i] = fmaf(w, sxh[i * EV_MAXC + c], acc[i]);
                 }
@@ -433,9 +485,9 @@ enc_vq_group_kernel(const __grid_constant__ EvArgs a) {
             int besti[EV_VPC];
 #pragma unroll
             for (int i = 0; i < EV_VPC; ++i) { best[i] = INFINITY; besti[i] = 0x7fffffff; }
-            const bool vec4 = (sl.sub_d & 3) == 0 && (reinterpret_cast<uintptr_t>(sl.cb) & 15) == 0;
+            const bool vec4 = (sl.sub_d & 3) == 0 && (cb_pitch[s] & 3) == 0 && (reinterpret_cast<uintptr_t>(cbp[s]) & 15) == 0;
             for (int k = tid; k < sl.K; k += EV_THREADS) {
-                const float* er = sl.cb + (size_t)k * sl.sub_d;
+                const float* er = cbp[s] + (size_t)k * cb_pitch[s];
                 float e2 = 0.f, dot[EV_VPC];
 #pragma unroll
                 for (int i = 0; i < EV_VPC; ++i) dot[i] = 0.f;
@@ -447,12 +499,12 @@ enc_vq_group_kernel(const __grid_constant__ EvArgs a) {
                 if (vec4) {
 #pragma unroll 4
                     for (int d = 0; d < sl.sub_d; d += 4) {
-                        const float4 e4 = __ldg(reinterpret_cast<const float4*>(er + d));
+                        const float4 e4 = *reinterpret_cast<const float4*>(er + d);
                         fold(e4.x, d); fold(e4.y, d + 1); fold(e4.z, d + 2); fold(e4.w, d + 3);
                     }
                 } else {
 #pragma unroll 4
-                    for (int d = 0; d < sl.sub_d; ++d) fold(__ldg(er + d), d);
+                    for (int d = 0; d < sl.sub_d; ++d) fold(er[d], d);
                 }
 #pragma unroll
                 for (int i = 0; i < EV_VPC; ++i) {
@@ -492,7 +544,7 @@ enc_vq_group_kernel(const __grid_constant__ EvArgs a) {
             for (int e = tid; e < nv * sl.sub_d; e += EV_THREADS) {
                 const int i = e / sl.sub_d, d = e - i * sl.sub_d;
                 const float xv = slat[i * EV_MAXC + sl.d0 + d];
-                const float qv = __ldg(&sl.cb[(size_t)sfin[i] * sl.sub_d + d]);
+                const float qv = cbp[s][(size_t)sfin[i] * cb_pitch[s] + d];
                 const float diff = __fsub_rn(qv, xv);
                 if (a.quant_out) a.quant_out[((size_t)b * D + sl.d0 + d) * a.F4 + q_first + rank + EV_GROUP * i] = __fadd_rn(xv, diff);
                 err += (double)diff * (double)diff;
@@ -594,8 +646,8 @@ extern "C" int wae_encoder_vq_forward(const wae_encoder* enc, const float* x, co
     const long long items = (long long)B * a.tiles_per_utt;
     WAE_REQUIRE(items < (1ll << 27), "wae_encoder_vq_forward: too many work items");
     a.nitems = (int)items;
-    const size_t smem = ((size_t)EV_STAGES * EV_STAGE_FLOATS + (size_t)16 * EV_HALF + (size_t)6 * EV_VPC * EV_MAXC + EV_VPC +
-                         (EV_THREADS / 32) * EV_VPC * 2 + EV_VPC + 8) * sizeof(float);
+    static_assert(EV_RED_FLOATS >= 6 * EV_VPC * EV_MAXC + EV_VPC + (EV_THREADS / 32) * EV_VPC * 2 + EV_VPC + 8, "tail arrays alias the partial sums");
+    const size_t smem = ((size_t)EV_STAGES * EV_STAGE_FLOATS + (size_t)EV_RED_FLOATS) * sizeof(float);
     WAE_CHECK_CUDA(cudaFuncSetAttribute(enc_vq_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // persistent grid of co-resident groups of 8 CTAs (a group spins on its barrier: all of its CTAs must be running)
     int per_sm = 0, dev = 0, sms = 0;
