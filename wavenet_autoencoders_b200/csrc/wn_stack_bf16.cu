@@ -2587,22 +2587,24 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
     uint64_t* bars = reinterpret_cast<uint64_t*>(act + nks * A_TILE_BYTES);
     uint64_t* full = bars;
     uint64_t* empty = bars + HEADP_STAGES;
-    uint64_t* accs_full = bars + 2 * HEADP_STAGES;
-    uint64_t* epis_done = accs_full + 1;
-    uint64_t* acc3_full = accs_full + 2;
-    uint64_t* epi3_done = accs_full + 3;
-    uint64_t* acc4_full = accs_full + 4;
-    uint64_t* epi4_done = accs_full + 5;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accs_full + 6);
+    uint64_t* accs_full = bars + 2 * HEADP_STAGES;      // [2] by tile parity, like every barrier below
+    uint64_t* epis_done = accs_full + 2;
+    uint64_t* acc3_full = accs_full + 4;
+    uint64_t* epi3_done = accs_full + 6;
+    uint64_t* acc4_full = accs_full + 8;
+    uint64_t* epi4_done = accs_full + 10;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accs_full + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int crank = (int)cluster_ctarank();
     const bool leader = (crank == 0);
     if (threadIdx.x == 0) {
         for (int s = 0; s < HEADP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(accs_full, 1); mbar_init(epis_done, 2);       // one elected epilogue thread per CTA
-        mbar_init(acc3_full, 1); mbar_init(epi3_done, 2);
-        mbar_init(acc4_full, 1); mbar_init(epi4_done, 2);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&accs_full[i], 1); mbar_init(&epis_done[i], 2);       // one elected epilogue thread per CTA
+            mbar_init(&acc3_full[i], 1); mbar_init(&epi3_done[i], 2);
+            mbar_init(&acc4_full[i], 1); mbar_init(&epi4_done[i], 2);
+        }
         fence_mbar_init();
         tma_prefetch_desc(&a.tm_h);
         tma_prefetch_desc(&a.tm_ws);
@@ -2615,8 +2617,10 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
     cluster_sync();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base;          // skip accumulator, columns [0, S)
-    const uint32_t tmem_34 = tmem_base + 256;   // GEMM3 then GEMM4 accumulator, columns [256, 512)
+    // TMEM ping-pong (as layer_bf16_v4_kernel): tile `it` owns the 256-column buffer it & 1 for its whole life -- skip GEMM, drained
+    // by EPI_S, GEMM3 into the same columns, drained by EPI3, GEMM4, drained by EPI4 -- and the NEXT tile's skip GEMM (40 of the 48
+    // k-blocks, the part that streams h_all from HBM) runs in the other buffer underneath.  Before, GEMM3 / GEMM4 and their
+    // epilogues sat between two skip GEMMs and the 4-deep TMA ring ran dry for ~25 % of every tile (profiles/r2_head_ncu.txt).
 
     const int ntiles = a.B * a.tiles_per_utt;
     const int nsuper = (ntiles + 1) / 2;
@@ -2627,38 +2631,41 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
     if (warp == 0) {
         if (elect_one()) {
             Ring ring(HEADP_STAGES);
-            for (int sup = cluster_id; sup < nsuper; sup += ncluster) {
+            const int nsk = a.L * nkh;                                    // skip-GEMM k-blocks per tile
+            const int ka = nsk / 5, kb2 = nsk / 2;                        // GEMM3 / GEMM4 of the previous tile are slotted in after these
+            auto load_skip = [&](int b, int t0, bool valid, int kbi) {
+                const int l = kbi / nkh, kb = kbi - l * nkh;
+                mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
+                if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + ws_half));
+                // past the last tile (odd tail) the plane coordinate leaves the tensor: TMA zero-fills the box
+                tma_load_3d_2cta(&a.tm_h, fb, sa, kb * BK, t0, valid ? l * a.B + b : a.L * a.B);
+                tma_load_3d_2cta(&a.tm_ws, fb, sa + A_TILE_BYTES, kb * BK, crank * ws_rows, l);
+                ring.advance();
+            };
+            auto load_w = [&](const CUtensorMap* tm, int rows, uint32_t half) {
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
+                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
+                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
+                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * half);
+                    tma_load_3d_2cta(tm, fb, sa + A_TILE_BYTES, kb * BK, crank * rows, 0);
+                    ring.advance();
+                }
+            };
+            int it = 0;
+            for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
                 const int tile = sup * 2 + crank;
                 const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
                 const bool valid = tile < ntiles;
-                for (int l = 0; l < a.L; ++l)
-                    for (int kb = 0; kb < nkh; ++kb) {
-                        mbar_wait(&empty[ring.stage], ring.phase ^ 1);
-                        uint8_t* sa = smem + ring.stage * STAGE_BYTES;
-                        const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
-                        if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + ws_half));
-                        // past the last tile (odd tail) the plane coordinate leaves the tensor: TMA zero-fills the box
-                        tma_load_3d_2cta(&a.tm_h, fb, sa, kb * BK, t0, valid ? l * a.B + b : a.L * a.B);
-                        tma_load_3d_2cta(&a.tm_ws, fb, sa + A_TILE_BYTES, kb * BK, crank * ws_rows, l);
-                        ring.advance();
-                    }
-                for (int kb = 0; kb < nks; ++kb) {
-                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
-                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
-                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
-                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * ws_half);
-                    tma_load_3d_2cta(&a.tm_w3, fb, sa + A_TILE_BYTES, kb * BK, crank * ws_rows, 0);
-                    ring.advance();
-                }
-                for (int kb = 0; kb < nks; ++kb) {
-                    mbar_wait(&empty[ring.stage], ring.phase ^ 1);
-                    uint8_t* sa = smem + ring.stage * STAGE_BYTES;
-                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
-                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * w4_half);
-                    tma_load_3d_2cta(&a.tm_w4, fb, sa + A_TILE_BYTES, kb * BK, crank * w4_rows, 0);
-                    ring.advance();
+                for (int kbi = 0; kbi < nsk; ++kbi) {
+                    if (it > 0 && kbi == ka) load_w(&a.tm_w3, ws_rows, ws_half);
+                    if (it > 0 && kbi == kb2) load_w(&a.tm_w4, w4_rows, w4_half);
+                    load_skip(b, t0, valid, kbi);
                 }
             }
+            if (it > 0) { load_w(&a.tm_w3, ws_rows, ws_half); load_w(&a.tm_w4, w4_rows, w4_half); }
         }
     } else if (warp == 1) {
         if (leader && elect_one()) {
@@ -2671,42 +2678,41 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
                 for (int k = 0; k < BK / 16; ++k)
                     umma_bf16_2cta(tmem_d, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (zero_init && k == 0) ? 0u : 1u);
             };
+            const int nsk = a.L * nkh, ka = nsk / 5, kb2 = nsk / 2;
+            auto gemm34 = [&](int jt, bool is4) {        // GEMM3 / GEMM4 of tile jt (per-cluster count) into ITS buffer, from `act`
+                const uint32_t buf = tmem_base + (uint32_t)((jt & 1) * 256);
+                mbar_wait(is4 ? &epi3_done[jt & 1] : &epis_done[jt & 1], (uint32_t)((jt >> 1) & 1));   // act written, buffer drained
+                tc_fence_after();
+                for (int kb = 0; kb < nks; ++kb) {
+                    mbar_wait(&full[ring.stage], ring.phase);
+                    tc_fence_after();
+                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
+                    issue2(buf, smem_u32(act + kb * A_TILE_BYTES), sb, is4 ? idesc_4 : idesc_s, kb == 0);
+                    umma_commit_2cta(&empty[ring.stage], 3);
+                    ring.advance();
+                }
+                umma_commit_2cta(is4 ? &acc4_full[jt & 1] : &acc3_full[jt & 1], 3);
+            };
             int it = 0;
             for (int sup = cluster_id; sup < nsuper; sup += ncluster, ++it) {
-                // skip accumulator region was drained by EPI_S of the previous tile (waited below, before GEMM3)
-                for (int kb = 0; kb < a.L * nkh; ++kb) {
+                const uint32_t buf = tmem_base + (uint32_t)((it & 1) * 256);
+                if (it >= 2) {               // the buffer's previous tenant (tile it-2) was drained by its EPI4
+                    mbar_wait(&epi4_done[it & 1], (uint32_t)(((it - 2) >> 1) & 1));
+                    tc_fence_after();
+                }
+                for (int kbi = 0; kbi < nsk; ++kbi) {
+                    if (it > 0 && kbi == ka) gemm34(it - 1, false);
+                    if (it > 0 && kbi == kb2) gemm34(it - 1, true);
                     mbar_wait(&full[ring.stage], ring.phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
-                    issue2(tmem_s, sa, sa + A_TILE_BYTES, idesc_s, kb == 0);
+                    issue2(buf, sa, sa + A_TILE_BYTES, idesc_s, kbi == 0);
                     umma_commit_2cta(&empty[ring.stage], 3);
                     ring.advance();
                 }
-                umma_commit_2cta(accs_full, 3);
-                mbar_wait(epis_done, it & 1);
-                tc_fence_after();
-                if (it > 0) { mbar_wait(epi4_done, (it - 1) & 1); tc_fence_after(); }
-                for (int kb = 0; kb < nks; ++kb) {
-                    mbar_wait(&full[ring.stage], ring.phase);
-                    tc_fence_after();
-                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
-                    issue2(tmem_34, smem_u32(act + kb * A_TILE_BYTES), sb, idesc_s, kb == 0);
-                    umma_commit_2cta(&empty[ring.stage], 3);
-                    ring.advance();
-                }
-                umma_commit_2cta(acc3_full, 3);
-                mbar_wait(epi3_done, it & 1);
-                tc_fence_after();
-                for (int kb = 0; kb < nks; ++kb) {
-                    mbar_wait(&full[ring.stage], ring.phase);
-                    tc_fence_after();
-                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
-                    issue2(tmem_34, smem_u32(act + kb * A_TILE_BYTES), sb, idesc_4, kb == 0);
-                    umma_commit_2cta(&empty[ring.stage], 3);
-                    ring.advance();
-                }
-                umma_commit_2cta(acc4_full, 3);
+                umma_commit_2cta(&accs_full[it & 1], 3);
             }
+            if (it > 0) { gemm34(it - 1, false); gemm34(it - 1, true); }
         }
     } else {
         const int q = warp & 3;
@@ -2724,6 +2730,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
             const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
             const int t = t0 + row;
             const bool live = valid && (t < a.T);
+            const uint32_t tbuf = tmem_base + (uint32_t)((it & 1) * 256);     // this tile's accumulator buffer
+            const uint32_t par = (uint32_t)((it >> 1) & 1), boff = (uint32_t)((it & 1) * 8);
 
             // relu(scale * (acc + bias)) / relu(acc + bias) -> bf16 -> `act` (A operand of the next GEMM)
             auto relu_to_act = [&](uint32_t tmem_acc, const float* bias, float scale, const CUtensorMap* tm_save) {
@@ -2757,17 +2765,17 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
                 }
             };
 
-            mbar_wait(accs_full, it & 1);
+            mbar_wait(&accs_full[it & 1], par);
             tc_fence_after();
-            relu_to_act(tmem_s, a.bs_sum, a.scale, &a.tm_r1);
-            if (threadIdx.x == 64) mbar_arrive_cluster(epis_remote);
+            relu_to_act(tbuf, a.bs_sum, a.scale, &a.tm_r1);
+            if (threadIdx.x == 64) mbar_arrive_cluster(epis_remote + boff);
 
-            mbar_wait(acc3_full, it & 1);
+            mbar_wait(&acc3_full[it & 1], par);
             tc_fence_after();
-            relu_to_act(tmem_34, a.b3, 1.0f, &a.tm_r2);
-            if (threadIdx.x == 64) mbar_arrive_cluster(epi3_remote);
+            relu_to_act(tbuf, a.b3, 1.0f, &a.tm_r2);
+            if (threadIdx.x == 64) mbar_arrive_cluster(epi3_remote + boff);
 
-            mbar_wait(acc4_full, it & 1);
+            mbar_wait(&acc4_full[it & 1], par);
             tc_fence_after();
             // loss straight from the accumulator: every thread holds 1/4 of the classes of its time step --
             // running max / sum of exponentials / the target's logit per thread, merged over the four column groups below
@@ -2776,7 +2784,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
             float r_max = -INFINITY, r_sum = 0.f, r_tgt = 0.f;
             for (int c0 = cg * 16; c0 < a.Op; c0 += LAYER_NCG * 16) {
                 float v[16];
-                tmem_ld16(tmem_34 + lane_base + c0, v);
+                tmem_ld16(tbuf + lane_base + c0, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] += __ldg(a.b4 + c0 + i);
@@ -2800,7 +2808,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
             }
             tc_fence_before();
             asm volatile("bar.sync 1, %0;" ::"n"(32 * LAYER_EPI_WARPS) : "memory");
-            if (threadIdx.x == 64) mbar_arrive_cluster(epi4_remote);
+            if (threadIdx.x == 64) mbar_arrive_cluster(epi4_remote + boff);
             if (want_nll) {
                 float* red = nll_red + (size_t)cg * 3 * BM;       // [column group][max | sum | target logit][row]
                 red[row] = r_max; red[BM + row] = r_sum; red[2 * BM + row] = r_tgt;
