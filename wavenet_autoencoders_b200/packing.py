@@ -150,19 +150,72 @@ def _ru(x, m):
     return (x + m - 1) // m * m
 
 
-def _gather_layer_mats(wn, sh: StackShape):
-    """Per-layer folded fp32 matrices in natural layout."""
+_lane_streams = {}
+
+
+class Lanes:
+    """Fork / join of per-layer weight preparation over a few side streams.  A training step prepares ~100 small tensors per
+    pass (weight-norm folds, packing permutations, gradient reshapes) -- chains of 2 us launches that a single stream (and the
+    CUDA graph captured from it) executes one after the other; spread over lanes they become parallel branches of the graph.
+    ``with lanes.lane(i): ...`` runs a block on side stream i (forked from the caller's stream on first use), ``join()`` makes the
+    caller's stream wait for all of them.  Autograd replays each op's backward on the stream of its forward, so the weight-norm
+    backward and the gradient accumulation of a layer land on its lane as well.  Same kernels, same results."""
+
+    def __init__(self, device, n=8):
+        device = torch.device(device)
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), n)
+        if key not in _lane_streams:
+            _lane_streams[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+        self.side = _lane_streams[key]
+        self.used = []
+
+    def lane(self, i):
+        st = self.side[i % len(self.side)]
+        if st not in self.used:
+            st.wait_stream(self.main)
+            self.used.append(st)
+        return torch.cuda.stream(st)
+
+    def join(self):
+        for st in self.used:
+            self.main.wait_stream(st)
+        self.used = []
+
+
+class _NoLanes:
+    def lane(self, i):
+        import contextlib
+        return contextlib.nullcontext()
+
+    def join(self):
+        pass
+
+
+def _gather_layer_mats(wn, sh: StackShape, folded=None, lanes=None):
+    """Per-layer folded fp32 matrices in natural layout.  ``folded``: the already folded weights of training.live_weights (8 per
+    layer: conv, bias, conv1x1c, conv1x1g, conv1x1_out, bias, conv1x1_skip, bias) -- weight norm is then not evaluated again."""
     out = []
     dev = next(wn.parameters()).device
-    for f in wn.conv_layers:
-        w = folded_weight(f.conv).float()                       # (G, R, kw)
-        wc = folded_weight(f.conv1x1c).float()[:, :, 0] if sh.C else None   # (G, C)
-        wg = folded_weight(f.conv1x1g).float()[:, :, 0] if sh.Gi else None  # (G, Gi)
-        wo = folded_weight(f.conv1x1_out).float()[:, :, 0]      # (R, H)
-        ws = folded_weight(f.conv1x1_skip).float()[:, :, 0]     # (S, H)
-        out.append(dict(w=w, wc=wc, wg=wg, wo=wo, ws=ws,
-                        b=_bias(f.conv, sh.G, dev), bo=_bias(f.conv1x1_out, sh.R, dev),
-                        bs=_bias(f.conv1x1_skip, sh.S, dev)))
+    lanes = lanes or _NoLanes()
+    for l, f in enumerate(wn.conv_layers):
+        with lanes.lane(l):
+            if folded is not None:
+                fw = folded[8 * l: 8 * l + 8]
+                w, wc, wg, wo, ws = fw[0], fw[2], fw[3], fw[4], fw[6]
+                w = w.detach().float()
+                wc = wc.detach().float()[:, :, 0] if sh.C else None
+                wg = wg.detach().float()[:, :, 0] if sh.Gi else None
+                wo, ws = wo.detach().float()[:, :, 0], ws.detach().float()[:, :, 0]
+            else:
+                w = folded_weight(f.conv).float()                       # (G, R, kw)
+                wc = folded_weight(f.conv1x1c).float()[:, :, 0] if sh.C else None   # (G, C)
+                wg = folded_weight(f.conv1x1g).float()[:, :, 0] if sh.Gi else None  # (G, Gi)
+                wo = folded_weight(f.conv1x1_out).float()[:, :, 0]      # (R, H)
+                ws = folded_weight(f.conv1x1_skip).float()[:, :, 0]     # (S, H)
+            out.append(dict(w=w, wc=wc, wg=wg, wo=wo, ws=ws,
+                            b=_bias(f.conv, sh.G, dev), bo=_bias(f.conv1x1_out, sh.R, dev),
+                            bs=_bias(f.conv1x1_skip, sh.S, dev)))
     return out
 
 
@@ -236,22 +289,34 @@ def pack_f32(wn) -> Packed:
     return p
 
 
-def pack_bf16(wn) -> Packed:
+def pack_bf16(wn, folded=None, lanes=None) -> Packed:
+    """``folded`` / ``lanes`` (training): reuse training.live_weights' folded weights and spread the per-layer permutations
+    over side streams (Lanes); the caller joins the lanes before launching kernels that read the result."""
     sh = stack_shape(wn)
     H = sh.H
-    mats = _gather_layer_mats(wn, sh)
+    mats = _gather_layer_mats(wn, sh, folded, lanes)
     dev = mats[0]["w"].device
     Hp, Cp, Op = _ru(H, 64), _ru(sh.C, 64) if sh.C else 0, _ru(sh.O, 16)
     bf = torch.bfloat16
     p = Packed()
     p.shape = sh
     t = p.t
-    t["w1"] = torch.stack([_gate_rows_bf16(_w1_kmajor(m, sh, Cp), H) for m in mats]).to(bf).contiguous()         # [L][2*Hh][K1p]
-    t["wo"] = torch.stack([torch.nn.functional.pad(m["wo"], (0, Hp - H)) for m in mats]).to(bf).contiguous()     # [L][R][Hp]
-    t["ws"] = torch.stack([torch.nn.functional.pad(m["ws"], (0, Hp - H)) for m in mats]).to(bf).contiguous()     # [L][S][Hp]
+    ln = lanes or _NoLanes()
+    w1_rows, wo_rows, ws_rows = [], [], []
+    for l, m in enumerate(mats):
+        with ln.lane(l):
+            w1_rows.append(_gate_rows_bf16(_w1_kmajor(m, sh, Cp), H))
+            wo_rows.append(torch.nn.functional.pad(m["wo"], (0, Hp - H)))
+            ws_rows.append(torch.nn.functional.pad(m["ws"], (0, Hp - H)))
+    ln.join()
+    t["w1"] = torch.stack(w1_rows).to(bf).contiguous()         # [L][2*Hh][K1p]
+    t["wo"] = torch.stack(wo_rows).to(bf).contiguous()         # [L][R][Hp]
+    t["ws"] = torch.stack(ws_rows).to(bf).contiguous()         # [L][S][Hp]
     l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
-    t["w3"] = folded_weight(l1).float()[:, :, 0].to(bf).contiguous()                                              # [S][S]
-    w4 = folded_weight(l3).float()[:, :, 0]                                                                       # [O][S]
+    base = 8 * len(mats)
+    fold = (lambda m, i: folded[base + i].detach()) if folded is not None else (lambda m, i: folded_weight(m))
+    t["w3"] = fold(l1, 2).float()[:, :, 0].to(bf).contiguous()                                                    # [S][S]
+    w4 = fold(l3, 4).float()[:, :, 0]                                                                             # [O][S]
     t["w4"] = torch.nn.functional.pad(w4, (0, 0, 0, Op - sh.O)).to(bf).contiguous()                               # [Op][S]
     t["b1"] = torch.stack([m["b"] for m in mats]).contiguous()
     t["wg"] = torch.stack([m["wg"].t().contiguous() for m in mats]) if sh.Gi else None                            # [L][Gi][G]
@@ -259,7 +324,7 @@ def pack_bf16(wn) -> Packed:
     t["bs_sum"] = torch.stack([m["bs"] for m in mats]).sum(0).contiguous()
     t["b3"] = _bias(l1, sh.S, dev).contiguous()
     t["b4"] = torch.nn.functional.pad(_bias(l3, sh.O, dev), (0, Op - sh.O)).contiguous()
-    t["wf"] = folded_weight(wn.first_conv).float()[:, :, 0].t().contiguous()
+    t["wf"] = fold(wn.first_conv, 0).float()[:, :, 0].t().contiguous()
     t["bf"] = _bias(wn.first_conv, sh.R, dev).contiguous()
     s = _lib.StackBF16()
     s.d = sh.dims()

@@ -24,6 +24,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import torch
 from torch.nn import functional as F
 
@@ -39,17 +41,26 @@ def _fw(m):
     return m.weight
 
 
-def live_weights(wn):
-    """Flat list of the stack's folded weights and biases, fixed order (None where a conv has no bias / is absent)."""
+def live_weights(wn, lanes=None):
+    """Flat list of the stack's folded weights and biases, fixed order (None where a conv has no bias / is absent).
+    ``lanes`` (packing.Lanes): the folds of layer l run on side stream l -- and so will their backward."""
     out = []
-    for f in wn.conv_layers:
-        out += [_fw(f.conv), f.conv.bias,
-                _fw(f.conv1x1c) if f.conv1x1c is not None else None,
-                _fw(f.conv1x1g) if f.conv1x1g is not None else None,
-                _fw(f.conv1x1_out), f.conv1x1_out.bias, _fw(f.conv1x1_skip), f.conv1x1_skip.bias]
+    ln = lanes or packing._NoLanes()
+    for l, f in enumerate(wn.conv_layers):
+        with ln.lane(l):
+            out += [_fw(f.conv), f.conv.bias,
+                    _fw(f.conv1x1c) if f.conv1x1c is not None else None,
+                    _fw(f.conv1x1g) if f.conv1x1g is not None else None,
+                    _fw(f.conv1x1_out), f.conv1x1_out.bias, _fw(f.conv1x1_skip), f.conv1x1_skip.bias]
     l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
     out += [_fw(wn.first_conv), wn.first_conv.bias, _fw(l1), l1.bias, _fw(l3), l3.bias]
     return out
+
+
+def _lanes_for(wn, x):
+    """Side-stream lanes for the weight preparation of a CUDA training step (``wn.prep_lanes``, default 8; 0 disables)."""
+    n = int(getattr(wn, "prep_lanes", os.environ.get("WAE_PREP_LANES", "8")))
+    return packing.Lanes(x.device, n) if (x.is_cuda and n > 0) else None
 
 
 PER_LAYER = 8
@@ -112,7 +123,10 @@ class StackTrainFunction(torch.autograd.Function):
         dev = x.device
         L, R, H = sh.layers, sh.R, sh.H
         Hp, Cp = packing._ru(H, 64), (packing._ru(sh.C, 64) if sh.C else 0)
-        pk = packing.pack_bf16(wn)
+        lanes = getattr(wn, "_lanes", None)                 # forked by stack_*_train around live_weights; joined here
+        pk = packing.pack_bf16(wn, folded=weights, lanes=lanes)
+        if lanes is not None:
+            lanes.join()
         lib = _lib.lib()
         xf = x.detach().float().contiguous()
         cf = None if c_up is None else c_up.detach().float().contiguous()
@@ -181,7 +195,13 @@ class StackNLLFunction(torch.autograd.Function):
 
 def stack_nll_train(wn, x, c_up, gvec, target, shift=1):
     """Scalar teacher-forced NLL with autograd through the tcgen05 forward / backward (StackNLLFunction)."""
-    return StackNLLFunction.apply(wn, x, c_up, gvec, target, shift, *live_weights(wn))
+    wn._lanes = _lanes_for(wn, x)
+    try:
+        return StackNLLFunction.apply(wn, x, c_up, gvec, target, shift, *live_weights(wn, wn._lanes))
+    finally:
+        if wn._lanes is not None:
+            wn._lanes.join()
+        wn._lanes = None
 
 
 def tc_backward_supported(sh) -> bool:
@@ -307,8 +327,18 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
     if x_needs_grad:
         dxin = (dx0.float() @ Wf[:, :, 0].float()).transpose(1, 2).contiguous()
     dc_up = dc[..., :C].transpose(1, 2).contiguous() if C else None
-    grads = [g if g is None or w is None else g.to(w.dtype).reshape(w.shape) for g, w in zip(grads, weights)]
-    return dxin, dc_up, dgvec, grads
+    # the copies that bring permuted views into the parameter shapes: layer l on lane l (the weight-norm backward that consumes
+    # them runs there too); joined before returning, autograd assumes this node's outputs live on its own stream
+    lanes = packing.Lanes(dev, int(os.environ.get("WAE_PREP_LANES", "8")) or 1) if dev.type == "cuda" else packing._NoLanes()
+    out = []
+    for i, (g, w) in enumerate(zip(grads, weights)):
+        if g is None or w is None:
+            out.append(g)
+            continue
+        with lanes.lane(i // PER_LAYER if i < base else 0):
+            out.append(g.to(w.dtype).reshape(w.shape))
+    lanes.join()
+    return dxin, dc_up, dgvec, out
 
 
 def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_needs_grad=False, cdt=BF, adt=torch.float32,
@@ -466,4 +496,10 @@ def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_need
 def stack_forward_train(wn, x, c_up, gvec):
     """(B,O,T) logits with autograd through the tcgen05 forward + GEMM backward.  x one-hot / dense (B,Oin,T); c_up
     (B,C,T) already upsampled; gvec (B,Gi) speaker vectors (with autograd history back to the embedding)."""
-    return StackTrainFunction.apply(wn, x, c_up, gvec, *live_weights(wn))
+    wn._lanes = _lanes_for(wn, x)
+    try:
+        return StackTrainFunction.apply(wn, x, c_up, gvec, *live_weights(wn, wn._lanes))
+    finally:
+        if wn._lanes is not None:
+            wn._lanes.join()
+        wn._lanes = None

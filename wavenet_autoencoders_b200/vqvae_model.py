@@ -133,7 +133,10 @@ class Encoder(nn.Module):
         # flip VQ codes relative to the reference's fp32 path
         # benchmark=True: cuDNN's heuristic pick for these frame-rate shapes (16 x 256 x 100) is an implicit-GEMM kernel that
         # takes 60-90 us per layer; the autotuned choice is several times faster (shapes are static per model)
-        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False, benchmark=True):
+        # ``train_tf32`` (default off): TF32 tensor-core convolutions for the TRAINING forward / backward of the encoder -- what
+        # PyTorch >= 1.7 does by default on Ampere and later; only meaningful next to a bf16 decoder (precision="bf16")
+        tf32 = bool(getattr(self, "train_tf32", False)) and self.training and torch.is_grad_enabled()
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=tf32, benchmark=True):
             out = self.net(x)
         return self.lin(out.permute(0, 2, 1)).permute(0, 2, 1)
 
