@@ -630,6 +630,13 @@ def main():
         e1.record()
         barrier()
         extras["train_eager_ms_per_step"] = max_over_ranks(e0.elapsed_time(e1)) / nt
+        if world > 1:            # replicas must hold bit-identical parameters after the steps (same all-reduced gradients everywhere)
+            import torch.distributed as _d
+            chk = opt.flat_p.double().sum().reshape(1)
+            lo, hi = chk.clone(), chk.clone()
+            _d.all_reduce(lo, op=_d.ReduceOp.MIN)
+            _d.all_reduce(hi, op=_d.ReduceOp.MAX)
+            extras["train_replicas_in_sync"] = bool(float(lo) == float(hi))
         if world > 1:            # all-reduce alone, same flat buffer size (7.6 M fp32 gradients), device-timed
             import torch.distributed as _d
             flat = torch.zeros(sum(p.numel() for p in tm.parameters()), device=dev)
@@ -657,7 +664,8 @@ def main():
         del gstep
         extras["train_config"] = ("VQ-WAE step: 8 utt/GPU x 7680 samples, tcgen05 bf16 forward, tcgen05 backward (wae_stack_backward_bf16: "
                                   "dgrad GEMMs with the dilated taps as TMA boxes and fused gate / residual / ReLU epilogues, MN-major "
-                                  "split-K wgrads), loss + softmax gradient fused (forward_nll), fp32 master weights, Adam, grad-clip 100; "
+                                  "split-K wgrads), loss + softmax gradient fused (forward_nll), per-layer weight preparation forked over 8 side streams, "
+                                  "fp32 master weights, Adam, grad-clip 100; "
                                   "N > 1: flat gradient all-reduced in two buckets, the decoder's (80 % of the bytes) under the rest of the "
                                   "backward; the step is replayed as one CUDA graph")
         del tm, opt

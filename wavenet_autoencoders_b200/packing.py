@@ -183,6 +183,27 @@ class Lanes:
         self.used = []
 
 
+def join_lane_streams_into_current(device):
+    """Make the CURRENT stream wait for every lane stream of ``device`` that takes part in the ongoing work (all of them in
+    eager mode, the ones inside the capture while a CUDA graph is being captured).  For code that runs inside autograd hooks --
+    on whatever lane the last gradient of a bucket was accumulated -- and needs the gradients of ALL lanes."""
+    device = torch.device(device)
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    cur = torch.cuda.current_stream(device)
+    capturing = torch.cuda.is_current_stream_capturing()
+    for (dev_i, _), streams in _lane_streams.items():
+        if dev_i != idx:
+            continue
+        for st in streams:
+            if st == cur:
+                continue
+            if capturing:
+                with torch.cuda.stream(st):
+                    if not torch.cuda.is_current_stream_capturing():
+                        continue
+            cur.wait_stream(st)
+
+
 class _NoLanes:
     def lane(self, i):
         import contextlib

@@ -107,6 +107,11 @@ class BucketedAllReduce:
             return
         self.left[i] -= 1
         if self.left[i] == 0 and self.works[i] is None:
+            if self.flat_g.is_cuda:
+                # the bucket's gradients were accumulated on several side streams (packing.Lanes: layer l's weight-norm backward
+                # runs on lane l); the collective is ordered after the CURRENT stream only -- make it see all of them
+                from . import packing
+                packing.join_lane_streams_into_current(self.flat_g.device)
             self.works[i] = self.dist.all_reduce(self.slices[i], op=self.dist.ReduceOp.SUM, group=self.group, async_op=True)
             self.overlapped += 1
 

@@ -60,7 +60,14 @@ def live_weights(wn, lanes=None):
 def _lanes_for(wn, x):
     """Side-stream lanes for the weight preparation of a CUDA training step (``wn.prep_lanes``, default 8; 0 disables)."""
     n = int(getattr(wn, "prep_lanes", os.environ.get("WAE_PREP_LANES", "8")))
-    return packing.Lanes(x.device, n) if (x.is_cuda and n > 0) else None
+    if not (x.is_cuda and n > 0):
+        return None
+    # gradient accumulators of parameters first used on the main stream (an earlier eager step) now receive gradients produced
+    # on a lane: intended, autograd synchronises the two streams -- silence its per-step warning about it
+    quiet = getattr(torch.autograd.graph, "set_warn_on_accumulate_grad_stream_mismatch", None)
+    if quiet is not None:
+        quiet(False)
+    return packing.Lanes(x.device, n)
 
 
 PER_LAYER = 8
