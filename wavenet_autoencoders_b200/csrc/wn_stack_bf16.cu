@@ -249,25 +249,34 @@ gbias_bf16_kernel(const float* __restrict__ b1, const float* __restrict__ wg, co
 
 // first_conv on (B,Oin,T) fp32 input -> bf16 channels-last [B][T][R].  One-hot columns (the
 // mu-law input of every preset) are detected per sample and become a gather of one weight row;
-// anything else takes the dense dot product.  64 samples per block: the scan reads every input
-// row as 256 contiguous bytes (16 lanes x float4), 16 rows in flight per pass; the writer emits
-// 16-byte channel groups.
-constexpr int FC_T = 64;
+// anything else takes the dense dot product.  FC_T samples per block: the scan reads every input
+// row as FC_T * 4 contiguous bytes (FC_T / 4 lanes x float4), 1024 / FC_T rows per pass; the writer
+// emits 16-byte channel groups.  (64 samples per block = 256-byte runs 64 KB apart: 2.6 TB/s on the 262 MB one-hot tensor of
+// config 2; 256 samples = 1 KB runs.)
+#ifndef WAE_FC_T
+#define WAE_FC_T 256
+#endif
+constexpr int FC_T = WAE_FC_T;
+constexpr int FC_Q = FC_T / 4;           // lanes per input row
+constexpr int FC_ROWS = 256 / FC_Q;      // rows per pass
 __global__ void __launch_bounds__(256)
 first_conv_bf16_kernel(const float* __restrict__ x, const float* __restrict__ wf, const float* __restrict__ bf,
                        int T, int Oin, int R, int vec_ok, __nv_bfloat16* __restrict__ x0) {
     __shared__ int s_cnt[FC_T], s_pos[FC_T], s_bad[FC_T];
     const int b = blockIdx.y, t0 = blockIdx.x * FC_T, tid = threadIdx.x;
     const float* xb = x + (size_t)b * Oin * T;
-    if (tid < FC_T) { s_cnt[tid] = 0; s_pos[tid] = -1; s_bad[tid] = 0; }
+    for (int i = tid; i < FC_T; i += 256) { s_cnt[i] = 0; s_pos[i] = -1; s_bad[i] = 0; }
     __syncthreads();
     {
-        const int q = tid & 15, ol = tid >> 4;
+        const int q = tid % FC_Q, ol = tid / FC_Q;
         const int t = t0 + q * 4;
         int cnt[4] = {0, 0, 0, 0}, pos[4] = {-1, -1, -1, -1}, bad[4] = {0, 0, 0, 0};
         if (t < T) {
-#pragma unroll 4
-            for (int o = ol; o < Oin; o += 16) {
+#ifndef WAE_FC_UNROLL
+#define WAE_FC_UNROLL 4
+#endif
+#pragma unroll WAE_FC_UNROLL
+            for (int o = ol; o < Oin; o += FC_ROWS) {
                 float v[4];
                 const float* src = xb + (size_t)o * T + t;
                 if (vec_ok) {
