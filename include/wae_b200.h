@@ -215,6 +215,9 @@ typedef struct wae_stack_bf16 {
     wae_stack_dims d;
     const void *w1, *wo, *ws, *w3, *w4;                 /* bf16 */
     const float *b1, *wg, *bo, *bs_sum, *b3, *b4, *wf, *bf;
+    /* optional (NULL: computed per sample from wf / bf): the first conv as a bf16 row table for class-index input,
+     * [Oin + 1][R] with row o = bf16(wf[o] + bf) and row Oin = bf16(bf) (an out-of-range class = an all-zero one-hot column) */
+    const void* wfb;
 } wae_stack_bf16;
 
 size_t wae_stack_workspace_bf16(const wae_stack_dims* d, int B, int T);
@@ -265,6 +268,10 @@ typedef struct wae_cond_frontend {
     const int64_t* speaker_ids;
     const float* speaker_table;
     int n_speakers;
+    /* optional: the per-phase partial tap sums of every stage, concatenated [A(0..s-1) | B(0..s-1) | C(0..s-1)] per stage with
+     * A[p] = sum_{j < s-p} w[j], B[p] = sum_{s-p <= j < 2s-p} w[j], C[p] = sum_{j >= 2s-p} w[j] (sequential fp32 sums, j ascending);
+     * NULL: every block sums them itself */
+    const float* coef;
 } wae_cond_frontend;
 /*
  * Teacher-forced forward straight from the LATENT frames lat (B, C, F) fp32 (the VQ output, F * prod(scale) == T): ONE kernel

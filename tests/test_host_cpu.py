@@ -282,3 +282,45 @@ def test_representation_text_dump_matches_numpy_savetxt(tmp_path):
     VQVAE.dump_representation(tmp_path / "c.txt", a[:3, :1], decimals=3)
     np.savetxt(tmp_path / "d.txt", a[:3, :1], fmt="%.3f")
     assert (tmp_path / "c.txt").read_bytes() == (tmp_path / "d.txt").read_bytes()
+
+
+def test_frontend_and_encoder_structs_for_the_fused_kernels():
+    """Host logic of the round-2 fusions (no GPU): packing.pack_frontend expresses ConvInUpsampleNetwork / UpsampleNetwork as
+    the plain-array struct of wae_stack_forward_bf16_lat (or declines), Encoder.fused_struct mirrors vqvae_model.py:25-51 for
+    wae_encoder_vq_forward and wae_encoder_vq_supported agrees with the documented limits, frame arithmetic per SURVEY 9."""
+    import torch
+    from wavenet_autoencoders_b200 import _lib, packing, testing as T
+    from wavenet_autoencoders_b200.vqvae_model import Encoder
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    wn = WaveNet(**T.VQWAE).eval()
+    fe = packing.pack_frontend(wn)
+    assert fe is not None and fe.total_scale == 640 and fe.struct.n_stages == 4
+    assert [fe.struct.scale[i] for i in range(4)] == [4, 4, 8, 5]
+    assert fe.struct.conv_in_w_t and all(fe.struct.filter[i] for i in range(4))
+    wt = fe.keep[0]
+    assert torch.equal(wt, wn.upsample_net.conv_in.weight.detach()[:, :, 0].t())          # [in][out]
+    plain = WaveNet(**dict(T.VQWAE, upsample_net="UpsampleNetwork", upsample_params={"upsample_scales": [16, 40], "cin_channels": 64}))
+    fp = packing.pack_frontend(plain)
+    assert fp is not None and fp.struct.conv_in_w_t is None and fp.total_scale == 640
+    padded = WaveNet(**dict(T.VQWAE, upsample_params={"upsample_scales": [4, 4, 8, 5], "cin_channels": 64, "cin_pad": 2}, cin_pad=2))
+    assert packing.pack_frontend(padded) is None                                          # conv_in with context: staged path
+    fine = WaveNet(**dict(T.VQWAE, upsample_params={"upsample_scales": [2, 2], "cin_channels": 64, "cin_pad": 0}))
+    assert packing.pack_frontend(fine) is None                                            # 32 latent frames per 128-sample tile: staged path
+    assert packing.pack_frontend(WaveNet(**dict(T.VQWAE, upsample_conditional_features=False))) is None
+
+    enc = Encoder(hid=256, c_in=39, c_out=64)
+    st = enc.fused_struct()
+    assert st is not None and st.n_layers == 10 and st.hid == 256 and st.D == 64
+    spec = [(st.layer[i].cin, st.layer[i].cout, st.layer[i].k, st.layer[i].stride, st.layer[i].relu, st.layer[i].residual) for i in range(10)]
+    assert spec[0] == (39, 256, 3, 1, 1, 0) and spec[1] == (256, 256, 3, 1, 1, 1) and spec[2] == (256, 256, 5, 2, 1, 0)
+    assert spec[3] == (256, 256, 5, 2, 1, 0) and spec[4][2:] == (3, 1, 1, 1) and all(s_[2:] == (1, 1, 1, 1) for s_ in spec[6:])
+    assert Encoder(hid=768).fused_struct() is None                                        # wider than the kernel's 256 channels
+    assert Encoder(hid=64, c_in=13, c_out=16).fused_struct() is not None
+    assert [enc.out_frames(f) for f in (1, 2, 100, 300, 50)] == [1, 1, 25, 75, 13]        # SURVEY 9: 50 frames -> 13 latents
+    L = _lib.lib()
+    assert L.wae_encoder_vq_workspace(16, 100) == 4096 + 16 * 2 * 256 * 136 * 4
+    assert L.wae_encoder_vq_workspace(2, 1000) == 4096 + 2 * 11 * 2 * 256 * 136 * 4      # 250 latents -> 11 blocks of 24 per utterance
+    lanes = packing._NoLanes()
+    with lanes.lane(3):
+        pass
+    lanes.join()

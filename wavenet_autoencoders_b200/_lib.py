@@ -38,7 +38,7 @@ class StackF32(C.Structure):
 
 class StackBF16(C.Structure):
     _fields_ = [("d", StackDims)] + [(n, C.c_void_p) for n in
-                                    ("w1", "wo", "ws", "w3", "w4", "b1", "wg", "bo", "bs_sum", "b3", "b4", "wf", "bf")]
+                                    ("w1", "wo", "ws", "w3", "w4", "b1", "wg", "bo", "bs_sum", "b3", "b4", "wf", "bf", "wfb")]
 
 
 class StackSaved(C.Structure):
@@ -52,7 +52,7 @@ class StackBwd(C.Structure):
 
 class CondFrontend(C.Structure):
     _fields_ = [("conv_in_w_t", C.c_void_p), ("n_stages", C.c_int32), ("scale", C.c_int32 * 8), ("filter", C.c_void_p * 8),
-                ("speaker_ids", C.c_void_p), ("speaker_table", C.c_void_p), ("n_speakers", C.c_int32)]
+                ("speaker_ids", C.c_void_p), ("speaker_table", C.c_void_p), ("n_speakers", C.c_int32), ("coef", C.c_void_p)]
 
 
 class EncLayer(C.Structure):

@@ -272,10 +272,7 @@ first_conv_bf16_kernel(const float* __restrict__ x, const float* __restrict__ wf
         const int t = t0 + q * 4;
         int cnt[4] = {0, 0, 0, 0}, pos[4] = {-1, -1, -1, -1}, bad[4] = {0, 0, 0, 0};
         if (t < T) {
-#ifndef WAE_FC_UNROLL
-#define WAE_FC_UNROLL 4
-#endif
-#pragma unroll WAE_FC_UNROLL
+#pragma unroll 4
             for (int o = ol; o < Oin; o += FC_ROWS) {
                 float v[4];
                 const float* src = xb + (size_t)o * T + t;
@@ -444,11 +441,14 @@ struct CondFrontArgs {
     const float* filt[CF_MAX_STAGES];
     int scale[CF_MAX_STAGES];
     int ns, C, Cp, F, T, nt;     // nt: tiles per block (<= CF_NT, host-chosen so that a block needs <= CF_F0 latent frames)
+    int pitch;                   // floats per channel row of the two position buffers (>= positions a tile needs at any stage input, odd)
+    const float* coef;           // optional: the 3-coefficient tables of all stages, precomputed (else summed per block)
     __nv_bfloat16* out;          // [B][T][Cp]
     // optional: the first conv on class indices for the same samples (x0[b][t][:] = wf[idx[b][t]][:] + bf), one launch less
     const long long* x_idx;      // (B, T) or null
     const float* wf;             // [Oin][R]
     const float* bf;             // [R]
+    const __nv_bfloat16* wfb;    // optional [Oin + 1][R] bf16 rows wf[o] + bf (row Oin: bf alone): the gather is then a 16-byte copy
     int Oin, R;
     __nv_bfloat16* x0;           // [B][T][R]
 };
@@ -466,8 +466,9 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
     float* coef = cf_sm;
     float* y0 = cf_sm + ((ctot + 3) & ~3);
     float* buf0 = y0 + a.Cp * (CF_F0 + 1);
-    float* buf1 = buf0 + a.Cp * CF_PITCH;
-    int* ptab = reinterpret_cast<int*>(buf1 + a.Cp * CF_PITCH);
+    const int PITCH = a.pitch;
+    float* buf1 = buf0 + a.Cp * PITCH;
+    int* ptab = reinterpret_cast<int*>(buf1 + a.Cp * PITCH);
     const int b = blockIdx.y, tid = threadIdx.x;
     const int tile0 = blockIdx.x * a.nt;
     const int ntiles = (a.T + CF_T - 1) / CF_T;
@@ -479,7 +480,9 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
         s_len[a.ns] = len;
     }
     // partial tap sums per phase (as upsample_stage_kernel): out[f*s+p] = A[p] in[f-1] + B[p] in[f] + C[p] in[f+1]
-    {
+    if (a.coef != nullptr) {
+        for (int i = tid; i < ctot; i += 256) coef[i] = __ldg(&a.coef[i]);
+    } else {
         int off = 0;
         for (int i = 0; i < a.ns; ++i) {
             const int s = a.scale[i];
@@ -538,6 +541,7 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
     }
 
     const int chn = tid % a.Cp;                 // fixed channel per thread in the stage loops (Cp | 256), else strided fallback
+    const int k_lane = tid / a.Cp, k_step = max(1, 256 / a.Cp);
     const bool fixed_ch = (256 % a.Cp) == 0;
     const int c8n = a.Cp >> 3;
     for (int tile = tile0; tile < tile1; ++tile) {
@@ -571,7 +575,7 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
             }
             __syncthreads();
             if (fixed_ch) {
-                for (int k = tid / a.Cp; k < n1; k += 256 / a.Cp) {
+                for (int k = k_lane; k < n1; k += k_step) {
                     const int pt = ptab[k];
                     float v = 0.f;
                     if (pt >= 0) {
@@ -579,7 +583,7 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
                         const float* xr = cur + chn * cur_pitch + fo;
                         v = fmaf(cf[2 * s + p], xr[1], fmaf(cf[s + p], xr[0], cf[p] * xr[-1]));
                     }
-                    nxt[chn * CF_PITCH + k] = v;
+                    nxt[chn * PITCH + k] = v;
                 }
             } else {
                 for (int e = tid; e < a.Cp * n1; e += 256) {
@@ -590,11 +594,11 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
                         const float* xr = cur + ch * cur_pitch + fo;
                         v = fmaf(cf[2 * s + p], xr[1], fmaf(cf[s + p], xr[0], cf[p] * xr[-1]));
                     }
-                    nxt[ch * CF_PITCH + k] = v;
+                    nxt[ch * PITCH + k] = v;
                 }
             }
             __syncthreads();
-            cur = nxt; cur_pitch = CF_PITCH;
+            cur = nxt; cur_pitch = PITCH;
             nxt = (nxt == buf0) ? buf1 : buf0;
         }
         // last stage + layout change
@@ -604,19 +608,20 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
             const int nt = min(CF_T, a.T - t0);
             for (int k = tid; k < nt; k += 256) { const int t = t0 + k, f = t / s; ptab[k] = (f - lo_in) | ((t - f * s) << 16); }
             __syncthreads();
-            const int tt0 = tid / c8n, c8 = (tid - tt0 * c8n) * 8, tstep = 256 / c8n;
-            const bool reg = (256 % c8n) == 0;
-            for (int e = tid; e < nt * c8n; e += 256) {
-                const int tt = reg ? tt0 + (e / 256) * tstep : e / c8n;
-                const int cc8 = reg ? c8 : (e - tt * c8n) * 8;
+            // thread -> (sample lane tt0, channel group c8), samples tt0, tt0 + 256 / c8n, ...: no division in the loop.  (Signed
+            // divisions by run-time values were 3/4 of this kernel's instructions: profiles/r2_frontend_ncu.txt.)
+            const unsigned uc8n = (unsigned)c8n;
+            const bool reg = (256u % uc8n) == 0;
+            const int tt0 = (int)((unsigned)tid / uc8n), c8 = (tid - tt0 * c8n) * 8, tstep = reg ? 256 / c8n : 0;
+            for (int e = tid, tt_r = tt0; e < nt * c8n; e += 256, tt_r += tstep) {
+                int tt = tt_r, cc8 = c8;
+                if (!reg) { tt = (int)((unsigned)e / uc8n); cc8 = (e - tt * c8n) * 8; }
                 const int pt = ptab[tt], fo = pt & 0xffff, p = pt >> 16;
                 const float ca = cf[p], cb = cf[s + p], cc = cf[2 * s + p];
                 float v[8];
+                const float* xr = cur + cc8 * cur_pitch + fo;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float* xr = cur + (cc8 + j) * cur_pitch + fo;
-                    v[j] = fmaf(cc, xr[1], fmaf(cb, xr[0], ca * xr[-1]));
-                }
+                for (int j = 0; j < 8; ++j, xr += cur_pitch) v[j] = fmaf(cc, xr[1], fmaf(cb, xr[0], ca * xr[-1]));
                 uint4 o4;
                 o4.x = pack_bf16x2(v[0], v[1]); o4.y = pack_bf16x2(v[2], v[3]);
                 o4.z = pack_bf16x2(v[4], v[5]); o4.w = pack_bf16x2(v[6], v[7]);
@@ -628,6 +633,42 @@ cond_frontend_cl_kernel(const __grid_constant__ CondFrontArgs a) {
                 const int r8n = a.R >> 3;
                 const long long row0 = (long long)b * a.T + t0;
                 const int n_it = nt * r8n;
+                if (a.wfb != nullptr) {
+                    // thread -> fixed 16-byte column r of the row table, samples tq0, tq0 + 256 / r8n, ... (r8n | 256 for R in
+                    // {64, 128, 256}); otherwise an unsigned division per item
+                    const unsigned ur8n = (unsigned)r8n;
+                    const bool regr = (256u % ur8n) == 0;
+                    const int tq0 = (int)((unsigned)tid / ur8n), rq = (tid - tq0 * r8n) * 8;
+                    if (regr) {
+                        // pointer-increment form: sample tq0 + k * qstep, k = 0, 1, ...; four loads in flight
+                        const int qstep = 256 / r8n;
+                        const __nv_bfloat16* tab = a.wfb + rq;
+                        __nv_bfloat16* dst = a.x0 + (size_t)(row0 + tq0) * a.R + rq;
+                        const size_t dstep = (size_t)qstep * a.R;
+                        const int oob = a.Oin;
+                        for (int tq = tq0; tq < nt; tq += 4 * qstep, dst += 4 * dstep) {
+                            uint4 v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int tt = tq + u * qstep;
+                                if (tt < nt) {
+                                    const unsigned h = (unsigned)s_cls[tt];            // negative classes wrap to large values
+                                    v[u] = __ldg(reinterpret_cast<const uint4*>(tab + (size_t)(h < (unsigned)oob ? h : (unsigned)oob) * a.R));
+                                }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (tq + u * qstep < nt) *reinterpret_cast<uint4*>(dst + u * dstep) = v[u];
+                        }
+                    } else {
+                        for (int e = tid; e < n_it; e += 256) {
+                            const int tt = (int)((unsigned)e / ur8n), r = (e - tt * r8n) * 8;
+                            const int h = s_cls[tt];
+                            *reinterpret_cast<uint4*>(a.x0 + (size_t)(row0 + tt) * a.R + r) =
+                                __ldg(reinterpret_cast<const uint4*>(a.wfb + (size_t)((h >= 0 && h < a.Oin) ? h : a.Oin) * a.R + r));
+                        }
+                    }
+                } else
                 for (int e0 = tid; e0 < n_it; e0 += 256 * 4) {
                     float4 w0[4], w1[4];
                     int tts[4], rs[4];
@@ -3075,6 +3116,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         ca.lat = c; ca.win_t = fe->conv_in_w_t; ca.ns = fe->n_stages; ca.C = d.C; ca.Cp = Cp; ca.F = fe_frames; ca.T = T; ca.out = ws.ccl;
         ca.x_idx = fc_fused ? reinterpret_cast<const long long*>(x_idx) : nullptr;
         ca.wf = w->wf; ca.bf = w->bf; ca.Oin = d.Oin; ca.R = d.R; ca.x0 = ws.xa;
+        ca.wfb = static_cast<const __nv_bfloat16*>(w->wfb);
         int nt = CF_NT;
         for (;; --nt) {   // latent frames one block of nt tiles can touch (+ 2: blocks that do not start at a frame boundary)
             long long lo = 0, hi = (long long)nt * CF_T - 1;
@@ -3083,8 +3125,24 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
             WAE_REQUIRE(nt > 1, "wae_stack_forward_bf16_lat: total upsampling factor too small (%lld latent frames per 128-sample tile, max %d)",
                         hi - lo + 1 + 2, CF_F0);
         }
+        {   // enough blocks to keep ~4 per SM in flight; every block repeats conv_in for its handful of frames
+            const long long tiles = (long long)B * ((T + CF_T - 1) / CF_T);
+            const long long want = tiles / ((long long)num_sms() * 4);
+            if (want < nt) nt = want < 1 ? 1 : (int)want;
+        }
         ca.nt = nt;
-        const size_t sm = ((size_t)((ctot + 3) & ~3) + (size_t)Cp * (CF_F0 + 1) + (size_t)2 * Cp * CF_PITCH + CF_PITCH + 3) * sizeof(float);
+        int pitch = 5;
+        {
+            int need = CF_T;
+            for (int i = fe->n_stages - 1; i >= 1; --i) {      // positions of one tile at the input of stage i (levels 1 .. ns-1 live in the buffers)
+                need = (need + fe->scale[i] - 1) / fe->scale[i] + 3;
+                if (need + 1 > pitch) pitch = need + 1;
+            }
+            pitch |= 1;
+        }
+        ca.pitch = pitch;
+        ca.coef = fe->coef;
+        const size_t sm = ((size_t)((ctot + 3) & ~3) + (size_t)Cp * (CF_F0 + 1) + (size_t)2 * Cp * pitch + CF_PITCH + 3) * sizeof(float);
         WAE_REQUIRE(sm <= 200 * 1024, "wae_stack_forward_bf16_lat: C=%d needs %zu bytes of shared memory", d.C, sm);
         WAE_CHECK_CUDA(cudaFuncSetAttribute(cond_frontend_cl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         cond_frontend_cl_kernel<<<dim3(((T + CF_T - 1) / CF_T + nt - 1) / nt, B), 256, sm, stream>>>(ca);

@@ -143,6 +143,27 @@ def pack_frontend(wn):
         fe.scale[i] = int(s)
         fe.filter[i] = w.data_ptr()
         total *= int(s)
+    # the 3-coefficient form of every stage (what the kernels evaluate), summed once here in the kernels' order and precision
+    import numpy as np
+    coefs = []
+    for s_, w in zip(up.scales, keep[-len(up.scales):]):
+        wn_ = w.detach().cpu().numpy().astype(np.float32)
+        a = np.zeros(s_, np.float32); b = np.zeros(s_, np.float32); c = np.zeros(s_, np.float32)
+        for p in range(s_):
+            x = np.float32(0.0)
+            for j in range(0, s_ - p):
+                x = np.float32(x + wn_[j])
+            y = np.float32(0.0)
+            for j in range(s_ - p, 2 * s_ - p):
+                y = np.float32(y + wn_[j])
+            z = np.float32(0.0)
+            for j in range(2 * s_ - p, 2 * s_ + 1):
+                z = np.float32(z + wn_[j])
+            a[p], b[p], c[p] = x, y, z
+        coefs += [a, b, c]
+    coef = torch.tensor(np.concatenate(coefs), dtype=torch.float32, device=keep[-1].device)
+    keep.append(coef)
+    fe.coef = coef.data_ptr()
     return FrontendPack(fe, total, keep)
 
 
@@ -347,9 +368,11 @@ def pack_bf16(wn, folded=None, lanes=None) -> Packed:
     t["b4"] = torch.nn.functional.pad(_bias(l3, sh.O, dev), (0, Op - sh.O)).contiguous()
     t["wf"] = fold(wn.first_conv, 0).float()[:, :, 0].t().contiguous()
     t["bf"] = _bias(wn.first_conv, sh.R, dev).contiguous()
+    # class-index input: first conv = one row of bf16(wf + bf) per sample (the same fp32 add + rounding the kernels did per sample)
+    t["wfb"] = torch.cat([t["wf"] + t["bf"][None, :], t["bf"][None, :]], dim=0).to(bf).contiguous() if sh.Oin > 1 else None
     s = _lib.StackBF16()
     s.d = sh.dims()
-    for name in ("w1", "wo", "ws", "w3", "w4", "b1", "wg", "bo", "bs_sum", "b3", "b4", "wf", "bf"):
+    for name in ("w1", "wo", "ws", "w3", "w4", "b1", "wg", "bo", "bs_sum", "b3", "b4", "wf", "bf", "wfb"):
         setattr(s, name, _lib.ptr(t[name]))
     p.struct = s
     return p
