@@ -454,6 +454,27 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * The same synthesis with the waveform post-processing of synthesis.py:382-394 fused into the sampling step:
+ * the thread that emits utterance b's sample at step t also computes
+ *     x = table[class]                      (categorical: P.inv_mulaw_quantize; table = (mu + 1) floats built by the caller)
+ *       | inv_mulaw(sample, mu) | sample    (scalar samplers: scalar_is_mulaw = 1 / 0)
+ *     w = x + preemphasis_coef * w_prev     (audio.inv_preemphasis, w_prev = 0 before the first sample)
+ *     out_wave[b][t] = w / gain             (gain <= 0: no division)
+ * so no second pass over the samples and no one-hot / index tensor has to leave the device.  out_idx / out_dense stay optional.
+ */
+typedef struct wae_ar_post {
+    const float* table;        /* (mu + 1) fp32 on the device, or NULL for the scalar samplers */
+    int mu;                    /* quantize_channels (- 1), as the caller's mu-law convention has it */
+    int scalar_is_mulaw;
+    float preemphasis_coef, gain;
+    float* out_wave;           /* (B, T) fp32 */
+} wae_ar_post;
+int wae_ar_generate_wave(const wae_ar_weights* w, const float* c_btc, const float* gemb, const float* init,
+                         const float* forced, int Tf, const float* uniforms, int B, int T, int sample_mode,
+                         int apply_softmax, int32_t* out_idx, float* out_dense, const wae_ar_post* post, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/*
  * Waveform post-processing after autoregressive synthesis, one launch (replaces synthesis.py:382-394: argmax of the one-hot
  * output on the host, nnmnkwii P.inv_mulaw_quantize / P.inv_mulaw, audio.inv_preemphasis = lfilter([1], [1, -coef]), division by
  * hparams.global_gain_scale).

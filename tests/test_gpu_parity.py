@@ -828,6 +828,46 @@ def test_synthesis_postprocess_matches_oracle():
         waveform_from_synthesis(torch.tensor(idx), "mulaw-quantize", 256)             # CPU tensor: no fallback
 
 
+@pytest.mark.parametrize("cfg_name,prec", [("tiny", "fp32"), ("tiny", "bf16"), ("tiny_mol", "fp32"), ("tiny_mol", "bf16"), ("vqwae", "bf16")])
+def test_incremental_forward_with_fused_postprocess(cfg_name, prec):
+    """wae_ar_generate_wave: inverse mu-law, inverse pre-emphasis and gain computed INSIDE the synthesis kernel by
+    the thread that emits each sample.  Same sampled stream as the plain call (identical uniforms), and the waveform equals
+    (a) the float64 oracle on those samples <= 2e-5 and (b) the separate wae_synth_postprocess launch <= 2e-5 (another
+    summation order of the recurrence); without pre-emphasis the table lookup is exact."""
+    from oracle import postprocess_oracle as po
+    from wavenet_autoencoders_b200.postprocess import waveform_from_synthesis
+    cfg = T.CONFIGS[cfg_name]
+    m = build_model(cfg_name, 5, "cuda")
+    m.precision = prec
+    B, Tn = (3, 320) if cfg_name != "vqwae" else (2, 1280)
+    x, idx, c, spk = T.synth_inputs(cfg, B, Tn, 21)
+    scalar = bool(cfg["scalar_input"])
+    nu = (cfg["out_channels"] // 3 + 1) if scalar else None
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    u = torch.rand((Tn, B, nu) if scalar else (Tn, B), device="cuda", generator=gen)
+    kind = "raw" if scalar else "mulaw-quantize"
+    for post, coef, gain in ((None, 0.85, 0.0), ("inv_preemphasis", 0.97, 0.55)):
+        kw = dict(input_type=kind, quantize_channels=cfg["out_channels"] if not scalar else 256, postprocess=post,
+                  preemphasis_coef=coef, global_gain_scale=gain)
+        with torch.no_grad():
+            y0 = m.incremental_forward(initial_input=x[:, :, :1].cuda(), c=c.cuda(), g=spk.cuda(), T=Tn, uniforms=u,
+                                       return_indices=not scalar)
+            assert m.last_waveform is None
+            y1 = m.incremental_forward(initial_input=x[:, :, :1].cuda(), c=c.cuda(), g=spk.cuda(), T=Tn, uniforms=u,
+                                       return_indices=not scalar, wave_postprocess=kw)
+        assert torch.equal(y0, y1)                                   # the post-processing does not disturb the synthesis
+        wave = m.last_waveform
+        assert wave is not None and wave.shape == (B, Tn)
+        samples = y1.cpu().numpy() if not scalar else y1[:, 0].cpu().numpy()
+        ref = po.waveform(samples, kind, kw["quantize_channels"], post, coef, gain)
+        tol = 2e-5 * max(1.0, float(np.abs(ref).max()))
+        np.testing.assert_allclose(wave.cpu().numpy(), ref, rtol=0, atol=tol)
+        sep = waveform_from_synthesis(y1.long() if not scalar else y1, kind, kw["quantize_channels"], post, coef, gain)
+        np.testing.assert_allclose(wave.cpu().numpy(), sep.cpu().numpy(), rtol=0, atol=tol)
+        if post is None and not scalar:
+            np.testing.assert_array_equal(wave.cpu().numpy(), ref.astype(np.float32))
+
+
 def test_training_transpose_cast_matches_torch():
     """wae_train_transpose_cast: (B,O,T) fp32 -> (B,T,O) bf16, bit-identical to torch's transposing copy (round to nearest even),
     ragged tiles included."""

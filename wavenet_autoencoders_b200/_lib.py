@@ -69,6 +69,11 @@ class VqSlice(C.Structure):
                 ("idx_out", C.c_void_p), ("counts_out", C.c_void_p), ("sqerr_out", C.c_void_p)]
 
 
+class ArPost(C.Structure):
+    _fields_ = [("table", C.c_void_p), ("mu", C.c_int32), ("scalar_is_mulaw", C.c_int32), ("preemphasis_coef", C.c_float),
+                ("gain", C.c_float), ("out_wave", C.c_void_p)]
+
+
 class ArWeights(C.Structure):
     _fields_ = [
         ("d", StackDims),
@@ -146,6 +151,9 @@ SIGNATURES = {
     "wae_gemm_bf16_tn_bf16out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "wae_ar_workspace": (C.c_size_t, [C.POINTER(ArWeights), C.c_int, C.c_int]),
     "wae_ar_set_profile_buffer": (None, [C.c_void_p]),
+    "wae_ar_generate_wave": (C.c_int, [C.POINTER(ArWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                       C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(ArPost),
+                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "wae_ar_generate": (C.c_int, [C.POINTER(ArWeights), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -65,7 +65,23 @@ struct ArArgs {
     float* out_dense;                // (B,T,O) / (B,T) or null
     float skip_scale;
     long long* prof;                 // optional [gridDim.x][16] cycle counters (thread 0 of each CTA), or null
+    // optional waveform post-processing fused into the sampling step (synthesis.py:382-394): the lane that
+    // writes utterance b's sample also runs x = table[class] (or inv_mulaw / identity of the scalar sample), the inverse
+    // pre-emphasis recurrence w = x + coef * w_prev and the division by the gain -- nothing waits on it
+    const float* wave_table;         // [mu + 1] inverse mu-law of the classes (categorical), or null
+    float* out_wave;                 // (B,T) or null
+    float wave_coef, wave_inv_gain, wave_mu;
+    int wave_kind;                   // 0 classes through the table, 1 scalar mu-law sample -> inv_mulaw, 2 raw scalar
 };
+
+__device__ __forceinline__ float ar_wave_sample(const ArArgs& a, int pick, float xs) {
+    if (a.wave_kind == 0) return __ldg(&a.wave_table[pick]);
+    if (a.wave_kind == 1) {
+        const float m = (exp2f(fabsf(xs) * log2f(1.0f + a.wave_mu)) - 1.0f) / a.wave_mu;
+        return xs > 0.f ? m : (xs < 0.f ? -m : 0.f);
+    }
+    return xs;
+}
 
 __host__ __device__ inline int part(int n, int r, int cs) { return (n * r) / cs; }   // n*r < 2^31 (n <= 1024 rows, r <= 16)
 
@@ -324,6 +340,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
 
     unsigned j1 = 0, j2 = 0;  // consumed-blob counters of the two weight rings
     AR_PROF_DECL;
+    float wave_w = 0.f;       // inverse pre-emphasis state of this warp's utterance (lane 0 of the writer CTA)
 
     for (int t = 0; t < a.T; ++t) {
         // random draw(s) of this step: issue the (HBM-latency) load now, consume it after the head
@@ -641,6 +658,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                     if (lane == 0) {
                         cur_idx[u] = pick;
                         if (writer && a.out_idx) a.out_idx[(size_t)b * a.T + t] = pick;
+                        if (writer && a.out_wave) {
+                            wave_w = fmaf(a.wave_coef, wave_w, ar_wave_sample(a, pick, 0.f));
+                            a.out_wave[(size_t)b * a.T + t] = wave_w * a.wave_inv_gain;
+                        }
                     }
                 } else {
                     const float inv = 1.f / total;
@@ -692,6 +713,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_kernel(const __grid_constant
                     inbuf[u * Oin] = xs;
                     cur_idx[u] = -1;
                     if (writer && a.out_dense) a.out_dense[(size_t)b * a.T + t] = xs;
+                    if (writer && a.out_wave) {
+                        wave_w = fmaf(a.wave_coef, wave_w, ar_wave_sample(a, 0, xs));
+                        a.out_wave[(size_t)b * a.T + t] = wave_w * a.wave_inv_gain;
+                    }
                 }
             }
         }
@@ -1182,6 +1207,7 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
     unsigned j1 = 0, j2 = 0;
     uint32_t hph = 0, xph = 0;                                   // phase parities of h_full / x_full
     AR_PROF_DECL;
+    float wave_w = 0.f;       // inverse pre-emphasis state of this warp's utterance (lane 0 of the writer CTA)
     for (int t = 0; t < a.T; ++t) {
         float u_pref = 0.f;
         if (warp < U && a.uniforms != nullptr) {
@@ -1483,6 +1509,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 inbuf[u * Oin] = xs;
                 cur_idx[u] = -1;
                 if (writer && a.out_dense) a.out_dense[(size_t)b * a.T + t] = xs;
+                if (writer && a.out_wave) {
+                    wave_w = fmaf(a.wave_coef, wave_w, ar_wave_sample(a, 0, xs));
+                    a.out_wave[(size_t)b * a.T + t] = wave_w * a.wave_inv_gain;
+                }
             }
         } else if (warp < U) {
             const int u = warp, b = cid * U + u;
@@ -1525,6 +1555,10 @@ __global__ void __launch_bounds__(AR_THREADS, 1) ar_mma_kernel(const __grid_cons
                 if (lane == 0) {
                     cur_idx[u] = pick;
                     if (writer && a.out_idx) a.out_idx[(size_t)b * a.T + t] = pick;
+                    if (writer && a.out_wave) {
+                        wave_w = fmaf(a.wave_coef, wave_w, ar_wave_sample(a, pick, 0.f));
+                        a.out_wave[(size_t)b * a.T + t] = wave_w * a.wave_inv_gain;
+                    }
                 }
             } else {
                 const float inv = 1.f / total;
@@ -1608,10 +1642,36 @@ size_t wae_ar_workspace(const wae_ar_weights* w, int B, int T) {
     return n;
 }
 
+static int ar_generate_impl(const wae_ar_weights* w, const float* c_btc, const float* gemb, const float* init,
+                            const float* forced, int Tf, const float* uniforms, int B, int T, int sample_mode,
+                            int apply_softmax, int32_t* out_idx, float* out_dense, const wae_ar_post* post, void* workspace,
+                            size_t workspace_bytes, void* stream_);
+
 int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* gemb, const float* init,
                     const float* forced, int Tf, const float* uniforms, int B, int T, int sample_mode,
                     int apply_softmax, int32_t* out_idx, float* out_dense, void* workspace, size_t workspace_bytes,
                     void* stream_) {
+    return ar_generate_impl(w, c_btc, gemb, init, forced, Tf, uniforms, B, T, sample_mode, apply_softmax, out_idx, out_dense, nullptr,
+                            workspace, workspace_bytes, stream_);
+}
+
+int wae_ar_generate_wave(const wae_ar_weights* w, const float* c_btc, const float* gemb, const float* init,
+                         const float* forced, int Tf, const float* uniforms, int B, int T, int sample_mode,
+                         int apply_softmax, int32_t* out_idx, float* out_dense, const wae_ar_post* post, void* workspace,
+                         size_t workspace_bytes, void* stream_) {
+    WAE_REQUIRE(w != nullptr && post != nullptr && post->out_wave != nullptr, "wae_ar_generate_wave: null post-processing descriptor / output");
+    WAE_REQUIRE(sample_mode != WAE_AR_SAMPLE_NONE, "wae_ar_generate_wave: needs a sampling mode (a waveform of logits is undefined)");
+    WAE_REQUIRE(fabsf(post->preemphasis_coef) < 1.f, "wae_ar_generate_wave: |coef| must be < 1");
+    if (sample_mode == WAE_AR_SAMPLE_CATEGORICAL)
+        WAE_REQUIRE(post->table != nullptr && post->mu >= w->d.O - 1, "wae_ar_generate_wave: categorical sampling needs the inverse mu-law table with >= O entries");
+    return ar_generate_impl(w, c_btc, gemb, init, forced, Tf, uniforms, B, T, sample_mode, apply_softmax, out_idx, out_dense, post,
+                            workspace, workspace_bytes, stream_);
+}
+
+static int ar_generate_impl(const wae_ar_weights* w, const float* c_btc, const float* gemb, const float* init,
+                            const float* forced, int Tf, const float* uniforms, int B, int T, int sample_mode,
+                            int apply_softmax, int32_t* out_idx, float* out_dense, const wae_ar_post* post, void* workspace,
+                            size_t workspace_bytes, void* stream_) {
     if (int rc = wae::require_sm100()) return rc;
     WAE_REQUIRE(w && init && workspace, "wae_ar_generate: null pointer");
     const wae_stack_dims& d = w->d;
@@ -1665,6 +1725,14 @@ int wae_ar_generate(const wae_ar_weights* w, const float* c_btc, const float* ge
         WAE_REQUIRE(a.nu <= 32, "wae_ar_generate: at most 31 mixture components");
     }
     a.out_idx = out_idx; a.out_dense = out_dense;
+    if (post != nullptr) {
+        a.out_wave = post->out_wave;
+        a.wave_table = post->table;
+        a.wave_coef = post->preemphasis_coef;
+        a.wave_inv_gain = post->gain > 0.f ? 1.0f / post->gain : 1.0f;
+        a.wave_mu = (float)post->mu;
+        a.wave_kind = (sample_mode == WAE_AR_SAMPLE_CATEGORICAL) ? 0 : (post->scalar_is_mulaw ? 1 : 2);
+    }
     a.skip_scale = (float)sqrt(1.0 / (double)d.layers);
     a.prof = g_ar_prof;
 

@@ -88,6 +88,7 @@ class WaveNet(nn.Module):
         self.fuse_frontend = True          # bf16 inference: conv_in + all upsampler stages inside the stack's conditioning kernel
         self.train_impl = "kernels"        # "kernels": tcgen05 forward + GEMM backward (bf16, CUDA) | "autograd": torch ops
         self.last_sampled_indices = None  # (B,T) int32 of the last categorical incremental_forward
+        self.last_waveform = None         # (B,T) fp32 of the last incremental_forward(wave_postprocess=...)
         self.last_ar_variant = None       # (weight type, cluster size, utterances per cluster) the last synthesis ran with
         self._packs = {}
         self._ws = packing.WorkspaceCache()
@@ -375,10 +376,13 @@ class WaveNet(nn.Module):
     # ------------------------------------------------------------------ autoregressive synthesis
     def incremental_forward(self, initial_input=None, c=None, g=None, T=100, test_inputs=None,
                             tqdm=lambda x: x, softmax=True, quantize=True, log_scale_min=-50.0,
-                            uniforms=None, generator=None, return_indices=False):
+                            uniforms=None, generator=None, return_indices=False, wave_postprocess=None):
         """wavenet.py:218-346.  Extra (additive) keywords: ``uniforms`` -- the (T,B[,n]) random draws the fused
         sampler consumes (default: torch.rand with ``generator``); ``return_indices`` -- return the (B,T) int32 sampled
-        classes instead of materialising the (B,O,T) one-hot tensor."""
+        classes instead of materialising the (B,O,T) one-hot tensor; ``wave_postprocess`` -- a dict with the keywords of
+        ``postprocess.waveform_from_synthesis`` (input_type, quantize_channels, postprocess, preemphasis_coef,
+        global_gain_scale): the waveform post-processing of synthesis.py:382-394 then runs INSIDE the synthesis kernel, sample
+        by sample, and the (B,T) fp32 waveform is left in ``self.last_waveform``."""
         if self.training:
             raise RuntimeError("incremental_forward only supports eval mode")
         self.clear_buffer()
@@ -490,10 +494,23 @@ class WaveNet(nn.Module):
                 out_dense = torch.empty(B, T, dtype=torch.float32, device=dev)
             else:
                 out_dense = None
-            _lib.check(L.wae_ar_generate(pk.struct, _lib.ptr(c_btc), _lib.ptr(None if gvec is None else gvec.float().contiguous()),
-                                         _lib.ptr(init), _lib.ptr(forced), Tf, _lib.ptr(uniforms), B, T, mode,
-                                         1 if softmax else 0, _lib.ptr(out_idx), _lib.ptr(out_dense),
-                                         _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "wae_ar_generate")
+            gv_ar = None if gvec is None else gvec.float().contiguous()
+            self.last_waveform = None
+            if wave_postprocess is not None:
+                if mode == _lib.AR_SAMPLE_NONE:
+                    raise ValueError("wave_postprocess needs sampling (quantize=True or a scalar-output model)")
+                from .. import postprocess as _pp
+                post, wave, keep = _pp.ar_post_struct(dev, B, T, categorical=(mode == _lib.AR_SAMPLE_CATEGORICAL), **wave_postprocess)
+                _lib.check(L.wae_ar_generate_wave(pk.struct, _lib.ptr(c_btc), _lib.ptr(gv_ar), _lib.ptr(init), _lib.ptr(forced), Tf,
+                                                  _lib.ptr(uniforms), B, T, mode, 1 if softmax else 0, _lib.ptr(out_idx),
+                                                  _lib.ptr(out_dense), post, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                           "wae_ar_generate_wave")
+                self.last_waveform = wave
+            else:
+                _lib.check(L.wae_ar_generate(pk.struct, _lib.ptr(c_btc), _lib.ptr(gv_ar),
+                                             _lib.ptr(init), _lib.ptr(forced), Tf, _lib.ptr(uniforms), B, T, mode,
+                                             1 if softmax else 0, _lib.ptr(out_idx), _lib.ptr(out_dense),
+                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)), "wae_ar_generate")
             if mode == _lib.AR_SAMPLE_CATEGORICAL:
                 self.last_sampled_indices = out_idx
                 if return_indices:
