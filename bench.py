@@ -485,6 +485,30 @@ def main():
                 "head_frac": head_flops / (float(ms_kind[2]) / max(int(n_kind[2]), 1) * 1e-3) / 1e12 / peak_tf,
                 "stack_frac": B * T_SAMPLES * FLOP_PER_SAMPLE_TOTAL * prof_steps
                               / ((float(ms_kind[0]) + float(ms_kind[1]) + float(ms_kind[2])) * 1e-3) / 1e12 / peak_tf}
+    # the same fractions on the e2e path (class-index input: first conv gathered by the front-end kernel; NLL from the head
+    # kernel's accumulator, no logits written) -- the decoder stack as the e2e number runs it
+    try:
+        i_dev, m_dev, g_dev = idx_p.to(dev), mfcc_p.to(dev), g_p.to(dev)
+        L.wae_profile_enable(1)
+        with torch.no_grad():
+            for _ in range(2):
+                model.forward_nll(i_dev, m_dev, g_dev, i_dev, 1)
+            torch.cuda.synchronize()
+            L.wae_profile_read(ms_kind, n_kind, 4)
+            for _ in range(prof_steps):
+                model.forward_nll(i_dev, m_dev, g_dev, i_dev, 1)
+            torch.cuda.synchronize()
+        L.wae_profile_read(ms_kind, n_kind, 4)
+        L.wae_profile_enable(0)
+        roofline["index_nll_path"] = {
+            "stack_frac": B * T_SAMPLES * FLOP_PER_SAMPLE_TOTAL * prof_steps
+                          / ((float(ms_kind[0]) + float(ms_kind[1]) + float(ms_kind[2])) * 1e-3) / 1e12 / peak_tf,
+            "head_frac": head_flops / (float(ms_kind[2]) / max(int(n_kind[2]), 1) * 1e-3) / 1e12 / peak_tf,
+            "prep_ms": float(ms_kind[0]) / prof_steps, "layers_ms": float(ms_kind[1]) / prof_steps, "head_ms": float(ms_kind[2]) / prof_steps,
+            "what": "prep (gate bias + front-end kernel incl. the first-conv gather) + 20 layer kernels + head kernel in NLL mode, "
+                    "every FLOP of SURVEY 8(d)'s 11,403,264 per sample counted once, vs the burst bf16 peak"}
+    except Exception as e:      # never let an auxiliary measurement take the line down
+        roofline["index_nll_path"] = {"error": str(e)[:200]}
     try:
         roofline["traffic"] = json.load(open(os.path.join(ROOT, "profiles", "layer_kernel_traffic.json")))["dram_bytes_per_launch"]
     except Exception:

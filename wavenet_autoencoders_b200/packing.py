@@ -92,7 +92,19 @@ def generation() -> int:
 def params_fingerprint(wn) -> tuple:
     """Changes whenever any parameter of the module is modified in place, replaced, or rewritten through raw pointers by this
     package's optimiser (bump_generation)."""
-    return (_generation,) + tuple((p.data_ptr(), p._version) for p in wn.parameters())
+    # called on every forward: walk a cached module list and the modules' own parameter dicts instead of Module.parameters()
+    # (whose generator / de-duplication machinery costs ~0.3 ms for the 316 parameters of the vqwae decoder)
+    mods = wn.__dict__.get("_fp_modules")
+    if mods is None or sum(len(m._modules) for m in mods) != len(mods) - 1:      # a sub-module was added / removed: rebuild
+        mods = list(wn.modules())
+        wn.__dict__["_fp_modules"] = mods
+    fp = [_generation]
+    for m in mods:
+        for p in m._parameters.values():
+            if p is not None:
+                fp.append(p.data_ptr())
+                fp.append(p._version)
+    return tuple(fp)
 
 
 @dataclass
