@@ -464,6 +464,12 @@ class WaveNet(nn.Module):
             else:
                 wtype = "bf16" if self.ar_impl == "simt" else "bf16mma"
             cluster = self.ar_cluster or (16 if wtype == "fp32" else 8)
+            if self.ar_cluster is None and wtype == "fp32" and self.ar_utts_per_cluster in (None, 1, 2):
+                # fp32 weights: 16 CTAs per cluster halve every CTA's slice, but only ~7 such clusters are co-resident; more
+                # utterance groups than that run in waves (32 utterances: 366 us per step), while 8-CTA clusters (18 co-resident,
+                # two utterances each still fit shared memory) take them in one (228 us) -- tools/ar_fp32_sweep.py
+                if -(-B // (self.ar_utts_per_cluster or 2)) > 7:
+                    cluster = 8
             if wtype == "bf16mma":
                 sh = packing.stack_shape(self)     # the tensor-core kernel exchanges bf16 pairs: slice boundaries must be even
                 even = lambda cs: not any(packing.part(n, r, cs) % 2 for n in (sh.H, sh.R, sh.S) for r in range(1, cs))
