@@ -612,6 +612,10 @@ def test_encoder_vq_fused_kernel(frames, B, sliced):
             ref = m.encoder.lin(m.encoder.net(x).permute(0, 2, 1)).permute(0, 2, 1)
         assert lat.shape == ref.shape
         assert rel_err(lat.cpu().numpy(), ref.cpu().numpy()) < 1e-5
+        if frames <= 300:                                    # the numpy oracle (pinned to the reference's latents, test_oracle_cpu.py)
+            from oracle import encoder_oracle as eo
+            olat = eo.encoder_forward({k: v.cpu().numpy() for k, v in m.state_dict().items() if k.startswith("encoder.")}, x.cpu().numpy())
+            assert rel_err(lat.cpu().numpy(), olat) < 1e-5
         qs, ls, ps = m.vq(lat)                               # standalone search kernel on the same latents
         assert torch.equal(m.vq.last_codes, codes)
         assert torch.equal(qs.contiguous(), quant)

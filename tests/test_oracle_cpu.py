@@ -194,6 +194,27 @@ def test_oracle_vqvae_composition():
     assert rel_err(y, g["logits"]) < 2e-5
 
 
+@pytest.mark.parametrize("case,hid,K,seed", [("vqvae_tiny", 48, 32, 5), ("vqvae_vqwae", 256, 256, None)])
+def test_encoder_oracle_matches_reference_latents(case, hid, K, seed):
+    """oracle/encoder_oracle.py (numpy restatement of vqvae_model.py:9-51) against the latents the REAL reference's encoder
+    produced (goldens), and the reference's codes from the C oracle's search on those latents (row f3's checker)."""
+    from oracle import encoder_oracle as eo
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    g = load_golden(case)
+    cfg = T.CONFIGS["tiny" if case == "vqvae_tiny" else "vqwae"]
+    torch.manual_seed(0)
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    m = VQVAE(c_in=39, hid=cfg["cin_channels"], K=K, wavenet=WaveNet(**cfg), encoder_hid=hid).eval()
+    m.load_state_dict(T.synth_state_dict(m, int(g["seed"]) if seed is None else seed))
+    sd = {k: v.numpy() for k, v in m.state_dict().items() if k.startswith("encoder.")}
+    lat = eo.encoder_forward(sd, g["mfcc"])
+    assert lat.shape == g["latents"].shape
+    assert rel_err(lat, g["latents"]) < 2e-6
+    if "codes" in g:
+        _, _, _, idx = vq_oracle.vq_forward(lat, m.vq.embedding.weight.detach().numpy())
+        np.testing.assert_array_equal(idx, g["codes"])
+
+
 def test_postprocess_oracle_known_values():
     """The restated mu-law inverse (nnmnkwii's published formula; parity unpinned) at values derivable by hand, its consistency
     with the forward companding of the same library, and the IIR against a direct recurrence."""
