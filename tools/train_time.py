@@ -11,9 +11,10 @@ rs = np.random.RandomState(7); Bt, Tt = 8, 7680
 ti = torch.tensor(rs.randint(0, 256, size=(Bt, Tt)), dtype=torch.long, device=dev)
 tmf = torch.tensor(rs.normal(size=(Bt, 39, Tt // 160)), dtype=torch.float32, device=dev)
 tg = torch.tensor(rs.randint(0, 153, size=(Bt, 1)), dtype=torch.long, device=dev)
-for fused, tf32 in ((True, False), (True, True), (False, False)):
+for fused, tf32, cl in ((True, False, False), (True, False, True), (True, True, True), (True, True, False)):
     tm = bench.build_vqvae(dev).train(); tm.wavenet.precision = "bf16"; tm.wavenet.train_impl = "kernels"
     tm.encoder.train_tf32 = tf32
+    tm.encoder.train_channels_last = cl
     opt = TS.FlatAdam(tm)
     orig = TS.train_step
     TS.train_step = lambda *a, **k: orig(*a, fused_loss=fused, **k)
@@ -24,5 +25,5 @@ for fused, tf32 in ((True, False), (True, True), (False, False)):
     torch.cuda.synchronize(); e0.record()
     for _ in range(20): loss = gs(ti, tmf, tg)
     e1.record(); torch.cuda.synchronize()
-    print(f"fused_loss={fused} encoder_tf32={tf32}: graphed train step {e0.elapsed_time(e1) / 20:.3f} ms, loss {float(loss):.4f}")
+    print(f"fused_loss={fused} encoder_tf32={tf32} channels_last={cl}: graphed train step {e0.elapsed_time(e1) / 20:.3f} ms, loss {float(loss):.4f}")
     del gs, tm, opt

@@ -137,7 +137,18 @@ class Encoder(nn.Module):
         # PyTorch >= 1.7 does by default on Ampere and later; only meaningful next to a bf16 decoder (precision="bf16")
         tf32 = bool(getattr(self, "train_tf32", False)) and self.training and torch.is_grad_enabled()
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=tf32, benchmark=True):
-            out = self.net(x)
+            if getattr(self, "train_channels_last", False) and x.is_cuda and self.training and torch.is_grad_enabled():
+                # experiment switch: the same convolutions as (B, C, 1, T) channels-last 2-D convolutions, so that cuDNN's NHWC
+                # forward / wgrad kernels need no layout conversion around every layer
+                h = x.unsqueeze(2).contiguous(memory_format=torch.channels_last)
+                for m in self.net:
+                    conv = m.conv
+                    y = torch.relu(torch.nn.functional.conv2d(h, conv.weight.unsqueeze(2), conv.bias, stride=(1, conv.stride[0]),
+                                                              padding=(0, conv.padding[0])))
+                    h = y + h if (m.stride == 1 and m.dim_in == m.dim_out) else y
+                out = h.squeeze(2)
+            else:
+                out = self.net(x)
         return self.lin(out.permute(0, 2, 1)).permute(0, 2, 1)
 
 
