@@ -334,6 +334,17 @@ size_t wae_stack_backward_workspace_bf16(const wae_stack_dims* d, int B, int T);
 int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
                             size_t workspace_bytes, void* stream);
 /*
+ * Two-stream variant: the dgrad chain (recompute + gate derivative, input gradients, head, dC, every bias column sum) runs on
+ * `stream`, every weight-gradient GEMM on `wgrad_stream`, ordered behind its producers by events; `stream` never waits for
+ * `wgrad_stream` (one dxo buffer per layer instead of a ping-pong pair: workspace from wae_stack_backward_workspace_bf16_2s).
+ * After the call dc, dx0 and the bias gradients (dgb, dbo, dbs, db3, db4) are complete in `stream` order; dw1, dwo, dws, dw3, dw4
+ * in `wgrad_stream` order -- the caller can go on with whatever needs dc (the upsampler / VQ / encoder backward) while the
+ * weight gradients drain underneath.
+ */
+size_t wae_stack_backward_workspace_bf16_2s(const wae_stack_dims* d, int B, int T);
+int wae_stack_backward_bf16_2s(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
+                               size_t workspace_bytes, void* stream, void* wgrad_stream);
+/*
  * Gradient of the teacher-forced cross-entropy (vqwae_train.py:760-766, mask of ones; the loss itself: wae_nll_sum) written
  * straight into the backward's operand: dY[b][t][o] = (softmax_o(logits[b][:][t]) - [o == target[b][t+shift]]) * g * inv_n for
  * t < T - shift, 0 after; (B,T,O) bf16.  g = *gscale (device scalar: the upstream gradient of the loss) or 1 if NULL.

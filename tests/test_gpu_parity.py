@@ -1073,3 +1073,51 @@ def test_packed_weights_follow_raw_pointer_optimizer_updates():
         fresh.wavenet.precision = prec
         with torch.no_grad():
             assert torch.equal(fresh(x, mfcc, spk)[0], y1), prec
+
+
+def test_two_stream_backward_equals_one_stream():
+    """wae_stack_backward_bf16_2s (weight-gradient GEMMs on a side stream nothing on the caller's stream waits for; the default
+    of the fused-loss training step) against the one-stream call: every parameter gradient of a VQ-WAE step at the 20-layer
+    vqwae decoder shape, equal up to the fp32 red.add order of the split-K wgrads (run-to-run spread of the one-stream call
+    itself is ~1e-8 of the vector; the bound is per tensor)."""
+    import os
+    from wavenet_autoencoders_b200 import train_step as TS
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    rs = np.random.RandomState(5)
+    B, Tn = 2, 1280
+    idx = torch.tensor(rs.randint(0, 256, size=(B, Tn)), dtype=torch.long).cuda()
+    mfcc = torch.tensor(rs.normal(size=(B, 39, Tn // 160)), dtype=torch.float32).cuda()
+    spk = torch.tensor(rs.randint(0, 153, size=(B, 1)), dtype=torch.long).cuda()
+    got = {}
+    old = os.environ.get("WAE_BWD_STREAMS")
+    try:
+        for streams in ("1", "2"):
+            os.environ["WAE_BWD_STREAMS"] = streams
+            torch.manual_seed(0)
+            m = VQVAE(c_in=39, hid=64, K=256, wavenet=WaveNet(**T.VQWAE), encoder_hid=256)
+            m.load_state_dict(T.synth_state_dict(m, 1))
+            m = m.cuda().train()
+            m.wavenet.precision, m.wavenet.train_impl = "bf16", "kernels"
+            opt = TS.FlatAdam(m)
+            opt.step = lambda: None                       # keep the gradients
+            n0 = _lib.launch_count()
+            loss = TS.train_step(m, opt, idx, mfcc, spk)
+            torch.cuda.synchronize()
+            assert _lib.launch_count() > n0
+            got[streams] = (float(loss), opt.flat_g.clone(), opt.offsets, [p.numel() for p in opt.params],
+                            [n for n, p in m.named_parameters() if p.requires_grad])
+    finally:
+        if old is None:
+            os.environ.pop("WAE_BWD_STREAMS", None)
+        else:
+            os.environ["WAE_BWD_STREAMS"] = old
+    (l1, a, offs, sizes, names), (l2, b, _, _, _) = got["1"], got["2"]
+    assert l1 == l2
+    assert float(a.abs().max()) > 0
+    for n, o, k in zip(names, offs, sizes):
+        x, y = a[o:o + k].double(), b[o:o + k].double()
+        if float(x.norm()) == 0.0:
+            assert float(y.norm()) == 0.0, n
+            continue
+        assert float((x - y).norm() / x.norm()) < 1e-4, n

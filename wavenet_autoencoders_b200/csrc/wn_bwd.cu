@@ -560,11 +560,12 @@ namespace {
 
 struct BwdWorkspace {
     __nv_bfloat16 *dY, *dp2, *dS, *dxa, *dxb, *dz;
+    __nv_bfloat16* dxl;          // two-stream variant: one dxo buffer per layer (the wgrad stream may lag behind the dgrad chain)
     float* gb;
     size_t total;
 };
 
-BwdWorkspace carve_bwd(const wae_stack_dims& d, int B, int T, void* base) {
+BwdWorkspace carve_bwd(const wae_stack_dims& d, int B, int T, void* base, bool per_layer_dx = false) {
     BwdWorkspace w;
     const size_t bt = (size_t)B * T;
     const int Hh = (d.G / 2 + 15) / 16 * 16, Gp = 2 * Hh, Op = (d.O + 15) / 16 * 16;
@@ -578,8 +579,21 @@ BwdWorkspace carve_bwd(const wae_stack_dims& d, int B, int T, void* base) {
     w.dxb = reinterpret_cast<__nv_bfloat16*>(take(bt * d.R * 2));
     w.dz = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.layers * bt * Gp * 2));
     w.gb = reinterpret_cast<float*>(take((size_t)d.layers * B * Gp * 4));
+    w.dxl = per_layer_dx ? reinterpret_cast<__nv_bfloat16*>(take((size_t)d.layers * bt * d.R * 2)) : nullptr;
     w.total = off;
     return w;
+}
+
+// events that order the wgrad stream behind the dgrad stream (two-stream variant); disable-timing events, reused round robin
+cudaEvent_t next_fork_event() {
+    static thread_local cudaEvent_t pool[256];
+    static thread_local int made = 0, next = 0;
+    if (made < 256) {
+        if (cudaEventCreateWithFlags(&pool[made], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        return pool[made++];
+    }
+    next = (next + 1) % 256;
+    return pool[next];
 }
 
 }  // namespace
@@ -593,8 +607,27 @@ size_t wae_stack_backward_workspace_bf16(const wae_stack_dims* d, int B, int T) 
     return carve_bwd(*d, B, T, nullptr).total;
 }
 
+size_t wae_stack_backward_workspace_bf16_2s(const wae_stack_dims* d, int B, int T) {
+    if (!d || B <= 0 || T <= 0) return 0;
+    return carve_bwd(*d, B, T, nullptr, true).total;
+}
+
+static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
+                               size_t workspace_bytes, void* stream_, void* wgrad_stream_);
+
 int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
                             size_t workspace_bytes, void* stream_) {
+    return stack_backward_impl(w, bw, dlogits, B, T, workspace, workspace_bytes, stream_, nullptr);
+}
+
+int wae_stack_backward_bf16_2s(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
+                               size_t workspace_bytes, void* stream_, void* wgrad_stream_) {
+    WAE_REQUIRE(wgrad_stream_ != nullptr && wgrad_stream_ != stream_, "wae_stack_backward_bf16_2s: needs a second, different stream");
+    return stack_backward_impl(w, bw, dlogits, B, T, workspace, workspace_bytes, stream_, wgrad_stream_);
+}
+
+static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
+                               size_t workspace_bytes, void* stream_, void* wgrad_stream_) {
     if (int rc = wae::require_sm100()) return rc;
     WAE_REQUIRE(w && bw && (dlogits || bw->dy) && workspace, "wae_stack_backward_bf16: null pointer");
     const wae_stack_dims& d = w->d;
@@ -609,9 +642,22 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
     WAE_REQUIRE(bw->dw1 && bw->dwo && bw->dws && bw->dw3 && bw->dw4 && bw->dgb && bw->dbo && bw->dbs && bw->db3 && bw->db4 && bw->dx0,
                 "wae_stack_backward_bf16: null output pointer");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return wae::set_error(WAE_ERR_ALIGN, "wae_stack_backward_bf16: workspace must be 256-byte aligned");
-    BwdWorkspace ws = carve_bwd(d, B, T, workspace);
+    const bool two = (wgrad_stream_ != nullptr);
+    BwdWorkspace ws = carve_bwd(d, B, T, workspace, two);
     if (workspace_bytes < ws.total) return wae::set_error(WAE_ERR_WORKSPACE, "wae_stack_backward_bf16: workspace %zu < %zu", workspace_bytes, ws.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
+    // two-stream variant: every weight-gradient GEMM goes to `sw`, ordered behind what the dgrad stream has produced so far;
+    // nothing on `st` ever waits for `sw` (per-layer dxo buffers: no buffer a wgrad reads is overwritten later), so the
+    // caller's stream is free again after the dgrad chain and the wgrads drain underneath whatever it runs next
+    cudaStream_t sw = two ? static_cast<cudaStream_t>(wgrad_stream_) : st;
+    auto fork = [&]() -> int {
+        if (!two) return WAE_OK;
+        cudaEvent_t e = next_fork_event();
+        if (e == nullptr) return wae::set_error(WAE_ERR_CUDA, "wae_stack_backward_bf16_2s: cannot create an event");
+        WAE_CHECK_CUDA(cudaEventRecord(e, st));
+        WAE_CHECK_CUDA(cudaStreamWaitEvent(sw, e, 0));
+        return WAE_OK;
+    };
     const uint64_t uT = (uint64_t)T;
 
     // ---- zero the accumulated outputs; gate biases; d logits -> (B,T,O) bf16 ----
@@ -648,6 +694,15 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
     MAP(m_dz, ws.dz, Gp, (uint64_t)L * B, BM);    MAP(m_dz64, ws.dz, Gp, (uint64_t)L * B, WG_KB);
     __nv_bfloat16* dxbuf[2] = {ws.dxa, ws.dxb};
     for (int i = 0; i < 2; ++i) { MAP(m_dx[i], dxbuf[i], R, B, BM); MAP(m_dx64[i], dxbuf[i], R, B, WG_KB); }
+    // two-stream variant: layer l's dxo lives in its own plane dxl[l] (written by layer l+1's input-gradient GEMM)
+    auto set_dx_maps = [&](int l) -> int {
+        if (!two) return WAE_OK;
+        const size_t plane = (size_t)B * T * R;
+        dxbuf[0] = ws.dxl + (size_t)l * plane;                                  // "cur": dxo_l
+        dxbuf[1] = ws.dxl + (size_t)(l > 0 ? l - 1 : 0) * plane;                // "cur ^ 1": dxo_{l-1}
+        for (int i = 0; i < 2; ++i) { MAP(m_dx[i], dxbuf[i], R, B, BM); MAP(m_dx64[i], dxbuf[i], R, B, WG_KB); }
+        return WAE_OK;
+    };
     MAP(m_dx0, bw->dx0, R, B, BM);
     CUtensorMap mw_w4t, mw_w3t, mw_w1, mw_wdh, mw_wdx, mw_wct;
 #define WMAP(m, ptr, K, N, planes, rows) if (int rc = make_tmap3(&(m), (ptr), (K), (N), (planes), (K), (uint64_t)(N) * (K), (rows))) return rc
@@ -684,7 +739,8 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
         WgradArgs a = base_wgrad();
         a.tm_a = m_dY64; a.tm_b[0] = m_r2_64; a.C = bw->dw4; a.ldc = S; a.M = Op;
         add_tile(a, 0, 0, S, 0, 0, 0);
-        if (int rc = launch_wgrad(a, st)) return rc;
+        if (int rc = fork()) return rc;
+        if (int rc = launch_wgrad(a, sw)) return rc;
         if (int rc = launch_colsum(ws.dY, B, T, Op, 0, bw->db4, st)) return rc;
     }
     {   // dp2 = (dY W4) * (r2 > 0)
@@ -697,7 +753,8 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
         WgradArgs a = base_wgrad();
         a.tm_a = m_dp2_64; a.tm_b[0] = m_r1_64; a.C = bw->dw3; a.ldc = S; a.M = S;
         add_tile(a, 0, 0, S, 0, 0, 0);
-        if (int rc = launch_wgrad(a, st)) return rc;
+        if (int rc = fork()) return rc;
+        if (int rc = launch_wgrad(a, sw)) return rc;
         if (int rc = launch_colsum(ws.dp2, B, T, S, 0, bw->db3, st)) return rc;
     }
     {   // dS = (dp2 W3) * (r1 > 0) * sqrt(1/L): gradient of the skip sum, the same for every layer
@@ -718,7 +775,8 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
                 while (nb < 4 && col < total_cols) { a.box[t][nb++] = WBox{0, col % Hp, 0, (col / Hp) * B}; col += 64; }
                 a.nt_nbox[t] = nb; a.nt_ncols[t] = nb * 64;
             }
-            if (int rc = launch_wgrad(a, st)) return rc;
+            if (int rc = fork()) return rc;
+        if (int rc = launch_wgrad(a, sw)) return rc;
         }
         if (int rc = launch_colsum(ws.dS, B, T, S, 0, bw->dbs, st)) return rc;
     }
@@ -729,6 +787,7 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
     for (int l = L - 1; l >= 0; --l) {
         const int dil = d.dilation[l];
         const bool has_dxo = (l < L - 1);
+        if (two) { cur = 0; if (int rc = set_dx_maps(l)) return rc; }
         __nv_bfloat16* dz_l = ws.dz + (size_t)l * B * T * Gp;
         {   // dh = dS Ws_l + dxo Wo_l ;  z = [x taps | c] W1^T + gb ;  dz = gate'(z) dh
             BwdGemmArgs g = base_gemm();
@@ -750,13 +809,15 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
             a.C = bw->dw1 + (size_t)l * Gp * K1p; a.ldc = K1p; a.M = Gp;
             for (int j = 0; j < kw; ++j) add_tile(a, 0, 0, R, -(kw - 1 - j) * dil, l * B, j * R);
             if (C > 0) add_tile(a, 1, 0, Cp, 0, 0, kw * R);
-            if (int rc = launch_wgrad(a, st)) return rc;
+            if (int rc = fork()) return rc;
+        if (int rc = launch_wgrad(a, sw)) return rc;
         }
         if (has_dxo) {   // dWo_l = dxo^T h_l, dbo_l
             WgradArgs a = base_wgrad();
             a.tm_a = m_dx64[cur]; a.tm_b[0] = m_h64; a.C = bw->dwo + (size_t)l * R * Hp; a.ldc = Hp; a.M = R;
             add_tile(a, 0, 0, Hp, 0, l * B, 0);
-            if (int rc = launch_wgrad(a, st)) return rc;
+            if (int rc = fork()) return rc;
+        if (int rc = launch_wgrad(a, sw)) return rc;
             if (int rc = launch_colsum(dxbuf[cur], B, T, R, 0, bw->dbo + (size_t)l * R, st)) return rc;
         }
         {   // d loss / d x_l = dxo_l + sum_j W1_j^T dz[t + (kw-1-j) d];  times sqrt(.5) it is dxo_{l-1}

@@ -194,8 +194,9 @@ class Lanes:
     caller's stream wait for all of them.  Autograd replays each op's backward on the stream of its forward, so the weight-norm
     backward and the gradient accumulation of a layer land on its lane as well.  Same kernels, same results."""
 
-    def __init__(self, device, n=8):
+    def __init__(self, device, n=8, also_wait=()):
         device = torch.device(device)
+        self.also_wait = tuple(also_wait)        # streams every lane additionally waits for at its fork
         self.main = torch.cuda.current_stream(device)
         key = (device.index if device.index is not None else torch.cuda.current_device(), n)
         if key not in _lane_streams:
@@ -207,6 +208,8 @@ class Lanes:
         st = self.side[i % len(self.side)]
         if st not in self.used:
             st.wait_stream(self.main)
+            for other in self.also_wait:
+                st.wait_stream(other)
             self.used.append(st)
         return torch.cuda.stream(st)
 
@@ -214,6 +217,18 @@ class Lanes:
         for st in self.used:
             self.main.wait_stream(st)
         self.used = []
+
+
+_wgrad_streams = {}
+
+
+def wgrad_stream(device):
+    """The side stream the two-stream decoder backward puts its weight-gradient GEMMs on (one per device)."""
+    device = torch.device(device)
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _wgrad_streams:
+        _wgrad_streams[key] = torch.cuda.Stream(device=device)
+    return _wgrad_streams[key]
 
 
 def join_lane_streams_into_current(device):

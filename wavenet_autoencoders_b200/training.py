@@ -53,7 +53,8 @@ def live_weights(wn, lanes=None):
                     _fw(f.conv1x1g) if f.conv1x1g is not None else None,
                     _fw(f.conv1x1_out), f.conv1x1_out.bias, _fw(f.conv1x1_skip), f.conv1x1_skip.bias]
     l1, l3 = wn.last_conv_layers[1], wn.last_conv_layers[3]
-    out += [_fw(wn.first_conv), wn.first_conv.bias, _fw(l1), l1.bias, _fw(l3), l3.bias]
+    with ln.lane(len(wn.conv_layers)):          # on a lane as well: their gradients come from the wgrad stream (two-stream backward)
+        out += [_fw(wn.first_conv), wn.first_conv.bias, _fw(l1), l1.bias, _fw(l3), l3.bias]
     return out
 
 
@@ -156,6 +157,7 @@ class StackTrainFunction(torch.autograd.Function):
         if not hasattr(wn, "_ws_bwd"):
             wn._ws_bwd = packing.WorkspaceCache()
         ctx.pk, ctx.ws_cache = pk, wn._ws_bwd
+        ctx.two_ok = lanes is not None            # the two-stream backward relies on the folds having run on lanes
         ctx.save_for_backward(xf, gf, x_all, h_all, c_cl, r1, r2, *[None if w is None else w.detach() for w in weights])
         return logits
 
@@ -196,7 +198,7 @@ class StackNLLFunction(torch.autograd.Function):
                                                 1.0 / float(B * (T - ctx.shift)), _lib.ptr(dy), _lib.stream_ptr(logits.device)),
                    "wae_train_ce_grad")
         dxin, dc_up, dgvec, grads = _stack_backward_tc(ctx.sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, None, ctx.x_needs_grad,
-                                                       ctx.pk, ctx.ws_cache, dy=dy)
+                                                       ctx.pk, ctx.ws_cache, dy=dy, two_ok=getattr(ctx, "two_ok", False))
         return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, None, None, *grads)
 
 
@@ -221,7 +223,7 @@ def _ru(x, m):
     return (x + m - 1) // m * m
 
 
-def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, dy=None):
+def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, dy=None, two_ok=False):
     """The backward on the tensor cores: pack the transposed weights, one call of wae_stack_backward_bf16, scatter the packed
     fp32 gradients to the parameter shapes.  Same return value as stack_backward."""
     lib = _lib.lib()
@@ -275,10 +277,21 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
         setattr(bw, k, o[k].data_ptr())
     bw.dy = _lib.ptr(dy)                                 # (B,T,O) bf16 from wae_train_ce_grad, or None: transpose-cast dlogits
     dl = None if dy is not None else dlogits.float().contiguous()
-    n = lib.wae_stack_backward_workspace_bf16(pk.struct.d, B, T)
-    ws = ws_cache.get(n, dev) if ws_cache is not None else torch.empty(n, dtype=torch.uint8, device=dev)
-    _lib.check(lib.wae_stack_backward_bf16(pk.struct, bw, _lib.ptr(dl), B, T, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
-               "wae_stack_backward_bf16")
+    # two streams (WAE_BWD_STREAMS=1 turns it off): the weight-gradient GEMMs go to a side stream nothing on this stream waits
+    # for -- this function returns dc / dx0 / bias gradients in stream order, and the upsampler / VQ / encoder backward that
+    # autograd runs next overlaps with the wgrads still draining
+    two = two_ok and os.environ.get("WAE_BWD_STREAMS", "2") != "1" and dev.type == "cuda"
+    sw = packing.wgrad_stream(dev) if two else None
+    if two:
+        n = lib.wae_stack_backward_workspace_bf16_2s(pk.struct.d, B, T)
+        ws = ws_cache.get(n, dev) if ws_cache is not None else torch.empty(n, dtype=torch.uint8, device=dev)
+        _lib.check(lib.wae_stack_backward_bf16_2s(pk.struct, bw, _lib.ptr(dl), B, T, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
+                                                  sw.cuda_stream), "wae_stack_backward_bf16_2s")
+    else:
+        n = lib.wae_stack_backward_workspace_bf16(pk.struct.d, B, T)
+        ws = ws_cache.get(n, dev) if ws_cache is not None else torch.empty(n, dtype=torch.uint8, device=dev)
+        _lib.check(lib.wae_stack_backward_bf16(pk.struct, bw, _lib.ptr(dl), B, T, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
+                   "wae_stack_backward_bf16")
     # ---- scatter to the parameter shapes ----
     grads = [None] * len(weights)
     dw1 = o["dw1"].view(L, Gp, K1p)[:, rows]                                                # (L,G,K1p) natural gate rows
@@ -336,15 +349,25 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
     dc_up = dc[..., :C].transpose(1, 2).contiguous() if C else None
     # the copies that bring permuted views into the parameter shapes: layer l on lane l (the weight-norm backward that consumes
     # them runs there too); joined before returning, autograd assumes this node's outputs live on its own stream
-    lanes = packing.Lanes(dev, int(os.environ.get("WAE_PREP_LANES", "8")) or 1) if dev.type == "cuda" else packing._NoLanes()
+    # Two-stream backward: the tensors that come out of the wgrad stream (dW1, dWc, dWo, dWs, dW3, dW4) are only touched on
+    # lanes that waited for it, and layer l's lane is the stream its weight-norm fold ran on in the forward, i.e. the stream
+    # autograd runs the fold's backward on -- so nothing on THIS stream ever waits for the wgrads.  Bias-like gradients (column
+    # sums, made on this stream) stay here: their accumulators live on this stream.
+    n_l = int(os.environ.get("WAE_PREP_LANES", "8")) or 1
+    lanes = packing.Lanes(dev, n_l, also_wait=(sw,) if two else ()) if dev.type == "cuda" else packing._NoLanes()
     out = []
     for i, (g, w) in enumerate(zip(grads, weights)):
         if g is None or w is None:
             out.append(g)
             continue
-        with lanes.lane(i // PER_LAYER if i < base else 0):
+        weight_like = (i % PER_LAYER in (0, 2, 3, 4, 6)) if i < base else ((i - base) % 2 == 0)      # the weight-normed tensors
+        if weight_like:
+            with lanes.lane(i // PER_LAYER if i < base else L):
+                out.append(g.to(w.dtype).reshape(w.shape))
+        else:
             out.append(g.to(w.dtype).reshape(w.shape))
-    lanes.join()
+    if not two:
+        lanes.join()
     return dxin, dc_up, dgvec, out
 
 
