@@ -97,6 +97,14 @@ int wae_vq_stats(const double* sqerr, const int32_t* counts, int nslices, int K,
  * in: (B*C, Tin), out: (B*C, Tin*s), w: (2s+1) fp32 (weight-norm already folded).
  */
 int wae_upsample_stage(const float* in, int rows, int Tin, int s, const float* w, float* out, void* stream);
+/*
+ * Backward of one stage under autograd (the training step differentiates upsample.py:37-49 through torch's interpolate + Conv2d
+ * in the reference): dy (rows, Tin*s) -> din (rows, Tin) (may be NULL) and dw (2s+1), the gradient of the folded filter.  Same
+ * three-coefficient form as the forward; block partials are added in a fixed order (reproducible bit for bit).  1 <= s <= 128.
+ */
+size_t wae_upsample_stage_backward_workspace(int rows, int s);
+int wae_upsample_stage_backward(const float* dy, const float* in, int rows, int Tin, int s, const float* w, float* din, float* dw,
+                                void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- frame-rate encoder layer ------------------------- */
 /*

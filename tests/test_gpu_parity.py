@@ -1121,3 +1121,39 @@ def test_two_stream_backward_equals_one_stream():
             assert float(y.norm()) == 0.0, n
             continue
         assert float((x - y).norm() / x.norm()) < 1e-4, n
+
+
+@pytest.mark.parametrize("scales,B,C,F", [([4, 4], 3, 16, 7), ([4, 4, 8, 5], 2, 64, 12), ([3, 7], 2, 5, 1)])
+def test_upsampler_training_kernels_match_torch_autograd(scales, B, C, F):
+    """UpsampleNetwork under autograd on the GPU (upsample.UpsampleStageFunction: wae_upsample_stage forward,
+    wae_upsample_stage_backward) against the reference's composite (F.interpolate + weight-normed Conv2d, upsample.py:37-49)
+    differentiated by torch in true fp32: output, d input, d weight_g / d weight_v of every stage; and the kernel gradient is
+    reproducible bit for bit (fixed-order partial sums, no atomics)."""
+    from wavenet_autoencoders_b200.wavenet_vocoder.upsample import UpsampleNetwork
+    torch.manual_seed(4)
+    net = UpsampleNetwork(scales, cin_channels=C).cuda()
+    for p in net.parameters():
+        p.data.mul_(1.0 + 0.3 * torch.randn_like(p))            # away from the constant initial filter
+    x = torch.randn(B, C, F, device="cuda")
+    gy = torch.randn(B, C, F * int(np.prod(scales)), device="cuda")
+    res = {}
+    for impl in ("autograd", "kernels", "kernels"):
+        net.train_impl = impl
+        net.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        n0 = _lib.launch_count()
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            y = net(xi)
+            (y * gy).sum().backward()
+        launched = _lib.launch_count() - n0
+        assert (launched >= 3 * len(scales)) if impl == "kernels" else (launched == 0)
+        cur = (y.detach().clone(), xi.grad.clone(), [p.grad.clone() for p in net.parameters()])
+        if impl in res:
+            for a, b in zip([res[impl][0], res[impl][1]] + res[impl][2], [cur[0], cur[1]] + cur[2]):
+                assert torch.equal(a, b)
+        res[impl] = cur
+    (y0, dx0, dp0), (y1, dx1, dp1) = res["autograd"], res["kernels"]
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) < 1e-5
+    assert rel_err(dx1.cpu().numpy(), dx0.cpu().numpy()) < 1e-5
+    for a, b in zip(dp0, dp1):
+        assert float((a - b).abs().max()) <= 1e-4 * max(float(a.abs().max()), 1e-3), (a.flatten(), b.flatten())   # fp32 sums of up to 4e5 terms in different orders

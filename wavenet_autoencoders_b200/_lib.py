@@ -98,6 +98,9 @@ SIGNATURES = {
                                    C.c_void_p, C.c_void_p]),
     "wae_vq_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_void_p, C.c_void_p]),
     "wae_upsample_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "wae_upsample_stage_backward_workspace": (C.c_size_t, [C.c_int, C.c_int]),
+    "wae_upsample_stage_backward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_size_t, C.c_void_p]),
     "wae_conv1d_relu_res": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "wae_stack_workspace_f32": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),

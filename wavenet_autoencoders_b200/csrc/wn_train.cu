@@ -439,3 +439,113 @@ extern "C" int wae_train_ce_grad(const float* logits, const int64_t* target, int
     WAE_CHECK_LAUNCH();
     return WAE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// backward of one conditioning-upsampler stage (wavenet_vocoder/upsample.py:37-49 under autograd)
+// ---------------------------------------------------------------------------------------------
+// The forward (upsample_stage_kernel, vq_search.cu) is out[f*s+p] = A[p] in[f-1] + B[p] in[f] + C[p] in[f+1] with the partial tap
+// sums A[p] = sum_{j < s-p} w[j], B[p] = sum_{s-p <= j < 2s-p} w[j], C[p] = sum_{j >= 2s-p} w[j].  So
+//   d in[f]  = sum_p B[p] dy[f s + p] + A[p] dy[(f+1) s + p] + C[p] dy[(f-1) s + p]            (3s FMAs per input frame)
+//   dA[p]    = sum_{rows, f} dy[f s + p] in[f-1],  dB, dC alike                                 (3 FMAs per output sample)
+//   d w[j]   = sum_{p < s-j} dA[p] + sum_{s-j <= p < 2s-j} dB[p] + sum_{p >= 2s-j} dC[p]
+// A block owns whole rows; its thread count is a multiple of s, so a thread keeps ONE phase p for every sample it visits and the
+// three running sums live in registers.  Block partials go to `partial[block][3s]`; upsample_dw_kernel adds them in a fixed order
+// (no atomics: the gradient is reproducible bit for bit) and folds them into d w.
+namespace {
+__global__ void __launch_bounds__(256)
+upsample_stage_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ in, int rows, int Tin, int s,
+                          const float* __restrict__ w, float* __restrict__ din, float* __restrict__ partial) {
+    extern __shared__ float ub_sm[];          // coef [3][s], then red [3][blockDim.x]
+    float* coef = ub_sm;
+    float* red = ub_sm + 3 * s;
+    const int nt = blockDim.x, tid = threadIdx.x;
+    for (int p = tid; p < s; p += nt) {
+        float a = 0.f, b = 0.f, c = 0.f;
+        for (int j = 0; j < s - p; ++j) a += __ldg(&w[j]);
+        for (int j = s - p; j < 2 * s - p; ++j) b += __ldg(&w[j]);
+        for (int j = 2 * s - p; j <= 2 * s; ++j) c += __ldg(&w[j]);
+        coef[p] = a; coef[s + p] = b; coef[2 * s + p] = c;
+    }
+    __syncthreads();
+    const int Tout = Tin * s;
+    const int p = tid % s, f0 = tid / s, Q = nt / s;
+    float sa = 0.f, sb = 0.f, sc = 0.f;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        const float* src = in + (size_t)r * Tin;
+        const float* g = dy + (size_t)r * Tout;
+        for (int f = f0; f < Tin; f += Q) {
+            const float gy = __ldg(&g[f * s + p]);
+            const float xm = (f > 0) ? __ldg(&src[f - 1]) : 0.f;
+            const float xp = (f + 1 < Tin) ? __ldg(&src[f + 1]) : 0.f;
+            sa = fmaf(gy, xm, sa);
+            sb = fmaf(gy, __ldg(&src[f]), sb);
+            sc = fmaf(gy, xp, sc);
+        }
+        if (din != nullptr) {
+            float* dst = din + (size_t)r * Tin;
+            for (int f = tid; f < Tin; f += nt) {
+                float acc = 0.f;
+                const float* g0 = g + (size_t)f * s;
+                for (int q = 0; q < s; ++q) acc = fmaf(coef[s + q], __ldg(&g0[q]), acc);
+                if (f + 1 < Tin) for (int q = 0; q < s; ++q) acc = fmaf(coef[q], __ldg(&g0[s + q]), acc);
+                if (f > 0) for (int q = 0; q < s; ++q) acc = fmaf(coef[2 * s + q], __ldg(&g0[q - s]), acc);
+                dst[f] = acc;
+            }
+        }
+    }
+    red[tid] = sa; red[nt + tid] = sb; red[2 * nt + tid] = sc;
+    __syncthreads();
+    for (int v = tid; v < 3 * s; v += nt) {
+        const int k = v / s, pp = v - k * s;
+        float acc = 0.f;
+        for (int q = 0; q < Q; ++q) acc += red[k * nt + q * s + pp];
+        partial[(size_t)blockIdx.x * 3 * s + v] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+upsample_dw_kernel(const float* __restrict__ partial, int nblocks, int s, float* __restrict__ dw) {
+    extern __shared__ float dcoef[];          // [3][s]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int v = warp; v < 3 * s; v += nw) {
+        float acc = 0.f;
+        for (int b = lane; b < nblocks; b += 32) acc += partial[(size_t)b * 3 * s + v];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) dcoef[v] = acc;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j <= 2 * s; j += blockDim.x) {
+        float acc = 0.f;
+        for (int p = 0; p < s; ++p) {
+            const int k = (j < s - p) ? 0 : (j < 2 * s - p ? 1 : 2);
+            acc += dcoef[k * s + p];
+        }
+        dw[j] = acc;
+    }
+}
+}  // namespace
+
+extern "C" size_t wae_upsample_stage_backward_workspace(int rows, int s) {
+    if (rows <= 0 || s <= 0) return 0;
+    const int nb = rows < 592 ? rows : 592;
+    return (size_t)nb * 3 * s * sizeof(float);
+}
+
+extern "C" int wae_upsample_stage_backward(const float* dy, const float* in, int rows, int Tin, int s, const float* w, float* din, float* dw,
+                                           void* workspace, size_t workspace_bytes, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(dy && in && w && dw && workspace, "wae_upsample_stage_backward: null pointer");
+    WAE_REQUIRE(rows > 0 && Tin > 0 && s >= 1 && s <= 128, "wae_upsample_stage_backward: need rows, Tin > 0 and 1 <= s <= 128 (rows=%d Tin=%d s=%d)", rows, Tin, s);
+    WAE_REQUIRE((long long)Tin * s < (1ll << 31), "wae_upsample_stage_backward: sizes too large");
+    const int nb = rows < 592 ? rows : 592;                      // 4 resident blocks per SM
+    if (workspace_bytes < (size_t)nb * 3 * s * sizeof(float)) return wae::set_error(WAE_ERR_WORKSPACE, "wae_upsample_stage_backward: workspace too small");
+    const int nt = (256 / s) * s;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    upsample_stage_bwd_kernel<<<(unsigned)nb, (unsigned)nt, (size_t)(3 * s + 3 * nt) * sizeof(float), st>>>(
+        dy, in, rows, Tin, s, w, din, static_cast<float*>(workspace));
+    WAE_CHECK_LAUNCH();
+    upsample_dw_kernel<<<1, 256, (size_t)3 * s * sizeof(float), st>>>(static_cast<const float*>(workspace), nb, s, dw);
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}

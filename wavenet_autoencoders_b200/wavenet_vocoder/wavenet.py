@@ -163,6 +163,14 @@ class WaveNet(nn.Module):
                                 "(no CPU fallback)")
 
     # ------------------------------------------------------------------ teacher-forced forward
+    def _upsample(self, c):
+        """The conditioning upsampler; under autograd its stages follow this model's ``train_impl`` ("kernels":
+        upsample.UpsampleStageFunction, "autograd": the torch composite of the reference)."""
+        inner = getattr(self.upsample_net, "upsample", self.upsample_net)
+        if isinstance(inner, upsample.UpsampleNetwork):
+            inner.train_impl = self.train_impl
+        return self.upsample_net(c)
+
     def forward(self, x, c=None, g=None, softmax=False):
         """x (B,O,T) one-hot / (B,1,T) scalar; c (B,C,Tc); g ids or (B,Gi[,1])  ->  (B,O,T) (wavenet.py:164-216).
         Additive: x may also be the (B,T) integer mu-law classes themselves (what the one-hot tensor is built from); the
@@ -202,7 +210,7 @@ class WaveNet(nn.Module):
                     c, up_w, up_s = deferred
                     last_stage = (up_w, up_s)
             if last_stage is None:
-                c = self.upsample_net(c)
+                c = self._upsample(c)
             if c.size(-1) * (last_stage[1] if last_stage else 1) != x.size(-1):
                 print(f"c {c.size() } x {x.size()}")
                 raise Exception
@@ -253,7 +261,7 @@ class WaveNet(nn.Module):
         B = x.size(0)
         gvec = self._speaker_vectors(g, B)
         if c is not None and self.upsample_net is not None:
-            c = self.upsample_net(c)
+            c = self._upsample(c)
             if c.size(-1) != x.size(-1):
                 print(f"c {c.size() } x {x.size()}")
                 raise Exception
