@@ -119,6 +119,24 @@ int wae_conv1d_relu_res(const float* x, const float* w, const float* bias, int B
  * dozen 64 x 64 tiles with a long serial reduction); `partial` holds splits x B x Cout x Tout floats, summed in a fixed order by
  * a second launch that also applies bias / ReLU / residual. */
 
+/*
+ * The same layer under autograd (the training step, vqwae_train.py:752-782, differentiates vqvae_model.py:9-21, :46-51): the
+ * parameters are read in their OWN layout (w = conv weight (Cout, Cin, k) / Linear weight (Cout, Cin)), because they change every
+ * step and a transposed copy per step would cost more than the strided reads of a few hundred KB.
+ *   forward_train    out as wae_conv1d_relu_res; relu_out (may be NULL) receives relu(conv + bias) before the residual add --
+ *                    the backward's ReLU mask
+ *   backward_input   dx (B, Cin, T) = conv_transpose(g * [r > 0], w) [+ g if residual]; g, r (B, Cout, Tout); r == NULL: no ReLU
+ *   backward_weight  dw (Cout, Cin, k) = sum_{b,u} (g * [r > 0])[b][co][u] x[b][ci][u stride + j - k/2], db (Cout, may be NULL)
+ *                    the column sums; partial: B * Cout * (Cin k + 1) floats, added over the utterances in a fixed order
+ * fp32 FMA chains, no atomics: reproducible bit for bit.
+ */
+int wae_enc_layer_forward_train(const float* x, const float* w, const float* bias, int B, int Cin, int T, int Cout, int k, int stride, int relu,
+                                int residual, float* out, float* relu_out, int splits, float* partial, void* stream);
+int wae_enc_layer_backward_input(const float* g, const float* r, const float* w, int B, int Cin, int T, int Cout, int k, int stride,
+                                 int residual, float* dx, int splits, float* partial, void* stream);
+int wae_enc_layer_backward_weight(const float* g, const float* r, const float* x, int B, int Cin, int T, int Cout, int k, int stride, float* dw,
+                                  float* db, float* partial, void* stream);
+
 /* ---- encoder + Linear + VQ search in one launch ------- */
 /*
  * The inference-time encoder of vqvae_model.py:25-51 (ConvReLURes blocks, then Linear hid -> D) followed by the nearest-codeword

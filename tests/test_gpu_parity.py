@@ -1157,3 +1157,49 @@ def test_upsampler_training_kernels_match_torch_autograd(scales, B, C, F):
     assert rel_err(dx1.cpu().numpy(), dx0.cpu().numpy()) < 1e-5
     for a, b in zip(dp0, dp1):
         assert float((a - b).abs().max()) <= 1e-4 * max(float(a.abs().max()), 1e-3), (a.flatten(), b.flatten())   # fp32 sums of up to 4e5 terms in different orders
+
+
+@pytest.mark.parametrize("hid,c_in,c_out,B,F", [(64, 13, 16, 3, 37), (256, 39, 64, 8, 48), (96, 7, 8, 1, 5)])
+def test_encoder_training_kernels_match_torch_autograd(hid, c_in, c_out, B, F):
+    """Encoder under autograd on the GPU (vqvae_model.EncoderTrainFunction: wae_enc_layer_forward_train / _backward_input /
+    _backward_weight) against the same torch modules differentiated by autograd in float64 on the CPU (the reference's
+    vqvae_model.py:9-51 arithmetic without any library's algorithm choice in between): latents, d input and the gradient of every
+    weight and bias (odd and even frame counts through the stride-2 blocks); the kernel path is reproducible bit for bit.  The
+    cuDNN fp32 path of the same modules on the GPU is printed beside it for scale."""
+    import copy
+    from wavenet_autoencoders_b200.vqvae_model import Encoder
+    torch.manual_seed(8)
+    enc = Encoder(hid=hid, c_in=c_in, c_out=c_out).cuda().train()
+    x = torch.randn(B, c_in, F, device="cuda")
+    gy = torch.randn(B, c_out, enc.out_frames(F), device="cuda")
+    ref = copy.deepcopy(enc).cpu().double()
+    xr = x.cpu().double().requires_grad_(True)
+    (ref(xr) * gy.cpu().double()).sum().backward()
+    with torch.no_grad():
+        want = [ref(xr).detach(), xr.grad] + [p.grad for p in ref.parameters()]
+    res = {}
+    for impl in ("autograd", "kernels", "kernels"):
+        enc.train_impl = impl
+        enc.zero_grad(set_to_none=True)
+        xi = x.clone().requires_grad_(True)
+        n0 = _lib.launch_count()
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            y = enc(xi)
+            (y * gy).sum().backward()
+        launched = _lib.launch_count() - n0
+        assert (launched >= 3 * 11) if impl == "kernels" else (launched == 0), launched
+        cur = [y.detach().clone(), xi.grad.clone()] + [p.grad.clone() for p in enc.parameters()]
+        if impl in res:
+            for a, b in zip(res[impl], cur):
+                assert torch.equal(a, b)
+        res[impl] = cur
+    names = ["latents", "d input"] + [n for n, _ in enc.named_parameters()]
+    errs = {}
+    for impl in ("kernels", "autograd"):
+        for n, a, b in zip(names, want, res[impl]):
+            assert a.shape == b.shape, n
+            errs[impl, n] = float((a - b.cpu().double()).norm() / max(float(a.norm()), 1e-20))
+    print("relative L2 error vs float64, kernels (cuDNN fp32 in brackets):",
+          " ".join(f"{n}={errs['kernels', n]:.1e}({errs['autograd', n]:.1e})" for n in names))
+    worst = max(((n, errs["kernels", n]) for n in names), key=lambda kv: kv[1])
+    assert worst[1] < 5e-6, worst

@@ -582,7 +582,8 @@ constexpr int EG_M = 64, EG_N = 64, EG_K = 32, EG_THREADS = 512;
 __global__ void __launch_bounds__(EG_THREADS)
 enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Cin*k][Cout] */, const float* __restrict__ bias, int Cin,
                 int T, int Cout, int k, int s, int Tout, int N, int relu, int residual, float* __restrict__ out, int k_per_split,
-                float* __restrict__ partial) {
+                float* __restrict__ partial, const float* __restrict__ mask = nullptr, int wmode = 0, int in_dil = 1,
+                float* __restrict__ relu_out = nullptr) {
     __shared__ __align__(16) float As[2][EG_K][EG_M];
     __shared__ __align__(16) float Bs[2][EG_K][EG_N];
     const int tid = threadIdx.x;
@@ -609,19 +610,40 @@ enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Ci
         rb[0] = rb[1] = rb[2] = rb[3] = 0.f;
         if (kidx < K) {
             const int co = co0 + fc;
-            const float* wr = wt + (size_t)kidx * Cout + co;
-            if (a_vec && co + 3 < Cout) ra = __ldg(reinterpret_cast<const float4*>(wr));
-            else {
-                if (co < Cout) ra.x = __ldg(wr);
-                if (co + 1 < Cout) ra.y = __ldg(wr + 1);
-                if (co + 2 < Cout) ra.z = __ldg(wr + 2);
-                if (co + 3 < Cout) ra.w = __ldg(wr + 3);
-            }
             const int ci = kidx / k, kk = kidx - ci * k;
+            if (wmode == 0) {
+                const float* wr = wt + (size_t)kidx * Cout + co;
+                if (a_vec && co + 3 < Cout) ra = __ldg(reinterpret_cast<const float4*>(wr));
+                else {
+                    if (co < Cout) ra.x = __ldg(wr);
+                    if (co + 1 < Cout) ra.y = __ldg(wr + 1);
+                    if (co + 2 < Cout) ra.z = __ldg(wr + 2);
+                    if (co + 3 < Cout) ra.w = __ldg(wr + 3);
+                }
+            } else {
+                // the parameter in its own layout, no transposed copy (training: the weights change every step).
+                // wmode 1: forward, wt = (Cout, Cin, k);  wmode 2: input gradient of that conv -- this launch's input channels
+                // are its output channels and the taps run backwards: wt = (Cin_here, Cout_here, k) read at tap k-1-kk
+                const size_t cstride = (wmode == 1) ? (size_t)Cin * k : (size_t)k;
+                const float* wr = (wmode == 1) ? wt + ((size_t)co * Cin + ci) * k + kk : wt + ((size_t)ci * Cout + co) * k + (k - 1 - kk);
+                if (co < Cout) ra.x = __ldg(wr);
+                if (co + 1 < Cout) ra.y = __ldg(wr + cstride);
+                if (co + 2 < Cout) ra.z = __ldg(wr + 2 * cstride);
+                if (co + 3 < Cout) ra.w = __ldg(wr + 3 * cstride);
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int t = ft[j] * s + kk - pad;
-                if (fb[j] >= 0 && t >= 0 && t < T) rb[j] = __ldg(&x[((size_t)fb[j] * Cin + ci) * T + t]);
+                int t = ft[j] * s + kk - pad;
+                if (in_dil > 1) {                     // input gradient of a strided conv: only every in_dil-th position holds a value
+                    if (t < 0 || (t % in_dil) != 0) continue;
+                    t /= in_dil;
+                }
+                if (fb[j] >= 0 && t >= 0 && t < T) {
+                    const size_t a = ((size_t)fb[j] * Cin + ci) * T + t;
+                    float v = __ldg(&x[a]);
+                    if (mask != nullptr && !(__ldg(&mask[a]) > 0.f)) v = 0.f;           // ReLU mask of the forward output
+                    rb[j] = v;
+                }
             }
         }
     };
@@ -671,6 +693,7 @@ enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Ci
             }
             float v = acc[i][j] + (bias ? __ldg(&bias[co]) : 0.f);
             if (relu) v = fmaxf(v, 0.f);
+            if (relu_out != nullptr) relu_out[((size_t)ob * Cout + co) * Tout + ot] = v;   // training: the ReLU output is the backward's mask
             if (residual) v += __ldg(&x[((size_t)ob * Cin + co) * T + ot]);            // stride 1, Cin == Cout: same indexing
             out[((size_t)ob * Cout + co) * Tout + ot] = v;
         }
@@ -679,7 +702,7 @@ enc_conv_kernel(const float* __restrict__ x, const float* __restrict__ wt /* [Ci
 // second pass of a split-K layer: sum the partial planes in a fixed order, then bias / ReLU / residual
 __global__ void __launch_bounds__(256)
 enc_reduce_kernel(const float* __restrict__ partial, int splits, const float* __restrict__ x, const float* __restrict__ bias, int Cin, int T,
-                  int Cout, int Tout, long long total, int relu, int residual, float* __restrict__ out) {
+                  int Cout, int Tout, long long total, int relu, int residual, float* __restrict__ out, float* __restrict__ relu_out = nullptr) {
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         float v = 0.f;
         for (int z = 0; z < splits; ++z) v += __ldg(&partial[(size_t)z * total + e]);
@@ -689,8 +712,94 @@ enc_reduce_kernel(const float* __restrict__ partial, int splits, const float* __
         const long long b = r / Cout;
         v += bias ? __ldg(&bias[co]) : 0.f;
         if (relu) v = fmaxf(v, 0.f);
+        if (relu_out != nullptr) relu_out[e] = v;
         if (residual) v += __ldg(&x[((size_t)b * Cin + co) * T + t]);
         out[e] = v;
+    }
+}
+
+// Weight and bias gradient of one encoder layer (training): with dr = g * [r > 0] (g the gradient of the layer's pre-residual
+// output, r the forward's ReLU output; mask == nullptr: dr = g, the final Linear),
+//   dw[co][ci][j] = sum_{b,u} dr[b][co][u] x[b][ci][u s + j - pad],   db[co] = sum_{b,u} dr[b][co][u]
+// as one SGEMM C[co][n] over n = (ci, j) plus one extra column of ones for the bias, 64 x 64 tiles, reduction over the frames
+// of ONE utterance per block (blockIdx.z = b); enc_wgrad_reduce_kernel adds the per-utterance planes in a fixed order and writes
+// dw in the parameter's own (Cout, Cin, k) layout.  Both operands have the frame index contiguous in memory; a block gathers
+// 32 frames x 64 rows per step (lanes along the rows: strided global reads of a few hundred KB that live in L2, conflict-free
+// shared-memory stores).
+__global__ void __launch_bounds__(EG_THREADS)
+enc_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ mask, const float* __restrict__ x, int Cout, int Tout, int Cin, int T,
+                 int k, int s, float* __restrict__ partial /* [B][Cout][Cin*k + 1] */) {
+    __shared__ __align__(16) float As[EG_K][EG_M];
+    __shared__ __align__(16) float Bs[EG_K][EG_N];
+    const int tid = threadIdx.x;
+    const int tx = tid & 31, ty = tid >> 5;
+    const int fm = tid & 63, fk = (tid >> 6) * 4;     // fetch: row fm of the tile, frames fk .. fk+3 of the chunk
+    const int co0 = blockIdx.y * EG_M, n0 = blockIdx.x * EG_N, b = blockIdx.z;
+    const int NW = Cin * k + 1, pad = k / 2;
+    const int co_f = co0 + fm, n_f = n0 + fm;
+    const int ci_f = n_f / k, j_f = n_f - ci_f * k;
+    const float* grow = g + ((size_t)b * Cout + co_f) * Tout;
+    const float* mrow = mask ? mask + ((size_t)b * Cout + co_f) * Tout : nullptr;
+    const float* xrow = x + ((size_t)b * Cin + ci_f) * T;
+    float acc[4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
+    for (int u0 = 0; u0 < Tout; u0 += EG_K) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int u = u0 + fk + i;
+            float a = 0.f, bv = 0.f;
+            if (u < Tout) {
+                if (co_f < Cout) {
+                    a = __ldg(&grow[u]);
+                    if (mrow != nullptr && !(__ldg(&mrow[u]) > 0.f)) a = 0.f;
+                }
+                if (n_f == NW - 1) bv = 1.f;
+                else if (n_f < NW - 1) {
+                    const int t = u * s + j_f - pad;
+                    if (t >= 0 && t < T) bv = __ldg(&xrow[t]);
+                }
+            }
+            As[fk + i][fm] = a;
+            Bs[fk + i][fm] = bv;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < EG_K; ++kk) {
+            const float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+            const float2 bb = *reinterpret_cast<const float2*>(&Bs[kk][tx * 2]);
+            const float a4[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][0] = fmaf(a4[i], bb.x, acc[i][0]);
+                acc[i][1] = fmaf(a4[i], bb.y, acc[i][1]);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int co = co0 + ty * 4 + i;
+        if (co >= Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = n0 + tx * 2 + j;
+            if (n < NW) partial[((size_t)b * Cout + co) * NW + n] = acc[i][j];
+        }
+    }
+}
+__global__ void __launch_bounds__(256)
+enc_wgrad_reduce_kernel(const float* __restrict__ partial, int B, int Cout, int NW, float* __restrict__ dw, float* __restrict__ db) {
+    const long long total = (long long)Cout * NW;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        float v = 0.f;
+        for (int b = 0; b < B; ++b) v += __ldg(&partial[(size_t)b * total + e]);
+        const int co = (int)(e / NW), n = (int)(e - (long long)co * NW);
+        if (n == NW - 1) {
+            if (db != nullptr) db[co] = v;
+        } else {
+            dw[(size_t)co * (NW - 1) + n] = v;
+        }
     }
 }
 }  // namespace
@@ -723,6 +832,91 @@ extern "C" int wae_conv1d_relu_res(const float* x, const float* w, const float* 
         enc_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, splits, x, bias, Cin, T, Cout, Tout, total, relu, residual, out);
         WAE_CHECK_LAUNCH();
     }
+    return WAE_OK;
+}
+
+// Training-side entry points of the encoder layers (vqvae_model.py:9-21, :46-51 under autograd): the same SGEMM kernel reading the
+// parameters in their own layout, the ReLU output kept for the backward, and the two gradients.
+extern "C" int wae_enc_layer_forward_train(const float* x, const float* w /* (Cout, Cin, k) */, const float* bias, int B, int Cin, int T, int Cout,
+                                           int k, int stride, int relu, int residual, float* out, float* relu_out, int splits, float* partial,
+                                           void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(x && w && out, "wae_enc_layer_forward_train: null pointer");
+    WAE_REQUIRE(B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && T > 0, "wae_enc_layer_forward_train: bad sizes");
+    WAE_REQUIRE((k & 1) == 1 && k >= 1 && stride >= 1, "wae_enc_layer_forward_train: odd k, stride >= 1 (k=%d stride=%d)", k, stride);
+    WAE_REQUIRE(!residual || (stride == 1 && Cin == Cout), "wae_enc_layer_forward_train: the residual needs stride 1 and Cin == Cout");
+    WAE_REQUIRE(splits >= 1 && splits <= 64 && (splits == 1 || partial != nullptr), "wae_enc_layer_forward_train: splits=%d needs a partial-sum buffer", splits);
+    const int Tout = (T - 1) / stride + 1;
+    const long long N = (long long)B * Tout;
+    WAE_REQUIRE(N < (1ll << 31) && (long long)Cin * k < (1ll << 31), "wae_enc_layer_forward_train: sizes too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int K = Cin * k, chunks = (K + EG_K - 1) / EG_K;
+    if (splits > chunks) splits = chunks;
+    const int k_per_split = (chunks + splits - 1) / splits * EG_K;
+    splits = (K + k_per_split - 1) / k_per_split;
+    enc_conv_kernel<<<dim3((unsigned)((N + EG_N - 1) / EG_N), (Cout + EG_M - 1) / EG_M, splits), EG_THREADS, 0, st>>>(
+        x, w, bias, Cin, T, Cout, k, stride, Tout, (int)N, relu, residual, out, k_per_split, splits > 1 ? partial : nullptr, nullptr, 1, 1, relu_out);
+    WAE_CHECK_LAUNCH();
+    if (splits > 1) {
+        const long long total = N * Cout;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        enc_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, splits, x, bias, Cin, T, Cout, Tout, total, relu, residual, out, relu_out);
+        WAE_CHECK_LAUNCH();
+    }
+    return WAE_OK;
+}
+
+// dx (B, Cin, T) = conv_transpose(g * [r > 0], w) [+ g]: the input gradient of out = relu(conv(x, w)) [+ x].  g, r: (B, Cout, Tout)
+// with Tout = (T-1)/stride + 1; r == NULL: no ReLU (the final Linear).
+extern "C" int wae_enc_layer_backward_input(const float* g, const float* r, const float* w /* (Cout, Cin, k) */, int B, int Cin, int T, int Cout,
+                                            int k, int stride, int residual, float* dx, int splits, float* partial, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(g && w && dx, "wae_enc_layer_backward_input: null pointer");
+    WAE_REQUIRE(B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && T > 0, "wae_enc_layer_backward_input: bad sizes");
+    WAE_REQUIRE((k & 1) == 1 && k >= 1 && stride >= 1, "wae_enc_layer_backward_input: odd k, stride >= 1 (k=%d stride=%d)", k, stride);
+    WAE_REQUIRE(!residual || (stride == 1 && Cin == Cout), "wae_enc_layer_backward_input: the residual needs stride 1 and Cin == Cout");
+    WAE_REQUIRE(splits >= 1 && splits <= 64 && (splits == 1 || partial != nullptr), "wae_enc_layer_backward_input: splits=%d needs a partial-sum buffer", splits);
+    const int Tg = (T - 1) / stride + 1;                    // frames of g
+    const long long N = (long long)B * T;
+    WAE_REQUIRE(N < (1ll << 31) && (long long)Cout * k < (1ll << 31), "wae_enc_layer_backward_input: sizes too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // as a convolution: input channels = Cout, output channels = Cin, output frames = T, taps reversed, input dilated by the stride
+    const int K = Cout * k, chunks = (K + EG_K - 1) / EG_K;
+    if (splits > chunks) splits = chunks;
+    const int k_per_split = (chunks + splits - 1) / splits * EG_K;
+    splits = (K + k_per_split - 1) / k_per_split;
+    enc_conv_kernel<<<dim3((unsigned)((N + EG_N - 1) / EG_N), (Cin + EG_M - 1) / EG_M, splits), EG_THREADS, 0, st>>>(
+        g, w, nullptr, Cout, Tg, Cin, k, 1, T, (int)N, 0, residual, dx, k_per_split, splits > 1 ? partial : nullptr, r, 2, stride, nullptr);
+    WAE_CHECK_LAUNCH();
+    if (splits > 1) {
+        const long long total = N * Cin;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        enc_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, splits, g, nullptr, Cout, Tg, Cin, T, total, 0, residual, dx, nullptr);
+        WAE_CHECK_LAUNCH();
+    }
+    return WAE_OK;
+}
+
+// dw (Cout, Cin, k), db (Cout, may be NULL) of the same layer; partial: B * Cout * (Cin*k + 1) floats.
+extern "C" int wae_enc_layer_backward_weight(const float* g, const float* r, const float* x, int B, int Cin, int T, int Cout, int k, int stride,
+                                             float* dw, float* db, float* partial, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(g && x && dw && partial, "wae_enc_layer_backward_weight: null pointer");
+    WAE_REQUIRE(B > 0 && B <= 65535 && Cin > 0 && Cout > 0 && T > 0, "wae_enc_layer_backward_weight: bad sizes");
+    WAE_REQUIRE((k & 1) == 1 && k >= 1 && stride >= 1, "wae_enc_layer_backward_weight: odd k, stride >= 1 (k=%d stride=%d)", k, stride);
+    const int Tout = (T - 1) / stride + 1, NW = Cin * k + 1;
+    WAE_REQUIRE((long long)Cout * NW < (1ll << 31) && (Cout + EG_M - 1) / EG_M <= 65535, "wae_enc_layer_backward_weight: sizes too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    enc_wgrad_kernel<<<dim3((unsigned)((NW + EG_N - 1) / EG_N), (unsigned)((Cout + EG_M - 1) / EG_M), (unsigned)B), EG_THREADS, 0, st>>>(
+        g, r, x, Cout, Tout, Cin, T, k, stride, partial);
+    WAE_CHECK_LAUNCH();
+    const long long total = (long long)Cout * NW;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    enc_wgrad_reduce_kernel<<<(unsigned)blocks, 256, 0, st>>>(partial, B, Cout, NW, dw, db);
+    WAE_CHECK_LAUNCH();
     return WAE_OK;
 }
 

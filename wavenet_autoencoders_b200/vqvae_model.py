@@ -24,6 +24,82 @@ class ConvReLURes(nn.Module):
         return out
 
 
+def _enc_splits(B, cin, cout, k, Tout):
+    """Split-K factor of one encoder-layer launch: a layer is a few dozen 64 x 64 output tiles with a serial reduction of
+    cin*k/32 chunks (~1.9 us each) -- cut the reduction into slices until there are enough blocks for the GPU or a slice is only
+    4 chunks long."""
+    tiles = -(-(B * Tout) // 64) * -(-cout // 64)
+    chunks = -(-(cin * k) // 32)
+    return max(1, min(chunks // 4, -(-148 // tiles), 8))
+
+
+class EncoderTrainFunction(torch.autograd.Function):
+    """The encoder (ConvReLURes blocks + Linear, vqvae_model.py:9-51) under autograd on this library's kernels: per layer
+    wae_enc_layer_forward_train, then wae_enc_layer_backward_weight / wae_enc_layer_backward_input in the backward -- fp32 FMA
+    SGEMMs reading the parameters in place, the ReLU output kept as the mask.  The reference's training step runs these frame-rate
+    convolutions through cuDNN (43 us per layer forward at 8 x 48 frames; here ~10)."""
+
+    @staticmethod
+    def forward(ctx, enc, x, *params):
+        from . import _lib
+        lib, st = _lib.lib(), _lib.stream_ptr(x.device)
+        specs = enc.layer_specs()
+        cur = x.detach().float().contiguous()
+        B = cur.shape[0]
+        ins, rs = [], []
+        for i, (cin, cout, k, s, relu, res) in enumerate(specs):
+            w, b = params[2 * i], params[2 * i + 1]
+            T = cur.shape[-1]
+            Tout = (T - 1) // s + 1
+            out = torch.empty(B, cout, Tout, dtype=torch.float32, device=cur.device)
+            r = torch.empty_like(out) if relu else None
+            splits = _enc_splits(B, cin, cout, k, Tout)
+            part = torch.empty(splits * out.numel(), dtype=torch.float32, device=cur.device) if splits > 1 else None
+            _lib.check(lib.wae_enc_layer_forward_train(_lib.ptr(cur), _lib.ptr(w.detach()), _lib.ptr(None if b is None else b.detach()), B, cin,
+                                                       T, cout, k, s, relu, res, _lib.ptr(out), _lib.ptr(r), splits, _lib.ptr(part), st),
+                       "wae_enc_layer_forward_train")
+            ins.append(cur)
+            rs.append(r)
+            cur = out
+        ctx.specs, ctx.n = specs, len(specs)
+        ctx.has_r = [r is not None for r in rs]
+        ctx.save_for_backward(*ins, *[r for r in rs if r is not None], *[p.detach() if p is not None else None for p in params])
+        return cur
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import _lib
+        lib, st = _lib.lib(), _lib.stream_ptr(g.device)
+        n, saved = ctx.n, ctx.saved_tensors
+        ins = saved[:n]
+        r_list = list(saved[n:n + sum(ctx.has_r)])
+        params = saved[n + sum(ctx.has_r):]
+        rs = [r_list.pop(0) if h else None for h in ctx.has_r]
+        grads = [None] * (2 * n)
+        g = g.contiguous().float()
+        B = g.shape[0]
+        dx = None
+        for i in range(n - 1, -1, -1):
+            cin, cout, k, s, relu, res = ctx.specs[i]
+            w, b, x, r = params[2 * i], params[2 * i + 1], ins[i], rs[i]
+            T = x.shape[-1]
+            dw = torch.empty_like(w, dtype=torch.float32)
+            db = torch.empty(cout, dtype=torch.float32, device=g.device) if b is not None else None
+            part = torch.empty(B * cout * (cin * k + 1), dtype=torch.float32, device=g.device)
+            _lib.check(lib.wae_enc_layer_backward_weight(_lib.ptr(g), _lib.ptr(r), _lib.ptr(x), B, cin, T, cout, k, s, _lib.ptr(dw),
+                                                         _lib.ptr(db), _lib.ptr(part), st), "wae_enc_layer_backward_weight")
+            grads[2 * i], grads[2 * i + 1] = dw, db
+            if i == 0 and not ctx.needs_input_grad[1]:
+                break
+            dx = torch.empty_like(x)
+            splits = _enc_splits(B, cout, cin, k, T)
+            part = torch.empty(splits * dx.numel(), dtype=torch.float32, device=g.device) if splits > 1 else None
+            _lib.check(lib.wae_enc_layer_backward_input(_lib.ptr(g), _lib.ptr(r), _lib.ptr(w), B, cin, T, cout, k, s, res, _lib.ptr(dx),
+                                                        splits, _lib.ptr(part), st), "wae_enc_layer_backward_input")
+            g = dx
+        return (None, dx if ctx.needs_input_grad[1] else None, *grads)
+
+
 class Encoder(nn.Module):
     def __init__(self, hid=768, c_in=39, c_out=64):
         super().__init__()
@@ -68,6 +144,19 @@ class Encoder(nn.Module):
         w, b = self._wt(self.lin.weight), self.lin.bias.detach().float().contiguous()
         run(cur, w, b, self.lin.in_features, T, self.lin.out_features, 1, 1, 0, 0, out)
         return out
+
+    def layer_specs(self):
+        """[(cin, cout, k, stride, relu, residual)] of the ConvReLURes blocks and the final Linear (a k = 1 layer without ReLU)."""
+        specs = [(m.dim_in, m.dim_out, m.conv.kernel_size[0], m.conv.stride[0], 1, int(m.stride == 1 and m.dim_in == m.dim_out))
+                 for m in self.net]
+        return specs + [(self.lin.in_features, self.lin.out_features, 1, 1, 0, 0)]
+
+    def _train_kernels_ok(self, x):
+        """Differentiable kernel path (``train_impl`` = "kernels", the default on CUDA; "autograd": torch modules / cuDNN)."""
+        return (x.is_cuda and x.dim() == 3 and getattr(self, "train_impl", "kernels") == "kernels" and x.shape[0] <= 65535
+                and not getattr(self, "train_tf32", False) and not getattr(self, "train_channels_last", False)
+                and all(m.conv.kernel_size[0] % 2 == 1 and m.conv.padding[0] == m.conv.kernel_size[0] // 2 and m.conv.dilation[0] == 1
+                        and m.conv.groups == 1 and m.conv.padding_mode == "zeros" for m in self.net))
 
     def out_frames(self, F):
         """Frames after the stride-2 blocks (SURVEY 9: F -> (F-1)//2+1 per block)."""
@@ -129,6 +218,12 @@ class Encoder(nn.Module):
     def forward(self, x):
         if self._kernels_ok(x):
             return self._forward_kernels(x)
+        if self._train_kernels_ok(x) and torch.is_grad_enabled():
+            params = []
+            for m in self.net:
+                params += [m.conv.weight, m.conv.bias]
+            params += [self.lin.weight, self.lin.bias]
+            return EncoderTrainFunction.apply(self, x, *params)
         # keep the (out-of-scope, cuDNN) encoder in true fp32: TF32 convolutions would move latents by ~1e-3 and
         # flip VQ codes relative to the reference's fp32 path
         # benchmark=True: cuDNN's heuristic pick for these frame-rate shapes (16 x 256 x 100) is an implicit-GEMM kernel that
