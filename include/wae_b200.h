@@ -328,7 +328,12 @@ typedef struct wae_stack_saved {
     void* c_cl;    /* [B][T][Cp]     conditioning, Cp = C rounded up to 64; NULL iff C == 0 */
     void* r1;      /* [B][T][S]      relu(skip sum * sqrt(1/L)): first hidden activation of the head (NULL: not kept) */
     void* r2;      /* [B][T][S]      relu(W3 r1 + b3): second hidden activation of the head (NULL: not kept) */
+    void* gate;    /* [L][B][Hh/16][4][T] x 16 bytes (= L*B*T*Hh*4 bytes, Hh = G/2 rounded up to 16) or NULL: tanh and sigmoid
+                      of every layer's gate pre-activations as bf16 (per 16-channel chunk: pieces 0,1 = tanh of channels 0-7 /
+                      8-15, pieces 2,3 = sigmoid), so that the backward need not recompute the gate GEMM (a third of its
+                      FLOPs).  Only where wae_stack_gate_save_supported() == 1; 256-byte aligned. */
 } wae_stack_saved;
+int wae_stack_gate_save_supported(const wae_stack_dims* d);
 int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B, int T,
                                 float* logits, const wae_stack_saved* save, void* workspace, size_t workspace_bytes,
                                 void* stream);
@@ -355,6 +360,8 @@ typedef struct wae_stack_bwd {
     float *dw1, *dwo, *dws, *dw3, *dw4, *dgb, *dbo, *dbs, *db3, *db4, *dc;
     void* dx0;
     const void* dy;   /* optional: d loss / d logits already as (B,T,O) bf16 (wae_train_ce_grad); then dlogits may be NULL */
+    const void* gate; /* optional: the gate factors kept by the forward (wae_stack_saved.gate); then the gate pre-activations are
+                         not recomputed: dz = [dh sig (1 - tanh^2) | dh tanh sig (1 - sig)] straight from them */
 } wae_stack_bwd;
 size_t wae_stack_backward_workspace_bf16(const wae_stack_dims* d, int B, int T);
 int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,

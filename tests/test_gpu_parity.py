@@ -501,7 +501,16 @@ def test_training_backward_matches_autograd(cfg_name):
     f32 = lambda t: None if t is None else t.float()
     assert training.tc_backward_supported(ctx.sh)                  # (a) exercises wae_stack_backward_bf16, not the library composite
     with torch.no_grad():
-        ra = training.stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, wts, lg.grad, r1=r1, r2=r2, pk=ctx.pk)
+        ra = training.stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, wts, lg.grad, r1=r1, r2=r2, pk=ctx.pk,
+                                     gate=getattr(ctx, "gate", None))
+        if getattr(ctx, "gate", None) is not None:
+            # the same backward with the gate GEMM recomputed (no kept factors): the two differ by the bf16 rounding of the kept
+            # tanh / sigmoid only
+            rc_ = training.stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, wts, lg.grad, r1=r1, r2=r2, pk=ctx.pk)
+            keep_ = [i for i, w in enumerate(wts) if w is not None and ra[3][i] is not None]
+            cs_, l2_ = _flat_stats([rc_[3][i] for i in keep_] + [rc_[1], rc_[2]], [ra[3][i] for i in keep_] + [ra[1], ra[2]])
+            print(f"{cfg_name}: kept gate factors vs recomputed gate GEMM: cosine {cs_:.6f} rel L2 {l2_:.3e}")
+            assert cs_ > 0.9995 and l2_ < 3e-2, (cs_, l2_)
         rb = training.stack_backward(ctx.sh, ctx.dil, xf, gf, f32(x_all), f32(h_all), f32(c_cl), wts, lg.grad, cdt=torch.float32)
     keep = [i for i, w in enumerate(wts) if w is not None and ra[3][i] is not None]
     cos_a, l2_a = _flat_stats([rb[3][i] for i in keep] + [rb[1], rb[2]], [ra[3][i] for i in keep] + [ra[1], ra[2]])

@@ -42,12 +42,13 @@ class StackBF16(C.Structure):
 
 
 class StackSaved(C.Structure):
-    _fields_ = [("x_all", C.c_void_p), ("h_all", C.c_void_p), ("c_cl", C.c_void_p), ("r1", C.c_void_p), ("r2", C.c_void_p)]
+    _fields_ = [("x_all", C.c_void_p), ("h_all", C.c_void_p), ("c_cl", C.c_void_p), ("r1", C.c_void_p), ("r2", C.c_void_p),
+                ("gate", C.c_void_p)]
 
 
 class StackBwd(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("wdh", "wdx", "wct", "w4t", "w3t", "x_all", "h_all", "c_cl", "r1", "r2", "gemb",
-                                           "dw1", "dwo", "dws", "dw3", "dw4", "dgb", "dbo", "dbs", "db3", "db4", "dc", "dx0", "dy")]
+                                           "dw1", "dwo", "dws", "dw3", "dw4", "dgb", "dbo", "dbs", "db3", "db4", "dc", "dx0", "dy", "gate")]
 
 
 class CondFrontend(C.Structure):
@@ -151,6 +152,7 @@ SIGNATURES = {
     "wae_profile_enable": (None, [C.c_int]),
     "wae_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wae_gemm_bf16_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "wae_stack_gate_save_supported": (C.c_int, [C.POINTER(StackDims)]),
     "wae_stack_backward_workspace_bf16": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),
     "wae_stack_backward_bf16": (C.c_int, [C.POINTER(StackBF16), C.POINTER(StackBwd), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                           C.c_void_p]),

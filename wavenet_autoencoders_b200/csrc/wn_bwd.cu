@@ -36,7 +36,9 @@ constexpr int BW_NCG = 4;                   // column groups of the epilogue
 constexpr int BW_STAGES = 3;                // x (16 KB activations + up to 32 KB weights)
 constexpr int BW_STAGE_BYTES = TILE_BYTES + 256 * BK * 2;
 
-enum { MODE_PLAIN = 0, MODE_MASK = 1, MODE_RESID = 2, MODE_GATE = 3, MODE_PLAIN_F32 = 4 };
+enum { MODE_PLAIN = 0, MODE_MASK = 1, MODE_RESID = 2, MODE_GATE = 3, MODE_PLAIN_F32 = 4, MODE_GATE_SAVED = 5 };
+// MODE_GATE_SAVED: as GATE, but tanh / sigmoid come from the factors the forward kept (LayerArgs::gsave layout) instead of a
+// recomputed gate GEMM: only the dh accumulator (N2 columns, at column 0 of its buffer -> two tiles ping-pong) exists, ng1 = 0.
 
 struct GGroup { int src, shift, c2off, nkb; };   // k-block group: A source map, time shift (row t + shift), plane offset, 64-channel blocks
 
@@ -47,6 +49,7 @@ struct BwdGemmArgs {
     CUtensorMap tm_out;        // bf16 output [B][T][N1], box {64, 128}
     float* out_f32;            // MODE_PLAIN_F32: [B*T][ldo]
     const float* vec;          // GATE: gb [B][N1] (conv bias + speaker term); PLAIN: bias [N1] or null
+    const uint4* gsave;        // GATE_SAVED: this layer's plane of kept gate factors [B][N2/16][4][T] x 16 bytes
     float alpha;
     int ldo, mode;
     int B, T, tiles_per_utt;
@@ -97,7 +100,9 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_gemm_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     const int ntiles = a.B * a.tiles_per_utt;
-    const int nbuf = (a.N1 + a.N2 <= 256) ? 2 : 1;     // accumulator sets that fit the 512 TMEM columns
+    const bool gate_saved = (a.mode == MODE_GATE_SAVED);
+    const int nbuf = (gate_saved || a.N1 + a.N2 <= 256) ? 2 : 1;     // accumulator sets that fit the 512 TMEM columns
+    const uint32_t acc2_off = gate_saved ? 0u : (uint32_t)a.N1;       // where the second GEMM's accumulator starts in its buffer
     const uint32_t b1_bytes = (uint32_t)a.N1 * BK * 2, b2_bytes = (uint32_t)a.N2 * BK * 2;
 
     if (warp == 0) {
@@ -150,7 +155,7 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_gemm_kernel(const __grid_co
                     mbar_wait(&full[ring.stage], ring.phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + ring.stage * BW_STAGE_BYTES);
-                    issue_kblock_k(buf + (uint32_t)a.N1, sa, sa + TILE_BYTES, idesc2, kb == 0);
+                    issue_kblock_k(buf + acc2_off, sa, sa + TILE_BYTES, idesc2, kb == 0);
                     umma_commit(&empty[ring.stage]);
                     ring.advance();
                 }
@@ -223,6 +228,42 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_gemm_kernel(const __grid_co
                         }
                         pa[i >> 1] = pack_bf16x2(da[0], da[1]);
                         pb[i >> 1] = pack_bf16x2(db[0], db[1]);
+                    }
+                    {
+                        const int kb = c0 / BK, c16 = (c0 % BK) / 8;
+                        const uint32_t base = stg_addr + kb * TILE_BYTES;
+                        st_shared_v4(base + sw128_off(row, c16), pa[0], pa[1], pa[2], pa[3]);
+                        st_shared_v4(base + sw128_off(row, c16 + 1), pa[4], pa[5], pa[6], pa[7]);
+                    }
+                    {
+                        const int c1 = Hh + c0, kb = c1 / BK, c16 = (c1 % BK) / 8;
+                        const uint32_t base = stg_addr + kb * TILE_BYTES;
+                        st_shared_v4(base + sw128_off(row, c16), pb[0], pb[1], pb[2], pb[3]);
+                        st_shared_v4(base + sw128_off(row, c16 + 1), pb[4], pb[5], pb[6], pb[7]);
+                    }
+                }
+            } else if (a.mode == MODE_GATE_SAVED) {
+                const int Hh = a.N2;
+                const bool live = (t0 + row < a.T);
+                for (int c0 = cg * 16; c0 < Hh; c0 += BW_NCG * 16) {
+                    float dh[16];
+                    tmem_ld16(buf + lane_base + c0, dh);
+                    uint4 g4[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+                    if (live) {
+                        const uint4* gp = a.gsave + ((size_t)(b * (Hh >> 4) + (c0 >> 4)) * 4) * a.T + (t0 + row);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) g4[p] = __ldg(gp + (size_t)p * a.T);
+                    }
+                    const uint32_t tw[8] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w};
+                    const uint32_t sw[8] = {g4[2].x, g4[2].y, g4[2].z, g4[2].w, g4[3].x, g4[3].y, g4[3].z, g4[3].w};
+                    tmem_ld_wait();
+                    uint32_t pa[8], pb[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float th0 = bf_lo(tw[i]), th1 = bf_hi(tw[i]), sg0 = bf_lo(sw[i]), sg1 = bf_hi(sw[i]);
+                        const float d0 = dh[2 * i], d1 = dh[2 * i + 1];
+                        pa[i] = pack_bf16x2(d0 * sg0 * (1.f - th0 * th0), d1 * sg1 * (1.f - th1 * th1));
+                        pb[i] = pack_bf16x2(d0 * th0 * sg0 * (1.f - sg0), d1 * th1 * sg1 * (1.f - sg1));
                     }
                     {
                         const int kb = c0 / BK, c16 = (c0 % BK) / 8;
@@ -796,8 +837,13 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
             CUtensorMap m_out;
             MAP(m_out, dz_l, Gp, B, BM);
             g.tm_out = m_out; g.mode = MODE_GATE; g.N1 = Gp; g.N2 = Hh; g.vec = ws.gb + (size_t)l * B * Gp;
-            for (int j = 0; j < kw; ++j) g.g1[g.ng1++] = GGroup{0, -(kw - 1 - j) * dil, l * B, R / 64};
-            if (C > 0) g.g1[g.ng1++] = GGroup{1, 0, 0, Cp / 64};
+            if (bw->gate != nullptr) {       // the forward kept tanh / sigmoid: no gate GEMM to recompute
+                g.mode = MODE_GATE_SAVED;
+                g.gsave = reinterpret_cast<const uint4*>(bw->gate) + (size_t)l * B * T * Hh / 4;
+            } else {
+                for (int j = 0; j < kw; ++j) g.g1[g.ng1++] = GGroup{0, -(kw - 1 - j) * dil, l * B, R / 64};
+                if (C > 0) g.g1[g.ng1++] = GGroup{1, 0, 0, Cp / 64};
+            }
             g.g2[g.ng2++] = GGroup{2, 0, 0, S / 64};
             if (has_dxo) g.g2[g.ng2++] = GGroup{3, 0, 0, R / 64};
             if (int rc = launch_bwd_gemm(g, st)) return rc;

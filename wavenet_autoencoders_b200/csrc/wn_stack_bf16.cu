@@ -722,6 +722,10 @@ struct LayerArgs {
     int B, T, R, G, Hp, Cp, kw, dil, layer, tiles_per_utt;   // G = 2 * Hh: gate rows incl. the zero padding of each half
     int Ha, Hb;          // h channels produced by gate pass A (min(Hh, 128)) and pass B (Hh - Ha; 0 = single pass)
     long long* prof;     // optional [gridDim.x][16] cycle counters (debug), or null
+    uint4* gsave;        // training forward (version-4 kernel): this layer's plane of the kept gate factors, or null -- tanh and
+                         // sigmoid of the gate pre-activations as bf16, [B][Hh/16][4][T] x 16 bytes: chunk k = channels 16k..16k+15,
+                         // pieces 0,1 = tanh of channels 0-7 / 8-15 of the chunk, pieces 2,3 = sigmoid; a warp's 32 rows of one
+                         // piece are 512 contiguous bytes.  The backward reads them instead of recomputing the gate GEMM.
 };
 
 // role-level cycle counters: compiled in only with -DWAE_LAYER_PROF (WAE_LAYER_PROF=1 python -m ...build); they cost registers
@@ -2038,6 +2042,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_pair2_kernel(cons
 #endif
 constexpr int V4_STAGES = WAE_V4_STAGES;
 
+template <bool kSaveGate>
 __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const __grid_constant__ LayerArgs a) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -2268,11 +2273,30 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                         *reinterpret_cast<float4*>(&bb[i]) = __ldg(reinterpret_cast<const float4*>(gbp + Hh + c0 + i));
                     }
                     tmem_ld_wait();
+                    if constexpr (kSaveGate) {
+                        uint32_t pt[8], ps[8];
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
-                        const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
-                        packed[i >> 1] = pack_bf16x2(h0, h1);
+                        for (int i = 0; i < 16; i += 2) {
+                            const float t0v = tanh_fast(va[i] + ba[i]), t1v = tanh_fast(va[i + 1] + ba[i + 1]);
+                            const float s0v = sigmoid_fast(vb[i] + bb[i]), s1v = sigmoid_fast(vb[i + 1] + bb[i + 1]);
+                            packed[i >> 1] = pack_bf16x2(t0v * s0v, t1v * s1v);
+                            pt[i >> 1] = pack_bf16x2(t0v, t1v);
+                            ps[i >> 1] = pack_bf16x2(s0v, s1v);
+                        }
+                        if (valid && t0 + row < a.T) {
+                            uint4* gp = a.gsave + ((size_t)(b * (Hh >> 4) + (c0 >> 4)) * 4) * a.T + (t0 + row);
+                            gp[0] = make_uint4(pt[0], pt[1], pt[2], pt[3]);
+                            gp[(size_t)a.T] = make_uint4(pt[4], pt[5], pt[6], pt[7]);
+                            gp[(size_t)2 * a.T] = make_uint4(ps[0], ps[1], ps[2], ps[3]);
+                            gp[(size_t)3 * a.T] = make_uint4(ps[4], ps[5], ps[6], ps[7]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            const float h0 = tanh_fast(va[i] + ba[i]) * sigmoid_fast(vb[i] + bb[i]);
+                            const float h1 = tanh_fast(va[i + 1] + ba[i + 1]) * sigmoid_fast(vb[i + 1] + bb[i + 1]);
+                            packed[i >> 1] = pack_bf16x2(h0, h1);
+                        }
                     }
                 } else {
 #pragma unroll
@@ -3202,7 +3226,13 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     if (cs == 4) nclusters = 33;   // 132 SMs: 4-CTA clusters cannot use all 148 (GPC granularity); more would queue a 2nd wave
     if (nclusters > nsuper) nclusters = nsuper;
     const int grid_layer = nclusters * cs;
-    if (v4) WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v4));
+    const bool save_gate = (save != nullptr && save->gate != nullptr);
+    WAE_REQUIRE(!save_gate || v4, "wae_stack_forward_bf16_save: the gate factors are only kept by the version-4 layer kernel "
+                "(wae_stack_gate_save_supported() == 0 for this shape / layer-kernel choice)");
+    if (v4) {
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_v4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v4));
+        WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_v4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v4));
+    }
     if (pair && !pair2 && !v4)
         WAE_CHECK_CUDA(cudaFuncSetAttribute(layer_bf16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_layer));
     const int hx_tiles = (Hp / BK) > (d.R / BK) ? (Hp / BK) : (d.R / BK);
@@ -3243,6 +3273,7 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         la.dil = d.dilation[l];
         la.layer = l;
         la.prof = (l == (d.layers > 5 ? 5 : 0)) ? g_layer_prof : nullptr;   // debug counters of one representative layer
+        la.gsave = save_gate ? reinterpret_cast<uint4*>(save->gate) + (size_t)l * B * T * (Gp / 2) / 4 : nullptr;
         {
             ProfScope prof(1, stream);
             cudaLaunchConfig_t cfg = {};
@@ -3257,7 +3288,8 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
             attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr;
             cfg.numAttrs = 1;
-            if (v4) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v4_kernel, la));
+            if (v4 && save_gate) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v4_kernel<true>, la));
+            else if (v4) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v4_kernel<false>, la));
             else if (v3) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v3_kernel, la));
             else if (pair2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_pair2_kernel, la));
             else if (v2) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v2_kernel, la));
@@ -3323,6 +3355,15 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
 int wae_stack_forward_bf16(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,
                            int T, float* logits, void* workspace, size_t workspace_bytes, void* stream) {
     return stack_forward_bf16_impl(w, x, nullptr, c, 0, nullptr, gemb, B, T, logits, nullptr, workspace, workspace_bytes, stream);
+}
+
+int wae_stack_gate_save_supported(const wae_stack_dims* d) {
+    // the condition under which stack_forward_bf16_impl picks the version-4 layer kernel (the one that can keep the gate factors)
+    if (d == nullptr || d->G < 2 || d->R <= 0) return 0;
+    const int H = d->G / 2, Hh = (H + 15) / 16 * 16, Gp = 2 * Hh, Hp = (H + BK - 1) / BK * BK;
+    const int Hb = Hh - (Hh < 128 ? Hh : 128);
+    const size_t smem_v4 = 1024 + (size_t)V4_STAGES * (A_TILE_BYTES + PAIR_B_BYTES) + (size_t)(Hp / BK + d->R / BK) * A_TILE_BYTES + 256 + 1024;
+    return ((g_layer_mode == 5) && Hb == 0 && Gp % 32 == 0 && d->R % 32 == 0 && d->R % BK == 0 && smem_v4 <= 232448) ? 1 : 0;
 }
 
 int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B,

@@ -145,7 +145,13 @@ class StackTrainFunction(torch.autograd.Function):
         c_cl = torch.empty(B, T, Cp, dtype=BF, device=dev) if sh.C else None
         r1 = torch.empty(B, T, sh.S, dtype=BF, device=dev)           # the head's two hidden activations (ReLU outputs)
         r2 = torch.empty(B, T, sh.S, dtype=BF, device=dev)
-        save = _lib.StackSaved(_lib.ptr(x_all), _lib.ptr(h_all), _lib.ptr(c_cl), _lib.ptr(r1), _lib.ptr(r2))
+        # the gate factors (tanh, sigmoid of every layer's gate pre-activations, bf16) kept by the version-4 layer kernel: the
+        # backward then skips the recompute of the gate GEMM, a third of its FLOPs (WAE_SAVE_GATE=0: recompute as before)
+        gate = None
+        if (os.environ.get("WAE_SAVE_GATE", "1") != "0" and tc_backward_supported(sh)
+                and lib.wae_stack_gate_save_supported(pk.struct.d) == 1):
+            gate = torch.empty(L * B * T * packing._ru(H, 16) * 4, dtype=torch.uint8, device=dev)
+        save = _lib.StackSaved(_lib.ptr(x_all), _lib.ptr(h_all), _lib.ptr(c_cl), _lib.ptr(r1), _lib.ptr(r2), _lib.ptr(gate))
         n = lib.wae_stack_workspace_bf16(pk.struct.d, B, T)
         ws = wn._ws.get(n, dev)
         _lib.check(lib.wae_stack_forward_bf16_save(pk.struct, _lib.ptr(xf), _lib.ptr(cf), _lib.ptr(gf), B, T, _lib.ptr(logits),
@@ -157,6 +163,7 @@ class StackTrainFunction(torch.autograd.Function):
         if not hasattr(wn, "_ws_bwd"):
             wn._ws_bwd = packing.WorkspaceCache()
         ctx.pk, ctx.ws_cache = pk, wn._ws_bwd
+        ctx.gate = gate
         ctx.two_ok = lanes is not None            # the two-stream backward relies on the folds having run on lanes
         ctx.save_for_backward(xf, gf, x_all, h_all, c_cl, r1, r2, *[None if w is None else w.detach() for w in weights])
         return logits
@@ -165,7 +172,7 @@ class StackTrainFunction(torch.autograd.Function):
     def backward(ctx, dlogits):
         xf, gf, x_all, h_all, c_cl, r1, r2, *weights = ctx.saved_tensors
         dxin, dc_up, dgvec, grads = stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, ctx.x_needs_grad,
-                                                   r1=r1, r2=r2, pk=ctx.pk, ws_cache=ctx.ws_cache)
+                                                   r1=r1, r2=r2, pk=ctx.pk, ws_cache=ctx.ws_cache, gate=ctx.gate)
         return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, *grads)
 
 
@@ -198,7 +205,8 @@ class StackNLLFunction(torch.autograd.Function):
                                                 1.0 / float(B * (T - ctx.shift)), _lib.ptr(dy), _lib.stream_ptr(logits.device)),
                    "wae_train_ce_grad")
         dxin, dc_up, dgvec, grads = _stack_backward_tc(ctx.sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, None, ctx.x_needs_grad,
-                                                       ctx.pk, ctx.ws_cache, dy=dy, two_ok=getattr(ctx, "two_ok", False))
+                                                       ctx.pk, ctx.ws_cache, dy=dy, two_ok=getattr(ctx, "two_ok", False),
+                                                       gate=getattr(ctx, "gate", None))
         return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, None, None, *grads)
 
 
@@ -223,7 +231,8 @@ def _ru(x, m):
     return (x + m - 1) // m * m
 
 
-def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, dy=None, two_ok=False):
+def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, dy=None, two_ok=False,
+                       gate=None):
     """The backward on the tensor cores: pack the transposed weights, one call of wae_stack_backward_bf16, scatter the packed
     fp32 gradients to the parameter shapes.  Same return value as stack_backward."""
     lib = _lib.lib()
@@ -276,6 +285,7 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
     for k in sizes:
         setattr(bw, k, o[k].data_ptr())
     bw.dy = _lib.ptr(dy)                                 # (B,T,O) bf16 from wae_train_ce_grad, or None: transpose-cast dlogits
+    bw.gate = _lib.ptr(gate)                             # kept gate factors (forward's StackSaved.gate), or None: recompute
     dl = None if dy is not None else dlogits.float().contiguous()
     # two streams (WAE_BWD_STREAMS=1 turns it off): the weight-gradient GEMMs go to a side stream nothing on this stream waits
     # for -- this function returns dc / dx0 / bias gradients in stream order, and the upsampler / VQ / encoder backward that
@@ -372,13 +382,13 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
 
 
 def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_needs_grad=False, cdt=BF, adt=torch.float32,
-                   r1=None, r2=None, pk=None, ws_cache=None):
+                   r1=None, r2=None, pk=None, ws_cache=None, gate=None):
     """Hand-derived backward of the decoder stack on saved channels-last activations.  cdt: GEMM operand dtype (bf16 on the
     GPU), adt: accumulation / element-wise dtype.  tests/test_host_cpu.py runs it in float64 against torch autograd.  With
     bf16 CUDA tensors, the head's saved hidden activations (r1, r2) and the packed forward weights (pk) it runs on the
     tensor-core kernels (_stack_backward_tc); shapes those do not cover keep the library-GEMM composite below."""
     if cdt == BF and x_all.is_cuda and r1 is not None and r2 is not None and pk is not None and tc_backward_supported(sh):
-        return _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache)
+        return _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, gate=gate)
     if True:
         L, R, G, H, S, C, O, kw = sh.layers, sh.R, sh.G, sh.H, sh.S, sh.C, sh.O, sh.kernel_size
         _, B, T, _ = x_all.shape
