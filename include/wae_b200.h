@@ -376,7 +376,9 @@ int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, co
  */
 size_t wae_stack_backward_workspace_bf16_2s(const wae_stack_dims* d, int B, int T);
 int wae_stack_backward_bf16_2s(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
-                               size_t workspace_bytes, void* stream, void* wgrad_stream);
+                               size_t workspace_bytes, void* stream, void* wgrad_stream, void* bias_stream);
+/* bias_stream (may be NULL = `stream`): a third stream for the bias-gradient column sums (HBM-bound, they then run beside the
+ * tensor-bound dgrad chain); dgb, dbo, dbs, db3, db4 are then complete in `bias_stream` order, dc and dx0 in `stream` order. */
 /*
  * Gradient of the teacher-forced cross-entropy (vqwae_train.py:760-766, mask of ones; the loss itself: wae_nll_sum) written
  * straight into the backward's operand: dY[b][t][o] = (softmax_o(logits[b][:][t]) - [o == target[b][t+shift]]) * g * inv_n for

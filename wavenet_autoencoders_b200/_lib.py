@@ -158,7 +158,7 @@ SIGNATURES = {
                                           C.c_void_p]),
     "wae_stack_backward_workspace_bf16_2s": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),
     "wae_stack_backward_bf16_2s": (C.c_int, [C.POINTER(StackBF16), C.POINTER(StackBwd), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
-                                             C.c_void_p, C.c_void_p]),
+                                             C.c_void_p, C.c_void_p, C.c_void_p]),
     "wae_train_ce_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p]),
     "wae_colsum_bf16": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "wae_gemm_bf16_nt": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),

@@ -654,21 +654,22 @@ size_t wae_stack_backward_workspace_bf16_2s(const wae_stack_dims* d, int B, int 
 }
 
 static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
-                               size_t workspace_bytes, void* stream_, void* wgrad_stream_);
+                               size_t workspace_bytes, void* stream_, void* wgrad_stream_, void* bias_stream_);
 
 int wae_stack_backward_bf16(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
                             size_t workspace_bytes, void* stream_) {
-    return stack_backward_impl(w, bw, dlogits, B, T, workspace, workspace_bytes, stream_, nullptr);
+    return stack_backward_impl(w, bw, dlogits, B, T, workspace, workspace_bytes, stream_, nullptr, nullptr);
 }
 
 int wae_stack_backward_bf16_2s(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
-                               size_t workspace_bytes, void* stream_, void* wgrad_stream_) {
+                               size_t workspace_bytes, void* stream_, void* wgrad_stream_, void* bias_stream_) {
     WAE_REQUIRE(wgrad_stream_ != nullptr && wgrad_stream_ != stream_, "wae_stack_backward_bf16_2s: needs a second, different stream");
-    return stack_backward_impl(w, bw, dlogits, B, T, workspace, workspace_bytes, stream_, wgrad_stream_);
+    WAE_REQUIRE(bias_stream_ == nullptr || bias_stream_ != wgrad_stream_, "wae_stack_backward_bf16_2s: bias_stream must differ from wgrad_stream");
+    return stack_backward_impl(w, bw, dlogits, B, T, workspace, workspace_bytes, stream_, wgrad_stream_, bias_stream_);
 }
 
 static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw, const float* dlogits, int B, int T, void* workspace,
-                               size_t workspace_bytes, void* stream_, void* wgrad_stream_) {
+                               size_t workspace_bytes, void* stream_, void* wgrad_stream_, void* bias_stream_) {
     if (int rc = wae::require_sm100()) return rc;
     WAE_REQUIRE(w && bw && (dlogits || bw->dy) && workspace, "wae_stack_backward_bf16: null pointer");
     const wae_stack_dims& d = w->d;
@@ -697,6 +698,17 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
         if (e == nullptr) return wae::set_error(WAE_ERR_CUDA, "wae_stack_backward_bf16_2s: cannot create an event");
         WAE_CHECK_CUDA(cudaEventRecord(e, st));
         WAE_CHECK_CUDA(cudaStreamWaitEvent(sw, e, 0));
+        return WAE_OK;
+    };
+    // the bias-gradient column sums (HBM-bound, 43 small launches) likewise: on `sc` they run beside the tensor-bound dgrad chain
+    // instead of inside it; the caller waits for `sc` before it reads dgb / dbo / dbs / db3 / db4
+    cudaStream_t sc = (two && bias_stream_ != nullptr && bias_stream_ != stream_) ? static_cast<cudaStream_t>(bias_stream_) : st;
+    auto fork_c = [&]() -> int {
+        if (sc == st) return WAE_OK;
+        cudaEvent_t e = next_fork_event();
+        if (e == nullptr) return wae::set_error(WAE_ERR_CUDA, "wae_stack_backward_bf16_2s: cannot create an event");
+        WAE_CHECK_CUDA(cudaEventRecord(e, st));
+        WAE_CHECK_CUDA(cudaStreamWaitEvent(sc, e, 0));
         return WAE_OK;
     };
     const uint64_t uT = (uint64_t)T;
@@ -782,7 +794,8 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
         add_tile(a, 0, 0, S, 0, 0, 0);
         if (int rc = fork()) return rc;
         if (int rc = launch_wgrad(a, sw)) return rc;
-        if (int rc = launch_colsum(ws.dY, B, T, Op, 0, bw->db4, st)) return rc;
+        if (int rc = fork_c()) return rc;
+        if (int rc = launch_colsum(ws.dY, B, T, Op, 0, bw->db4, sc)) return rc;
     }
     {   // dp2 = (dY W4) * (r2 > 0)
         BwdGemmArgs g = base_gemm();
@@ -796,7 +809,8 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
         add_tile(a, 0, 0, S, 0, 0, 0);
         if (int rc = fork()) return rc;
         if (int rc = launch_wgrad(a, sw)) return rc;
-        if (int rc = launch_colsum(ws.dp2, B, T, S, 0, bw->db3, st)) return rc;
+        if (int rc = fork_c()) return rc;
+        if (int rc = launch_colsum(ws.dp2, B, T, S, 0, bw->db3, sc)) return rc;
     }
     {   // dS = (dp2 W3) * (r1 > 0) * sqrt(1/L): gradient of the skip sum, the same for every layer
         BwdGemmArgs g = base_gemm();
@@ -819,7 +833,8 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
             if (int rc = fork()) return rc;
         if (int rc = launch_wgrad(a, sw)) return rc;
         }
-        if (int rc = launch_colsum(ws.dS, B, T, S, 0, bw->dbs, st)) return rc;
+        if (int rc = fork_c()) return rc;
+        if (int rc = launch_colsum(ws.dS, B, T, S, 0, bw->dbs, sc)) return rc;
     }
 
     // ---- residual layers, last to first ----
@@ -848,7 +863,8 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
             if (has_dxo) g.g2[g.ng2++] = GGroup{3, 0, 0, R / 64};
             if (int rc = launch_bwd_gemm(g, st)) return rc;
         }
-        if (int rc = launch_colsum(dz_l, B, T, Gp, 1, bw->dgb + (size_t)l * B * Gp, st)) return rc;
+        if (int rc = fork_c()) return rc;
+        if (int rc = launch_colsum(dz_l, B, T, Gp, 1, bw->dgb + (size_t)l * B * Gp, sc)) return rc;
         {   // dW1cat_l = dz^T [x taps | c]
             WgradArgs a = base_wgrad();
             a.tm_a = m_dz64; a.a_c2off = l * B; a.tm_b[0] = m_x64; a.tm_b[1] = m_c64;
@@ -864,7 +880,8 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
             add_tile(a, 0, 0, Hp, 0, l * B, 0);
             if (int rc = fork()) return rc;
         if (int rc = launch_wgrad(a, sw)) return rc;
-            if (int rc = launch_colsum(dxbuf[cur], B, T, R, 0, bw->dbo + (size_t)l * R, st)) return rc;
+            if (int rc = fork_c()) return rc;
+        if (int rc = launch_colsum(dxbuf[cur], B, T, R, 0, bw->dbo + (size_t)l * R, sc)) return rc;
         }
         {   // d loss / d x_l = dxo_l + sum_j W1_j^T dz[t + (kw-1-j) d];  times sqrt(.5) it is dxo_{l-1}
             BwdGemmArgs g = base_gemm();

@@ -222,10 +222,11 @@ class Lanes:
 _wgrad_streams = {}
 
 
-def wgrad_stream(device):
-    """The side stream the two-stream decoder backward puts its weight-gradient GEMMs on (one per device)."""
+def wgrad_stream(device, which="wgrad"):
+    """The side streams of the two-stream decoder backward (one each per device): "wgrad" for its weight-gradient GEMMs,
+    "bias" for the bias-gradient column sums."""
     device = torch.device(device)
-    key = device.index if device.index is not None else torch.cuda.current_device()
+    key = (device.index if device.index is not None else torch.cuda.current_device(), which)
     if key not in _wgrad_streams:
         _wgrad_streams[key] = torch.cuda.Stream(device=device)
     return _wgrad_streams[key]

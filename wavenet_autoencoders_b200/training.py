@@ -295,8 +295,11 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
     if two:
         n = lib.wae_stack_backward_workspace_bf16_2s(pk.struct.d, B, T)
         ws = ws_cache.get(n, dev) if ws_cache is not None else torch.empty(n, dtype=torch.uint8, device=dev)
+        sc = packing.wgrad_stream(dev, "bias") if os.environ.get("WAE_BWD_BIAS_STREAM", "1") != "0" else None
         _lib.check(lib.wae_stack_backward_bf16_2s(pk.struct, bw, _lib.ptr(dl), B, T, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev),
-                                                  sw.cuda_stream), "wae_stack_backward_bf16_2s")
+                                                  sw.cuda_stream, sc.cuda_stream if sc is not None else None), "wae_stack_backward_bf16_2s")
+        if sc is not None:
+            torch.cuda.current_stream(dev).wait_stream(sc)       # the column sums (dgb, dbo, ...) are consumed on this stream below
     else:
         n = lib.wae_stack_backward_workspace_bf16(pk.struct.d, B, T)
         ws = ws_cache.get(n, dev) if ws_cache is not None else torch.empty(n, dtype=torch.uint8, device=dev)
