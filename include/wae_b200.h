@@ -334,6 +334,13 @@ typedef struct wae_stack_saved {
                       FLOPs).  Only where wae_stack_gate_save_supported() == 1; 256-byte aligned. */
 } wae_stack_saved;
 int wae_stack_gate_save_supported(const wae_stack_dims* d);
+/* The same training forward from the (B, T) int64 classes of a one-hot-input model (the loader's one-hot tensor, vqwae_train.py:
+ * 509-520, is one_hot(classes)): the first conv is a row gather, the 256-wide fp32 one-hot never exists. */
+int wae_stack_forward_bf16_save_idx(const wae_stack_bf16* w, const int64_t* x_idx, const float* c, const float* gemb, int B, int T,
+                                    float* logits, const wae_stack_saved* save, void* workspace, size_t workspace_bytes, void* stream);
+/* out [n][O] bf16 = one_hot(idx[n], O) (O % 8 == 0; rows with an index outside [0, O) are all zero): the operand of the first
+ * conv's weight gradient (wae_gemm_bf16_nt) when the step's input is class indices. */
+int wae_onehot_bf16(const int64_t* idx, long long n, int O, void* out, void* stream);
 int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const float* c, const float* gemb, int B, int T,
                                 float* logits, const wae_stack_saved* save, void* workspace, size_t workspace_bytes,
                                 void* stream);

@@ -1101,8 +1101,8 @@ def test_two_stream_backward_equals_one_stream():
     got = {}
     old = os.environ.get("WAE_BWD_STREAMS")
     try:
-        for streams in ("1", "2"):
-            os.environ["WAE_BWD_STREAMS"] = streams
+        for streams in ("1", "2", "2idx"):
+            os.environ["WAE_BWD_STREAMS"] = streams[0]
             torch.manual_seed(0)
             m = VQVAE(c_in=39, hid=64, K=256, wavenet=WaveNet(**T.VQWAE), encoder_hid=256)
             m.load_state_dict(T.synth_state_dict(m, 1))
@@ -1111,7 +1111,7 @@ def test_two_stream_backward_equals_one_stream():
             opt = TS.FlatAdam(m)
             opt.step = lambda: None                       # keep the gradients
             n0 = _lib.launch_count()
-            loss = TS.train_step(m, opt, idx, mfcc, spk)
+            loss = TS.train_step(m, opt, idx, mfcc, spk, index_input=streams.endswith("idx"))   # one-hot tensor / the classes themselves
             torch.cuda.synchronize()
             assert _lib.launch_count() > n0
             got[streams] = (float(loss), opt.flat_g.clone(), opt.offsets, [p.numel() for p in opt.params],
@@ -1121,15 +1121,17 @@ def test_two_stream_backward_equals_one_stream():
             os.environ.pop("WAE_BWD_STREAMS", None)
         else:
             os.environ["WAE_BWD_STREAMS"] = old
-    (l1, a, offs, sizes, names), (l2, b, _, _, _) = got["1"], got["2"]
-    assert l1 == l2
+    (l1, a, offs, sizes, names) = got["1"]
     assert float(a.abs().max()) > 0
-    for n, o, k in zip(names, offs, sizes):
-        x, y = a[o:o + k].double(), b[o:o + k].double()
-        if float(x.norm()) == 0.0:
-            assert float(y.norm()) == 0.0, n
-            continue
-        assert float((x - y).norm() / x.norm()) < 1e-4, n
+    for other in ("2", "2idx"):
+        l2, b = got[other][0], got[other][1]
+        assert l1 == l2, other
+        for n, o, k in zip(names, offs, sizes):
+            x, y = a[o:o + k].double(), b[o:o + k].double()
+            if float(x.norm()) == 0.0:
+                assert float(y.norm()) == 0.0, (other, n)
+                continue
+            assert float((x - y).norm() / x.norm()) < 1e-4, (other, n)
 
 
 @pytest.mark.parametrize("scales,B,C,F", [([4, 4], 3, 16, 7), ([4, 4, 8, 5], 2, 64, 12), ([3, 7], 2, 5, 1)])

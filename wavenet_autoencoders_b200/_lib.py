@@ -153,6 +153,9 @@ SIGNATURES = {
     "wae_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "wae_gemm_bf16_tn": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "wae_stack_gate_save_supported": (C.c_int, [C.POINTER(StackDims)]),
+    "wae_stack_forward_bf16_save_idx": (C.c_int, [C.POINTER(StackBF16), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                                  C.POINTER(StackSaved), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wae_onehot_bf16": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
     "wae_stack_backward_workspace_bf16": (C.c_size_t, [C.POINTER(StackDims), C.c_int, C.c_int]),
     "wae_stack_backward_bf16": (C.c_int, [C.POINTER(StackBF16), C.POINTER(StackBwd), C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
                                           C.c_void_p]),

@@ -3373,6 +3373,13 @@ int wae_stack_forward_bf16_save(const wae_stack_bf16* w, const float* x, const f
     return stack_forward_bf16_impl(w, x, nullptr, c, 0, nullptr, gemb, B, T, logits, save, workspace, workspace_bytes, stream);
 }
 
+int wae_stack_forward_bf16_save_idx(const wae_stack_bf16* w, const int64_t* x_idx, const float* c, const float* gemb, int B, int T,
+                                    float* logits, const wae_stack_saved* save, void* workspace, size_t workspace_bytes, void* stream) {
+    WAE_REQUIRE(save != nullptr && w && x_idx, "wae_stack_forward_bf16_save_idx: null pointer");
+    WAE_REQUIRE(w->d.Oin > 1, "wae_stack_forward_bf16_save_idx: class indices need a one-hot-input model (Oin > 1)");
+    return stack_forward_bf16_impl(w, nullptr, x_idx, c, 0, nullptr, gemb, B, T, logits, save, workspace, workspace_bytes, stream);
+}
+
 int wae_stack_forward_bf16_up(const wae_stack_bf16* w, const float* x, const float* c_frames, int Tc, int up_scale,
                               const float* up_filter, const float* gemb, int B, int T, float* logits, void* workspace,
                               size_t workspace_bytes, void* stream) {

@@ -549,3 +549,32 @@ extern "C" int wae_upsample_stage_backward(const float* dy, const float* in, int
     WAE_CHECK_LAUNCH();
     return WAE_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// one-hot rows as bf16: the B operand of the first conv's weight gradient when the step's input is class indices
+// ---------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256)
+onehot_bf16_kernel(const long long* __restrict__ idx, long long n, int O8, uint4* __restrict__ out) {
+    const long long total = n * O8;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long row = e / O8;
+        const int c0 = (int)(e - row * O8) * 8;
+        const long long k = __ldg(&idx[row]) - c0;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (k >= 0 && k < 8) w[k >> 1] = (k & 1) ? 0x3f800000u : 0x00003f80u;      // bf16 1.0 = 0x3f80
+        out[e] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+}  // namespace
+
+extern "C" int wae_onehot_bf16(const int64_t* idx, long long n, int O, void* out, void* stream) {
+    if (int rc = wae::require_sm100()) return rc;
+    WAE_REQUIRE(idx && out && n > 0 && O > 0 && O % 8 == 0, "wae_onehot_bf16: n=%lld O=%d (O must be a multiple of 8)", n, O);
+    long long blocks = (n * (O / 8) + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    onehot_bf16_kernel<<<(unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const long long*>(idx), n, O / 8,
+                                                                                       static_cast<uint4*>(out));
+    WAE_CHECK_LAUNCH();
+    return WAE_OK;
+}

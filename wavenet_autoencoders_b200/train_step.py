@@ -150,13 +150,17 @@ class FlatAdam:
         packing.bump_generation()        # parameters changed through raw pointers: packed-weight caches must re-pack
 
 
-def train_step(model, opt, idx, mfcc, g, clip=100.0, world=1, timers=None, fused_loss=True):
+def train_step(model, opt, idx, mfcc, g, clip=100.0, world=1, timers=None, fused_loss=True, index_input=True):
     """idx (B,T) int64 mu-law classes; mfcc (B,39,frames); g (B,1) speaker ids.  Returns the loss tensor (no sync)."""
-    x = F.one_hot(idx, 256).float().transpose(1, 2)                        # the collate's one-hot input (vqwae_train.py:509-520)
     opt.zero_grad(set_to_none=True)
     if world > 1 and getattr(opt, "bucketed", None) is not None:
         opt.bucketed.start_step()
     # vqwae_train.py:760-766: y_hat[:, :, :-1] predicts y[:, 1:]; full-length synthetic windows -> the mask is all ones
+    wn = getattr(model, "wavenet", None)
+    index_input = (index_input and fused_loss and hasattr(model, "forward_nll") and wn is not None and idx.is_cuda
+                   and getattr(wn, "fused_training_ok", lambda _x: False)(idx))
+    # the collate's one-hot input (vqwae_train.py:509-520) is one_hot(classes): the fused kernel path takes the classes themselves
+    x = idx if index_input else F.one_hot(idx, 256).float().transpose(1, 2)
     if fused_loss and hasattr(model, "forward_nll"):
         nll, vq_loss, _ = model.forward_nll(x, mfcc, g, idx, 1)            # decoder loss + backward fused (training.StackNLLFunction)
         loss = nll + vq_loss

@@ -127,16 +127,24 @@ class StackTrainFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, wn, x, c_up, gvec, *weights):
         sh = packing.stack_shape(wn)
-        B, _, T = x.shape
+        B, T = x.shape[0], x.shape[-1]
         dev = x.device
         L, R, H = sh.layers, sh.R, sh.H
         Hp, Cp = packing._ru(H, 64), (packing._ru(sh.C, 64) if sh.C else 0)
-        lanes = getattr(wn, "_lanes", None)                 # forked by stack_*_train around live_weights; joined here
-        pk = packing.pack_bf16(wn, folded=weights, lanes=lanes)
-        if lanes is not None:
-            lanes.join()
+        prep = getattr(wn, "_prep", None)
+        if prep is not None:                                # begin_weight_prep ran at the start of the step: just wait for its stream
+            lanes, pk = prep["lanes"], prep["pk"]
+            torch.cuda.current_stream(dev).wait_stream(prep["stream"])
+            ctx.bwp = prep["bwp"]
+        else:
+            lanes = getattr(wn, "_lanes", None)             # forked by stack_*_train around live_weights; joined here
+            pk = packing.pack_bf16(wn, folded=weights, lanes=lanes)
+            if lanes is not None:
+                lanes.join()
+            ctx.bwp = None
         lib = _lib.lib()
-        xf = x.detach().float().contiguous()
+        x_is_index = not torch.is_floating_point(x)         # (B,T) classes of a one-hot-input model: the one-hot tensor never exists
+        xf = x.detach().long().contiguous() if x_is_index else x.detach().float().contiguous()
         cf = None if c_up is None else c_up.detach().float().contiguous()
         gf = None if gvec is None else gvec.detach().float().contiguous()
         logits = torch.empty(B, sh.O, T, dtype=torch.float32, device=dev)
@@ -154,11 +162,11 @@ class StackTrainFunction(torch.autograd.Function):
         save = _lib.StackSaved(_lib.ptr(x_all), _lib.ptr(h_all), _lib.ptr(c_cl), _lib.ptr(r1), _lib.ptr(r2), _lib.ptr(gate))
         n = lib.wae_stack_workspace_bf16(pk.struct.d, B, T)
         ws = wn._ws.get(n, dev)
-        _lib.check(lib.wae_stack_forward_bf16_save(pk.struct, _lib.ptr(xf), _lib.ptr(cf), _lib.ptr(gf), B, T, _lib.ptr(logits),
-                                                   save, _lib.ptr(ws), ws.numel(), _lib.stream_ptr(dev)),
-                   "wae_stack_forward_bf16_save")
+        fwd = lib.wae_stack_forward_bf16_save_idx if x_is_index else lib.wae_stack_forward_bf16_save
+        _lib.check(fwd(pk.struct, _lib.ptr(xf), _lib.ptr(cf), _lib.ptr(gf), B, T, _lib.ptr(logits), save, _lib.ptr(ws), ws.numel(),
+                       _lib.stream_ptr(dev)), "wae_stack_forward_bf16_save")
         ctx.sh, ctx.dil = sh, list(sh.dilations)
-        ctx.x_needs_grad = x.requires_grad
+        ctx.x_needs_grad = (not x_is_index) and x.requires_grad
         ctx.c_present, ctx.g_present = c_up is not None, gvec is not None
         if not hasattr(wn, "_ws_bwd"):
             wn._ws_bwd = packing.WorkspaceCache()
@@ -172,7 +180,7 @@ class StackTrainFunction(torch.autograd.Function):
     def backward(ctx, dlogits):
         xf, gf, x_all, h_all, c_cl, r1, r2, *weights = ctx.saved_tensors
         dxin, dc_up, dgvec, grads = stack_backward(ctx.sh, ctx.dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, ctx.x_needs_grad,
-                                                   r1=r1, r2=r2, pk=ctx.pk, ws_cache=ctx.ws_cache, gate=ctx.gate)
+                                                   r1=r1, r2=r2, pk=ctx.pk, ws_cache=ctx.ws_cache, gate=ctx.gate, bwp=getattr(ctx, "bwp", None))
         return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, *grads)
 
 
@@ -206,12 +214,19 @@ class StackNLLFunction(torch.autograd.Function):
                    "wae_train_ce_grad")
         dxin, dc_up, dgvec, grads = _stack_backward_tc(ctx.sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, None, ctx.x_needs_grad,
                                                        ctx.pk, ctx.ws_cache, dy=dy, two_ok=getattr(ctx, "two_ok", False),
-                                                       gate=getattr(ctx, "gate", None))
+                                                       gate=getattr(ctx, "gate", None), bwp=getattr(ctx, "bwp", None))
         return (None, dxin, dc_up if ctx.c_present else None, dgvec.to(gf.dtype) if ctx.g_present else None, None, None, *grads)
 
 
 def stack_nll_train(wn, x, c_up, gvec, target, shift=1):
-    """Scalar teacher-forced NLL with autograd through the tcgen05 forward / backward (StackNLLFunction)."""
+    """Scalar teacher-forced NLL with autograd through the tcgen05 forward / backward (StackNLLFunction).  x: (B,Oin,T) float
+    or, for a one-hot-input model, the (B,T) integer classes."""
+    prep = getattr(wn, "_prep", None)
+    if prep is not None:                      # weights prepared on a side stream since the start of the step (begin_weight_prep)
+        try:
+            return StackNLLFunction.apply(wn, x, c_up, gvec, target, shift, *prep["weights"])
+        finally:
+            wn._prep = None
     wn._lanes = _lanes_for(wn, x)
     try:
         return StackNLLFunction.apply(wn, x, c_up, gvec, target, shift, *live_weights(wn, wn._lanes))
@@ -231,26 +246,22 @@ def _ru(x, m):
     return (x + m - 1) // m * m
 
 
-def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, dy=None, two_ok=False,
-                       gate=None):
-    """The backward on the tensor cores: pack the transposed weights, one call of wae_stack_backward_bf16, scatter the packed
-    fp32 gradients to the parameter shapes.  Same return value as stack_backward."""
-    lib = _lib.lib()
-    L, R, G, H, S, C, O, kw, Gi = sh.layers, sh.R, sh.G, sh.H, sh.S, sh.C, sh.O, sh.kernel_size, sh.Gi
-    _, B, T, _ = x_all.shape
-    dev = x_all.device
+def pack_backward_weights(sh, weights, dev):
+    """The weights in the transposed K-major forms of the backward's dgrad GEMMs (include/wae_b200.h, wae_stack_bwd): tiny
+    tensors, a handful of launches for all layers.  Depends on the weights only, so a training step builds them on its
+    weight-preparation stream during the forward (begin_weight_prep) instead of between the loss and the first backward GEMM."""
+    L, R, H, S, C, kw = sh.layers, sh.R, sh.H, sh.S, sh.C, sh.kernel_size
     Hh, Hp, Cp = _ru(H, 16), _ru(H, 64), (_ru(C, 64) if C else 0)
     Gp = 2 * Hh
-    Gq, K1p = _ru(Gp, 64), kw * R + Cp
+    Gq = _ru(Gp, 64)
     f32 = torch.float32
 
     def lw(l, k):
-        return weights[l * PER_LAYER + k]
+        return weights[l * PER_LAYER + k].detach()
 
     base = L * PER_LAYER
-    Wf, W3, W4 = weights[base], weights[base + 2], weights[base + 4]
+    W3, W4 = weights[base + 2].detach(), weights[base + 4].detach()
     rows = torch.cat([torch.arange(H, device=dev), Hh + torch.arange(H, device=dev)])     # natural gate row -> packed row
-    # ---- weights in the transposed K-major forms of the dgrad GEMMs (tiny tensors, a handful of launches for all layers) ----
     W1 = torch.stack([lw(l, 0) for l in range(L)]).float()                                  # (L,G,R,kw)
     wdx = torch.zeros(L, R, kw, Gq, dtype=f32, device=dev)
     wdx[:, :, :, rows] = W1.permute(0, 2, 3, 1)
@@ -269,6 +280,51 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
         wct = wct.reshape(Cp, L * Gq).to(BF).contiguous()
     w4t = W4[:, :, 0].float().t().to(BF).contiguous()                                        # (S,O)
     w3t = W3[:, :, 0].float().t().to(BF).contiguous()                                        # (S,S)
+    return dict(wdx=wdx, wdh=wdh, wct=wct, w4t=w4t, w3t=w3t)
+
+
+def begin_weight_prep(wn, device):
+    """Start the decoder's per-step weight preparation (weight-norm folds, forward packing, the backward's transposed packs) on a
+    side stream forked from the current one -- called at the very start of a training step, so that it runs beside the encoder /
+    VQ / upsampler instead of after them (it depends on the parameters only).  stack_nll_train / stack_forward_train pick the
+    result up from ``wn._prep`` and make the current stream wait for it."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        return None
+    prep = packing.wgrad_stream(device, "prep")
+    prep.wait_stream(torch.cuda.current_stream(device))
+    with torch.cuda.stream(prep):
+        lanes = _lanes_for(wn, next(wn.parameters()))
+        weights = live_weights(wn, lanes)
+        pk = packing.pack_bf16(wn, folded=weights, lanes=lanes)            # joins the lanes into the prep stream
+        sh = packing.stack_shape(wn)
+        bwp = pack_backward_weights(sh, weights, device) if tc_backward_supported(sh) else None
+    wn._prep = dict(stream=prep, lanes=lanes, weights=weights, pk=pk, bwp=bwp)
+    return wn._prep
+
+
+def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, dy=None, two_ok=False,
+                       gate=None, bwp=None):
+    """The backward on the tensor cores: pack the transposed weights, one call of wae_stack_backward_bf16, scatter the packed
+    fp32 gradients to the parameter shapes.  Same return value as stack_backward."""
+    lib = _lib.lib()
+    L, R, G, H, S, C, O, kw, Gi = sh.layers, sh.R, sh.G, sh.H, sh.S, sh.C, sh.O, sh.kernel_size, sh.Gi
+    _, B, T, _ = x_all.shape
+    dev = x_all.device
+    Hh, Hp, Cp = _ru(H, 16), _ru(H, 64), (_ru(C, 64) if C else 0)
+    Gp = 2 * Hh
+    Gq, K1p = _ru(Gp, 64), kw * R + Cp
+    f32 = torch.float32
+
+    def lw(l, k):
+        return weights[l * PER_LAYER + k]
+
+    base = L * PER_LAYER
+    Wf, W3, W4 = weights[base], weights[base + 2], weights[base + 4]
+    rows = torch.cat([torch.arange(H, device=dev), Hh + torch.arange(H, device=dev)])     # natural gate row -> packed row
+    if bwp is None:
+        bwp = pack_backward_weights(sh, weights, dev)
+    wdx, wdh, wct, w4t, w3t = bwp["wdx"], bwp["wdh"], bwp["wct"], bwp["w4t"], bwp["w3t"]
     # ---- outputs ----
     sizes = dict(dw1=L * Gp * K1p, dwo=L * R * Hp, dws=S * L * Hp, dw3=S * S, dw4=O * S, dgb=L * B * Gp, dbo=L * R, dbs=S, db3=S, db4=O)
     flat = torch.empty(sum(sizes.values()), dtype=f32, device=dev)                          # zeroed by the call
@@ -341,10 +397,16 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
     if weights[base + 5] is not None:
         grads[base + 5] = o["db4"]
     # ---- first conv: x0 = Wf x + bf.  dWf = dx0^T x^T as one more MN-major wgrad over the transposed-cast input ----
-    Oin = xf.shape[1]
+    x_is_index = not torch.is_floating_point(xf)
+    Oin = sh.Oin if x_is_index else xf.shape[1]
     st = _lib.stream_ptr(dev)
     dWf = torch.zeros(R, _ru(Oin, 16), dtype=f32, device=dev)
-    if Oin % 16 == 0 and B <= 65535:
+    if x_is_index:                                                                           # (B,T) classes: bf16 one-hot rows in one launch
+        xT = torch.empty(B, T, _ru(Oin, 16), dtype=BF, device=dev)
+        _lib.check(lib.wae_onehot_bf16(_lib.ptr(xf), B * T, _ru(Oin, 16), _lib.ptr(xT), st), "wae_onehot_bf16")
+        _lib.check(lib.wae_gemm_bf16_nt(_lib.ptr(dx0), _lib.ptr(xT), _lib.ptr(dWf), R, _ru(Oin, 16), B * T, st), "wae_gemm_bf16_nt")
+        grads[base] = dWf[:, :Oin].unsqueeze(-1)
+    elif Oin % 16 == 0 and B <= 65535:
         xT = torch.empty(B, T, Oin, dtype=BF, device=dev)                                   # exact for the one-hot input of every preset
         _lib.check(lib.wae_train_transpose_cast(_lib.ptr(xf), B, Oin, T, _lib.ptr(xT), st), "wae_train_transpose_cast")
         _lib.check(lib.wae_gemm_bf16_nt(_lib.ptr(dx0), _lib.ptr(xT), _lib.ptr(dWf), R, Oin, B * T, st), "wae_gemm_bf16_nt")
@@ -385,13 +447,13 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
 
 
 def stack_backward(sh, dil, xf, gf, x_all, h_all, c_cl, weights, dlogits, x_needs_grad=False, cdt=BF, adt=torch.float32,
-                   r1=None, r2=None, pk=None, ws_cache=None, gate=None):
+                   r1=None, r2=None, pk=None, ws_cache=None, gate=None, bwp=None):
     """Hand-derived backward of the decoder stack on saved channels-last activations.  cdt: GEMM operand dtype (bf16 on the
     GPU), adt: accumulation / element-wise dtype.  tests/test_host_cpu.py runs it in float64 against torch autograd.  With
     bf16 CUDA tensors, the head's saved hidden activations (r1, r2) and the packed forward weights (pk) it runs on the
     tensor-core kernels (_stack_backward_tc); shapes those do not cover keep the library-GEMM composite below."""
     if cdt == BF and x_all.is_cuda and r1 is not None and r2 is not None and pk is not None and tc_backward_supported(sh):
-        return _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, gate=gate)
+        return _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits, x_needs_grad, pk, ws_cache, gate=gate, bwp=bwp)
     if True:
         L, R, G, H, S, C, O, kw = sh.layers, sh.R, sh.G, sh.H, sh.S, sh.C, sh.O, sh.kernel_size
         _, B, T, _ = x_all.shape

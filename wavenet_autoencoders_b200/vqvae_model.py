@@ -273,8 +273,16 @@ class VQVAE(nn.Module):
     def forward_nll(self, x, c, g, target, shift=1):
         """Additive: (teacher-forced NLL of the decoder, vq_loss, perplexity) -- the three quantities the reference's training
         step combines (vqwae_train.py:752-766) -- with loss and backward of the decoder fused (WaveNet.forward_nll)."""
-        quant, vq_loss, perp = self._encode_quantize(c)
-        return self.wavenet.forward_nll(x, quant, g, target, shift), vq_loss, perp
+        wn = self.wavenet
+        if (torch.is_grad_enabled() and x.is_cuda and any(p.requires_grad for p in wn.parameters()) and wn.fused_training_ok(x)):
+            # the decoder's weight preparation depends on the parameters only: start it on a side stream now, beside the encoder
+            from . import training
+            training.begin_weight_prep(wn, x.device)
+        try:
+            quant, vq_loss, perp = self._encode_quantize(c)
+            return wn.forward_nll(x, quant, g, target, shift), vq_loss, perp
+        finally:
+            wn._prep = None
 
     def incremental_forward(self, initial_input, c, g, T, softmax, quantize, tqdm, log_scale_min, **extra):
         """vqvae_model.py:74-80.  ``extra``: the additive keywords of ``WaveNet.incremental_forward`` (``uniforms``,

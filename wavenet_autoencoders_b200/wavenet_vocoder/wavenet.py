@@ -245,10 +245,9 @@ class WaveNet(nn.Module):
         (B,O,T) log-softmax and its gradient are never materialised.  Without, it is ``losses.teacher_forced_nll``."""
         from .. import losses, training
         needs_grad = torch.is_grad_enabled() and ((c is not None and c.requires_grad) or any(p.requires_grad for p in self.parameters()))
-        fused = (needs_grad and self.train_impl == "kernels" and self.precision == "bf16" and x.is_cuda
-                 and training.tc_backward_supported(packing.stack_shape(self))
-                 and not (self.training and any(f.dropout > 0 for f in self.conv_layers)))
+        fused = needs_grad and self.fused_training_ok(x)
         if not fused:
+            self._prep = None
             if (not needs_grad and self.precision == "bf16" and x.is_cuda and not torch.is_floating_point(x) and x.dim() == 2
                     and not self.scalar_input):
                 return self._nll_from_indices(x, c, g, target, shift)
@@ -256,8 +255,8 @@ class WaveNet(nn.Module):
             if needs_grad:
                 return F.cross_entropy(y[:, :, :y.size(-1) - shift], target[:, shift:])
             return losses.teacher_forced_nll(y, target, shift)
-        if not torch.is_floating_point(x) and x.dim() == 2 and not self.scalar_input:
-            x = F.one_hot(x.long(), self.out_channels).float().transpose(1, 2)
+        # (B,T) integer classes of a one-hot-input model go to the kernels as they are (first conv = row gather,
+        # wae_stack_forward_bf16_save_idx): the (B,256,T) fp32 one-hot of the loader (vqwae_train.py:509-520) never exists
         B = x.size(0)
         gvec = self._speaker_vectors(g, B)
         if c is not None and self.upsample_net is not None:
@@ -266,6 +265,14 @@ class WaveNet(nn.Module):
                 print(f"c {c.size() } x {x.size()}")
                 raise Exception
         return training.stack_nll_train(self, x, c, gvec, target, shift)
+
+    def fused_training_ok(self, x):
+        """True if a gradient-requiring teacher-forced step on ``x`` takes the fused kernel path (training.StackNLLFunction)."""
+        from .. import training
+        return (self.train_impl == "kernels" and self.precision == "bf16" and x.is_cuda
+                and training.tc_backward_supported(packing.stack_shape(self))
+                and not (self.training and any(f.dropout > 0 for f in self.conv_layers))
+                and (torch.is_floating_point(x) or (x.dim() == 2 and not self.scalar_input)))
 
     def _nll_from_indices(self, x_idx, c, g, target, shift, logits_out=None):
         """Inference, bf16, class-index input: the NLL comes out of the head kernel's accumulator (wae_stack_nll_bf16_idx);
