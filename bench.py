@@ -686,12 +686,14 @@ def main():
             except OSError as e:
                 extras["nccl"] = [f"no NCCL log: {e}"]
         del gstep
-        extras["train_config"] = ("VQ-WAE step: 8 utt/GPU x 7680 samples, tcgen05 bf16 forward, tcgen05 backward (wae_stack_backward_bf16: "
-                                  "dgrad GEMMs with the dilated taps as TMA boxes and fused gate / residual / ReLU epilogues, MN-major "
-                                  "split-K wgrads), loss + softmax gradient fused (forward_nll), per-layer weight preparation forked over 8 side streams, "
-                                  "fp32 master weights, Adam, grad-clip 100; "
-                                  "N > 1: flat gradient all-reduced in two buckets, the decoder's (80 % of the bytes) under the rest of the "
-                                  "backward; the step is replayed as one CUDA graph")
+        extras["train_config"] = ("VQ-WAE step: 8 utt/GPU x 7680 samples, class-index input (first conv = row gather), tcgen05 bf16 forward "
+                                  "keeping tanh / sigmoid of the gates, tcgen05 backward (wae_stack_backward_bf16_2s: dgrad GEMMs with the "
+                                  "dilated taps as TMA boxes and fused gate / residual / ReLU epilogues on the main stream, MN-major split-K "
+                                  "wgrads and the bias column sums on side streams), loss + softmax gradient fused (forward_nll), encoder and "
+                                  "conditioning upsampler forward + backward on this library's fp32 kernels (no cuDNN / cuBLAS convolution in "
+                                  "the step), decoder weight preparation forked at the start of the step over 9 side streams, fp32 master "
+                                  "weights, Adam, grad-clip 100; N > 1: flat gradient all-reduced in two buckets, the decoder's (80 % of the "
+                                  "bytes) under the rest of the backward; the step is replayed as one CUDA graph")
         del tm, opt
         torch.backends.cudnn.benchmark = False
         torch.cuda.empty_cache()
