@@ -50,6 +50,8 @@ struct BwdGemmArgs {
     float* out_f32;            // MODE_PLAIN_F32: [B*T][ldo]
     const float* vec;          // GATE: gb [B][N1] (conv bias + speaker term); PLAIN: bias [N1] or null
     const uint4* gsave;        // GATE_SAVED: this layer's plane of kept gate factors [B][N2/16][4][T] x 16 bytes
+    float* csum;               // optional: column sums of the bf16 output (the bias gradient that belongs to it), accumulated with
+    int csum_per_utt;          // red.add from the staged tile -- [N1], or [B][N1] per utterance; saves a pass over the output
     float alpha;
     int ldo, mode;
     int B, T, tiles_per_utt;
@@ -332,6 +334,25 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_gemm_kernel(const __grid_co
                     for (int j = 0; j < nout_tiles; ++j) tma_store_3d(&a.tm_out, stg + j * TILE_BYTES, j * BK, t0, b);
                     tma_store_commit();
                 }
+            }
+            if (to_smem && a.csum != nullptr) {
+                // column sums of the tile as it was stored (bf16-rounded; rows past T are zero): thread -> (column, half of the rows).
+                // The staging tiles are only read here and by the TMA store; the next tile overwrites them behind the barrier above.
+                const int et = (int)threadIdx.x - 64, col = et & 255, r0 = (et >> 8) * 64;
+                if (col < a.N1) {
+                    const uint32_t base = stg_addr + (uint32_t)((col >> 6) * TILE_BYTES) + (uint32_t)((col & 7) * 2);
+                    const int c16 = (col & 63) >> 3;
+                    float sum = 0.f;
+#pragma unroll 8
+                    for (int r = r0; r < r0 + 64; ++r) {
+                        uint16_t v;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + sw128_off(r, c16)));
+                        sum += __uint_as_float((uint32_t)v << 16);
+                    }
+                    atomicAdd(a.csum + (a.csum_per_utt ? (size_t)b * a.N1 : (size_t)0) + col, sum);
+                }
+                // MASK / RESID: thread 64 fetches the next tile's aux operand INTO the staging tiles at the top of the loop
+                if (has_aux) asm volatile("bar.sync 1, %0;" ::"n"(32 * 16) : "memory");
             }
         }
         if (threadIdx.x == 64) tma_store_wait_all();
@@ -685,6 +706,9 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
                 "wae_stack_backward_bf16: null output pointer");
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) != 0) return wae::set_error(WAE_ERR_ALIGN, "wae_stack_backward_bf16: workspace must be 256-byte aligned");
     const bool two = (wgrad_stream_ != nullptr);
+    // bias gradients (column sums of dp2, dS, dz_l, dxo_l) from the epilogue of the GEMM that produces the tensor (WAE_BWD_FUSE_COLSUM=0:
+    // separate colsum_bf16_kernel launches, a second pass over every one of them)
+    static const bool fuse_csum = [] { const char* e = getenv("WAE_BWD_FUSE_COLSUM"); return !(e && e[0] == '0'); }();
     BwdWorkspace ws = carve_bwd(d, B, T, workspace, two);
     if (workspace_bytes < ws.total) return wae::set_error(WAE_ERR_WORKSPACE, "wae_stack_backward_bf16: workspace %zu < %zu", workspace_bytes, ws.total);
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
@@ -801,6 +825,7 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
         BwdGemmArgs g = base_gemm();
         g.tm_a[0] = m_dY; g.tm_b1 = mw_w4t; g.tm_aux = m_r2; g.tm_out = m_dp2; g.mode = MODE_MASK; g.N1 = S;
         g.ng1 = 1; g.g1[0] = GGroup{0, 0, 0, (Op + 63) / 64};
+        g.csum = fuse_csum ? bw->db3 : nullptr;
         if (int rc = launch_bwd_gemm(g, st)) return rc;
     }
     {   // dW3 = dp2^T r1, db3
@@ -809,13 +834,16 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
         add_tile(a, 0, 0, S, 0, 0, 0);
         if (int rc = fork()) return rc;
         if (int rc = launch_wgrad(a, sw)) return rc;
-        if (int rc = fork_c()) return rc;
-        if (int rc = launch_colsum(ws.dp2, B, T, S, 0, bw->db3, sc)) return rc;
+        if (!fuse_csum) {
+            if (int rc = fork_c()) return rc;
+            if (int rc = launch_colsum(ws.dp2, B, T, S, 0, bw->db3, sc)) return rc;
+        }
     }
     {   // dS = (dp2 W3) * (r1 > 0) * sqrt(1/L): gradient of the skip sum, the same for every layer
         BwdGemmArgs g = base_gemm();
         g.tm_a[0] = m_dp2; g.tm_b1 = mw_w3t; g.tm_aux = m_r1; g.tm_out = m_dS; g.mode = MODE_MASK; g.N1 = S; g.alpha = scale;
         g.ng1 = 1; g.g1[0] = GGroup{0, 0, 0, S / 64};
+        g.csum = fuse_csum ? bw->dbs : nullptr;
         if (int rc = launch_bwd_gemm(g, st)) return rc;
     }
     {   // dWs of ALL layers: dS^T [h_0 | h_1 | ...]  (columns l*Hp + h), dbs
@@ -833,8 +861,10 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
             if (int rc = fork()) return rc;
         if (int rc = launch_wgrad(a, sw)) return rc;
         }
-        if (int rc = fork_c()) return rc;
-        if (int rc = launch_colsum(ws.dS, B, T, S, 0, bw->dbs, sc)) return rc;
+        if (!fuse_csum) {
+            if (int rc = fork_c()) return rc;
+            if (int rc = launch_colsum(ws.dS, B, T, S, 0, bw->dbs, sc)) return rc;
+        }
     }
 
     // ---- residual layers, last to first ----
@@ -861,10 +891,13 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
             }
             g.g2[g.ng2++] = GGroup{2, 0, 0, S / 64};
             if (has_dxo) g.g2[g.ng2++] = GGroup{3, 0, 0, R / 64};
+            if (fuse_csum) { g.csum = bw->dgb + (size_t)l * B * Gp; g.csum_per_utt = 1; }
             if (int rc = launch_bwd_gemm(g, st)) return rc;
         }
-        if (int rc = fork_c()) return rc;
-        if (int rc = launch_colsum(dz_l, B, T, Gp, 1, bw->dgb + (size_t)l * B * Gp, sc)) return rc;
+        if (!fuse_csum) {
+            if (int rc = fork_c()) return rc;
+            if (int rc = launch_colsum(dz_l, B, T, Gp, 1, bw->dgb + (size_t)l * B * Gp, sc)) return rc;
+        }
         {   // dW1cat_l = dz^T [x taps | c]
             WgradArgs a = base_wgrad();
             a.tm_a = m_dz64; a.a_c2off = l * B; a.tm_b[0] = m_x64; a.tm_b[1] = m_c64;
@@ -880,8 +913,10 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
             add_tile(a, 0, 0, Hp, 0, l * B, 0);
             if (int rc = fork()) return rc;
         if (int rc = launch_wgrad(a, sw)) return rc;
-            if (int rc = fork_c()) return rc;
-        if (int rc = launch_colsum(dxbuf[cur], B, T, R, 0, bw->dbo + (size_t)l * R, sc)) return rc;
+            if (!fuse_csum) {
+                if (int rc = fork_c()) return rc;
+                if (int rc = launch_colsum(dxbuf[cur], B, T, R, 0, bw->dbo + (size_t)l * R, sc)) return rc;
+            }
         }
         {   // d loss / d x_l = dxo_l + sum_j W1_j^T dz[t + (kw-1-j) d];  times sqrt(.5) it is dxo_{l-1}
             BwdGemmArgs g = base_gemm();
@@ -889,6 +924,7 @@ static int stack_backward_impl(const wae_stack_bf16* w, const wae_stack_bwd* bw,
             g.tm_aux = m_dx[cur]; g.mode = has_dxo ? MODE_RESID : MODE_PLAIN;
             g.tm_out = (l == 0) ? m_dx0 : m_dx[cur ^ 1];
             g.alpha = (l > 0) ? rs : 1.f;
+            if (fuse_csum && l > 0) g.csum = bw->dbo + (size_t)(l - 1) * R;      // this GEMM's output is dxo_{l-1}: its column sums are dbo_{l-1}
             for (int j = 0; j < kw; ++j) g.g1[g.ng1++] = GGroup{0, (kw - 1 - j) * dil, l * B, Gq / 64};
             if (int rc = launch_bwd_gemm(g, st)) return rc;
         }
