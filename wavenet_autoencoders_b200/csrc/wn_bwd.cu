@@ -198,6 +198,24 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_gemm_kernel(const __grid_co
                 }
                 if (it > 0 && !has_aux) asm volatile("bar.sync 1, %0;" ::"n"(32 * 16) : "memory");
             }
+            // GATE_SAVED: the kept gate factors of this thread's (at most two) 16-channel chunks do not depend on the GEMM -- fetch
+            // them before waiting for the accumulator, so that their DRAM latency hides behind the MMAs
+            uint4 gpre[2][4];
+            if (a.mode == MODE_GATE_SAVED) {
+                const int Hh = a.N2;
+                const bool live = (t0 + row < a.T);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c0 = (cg + u * BW_NCG) * 16;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) gpre[u][p] = make_uint4(0u, 0u, 0u, 0u);
+                    if (live && c0 < Hh) {
+                        const uint4* gp = a.gsave + ((size_t)(b * (Hh >> 4) + (c0 >> 4)) * 4) * a.T + (t0 + row);
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) gpre[u][p] = __ldg(gp + (size_t)p * a.T);
+                    }
+                }
+            }
             mbar_wait(&acc_full[bsel], (uint32_t)(n_mine & 1));
             tc_fence_after();
             if (has_aux) mbar_wait(aux_full, (uint32_t)(it & 1));
@@ -246,16 +264,13 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_gemm_kernel(const __grid_co
                 }
             } else if (a.mode == MODE_GATE_SAVED) {
                 const int Hh = a.N2;
-                const bool live = (t0 + row < a.T);
-                for (int c0 = cg * 16; c0 < Hh; c0 += BW_NCG * 16) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int c0 = (cg + u * BW_NCG) * 16;
+                    if (c0 >= Hh) break;
                     float dh[16];
                     tmem_ld16(buf + lane_base + c0, dh);
-                    uint4 g4[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
-                    if (live) {
-                        const uint4* gp = a.gsave + ((size_t)(b * (Hh >> 4) + (c0 >> 4)) * 4) * a.T + (t0 + row);
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) g4[p] = __ldg(gp + (size_t)p * a.T);
-                    }
+                    const uint4* g4 = gpre[u];
                     const uint32_t tw[8] = {g4[0].x, g4[0].y, g4[0].z, g4[0].w, g4[1].x, g4[1].y, g4[1].z, g4[1].w};
                     const uint32_t sw[8] = {g4[2].x, g4[2].y, g4[2].z, g4[2].w, g4[3].x, g4[3].y, g4[3].z, g4[3].w};
                     tmem_ld_wait();
