@@ -2049,8 +2049,13 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
     const int STAGE_BYTES = A_TILE_BYTES + PAIR_B_BYTES;
     const int nkh = a.Hp / BK, nkr = a.R / BK;
     uint8_t* hbuf = smem + V4_STAGES * STAGE_BYTES;               // h tiles: GEMM2 A operand + TMA store source
+#ifdef WAE_V4_XALIAS   // timing experiment only (wrong numerics): the x / x' staging aliases ring stages 0-1, its 64 KB go to extra stages
+    uint8_t* xres = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hbuf + nkh * A_TILE_BYTES);
+#else
     uint8_t* xres = hbuf + nkh * A_TILE_BYTES;                    // x tile (residual) in, x' out, TMA store source
     uint64_t* bars = reinterpret_cast<uint64_t*>(xres + nkr * A_TILE_BYTES);
+#endif
     uint64_t* full = bars;                        // [V4_STAGES]  used in the leader only
     uint64_t* empty = bars + V4_STAGES;           // [V4_STAGES]  one per CTA (commit is multicast)
     uint64_t* acc1_full = bars + 2 * V4_STAGES;   // [2]  GEMM1 of the tile in buffer b is complete
@@ -3203,7 +3208,11 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
     // Layer-kernel variant: CTA pairs (cta_group::2, default) or the 1-CTA kernel in clusters of 1/2/4 with weight multicast.
     // version 2 on CTA pairs: single gate pass, weight halves must stay multiples of 16 rows
     const bool pair2 = (g_layer_mode == 3) && Hb == 0 && Gp % 32 == 0 && d.R % 32 == 0;
+#ifdef WAE_V4_XALIAS
+    const size_t smem_v4 = 1024 + (size_t)V4_STAGES * (A_TILE_BYTES + PAIR_B_BYTES) + (size_t)(Hp / BK) * A_TILE_BYTES + 256 + 1024;
+#else
     const size_t smem_v4 = 1024 + (size_t)V4_STAGES * (A_TILE_BYTES + PAIR_B_BYTES) + (size_t)(Hp / BK + d.R / BK) * A_TILE_BYTES + 256 + 1024;
+#endif
     const bool v4 = (g_layer_mode == 5) && Hb == 0 && Gp % 32 == 0 && d.R % 32 == 0 && smem_v4 <= 232448;    // CTA pairs + TMEM ping-pong
     const bool v3 = !v4 && (g_layer_mode == 4 || g_layer_mode == 5) && Hb == 0;                            // TMEM ping-pong (single gate pass only)
     const bool v2 = !v4 && !v3 && !pair2 && ((g_layer_mode == 2) || (g_layer_mode == 3) || (g_layer_mode == 4) || (g_layer_mode == 5) || Hb > 0 || save != nullptr);   // only the 1-CTA version 2 has the second gate pass
