@@ -33,8 +33,8 @@ namespace {
 
 constexpr int BW_THREADS = 64 + 32 * 16;    // producer warp, MMA warp, 16 epilogue warps (as the forward layer kernels)
 constexpr int BW_NCG = 4;                   // column groups of the epilogue
-constexpr int BW_STAGES = 3;                // x (16 KB activations + up to 32 KB weights)
-constexpr int BW_STAGE_BYTES = TILE_BYTES + 256 * BK * 2;
+constexpr int BW_MAX_STAGES = 8;            // ring depth and stage size are chosen per launch (launch_bwd_gemm): a stage is 16 KB of activations
+                                            // + the widest weight k-block of the launch, as many stages as fit beside the output staging
 
 enum { MODE_PLAIN = 0, MODE_MASK = 1, MODE_RESID = 2, MODE_GATE = 3, MODE_PLAIN_F32 = 4, MODE_GATE_SAVED = 5 };
 // MODE_GATE_SAVED: as GATE, but tanh / sigmoid come from the factors the forward kept (LayerArgs::gsave layout) instead of a
@@ -57,6 +57,7 @@ struct BwdGemmArgs {
     int B, T, tiles_per_utt;
     int N1, N2;                // accumulator widths (multiples of 16, <= 256); N2 = 0: single GEMM
     int ng1, ng2, wl1, wl2;    // group counts, weight plane (layer) of each GEMM
+    int nstages, stage_bytes;  // ring geometry (set by launch_bwd_gemm)
     GGroup g1[WAE_MAX_LAYERS], g2[4];
 };
 
@@ -74,11 +75,12 @@ __global__ void __launch_bounds__(BW_THREADS, 1) bwd_gemm_kernel(const __grid_co
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int nout_tiles = (a.N1 + BK - 1) / BK;
+    const int BW_STAGES = a.nstages, BW_STAGE_BYTES = a.stage_bytes;
     uint8_t* stg = smem + BW_STAGES * BW_STAGE_BYTES;                  // output staging (aux operand in, result out), 16 KB tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(stg + nout_tiles * TILE_BYTES);
     uint64_t* full = bars;
-    uint64_t* empty = bars + BW_STAGES;
-    uint64_t* acc_full = bars + 2 * BW_STAGES;    // [2]
+    uint64_t* empty = bars + BW_MAX_STAGES;
+    uint64_t* acc_full = bars + 2 * BW_MAX_STAGES;    // [2]
     uint64_t* epi_done = acc_full + 2;            // [2]
     uint64_t* aux_full = acc_full + 4;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 5);
@@ -538,7 +540,19 @@ int num_sms_bwd() {
 
 int launch_bwd_gemm(BwdGemmArgs& g, cudaStream_t st) {
     const int nout_tiles = (g.N1 + BK - 1) / BK;
-    const size_t smem = 1024 + (size_t)BW_STAGES * BW_STAGE_BYTES + (size_t)nout_tiles * TILE_BYTES + 256;
+    // ring geometry: a stage holds one 16 KB activation tile + the widest weight k-block of this launch (N x 64 bf16, rounded to the
+    // 1 KB swizzle atom); as many stages as fit beside the output staging, at most BW_MAX_STAGES.  The light GEMMs (dh with N = 128,
+    // dC with N = 64) are bound by the TMA round trip: bytes in flight are what they need (gate-derivative GEMM alone: 33.9 us with
+    // 3 x 48 KB stages of which 32 KB were used, profiles/r2_bwd_gemm_ncu.txt)
+    const int w1 = (g.ng1 > 0) ? g.N1 : 0, w2 = (g.ng2 > 0) ? g.N2 : 0;
+    const int wide = (w1 > w2 ? w1 : w2) > 16 ? (w1 > w2 ? w1 : w2) : 16;
+    g.stage_bytes = TILE_BYTES + ((wide * BK * 2 + 1023) / 1024) * 1024;
+    const size_t fixed = 1024 + (size_t)nout_tiles * TILE_BYTES + 256 + 64;
+    int nst = (int)((232448 - fixed) / (size_t)g.stage_bytes);
+    if (nst > BW_MAX_STAGES) nst = BW_MAX_STAGES;
+    WAE_REQUIRE(nst >= 2, "bwd_gemm: no room for a 2-stage ring (stage %d bytes)", g.stage_bytes);
+    g.nstages = nst;
+    const size_t smem = 1024 + (size_t)g.nstages * g.stage_bytes + (size_t)nout_tiles * TILE_BYTES + 256 + 64;
     WAE_REQUIRE(smem <= 232448, "bwd_gemm: shared memory %zu too large", smem);
     WAE_REQUIRE(g.N1 % 16 == 0 && g.N1 >= 16 && g.N1 <= 256 && g.N2 % 16 == 0 && g.N2 <= 256 && (g.N2 == 0 || g.N1 + g.N2 <= 512),
                 "bwd_gemm: accumulator widths N1=%d N2=%d", g.N1, g.N2);

@@ -4,6 +4,8 @@ Inference: encoder, its final Linear and the VQ search are ONE kernel (wae_encod
 utterance with the activations in shared memory); the decoder is the tcgen05 stack.  Under autograd the encoder is
 the torch modules (frame rate, < 2 % of the FLOPs).
 """
+import os
+
 import torch
 from torch import nn
 
@@ -27,10 +29,10 @@ class ConvReLURes(nn.Module):
 def _enc_splits(B, cin, cout, k, Tout):
     """Split-K factor of one encoder-layer launch: a layer is a few dozen 64 x 64 output tiles with a serial reduction of
     cin*k/32 chunks (~1.9 us each) -- cut the reduction into slices until there are enough blocks for the GPU or a slice is only
-    4 chunks long."""
+    2 chunks long (the latent-rate layers of a training step are 8 tiles: 17-21 us per launch with 4-chunk slices, ncu)."""
     tiles = -(-(B * Tout) // 64) * -(-cout // 64)
     chunks = -(-(cin * k) // 32)
-    return max(1, min(chunks // 4, -(-148 // tiles), 8))
+    return max(1, min(chunks // int(os.environ.get("WAE_ENC_MIN_CHUNKS", "1")), -(-148 // tiles), int(os.environ.get("WAE_ENC_MAX_SPLITS", "16"))))
 
 
 class EncoderTrainFunction(torch.autograd.Function):
