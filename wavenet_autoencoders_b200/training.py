@@ -356,6 +356,16 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
                                                   sw.cuda_stream, sc.cuda_stream if sc is not None else None), "wae_stack_backward_bf16_2s")
         if sc is not None:
             torch.cuda.current_stream(dev).wait_stream(sc)       # the column sums (dgb, dbo, ...) are consumed on this stream below
+        # Everything the side streams still read or write after this function has returned was allocated on THIS stream: without a
+        # note to the caching allocator, the blocks of the saved activations (released by autograd as soon as this node is done), of
+        # dy and of the gradient buffer could be handed to the next allocation on this stream -- the upsampler / encoder backward
+        # -- while a lagging weight-gradient GEMM is still using them.  (During graph capture the allocator then keeps such blocks
+        # until the capture ends.)
+        for t in (x_all, h_all, c_cl, r1, r2, dy, flat, xf):
+            if t is not None and t.is_cuda:
+                t.record_stream(sw)
+                if sc is not None:
+                    t.record_stream(sc)
     else:
         n = lib.wae_stack_backward_workspace_bf16(pk.struct.d, B, T)
         ws = ws_cache.get(n, dev) if ws_cache is not None else torch.empty(n, dtype=torch.uint8, device=dev)
@@ -438,6 +448,8 @@ def _stack_backward_tc(sh, xf, gf, x_all, h_all, c_cl, r1, r2, weights, dlogits,
         weight_like = (i % PER_LAYER in (0, 2, 3, 4, 6)) if i < base else ((i - base) % 2 == 0)      # the weight-normed tensors
         if weight_like:
             with lanes.lane(i // PER_LAYER if i < base else L):
+                if two and g.is_cuda:
+                    g.record_stream(torch.cuda.current_stream(dev))      # the lane reads a block that belongs to this node's stream
                 out.append(g.to(w.dtype).reshape(w.shape))
         else:
             out.append(g.to(w.dtype).reshape(w.shape))
