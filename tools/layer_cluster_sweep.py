@@ -2,8 +2,10 @@
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-import bench
 from wavenet_autoencoders_b200 import _lib
+if os.environ.get("WAE_LIB_VARIANT"):      # experiment build (tools/build_variant.py); the product loads libwae_b200.so
+    _lib.LIB_PATH = _lib.PKG / "variants" / f"libwae_{os.environ['WAE_LIB_VARIANT']}.so"
+import bench
 L = _lib.lib()
 m = bench.build_vqvae("cuda"); m.wavenet.precision = "bf16"
 idx, mfcc, g = bench.synth_batch(16, 1000)

@@ -1278,16 +1278,17 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
             Ring ring(V2_STAGES);
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;
-                for (int pass = 0; pass < npass; ++pass)
+                for (int pass = 0; pass < npass; ++pass) {
+                int xj = 0, xsh = (a.kw - 1) * a.dil;     // tap cursor as counters: no division on the issue path (see layer_bf16_v4_kernel)
                 for (int kb = 0; kb < nk1; ++kb) {
                     mbar_wait(&empty[ring.stage], ring.phase ^ 1);
                     uint8_t* sa = smem + ring.stage * STAGE_BYTES;
                     mbar_arrive_expect_tx(&full[ring.stage], A_TILE_BYTES + (pass == 0 ? w1_bytes : w1b_bytes));
                     int kcol;
                     if (kb < nk_old) {
-                        const int tap = kb / rk, r0 = (kb % rk) * BK;
-                        tma_load_3d(&a.tm_x, &full[ring.stage], sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
-                        kcol = tap * a.R + r0;
+                        tma_load_3d(&a.tm_x, &full[ring.stage], sa, xj * BK, t0 - xsh, b);
+                        kcol = kb * BK;                     // = tap * R + r0
+                        if (++xj == rk) { xj = 0; xsh -= a.dil; }
                     } else if (kb < nk_old + nk_c) {
                         const int c0 = (kb - nk_old) * BK;
                         tma_load_3d(&a.tm_c, &full[ring.stage], sa, c0, t0, b);
@@ -1300,6 +1301,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v2_kernel(const _
                     if (pass == 0) tma_load_3d(&a.tm_w1, &full[ring.stage], sa + A_TILE_BYTES, kcol, 0, a.layer);
                     else tma_load_3d(&a.tm_w1b, &full[ring.stage], sa + A_TILE_BYTES, kcol, 2 * a.Ha, a.layer);
                     ring.advance();
+                }
                 }
                 if (has_out) {
                     for (int kb = 0; kb < nkh; ++kb) {
@@ -2108,7 +2110,12 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
     const int nk_x = a.kw * rk;                  // tap k-blocks, oldest tap first
     const int nk_c = a.Cp / BK;
     const int nk1 = nk_x + nk_c;
-    const int ksplit = (nk1 * 5) / 8;            // GEMM2 of the previous tile is issued after this many k-blocks of GEMM1
+#ifdef WAE_V4_KSPLIT
+    const int ksplit = WAE_V4_KSPLIT;
+#else
+    const int ksplit = (nk1 * 3) / 4;            // GEMM2 of the previous tile is issued after this many k-blocks of GEMM1 (13 k-blocks:
+                                                 // 6: 113.9 us, 8: 113.0, 9: 110.4, 10: 110.6, 11: 113.0, 12: 114.6 per launch)
+#endif
     const bool has_out = (a.x_out != nullptr);
     const int w1_rows = a.G / 2, wo_rows = a.R / 2;       // weight rows held by this CTA
     const uint32_t w1_half = (uint32_t)w1_rows * BK * 2, wo_half = (uint32_t)wo_rows * BK * 2;
@@ -2118,40 +2125,61 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
         if (elect_one()) {
             Ring ring(V4_STAGES);
             long long p_we = 0, p_iss = 0; const long long p_t0 = clock64(); LPROF_BEGIN();
-            auto load_g1 = [&](int b, int t0, int kb) {
+            // This thread's instruction latency sits on the refill path of every ring slot (one thread, dependent instructions:
+            // ~5 cycles each), so the issue path carries no division and no per-stage address arithmetic beyond increments: the
+            // k-block's TMA coordinates (tap -> time shift, channel offset) advance as counters.  The first version computed
+            // kb / rk and kb % rk per stage (95 SASS instructions with an I2F / MUFU.RCP / F2I chain ~ 450 cycles per stage
+            // against the 512 cycles the tensor pipe needs to consume one).
+            const uint32_t fb0 = mapa(smem_u32(&full[0]), 0);                 // the leader's full barriers (8 bytes apart)
+            const int w_row0 = crank * w1_rows, wo_row0 = crank * wo_rows;
+#ifdef WAE_V4_NOW
+            const uint32_t g1_tx = 2 * A_TILE_BYTES, wo_tx = 2 * wo_half;
+#else
+            const uint32_t g1_tx = 2 * (A_TILE_BYTES + w1_half), wo_tx = 2 * wo_half;
+#endif
+            int kb = 0, xj = 0, xsh = 0, b = 0, t0 = 0;                       // GEMM1 cursor of the current tile
+#ifdef WAE_V4_STAGGER
+            const int kb_first = (cluster_id * WAE_V4_STAGGER) % nk1;
+#else
+            const int kb_first = 0;
+#endif
+            auto load_g1 = [&]() {
                 LPROF(p_iss);
                 mbar_wait(&empty[ring.stage], ring.phase ^ 1);
                 LPROF(p_we);
                 if (LPROF_ON) t_issue[ring.stage] = clock64();
                 uint8_t* sa = smem + ring.stage * STAGE_BYTES;
-                const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
+                const uint32_t fb = fb0 + ring.stage * 8;
 #ifdef WAE_V4_FAKESHARE   // timing experiment only (wrong numerics): what would sharing one staged x window between the taps be worth?
                 const bool skip_a = (kb < nk_x) && (kb / rk < a.kw - 1) && (a.dil <= WAE_V4_FAKESHARE);
-                if (leader) mbar_arrive_expect_tx(&full[ring.stage], skip_a ? 2 * w1_half : 2 * (A_TILE_BYTES + w1_half));
+                if (leader) mbar_arrive_expect_tx(&full[ring.stage], skip_a ? 2 * w1_half : g1_tx);
                 if (skip_a) {
+                    if (++xj == rk) { xj = 0; xsh -= a.dil; }
                 } else
 #else
-                if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + w1_half));
+                if (leader) mbar_arrive_expect_tx(&full[ring.stage], g1_tx);
 #endif
                 if (kb < nk_x) {
-                    const int tap = kb / rk, r0 = (kb % rk) * BK;
-                    tma_load_3d_2cta(&a.tm_x, fb, sa, r0, t0 - (a.kw - 1 - tap) * a.dil, b);
+                    tma_load_3d_2cta(&a.tm_x, fb, sa, xj * BK, t0 - xsh, b);
+                    if (++xj == rk) { xj = 0; xsh -= a.dil; }
                 } else {
                     tma_load_3d_2cta(&a.tm_c, fb, sa, (kb - nk_x) * BK, t0, b);
                 }
-                tma_load_3d_2cta(&a.tm_w1, fb, sa + A_TILE_BYTES, kb * BK, crank * w1_rows, a.layer);
+#ifndef WAE_V4_NOW        // (WAE_V4_NOW: timing experiment only, wrong numerics -- the weight k-blocks are never loaded)
+                tma_load_3d_2cta(&a.tm_w1, fb, sa + A_TILE_BYTES, kb * BK, w_row0, a.layer);
+#endif
+                if (++kb == nk1) { kb = 0; xj = 0; xsh = (a.kw - 1) * a.dil; }      // wraps when the tile started at kb_first > 0
                 ring.advance();
             };
             auto load_wo = [&]() {
-                for (int kb = 0; kb < nkh; ++kb) {
+                for (int k2 = 0; k2 < nkh; ++k2) {
                     LPROF(p_iss);
                     mbar_wait(&empty[ring.stage], ring.phase ^ 1);
                     LPROF(p_we);
                     if (LPROF_ON) t_issue[ring.stage] = clock64();
                     uint8_t* sa = smem + ring.stage * STAGE_BYTES;
-                    const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);
-                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * wo_half);
-                    tma_load_3d_2cta(&a.tm_wo, fb, sa + A_TILE_BYTES, kb * BK, crank * wo_rows, a.layer);
+                    if (leader) mbar_arrive_expect_tx(&full[ring.stage], wo_tx);
+                    tma_load_3d_2cta(&a.tm_wo, fb0 + ring.stage * 8, sa + A_TILE_BYTES, k2 * BK, wo_row0, a.layer);
                     ring.advance();
                 }
             };
@@ -2159,10 +2187,16 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
             for (int s0 = cluster_id; s0 < nsuper; s0 += ncluster, ++it) {
                 const int sup = rev ? nsuper - 1 - s0 : s0;
                 const int tile = sup * 2 + crank;
-                const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
-                for (int kb = 0; kb < ksplit; ++kb) load_g1(b, t0, kb);
+                b = tile / a.tiles_per_utt; t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
+                // The accumulation order over the k-blocks is free, so each CTA pair starts its walk at a different k-block (and
+                // wraps): otherwise all 74 pairs, which run in near lockstep, ask the L2 for the SAME 32 KB of weights at the
+                // same moment.  Results stay deterministic (the start depends on the pair's index only).
+                kb = kb_first;
+                if (kb_first < nk_x) { xj = kb_first % rk; xsh = (a.kw - 1 - kb_first / rk) * a.dil; }
+                else { xj = 0; xsh = 0; }                                        // conditioning blocks first; the wrap resets the tap cursor
+                for (int i = 0; i < ksplit; ++i) load_g1();
                 if (has_out && it > 0) load_wo();
-                for (int kb = ksplit; kb < nk1; ++kb) load_g1(b, t0, kb);
+                for (int i = ksplit; i < nk1; ++i) load_g1();
             }
             if (has_out && it > 0) load_wo();
             if (LPROF_ON && a.prof) { long long* pp = a.prof + blockIdx.x * 16; pp[0] = p_we; pp[1] = clock64() - p_t0; }
@@ -2712,15 +2746,20 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
             Ring ring(HEADP_STAGES);
             const int nsk = a.L * nkh;                                    // skip-GEMM k-blocks per tile
             const int ka = nsk / 5, kb2 = nsk / 2;                        // GEMM3 / GEMM4 of the previous tile are slotted in after these
-            auto load_skip = [&](int b, int t0, bool valid, int kbi) {
-                const int l = kbi / nkh, kb = kbi - l * nkh;
+            // no division on the issue path (this one thread's instruction latency is part of every ring slot's refill time,
+            // see layer_bf16_v4_kernel): the (layer, k-block) cursor of the skip GEMM advances as counters
+            const uint32_t fb0 = mapa(smem_u32(&full[0]), 0);                  // the leader's full barriers (8 bytes apart)
+            const int ws_row0 = crank * ws_rows;
+            const uint32_t skip_tx = 2 * (A_TILE_BYTES + ws_half);
+            int sl = 0, skb = 0, splane = 0;                                   // cursor: layer, k-block inside it, h_all plane
+            auto load_skip = [&](int t0, int pstep) {
                 mbar_wait(&empty[ring.stage], ring.phase ^ 1);
                 uint8_t* sa = smem + ring.stage * STAGE_BYTES;
-                const uint32_t fb = mapa(smem_u32(&full[ring.stage]), 0);      // the leader's full barrier
-                if (leader) mbar_arrive_expect_tx(&full[ring.stage], 2 * (A_TILE_BYTES + ws_half));
-                // past the last tile (odd tail) the plane coordinate leaves the tensor: TMA zero-fills the box
-                tma_load_3d_2cta(&a.tm_h, fb, sa, kb * BK, t0, valid ? l * a.B + b : a.L * a.B);
-                tma_load_3d_2cta(&a.tm_ws, fb, sa + A_TILE_BYTES, kb * BK, crank * ws_rows, l);
+                const uint32_t fb = fb0 + ring.stage * 8;
+                if (leader) mbar_arrive_expect_tx(&full[ring.stage], skip_tx);
+                tma_load_3d_2cta(&a.tm_h, fb, sa, skb * BK, t0, splane);
+                tma_load_3d_2cta(&a.tm_ws, fb, sa + A_TILE_BYTES, skb * BK, ws_row0, sl);
+                if (++skb == nkh) { skb = 0; ++sl; splane += pstep; }
                 ring.advance();
             };
             auto load_w = [&](const CUtensorMap* tm, int rows, uint32_t half) {
@@ -2738,10 +2777,13 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
                 const int tile = sup * 2 + crank;
                 const int b = tile / a.tiles_per_utt, t0 = (tile % a.tiles_per_utt) * BM;   // b >= B past the end: zero fill
                 const bool valid = tile < ntiles;
+                // past the last tile (odd tail) the plane coordinate leaves the tensor: TMA zero-fills the box
+                sl = 0; skb = 0; splane = valid ? b : a.L * a.B;
+                const int pstep = valid ? a.B : 0;
                 for (int kbi = 0; kbi < nsk; ++kbi) {
                     if (it > 0 && kbi == ka) load_w(&a.tm_w3, ws_rows, ws_half);
                     if (it > 0 && kbi == kb2) load_w(&a.tm_w4, w4_rows, w4_half);
-                    load_skip(b, t0, valid, kbi);
+                    load_skip(t0, pstep);
                 }
             }
             if (it > 0) { load_w(&a.tm_w3, ws_rows, ws_half); load_w(&a.tm_w4, w4_rows, w4_half); }
