@@ -2207,6 +2207,10 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
             Ring ring(V4_STAGES);
             const uint32_t idesc1 = umma_idesc_bf16(2 * BM, a.G);
             const uint32_t idesc2 = umma_idesc_bf16(2 * BM, a.R);
+            // operand descriptors of ring stage 0; stage s adds s * STAGE_BYTES / 16 to the 14-bit address field (no carry: the whole
+            // shared-memory window is < 256 KB) -- one multiply-add per stage between "data landed" and the first MMA
+            const uint64_t ad_ring = umma_desc_sw128(smem_u32(smem)), bd_ring = umma_desc_sw128(smem_u32(smem) + A_TILE_BYTES);
+            const uint64_t ad_h = umma_desc_sw128(smem_u32(hbuf));
             long long m_full = 0, m_e1 = 0, m_e2 = 0, m_iss = 0, m_lat = 0; const long long m_t0 = clock64(); LPROF_BEGIN();
             auto gemm2 = [&](int jt) {       // tile number jt (per-cluster count) -> its own buffer, zero-initialised
                 const uint32_t buf = tmem_base + (uint32_t)((jt & 1) * 256);
@@ -2220,8 +2224,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                     LPROF(m_full);
                     if (LPROF_ON) m_lat += clock64() - t_issue[ring.stage];
                     tc_fence_after();
-                    const uint32_t sb = smem_u32(smem + ring.stage * STAGE_BYTES + A_TILE_BYTES);
-                    const uint64_t ad = umma_desc_sw128(smem_u32(hbuf + kb * A_TILE_BYTES)), bd = umma_desc_sw128(sb);
+                    const uint64_t ad = ad_h + (uint64_t)(kb * (A_TILE_BYTES >> 4)), bd = bd_ring + (uint64_t)(ring.stage * (STAGE_BYTES >> 4));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         umma_bf16_2cta(buf, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc2, (kb == 0 && k == 0) ? 0u : 1u);
@@ -2247,8 +2250,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
                     LPROF(m_full);
                     if (LPROF_ON) m_lat += clock64() - t_issue[ring.stage];
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + ring.stage * STAGE_BYTES);
-                    const uint64_t ad = umma_desc_sw128(sa), bd = umma_desc_sw128(sa + A_TILE_BYTES);
+                    const uint64_t so = (uint64_t)(ring.stage * (STAGE_BYTES >> 4));
+                    const uint64_t ad = ad_ring + so, bd = bd_ring + so;
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         umma_bf16_2cta(buf, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc1, (kb == 0 && k == 0) ? 0u : 1u);
