@@ -77,6 +77,37 @@ def test_forward_bf16_matches_reference_golden(case):
     assert err < TOL_BF16_CASE[case], err
 
 
+def test_programmatic_launch_chain_is_bit_identical(monkeypatch):
+    """The version-4 layer kernels and the head are launched programmatically behind each other (griddepcontrol: the next
+    kernel's prologue runs under the previous kernel's tail, its body waits for the previous kernel to complete).  The logits
+    must be bit-identical to the fully serialised chain (WAE_PDL=0) -- eagerly, back to back without a synchronisation in
+    between (the case in which a missing wait would show), and inside a replayed CUDA graph."""
+    g, cfg, m, x, c, spk = _inputs("wavenet_vqwae_b2")
+    m.precision = "bf16"
+    with torch.no_grad():
+        monkeypatch.setenv("WAE_PDL", "0")
+        y_serial = m(x, c, spk).clone()
+        monkeypatch.setenv("WAE_PDL", "1")
+        ys = [m(x, c, spk).clone() for _ in range(4)]
+        torch.cuda.synchronize()
+        for y in ys:
+            assert torch.equal(y, y_serial)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m(x, c, spk)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            y_graph = m(x, c, spk)
+        for _ in range(3):
+            y_graph.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(y_graph, y_serial)
+
+
 @pytest.mark.parametrize("case", ["wavenet_tiny", "wavenet_vqwae"])
 def test_forward_bf16_fused_last_upsample_stage(case):
     """wae_stack_forward_bf16_up (last upsampler stage fused into the stack) against the unfused call on the

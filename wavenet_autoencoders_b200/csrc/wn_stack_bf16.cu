@@ -86,6 +86,18 @@ int make_tmap(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64
 // ---------------------------------------------------------------------------------------------
 // device: pipeline bookkeeping
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (the layer chain and the head): a kernel launched with the programmatic-serialization attribute
+// may be scheduled onto SMs as soon as every CTA of the kernel in front of it has executed pdl_launch_dependents() or exited --
+// here: as the previous layer's CTAs finish their last tile.  Its prologue (barrier init, TMEM allocation, descriptor prefetch)
+// then runs under the previous layer's tail, and pdl_wait() holds everything that reads or overwrites global memory until the
+// previous kernel has completed and flushed.  Without the attribute both calls are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+static bool pdl_enabled() {      // WAE_PDL=0 launches the chain fully serialised (read per call: tests toggle it inside one process)
+    const char* e = getenv("WAE_PDL");
+    return !(e && e[0] == '0');
+}
+
 struct Ring {  // smem stage ring shared by the producer and the MMA issuer (each keeps its own cursor)
     uint32_t stage = 0, phase = 0;
     int nstages;
@@ -2095,6 +2107,8 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) layer_bf16_v4_kernel(const _
     cluster_sync();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();     // the next layer's CTAs may take over SMs as this layer's CTAs exit ...
+    pdl_wait();                  // ... and this one touches global memory only after the previous kernel has completed
 
     const int ntiles = a.B * a.tiles_per_utt;
     const int nsuper = (ntiles + 1) / 2;
@@ -2732,6 +2746,7 @@ __global__ void __launch_bounds__(LAYER_THREADS, 1) head_bf16_pair_kernel(const 
     __syncthreads();
     cluster_sync();
     tc_fence_after();
+    pdl_wait();                  // launched programmatically behind the last layer kernel (see pdl_wait)
     const uint32_t tmem_base = *tmem_slot;
     // TMEM ping-pong (as layer_bf16_v4_kernel): tile `it` owns the 256-column buffer it & 1 for its whole life -- skip GEMM, drained
     // by EPI_S, GEMM3 into the same columns, drained by EPI3, GEMM4, drained by EPI4 -- and the NEXT tile's skip GEMM (40 of the 48
@@ -3335,13 +3350,21 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
             cfg.blockDim = dim3(LAYER_THREADS);
             cfg.dynamicSmemBytes = v4 ? smem_v4 : v3 ? smem_v3 : pair2 ? smem_pair2 : (v2 ? smem_v2 : smem_layer);
             cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
+            cudaLaunchAttribute attr[2];
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = (unsigned)cs;
             attr[0].val.clusterDim.y = 1;
             attr[0].val.clusterDim.z = 1;
+            // Programmatic launch only where the kernel in front on this stream is the previous layer's launch of this loop
+            // (l >= 1) and only for the version-4 kernel, which has the pdl_wait().  Layer 0 keeps the ordinary full dependency:
+            // what precedes it is arbitrary (event waits on weight-preparation streams, memsets, other libraries' kernels), and
+            // under stream capture a programmatic launch turns EVERY pending dependency of the stream into a programmatic edge
+            // (tried on the backward GEMM chain with its cross-stream events: a weight gradient came out zero in the replayed
+            // graph, profiles/r2_layer_v4_experiments.txt).
+            attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[1].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr;
-            cfg.numAttrs = 1;
+            cfg.numAttrs = (v4 && l >= 1 && pdl_enabled()) ? 2 : 1;
             if (v4 && save_gate) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v4_kernel<true>, la));
             else if (v4) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v4_kernel<false>, la));
             else if (v3) WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, layer_bf16_v3_kernel, la));
@@ -3391,11 +3414,13 @@ static int stack_forward_bf16_impl(const wae_stack_bf16* w, const float* x, cons
         cfg.blockDim = dim3(LAYER_THREADS);
         cfg.dynamicSmemBytes = smem_headp;
         cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = (pdl_enabled() && d.layers >= 1) ? 2 : 1;    // the kernel in front is the last layer's launch above
         WAE_CHECK_CUDA(cudaLaunchKernelEx(&cfg, head_bf16_pair_kernel, ha));
     } else {
         WAE_CHECK_CUDA(cudaFuncSetAttribute(head_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_head));
