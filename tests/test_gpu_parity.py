@@ -842,6 +842,42 @@ def test_graphed_forward_matches_eager():
         assert abs(float(perp) - float(pp)) <= 1e-5 * max(1.0, abs(float(pp)))
 
 
+def test_graphed_forward_pipelined_results():
+    """GraphedForward.submit / result (losses read one step behind): every ticket returns the scalars the synchronous call gives
+    for ITS inputs, with two steps in flight and the slots reused."""
+    from wavenet_autoencoders_b200.graphed import GraphedForward
+    from wavenet_autoencoders_b200.vqvae_model import VQVAE
+    from wavenet_autoencoders_b200.wavenet_vocoder import WaveNet
+    cfg = T.CONFIGS["tiny"]
+    torch.manual_seed(0)
+    m = VQVAE(c_in=39, hid=cfg["cin_channels"], K=32, wavenet=WaveNet(**cfg), encoder_hid=48).eval()
+    m.load_state_dict(T.synth_state_dict(m, 5))
+    m = m.cuda()
+    m.wavenet.precision = "bf16"
+    g0 = load_golden("vqvae_tiny")
+    idx, mfcc, spk = torch.tensor(g0["idx"]).cuda(), torch.tensor(g0["mfcc"]).cuda(), torch.tensor(g0["g"]).cuda()
+    gf = GraphedForward(m, idx, mfcc, spk, with_logits=False)
+    gen = torch.Generator().manual_seed(11)
+    batches = [(torch.randint(0, cfg["out_channels"], idx.shape, generator=gen).pin_memory(),
+                torch.randn(mfcc.shape, generator=gen).pin_memory(),
+                torch.randint(0, cfg["n_speakers"], spk.shape, generator=gen).pin_memory()) for _ in range(5)]
+    want = []
+    for b in batches:
+        _, vq_loss, perp, nll = gf(*b)
+        want.append((float(nll), float(vq_loss), float(perp)))
+    assert len({w[0] for w in want}) == len(want)          # the batches do give different losses
+    got, prev = [], None
+    for b in batches:
+        t = gf.submit(*b)
+        if prev is not None:
+            got.append(gf.result(prev))
+        prev = t
+    got.append(gf.result(prev))
+    for gvals, wvals in zip(got, want):                    # the NLL is summed with double atomics: equal up to the summation order
+        for a, b in zip(gvals, wvals):
+            assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (got, want)
+
+
 def test_synthesis_postprocess_matches_oracle():
     """wae_synth_postprocess (inverse mu-law + inverse pre-emphasis + gain, synthesis.py:382-394) against the float64 numpy /
     scipy restatement: all three input types, ragged T (shorter than the 256 segments, not a multiple of them), T = 48000."""
